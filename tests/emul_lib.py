@@ -1,0 +1,64 @@
+"""ctypes binding of the host emulation of the DEVICE code (tests/emul/*.cpp compile
+nutdb_b200/csrc/*_core.cuh for the CPU).  Test harness only; never used by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_EMUL = os.path.join(_HERE, "emul")
+_CSRC = os.path.join(os.path.dirname(_HERE), "nutdb_b200", "csrc")
+_libs = {}
+
+
+def _build(name, src):
+    so = os.path.join(_EMUL, f"lib{name}.so")
+    deps = [os.path.join(_EMUL, src)] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)
+                                         if f.endswith((".cuh", ".hpp", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so,
+                               os.path.join(_EMUL, src)])
+    return so
+
+
+def lex_lib():
+    if "lex" not in _libs:
+        L = C.CDLL(_build("emul_lex", "emul_lex.cpp"))
+        L.emul_lex.restype = C.c_int64
+        L.emul_lex.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                               C.POINTER(C.c_uint32)]
+        L.emul_keyword.restype = C.c_uint8
+        L.emul_keyword.argtypes = [C.c_char_p, C.c_uint32]
+        _libs["lex"] = L
+    return _libs["lex"]
+
+
+def lex(text, offs, emit_all=False, chunk=32):
+    """Run the device lexer logic on the host.  -> dict(type,start,end,kw, seg_begin, seg_end)"""
+    L = lex_lib()
+    text = np.frombuffer(bytes(text), np.uint8) if not isinstance(text, np.ndarray) else text
+    text = np.ascontiguousarray(text)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    n = int(offs[-1] - offs[0])
+    nstmt = len(offs) - 1
+    cap = 2 * n + 2 * nstmt + 16
+    ty = np.zeros(cap, np.uint8)
+    st = np.zeros(cap, np.uint32)
+    en = np.zeros(cap, np.uint32)
+    kw = np.zeros(cap, np.uint8)
+    sb = np.zeros(nstmt + 1, np.uint32)
+    se = np.zeros(nstmt + 1, np.uint32)
+    nseg = C.c_uint32(0)
+    base = text.ctypes.data + int(offs[0])
+    nt = L.emul_lex(base, n, offs.ctypes.data, nstmt, int(emit_all), chunk, ty.ctypes.data, st.ctypes.data,
+                    en.ctypes.data, kw.ctypes.data, cap, sb.ctypes.data, se.ctypes.data, C.byref(nseg))
+    assert nt >= 0, "token capacity overflow"
+    return dict(type=ty[:nt], start=st[:nt], end=en[:nt], kw=kw[:nt], seg_begin=sb[:nseg.value],
+                seg_end=se[:nseg.value], n_seg=nseg.value)
+
+
+def keyword(word):
+    b = word.encode()
+    return lex_lib().emul_keyword(b, len(b))
