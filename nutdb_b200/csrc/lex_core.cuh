@@ -603,8 +603,11 @@ NUTDB_HD void entry_lookback(Src& src, uint32_t pos, uint32_t batch_begin, uint8
   prev = 0;
   esc = 0;
   prev_esc = 0;
-  if (pos == batch_begin || src.boundary(pos)) return;
+  if (pos == batch_begin) return;
   prev = src.byte(pos - 1);
+  // a statement starts at pos: the walker still needs the last byte of the PREVIOUS statement to
+  // finish its final token in flush_eof(); esc/prev_esc are reset by begin_statement() anyway
+  if (src.boundary(pos)) return;
   uint32_t n = 0;  // backslashes directly before pos
   uint32_t p = pos;
   while (p > batch_begin && !src.boundary(p) && src.byte(p - 1) == '\\') {

@@ -1,0 +1,130 @@
+// TEST HARNESS (not shipped): runs the device lexer + parser logic (lex_core.cuh, parse_core.cuh)
+// on the host, statement by statement, producing the same arrays the CUDA path produces.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../nutdb_b200/csrc/lex_tables.hpp"
+#include "../../nutdb_b200/csrc/parse_core.cuh"
+
+using namespace nlex;
+
+extern "C" int64_t emul_lex(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_t nstmt, int emit_all,
+                            uint32_t chunk, uint8_t* tok_type, uint32_t* tok_start, uint32_t* tok_end, uint8_t* tok_kw,
+                            uint32_t cap, uint32_t* seg_tok_begin, uint32_t* seg_tok_end, uint32_t* n_seg_out);
+
+namespace {
+struct HTok {
+  const uint8_t* ty;
+  const uint32_t* st;
+  const uint32_t* en;
+  const uint8_t* kw;
+  uint32_t n;
+  uint8_t type(uint32_t i) const { return i < n ? ty[i] : (uint8_t)NUTDB_TT_EOF; }
+  uint8_t kwid(uint32_t i) const { return i < n ? kw[i] : 0; }
+  uint32_t start(uint32_t i) const { return i < n ? st[i] : 0; }
+  uint32_t end(uint32_t i) const { return i < n ? en[i] : 0; }
+};
+struct HTokAdapter {
+  HTok h;
+  uint8_t type(uint32_t i) const { return h.type(i); }
+  uint8_t kw(uint32_t i) const { return h.kwid(i); }
+  uint32_t start(uint32_t i) const { return h.start(i); }
+  uint32_t end(uint32_t i) const { return h.end(i); }
+};
+struct HNodes {
+  std::vector<NutdbNode>& v;
+  uint32_t cap;
+  NutdbNode get(uint32_t i) const { return v[i]; }
+  void set(uint32_t i, const NutdbNode& x) {
+    if (i >= v.size()) v.resize(i + 1);
+    v[i] = x;
+  }
+  uint32_t capacity() const { return cap; }
+};
+struct HText {
+  const uint8_t* p;
+  uint32_t n;
+  uint8_t byte(uint32_t i) const { return i < n ? p[i] : 0; }
+};
+}  // namespace
+
+extern "C" {
+
+// Parses every statement.  Outputs: stmt[nstmt] (NutdbStmt), nodes (compact, caller cap), errors.
+// Returns 0, or -1 on capacity overflow.
+int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, uint32_t chunk, uint32_t stack_cap,
+                     NutdbStmt* stmt, NutdbNode* nodes, uint64_t node_cap, uint64_t* n_nodes, NutdbError* errs,
+                     uint64_t err_cap, uint64_t* n_errs, uint8_t* tok_type, uint32_t* tok_start, uint32_t* tok_end,
+                     uint8_t* tok_kw, uint32_t tok_cap, uint64_t* n_tok) {
+  uint32_t n = (uint32_t)(offs[nstmt] - offs[0]);
+  const uint8_t* base = text + offs[0];
+  std::vector<uint32_t> sb(nstmt + 1), se(nstmt + 1);
+  uint32_t nseg = 0;
+  int64_t nt = emul_lex(base, n, offs, nstmt, 0, chunk, tok_type, tok_start, tok_end, tok_kw, tok_cap, sb.data(),
+                        se.data(), &nseg);
+  if (nt < 0) return -1;
+  *n_tok = (uint64_t)nt;
+  uint64_t nn = 0, ne = 0;
+  uint32_t seg = 0;
+  std::vector<uint32_t> stack(stack_cap);
+  std::vector<NutdbNode> tmp;
+  for (uint64_t s = 0; s < nstmt; s++) {
+    uint32_t len = (uint32_t)(offs[s + 1] - offs[s]);
+    NutdbStmt& S = stmt[s];
+    std::memset(&S, 0, sizeof(S));
+    npar::ParseResult res;
+    HText tx{base + (offs[s] - offs[0]), len};
+    tmp.clear();
+    if (len == 0) {
+      // Parser::parse("") : the first token is EOF => EmptyQuery (mod.rs:141-144)
+      S.status = NUTDB_ST_SYNTAX_ERROR;
+      S.tok_begin = (uint32_t)nt;
+      S.tok_count = 0;
+      S.tok_used = 1;
+      res.status = NUTDB_ST_SYNTAX_ERROR;
+      res.err_code = NUTDB_SE_EmptyQuery;
+      res.err_has_pos = false;
+      res.err_pos = res.err_a = res.err_b = res.err_c = 0;
+    } else {
+      uint32_t b = sb[seg], e = se[seg];
+      seg++;
+      HTokAdapter tk{HTok{tok_type + b, tok_start + b, tok_end + b, tok_kw + b, e - b}};
+      HNodes nd{tmp, 2 * (e - b) + 8};
+      npar::Machine<HTokAdapter, HNodes, HText> m(npar::PARSE_TABLES, tk, nd, tx, stack.data(), stack_cap, res);
+      m.run(NUTDB_PROGRAM_ENTRY);
+      S.status = res.status;
+      S.tok_begin = b;
+      S.tok_count = e - b;
+      S.tok_used = res.tok_used;
+    }
+    if (res.status == NUTDB_ST_OK) {
+      if (nn + res.node_count > node_cap) return -1;
+      S.node_begin = (uint32_t)nn;
+      S.node_count = res.node_count;
+      std::memcpy(nodes + nn, tmp.data(), sizeof(NutdbNode) * res.node_count);
+      nn += res.node_count;
+    } else {
+      S.node_begin = (uint32_t)nn;
+      S.node_count = 0;
+      if (ne >= err_cap) return -1;
+      NutdbError& E = errs[ne++];
+      std::memset(&E, 0, sizeof(E));
+      E.stmt = (uint32_t)s;
+      E.cls = (uint16_t)res.status;
+      E.code = res.err_code;
+      E.a = res.err_a;
+      E.b = res.err_b;
+      E.c = res.err_c;
+      if (res.err_has_pos) {
+        E.pos = res.err_pos;
+        npar::get_pos(tx, res.err_pos, E.line, E.col);
+      }
+    }
+  }
+  *n_nodes = nn;
+  *n_errs = ne;
+  return 0;
+}
+
+}  // extern "C"

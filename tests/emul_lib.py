@@ -62,3 +62,48 @@ def lex(text, offs, emit_all=False, chunk=32):
 def keyword(word):
     b = word.encode()
     return lex_lib().emul_keyword(b, len(b))
+
+
+def parse_lib():
+    if "parse" not in _libs:
+        so = os.path.join(_EMUL, "libemul_parse.so")
+        srcs = [os.path.join(_EMUL, "emul_parse.cpp"), os.path.join(_EMUL, "emul_lex.cpp")]
+        deps = srcs + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".hpp", ".h"))]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so] + srcs)
+        L = C.CDLL(so)
+        L.emul_parse_batch.restype = C.c_int
+        L.emul_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+                                       C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
+                                       C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_uint32, C.POINTER(C.c_uint64)]
+        _libs["parse"] = L
+    return _libs["parse"]
+
+
+def parse_batch(text, offs, chunk=32, stack_cap=4096):
+    """Device lexer+parser logic on the host -> object with the NutdbBatch arrays."""
+    from oracle_lib import NODE_DT, STMT_DT, ERR_DT, Batch
+    L = parse_lib()
+    text = np.frombuffer(bytes(text), np.uint8) if not isinstance(text, np.ndarray) else text
+    text = np.ascontiguousarray(text)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    n = int(offs[-1] - offs[0])
+    nstmt = len(offs) - 1
+    tcap = n + 2 * nstmt + 16
+    b = Batch()
+    b.stmt = np.zeros(nstmt, STMT_DT)
+    node = np.zeros(2 * tcap + 16, NODE_DT)
+    err = np.zeros(nstmt + 1, ERR_DT)
+    ty = np.zeros(tcap, np.uint8)
+    st = np.zeros(tcap, np.uint32)
+    en = np.zeros(tcap, np.uint32)
+    kw = np.zeros(tcap, np.uint8)
+    nn, ne, nt = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    rc = L.emul_parse_batch(text.ctypes.data, offs.ctypes.data, nstmt, chunk, stack_cap, b.stmt.ctypes.data,
+                            node.ctypes.data, len(node), C.byref(nn), err.ctypes.data, len(err), C.byref(ne),
+                            ty.ctypes.data, st.ctypes.data, en.ctypes.data, kw.ctypes.data, tcap, C.byref(nt))
+    assert rc == 0, "emul_parse_batch overflow"
+    b.node, b.err = node[:nn.value], err[:ne.value]
+    b.tok_type, b.tok_start, b.tok_end, b.tok_kw = ty[:nt.value], st[:nt.value], en[:nt.value], kw[:nt.value]
+    return b

@@ -1,0 +1,75 @@
+"""Mutation fuzzer shared by the CPU (host-emulated device code) and GPU parity tests."""
+import numpy as np
+
+ALPHABET = [b"'", b'"', b"`", b"\\", b"-", b"--", b"/*", b"*/", b"*", b"/", b"\n", b"\r", b"\r\n", b"\t", b" ", b";",
+            b"(", b")", b"[", b"]", b"{", b"}", b",", b".", b":", b"!", b"=", b"<", b">", b"<>", b"<<", b">=", b"@",
+            b"$", b"#", b"?", b"0", b"1", b"9", b"0x", b"1.", b".5", b"a", b"x", b"_", b"e", b"\xc3\xa9",
+            b"\xe4\xbd\xa0", b"\xf0\x9f\x98\x80", b"~", b"+", b"%", b"&", b"|", b"^", b" not ", b" and ", b" or ",
+            b" is ", b" null ", b" in ", b" between ", b" like ", b" select ", b" from ", b" as ", b" case ",
+            b" when ", b" then ", b" else ", b" end ", b" if ", b" interval ", b" union ", b" all ", b" with ",
+            b" desc ", b" asc ", b" limit ", b" join ", b" on ", b" using ", b" true ", b" false ", b"\\u{41}",
+            b"\\u{D800}", b"\\u", b"''", b'""', b" $1 2 ", b" exists ", b" distinct ", b" order by ", b" group by "]
+
+
+def mutate(stmt, rng, n_mut):
+    s = bytearray(stmt)
+    for _ in range(n_mut):
+        k = rng.integers(0, 4)
+        pos = int(rng.integers(0, len(s) + 1))
+        if k == 0 and len(s) > 0:       # delete a short range
+            ln = int(rng.integers(1, 6))
+            del s[pos:pos + ln]
+        elif k == 1:                    # insert
+            s[pos:pos] = ALPHABET[int(rng.integers(0, len(ALPHABET)))]
+        elif k == 2 and len(s) > 0:     # replace
+            ln = int(rng.integers(1, 4))
+            s[pos:pos + ln] = ALPHABET[int(rng.integers(0, len(ALPHABET)))]
+        elif len(s) > 0:                # truncate
+            if rng.integers(0, 4) == 0:
+                del s[pos:]
+    # keep the &str precondition of the reference: valid UTF-8 only
+    try:
+        bytes(s).decode("utf-8")
+    except UnicodeDecodeError:
+        s = bytearray(bytes(s).decode("utf-8", "ignore").encode("utf-8"))
+    return bytes(s)
+
+
+def fuzz_statements(seeds, count, seed=1234, max_mut=4):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        base = seeds[int(rng.integers(0, len(seeds)))]
+        out.append(mutate(base, rng, int(rng.integers(1, max_mut + 1))))
+    return out
+
+
+EXTRA_SEEDS = [
+    b"SELECT a, b AS c FROM db.t WHERE x = 1 AND y != 'abc' ORDER BY a DESC LIMIT 10, 20",
+    b"SELECT 1 = 1, 0x10 = 16, 1.0 = 1.00, 'a''b' = \"a'b\", null is null, -1 = -1, 1 != 2",
+    b"WITH a AS (SELECT 1) SELECT * FROM a UNION ALL SELECT 2 INTERSECT SELECT 3 EXCEPT SELECT 4",
+    b"INSERT INTO t (a, b) VALUES (1, 'x'), (2, 'y')",
+    b"INSERT INTO t FROM f(1, 2)",
+    b"INSERT INTO t SELECT * FROM u",
+    b"CREATE TABLE IF NOT EXISTS t (a Int8 DEFAULT 1 COMMENT 'c', b Array(Nullable(String)), INDEX i f(a), "
+    b"CONSTRAINT c CHECK a > 0, e Enum('a' = 1, 'b'), m Map(String, Int8), d Decimal32(3), t Tuple(Int8, Chars(4))) "
+    b"PRIMARY KEY a ORDER BY a, b PARTITION BY a COMMENT 'tbl'",
+    b"CREATE VIEW v UPDATE BY s PRIMARY KEY a ORDER BY a PARTITION BY b COMMENT 'v' AS SELECT 1",
+    b"ALTER TABLE t ADD IF NOT EXISTS INDEX i f(x) AFTER j",
+    b"ALTER TABLE t ADD COLUMN c Int8",
+    b"ALTER TABLE t DROP IF EXISTS PARTITION 'p'",
+    b"ALTER TABLE t RENAME COLUMN a b",
+    b"ALTER TABLE t RENAME TABLE u",
+    b"DESCRIBE TABLE t", b"DESCRIBE DATABASE", b"DROP VIEW IF EXISTS v", b"TRUNCATE TABLE t",
+    b"OPTIMIZE TABLE t ON PARTITION 'p'", b"SET @cfg = 1 + 2", b"EXPLAIN (SELECT 1)",
+    b"SELECT CASE x WHEN 1 THEN 'a' WHEN 2 THEN 'b' ELSE 'c' END, CASE WHEN a THEN b END, IF a THEN b ELSE c END",
+    b"SELECT a NOT IN (1, 2), b NOT LIKE 'x', c NOT BETWEEN 1 AND 2, d BETWEEN 1 AND 2 AND e, NOT EXISTS(SELECT 1), "
+    b"x IS NOT NULL, y IS NULL, NOT true, ~a[1], -5, +x, INTERVAL 5 DAY, $1 2, [1, 2], {1: 2, 3: 4}, (1, 2), t.*, `q`.`r`",
+    b"SELECT a FROM t LEFT SEMI JOIN u ON a = b FULL OUTER JOIN v USING (x, y) RIGHT ANTI JOIN w ON true JOIN z ON 1",
+    b"SELECT DISTINCT ON (a, b) a, b FROM t GROUP BY a, b HAVING count(a) > 1 LIMIT 5 OFFSET 2 WITH TIES",
+    b"SELECT 'a\\u{767D}b', 'x\\ty', \"q\\\"r\", 'it''s', '\\u{+41}', '\\ux'",
+    b"select 1 -- trailing comment\n , 2 /* block ** comment **/ from t",
+    b"SELECT true AND a, false AND a, a AND true, a OR false, true XOR a, a XOR false, 1 = 1 AND b, NOT (1 = 2)",
+    b"select a + 1 not exists (select 1), b not exists (1, 2) and c, (a, b) not exists ()",
+    b"SELECT 340282366920938463463374607431768211455, 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF, 1e5",
+]

@@ -1,0 +1,76 @@
+"""Shared comparison of a batch result (GPU or host-emulated device code) against the oracle."""
+import numpy as np
+
+import oracle_lib as O
+
+
+def make_batch(stmts):
+    raws = [s.encode("utf-8") if isinstance(s, str) else bytes(s) for s in stmts]
+    offs = np.zeros(len(raws) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in raws])
+    return np.frombuffer(b"".join(raws) + b"\0" * 16, np.uint8), offs
+
+
+def describe(stmts, i):
+    s = stmts[i]
+    return repr(s if len(s) < 300 else s[:300])
+
+
+def compare_with_oracle(got, text, offs, stmts=None, check_tokens=True):
+    """Bit-exact comparison; returns list of mismatch descriptions (empty = parity)."""
+    want = O.parse_batch(text, offs)
+    bad = []
+    n = len(offs) - 1
+    gs, ws = got.stmt, want.stmt
+
+    def sql(i):
+        return bytes(text[int(offs[i]):int(offs[i + 1])])
+
+    st_bad = np.nonzero(gs["status"] != ws["status"])[0]
+    for i in st_bad[:5]:
+        bad.append(f"stmt {i}: status {gs['status'][i]} != oracle {ws['status'][i]}: {sql(i)!r}")
+    nc_bad = np.nonzero(gs["node_count"] != ws["node_count"])[0]
+    for i in nc_bad[:5]:
+        bad.append(f"stmt {i}: node_count {gs['node_count'][i]} != oracle {ws['node_count'][i]}: {sql(i)!r}")
+    tu_bad = np.nonzero(gs["tok_used"] != ws["tok_used"])[0]
+    for i in tu_bad[:5]:
+        bad.append(f"stmt {i}: tok_used {gs['tok_used'][i]} != oracle {ws['tok_used'][i]}: {sql(i)!r}")
+    if bad:
+        return bad
+    # nodes: same counts per statement => compare the concatenation when layouts agree
+    if not np.array_equal(gs["node_begin"], ws["node_begin"]):
+        bad.append("node_begin arrays differ although node counts agree")
+        return bad
+    if len(got.node) != len(want.node) or not np.array_equal(got.node, want.node):
+        m = min(len(got.node), len(want.node))
+        d = np.nonzero(got.node[:m] != want.node[:m])[0]
+        k = int(d[0]) if len(d) else m
+        i = int(np.searchsorted(ws["node_begin"], k, side="right") - 1)
+        bad.append(f"stmt {i}: node {k - int(ws['node_begin'][i])} differs: got {got.node[k] if k < len(got.node) else None}"
+                   f" oracle {want.node[k] if k < len(want.node) else None}: {sql(i)!r}")
+        return bad
+    # errors
+    ge = np.sort(got.err, order="stmt")
+    we = np.sort(want.err, order="stmt")
+    if len(ge) != len(we) or not np.array_equal(ge, we):
+        m = min(len(ge), len(we))
+        d = np.nonzero(ge[:m] != we[:m])[0]
+        k = int(d[0]) if len(d) else m
+        i = int(we["stmt"][k]) if k < len(we) else -1
+        bad.append(f"error record {k} differs: got {ge[k] if k < len(ge) else None} oracle {we[k] if k < len(we) else None}"
+                   f": {sql(i)!r}")
+        return bad
+    if check_tokens:
+        # tokens the reference pulled == the first tok_used tokens of each statement
+        for i in range(n):
+            u = int(ws["tok_used"][i])
+            if int(offs[i + 1]) == int(offs[i]):
+                continue
+            gb, wb = int(gs["tok_begin"][i]), int(ws["tok_begin"][i])
+            if not (np.array_equal(got.tok_type[gb:gb + u], want.tok_type[wb:wb + u]) and
+                    np.array_equal(got.tok_start[gb:gb + u], want.tok_start[wb:wb + u]) and
+                    np.array_equal(got.tok_end[gb:gb + u], want.tok_end[wb:wb + u])):
+                bad.append(f"stmt {i}: pulled tokens differ: {sql(i)!r}")
+                if len(bad) > 3:
+                    break
+    return bad

@@ -1,0 +1,75 @@
+"""The DEVICE code (nutdb_b200/csrc/lex_core.cuh + parse_core.cuh) compiled for the host and driven
+with the kernel's chunk decomposition, compared bit-for-bit with the oracle.  Runs without a GPU;
+the same comparisons run against the real kernels in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import emul_lib as E
+import fuzz
+import oracle_lib as O
+import parity as P
+from nutdb_b200 import workload as W
+
+CORPUS = W.corpus_statements()
+APP_D = ["SELECT * FROM table WHERE 1 = 1", "", "  ", ";", "-- c", "SELECT 1d", "SELECT a FROM t ORDER BY a ASC",
+         "SELECT $0", "SELECT 'abc", "select 1; 'oops", "\t1d", "select `你 好`, 'he''llo' -- x"]
+
+
+def check(stmts, chunk=32):
+    text, offs = P.make_batch(stmts)
+    got = E.parse_batch(text, offs, chunk=chunk)
+    bad = P.compare_with_oracle(got, text, offs)
+    assert not bad, "\n".join(bad)
+    return got
+
+
+@pytest.mark.parametrize("chunk", [32, 7, 1])
+def test_corpus_and_known_vectors(chunk):
+    got = check(CORPUS + APP_D, chunk)
+    assert (got.stmt["status"][:len(CORPUS)] == 0).all()  # tests/parser_test.rs:19-34
+
+
+@pytest.mark.parametrize("config", [2, 3, 4])
+def test_synthetic_config(config):
+    text, offs = W.generate(config, 192 << 10)
+    got = E.parse_batch(text, offs)
+    bad = P.compare_with_oracle(got, text, offs)
+    assert not bad, "\n".join(bad)
+    ok = (got.stmt["status"] == 0).mean()
+    if config == 3:
+        assert 0.90 < ok < 0.99   # 5 % malformed by construction
+    else:
+        assert ok == 1.0
+
+
+@pytest.mark.parametrize("seed,chunk", [(1, 32), (2, 32), (3, 5)])
+def test_mutation_fuzz(seed, chunk):
+    stmts = fuzz.fuzz_statements(CORPUS + fuzz.EXTRA_SEEDS, 1500, seed=seed)
+    check(stmts, chunk)
+
+
+def test_extra_seeds_unmutated():
+    check(fuzz.EXTRA_SEEDS)
+
+
+def test_full_token_stream_incl_whitespace_and_comments():
+    # verify mode of the lexer (emit_all): every token of the reference tokenizer, up to the first error
+    stmts = [s for s in CORPUS + [x.encode() for x in APP_D] + fuzz.fuzz_statements(CORPUS, 300, seed=9) if len(s)]
+    text, offs = P.make_batch(stmts)
+    got = E.lex(text, offs, emit_all=True)
+    for i, s in enumerate(stmts):
+        want, err = O.tokenize(s)
+        b, e = int(got["seg_begin"][i]), int(got["seg_end"][i])
+        g = list(zip(got["type"][b:e].tolist(), got["start"][b:e].tolist(), got["end"][b:e].tolist()))
+        assert g[:len(want)] == want, s
+        if err is not None:
+            assert g[len(want)] == (40, err["pos"], err["site"]), s
+
+
+def test_keyword_hash_matches_keyword_table():
+    L = O.lib()
+    for k in range(1, 116):
+        w = L.ora_keyword_text(k).decode()
+        assert E.keyword(w) == k and E.keyword(w.upper()) == k and E.keyword(w.capitalize()) == k
+    for w in ["selec", "selectt", "a", "tables", "fro", "x" * 10, "nulls", "byy"]:
+        assert E.keyword(w) == 0
