@@ -307,8 +307,10 @@ typedef struct {
   uint32_t a, b, c;
 } NutdbError;
 
-/* Output of one batch.  All pointers are HOST pointers owned by the library until
- * nutdb_gpu_batch_free(); the device copies stay alive too (see nutdb_gpu_batch_device). */
+/* Output of one batch.  All pointers are HOST pointers (pinned memory) owned by the CONTEXT: they
+ * stay valid until nutdb_gpu_batch_free() or the next nutdb_gpu_parse_batch() on the same context,
+ * whichever comes first (one live batch per context; the buffers are re-used, grow-only).  The
+ * device copies stay alive for the same time (see nutdb_gpu_batch_device). */
 typedef struct {
   uint64_t n_stmt;
   uint64_t n_tok;
@@ -330,6 +332,8 @@ typedef struct NutdbCtx NutdbCtx;
 #define NUTDB_F_NO_TOKENS 1u /* do not copy the token arrays back to the host (reference never exposes tokens) */
 #define NUTDB_F_DEVICE_INPUT 2u /* `sql` and `stmt_off` are device pointers on the ctx's device */
 #define NUTDB_F_NO_HOST_COPY 4u /* leave every output on the device (use nutdb_gpu_batch_device) */
+#define NUTDB_F_ALL_TOKENS 8u /* lexer verify mode: token arrays also hold Whitespace / Comment tokens (the full stream of
+                                 Tokenizer::next_token, tokenizer/mod.rs:66); statements are not parsed */
 
 enum {
   NUTDB_OK = 0,

@@ -265,8 +265,8 @@ struct LexCarry {
 
 // Sink concept:
 //   void token(uint32_t index, uint8_t type, uint32_t start_rel, uint32_t end_rel, uint8_t kw);
-//   void seg_begin(uint32_t seg, uint32_t first_token_index);
-//   void seg_end(uint32_t seg, uint32_t end_token_index);
+//   void seg_begin(uint32_t seg, uint32_t first_token_index, uint32_t stmt_start_abs);
+//   void seg_end(uint32_t seg, uint32_t end_token_index, uint32_t stmt_start_abs);
 // Src concept:
 //   uint8_t byte(uint32_t abs_pos);       // any position of the batch (used for short look-backs)
 //   bool boundary(uint32_t abs_pos);      // a statement starts at abs_pos
@@ -408,7 +408,7 @@ struct Walker {
       default: finish_code_token(e, true, true); break;
     }
     emit(NUTDB_TT_EOF, e, e);
-    if (!counting) sink.seg_end(c.seg, c.count);
+    if (!counting) sink.seg_end(c.seg, c.count, c.stmt_start);
   }
 
   NUTDB_HD void begin_statement(uint32_t pos) {
@@ -422,7 +422,7 @@ struct Walker {
     c.stmt_start = pos;
     c.tok_start = pos;
     c.nseg_seen++;
-    if (!counting) sink.seg_begin(c.seg, c.count);
+    if (!counting) sink.seg_begin(c.seg, c.count, c.stmt_start);
   }
 
   // Process the byte at absolute offset pos.  `first_of_batch` suppresses the EOF flush of a
@@ -729,8 +729,8 @@ NUTDB_HD CSum csum_then(const CSum& a, const CSum& b) {
 
 struct CountSink {
   NUTDB_HD void token(uint32_t, uint8_t, uint32_t, uint32_t, uint8_t) {}
-  NUTDB_HD void seg_begin(uint32_t, uint32_t) {}
-  NUTDB_HD void seg_end(uint32_t, uint32_t) {}
+  NUTDB_HD void seg_begin(uint32_t, uint32_t, uint32_t) {}
+  NUTDB_HD void seg_end(uint32_t, uint32_t, uint32_t) {}
 };
 
 #define NUTDB_NO_TOK 0xFFFFFFFFu

@@ -1,0 +1,1028 @@
+// nutdb_gpu.cu -- CUDA kernels (sm_100a) and the C ABI of libnutdb_gpu.so (include/nutdb_gpu.h).
+//
+// Pipeline of one nutdb_gpu_parse_batch() call (replaces n calls of Parser::parse,
+// reference src/parser/mod.rs:27):
+//
+//   k_prep        statement offsets -> 32-bit relative offsets + a bitmap of statement starts
+//   k_lex_A       per 32-byte chunk: transition function of the context automaton (strings, quoted
+//                 identifiers, comments); block scan; S: k_scan_vec8 over the tile aggregates
+//   k_lex_B       same for the code-token automaton, entry context now known
+//   k_lex_C       per chunk: number of tokens / statement starts / token in progress; block scan
+//   k_lex_D       per chunk: emit tokens (type, payload span, keyword id) at their final index
+//   k_parse       one thread per statement: bytecode pushdown automaton -> post-order nodes into a
+//                 per-statement scratch range; first error in pull order + (line, col)
+//   k_parse_retry statements that overflowed the fast path's stack / node range (deep nesting)
+//   k_stmt_sums, k_scan_u2, k_finalize   dense node / error arrays in statement order
+//
+// Lexer kernels stage their 8 KB tile in shared memory TRANSPOSED (word w of chunk c at
+// [w][c], row padded by one word) so that 32 lanes walking 32 different chunks byte by byte hit
+// 32 different banks.  No CPU fallback anywhere: without a device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lex_tables.hpp"
+#include "parse_core.cuh"
+
+using namespace nlex;
+
+#define LEX_THREADS 256
+#define LEX_CHUNK 32
+#define LEX_TILE (LEX_THREADS * LEX_CHUNK)
+#define LEX_ROW (LEX_THREADS + 1)
+#define SCAN_THREADS 1024
+#define PARSE_THREADS 128
+#define PARSE_STACK 160      // words of local stack in the fast path
+#define FIN_THREADS 256
+#define NODE_SLACK 8u        // fast-path node range of a statement = its token count + NODE_SLACK
+#define RETRY_NONE 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------
+// device views
+// ------------------------------------------------------------------------------------------
+struct TileSrc {
+  const uint8_t* text;
+  const uint32_t* bitmap;
+  const uint32_t* sm;  // transposed tile
+  const uint32_t* bm;  // boundary bits of the tile, one word per chunk
+  uint32_t tile_begin, n;
+  __device__ __forceinline__ uint8_t byte(uint32_t p) const {
+    uint32_t r = p - tile_begin;
+    if (r < LEX_TILE) {
+      uint32_t w = sm[((r >> 2) & 7u) * LEX_ROW + (r >> 5)];
+      return (uint8_t)(w >> ((r & 3u) * 8u));
+    }
+    return p < n ? text[p] : (uint8_t)0;
+  }
+  __device__ __forceinline__ bool boundary(uint32_t p) const {
+    uint32_t r = p - tile_begin;
+    if (r < LEX_TILE) return (bm[r >> 5] >> (r & 31u)) & 1u;
+    return p < n && ((bitmap[p >> 5] >> (p & 31u)) & 1u);
+  }
+};
+
+__device__ __forceinline__ void stage_tile(const uint8_t* text, const uint32_t* bitmap, uint32_t tile_begin, uint32_t n,
+                                           uint32_t* sm, uint32_t* bm) {
+  const uint4* src = reinterpret_cast<const uint4*>(text + tile_begin);
+#pragma unroll
+  for (uint32_t k = threadIdx.x; k < LEX_TILE / 16; k += LEX_THREADS) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (tile_begin + 16u * k < n) v = __ldg(src + k);
+    uint32_t chunk = k >> 1, w = (k & 1u) * 4u;
+    sm[(w + 0) * LEX_ROW + chunk] = v.x;
+    sm[(w + 1) * LEX_ROW + chunk] = v.y;
+    sm[(w + 2) * LEX_ROW + chunk] = v.z;
+    sm[(w + 3) * LEX_ROW + chunk] = v.w;
+  }
+  bm[threadIdx.x] = bitmap[(tile_begin >> 5) + threadIdx.x];
+}
+
+__device__ __forceinline__ void stage_tables(const LexTables* g, LexTables* s) {
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* b = reinterpret_cast<uint32_t*>(s);
+  for (uint32_t i = threadIdx.x; i < sizeof(LexTables) / 4; i += blockDim.x) b[i] = a[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// scans
+// ------------------------------------------------------------------------------------------
+struct Vec8Op {
+  typedef uint32_t T;
+  __device__ static T identity() { return NUTDB_VEC8_ID; }
+  __device__ static T then(T a, T b) { return vec8_then(a, b); }
+  __device__ static T shfl_up(T v, int d) { return __shfl_up_sync(0xFFFFFFFFu, v, d); }
+};
+
+// CSum packed in a uint4: x=count, y=nseg | escaped<<31, z=tok_start, w=stmt_start | has_tok<<31
+__device__ __forceinline__ uint4 csum_pack(const CSum& c) {
+  return make_uint4(c.count, c.nseg | ((uint32_t)(c.escaped != 0) << 31), c.tok_start,
+                    c.stmt_start | ((uint32_t)(c.has_tok != 0) << 31));
+}
+__device__ __forceinline__ CSum csum_unpack(const uint4& v) {
+  CSum c;
+  c.count = v.x;
+  c.nseg = v.y & 0x7FFFFFFFu;
+  c.escaped = (uint8_t)(v.y >> 31);
+  c.tok_start = v.z;
+  c.stmt_start = v.w & 0x7FFFFFFFu;
+  c.has_tok = (uint8_t)(v.w >> 31);
+  return c;
+}
+struct CSumOp {
+  typedef uint4 T;
+  __device__ static T identity() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static T then(const T& a, const T& b) {
+    T r;
+    r.x = a.x + b.x;
+    const bool bt = (b.w >> 31) != 0;
+    const uint32_t nseg = (a.y & 0x7FFFFFFFu) + (b.y & 0x7FFFFFFFu);
+    const uint32_t esc = bt ? (b.y >> 31) : ((a.y | b.y) >> 31);
+    r.y = nseg | (esc << 31);
+    r.z = bt ? b.z : a.z;
+    const uint32_t ss = (b.y & 0x7FFFFFFFu) ? (b.w & 0x7FFFFFFFu) : (a.w & 0x7FFFFFFFu);
+    r.w = ss | ((a.w | b.w) & 0x80000000u);
+    return r;
+  }
+  __device__ static T shfl_up(const T& v, int d) {
+    return make_uint4(__shfl_up_sync(0xFFFFFFFFu, v.x, d), __shfl_up_sync(0xFFFFFFFFu, v.y, d),
+                      __shfl_up_sync(0xFFFFFFFFu, v.z, d), __shfl_up_sync(0xFFFFFFFFu, v.w, d));
+  }
+};
+struct U2AddOp {
+  typedef uint2 T;
+  __device__ static T identity() { return make_uint2(0u, 0u); }
+  __device__ static T then(const T& a, const T& b) { return make_uint2(a.x + b.x, a.y + b.y); }
+  __device__ static T shfl_up(const T& v, int d) {
+    return make_uint2(__shfl_up_sync(0xFFFFFFFFu, v.x, d), __shfl_up_sync(0xFFFFFFFFu, v.y, d));
+  }
+};
+
+// Ordered (non-commutative) block scan.  `ws` = shared array of 32 elements.  Returns the
+// exclusive prefix; `incl` = inclusive value; every thread gets the block total in `total`.
+template <class Op>
+__device__ __forceinline__ typename Op::T block_scan(typename Op::T v, typename Op::T* ws, typename Op::T& incl,
+                                                     typename Op::T& total) {
+  typedef typename Op::T T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = Op::shfl_up(v, d);
+    if (lane >= d) v = Op::then(o, v);
+  }
+  T prev = Op::shfl_up(v, 1);
+  if (lane == 0) prev = Op::identity();
+  if (lane == 31) ws[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < nwarps ? ws[lane] : Op::identity();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      T o = Op::shfl_up(w, d);
+      if (lane >= d) w = Op::then(o, w);
+    }
+    ws[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  T base = warp ? ws[warp - 1] : Op::identity();
+  total = ws[nwarps - 1];
+  incl = Op::then(base, v);
+  T excl = Op::then(base, prev);
+  __syncthreads();  // ws may be reused by the caller
+  return excl;
+}
+
+// Single-block scan over per-tile aggregates: out[i] = exclusive prefix, *total = everything.
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const typename Op::T* __restrict__ in,
+                                                             typename Op::T* __restrict__ out, uint32_t n,
+                                                             typename Op::T* __restrict__ total_out) {
+  typedef typename Op::T T;
+  __shared__ T ws[32];
+  const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+  T f = Op::identity();
+  for (uint32_t i = lo; i < hi; i++) f = Op::then(f, in[i]);
+  T incl, total;
+  T g = block_scan<Op>(f, ws, incl, total);
+  for (uint32_t i = lo; i < hi; i++) {
+    T x = in[i];
+    out[i] = g;
+    g = Op::then(g, x);
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = total;
+}
+
+// vec8 variant: stores only the ENTRY STATE of each tile (the automaton starts in state 0)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_vec8(const uint32_t* __restrict__ in, uint8_t* __restrict__ entry,
+                                                            uint32_t n) {
+  __shared__ uint32_t ws[32];
+  const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+  uint32_t f = NUTDB_VEC8_ID;
+  for (uint32_t i = lo; i < hi; i++) f = vec8_then(f, in[i]);
+  uint32_t incl, total;
+  uint32_t g = block_scan<Vec8Op>(f, ws, incl, total);
+  for (uint32_t i = lo; i < hi; i++) {
+    entry[i] = (uint8_t)vec8_apply(g, 0u);
+    g = vec8_then(g, in[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_prep
+// ------------------------------------------------------------------------------------------
+__global__ void k_prep(const uint64_t* __restrict__ off, uint64_t nstmt, uint32_t* __restrict__ off32,
+                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ bad) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nstmt) return;
+  const uint64_t base = off[0];
+  const uint64_t o = off[s];
+  if (o < base) {
+    atomicOr(bad, 1u);
+    return;
+  }
+  off32[s] = (uint32_t)(o - base);
+  if (s < nstmt) {
+    const uint64_t e = off[s + 1];
+    if (e < o) atomicOr(bad, 1u);
+    else if (e > o) {
+      uint32_t p = (uint32_t)(o - base);
+      atomicOr(&bitmap[p >> 5], 1u << (p & 31u));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// lexer kernels
+// ------------------------------------------------------------------------------------------
+struct LexShared {
+  LexTables T;
+  uint32_t sm[8 * LEX_ROW];
+  uint32_t bm[LEX_THREADS];
+};
+
+__global__ void __launch_bounds__(LEX_THREADS) k_lex_A(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
+                                                       uint32_t n, const LexTables* __restrict__ gT,
+                                                       uint32_t* __restrict__ localA, uint32_t* __restrict__ tileA) {
+  __shared__ LexShared S;
+  __shared__ uint32_t ws[32];
+  const uint32_t tile_begin = blockIdx.x * LEX_TILE;
+  stage_tables(gT, &S.T);
+  stage_tile(text, bitmap, tile_begin, n, S.sm, S.bm);
+  __syncthreads();
+  TileSrc src{text, bitmap, S.sm, S.bm, tile_begin, n};
+  const uint32_t begin = tile_begin + threadIdx.x * LEX_CHUNK;
+  uint32_t f = NUTDB_VEC8_ID;
+  if (begin < n) f = chunk_sim_A(S.T, src, begin, min(begin + LEX_CHUNK, n));
+  uint32_t incl, total;
+  uint32_t excl = block_scan<Vec8Op>(f, ws, incl, total);
+  localA[blockIdx.x * LEX_THREADS + threadIdx.x] = excl;
+  if (threadIdx.x == 0) tileA[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(LEX_THREADS) k_lex_B(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
+                                                       uint32_t n, const LexTables* __restrict__ gT,
+                                                       const uint32_t* __restrict__ localA,
+                                                       const uint8_t* __restrict__ tileEntA, uint32_t* __restrict__ localB,
+                                                       uint32_t* __restrict__ tileB) {
+  __shared__ LexShared S;
+  __shared__ uint32_t ws[32];
+  const uint32_t tile_begin = blockIdx.x * LEX_TILE;
+  stage_tables(gT, &S.T);
+  stage_tile(text, bitmap, tile_begin, n, S.sm, S.bm);
+  __syncthreads();
+  TileSrc src{text, bitmap, S.sm, S.bm, tile_begin, n};
+  const uint32_t chunk = blockIdx.x * LEX_THREADS + threadIdx.x;
+  const uint32_t begin = tile_begin + threadIdx.x * LEX_CHUNK;
+  uint32_t f = NUTDB_VEC8_ID;
+  if (begin < n) {
+    const uint8_t entA = (uint8_t)vec8_apply(localA[chunk], tileEntA[blockIdx.x]);
+    f = chunk_sim_B(S.T, src, begin, min(begin + LEX_CHUNK, n), entA);
+  }
+  uint32_t incl, total;
+  uint32_t excl = block_scan<Vec8Op>(f, ws, incl, total);
+  localB[chunk] = excl;
+  if (threadIdx.x == 0) tileB[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(LEX_THREADS) k_lex_C(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
+                                                       uint32_t n, const LexTables* __restrict__ gT,
+                                                       const uint32_t* __restrict__ localA,
+                                                       const uint8_t* __restrict__ tileEntA,
+                                                       const uint32_t* __restrict__ localB,
+                                                       const uint8_t* __restrict__ tileEntB, int emit_all,
+                                                       uint4* __restrict__ localC, uint4* __restrict__ tileC) {
+  __shared__ LexShared S;
+  __shared__ uint4 ws[32];
+  const uint32_t tile_begin = blockIdx.x * LEX_TILE;
+  stage_tables(gT, &S.T);
+  stage_tile(text, bitmap, tile_begin, n, S.sm, S.bm);
+  __syncthreads();
+  TileSrc src{text, bitmap, S.sm, S.bm, tile_begin, n};
+  const uint32_t chunk = blockIdx.x * LEX_THREADS + threadIdx.x;
+  const uint32_t begin = tile_begin + threadIdx.x * LEX_CHUNK;
+  uint4 v = CSumOp::identity();
+  if (begin < n) {
+    const uint8_t entA = (uint8_t)vec8_apply(localA[chunk], tileEntA[blockIdx.x]);
+    const uint8_t entB = (uint8_t)vec8_apply(localB[chunk], tileEntB[blockIdx.x]);
+    v = csum_pack(chunk_count(S.T, src, begin, begin + LEX_CHUNK, n, entA, entB, emit_all != 0));
+  }
+  uint4 incl, total;
+  uint4 excl = block_scan<CSumOp>(v, ws, incl, total);
+  localC[chunk] = excl;
+  if (threadIdx.x == 0) tileC[blockIdx.x] = total;
+}
+
+struct DevSink {
+  uint8_t* type;
+  uint32_t* start;
+  uint32_t* end;
+  uint8_t* kw;
+  uint32_t cap;
+  uint32_t* stmt_tok_begin;
+  uint32_t* stmt_tok_end;
+  const uint32_t* off32;
+  uint32_t nstmt;
+  __device__ __forceinline__ void token(uint32_t i, uint8_t t, uint32_t s, uint32_t e, uint8_t k) {
+    if (i < cap) {
+      type[i] = t;
+      start[i] = s;
+      end[i] = e;
+      kw[i] = k;
+    }
+  }
+  // index of the (non-empty) statement starting at byte `pos`: the LAST s with off32[s] == pos
+  __device__ uint32_t find_stmt(uint32_t pos) const {
+    uint32_t lo = 0, hi = nstmt;  // first s in [0,nstmt) with off32[s] > pos
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (off32[mid] > pos) hi = mid;
+      else lo = mid + 1;
+    }
+    return lo - 1;
+  }
+  __device__ __forceinline__ void seg_begin(uint32_t, uint32_t first, uint32_t stmt_start) {
+    stmt_tok_begin[find_stmt(stmt_start)] = first;
+  }
+  __device__ __forceinline__ void seg_end(uint32_t, uint32_t endi, uint32_t stmt_start) {
+    stmt_tok_end[find_stmt(stmt_start)] = endi;
+  }
+};
+
+__global__ void __launch_bounds__(LEX_THREADS) k_lex_D(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
+                                                       uint32_t n, const LexTables* __restrict__ gT,
+                                                       const uint32_t* __restrict__ localA,
+                                                       const uint8_t* __restrict__ tileEntA,
+                                                       const uint32_t* __restrict__ localB,
+                                                       const uint8_t* __restrict__ tileEntB, int emit_all,
+                                                       const uint4* __restrict__ localC,
+                                                       const uint4* __restrict__ tilePrefC, DevSink sink) {
+  __shared__ LexShared S;
+  const uint32_t tile_begin = blockIdx.x * LEX_TILE;
+  stage_tables(gT, &S.T);
+  stage_tile(text, bitmap, tile_begin, n, S.sm, S.bm);
+  __syncthreads();
+  TileSrc src{text, bitmap, S.sm, S.bm, tile_begin, n};
+  const uint32_t chunk = blockIdx.x * LEX_THREADS + threadIdx.x;
+  const uint32_t begin = tile_begin + threadIdx.x * LEX_CHUNK;
+  if (begin >= n) return;
+  const uint8_t entA = (uint8_t)vec8_apply(localA[chunk], tileEntA[blockIdx.x]);
+  const uint8_t entB = (uint8_t)vec8_apply(localB[chunk], tileEntB[blockIdx.x]);
+  const CSum prefix = csum_unpack(CSumOp::then(tilePrefC[blockIdx.x], localC[chunk]));
+  if (emit_all) chunk_walk<true>(S.T, src, sink, begin, begin + LEX_CHUNK, n, entA, entB, prefix, false);
+  else chunk_walk<false>(S.T, src, sink, begin, begin + LEX_CHUNK, n, entA, entB, prefix, false);
+}
+
+// ------------------------------------------------------------------------------------------
+// parser kernels
+// ------------------------------------------------------------------------------------------
+struct DTok {
+  const uint8_t* ty;
+  const uint32_t* st;
+  const uint32_t* en;
+  const uint8_t* kwp;
+  uint32_t n;
+  __device__ __forceinline__ uint8_t type(uint32_t i) const { return i < n ? ty[i] : (uint8_t)NUTDB_TT_EOF; }
+  __device__ __forceinline__ uint8_t kw(uint32_t i) const { return i < n ? kwp[i] : (uint8_t)0; }
+  __device__ __forceinline__ uint32_t start(uint32_t i) const { return i < n ? st[i] : 0u; }
+  __device__ __forceinline__ uint32_t end(uint32_t i) const { return i < n ? en[i] : 0u; }
+};
+struct DNodes {
+  uint4* p;
+  uint32_t cap;
+  __device__ __forceinline__ NutdbNode get(uint32_t i) const {
+    uint4 v = p[i];
+    NutdbNode x;
+    x.kind = (uint8_t)(v.x & 0xFF);
+    x.sub = (uint8_t)((v.x >> 8) & 0xFF);
+    x.aux = (uint16_t)(v.x >> 16);
+    x.parent = v.y;
+    x.a = v.z;
+    x.b = v.w;
+    return x;
+  }
+  __device__ __forceinline__ void set(uint32_t i, const NutdbNode& x) {
+    p[i] = make_uint4((uint32_t)x.kind | ((uint32_t)x.sub << 8) | ((uint32_t)x.aux << 16), x.parent, x.a, x.b);
+  }
+  __device__ __forceinline__ uint32_t capacity() const { return cap; }
+};
+struct DText {
+  const uint8_t* p;
+  uint32_t n;
+  __device__ __forceinline__ uint8_t byte(uint32_t i) const { return i < n ? p[i] : (uint8_t)0; }
+};
+
+__device__ __forceinline__ void stage_parse_tables(const npar::ParseTables* g, npar::ParseTables* s) {
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* b = reinterpret_cast<uint32_t*>(s);
+  for (uint32_t i = threadIdx.x; i < sizeof(npar::ParseTables) / 4; i += blockDim.x) b[i] = a[i];
+}
+
+// writes the result of one statement: its NutdbStmt and, on failure, the error record at the
+// start of its node range (picked up by k_finalize)
+__device__ __forceinline__ void store_result(const npar::ParseResult& res, uint32_t s, uint32_t tb, uint32_t tc,
+                                             uint32_t where, const DText& tx, uint4* node_range, NutdbStmt* stmt) {
+  NutdbStmt S;
+  S.status = res.status;
+  S.tok_begin = tb;
+  S.tok_count = tc;
+  S.node_begin = where;  // temporary: location of the node range (RETRY_NONE = fast-path scratch)
+  S.node_count = res.status == NUTDB_ST_OK ? res.node_count : 0u;
+  S.tok_used = res.tok_used;
+  stmt[s] = S;
+  if (res.status != NUTDB_ST_OK) {
+    uint32_t line = 0, col = 0, pos = 0;
+    if (res.err_has_pos) {
+      pos = res.err_pos;
+      npar::get_pos(tx, pos, line, col);
+    }
+    node_range[0] = make_uint4(s, (uint32_t)res.status | ((uint32_t)res.err_code << 16), line, col);
+    node_range[1] = make_uint4(pos, res.err_a, res.err_b, res.err_c);
+  }
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS) k_parse(
+    const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, uint32_t nstmt, uint32_t ntok,
+    const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end,
+    const uint8_t* __restrict__ tok_kw, const uint32_t* __restrict__ stmt_tok_begin,
+    const uint32_t* __restrict__ stmt_tok_end, const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt,
+    uint4* __restrict__ scratch, uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, int lex_only) {
+  __shared__ npar::ParseTables P;
+  stage_parse_tables(gP, &P);
+  __syncthreads();
+  const uint32_t s = blockIdx.x * PARSE_THREADS + threadIdx.x;
+  if (s >= nstmt) return;
+  const uint32_t o = off32[s], len = off32[s + 1] - o;
+  if (len == 0) {
+    // Parser::parse(""): the first token is EOF => EmptyQuery (mod.rs:141-144); k_finalize writes the record
+    NutdbStmt S;
+    S.status = lex_only ? NUTDB_ST_OK : NUTDB_ST_SYNTAX_ERROR;
+    S.tok_begin = ntok;
+    S.tok_count = 0;
+    S.node_begin = RETRY_NONE;
+    S.node_count = 0;
+    S.tok_used = lex_only ? 0 : 1;
+    stmt[s] = S;
+    return;
+  }
+  const uint32_t tb = stmt_tok_begin[s], tc = stmt_tok_end[s] - tb;
+  if (lex_only) {
+    NutdbStmt S;
+    S.status = NUTDB_ST_OK;
+    S.tok_begin = tb;
+    S.tok_count = tc;
+    S.node_begin = RETRY_NONE;
+    S.node_count = 0;
+    S.tok_used = 0;
+    stmt[s] = S;
+    return;
+  }
+  uint32_t stack[PARSE_STACK];
+  DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
+  uint4* range = scratch + ((size_t)tb + (size_t)NODE_SLACK * s);
+  DNodes nd{range, tc + NODE_SLACK};
+  DText tx{text + o, len};
+  npar::ParseResult res;
+  npar::Machine<DTok, DNodes, DText> m(P, tk, nd, tx, stack, PARSE_STACK, res);
+  m.run(NUTDB_PROGRAM_ENTRY);
+  if (res.status == NUTDB_ST_LIMIT) retry_list[atomicAdd(retry_count, 1u)] = make_uint2(s, tc);
+  store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
+}
+
+// one thread per statement of the retry list, stack and node range in global scratch
+__global__ void __launch_bounds__(PARSE_THREADS) k_parse_retry(
+    const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint8_t* __restrict__ tok_type,
+    const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw,
+    const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt, const uint2* __restrict__ retry_list,
+    uint32_t nretry, const uint64_t* __restrict__ node_off, const uint64_t* __restrict__ stack_off,
+    uint4* __restrict__ retry_nodes, uint32_t* __restrict__ retry_stack) {
+  __shared__ npar::ParseTables P;
+  stage_parse_tables(gP, &P);
+  __syncthreads();
+  const uint32_t i = blockIdx.x * PARSE_THREADS + threadIdx.x;
+  if (i >= nretry) return;
+  const uint32_t s = retry_list[i].x;
+  const uint32_t o = off32[s], len = off32[s + 1] - o;
+  const NutdbStmt old = stmt[s];
+  const uint32_t tb = old.tok_begin, tc = old.tok_count;
+  DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
+  uint4* range = retry_nodes + node_off[i];
+  DNodes nd{range, (uint32_t)(node_off[i + 1] - node_off[i])};
+  DText tx{text + o, len};
+  npar::ParseResult res;
+  npar::Machine<DTok, DNodes, DText> m(P, tk, nd, tx, retry_stack + stack_off[i],
+                                       (uint32_t)(stack_off[i + 1] - stack_off[i]), res);
+  m.run(NUTDB_PROGRAM_ENTRY);
+  store_result(res, s, tb, tc, (uint32_t)node_off[i], tx, range, stmt);
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) k_stmt_sums(const NutdbStmt* __restrict__ stmt, uint32_t nstmt,
+                                                           uint2* __restrict__ tileS) {
+  __shared__ uint2 ws[32];
+  const uint32_t s = blockIdx.x * FIN_THREADS + threadIdx.x;
+  uint2 v = make_uint2(0u, 0u);
+  if (s < nstmt) {
+    const uint32_t st = stmt[s].status;
+    v = make_uint2(st == NUTDB_ST_OK ? stmt[s].node_count : 0u, st != NUTDB_ST_OK ? 1u : 0u);
+  }
+  uint2 incl, total;
+  block_scan<U2AddOp>(v, ws, incl, total);
+  if (threadIdx.x == 0) tileS[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict__ stmt, uint32_t nstmt,
+                                                          const uint2* __restrict__ tilePref,
+                                                          const uint4* __restrict__ scratch,
+                                                          const uint4* __restrict__ retry_nodes,
+                                                          uint4* __restrict__ node_out, uint4* __restrict__ err_out) {
+  __shared__ uint2 ws[32];
+  __shared__ uint32_t lbegin[FIN_THREADS + 1];
+  __shared__ const uint4* lsrc[FIN_THREADS];
+  const uint32_t s = blockIdx.x * FIN_THREADS + threadIdx.x;
+  uint2 v = make_uint2(0u, 0u);
+  const uint4* src = nullptr;
+  NutdbStmt S;
+  S.status = NUTDB_ST_OK;
+  if (s < nstmt) {
+    S = stmt[s];
+    v = make_uint2(S.status == NUTDB_ST_OK ? S.node_count : 0u, S.status != NUTDB_ST_OK ? 1u : 0u);
+    src = S.node_begin == RETRY_NONE ? scratch + ((size_t)S.tok_begin + (size_t)NODE_SLACK * s)
+                                     : retry_nodes + S.node_begin;
+  }
+  uint2 incl, total;
+  const uint2 excl = block_scan<U2AddOp>(v, ws, incl, total);
+  const uint2 base = tilePref[blockIdx.x];
+  lbegin[threadIdx.x] = excl.x;
+  lsrc[threadIdx.x] = src;
+  if (threadIdx.x == 0) lbegin[FIN_THREADS] = total.x;
+  if (s < nstmt) {
+    stmt[s].node_begin = base.x + excl.x;
+    if (v.y) {
+      uint4 e0, e1;
+      if (S.tok_count == 0) {  // empty statement: EmptyQuery, no position
+        e0 = make_uint4(s, (uint32_t)NUTDB_ST_SYNTAX_ERROR | ((uint32_t)NUTDB_SE_EmptyQuery << 16), 0u, 0u);
+        e1 = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        e0 = src[0];
+        e1 = src[1];
+      }
+      err_out[2 * (size_t)(base.y + excl.y)] = e0;
+      err_out[2 * (size_t)(base.y + excl.y) + 1] = e1;
+    }
+  }
+  __syncthreads();
+  const uint32_t nblock = lbegin[FIN_THREADS];
+  for (uint32_t j = threadIdx.x; j < nblock; j += FIN_THREADS) {
+    uint32_t lo = 0, hi = FIN_THREADS;  // last k with lbegin[k] <= j
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (lbegin[mid] <= j) lo = mid;
+      else hi = mid;
+    }
+    node_out[(size_t)base.x + j] = lsrc[lo][j - lbegin[lo]];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: context, buffers, the C ABI
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct NutdbCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  std::string err;
+  LexTables* dLex = nullptr;
+  npar::ParseTables* dPar = nullptr;
+  // device buffers (grow only)
+  DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+      tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
+      tileS, tilePrefS, nodes, errs, small;
+  // pinned host buffers
+  HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
+  float ms[5] = {0, 0, 0, 0, 0};
+  int launches = 0;
+  bool batch_live = false;
+  NutdbBatchDevice dev_view{};
+};
+
+namespace {
+
+bool ck(NutdbCtx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  c->err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+#define CK(call)                         \
+  do {                                   \
+    if (!ck(ctx, (call), #call)) return NUTDB_E_CUDA; \
+  } while (0)
+
+int ensure_dev(NutdbCtx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return NUTDB_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? NUTDB_E_NOMEM : NUTDB_E_CUDA;
+  }
+  b.cap = want;
+  return NUTDB_OK;
+}
+int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return NUTDB_OK;
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMallocHost(&b.p, want);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return NUTDB_E_NOMEM;
+  }
+  b.cap = want;
+  return NUTDB_OK;
+}
+#define ENSURE_DEV(buf, bytes)                      \
+  do {                                              \
+    int rc_ = ensure_dev(ctx, ctx->buf, (bytes));   \
+    if (rc_ != NUTDB_OK) return rc_;                \
+  } while (0)
+#define ENSURE_HOST(buf, bytes)                     \
+  do {                                              \
+    int rc_ = ensure_host(ctx, ctx->buf, (bytes));  \
+    if (rc_ != NUTDB_OK) return rc_;                \
+  } while (0)
+
+void free_all(NutdbCtx* c) {
+  DevBuf* d[] = {&c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+                 &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
+                 &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
+                 &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
+                 &c->small};
+  for (DevBuf* b : d)
+    if (b->p) cudaFree(b->p);
+  HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
+                  &c->hRetry};
+  for (HostBuf* b : h)
+    if (b->p) cudaFreeHost(b->p);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nutdb_gpu_version(void) { return "nutdb-gpu 0.1 (sm_100a)"; }
+
+NutdbCtx* nutdb_gpu_ctx_create(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return nullptr;  // no CPU fallback: without a CUDA device there is no context
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  NutdbCtx* ctx = new (std::nothrow) NutdbCtx();
+  if (!ctx) return nullptr;
+  ctx->device = device;
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 6 && ok; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  LexTables lt;
+  try {
+    build_lex_tables(lt);
+  } catch (...) {
+    ok = false;
+  }
+  ok = ok && cudaMalloc(&ctx->dLex, sizeof(LexTables)) == cudaSuccess &&
+       cudaMalloc(&ctx->dPar, sizeof(npar::ParseTables)) == cudaSuccess &&
+       cudaMemcpy(ctx->dLex, &lt, sizeof(lt), cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(ctx->dPar, &npar::PARSE_TABLES, sizeof(npar::ParseTables), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) ok = ensure_dev(ctx, ctx->small, 256) == NUTDB_OK && ensure_host(ctx, ctx->hSmall, 256) == NUTDB_OK;
+  if (!ok) {
+    nutdb_gpu_ctx_destroy(ctx);
+    return nullptr;
+  }
+  return ctx;
+}
+
+void nutdb_gpu_ctx_destroy(NutdbCtx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_all(ctx);
+  if (ctx->dLex) cudaFree(ctx->dLex);
+  if (ctx->dPar) cudaFree(ctx->dPar);
+  for (int i = 0; i < 6; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* nutdb_gpu_last_error(const NutdbCtx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+
+int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stmt_off, uint64_t n_stmt, uint32_t flags,
+                          NutdbBatch* out) {
+  if (!ctx) return NUTDB_E_CUDA;
+  if (!out || (!stmt_off) || (n_stmt > 0 && !sql && !(flags & NUTDB_F_DEVICE_INPUT))) {
+    ctx->err = "null argument";
+    return NUTDB_E_ARG;
+  }
+  if (n_stmt >= 0x7FFFFFFFull) {
+    ctx->err = "too many statements in one batch";
+    return NUTDB_E_ARG;
+  }
+  std::memset(out, 0, sizeof(*out));
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const bool dev_in = (flags & NUTDB_F_DEVICE_INPUT) != 0;
+  const bool lex_only = (flags & NUTDB_F_ALL_TOKENS) != 0;
+  const uint32_t nstmt = (uint32_t)n_stmt;
+  ctx->launches = 0;
+  ctx->batch_live = false;
+  uint32_t* hS = (uint32_t*)ctx->hSmall.p;
+  uint32_t* dS = (uint32_t*)ctx->small.p;  // [0]=bad offsets, [1]=retry count, [4..7]=CSum total, [8..9]=stmt totals
+
+  // ---- input ----
+  uint64_t off_first = 0, off_last = 0;
+  if (dev_in) {
+    CK(cudaMemcpyAsync(hS, stmt_off, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hS + 2, stmt_off + n_stmt, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(&off_first, hS, 8);
+    std::memcpy(&off_last, hS + 2, 8);
+  } else {
+    off_first = stmt_off[0];
+    off_last = stmt_off[n_stmt];
+  }
+  if (off_last < off_first || off_last - off_first >= 0x7FFFFFFFull) {
+    ctx->err = "statement offsets must ascend and span fewer than 2^31 bytes";
+    return NUTDB_E_ARG;
+  }
+  const uint32_t n = (uint32_t)(off_last - off_first);
+  const uint32_t ntiles = (n + LEX_TILE - 1) / LEX_TILE;
+  const size_t nchunks = (size_t)ntiles * LEX_THREADS;
+
+  CK(cudaEventRecord(ctx->ev[0], st));
+  ENSURE_DEV(off32, 4 * ((size_t)nstmt + 1));
+  ENSURE_DEV(bitmap, 4 * (nchunks + 1));
+  ENSURE_DEV(stmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
+  ENSURE_DEV(stmtTokBegin, 4 * ((size_t)nstmt + 1));
+  ENSURE_DEV(stmtTokEnd, 4 * ((size_t)nstmt + 1));
+  const uint8_t* dText = nullptr;
+  const uint64_t* dOff = nullptr;
+  if (dev_in) {
+    dOff = stmt_off;
+    const uint8_t* p = sql + off_first;
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+      dText = p;
+    } else {  // misaligned device input: one device-to-device copy into our aligned buffer
+      ENSURE_DEV(text, (size_t)ntiles * LEX_TILE + 16);
+      CK(cudaMemcpyAsync(ctx->text.p, p, n, cudaMemcpyDeviceToDevice, st));
+      dText = (const uint8_t*)ctx->text.p;
+    }
+  } else {
+    ENSURE_DEV(text, (size_t)ntiles * LEX_TILE + 16);
+    ENSURE_DEV(off64, 8 * ((size_t)nstmt + 1));
+    if (n) CK(cudaMemcpyAsync(ctx->text.p, sql + off_first, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->off64.p, stmt_off, 8 * ((size_t)nstmt + 1), cudaMemcpyHostToDevice, st));
+    dText = (const uint8_t*)ctx->text.p;
+    dOff = (const uint64_t*)ctx->off64.p;
+  }
+  CK(cudaEventRecord(ctx->ev[1], st));
+
+  // ---- lexer ----
+  CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 1), st));
+  CK(cudaMemsetAsync(dS, 0, 64, st));
+  {
+    const uint32_t blocks = (uint32_t)(((uint64_t)nstmt + 1 + 255) / 256);
+    k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p, dS);
+    ctx->launches++;
+  }
+  uint32_t ntok = 0;
+  if (n > 0) {
+    ENSURE_DEV(localA, 4 * nchunks);
+    ENSURE_DEV(localB, 4 * nchunks);
+    ENSURE_DEV(localC, 16 * nchunks);
+    ENSURE_DEV(tileA, 4 * (size_t)ntiles);
+    ENSURE_DEV(tileB, 4 * (size_t)ntiles);
+    ENSURE_DEV(tileC, 16 * (size_t)ntiles);
+    ENSURE_DEV(tilePrefC, 16 * (size_t)ntiles);
+    ENSURE_DEV(entA, ntiles);
+    ENSURE_DEV(entB, ntiles);
+    const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
+    k_lex_A<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p);
+    k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles);
+    k_lex_B<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
+                                            (const uint8_t*)ctx->entA.p, (uint32_t*)ctx->localB.p,
+                                            (uint32_t*)ctx->tileB.p);
+    k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileB.p, (uint8_t*)ctx->entB.p, ntiles);
+    k_lex_C<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
+                                            (const uint8_t*)ctx->entA.p, (const uint32_t*)ctx->localB.p,
+                                            (const uint8_t*)ctx->entB.p, lex_only ? 1 : 0, (uint4*)ctx->localC.p,
+                                            (uint4*)ctx->tileC.p);
+    k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p, ntiles,
+                                                     (uint4*)(dS + 4));
+    ctx->launches += 6;
+    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hS[0]) {
+      ctx->err = "statement offsets must ascend";
+      return NUTDB_E_ARG;
+    }
+    ntok = hS[4];
+    ENSURE_DEV(tokType, (size_t)ntok + 16);
+    ENSURE_DEV(tokKw, (size_t)ntok + 16);
+    ENSURE_DEV(tokStart, 4 * ((size_t)ntok + 4));
+    ENSURE_DEV(tokEnd, 4 * ((size_t)ntok + 4));
+    DevSink sink{(uint8_t*)ctx->tokType.p, (uint32_t*)ctx->tokStart.p, (uint32_t*)ctx->tokEnd.p, (uint8_t*)ctx->tokKw.p,
+                 ntok, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p, (const uint32_t*)ctx->off32.p, nstmt};
+    k_lex_D<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
+                                            (const uint8_t*)ctx->entA.p, (const uint32_t*)ctx->localB.p,
+                                            (const uint8_t*)ctx->entB.p, lex_only ? 1 : 0, (const uint4*)ctx->localC.p,
+                                            (const uint4*)ctx->tilePrefC.p, sink);
+    ctx->launches++;
+  } else {
+    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hS[0]) {
+      ctx->err = "statement offsets must ascend";
+      return NUTDB_E_ARG;
+    }
+  }
+  CK(cudaEventRecord(ctx->ev[2], st));
+
+  // ---- parser ----
+  uint64_t n_node = 0, n_err = 0;
+  if (nstmt > 0) {
+    const size_t scratch_nodes = (size_t)ntok + (size_t)NODE_SLACK * nstmt + 4;
+    if (!lex_only) ENSURE_DEV(scratch, 16 * scratch_nodes);
+    ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
+    const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
+    k_parse<<<pblocks, PARSE_THREADS, 0, st>>>(
+        dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
+        (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p,
+        (const uint32_t*)ctx->stmtTokBegin.p, (const uint32_t*)ctx->stmtTokEnd.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
+        (uint4*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, lex_only ? 1 : 0);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(hS, dS, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t nretry = hS[1];
+    if (nretry > 0) {
+      // deep statements: per-statement stack and node ranges sized from their token counts
+      ENSURE_HOST(hRetry, 8 * (size_t)nretry);
+      const uint2* hl = (const uint2*)ctx->hRetry.p;
+      CK(cudaMemcpyAsync(ctx->hRetry.p, ctx->retryList.p, 8 * (size_t)nretry, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      std::vector<uint64_t> noff(nretry + 1), soff(nretry + 1);
+      noff[0] = soff[0] = 0;
+      for (uint32_t i = 0; i < nretry; i++) {
+        uint64_t tc = hl[i].y;
+        noff[i + 1] = noff[i] + 2 * tc + 8;
+        soff[i + 1] = soff[i] + 8 * tc + 64;
+      }
+      if (noff[nretry] >= 0xFFFFFFF0ull) {
+        ctx->err = "deep-statement scratch exceeds 2^32 nodes";
+        return NUTDB_E_NOMEM;
+      }
+      ENSURE_DEV(retryNodeOff, 8 * ((size_t)nretry + 1));
+      ENSURE_DEV(retryStackOff, 8 * ((size_t)nretry + 1));
+      ENSURE_DEV(retryNodes, 16 * (size_t)noff[nretry] + 64);
+      ENSURE_DEV(retryStack, 4 * (size_t)soff[nretry] + 64);
+      CK(cudaMemcpyAsync(ctx->retryNodeOff.p, noff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->retryStackOff.p, soff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));  // noff/soff are stack vectors
+      k_parse_retry<<<(nretry + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
+          dText, (const uint32_t*)ctx->off32.p, (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
+          (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
+          (const uint2*)ctx->retryList.p, nretry, (const uint64_t*)ctx->retryNodeOff.p,
+          (const uint64_t*)ctx->retryStackOff.p, (uint4*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p);
+      ctx->launches++;
+    }
+    const uint32_t stiles = (nstmt + FIN_THREADS - 1) / FIN_THREADS;
+    ENSURE_DEV(tileS, 8 * (size_t)stiles);
+    ENSURE_DEV(tilePrefS, 8 * (size_t)stiles);
+    k_stmt_sums<<<stiles, FIN_THREADS, 0, st>>>((const NutdbStmt*)ctx->stmt.p, nstmt, (uint2*)ctx->tileS.p);
+    k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->tileS.p, (uint2*)ctx->tilePrefS.p, stiles,
+                                                      (uint2*)(dS + 8));
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    n_node = hS[8];
+    n_err = hS[9];
+    ENSURE_DEV(nodes, 16 * (n_node + 1));
+    ENSURE_DEV(errs, 32 * (n_err + 1));
+    k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
+                                               (const uint4*)ctx->scratch.p, (const uint4*)ctx->retryNodes.p,
+                                               (uint4*)ctx->nodes.p, (uint4*)ctx->errs.p);
+    ctx->launches++;
+  }
+  CK(cudaEventRecord(ctx->ev[3], st));
+
+  // ---- output ----
+  out->n_stmt = nstmt;
+  out->n_tok = ntok;
+  out->n_node = n_node;
+  out->n_err = n_err;
+  if (!(flags & NUTDB_F_NO_HOST_COPY)) {
+    ENSURE_HOST(hStmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
+    ENSURE_HOST(hNode, 16 * (n_node + 1));
+    ENSURE_HOST(hErr, 32 * (n_err + 1));
+    if (nstmt) CK(cudaMemcpyAsync(ctx->hStmt.p, ctx->stmt.p, sizeof(NutdbStmt) * (size_t)nstmt, cudaMemcpyDeviceToHost, st));
+    if (n_node) CK(cudaMemcpyAsync(ctx->hNode.p, ctx->nodes.p, 16 * n_node, cudaMemcpyDeviceToHost, st));
+    if (n_err) CK(cudaMemcpyAsync(ctx->hErr.p, ctx->errs.p, 32 * n_err, cudaMemcpyDeviceToHost, st));
+    out->stmt = (const NutdbStmt*)ctx->hStmt.p;
+    out->node = (const NutdbNode*)ctx->hNode.p;
+    out->err = (const NutdbError*)ctx->hErr.p;
+    if (!(flags & NUTDB_F_NO_TOKENS)) {
+      ENSURE_HOST(hTokType, (size_t)ntok + 16);
+      ENSURE_HOST(hTokKw, (size_t)ntok + 16);
+      ENSURE_HOST(hTokStart, 4 * ((size_t)ntok + 4));
+      ENSURE_HOST(hTokEnd, 4 * ((size_t)ntok + 4));
+      if (ntok) {
+        CK(cudaMemcpyAsync(ctx->hTokType.p, ctx->tokType.p, ntok, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->hTokKw.p, ctx->tokKw.p, ntok, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->hTokStart.p, ctx->tokStart.p, 4 * (size_t)ntok, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->hTokEnd.p, ctx->tokEnd.p, 4 * (size_t)ntok, cudaMemcpyDeviceToHost, st));
+      }
+      out->tok_type = (const uint8_t*)ctx->hTokType.p;
+      out->tok_kw = (const uint8_t*)ctx->hTokKw.p;
+      out->tok_start = (const uint32_t*)ctx->hTokStart.p;
+      out->tok_end = (const uint32_t*)ctx->hTokEnd.p;
+    }
+  }
+  CK(cudaEventRecord(ctx->ev[4], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->ms[2], ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&ctx->ms[3], ctx->ev[3], ctx->ev[4]);
+  cudaEventElapsedTime(&ctx->ms[4], ctx->ev[0], ctx->ev[4]);
+  ctx->dev_view.stmt = ctx->stmt.p;
+  ctx->dev_view.tok_type = ctx->tokType.p;
+  ctx->dev_view.tok_start = ctx->tokStart.p;
+  ctx->dev_view.tok_end = ctx->tokEnd.p;
+  ctx->dev_view.tok_kw = ctx->tokKw.p;
+  ctx->dev_view.node = ctx->nodes.p;
+  ctx->dev_view.err = ctx->errs.p;
+  ctx->batch_live = true;
+  out->impl = ctx;
+  return NUTDB_OK;
+}
+
+void nutdb_gpu_batch_free(NutdbCtx* ctx, NutdbBatch* batch) {
+  // Output buffers are owned by the context and re-used by the next batch (grow-only), so
+  // releasing a batch only invalidates the caller's view.
+  if (ctx) ctx->batch_live = false;
+  if (batch) std::memset(batch, 0, sizeof(*batch));
+}
+
+int nutdb_gpu_batch_device(const NutdbBatch* batch, NutdbBatchDevice* out) {
+  if (!batch || !out || !batch->impl) return NUTDB_E_ARG;
+  const NutdbCtx* ctx = (const NutdbCtx*)batch->impl;
+  if (!ctx->batch_live) return NUTDB_E_ARG;
+  *out = ctx->dev_view;
+  return NUTDB_OK;
+}
+
+int nutdb_gpu_parse(NutdbCtx* ctx, const uint8_t* sql, uint64_t len, NutdbBatch* out) {
+  const uint64_t off[2] = {0, len};
+  static const uint8_t empty[1] = {0};
+  return nutdb_gpu_parse_batch(ctx, sql ? sql : empty, off, 1, 0, out);
+}
+
+int nutdb_gpu_last_timing(const NutdbCtx* ctx, float ms[5]) {
+  if (!ctx || !ms) return NUTDB_E_ARG;
+  for (int i = 0; i < 5; i++) ms[i] = ctx->ms[i];
+  return NUTDB_OK;
+}
+
+int nutdb_gpu_last_launches(const NutdbCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

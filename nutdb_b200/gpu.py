@@ -1,0 +1,147 @@
+"""ctypes binding of libnutdb_gpu.so (the C ABI in include/nutdb_gpu.h).
+
+This is the only way the package reaches the parser: there is no Python or CPU implementation
+behind it, and loading fails loudly when the CUDA library is missing or no device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+F_NO_TOKENS, F_DEVICE_INPUT, F_NO_HOST_COPY, F_ALL_TOKENS = 1, 2, 4, 8
+
+NODE_DT = np.dtype([("kind", "u1"), ("sub", "u1"), ("aux", "<u2"), ("parent", "<u4"), ("a", "<u4"), ("b", "<u4")])
+STMT_DT = np.dtype([("status", "<u4"), ("tok_begin", "<u4"), ("tok_count", "<u4"), ("node_begin", "<u4"),
+                    ("node_count", "<u4"), ("tok_used", "<u4")])
+ERR_DT = np.dtype([("stmt", "<u4"), ("cls", "<u2"), ("code", "<u2"), ("line", "<u4"), ("col", "<u4"),
+                   ("pos", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
+
+
+class NutdbBatch(C.Structure):
+    _fields_ = [("n_stmt", C.c_uint64), ("n_tok", C.c_uint64), ("n_node", C.c_uint64), ("n_err", C.c_uint64),
+                ("stmt", C.c_void_p), ("tok_type", C.c_void_p), ("tok_start", C.c_void_p), ("tok_end", C.c_void_p),
+                ("tok_kw", C.c_void_p), ("node", C.c_void_p), ("err", C.c_void_p), ("impl", C.c_void_p)]
+
+
+class NutdbBatchDevice(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("stmt", "tok_type", "tok_start", "tok_end", "tok_kw", "node", "err")]
+
+
+class NutdbGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libnutdb_gpu.so (building it in-tree with nvcc if stale).  Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = _build.GPU_SO
+    try:
+        so = _build.build_gpu()
+    except Exception as e:  # no nvcc on this machine: use the prebuilt library if there is one
+        if not os.path.exists(so):
+            raise NutdbGpuError(f"libnutdb_gpu.so is missing and cannot be built: {e}") from e
+    L = C.CDLL(so)
+    L.nutdb_gpu_ctx_create.restype = C.c_void_p
+    L.nutdb_gpu_ctx_create.argtypes = [C.c_int]
+    L.nutdb_gpu_ctx_destroy.argtypes = [C.c_void_p]
+    L.nutdb_gpu_last_error.restype = C.c_char_p
+    L.nutdb_gpu_last_error.argtypes = [C.c_void_p]
+    L.nutdb_gpu_parse_batch.restype = C.c_int
+    L.nutdb_gpu_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                                        C.POINTER(NutdbBatch)]
+    L.nutdb_gpu_batch_free.argtypes = [C.c_void_p, C.POINTER(NutdbBatch)]
+    L.nutdb_gpu_batch_device.restype = C.c_int
+    L.nutdb_gpu_batch_device.argtypes = [C.POINTER(NutdbBatch), C.POINTER(NutdbBatchDevice)]
+    L.nutdb_gpu_parse.restype = C.c_int
+    L.nutdb_gpu_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(NutdbBatch)]
+    L.nutdb_gpu_last_timing.restype = C.c_int
+    L.nutdb_gpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float * 5)]
+    L.nutdb_gpu_last_launches.restype = C.c_int
+    L.nutdb_gpu_last_launches.argtypes = [C.c_void_p]
+    L.nutdb_gpu_version.restype = C.c_char_p
+    for f in ("nutdb_fmt_debug", "nutdb_fmt_error"):
+        getattr(L, f).restype = C.c_size_t
+        getattr(L, f).argtypes = [C.POINTER(NutdbBatch), C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    _lib = L
+    return L
+
+
+def _view(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype)
+    dtype = np.dtype(dtype)
+    buf = (C.c_uint8 * (count * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype, count)
+
+
+class Batch:
+    """Result of one parse_batch call: numpy arrays with the layout of NutdbBatch."""
+
+    def __init__(self, ctx, raw, copy):
+        self._ctx, self.raw = ctx, raw
+        g = (lambda a: a.copy()) if copy else (lambda a: a)
+        self.n_stmt, self.n_tok, self.n_node, self.n_err = raw.n_stmt, raw.n_tok, raw.n_node, raw.n_err
+        self.stmt = g(_view(raw.stmt, raw.n_stmt, STMT_DT))
+        self.node = g(_view(raw.node, raw.n_node, NODE_DT))
+        self.err = g(_view(raw.err, raw.n_err, ERR_DT))
+        self.tok_type = g(_view(raw.tok_type, raw.n_tok, np.uint8))
+        self.tok_kw = g(_view(raw.tok_kw, raw.n_tok, np.uint8))
+        self.tok_start = g(_view(raw.tok_start, raw.n_tok, np.uint32))
+        self.tok_end = g(_view(raw.tok_end, raw.n_tok, np.uint32))
+
+    def device_pointers(self):
+        d = NutdbBatchDevice()
+        rc = lib().nutdb_gpu_batch_device(C.byref(self.raw), C.byref(d))
+        if rc != 0:
+            raise NutdbGpuError("batch is no longer live")
+        return {n: getattr(d, n) for n, _ in NutdbBatchDevice._fields_}
+
+
+class Context:
+    """One CUDA device (one process per GPU).  Not thread-safe; one live batch at a time."""
+
+    def __init__(self, device=0):
+        self._h = lib().nutdb_gpu_ctx_create(device)
+        if not self._h:
+            raise NutdbGpuError(f"cannot create a nutdb GPU context on CUDA device {device}: no usable device. "
+                                "There is no CPU fallback.")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nutdb_gpu_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def last_error(self):
+        return lib().nutdb_gpu_last_error(self._h).decode()
+
+    def parse_batch_raw(self, sql_ptr, off_ptr, n_stmt, flags=0, copy=True):
+        raw = NutdbBatch()
+        rc = lib().nutdb_gpu_parse_batch(self._h, sql_ptr, off_ptr, n_stmt, flags, C.byref(raw))
+        if rc != 0:
+            raise NutdbGpuError(f"nutdb_gpu_parse_batch failed ({rc}): {self.last_error()}")
+        return Batch(self, raw, copy)
+
+    def parse_batch(self, text, offs, flags=0, copy=True):
+        """text: bytes / uint8 array holding all statements; offs: uint64[n+1] ascending offsets into it."""
+        t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text)
+        o = np.ascontiguousarray(offs, np.uint64)
+        assert t.dtype == np.uint8 and o.ndim == 1 and len(o) >= 1
+        return self.parse_batch_raw(t.ctypes.data, o.ctypes.data, len(o) - 1, flags, copy)
+
+    def timing(self):
+        ms = (C.c_float * 5)()
+        lib().nutdb_gpu_last_timing(self._h, C.byref(ms))
+        return dict(h2d=ms[0], lex=ms[1], parse=ms[2], d2h=ms[3], total=ms[4])
+
+    def launches(self):
+        return lib().nutdb_gpu_last_launches(self._h)

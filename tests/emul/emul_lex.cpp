@@ -34,8 +34,8 @@ struct ArraySink {
     end[i] = e;
     kw[i] = k;
   }
-  void seg_begin(uint32_t seg, uint32_t first) { seg_begin_arr[seg] = first; }
-  void seg_end(uint32_t seg, uint32_t endi) { seg_end_arr[seg] = endi; }
+  void seg_begin(uint32_t seg, uint32_t first, uint32_t) { seg_begin_arr[seg] = first; }
+  void seg_end(uint32_t seg, uint32_t endi, uint32_t) { seg_end_arr[seg] = endi; }
 };
 LexTables g_tables;
 bool g_init = false;

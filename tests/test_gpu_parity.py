@@ -1,0 +1,125 @@
+"""Parity of the CUDA path (through the C ABI of libnutdb_gpu.so) with the oracle: bit-exact
+statement records, flat ASTs, error records and pulled tokens.  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+
+import fuzz
+import oracle_lib as O
+import parity as P
+from nutdb_b200 import workload as W
+
+pytestmark = pytest.mark.gpu
+
+CORPUS = W.corpus_statements()
+APP_D = ["SELECT * FROM table WHERE 1 = 1", "", "  ", ";", "-- c", "SELECT 1d", "SELECT a FROM t ORDER BY a ASC",
+         "SELECT $0", "SELECT 'abc", "select 1; 'oops", "\t1d", "select `你 好`, 'he''llo' -- x"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from nutdb_b200 import gpu
+    c = gpu.Context(0)
+    yield c
+    c.close()
+
+
+def check(ctx, stmts):
+    text, offs = P.make_batch(stmts)
+    got = ctx.parse_batch(text, offs)
+    bad = P.compare_with_oracle(got, text, offs)
+    assert not bad, "\n".join(bad)
+    return got
+
+
+def test_corpus_and_known_vectors(ctx):
+    got = check(ctx, CORPUS + APP_D)
+    assert (got.stmt["status"][:len(CORPUS)] == 0).all()  # tests/parser_test.rs:19-34
+
+
+def test_single_statement_entry(ctx):
+    # nutdb_gpu_parse == Parser::parse(sql) (mod.rs:27)
+    import ctypes as C
+    from nutdb_b200 import gpu
+    for s in [b"SELECT * FROM table WHERE 1 = 1", b"", b"SELECT 1d"]:
+        raw = gpu.NutdbBatch()
+        rc = gpu.lib().nutdb_gpu_parse(ctx._h, s, len(s), C.byref(raw))
+        assert rc == 0
+        b = gpu.Batch(ctx, raw, True)
+        want = O.parse(s)
+        assert int(b.stmt["status"][0]) == want.status
+        assert np.array_equal(b.node, want.nodes)
+
+
+def test_empty_and_degenerate_batches(ctx):
+    b = ctx.parse_batch(np.zeros(16, np.uint8), np.zeros(1, np.uint64))
+    assert b.n_stmt == 0 and b.n_node == 0 and b.n_err == 0
+    check(ctx, ["", "", ""])
+    check(ctx, ["", "select 1", "", "", "select 2", ""])
+    check(ctx, ["x" * 8192, "select 1"])             # statement = exactly one tile
+    check(ctx, ["select '" + "a" * 20000 + "'", "select 1 /* " + "c" * 9000 + " */, 2"])  # tokens spanning tiles
+
+
+@pytest.mark.parametrize("config", [2, 3, 4])
+def test_synthetic_config(ctx, config):
+    text, offs = W.generate(config, 4 << 20)
+    got = ctx.parse_batch(text, offs)
+    bad = P.compare_with_oracle(got, text, offs, check_tokens=(config != 2))
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_mutation_fuzz(ctx, seed):
+    stmts = fuzz.fuzz_statements(CORPUS + fuzz.EXTRA_SEEDS, 8000, seed=seed, max_mut=5)
+    check(ctx, stmts)
+
+
+def test_full_token_stream_incl_whitespace_and_comments(ctx):
+    from nutdb_b200 import gpu
+    stmts = [s for s in CORPUS + [x.encode() for x in APP_D] + fuzz.fuzz_statements(CORPUS, 400, seed=9) if len(s)]
+    text, offs = P.make_batch(stmts)
+    got = ctx.parse_batch(text, offs, flags=gpu.F_ALL_TOKENS)
+    for i, s in enumerate(stmts):
+        want, err = O.tokenize(s)
+        b = int(got.stmt["tok_begin"][i])
+        e = b + int(got.stmt["tok_count"][i])
+        g = list(zip(got.tok_type[b:e].tolist(), got.tok_start[b:e].tolist(), got.tok_end[b:e].tolist()))
+        assert g[:len(want)] == want, s
+        if err is not None:
+            assert g[len(want)] == (40, err["pos"], err["site"]), s
+
+
+def test_deep_nesting_takes_the_retry_path(ctx):
+    d = 256
+    stmts = ["select " + "(" * d + "1" + ")" * d, "select " + "(select " * d + "1" + ")" * d,
+             "select " + "[" * d + "1" + "]" * d + " from t", "select " + "f(" * d + "x" + ")" * d,
+             "select " + "not " * 300 + "x", "select " + "CASE WHEN a THEN " * 100 + "1" + " END" * 100]
+    got = check(ctx, stmts)
+    assert (got.stmt["status"] == 0).all()
+
+
+def test_device_input_and_no_host_copy(ctx):
+    import torch
+    from nutdb_b200 import gpu
+    text, offs = W.generate(2, 1 << 20)
+    dt = torch.from_numpy(text).cuda()
+    do = torch.from_numpy(offs.astype(np.int64)).cuda()
+    torch.cuda.synchronize()
+    got = ctx.parse_batch_raw(dt.data_ptr(), do.data_ptr(), len(offs) - 1, gpu.F_DEVICE_INPUT)
+    bad = P.compare_with_oracle(got, text, offs, check_tokens=False)
+    assert not bad, "\n".join(bad)
+    # misaligned device text pointer
+    dt2 = torch.zeros(len(text) + 3, dtype=torch.uint8, device="cuda")
+    dt2[3:] = dt
+    torch.cuda.synchronize()
+    got2 = ctx.parse_batch_raw(dt2.data_ptr() + 3, do.data_ptr(), len(offs) - 1, gpu.F_DEVICE_INPUT)
+    assert np.array_equal(got2.node, got.node) and np.array_equal(got2.stmt, got.stmt)
+    got3 = ctx.parse_batch_raw(dt.data_ptr(), do.data_ptr(), len(offs) - 1, gpu.F_DEVICE_INPUT | gpu.F_NO_HOST_COPY)
+    assert got3.n_node == got.n_node and len(got3.node) == 0
+    ptrs = got3.device_pointers()
+    assert ptrs["node"] and ptrs["stmt"]
+
+
+def test_bad_arguments(ctx):
+    from nutdb_b200 import gpu
+    with pytest.raises(gpu.NutdbGpuError):
+        ctx.parse_batch(b"select 1", np.array([0, 8, 4], np.uint64))
