@@ -369,6 +369,15 @@ int nutdb_gpu_last_timing(const NutdbCtx *ctx, float ms[5]);
 /* Number of kernel launches issued by the last parse_batch call. */
 int nutdb_gpu_last_launches(const NutdbCtx *ctx);
 
+/* Per-kernel timing: with profiling on, every kernel launch of parse_batch is bracketed by CUDA
+ * events on the library's stream.  nutdb_gpu_kernel_timing returns the number of launches of the
+ * last call and, for 0 <= i < that number, the kernel's name and duration in milliseconds. */
+void nutdb_gpu_set_profiling(NutdbCtx *ctx, int on);
+int nutdb_gpu_kernel_timing(const NutdbCtx *ctx, int i, const char **name, float *ms);
+/* The cudaStream_t every kernel and copy of this context is issued on (for callers that want to
+ * order their own work or record their own events against it). */
+void *nutdb_gpu_ctx_stream(const NutdbCtx *ctx);
+
 /* Host-side helpers (pure CPU formatting of results; no parsing):
  * Rust `{:?}` text of statement i's AST, and `Display` text of its error, written
  * NUL-terminated into buf (returns needed length). `sql` must be the statement's own text. */

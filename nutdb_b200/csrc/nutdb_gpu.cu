@@ -619,6 +619,24 @@ struct NutdbCtx {
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
   float ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
+  // optional per-kernel timing (nutdb_gpu_set_profiling): events around every launch
+  bool profiling = false;
+  struct KRec {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  std::vector<KRec> recs;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<std::pair<const char*, float>> kernel_ms;
+  cudaEvent_t take_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  }
   bool batch_live = false;
   NutdbBatchDevice dev_view{};
 };
@@ -670,6 +688,22 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   b.cap = want;
   return NUTDB_OK;
 }
+// LAUNCH(name, kernel<<<...>>>(...)): counts the launch and, in profiling mode, brackets it with events
+#define LAUNCH(name, ...)                                  \
+  do {                                                     \
+    NutdbCtx::KRec r_{name, nullptr, nullptr};             \
+    if (ctx->profiling) {                                  \
+      r_.a = ctx->take_event();                            \
+      r_.b = ctx->take_event();                            \
+      cudaEventRecord(r_.a, st);                           \
+    }                                                      \
+    __VA_ARGS__;                                           \
+    ctx->launches++;                                       \
+    if (ctx->profiling) {                                  \
+      cudaEventRecord(r_.b, st);                           \
+      ctx->recs.push_back(r_);                             \
+    }                                                      \
+  } while (0)
 #define ENSURE_DEV(buf, bytes)                      \
   do {                                              \
     int rc_ = ensure_dev(ctx, ctx->buf, (bytes));   \
@@ -740,6 +774,7 @@ void nutdb_gpu_ctx_destroy(NutdbCtx* ctx) {
   if (ctx->dPar) cudaFree(ctx->dPar);
   for (int i = 0; i < 6; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -765,6 +800,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   const uint32_t nstmt = (uint32_t)n_stmt;
   ctx->launches = 0;
   ctx->batch_live = false;
+  ctx->recs.clear();
+  ctx->ev_used = 0;
   uint32_t* hS = (uint32_t*)ctx->hSmall.p;
   uint32_t* dS = (uint32_t*)ctx->small.p;  // [0]=bad offsets, [1]=retry count, [4..7]=CSum total, [8..9]=stmt totals
 
@@ -821,8 +858,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   CK(cudaMemsetAsync(dS, 0, 64, st));
   {
     const uint32_t blocks = (uint32_t)(((uint64_t)nstmt + 1 + 255) / 256);
-    k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p, dS);
-    ctx->launches++;
+    LAUNCH("k_prep", k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p, dS));
   }
   uint32_t ntok = 0;
   if (n > 0) {
@@ -836,19 +872,18 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(entA, ntiles);
     ENSURE_DEV(entB, ntiles);
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
-    k_lex_A<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p);
-    k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles);
-    k_lex_B<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
+    LAUNCH("k_lex_A", k_lex_A<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p));
+    LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
+    LAUNCH("k_lex_B", k_lex_B<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
                                             (const uint8_t*)ctx->entA.p, (uint32_t*)ctx->localB.p,
-                                            (uint32_t*)ctx->tileB.p);
-    k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileB.p, (uint8_t*)ctx->entB.p, ntiles);
-    k_lex_C<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
+                                            (uint32_t*)ctx->tileB.p));
+    LAUNCH("k_scan_B", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileB.p, (uint8_t*)ctx->entB.p, ntiles));
+    LAUNCH("k_lex_C", k_lex_C<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
                                             (const uint8_t*)ctx->entA.p, (const uint32_t*)ctx->localB.p,
                                             (const uint8_t*)ctx->entB.p, lex_only ? 1 : 0, (uint4*)ctx->localC.p,
-                                            (uint4*)ctx->tileC.p);
-    k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p, ntiles,
-                                                     (uint4*)(dS + 4));
-    ctx->launches += 6;
+                                            (uint4*)ctx->tileC.p));
+    LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p, ntiles,
+                                                     (uint4*)(dS + 4)));
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (hS[0]) {
@@ -862,11 +897,10 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(tokEnd, 4 * ((size_t)ntok + 4));
     DevSink sink{(uint8_t*)ctx->tokType.p, (uint32_t*)ctx->tokStart.p, (uint32_t*)ctx->tokEnd.p, (uint8_t*)ctx->tokKw.p,
                  ntok, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p, (const uint32_t*)ctx->off32.p, nstmt};
-    k_lex_D<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
+    LAUNCH("k_lex_D", k_lex_D<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
                                             (const uint8_t*)ctx->entA.p, (const uint32_t*)ctx->localB.p,
                                             (const uint8_t*)ctx->entB.p, lex_only ? 1 : 0, (const uint4*)ctx->localC.p,
-                                            (const uint4*)ctx->tilePrefC.p, sink);
-    ctx->launches++;
+                                            (const uint4*)ctx->tilePrefC.p, sink));
   } else {
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -884,12 +918,11 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     if (!lex_only) ENSURE_DEV(scratch, 16 * scratch_nodes);
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
     const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
-    k_parse<<<pblocks, PARSE_THREADS, 0, st>>>(
+    LAUNCH("k_parse", k_parse<<<pblocks, PARSE_THREADS, 0, st>>>(
         dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
         (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p,
         (const uint32_t*)ctx->stmtTokBegin.p, (const uint32_t*)ctx->stmtTokEnd.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
-        (uint4*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, lex_only ? 1 : 0);
-    ctx->launches++;
+        (uint4*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, lex_only ? 1 : 0));
     CK(cudaMemcpyAsync(hS, dS, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t nretry = hS[1];
@@ -917,30 +950,27 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
       CK(cudaMemcpyAsync(ctx->retryNodeOff.p, noff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->retryStackOff.p, soff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
       CK(cudaStreamSynchronize(st));  // noff/soff are stack vectors
-      k_parse_retry<<<(nretry + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
+      LAUNCH("k_parse_retry", k_parse_retry<<<(nretry + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
           dText, (const uint32_t*)ctx->off32.p, (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
           (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
           (const uint2*)ctx->retryList.p, nretry, (const uint64_t*)ctx->retryNodeOff.p,
-          (const uint64_t*)ctx->retryStackOff.p, (uint4*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p);
-      ctx->launches++;
+          (const uint64_t*)ctx->retryStackOff.p, (uint4*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p));
     }
     const uint32_t stiles = (nstmt + FIN_THREADS - 1) / FIN_THREADS;
     ENSURE_DEV(tileS, 8 * (size_t)stiles);
     ENSURE_DEV(tilePrefS, 8 * (size_t)stiles);
-    k_stmt_sums<<<stiles, FIN_THREADS, 0, st>>>((const NutdbStmt*)ctx->stmt.p, nstmt, (uint2*)ctx->tileS.p);
-    k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->tileS.p, (uint2*)ctx->tilePrefS.p, stiles,
-                                                      (uint2*)(dS + 8));
-    ctx->launches += 2;
+    LAUNCH("k_stmt_sums", k_stmt_sums<<<stiles, FIN_THREADS, 0, st>>>((const NutdbStmt*)ctx->stmt.p, nstmt, (uint2*)ctx->tileS.p));
+    LAUNCH("k_scan_S", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->tileS.p, (uint2*)ctx->tilePrefS.p, stiles,
+                                                      (uint2*)(dS + 8)));
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     n_node = hS[8];
     n_err = hS[9];
     ENSURE_DEV(nodes, 16 * (n_node + 1));
     ENSURE_DEV(errs, 32 * (n_err + 1));
-    k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
+    LAUNCH("k_finalize", k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
                                                (const uint4*)ctx->scratch.p, (const uint4*)ctx->retryNodes.p,
-                                               (uint4*)ctx->nodes.p, (uint4*)ctx->errs.p);
-    ctx->launches++;
+                                               (uint4*)ctx->nodes.p, (uint4*)ctx->errs.p));
   }
   CK(cudaEventRecord(ctx->ev[3], st));
 
@@ -984,6 +1014,12 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   cudaEventElapsedTime(&ctx->ms[2], ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&ctx->ms[3], ctx->ev[3], ctx->ev[4]);
   cudaEventElapsedTime(&ctx->ms[4], ctx->ev[0], ctx->ev[4]);
+  ctx->kernel_ms.clear();
+  for (const NutdbCtx::KRec& r : ctx->recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    ctx->kernel_ms.emplace_back(r.name, ms);
+  }
   ctx->dev_view.stmt = ctx->stmt.p;
   ctx->dev_view.tok_type = ctx->tokType.p;
   ctx->dev_view.tok_start = ctx->tokStart.p;
@@ -1024,5 +1060,18 @@ int nutdb_gpu_last_timing(const NutdbCtx* ctx, float ms[5]) {
 }
 
 int nutdb_gpu_last_launches(const NutdbCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+void nutdb_gpu_set_profiling(NutdbCtx* ctx, int on) {
+  if (ctx) ctx->profiling = on != 0;
+}
+int nutdb_gpu_kernel_timing(const NutdbCtx* ctx, int i, const char** name, float* ms) {
+  if (!ctx) return 0;
+  if (i >= 0 && (size_t)i < ctx->kernel_ms.size()) {
+    if (name) *name = ctx->kernel_ms[i].first;
+    if (ms) *ms = ctx->kernel_ms[i].second;
+  }
+  return (int)ctx->kernel_ms.size();
+}
+void* nutdb_gpu_ctx_stream(const NutdbCtx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 }  // extern "C"

@@ -66,6 +66,11 @@ def lib():
     L.nutdb_gpu_last_launches.restype = C.c_int
     L.nutdb_gpu_last_launches.argtypes = [C.c_void_p]
     L.nutdb_gpu_version.restype = C.c_char_p
+    L.nutdb_gpu_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.nutdb_gpu_kernel_timing.restype = C.c_int
+    L.nutdb_gpu_kernel_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+    L.nutdb_gpu_ctx_stream.restype = C.c_void_p
+    L.nutdb_gpu_ctx_stream.argtypes = [C.c_void_p]
     for f in ("nutdb_fmt_debug", "nutdb_fmt_error"):
         getattr(L, f).restype = C.c_size_t
         getattr(L, f).argtypes = [C.POINTER(NutdbBatch), C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -145,3 +150,21 @@ class Context:
 
     def launches(self):
         return lib().nutdb_gpu_last_launches(self._h)
+
+    def set_profiling(self, on):
+        lib().nutdb_gpu_set_profiling(self._h, 1 if on else 0)
+
+    def kernel_timing(self):
+        """[(kernel name, ms)] of the last parse_batch call (needs set_profiling(True))."""
+        L = lib()
+        n = L.nutdb_gpu_kernel_timing(self._h, -1, None, None)
+        out = []
+        for i in range(n):
+            name, ms = C.c_char_p(), C.c_float()
+            L.nutdb_gpu_kernel_timing(self._h, i, C.byref(name), C.byref(ms))
+            out.append((name.value.decode(), ms.value))
+        return out
+
+    def stream(self):
+        """cudaStream_t (as int) that all work of this context is issued on."""
+        return lib().nutdb_gpu_ctx_stream(self._h)
