@@ -123,3 +123,22 @@ def test_bad_arguments(ctx):
     from nutdb_b200 import gpu
     with pytest.raises(gpu.NutdbGpuError):
         ctx.parse_batch(b"select 1", np.array([0, 8, 4], np.uint64))
+
+
+def test_parser_parse_mirrors_the_reference_entry(ctx):
+    # tests/parser_test.rs:3-34: every corpus file parses Ok; plus the Display / Debug texts
+    from nutdb_b200.parser import Parser, ParseError
+    for s in CORPUS:
+        st = Parser.parse(s)
+        assert repr(st) == O.parse(s).debug
+    with pytest.raises(ParseError) as ei:
+        Parser.parse("SELECT 1d")
+    assert str(ei.value) == O.parse("SELECT 1d").error == \
+        "Lex Error: Unexpected Char: 'd' cannot be a part of integer literal near line 1 col 9"
+    with pytest.raises(ParseError) as ei:
+        Parser.parse("")
+    assert str(ei.value) == "Syntax Error: empty query"
+    res = Parser.parse_many(fuzz.EXTRA_SEEDS + [b"select $0", b"select 'abc"])
+    for s, r in zip(fuzz.EXTRA_SEEDS + [b"select $0", b"select 'abc"], res):
+        want = O.parse(s)
+        assert (repr(r) == want.debug) if want.ok else (str(r) == want.error)
