@@ -758,13 +758,12 @@ NUTDB_HD LexCarry chunk_walk(const LexTables& T, Src& src, Sink& sink, uint32_t 
   return w.c;
 }
 
-template <class Src>
-NUTDB_HD CSum chunk_count(const LexTables& T, Src& src, uint32_t begin, uint32_t end, uint32_t batch_end,
-                          uint8_t entryA, uint8_t entryB, bool emit_all) {
+template <bool EmitAll, class Src>
+NUTDB_HD CSum chunk_count_t(const LexTables& T, Src& src, uint32_t begin, uint32_t end, uint32_t batch_end,
+                            uint8_t entryA, uint8_t entryB) {
   CountSink sink;
   CSum zero = csum_identity();
-  LexCarry c = emit_all ? chunk_walk<true>(T, src, sink, begin, end, batch_end, entryA, entryB, zero, true)
-                        : chunk_walk<false>(T, src, sink, begin, end, batch_end, entryA, entryB, zero, true);
+  LexCarry c = chunk_walk<EmitAll>(T, src, sink, begin, end, batch_end, entryA, entryB, zero, true);
   CSum s;
   s.count = c.count;
   s.nseg = c.nseg_seen;
@@ -773,6 +772,12 @@ NUTDB_HD CSum chunk_count(const LexTables& T, Src& src, uint32_t begin, uint32_t
   s.escaped = c.escaped;
   s.stmt_start = c.stmt_start;
   return s;
+}
+template <class Src>
+NUTDB_HD CSum chunk_count(const LexTables& T, Src& src, uint32_t begin, uint32_t end, uint32_t batch_end,
+                          uint8_t entryA, uint8_t entryB, bool emit_all) {
+  return emit_all ? chunk_count_t<true>(T, src, begin, end, batch_end, entryA, entryB)
+                  : chunk_count_t<false>(T, src, begin, end, batch_end, entryA, entryB);
 }
 
 }  // namespace nlex

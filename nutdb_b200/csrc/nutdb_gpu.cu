@@ -290,12 +290,13 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_B(const uint8_t* __restrict
   if (threadIdx.x == 0) tileB[blockIdx.x] = total;
 }
 
+template <bool EmitAll>
 __global__ void __launch_bounds__(LEX_THREADS) k_lex_C(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
                                                        uint32_t n, const LexTables* __restrict__ gT,
                                                        const uint32_t* __restrict__ localA,
                                                        const uint8_t* __restrict__ tileEntA,
                                                        const uint32_t* __restrict__ localB,
-                                                       const uint8_t* __restrict__ tileEntB, int emit_all,
+                                                       const uint8_t* __restrict__ tileEntB,
                                                        uint4* __restrict__ localC, uint4* __restrict__ tileC) {
   __shared__ LexShared S;
   __shared__ uint4 ws[32];
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_C(const uint8_t* __restrict
   if (begin < n) {
     const uint8_t entA = (uint8_t)vec8_apply(localA[chunk], tileEntA[blockIdx.x]);
     const uint8_t entB = (uint8_t)vec8_apply(localB[chunk], tileEntB[blockIdx.x]);
-    v = csum_pack(chunk_count(S.T, src, begin, begin + LEX_CHUNK, n, entA, entB, emit_all != 0));
+    v = csum_pack(chunk_count_t<EmitAll>(S.T, src, begin, begin + LEX_CHUNK, n, entA, entB));
   }
   uint4 incl, total;
   uint4 excl = block_scan<CSumOp>(v, ws, incl, total);
@@ -354,12 +355,13 @@ struct DevSink {
   }
 };
 
+template <bool EmitAll>
 __global__ void __launch_bounds__(LEX_THREADS) k_lex_D(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
                                                        uint32_t n, const LexTables* __restrict__ gT,
                                                        const uint32_t* __restrict__ localA,
                                                        const uint8_t* __restrict__ tileEntA,
                                                        const uint32_t* __restrict__ localB,
-                                                       const uint8_t* __restrict__ tileEntB, int emit_all,
+                                                       const uint8_t* __restrict__ tileEntB,
                                                        const uint4* __restrict__ localC,
                                                        const uint4* __restrict__ tilePrefC, DevSink sink) {
   __shared__ LexShared S;
@@ -374,8 +376,7 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_D(const uint8_t* __restrict
   const uint8_t entA = (uint8_t)vec8_apply(localA[chunk], tileEntA[blockIdx.x]);
   const uint8_t entB = (uint8_t)vec8_apply(localB[chunk], tileEntB[blockIdx.x]);
   const CSum prefix = csum_unpack(CSumOp::then(tilePrefC[blockIdx.x], localC[chunk]));
-  if (emit_all) chunk_walk<true>(S.T, src, sink, begin, begin + LEX_CHUNK, n, entA, entB, prefix, false);
-  else chunk_walk<false>(S.T, src, sink, begin, begin + LEX_CHUNK, n, entA, entB, prefix, false);
+  chunk_walk<EmitAll>(S.T, src, sink, begin, begin + LEX_CHUNK, n, entA, entB, prefix, false);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -878,10 +879,16 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
                                             (const uint8_t*)ctx->entA.p, (uint32_t*)ctx->localB.p,
                                             (uint32_t*)ctx->tileB.p));
     LAUNCH("k_scan_B", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileB.p, (uint8_t*)ctx->entB.p, ntiles));
-    LAUNCH("k_lex_C", k_lex_C<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
-                                            (const uint8_t*)ctx->entA.p, (const uint32_t*)ctx->localB.p,
-                                            (const uint8_t*)ctx->entB.p, lex_only ? 1 : 0, (uint4*)ctx->localC.p,
-                                            (uint4*)ctx->tileC.p));
+    if (lex_only)
+      LAUNCH("k_lex_C", k_lex_C<true><<<ntiles, LEX_THREADS, 0, st>>>(
+                            dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
+                            (const uint32_t*)ctx->localB.p, (const uint8_t*)ctx->entB.p, (uint4*)ctx->localC.p,
+                            (uint4*)ctx->tileC.p));
+    else
+      LAUNCH("k_lex_C", k_lex_C<false><<<ntiles, LEX_THREADS, 0, st>>>(
+                            dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
+                            (const uint32_t*)ctx->localB.p, (const uint8_t*)ctx->entB.p, (uint4*)ctx->localC.p,
+                            (uint4*)ctx->tileC.p));
     LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p, ntiles,
                                                      (uint4*)(dS + 4)));
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
@@ -897,10 +904,16 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(tokEnd, 4 * ((size_t)ntok + 4));
     DevSink sink{(uint8_t*)ctx->tokType.p, (uint32_t*)ctx->tokStart.p, (uint32_t*)ctx->tokEnd.p, (uint8_t*)ctx->tokKw.p,
                  ntok, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p, (const uint32_t*)ctx->off32.p, nstmt};
-    LAUNCH("k_lex_D", k_lex_D<<<ntiles, LEX_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p,
-                                            (const uint8_t*)ctx->entA.p, (const uint32_t*)ctx->localB.p,
-                                            (const uint8_t*)ctx->entB.p, lex_only ? 1 : 0, (const uint4*)ctx->localC.p,
-                                            (const uint4*)ctx->tilePrefC.p, sink));
+    if (lex_only)
+      LAUNCH("k_lex_D", k_lex_D<true><<<ntiles, LEX_THREADS, 0, st>>>(
+                            dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
+                            (const uint32_t*)ctx->localB.p, (const uint8_t*)ctx->entB.p, (const uint4*)ctx->localC.p,
+                            (const uint4*)ctx->tilePrefC.p, sink));
+    else
+      LAUNCH("k_lex_D", k_lex_D<false><<<ntiles, LEX_THREADS, 0, st>>>(
+                            dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
+                            (const uint32_t*)ctx->localB.p, (const uint8_t*)ctx->entB.p, (const uint4*)ctx->localC.p,
+                            (const uint4*)ctx->tilePrefC.p, sink));
   } else {
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
