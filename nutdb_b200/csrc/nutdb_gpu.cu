@@ -394,21 +394,19 @@ struct DTok {
   __device__ __forceinline__ uint32_t end(uint32_t i) const { return i < n ? en[i] : 0u; }
 };
 struct DNodes {
-  uint4* p;
+  uint2* p;
   uint32_t cap;
-  __device__ __forceinline__ NutdbNode get(uint32_t i) const {
-    uint4 v = p[i];
-    NutdbNode x;
+  __device__ __forceinline__ npar::CNode get(uint32_t i) const {
+    uint2 v = p[i];
+    npar::CNode x;
     x.kind = (uint8_t)(v.x & 0xFF);
     x.sub = (uint8_t)((v.x >> 8) & 0xFF);
     x.aux = (uint16_t)(v.x >> 16);
-    x.parent = v.y;
-    x.a = v.z;
-    x.b = v.w;
+    x.x = v.y;
     return x;
   }
-  __device__ __forceinline__ void set(uint32_t i, const NutdbNode& x) {
-    p[i] = make_uint4((uint32_t)x.kind | ((uint32_t)x.sub << 8) | ((uint32_t)x.aux << 16), x.parent, x.a, x.b);
+  __device__ __forceinline__ void set(uint32_t i, const npar::CNode& x) {
+    p[i] = make_uint2((uint32_t)x.kind | ((uint32_t)x.sub << 8) | ((uint32_t)x.aux << 16), x.x);
   }
   __device__ __forceinline__ uint32_t capacity() const { return cap; }
 };
@@ -427,7 +425,7 @@ __device__ __forceinline__ void stage_parse_tables(const npar::ParseTables* g, n
 // writes the result of one statement: its NutdbStmt and, on failure, the error record at the
 // start of its node range (picked up by k_finalize)
 __device__ __forceinline__ void store_result(const npar::ParseResult& res, uint32_t s, uint32_t tb, uint32_t tc,
-                                             uint32_t where, const DText& tx, uint4* node_range, NutdbStmt* stmt) {
+                                             uint32_t where, const DText& tx, uint2* node_range, NutdbStmt* stmt) {
   NutdbStmt S;
   S.status = res.status;
   S.tok_begin = tb;
@@ -442,8 +440,11 @@ __device__ __forceinline__ void store_result(const npar::ParseResult& res, uint3
       pos = res.err_pos;
       npar::get_pos(tx, pos, line, col);
     }
-    node_range[0] = make_uint4(s, (uint32_t)res.status | ((uint32_t)res.err_code << 16), line, col);
-    node_range[1] = make_uint4(pos, res.err_a, res.err_b, res.err_c);
+    // the error record (32 bytes) parks in the statement's own (now unused) compact-node range
+    node_range[0] = make_uint2(s, (uint32_t)res.status | ((uint32_t)res.err_code << 16));
+    node_range[1] = make_uint2(line, col);
+    node_range[2] = make_uint2(pos, res.err_a);
+    node_range[3] = make_uint2(res.err_b, res.err_c);
   }
 }
 
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
     const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end,
     const uint8_t* __restrict__ tok_kw, const uint32_t* __restrict__ stmt_tok_begin,
     const uint32_t* __restrict__ stmt_tok_end, const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt,
-    uint4* __restrict__ scratch, uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, int lex_only) {
+    uint2* __restrict__ scratch, uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, int lex_only) {
   __shared__ npar::ParseTables P;
   stage_parse_tables(gP, &P);
   __syncthreads();
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
   }
   uint32_t stack[PARSE_STACK];
   DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
-  uint4* range = scratch + ((size_t)tb + (size_t)NODE_SLACK * s);
+  uint2* range = scratch + ((size_t)tb + (size_t)NODE_SLACK * s);
   DNodes nd{range, tc + NODE_SLACK};
   DText tx{text + o, len};
   npar::ParseResult res;
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse_retry(
     const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw,
     const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt, const uint2* __restrict__ retry_list,
     uint32_t nretry, const uint64_t* __restrict__ node_off, const uint64_t* __restrict__ stack_off,
-    uint4* __restrict__ retry_nodes, uint32_t* __restrict__ retry_stack) {
+    uint2* __restrict__ retry_nodes, uint32_t* __restrict__ retry_stack) {
   __shared__ npar::ParseTables P;
   stage_parse_tables(gP, &P);
   __syncthreads();
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse_retry(
   const NutdbStmt old = stmt[s];
   const uint32_t tb = old.tok_begin, tc = old.tok_count;
   DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
-  uint4* range = retry_nodes + node_off[i];
+  uint2* range = retry_nodes + node_off[i];
   DNodes nd{range, (uint32_t)(node_off[i + 1] - node_off[i])};
   DText tx{text + o, len};
   npar::ParseResult res;
@@ -536,19 +537,47 @@ __global__ void __launch_bounds__(FIN_THREADS) k_stmt_sums(const NutdbStmt* __re
   if (threadIdx.x == 0) tileS[blockIdx.x] = total;
 }
 
+struct ExpandOut {
+  uint32_t* o;  // NutdbNode records of this statement as words: [w0, parent, a, b] per node
+  __device__ __forceinline__ void body(uint32_t j, uint8_t kind, uint8_t sub, uint16_t aux, uint32_t a, uint32_t b) {
+    o[4 * (size_t)j] = (uint32_t)kind | ((uint32_t)sub << 8) | ((uint32_t)aux << 16);
+    *reinterpret_cast<uint2*>(o + 4 * (size_t)j + 2) = make_uint2(a, b);
+  }
+  __device__ __forceinline__ void parent(uint32_t j, uint32_t p) { o[4 * (size_t)j + 1] = p; }
+};
+struct CompactSrc {
+  const uint2* p;
+  __device__ __forceinline__ npar::CNode operator()(uint32_t i) const {
+    uint2 v = p[i];
+    npar::CNode x;
+    x.kind = (uint8_t)(v.x & 0xFF);
+    x.sub = (uint8_t)((v.x >> 8) & 0xFF);
+    x.aux = (uint16_t)(v.x >> 16);
+    x.x = v.y;
+    return x;
+  }
+};
+
+// Dense outputs in statement order.  A block owns FIN_THREADS consecutive statements, i.e. one
+// contiguous range of output nodes; one thread per output node expands the compact node (byte
+// span from the token arrays, child count, parent links of its children).
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict__ stmt, uint32_t nstmt,
                                                           const uint2* __restrict__ tilePref,
-                                                          const uint4* __restrict__ scratch,
-                                                          const uint4* __restrict__ retry_nodes,
-                                                          uint4* __restrict__ node_out, uint4* __restrict__ err_out) {
+                                                          const uint2* __restrict__ scratch,
+                                                          const uint2* __restrict__ retry_nodes,
+                                                          const uint32_t* __restrict__ tok_start,
+                                                          const uint32_t* __restrict__ tok_end,
+                                                          uint32_t* __restrict__ node_out, uint4* __restrict__ err_out) {
   __shared__ uint2 ws[32];
   __shared__ uint32_t lbegin[FIN_THREADS + 1];
-  __shared__ const uint4* lsrc[FIN_THREADS];
+  __shared__ uint32_t ltok[FIN_THREADS];
+  __shared__ const uint2* lsrc[FIN_THREADS];
   const uint32_t s = blockIdx.x * FIN_THREADS + threadIdx.x;
   uint2 v = make_uint2(0u, 0u);
-  const uint4* src = nullptr;
+  const uint2* src = nullptr;
   NutdbStmt S;
   S.status = NUTDB_ST_OK;
+  S.tok_begin = 0;
   if (s < nstmt) {
     S = stmt[s];
     v = make_uint2(S.status == NUTDB_ST_OK ? S.node_count : 0u, S.status != NUTDB_ST_OK ? 1u : 0u);
@@ -560,6 +589,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
   const uint2 base = tilePref[blockIdx.x];
   lbegin[threadIdx.x] = excl.x;
   lsrc[threadIdx.x] = src;
+  ltok[threadIdx.x] = S.tok_begin;
   if (threadIdx.x == 0) lbegin[FIN_THREADS] = total.x;
   if (s < nstmt) {
     stmt[s].node_begin = base.x + excl.x;
@@ -569,8 +599,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
         e0 = make_uint4(s, (uint32_t)NUTDB_ST_SYNTAX_ERROR | ((uint32_t)NUTDB_SE_EmptyQuery << 16), 0u, 0u);
         e1 = make_uint4(0u, 0u, 0u, 0u);
       } else {
-        e0 = src[0];
-        e1 = src[1];
+        const uint2 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3];
+        e0 = make_uint4(r0.x, r0.y, r1.x, r1.y);
+        e1 = make_uint4(r2.x, r2.y, r3.x, r3.y);
       }
       err_out[2 * (size_t)(base.y + excl.y)] = e0;
       err_out[2 * (size_t)(base.y + excl.y) + 1] = e1;
@@ -585,7 +616,14 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
       if (lbegin[mid] <= j) lo = mid;
       else hi = mid;
     }
-    node_out[(size_t)base.x + j] = lsrc[lo][j - lbegin[lo]];
+    // `lo` owns node j (statements without nodes share their offset with the next one and are skipped
+    // by "last k"); its nodes are [lbegin[lo], lbegin[lo+1]) of this block's range
+    const uint32_t first = lbegin[lo];
+    const uint32_t count = lbegin[lo + 1] - first;
+    CompactSrc cn{lsrc[lo]};
+    DTok tk{nullptr, tok_start + ltok[lo], tok_end + ltok[lo], nullptr, 0xFFFFFFFFu};
+    ExpandOut out{node_out + 4 * ((size_t)base.x + first)};
+    npar::expand_node(cn, j - first, count, tk, out);
   }
 }
 
@@ -928,14 +966,14 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   uint64_t n_node = 0, n_err = 0;
   if (nstmt > 0) {
     const size_t scratch_nodes = (size_t)ntok + (size_t)NODE_SLACK * nstmt + 4;
-    if (!lex_only) ENSURE_DEV(scratch, 16 * scratch_nodes);
+    if (!lex_only) ENSURE_DEV(scratch, 8 * scratch_nodes);
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
     const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
     LAUNCH("k_parse", k_parse<<<pblocks, PARSE_THREADS, 0, st>>>(
         dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
         (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p,
         (const uint32_t*)ctx->stmtTokBegin.p, (const uint32_t*)ctx->stmtTokEnd.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
-        (uint4*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, lex_only ? 1 : 0));
+        (uint2*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, lex_only ? 1 : 0));
     CK(cudaMemcpyAsync(hS, dS, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t nretry = hS[1];
@@ -958,7 +996,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
       }
       ENSURE_DEV(retryNodeOff, 8 * ((size_t)nretry + 1));
       ENSURE_DEV(retryStackOff, 8 * ((size_t)nretry + 1));
-      ENSURE_DEV(retryNodes, 16 * (size_t)noff[nretry] + 64);
+      ENSURE_DEV(retryNodes, 8 * (size_t)noff[nretry] + 64);
       ENSURE_DEV(retryStack, 4 * (size_t)soff[nretry] + 64);
       CK(cudaMemcpyAsync(ctx->retryNodeOff.p, noff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->retryStackOff.p, soff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
@@ -967,7 +1005,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
           dText, (const uint32_t*)ctx->off32.p, (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
           (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
           (const uint2*)ctx->retryList.p, nretry, (const uint64_t*)ctx->retryNodeOff.p,
-          (const uint64_t*)ctx->retryStackOff.p, (uint4*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p));
+          (const uint64_t*)ctx->retryStackOff.p, (uint2*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p));
     }
     const uint32_t stiles = (nstmt + FIN_THREADS - 1) / FIN_THREADS;
     ENSURE_DEV(tileS, 8 * (size_t)stiles);
@@ -982,8 +1020,9 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(nodes, 16 * (n_node + 1));
     ENSURE_DEV(errs, 32 * (n_err + 1));
     LAUNCH("k_finalize", k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
-                                               (const uint4*)ctx->scratch.p, (const uint4*)ctx->retryNodes.p,
-                                               (uint4*)ctx->nodes.p, (uint4*)ctx->errs.p));
+                                               (const uint2*)ctx->scratch.p, (const uint2*)ctx->retryNodes.p,
+                                               (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
+                                               (uint32_t*)ctx->nodes.p, (uint4*)ctx->errs.p));
   }
   CK(cudaEventRecord(ctx->ev[3], st));
 

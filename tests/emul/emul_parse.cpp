@@ -33,14 +33,29 @@ struct HTokAdapter {
   uint32_t end(uint32_t i) const { return h.end(i); }
 };
 struct HNodes {
-  std::vector<NutdbNode>& v;
+  std::vector<npar::CNode>& v;
   uint32_t cap;
-  NutdbNode get(uint32_t i) const { return v[i]; }
-  void set(uint32_t i, const NutdbNode& x) {
+  npar::CNode get(uint32_t i) const { return v[i]; }
+  void set(uint32_t i, const npar::CNode& x) {
     if (i >= v.size()) v.resize(i + 1);
     v[i] = x;
   }
   uint32_t capacity() const { return cap; }
+};
+struct HCompact {
+  const std::vector<npar::CNode>& v;
+  npar::CNode operator()(uint32_t i) const { return v[i]; }
+};
+struct HOut {
+  NutdbNode* o;
+  void body(uint32_t j, uint8_t kind, uint8_t sub, uint16_t aux, uint32_t a, uint32_t b) {
+    o[j].kind = kind;
+    o[j].sub = sub;
+    o[j].aux = aux;
+    o[j].a = a;
+    o[j].b = b;
+  }
+  void parent(uint32_t j, uint32_t p) { o[j].parent = p; }
 };
 struct HText {
   const uint8_t* p;
@@ -68,7 +83,7 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
   uint64_t nn = 0, ne = 0;
   uint32_t seg = 0;
   std::vector<uint32_t> stack(stack_cap);
-  std::vector<NutdbNode> tmp;
+  std::vector<npar::CNode> tmp;
   for (uint64_t s = 0; s < nstmt; s++) {
     uint32_t len = (uint32_t)(offs[s + 1] - offs[s]);
     NutdbStmt& S = stmt[s];
@@ -102,7 +117,13 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
       if (nn + res.node_count > node_cap) return -1;
       S.node_begin = (uint32_t)nn;
       S.node_count = res.node_count;
-      std::memcpy(nodes + nn, tmp.data(), sizeof(NutdbNode) * res.node_count);
+      {  // same per-node expansion the device runs with one thread per node
+        uint32_t b = S.tok_begin;
+        HTokAdapter tk{HTok{tok_type + b, tok_start + b, tok_end + b, tok_kw + b, S.tok_count}};
+        HCompact cn{tmp};
+        HOut out{nodes + nn};
+        for (uint32_t j = 0; j < res.node_count; j++) npar::expand_node(cn, j, res.node_count, tk, out);
+      }
       nn += res.node_count;
     } else {
       S.node_begin = (uint32_t)nn;
