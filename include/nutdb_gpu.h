@@ -320,7 +320,7 @@ typedef struct {
   const uint8_t *tok_type;  /* [n_tok]  NUTDB_TT_* (no Whitespace / Comment) */
   const uint32_t *tok_start;/* [n_tok]  payload span start, statement-relative */
   const uint32_t *tok_end;  /* [n_tok] */
-  const uint8_t *tok_kw;    /* [n_tok]  keyword id or 0 */
+  const uint8_t *tok_kw;    /* [n_tok]  KeywordOrIdentifier: keyword id or 0; Integer/HexLiteral: digit count (max 255); else 0 */
   const NutdbNode *node;    /* [n_node] */
   const NutdbError *err;    /* [n_err]  sorted by .stmt */
   void *impl;               /* opaque */
@@ -374,6 +374,9 @@ int nutdb_gpu_last_launches(const NutdbCtx *ctx);
  * last call and, for 0 <= i < that number, the kernel's name and duration in milliseconds. */
 void nutdb_gpu_set_profiling(NutdbCtx *ctx, int on);
 int nutdb_gpu_kernel_timing(const NutdbCtx *ctx, int i, const char **name, float *ms);
+/* Statements of the last batch that the straight-line parser declined and the exact automaton
+ * parsed (everything malformed, plus constructs outside the common shapes). */
+uint64_t nutdb_gpu_last_slow_statements(const NutdbCtx *ctx);
 /* The cudaStream_t every kernel and copy of this context is issued on (for callers that want to
  * order their own work or record their own events against it). */
 void *nutdb_gpu_ctx_stream(const NutdbCtx *ctx);

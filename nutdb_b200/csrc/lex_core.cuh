@@ -283,6 +283,10 @@ struct Walker {
 
   NUTDB_HD void emit(uint8_t type, uint32_t start_abs, uint32_t end_abs, uint8_t kw = 0) {
     if (!EmitAll && (type == NUTDB_TT_Whitespace || type == NUTDB_TT_Comment)) return;
+    // side byte of integer / hex literals: number of digits (saturated), so the parser can accept the
+    // common "too short to overflow" case (literal.rs:18-31) without touching the text
+    if (type == NUTDB_TT_IntegerLiteral || type == NUTDB_TT_HexLiteral)
+      kw = (uint8_t)((end_abs - start_abs) > 255u ? 255u : (end_abs - start_abs));
     if (!counting) sink.token(c.count, type, start_abs - c.stmt_start, end_abs - c.stmt_start, kw);
     c.count++;
   }

@@ -27,7 +27,7 @@
 #include <vector>
 
 #include "lex_tables.hpp"
-#include "parse_core.cuh"
+#include "parse_fast.cuh"
 
 using namespace nlex;
 
@@ -448,15 +448,15 @@ __device__ __forceinline__ void store_result(const npar::ParseResult& res, uint3
   }
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS) k_parse(
+// Pass 1, one thread per statement: the straight-line parser (parse_fast.cuh).  Statements it
+// declines go to the slow list.  Small code, no interpreter state: this is where a query log's
+// bulk is parsed.
+__global__ void __launch_bounds__(PARSE_THREADS) k_parse_fast(
     const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, uint32_t nstmt, uint32_t ntok,
     const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end,
     const uint8_t* __restrict__ tok_kw, const uint32_t* __restrict__ stmt_tok_begin,
-    const uint32_t* __restrict__ stmt_tok_end, const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt,
-    uint2* __restrict__ scratch, uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, int lex_only) {
-  __shared__ npar::ParseTables P;
-  stage_parse_tables(gP, &P);
-  __syncthreads();
+    const uint32_t* __restrict__ stmt_tok_end, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
+    uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count, int lex_only) {
   const uint32_t s = blockIdx.x * PARSE_THREADS + threadIdx.x;
   if (s >= nstmt) return;
   const uint32_t o = off32[s], len = off32[s + 1] - o;
@@ -484,6 +484,43 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
     stmt[s] = S;
     return;
   }
+  DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
+  uint2* range = scratch + ((size_t)tb + (size_t)NODE_SLACK * s);
+  DNodes nd{range, tc + NODE_SLACK};
+  DText tx{text + o, len};
+  npar::ParseResult res;
+  npar::FastParser<DTok, DNodes, DText> f(tk, nd, tx);
+  if (f.try_parse(res)) {
+    store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
+  } else {
+    NutdbStmt S;  // token range for the slow pass
+    S.status = NUTDB_ST_LIMIT;
+    S.tok_begin = tb;
+    S.tok_count = tc;
+    S.node_begin = RETRY_NONE;
+    S.node_count = 0;
+    S.tok_used = 0;
+    stmt[s] = S;
+    slow_list[atomicAdd(slow_count, 1u)] = s;
+  }
+}
+
+// Pass 2, one thread per statement of the slow list: the exact bytecode automaton (parse_core.cuh)
+// for the whole grammar, every error and constant folding.
+__global__ void __launch_bounds__(PARSE_THREADS) k_parse(
+    const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint32_t* __restrict__ slow_list,
+    uint32_t nslow, const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start,
+    const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw,
+    const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
+    uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count) {
+  __shared__ npar::ParseTables P;
+  stage_parse_tables(gP, &P);
+  __syncthreads();
+  const uint32_t i = blockIdx.x * PARSE_THREADS + threadIdx.x;
+  if (i >= nslow) return;
+  const uint32_t s = slow_list[i];
+  const uint32_t o = off32[s], len = off32[s + 1] - o;
+  const uint32_t tb = stmt[s].tok_begin, tc = stmt[s].tok_count;
   uint32_t stack[PARSE_STACK];
   DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
   uint2* range = scratch + ((size_t)tb + (size_t)NODE_SLACK * s);
@@ -653,11 +690,12 @@ struct NutdbCtx {
   // device buffers (grow only)
   DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small;
+      tileS, tilePrefS, nodes, errs, small, slowList;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
   float ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
+  uint32_t n_slow = 0;  // statements of the last batch that needed the exact automaton
   // optional per-kernel timing (nutdb_gpu_set_profiling): events around every launch
   bool profiling = false;
   struct KRec {
@@ -759,7 +797,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small};
+                 &c->small, &c->slowList};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
   HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
@@ -969,13 +1007,26 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     if (!lex_only) ENSURE_DEV(scratch, 8 * scratch_nodes);
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
     const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
-    LAUNCH("k_parse", k_parse<<<pblocks, PARSE_THREADS, 0, st>>>(
-        dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
-        (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p,
-        (const uint32_t*)ctx->stmtTokBegin.p, (const uint32_t*)ctx->stmtTokEnd.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
-        (uint2*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, lex_only ? 1 : 0));
-    CK(cudaMemcpyAsync(hS, dS, 8, cudaMemcpyDeviceToHost, st));
+    ENSURE_DEV(slowList, 4 * ((size_t)nstmt + 1));
+    LAUNCH("k_parse_fast", k_parse_fast<<<pblocks, PARSE_THREADS, 0, st>>>(
+                               dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
+                               (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
+                               (const uint8_t*)ctx->tokKw.p, (const uint32_t*)ctx->stmtTokBegin.p,
+                               (const uint32_t*)ctx->stmtTokEnd.p, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
+                               (uint32_t*)ctx->slowList.p, dS + 2, lex_only ? 1 : 0));
+    CK(cudaMemcpyAsync(hS, dS, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const uint32_t nslow = hS[2];
+    ctx->n_slow = nslow;
+    if (nslow > 0) {
+      LAUNCH("k_parse", k_parse<<<(nslow + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
+                            dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, nslow,
+                            (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
+                            (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar,
+                            (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1));
+      CK(cudaMemcpyAsync(hS, dS, 16, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
     const uint32_t nretry = hS[1];
     if (nretry > 0) {
       // deep statements: per-statement stack and node ranges sized from their token counts
@@ -1124,6 +1175,7 @@ int nutdb_gpu_kernel_timing(const NutdbCtx* ctx, int i, const char** name, float
   }
   return (int)ctx->kernel_ms.size();
 }
+uint64_t nutdb_gpu_last_slow_statements(const NutdbCtx* ctx) { return ctx ? ctx->n_slow : 0; }
 void* nutdb_gpu_ctx_stream(const NutdbCtx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 }  // extern "C"

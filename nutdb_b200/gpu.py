@@ -69,6 +69,8 @@ def lib():
     L.nutdb_gpu_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.nutdb_gpu_kernel_timing.restype = C.c_int
     L.nutdb_gpu_kernel_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+    L.nutdb_gpu_last_slow_statements.restype = C.c_uint64
+    L.nutdb_gpu_last_slow_statements.argtypes = [C.c_void_p]
     L.nutdb_gpu_ctx_stream.restype = C.c_void_p
     L.nutdb_gpu_ctx_stream.argtypes = [C.c_void_p]
     for f in ("nutdb_fmt_debug", "nutdb_fmt_error"):
@@ -150,6 +152,9 @@ class Context:
 
     def launches(self):
         return lib().nutdb_gpu_last_launches(self._h)
+
+    def slow_statements(self):
+        return lib().nutdb_gpu_last_slow_statements(self._h)
 
     def set_profiling(self, on):
         lib().nutdb_gpu_set_profiling(self._h, 1 if on else 0)

@@ -5,7 +5,7 @@
 #include <vector>
 
 #include "../../nutdb_b200/csrc/lex_tables.hpp"
-#include "../../nutdb_b200/csrc/parse_core.cuh"
+#include "../../nutdb_b200/csrc/parse_fast.cuh"
 
 using namespace nlex;
 
@@ -64,7 +64,14 @@ struct HText {
 };
 }  // namespace
 
+static int g_use_fast = 1;
+static uint64_t g_fast_hits = 0;
+
 extern "C" {
+
+void emul_set_fast(int on) { g_use_fast = on; }
+uint64_t emul_fast_hits(void) { return g_fast_hits; }
+void emul_reset_fast_hits(void) { g_fast_hits = 0; }
 
 // Parses every statement.  Outputs: stmt[nstmt] (NutdbStmt), nodes (compact, caller cap), errors.
 // Returns 0, or -1 on capacity overflow.
@@ -106,8 +113,18 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
       seg++;
       HTokAdapter tk{HTok{tok_type + b, tok_start + b, tok_end + b, tok_kw + b, e - b}};
       HNodes nd{tmp, 2 * (e - b) + 8};
-      npar::Machine<HTokAdapter, HNodes, HText> m(npar::PARSE_TABLES, tk, nd, tx, stack.data(), stack_cap, res);
-      m.run(NUTDB_PROGRAM_ENTRY);
+      // same order as the device: the straight-line parser first, the exact automaton if it declines
+      bool fast = false;
+      if (g_use_fast) {
+        npar::FastParser<HTokAdapter, HNodes, HText> f(tk, nd, tx);
+        fast = f.try_parse(res);
+      }
+      if (fast) {
+        g_fast_hits++;
+      } else {
+        npar::Machine<HTokAdapter, HNodes, HText> m(npar::PARSE_TABLES, tk, nd, tx, stack.data(), stack_cap, res);
+        m.run(NUTDB_PROGRAM_ENTRY);
+      }
       S.status = res.status;
       S.tok_begin = b;
       S.tok_count = e - b;

@@ -77,8 +77,21 @@ def parse_lib():
                                        C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
                                        C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_uint32, C.POINTER(C.c_uint64)]
+        L.emul_fast_hits.restype = C.c_uint64
         _libs["parse"] = L
     return _libs["parse"]
+
+
+def set_fast(on):
+    parse_lib().emul_set_fast(1 if on else 0)
+
+
+def fast_hits(reset=True):
+    L = parse_lib()
+    h = L.emul_fast_hits()
+    if reset:
+        L.emul_reset_fast_hits()
+    return h
 
 
 def parse_batch(text, offs, chunk=32, stack_cap=4096):

@@ -73,3 +73,20 @@ EXTRA_SEEDS = [
     b"select a + 1 not exists (select 1), b not exists (1, 2) and c, (a, b) not exists ()",
     b"SELECT 340282366920938463463374607431768211455, 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF, 1e5",
 ]
+
+
+# statements inside (and just outside) the subset the straight-line parser (parse_fast.cuh) accepts
+SIMPLE_SEEDS = [
+    b"SELECT a, b.c, t.*, f(x, y + 1), g(), (a + b) * c, (1, 2), x IN (1, 2, 3), -5, -1.5, +7, 'it''s', \"d\\\"q\", `q`.`r`, "
+    b"0x1F AS h FROM t AS u WHERE a = 1 AND (b < 2 OR c LIKE 'x%') XOR d >= 3 GROUP BY a, b HAVING count(a) > 1 "
+    b"ORDER BY a DESC, b LIMIT 5, 10 WITH TIES;",
+    b"SELECT a FROM `tbl` WHERE x ILIKE 'y' ORDER BY f(a) DESC LIMIT 3 OFFSET 0x10",
+    b"INSERT INTO t VALUES (1, 'a', -2.5, f(3)), (2, 'b', 0.5, g(4, 5))",
+    b"INSERT INTO `t` (`a`, b) VALUES ((1 + 2) * 3, (4, 5))",
+    b"CREATE TABLE IF NOT EXISTS t (a Int8 DEFAULT 1 + 2 COMMENT 'x', b Array(Nullable(String(10))), c Decimal32(3), "
+    b"d Chars(4), e String, `f` Dictionary(UInt64)) PRIMARY KEY a, b ORDER BY f(a) PARTITION BY a % 4 COMMENT 'tbl'",
+    b"SELECT 1 = 1, a = 1, true AND a, a OR false, 1 < 2 = 3 != 4, a | b ^ c & d << 2 >> 1 + 3 * 4 / 5 % 6 - 7",
+    b"SELECT a b", b"SELECT a, FROM t", b"SELECT f(a, FROM t", b"SELECT (a, b FROM t", b"SELECT a FROM t WHERE",
+    b"SELECT a FROM t LIMIT 99999999999999999999", b"SELECT a FROM t ORDER BY a ASC",
+    b"select date, type, value, level from table where date = 'x'", b"select f (a) , g( b )from t",
+]

@@ -48,6 +48,42 @@ def test_mutation_fuzz(seed, chunk):
     check(stmts, chunk)
 
 
+def simple_seeds():
+    text, offs = W.generate(2, 64 << 10, seed=99)
+    return [bytes(text[int(offs[i]):int(offs[i + 1])]) for i in range(len(offs) - 1)][:300] + fuzz.SIMPLE_SEEDS
+
+
+@pytest.mark.parametrize("seed", [100, 101])
+def test_mutation_fuzz_around_the_fast_path(seed):
+    # mutated short statements: many stay inside the straight-line parser's subset, the rest must be
+    # declined and parsed by the automaton -- either way the result is the oracle's
+    E.fast_hits()
+    stmts = fuzz.fuzz_statements(simple_seeds(), 5000, seed=seed, max_mut=3)
+    check(stmts)
+    assert E.fast_hits() > 500
+
+
+def test_fast_path_and_automaton_agree():
+    stmts = simple_seeds()
+    text, offs = P.make_batch(stmts)
+    E.fast_hits()
+    a = E.parse_batch(text, offs)
+    assert E.fast_hits() > 300
+    E.set_fast(False)
+    try:
+        b = E.parse_batch(text, offs)
+    finally:
+        E.set_fast(True)
+    assert np.array_equal(a.node, b.node) and np.array_equal(a.stmt, b.stmt) and np.array_equal(a.err, b.err)
+
+
+def test_config2_is_entirely_fast_path():
+    text, offs = W.generate(2, 128 << 10)
+    E.fast_hits()
+    E.parse_batch(text, offs)
+    assert E.fast_hits() == len(offs) - 1
+
+
 def test_extra_seeds_unmutated():
     check(fuzz.EXTRA_SEEDS)
 

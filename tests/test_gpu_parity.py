@@ -73,6 +73,18 @@ def test_mutation_fuzz(ctx, seed):
     check(ctx, stmts)
 
 
+def test_fast_path_fuzz(ctx):
+    text, offs = W.generate(2, 64 << 10, seed=99)
+    seeds = [bytes(text[int(offs[i]):int(offs[i + 1])]) for i in range(len(offs) - 1)][:300] + fuzz.SIMPLE_SEEDS
+    for seed in (100, 101, 102):
+        stmts = fuzz.fuzz_statements(seeds, 8000, seed=seed, max_mut=3)
+        check(ctx, stmts)
+        assert 0 < ctx.slow_statements() < len(stmts)
+    text, offs = W.generate(2, 1 << 20)
+    ctx.parse_batch(text, offs)
+    assert ctx.slow_statements() == 0     # config 2 is parsed entirely by the straight-line parser
+
+
 def test_full_token_stream_incl_whitespace_and_comments(ctx):
     from nutdb_b200 import gpu
     stmts = [s for s in CORPUS + [x.encode() for x in APP_D] + fuzz.fuzz_statements(CORPUS, 400, seed=9) if len(s)]
