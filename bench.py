@@ -224,6 +224,7 @@ def main():
     n_tok, n_node, n_err = int(b.n_tok), int(b.n_node), int(b.n_err)
     launches_per_step = ctx.launches()
     n_slow = int(ctx.slow_statements())
+    n_punt = int(ctx.exact_lexed_statements())
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -305,6 +306,7 @@ def main():
         b_alg = n_in + 9 * T + 16 * M + 16 * n_stmt
         # algorithmic bytes of each kernel (DESIGN.md "Roofline accounting")
         alg = {"k_lex_A": n_in, "k_lex_B": n_in, "k_lex_C": n_in, "k_lex_D": n_in + 9 * T,
+               "k_lex2_fn": n_in, "k_lex2_count": n_in, "k_lex2_emit": n_in + 9 * T,
                "k_parse_fast": 9 * T + 16 * M + 16 * n_stmt, "k_parse": 9 * T + 16 * M + 16 * n_stmt,
                "k_finalize": 16 * M + 16 * n_stmt}
         dom = max((k for k in kernel_ms if k in alg), key=lambda k: kernel_ms[k])
@@ -324,7 +326,7 @@ def main():
             "statements_per_s": tot_stmts / (dev_ms_max * 1e-3),
             "config": {"workload": WORKLOADS[args.config], "bytes_per_gpu": n_in, "statements_per_gpu": n_stmt,
                        "tokens_per_gpu": n_tok, "nodes_per_gpu": n_node, "error_statements_per_gpu": n_err,
-                       "automaton_statements_per_gpu": n_slow,
+                       "automaton_statements_per_gpu": n_slow, "exact_lexed_statements_per_gpu": n_punt,
                        "sharding": "statement ranges, one shard per GPU, outputs stay sharded",
                        "l2": "input (1 GiB class) and every intermediate array are larger than the 126 MB L2; no flush needed"},
             "gpu_launches": launches_per_step * args.steps,

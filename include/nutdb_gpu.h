@@ -204,7 +204,9 @@ enum {
   NUTDB_ST_OK = 0,
   NUTDB_ST_LEX_ERROR = 1,    /* ParseError::LexError  (src/parser/error.rs:10) */
   NUTDB_ST_SYNTAX_ERROR = 2, /* ParseError::SyntaxError (src/parser/error.rs:12) */
-  NUTDB_ST_LIMIT = 3         /* nesting deeper than the device parser's stack (no reference equivalent; the reference would overflow its call stack) */
+  NUTDB_ST_LIMIT = 3,        /* nesting deeper than the device parser's stack (no reference equivalent; the reference would overflow its call stack) */
+  NUTDB_ST_REFERENCE_PANIC = 4 /* the reference panics instead of returning: an escaped string literal that ends in a lone
+                                  backslash after `\u` swallowed its partner reaches unreachable!() (literal.rs:63) */
 };
 
 /* SyntaxError variants (src/parser/error.rs:17-56), in declaration order, 1-based. */
@@ -377,6 +379,9 @@ int nutdb_gpu_kernel_timing(const NutdbCtx *ctx, int i, const char **name, float
 /* Statements of the last batch that the straight-line parser declined and the exact automaton
  * parsed (everything malformed, plus constructs outside the common shapes). */
 uint64_t nutdb_gpu_last_slow_statements(const NutdbCtx *ctx);
+/* Statements of the last batch that the warp-cooperative lexer handed to the exact walker (every
+ * statement with a lex error, hex literals, `$n`, `@name`, code tokens longer than 32 bytes ...). */
+uint64_t nutdb_gpu_last_exact_lexed_statements(const NutdbCtx *ctx);
 /* The cudaStream_t every kernel and copy of this context is issued on (for callers that want to
  * order their own work or record their own events against it). */
 void *nutdb_gpu_ctx_stream(const NutdbCtx *ctx);

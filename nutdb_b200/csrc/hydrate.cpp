@@ -981,6 +981,7 @@ size_t nutdb_fmt_error(const NutdbBatch* batch, uint64_t i, const uint8_t* sql, 
   std::string r;
   if (e->cls == NUTDB_ST_LEX_ERROR) r = lex_error_text(*e, sql, len);
   else if (e->cls == NUTDB_ST_SYNTAX_ERROR) r = syntax_error_text(*e, sql, len);
+  else if (e->cls == NUTDB_ST_REFERENCE_PANIC) r = "the reference panics on this input (unreachable!() at literal.rs:63)";
   else r = "nesting exceeds the device parser's limits";
   return deliver(r, buf, cap);
 }

@@ -1,0 +1,504 @@
+// lex2_core.cuh -- the warp-cooperative lexer: one LANE per byte, 32 bytes per step.
+//
+// lex_core.cuh walks every byte through a branchy state machine in one thread; that is exact
+// for every input but costs ~60 warp-instructions per byte on the GPU (divergence).  This file
+// lexes the same language with mask arithmetic:
+//
+//   stage 1 (per lane)   byte -> class bits; 12 warp ballots turn them into 32-bit masks
+//   stage 2 (uniform)    the CONTEXT automaton (strings, quoted identifiers, comments) only steps at
+//                        its sparse event bytes (quotes, newlines, "--", "/*", "*/", statement
+//                        starts), iterating over the set bits of an event mask; string / quoted
+//                        identifier tokens are produced here, at their closing quote
+//   stage 3 (per lane)   code tokens: every lane decides from the masks of its own and the previous
+//                        window whether a token ENDS at its byte, finds the token's start by bit
+//                        scanning (a token longer than the 32-byte look-back is left to the exact
+//                        path), checks the reference's end-of-token rule and classifies keywords
+//   stage 4 (per lane)   token index = running count + popcount of the emitting lanes below
+//
+// Only VALID text is handled natively.  Whatever the reference would reject with a lex error
+// (tokenizer/mod.rs error sites) and a few rare valid forms (hex literals, `$n`, `@name`, runs of
+// three or more of `< > = !`, code tokens longer than 32 bytes) mark their STATEMENT for an exact
+// re-lex by the walker of lex_core.cuh into an extra token region -- per statement, so one odd
+// statement costs one thread a few hundred bytes of sequential work, not the batch its speed.
+//
+// Every function is NUTDB_HD and lane-explicit, so tests/emul runs the identical logic on the
+// host by looping over the 32 lanes.
+#pragma once
+#include "lex_core.cuh"
+
+namespace nlex2 {
+
+using namespace nlex;
+
+enum : uint16_t {
+  K_SQ = 1, K_DQ = 2, K_BT = 4, K_NL = 8, K_BS = 16, K_DASH = 32, K_SLASH = 64, K_STAR = 128,
+  K_L = 256, K_D = 512, K_DOT = 1024, K_OP = 2048, K_P = 4096, K_WS = 8192, K_X = 16384
+};
+
+struct Lex2Tables {
+  uint16_t cls[256];
+};
+
+inline void build_lex2_tables(Lex2Tables& T) {
+  for (int i = 0; i < 256; i++) {
+    uint16_t k = K_X;
+    uint8_t c = (uint8_t)i;
+    if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_') k = K_L;
+    else if (c >= '0' && c <= '9') k = K_D;
+    else
+      switch (c) {
+        case '\'': k = K_SQ; break;
+        case '"': k = K_DQ; break;
+        case '`': k = K_BT; break;
+        case '\n': case '\r': k = K_NL | K_WS; break;
+        case ' ': case '\t': k = K_WS; break;
+        case '\\': k = K_BS | K_X; break;
+        case '-': k = K_DASH; break;
+        case '/': k = K_SLASH; break;
+        case '*': k = K_STAR | K_P; break;
+        case '.': k = K_DOT; break;
+        case '<': case '>': case '=': case '!': k = K_OP; break;
+        case '(': case ')': case '[': case ']': case '{': case '}': case ',': case ':': case '+': case '%':
+        case '&': case '|': case '^': case '~': case ';': k = K_P; break;
+        default: break;  // '@' '$' '#' '?' controls, DEL, every byte >= 0x80: invalid in code or left to the exact path
+      }
+    T.cls[i] = k;
+  }
+}
+
+// raw class masks of one 32-byte window (bit i = byte base+i); bytes at or beyond the batch end are 0
+struct Win {
+  uint32_t sq, dq, bt, nl, bs, dash, slash, star, L, D, DOT, OP;
+  uint32_t bnd;    // a statement starts at this byte; also set at position n (virtual end) if inside the window
+  uint32_t valid;  // bytes that exist (< n)
+};
+
+// what the next window starts with (needed by the last lane / last event of this window)
+struct Next {
+  uint8_t byte;   // 0 if there is none
+  uint8_t bnd;    // a statement starts there (or it is the batch end)
+  uint16_t cls;
+};
+
+struct Carry2 {
+  uint8_t s = A_C;        // context state after the previous window (transient states only if its last byte set them)
+  uint8_t esc = 0;        // previous window ended with an odd run of backslashes
+  uint8_t reopen = 0;     // previous window ended with a closing quote whose twin opens this window ('' / "")
+  uint8_t escaped = 0;    // string in progress has seen '' / "" / a backslash (mod.rs:122,137,157)
+  uint8_t prev = 0;       // last byte of the previous window
+  uint32_t str_start = 0; // absolute offset of the opening quote in progress
+  uint32_t stmt_start = 0;
+  uint32_t count = 0;     // tokens emitted so far
+};
+
+NUTDB_HD uint8_t decay(uint8_t s) { return s == A_CX ? (uint8_t)A_C : (s == A_BC0 ? (uint8_t)A_BC : s); }
+NUTDB_HD uint32_t bits_range(int lo, int hi) {  // bits lo..hi inclusive, 0 <= lo, hi <= 31
+  if (hi < lo) return 0u;
+  const uint32_t up = hi >= 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u);
+  return up & ~((1u << lo) - 1u);
+}
+NUTDB_HD int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+NUTDB_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+NUTDB_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+NUTDB_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+// lane i is preceded by an odd run of backslashes (run may continue from the previous window)
+NUTDB_HD bool lane_esc(uint32_t bs, int lane, uint8_t carry_in) {
+  if (lane == 0) return carry_in != 0;
+  const uint32_t y = bs << (32 - lane);  // bit 31 = byte lane-1
+  const int run = clz32(~y);             // consecutive backslashes right below `lane`
+  if (run >= lane) return ((lane & 1) != 0) != (carry_in != 0);
+  return (run & 1) != 0;
+}
+NUTDB_HD uint8_t esc_carry_out(uint32_t bs, uint8_t carry_in) {
+  const int run = clz32(~bs);  // backslashes ending at bit 31
+  if (run >= 32) return carry_in;  // 32 more: parity unchanged
+  return (uint8_t)(run & 1);
+}
+
+struct Events {
+  uint32_t quotes, dd, slst, stsl, all, own;
+};
+NUTDB_HD Events make_events(const Win& w, uint32_t esc, uint8_t prev) {
+  Events e;
+  e.quotes = (w.sq | w.dq) & ~esc;
+  e.dd = w.dash & ((w.dash << 1) | (prev == '-' ? 1u : 0u)) & ~w.bnd;
+  e.slst = w.star & ((w.slash << 1) | (prev == '/' ? 1u : 0u)) & ~w.bnd;
+  e.stsl = w.slash & ((w.star << 1) | (prev == '*' ? 1u : 0u)) & ~w.bnd;
+  e.own = (e.quotes | w.bt | w.nl | e.dd | e.slst | e.stsl) & w.valid;
+  e.all = e.own | w.bnd;
+  return e;
+}
+NUTDB_HD uint8_t event_type(const Win& w, const Events& ev, int e) {
+  const uint32_t b = 1u << e;
+  if (ev.quotes & b) return (w.sq & b) ? (uint8_t)EV_SQ : (uint8_t)EV_DQ;
+  if (w.bt & b) return EV_BT;
+  if (w.nl & b) return EV_NL;
+  if (ev.dd & b) return EV_DD;
+  if (ev.slst & b) return EV_SLST;
+  return EV_STSL;
+}
+
+// ---- phase 1: transition FUNCTION of the context automaton over one window (8 entry states at once) ----
+NUTDB_HD uint32_t ctx_window_fn(const LexTables& T, const Win& w, const Events& ev, uint32_t run) {
+  uint32_t todo = ev.all;
+  int last = -1;
+  while (todo) {
+    const int e = ctz32(todo);
+    todo &= todo - 1;
+    if ((w.bnd >> e) & 1u) {
+      run = 0u;  // constant function -> A_C: a statement starts here
+      last = -100;
+      if (!((ev.own >> e) & 1u)) continue;
+    }
+    if (e > last + 1 && last >= -1) run = vec8_then_row(run, T.a_row[EV_OTHER][0], T.a_row[EV_OTHER][1]);
+    const uint8_t t = event_type(w, ev, e);
+    run = vec8_then_row(run, T.a_row[t][0], T.a_row[t][1]);
+    last = e;
+  }
+  if (last < 31 && last >= -1) run = vec8_then_row(run, T.a_row[EV_OTHER][0], T.a_row[EV_OTHER][1]);
+  return run;
+}
+
+// ---- phase 2/3, stage 2: concrete walk of the context automaton over one window ----
+struct CtxOut {
+  uint32_t ct = 0;        // code bytes that may be (part of) a code token
+  uint32_t in_str = 0;    // bytes lexed inside '..' / ".."
+  uint32_t in_bt = 0;     // bytes lexed inside `..`
+  uint32_t close = 0;     // final closing quote of a string / quoted identifier: this lane emits the token
+  uint32_t bad = 0;       // the statement containing this byte needs the exact path
+  uint32_t bad_prev = 0;  // the statement ENDING right before this (statement start) byte needs the exact path
+  uint8_t cap_type = 0;   // token of `lane` if close has its bit
+  uint32_t cap_start = 0;
+};
+
+NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Next& nx, int lane, Carry2& c, CtxOut& o) {
+  uint32_t todo = ev.all, consumed = 0;
+  uint8_t s = c.s;
+  int s_pos = -1, p0 = 0, reopen_at = c.reopen ? 0 : -1;
+  uint32_t m_code = 0, m_str = 0, m_bt = 0;
+  auto assign = [&](int lo, int hi) {
+    if (hi < lo) return;
+    const uint32_t r = bits_range(lo, hi);
+    if (s <= A_CX) m_code |= r;
+    else if (s == A_SQ || s == A_DQ) {
+      m_str |= r;
+      if (w.bs & r) c.escaped = 1;
+    } else if (s == A_BT) m_bt |= r;
+  };
+  while (todo) {
+    const int e = ctz32(todo);
+    todo &= todo - 1;
+    if ((w.bnd >> e) & 1u) {
+      assign(p0, e - 1);
+      const uint8_t sa = (e == s_pos + 1) ? s : decay(s);
+      if (sa == A_SQ || sa == A_DQ || sa == A_BT || sa == A_BC0 || sa == A_BC) o.bad_prev |= 1u << e;
+      s = A_C;
+      s_pos = -100;
+      reopen_at = -1;
+      c.escaped = 0;
+      c.stmt_start = base + (uint32_t)e;
+      p0 = e;
+      if (!((ev.own >> e) & 1u)) continue;
+    }
+    assign(p0, e);
+    p0 = e + 1;
+    const uint8_t a0 = (e == s_pos + 1) ? s : decay(s);
+    const uint8_t t = event_type(w, ev, e);
+    const uint8_t a1 = a_next(a0, t);
+    if (a0 <= A_CX) {
+      if (t == EV_SQ || t == EV_DQ) {
+        if (reopen_at == e) c.escaped = 1;  // second half of '' / ""
+        else {
+          c.str_start = base + (uint32_t)e;
+          c.escaped = 0;
+        }
+      } else if (t == EV_BT) {
+        c.str_start = base + (uint32_t)e;
+      } else if ((t == EV_DD || t == EV_SLST) && a0 == A_C) {
+        consumed |= 1u << e;  // second byte of "--" / "/*": not a token
+      }
+    } else if ((a0 == A_SQ && t == EV_SQ) || (a0 == A_DQ && t == EV_DQ)) {
+      const uint32_t same = t == EV_SQ ? w.sq : w.dq;
+      bool twin;
+      if (e < 31) twin = ((same >> (e + 1)) & 1u) && !((w.bnd >> (e + 1)) & 1u);
+      else twin = !nx.bnd && nx.byte == (t == EV_SQ ? '\'' : '"');
+      if (twin) {
+        reopen_at = e + 1;
+      } else {
+        o.close |= 1u << e;
+        if (lane == e) {
+          o.cap_type = c.escaped ? (t == EV_SQ ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
+                                 : (uint8_t)NUTDB_TT_RawStringLiteral;
+          o.cap_start = c.str_start + 1;
+        }
+      }
+    } else if (a0 == A_BT && t == EV_BT) {
+      o.close |= 1u << e;
+      // `` : Incomplete (tokenizer/mod.rs:323).  Decided from the previous byte, not from str_start: the
+      // counting pass (which flags statements) does not know carried offsets at a segment start.
+      if (e > 0 ? ((w.bt >> (e - 1)) & 1u) != 0 : c.prev == '`') o.bad |= 1u << e;
+      if (lane == e) {
+        o.cap_type = NUTDB_TT_DelimitedIdentifier;
+        o.cap_start = c.str_start + 1;
+      }
+    }
+    s = a1;
+    s_pos = e;
+  }
+  assign(p0, 31);
+  if (s_pos < 31) s = decay(s);
+  c.s = s;
+  c.reopen = reopen_at == 32 ? 1 : 0;
+  o.ct = m_code & ~consumed & w.valid;
+  o.in_str = m_str & w.valid;
+  o.in_bt = m_bt & w.valid;
+}
+
+// ---- stage 3: what token (if any) ENDS at this lane's byte ----
+struct Hist {  // class masks of the previous window, restricted to code-token bytes
+  uint32_t L = 0, D = 0, DOT = 0, OP = 0, bnd = 0;
+};
+struct LaneTok {
+  uint8_t has = 0;     // a token ends here
+  uint8_t type = 0;
+  uint8_t kw = 0;
+  uint8_t eof = 0;     // the statement ends after this byte: EOF token follows
+  uint8_t bad = 0;     // statement needs the exact path
+  uint32_t start = 0;  // absolute
+  uint32_t end = 0;
+};
+
+// start of the run ending at 64-bit position pos, where cont bit q = "byte q continues byte q-1"; -1 = beyond look-back
+NUTDB_HD int run_start(uint64_t cont, int pos) {
+  const uint64_t below = pos >= 63 ? ~0ull : ((2ull << pos) - 1ull);
+  const uint64_t stop = ~cont & below;  // positions <= pos that do NOT continue
+  if (!stop) return -1;
+  const int r = 63 - clz64(stop);
+  return r == 0 ? -1 : r;  // position 0 always "stops" (nothing is known below it): the run may extend further back
+}
+
+template <class Src>
+NUTDB_HD LaneTok lane_token(const LexTables& T, Src& src, int lane, uint32_t base, uint8_t b, uint16_t k, const Win& w,
+                            const CtxOut& o, const Hist& h, const Next& nx, uint32_t esc_mask, uint8_t prev_byte) {
+  LaneTok r;
+  const uint32_t bit = 1u << lane;
+  if (!(w.valid & bit)) return r;
+  const uint32_t pos = base + (uint32_t)lane;
+  // the byte after this one
+  const bool nbnd = lane < 31 ? ((w.bnd >> (lane + 1)) & 1u) != 0 : nx.bnd != 0;
+  const uint8_t nb = lane < 31 ? (nbnd ? (uint8_t)0 : src.byte(pos + 1)) : (nbnd ? (uint8_t)0 : nx.byte);
+  r.eof = nbnd ? 1 : 0;
+  if (o.close & bit) {  // string / quoted identifier closed here (stage 2)
+    r.has = 1;
+    r.type = o.cap_type;
+    r.start = o.cap_start;
+    r.end = pos;
+    if (o.bad & bit) r.bad = 1;
+    return r;
+  }
+  if (o.in_str & bit) {  // raw CR / LF inside a string literal is an error unless escaped (mod.rs:147-170)
+    if (b == '\r') {
+      if (!(esc_mask & bit)) r.bad = 1;
+    } else if (b == '\n') {
+      const bool pesc = lane > 0 ? ((esc_mask >> (lane - 1)) & 1u) != 0 : false;
+      const uint8_t pb = lane > 0 ? src.byte(pos - 1) : prev_byte;
+      if (!(esc_mask & bit) && !(pb == '\r' && pesc)) r.bad = 1;
+    }
+    return r;
+  }
+  if (o.in_bt & bit) {
+    if (k & K_NL) r.bad = 1;
+    return r;
+  }
+  if (!(o.ct & bit)) return r;  // comment bytes, consumed second bytes of "--" and "/*"
+  const uint16_t nk = nbnd ? (uint16_t)0 : (lane < 31 ? (uint16_t)0xFFFF : nx.cls);  // class of next byte (lane 31 only)
+  const uint32_t ctL = w.L & o.ct, ctD = w.D & o.ct, ctDOT = w.DOT & o.ct, ctOP = w.OP & o.ct;
+  const uint64_t L64 = ((uint64_t)ctL << 32) | h.L, D64 = ((uint64_t)ctD << 32) | h.D;
+  const uint64_t DOT64 = ((uint64_t)ctDOT << 32) | h.DOT, OP64 = ((uint64_t)ctOP << 32) | h.OP;
+  const uint64_t bnd64 = ((uint64_t)w.bnd << 32) | h.bnd;
+  const uint64_t W64 = L64 | D64;
+  const int p = 32 + lane;
+  auto next_is = [&](uint32_t mask, uint16_t cls) -> bool {  // next byte is of that class (same statement)
+    if (nbnd) return false;
+    return lane < 31 ? ((mask >> (lane + 1)) & 1u) != 0 : (nk & cls) != 0;
+  };
+  auto ident_end_ok = [&]() { return nbnd || (T.prop[nb] & PR_IDENT_END); };
+  auto num_end_ok = [&]() { return nbnd || (T.prop[nb] & PR_NUM_END); };
+  if (k & (K_L | K_D)) {
+    // raw class of the next byte is enough: inside code a word byte cannot change the context
+    if (next_is(w.L | w.D, K_L | K_D)) return r;  // the run continues
+    const uint64_t contW = W64 & (W64 << 1) & ~bnd64;
+    const int st = run_start(contW, p);
+    if (st < 0) { r.bad = 1; return r; }
+    const uint64_t span = ((p >= 63 ? ~0ull : ((2ull << p) - 1ull))) & ~((1ull << st) - 1ull);
+    const uint32_t abs_st = base + (uint32_t)st - 32u;
+    if (!((D64 >> st) & 1ull)) {  // identifier / keyword (tokenizer/mod.rs:262-282)
+      if (!ident_end_ok()) { r.bad = 1; return r; }
+      r.has = 1;
+      r.type = NUTDB_TT_KeywordOrIdentifier;
+      r.start = abs_st;
+      r.end = pos + 1;
+      const uint32_t len = r.end - r.start;
+      if (len >= 2 && len <= 10) {
+        Src& sr = src;
+        const uint32_t s0 = r.start;
+        r.kw = keyword_lookup(T, len, [&sr, s0](uint32_t i) { return sr.byte(s0 + i); });
+      }
+      return r;
+    }
+    if (L64 & span) { r.bad = 1; return r; }  // 1abc, 0x1F ...: error or hex -> exact path
+    const bool left_dot = st > 0 && ((DOT64 >> (st - 1)) & 1ull) && !((bnd64 >> st) & 1ull);
+    if (next_is(w.DOT, K_DOT)) {  // digits '.' ...: the token ends later
+      if (left_dot) r.bad = 1;    // second dot of one numeric token: error
+      return r;
+    }
+    if (!num_end_ok()) { r.bad = 1; return r; }
+    r.has = 1;
+    r.end = pos + 1;
+    if (!left_dot) {  // integer literal (tokenizer/mod.rs:196-238)
+      r.type = NUTDB_TT_IntegerLiteral;
+      r.start = abs_st;
+      const uint32_t len = r.end - r.start;
+      r.kw = (uint8_t)(len > 255u ? 255u : len);
+      return r;
+    }
+    // float: [digits] '.' digits (tokenizer/mod.rs:246-258)
+    const int d = st - 1;
+    int fs = d;
+    if (d > 0 && ((W64 >> (d - 1)) & 1ull) && !((bnd64 >> d) & 1ull)) {
+      const int ls = run_start(contW, d - 1);
+      if (ls < 0) { r.bad = 1; return r; }
+      if ((D64 >> ls) & 1ull) {  // digits before the dot belong to the literal
+        fs = ls;
+        if (ls > 0 && ((DOT64 >> (ls - 1)) & 1ull) && !((bnd64 >> ls) & 1ull)) r.bad = 1;  // 1.2.3
+      }
+    } else if (d == 0) {
+      r.bad = 1;  // cannot see what precedes the dot
+    }
+    r.type = NUTDB_TT_FloatLiteral;
+    r.start = base + (uint32_t)fs - 32u;
+    return r;
+  }
+  if (k & K_DOT) {
+    if (next_is(w.D, K_D)) return r;  // '.' digits: ends at the last digit
+    bool is_float = false;
+    int fs = p;
+    if (((W64 >> (p - 1)) & 1ull) && !((bnd64 >> p) & 1ull)) {
+      const uint64_t contW = W64 & (W64 << 1) & ~bnd64;
+      const int ls = run_start(contW, p - 1);
+      if (ls < 0) { r.bad = 1; return r; }
+      if ((D64 >> ls) & 1ull) {  // digits '.'  (a word with letters in it before the dot is flagged by its own lane)
+        is_float = true;
+        fs = ls;
+        if (ls > 0 && ((DOT64 >> (ls - 1)) & 1ull) && !((bnd64 >> ls) & 1ull)) r.bad = 1;  // .5.
+      }
+    }
+    r.has = 1;
+    r.end = pos + 1;
+    if (is_float) {
+      if (!num_end_ok()) { r.bad = 1; return r; }
+      r.type = NUTDB_TT_FloatLiteral;
+      r.start = base + (uint32_t)fs - 32u;
+    } else {
+      r.type = NUTDB_TT_Dot;  // no end check (tokenizer/mod.rs:248-250)
+      r.start = pos;
+    }
+    return r;
+  }
+  if (k & K_OP) {  // < > = ! : at most two in a row are handled here (tokenizer/mod.rs:393-428)
+    const uint64_t contO = OP64 & (OP64 << 1) & ~bnd64;
+    const int st = run_start(contO, p);
+    if (st < 0 || p - st >= 2) { r.bad = 1; return r; }
+    const bool more = next_is(w.OP, K_OP);
+    auto pair_type = [](uint8_t c0, uint8_t c1) -> uint8_t {
+      if (c0 == '<') return c1 == '=' ? NUTDB_TT_LtEq : (c1 == '>' ? NUTDB_TT_NotEq : (c1 == '<' ? NUTDB_TT_BitLShift : 0));
+      if (c0 == '>') return c1 == '=' ? NUTDB_TT_GtEq : (c1 == '>' ? NUTDB_TT_BitRShift : 0);
+      if (c0 == '!') return c1 == '=' ? NUTDB_TT_NotEq : 0;
+      return 0;
+    };
+    auto single_type = [](uint8_t c0) -> uint8_t {
+      return c0 == '<' ? NUTDB_TT_Lt : (c0 == '>' ? NUTDB_TT_Gt : (c0 == '=' ? NUTDB_TT_Eq : 0xFF));
+    };
+    if (p - st == 0) {
+      if (more) {
+        if (pair_type(b, nb)) return r;  // first half of a two-character operator
+      }
+      const uint8_t ty = single_type(b);
+      if (ty == 0xFF) { r.bad = 1; return r; }  // lone '!'
+      r.has = 1;
+      r.type = ty;
+      r.start = pos;
+      r.end = pos + 1;
+      return r;
+    }
+    if (more) { r.bad = 1; return r; }  // three or more
+    const uint8_t pb = lane > 0 ? src.byte(pos - 1) : prev_byte;
+    const uint8_t pt = pair_type(pb, b);
+    r.has = 1;
+    r.end = pos + 1;
+    if (pt) {
+      r.type = pt;
+      r.start = pos - 1;
+    } else {
+      const uint8_t ty = single_type(b);
+      if (ty == 0xFF) { r.bad = 1; r.has = 0; return r; }
+      r.type = ty;
+      r.start = pos;
+    }
+    return r;
+  }
+  if (k & K_P) {
+    r.has = 1;
+    r.type = T.single_tt[b];
+    r.start = pos;
+    r.end = pos + 1;
+    return r;
+  }
+  if (k & K_DASH) {
+    if (!nbnd && nb == '-') return r;  // "--" opens a comment at the next byte
+    r.has = 1;
+    r.type = NUTDB_TT_Minus;
+    r.start = pos;
+    r.end = pos + 1;
+    return r;
+  }
+  if (k & K_SLASH) {
+    if (!nbnd && nb == '*') return r;  // "/*"
+    r.has = 1;
+    r.type = NUTDB_TT_Div;
+    r.start = pos;
+    r.end = pos + 1;
+    return r;
+  }
+  if (k & K_WS) return r;
+  if ((k & (K_SQ | K_DQ | K_BT)) && !(esc_mask & bit)) return r;  // an opening quote: stage 2 handles the literal
+  r.bad = 1;  // invalid character in code, '@', '$', an escaped quote outside a string ...
+  return r;
+}
+
+}  // namespace nlex2

@@ -379,6 +379,9 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_D(const uint8_t* __restrict
   chunk_walk<EmitAll>(S.T, src, sink, begin, begin + LEX_CHUNK, n, entA, entB, prefix, false);
 }
 
+#include "lex2_core.cuh"
+#include "lex2_kernels.cuh"
+
 // ------------------------------------------------------------------------------------------
 // parser kernels
 // ------------------------------------------------------------------------------------------
@@ -410,6 +413,15 @@ struct DNodes {
   }
   __device__ __forceinline__ uint32_t capacity() const { return cap; }
 };
+// First compact-node slot of statement s.  Token ranges of natively lexed statements ascend with s, so
+// tok_begin + NODE_SLACK*s gives disjoint ranges of tok_count + NODE_SLACK slots; statements lexed by the
+// exact walker (punt[s] = 1 + their position in the extra token region) get ranges behind all of those.
+__device__ __forceinline__ size_t node_slot(uint32_t s, uint32_t tb, uint32_t nstmt, const uint32_t* __restrict__ punt) {
+  const uint32_t p = punt[s];
+  if (p == 0u) return (size_t)tb + (size_t)NODE_SLACK * s;
+  return (size_t)NODE_SLACK * nstmt + (size_t)tb + (size_t)NODE_SLACK * (p - 1u);
+}
+
 struct DText {
   const uint8_t* p;
   uint32_t n;
@@ -456,7 +468,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse_fast(
     const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end,
     const uint8_t* __restrict__ tok_kw, const uint32_t* __restrict__ stmt_tok_begin,
     const uint32_t* __restrict__ stmt_tok_end, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
-    uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count, int lex_only) {
+    uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count, const uint32_t* __restrict__ punt,
+    int lex_only) {
   const uint32_t s = blockIdx.x * PARSE_THREADS + threadIdx.x;
   if (s >= nstmt) return;
   const uint32_t o = off32[s], len = off32[s + 1] - o;
@@ -485,7 +498,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse_fast(
     return;
   }
   DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
-  uint2* range = scratch + ((size_t)tb + (size_t)NODE_SLACK * s);
+  uint2* range = scratch + node_slot(s, tb, nstmt, punt);
   DNodes nd{range, tc + NODE_SLACK};
   DText tx{text + o, len};
   npar::ParseResult res;
@@ -512,7 +525,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
     uint32_t nslow, const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start,
     const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw,
     const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
-    uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count) {
+    uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, uint32_t nstmt,
+    const uint32_t* __restrict__ punt) {
   __shared__ npar::ParseTables P;
   stage_parse_tables(gP, &P);
   __syncthreads();
@@ -523,7 +537,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
   const uint32_t tb = stmt[s].tok_begin, tc = stmt[s].tok_count;
   uint32_t stack[PARSE_STACK];
   DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
-  uint2* range = scratch + ((size_t)tb + (size_t)NODE_SLACK * s);
+  uint2* range = scratch + node_slot(s, tb, nstmt, punt);
   DNodes nd{range, tc + NODE_SLACK};
   DText tx{text + o, len};
   npar::ParseResult res;
@@ -604,6 +618,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
                                                           const uint2* __restrict__ retry_nodes,
                                                           const uint32_t* __restrict__ tok_start,
                                                           const uint32_t* __restrict__ tok_end,
+                                                          const uint32_t* __restrict__ punt,
                                                           uint32_t* __restrict__ node_out, uint4* __restrict__ err_out) {
   __shared__ uint2 ws[32];
   __shared__ uint32_t lbegin[FIN_THREADS + 1];
@@ -618,7 +633,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
   if (s < nstmt) {
     S = stmt[s];
     v = make_uint2(S.status == NUTDB_ST_OK ? S.node_count : 0u, S.status != NUTDB_ST_OK ? 1u : 0u);
-    src = S.node_begin == RETRY_NONE ? scratch + ((size_t)S.tok_begin + (size_t)NODE_SLACK * s)
+    src = S.node_begin == RETRY_NONE ? (S.tok_count ? scratch + node_slot(s, S.tok_begin, nstmt, punt) : scratch)
                                      : retry_nodes + S.node_begin;
   }
   uint2 incl, total;
@@ -687,10 +702,12 @@ struct NutdbCtx {
   std::string err;
   LexTables* dLex = nullptr;
   npar::ParseTables* dPar = nullptr;
+  nlex2::Lex2Tables* dLex2 = nullptr;
+  uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
   DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList;
+      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
   float ms[5] = {0, 0, 0, 0, 0};
@@ -797,7 +814,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList};
+                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
   HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
@@ -834,6 +851,12 @@ NutdbCtx* nutdb_gpu_ctx_create(int device) {
        cudaMalloc(&ctx->dPar, sizeof(npar::ParseTables)) == cudaSuccess &&
        cudaMemcpy(ctx->dLex, &lt, sizeof(lt), cudaMemcpyHostToDevice) == cudaSuccess &&
        cudaMemcpy(ctx->dPar, &npar::PARSE_TABLES, sizeof(npar::ParseTables), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    nlex2::Lex2Tables l2;
+    nlex2::build_lex2_tables(l2);
+    ok = cudaMalloc(&ctx->dLex2, sizeof(l2)) == cudaSuccess &&
+         cudaMemcpy(ctx->dLex2, &l2, sizeof(l2), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
   if (ok) ok = ensure_dev(ctx, ctx->small, 256) == NUTDB_OK && ensure_host(ctx, ctx->hSmall, 256) == NUTDB_OK;
   if (!ok) {
     nutdb_gpu_ctx_destroy(ctx);
@@ -849,6 +872,7 @@ void nutdb_gpu_ctx_destroy(NutdbCtx* ctx) {
   free_all(ctx);
   if (ctx->dLex) cudaFree(ctx->dLex);
   if (ctx->dPar) cudaFree(ctx->dPar);
+  if (ctx->dLex2) cudaFree(ctx->dLex2);
   for (int i = 0; i < 6; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -931,6 +955,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   CK(cudaEventRecord(ctx->ev[1], st));
 
   // ---- lexer ----
+  ENSURE_DEV(puntFlag, 4 * ((size_t)nstmt + 1));
+  CK(cudaMemsetAsync(ctx->puntFlag.p, 0, 4 * ((size_t)nstmt + 1), st));
   CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 1), st));
   CK(cudaMemsetAsync(dS, 0, 64, st));
   {
@@ -938,7 +964,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_prep", k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p, dS));
   }
   uint32_t ntok = 0;
-  if (n > 0) {
+  ctx->n_punt = 0;
+  if (n > 0 && lex_only) {  // verify mode: the thread-per-chunk walker (exact for every input, emits every token)
     ENSURE_DEV(localA, 4 * nchunks);
     ENSURE_DEV(localB, 4 * nchunks);
     ENSURE_DEV(localC, 16 * nchunks);
@@ -990,6 +1017,73 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
                             dText, bm, n, ctx->dLex, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
                             (const uint32_t*)ctx->localB.p, (const uint8_t*)ctx->entB.p, (const uint4*)ctx->localC.p,
                             (const uint4*)ctx->tilePrefC.p, sink));
+  } else if (n > 0) {
+    // ---- warp-cooperative lexer (lex2_core.cuh) + exact walker for the statements it flags ----
+    const size_t nwarps = (size_t)ntiles * L2_WARPS;
+    ENSURE_DEV(localA, 4 * nwarps);
+    ENSURE_DEV(localC, 16 * nwarps);
+    ENSURE_DEV(tileA, 4 * (size_t)ntiles);
+    ENSURE_DEV(tileC, 16 * (size_t)ntiles);
+    ENSURE_DEV(tilePrefC, 16 * (size_t)ntiles);
+    ENSURE_DEV(entA, ntiles);
+    ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
+    const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
+    Lex2Out lo{nullptr, nullptr, nullptr, nullptr, 0, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
+               (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->puntList.p, dS + 3};
+    LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2,
+                                                                  (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p));
+    LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
+    LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
+                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
+                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr, lo));
+    LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p,
+                                                                        ntiles, (uint4*)(dS + 4)));
+    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hS[0]) {
+      ctx->err = "statement offsets must ascend";
+      return NUTDB_E_ARG;
+    }
+    const uint32_t ntok_main = hS[4], npunt = hS[3];
+    uint32_t n_extra = 0;
+    ctx->n_punt = npunt;
+    ExactSink xs{nullptr, nullptr, nullptr, nullptr, 0};
+    if (npunt > 0) {
+      ENSURE_DEV(puntCounts, 8 * (size_t)npunt);
+      ENSURE_DEV(puntOffs, 8 * (size_t)npunt);
+      LAUNCH("k_lex_exact_count", k_lex_exact<false><<<(npunt + 127) / 128, 128, 0, st>>>(
+                                      dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p,
+                                      npunt, (uint2*)ctx->puntCounts.p, nullptr, 0u, xs, nullptr, nullptr, nullptr));
+      LAUNCH("k_scan_P", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->puntCounts.p,
+                                                                           (uint2*)ctx->puntOffs.p, npunt, (uint2*)(dS + 10)));
+      CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      n_extra = hS[10];
+    }
+    if ((uint64_t)ntok_main + n_extra >= 0xFFFFFFF0ull) {
+      ctx->err = "too many tokens in one batch";
+      return NUTDB_E_ARG;
+    }
+    ntok = ntok_main + n_extra;
+    ENSURE_DEV(tokType, (size_t)ntok + 16);
+    ENSURE_DEV(tokKw, (size_t)ntok + 16);
+    ENSURE_DEV(tokStart, 4 * ((size_t)ntok + 4));
+    ENSURE_DEV(tokEnd, 4 * ((size_t)ntok + 4));
+    lo.type = (uint8_t*)ctx->tokType.p;
+    lo.start = (uint32_t*)ctx->tokStart.p;
+    lo.end = (uint32_t*)ctx->tokEnd.p;
+    lo.kw = (uint8_t*)ctx->tokKw.p;
+    lo.cap = ntok_main;
+    LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
+                              dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
+                              (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p, lo));
+    if (npunt > 0) {
+      xs = ExactSink{lo.type, lo.start, lo.end, lo.kw, ntok};
+      LAUNCH("k_lex_exact_emit", k_lex_exact<true><<<(npunt + 127) / 128, 128, 0, st>>>(
+                                     dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p, npunt,
+                                     nullptr, (const uint2*)ctx->puntOffs.p, ntok_main, xs, (uint32_t*)ctx->stmtTokBegin.p,
+                                     (uint32_t*)ctx->stmtTokEnd.p, (uint32_t*)ctx->puntFlag.p));
+    }
   } else {
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1003,7 +1097,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   // ---- parser ----
   uint64_t n_node = 0, n_err = 0;
   if (nstmt > 0) {
-    const size_t scratch_nodes = (size_t)ntok + (size_t)NODE_SLACK * nstmt + 4;
+    const size_t scratch_nodes = (size_t)ntok + (size_t)NODE_SLACK * ((size_t)nstmt + ctx->n_punt) + 4;
     if (!lex_only) ENSURE_DEV(scratch, 8 * scratch_nodes);
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
     const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
@@ -1013,7 +1107,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                (const uint8_t*)ctx->tokKw.p, (const uint32_t*)ctx->stmtTokBegin.p,
                                (const uint32_t*)ctx->stmtTokEnd.p, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
-                               (uint32_t*)ctx->slowList.p, dS + 2, lex_only ? 1 : 0));
+                               (uint32_t*)ctx->slowList.p, dS + 2, (const uint32_t*)ctx->puntFlag.p, lex_only ? 1 : 0));
     CK(cudaMemcpyAsync(hS, dS, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t nslow = hS[2];
@@ -1023,7 +1117,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
                             dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, nslow,
                             (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
                             (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar,
-                            (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1));
+                            (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, nstmt,
+                            (const uint32_t*)ctx->puntFlag.p));
       CK(cudaMemcpyAsync(hS, dS, 16, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
     }
@@ -1073,7 +1168,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_finalize", k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
                                                (const uint2*)ctx->scratch.p, (const uint2*)ctx->retryNodes.p,
                                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
-                                               (uint32_t*)ctx->nodes.p, (uint4*)ctx->errs.p));
+                                               (const uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->nodes.p,
+                                               (uint4*)ctx->errs.p));
   }
   CK(cudaEventRecord(ctx->ev[3], st));
 
@@ -1176,6 +1272,7 @@ int nutdb_gpu_kernel_timing(const NutdbCtx* ctx, int i, const char** name, float
   return (int)ctx->kernel_ms.size();
 }
 uint64_t nutdb_gpu_last_slow_statements(const NutdbCtx* ctx) { return ctx ? ctx->n_slow : 0; }
+uint64_t nutdb_gpu_last_exact_lexed_statements(const NutdbCtx* ctx) { return ctx ? ctx->n_punt : 0; }
 void* nutdb_gpu_ctx_stream(const NutdbCtx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 }  // extern "C"

@@ -71,6 +71,8 @@ def lib():
     L.nutdb_gpu_kernel_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     L.nutdb_gpu_last_slow_statements.restype = C.c_uint64
     L.nutdb_gpu_last_slow_statements.argtypes = [C.c_void_p]
+    L.nutdb_gpu_last_exact_lexed_statements.restype = C.c_uint64
+    L.nutdb_gpu_last_exact_lexed_statements.argtypes = [C.c_void_p]
     L.nutdb_gpu_ctx_stream.restype = C.c_void_p
     L.nutdb_gpu_ctx_stream.argtypes = [C.c_void_p]
     for f in ("nutdb_fmt_debug", "nutdb_fmt_error"):
@@ -155,6 +157,9 @@ class Context:
 
     def slow_statements(self):
         return lib().nutdb_gpu_last_slow_statements(self._h)
+
+    def exact_lexed_statements(self):
+        return lib().nutdb_gpu_last_exact_lexed_statements(self._h)
 
     def set_profiling(self, on):
         lib().nutdb_gpu_set_profiling(self._h, 1 if on else 0)

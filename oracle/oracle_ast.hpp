@@ -291,6 +291,8 @@ struct SyntaxError {
   uint32_t a = 0, b = 0, c = 0;
 };
 
+struct ReferencePanic {};  // the reference hits unreachable!() (literal.rs:63) -- it would panic, not return
+
 struct ParseErr {
   bool is_lex = false;
   TokenizeError lex;
@@ -349,7 +351,7 @@ inline bool unescape_string(sv raw, char32_t quote, std::string& res, std::strin
     } else if (ch == '\\') {
       char32_t nc;
       size_t nat;
-      if (!next_char(nc, nat)) abort();  // unreachable!() literal.rs:63
+      if (!next_char(nc, nat)) throw ReferencePanic{};  // unreachable!() literal.rs:63: reachable through `\\u` eating a char
       if (nc == 'n') res.push_back('\n');
       else if (nc == 'r') res.push_back('\r');
       else if (nc == 't') res.push_back('\t');

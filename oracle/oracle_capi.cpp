@@ -65,6 +65,11 @@ void parse_one(sv sql, int want, OneResult& out) {
     out.status = e.is_lex ? NUTDB_ST_LEX_ERROR : NUTDB_ST_SYNTAX_ERROR;
     fill_error_record(e, out.rec);
     if (want & 4) out.error = error_display(e);
+  } catch (const ReferencePanic&) {
+    out.status = NUTDB_ST_REFERENCE_PANIC;
+    std::memset(&out.rec, 0, sizeof(out.rec));
+    out.rec.cls = NUTDB_ST_REFERENCE_PANIC;
+    if (want & 4) out.error = "the reference panics on this input (unreachable!() at literal.rs:63)";
   }
   out.pulled = std::move(p.pulled);
 }
@@ -117,7 +122,13 @@ void ora_get_pos(const char* sql, size_t len, size_t cursor, uint32_t* line, uin
 int ora_unescape(const char* raw, size_t len, int quote, char* out, size_t cap, size_t* outlen) {
   std::string res, bad;
   Span hs;
-  bool ok = unescape_string(sv(raw, len), (char32_t)quote, res, bad, hs);
+  bool ok;
+  try {
+    ok = unescape_string(sv(raw, len), (char32_t)quote, res, bad, hs);
+  } catch (const ReferencePanic&) {
+    *outlen = 0;
+    return 2;
+  }
   const std::string& s = ok ? res : bad;
   *outlen = s.size();
   std::memcpy(out, s.data(), std::min(cap, s.size()));
@@ -261,6 +272,7 @@ double ora_bench(const char* text, const uint64_t* offs, uint64_t n, int nthread
           Statement st = p.parse_stmt();
           o++;
         } catch (const ParseErr&) {
+        } catch (const ReferencePanic&) {
         }
         k += p.pulled.size();
       }

@@ -13,6 +13,10 @@ extern "C" int64_t emul_lex(const uint8_t* text, uint32_t n, const uint64_t* off
                             uint32_t chunk, uint8_t* tok_type, uint32_t* tok_start, uint32_t* tok_end, uint8_t* tok_kw,
                             uint32_t cap, uint32_t* seg_tok_begin, uint32_t* seg_tok_end, uint32_t* n_seg_out);
 
+extern "C" int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_t nstmt, uint32_t seg_len,
+                             uint8_t* tok_type, uint32_t* tok_start, uint32_t* tok_end, uint8_t* tok_kw, uint32_t cap,
+                             uint32_t* stmt_tok_begin, uint32_t* stmt_tok_end);
+
 namespace {
 struct HTok {
   const uint8_t* ty;
@@ -65,11 +69,17 @@ struct HText {
 }  // namespace
 
 static int g_use_fast = 1;
+static int g_lexer = 2;          // 1 = thread-per-chunk walker, 2 = warp-cooperative lexer
+static uint32_t g_seg_len = 1024;
 static uint64_t g_fast_hits = 0;
 
 extern "C" {
 
 void emul_set_fast(int on) { g_use_fast = on; }
+void emul_set_lexer(int version, uint32_t seg_len) {
+  g_lexer = version;
+  g_seg_len = seg_len;
+}
 uint64_t emul_fast_hits(void) { return g_fast_hits; }
 void emul_reset_fast_hits(void) { g_fast_hits = 0; }
 
@@ -83,9 +93,13 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
   const uint8_t* base = text + offs[0];
   std::vector<uint32_t> sb(nstmt + 1), se(nstmt + 1);
   uint32_t nseg = 0;
-  int64_t nt = emul_lex(base, n, offs, nstmt, 0, chunk, tok_type, tok_start, tok_end, tok_kw, tok_cap, sb.data(),
-                        se.data(), &nseg);
-  if (nt < 0) return -1;
+  int64_t nt;
+  if (g_lexer == 2) {
+    nt = emul_lex2(base, n, offs, nstmt, g_seg_len, tok_type, tok_start, tok_end, tok_kw, tok_cap, sb.data(), se.data());
+  } else {
+    nt = emul_lex(base, n, offs, nstmt, 0, chunk, tok_type, tok_start, tok_end, tok_kw, tok_cap, sb.data(), se.data(), &nseg);
+  }
+  if (nt < 0) return (int)nt;
   *n_tok = (uint64_t)nt;
   uint64_t nn = 0, ne = 0;
   uint32_t seg = 0;
@@ -109,7 +123,8 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
       res.err_has_pos = false;
       res.err_pos = res.err_a = res.err_b = res.err_c = 0;
     } else {
-      uint32_t b = sb[seg], e = se[seg];
+      // lexer 1 indexes token ranges by non-empty statement ordinal, lexer 2 by statement
+      uint32_t b = g_lexer == 2 ? sb[s] : sb[seg], e = g_lexer == 2 ? se[s] : se[seg];
       seg++;
       HTokAdapter tk{HTok{tok_type + b, tok_start + b, tok_end + b, tok_kw + b, e - b}};
       HNodes nd{tmp, 2 * (e - b) + 8};

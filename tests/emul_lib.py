@@ -67,7 +67,8 @@ def keyword(word):
 def parse_lib():
     if "parse" not in _libs:
         so = os.path.join(_EMUL, "libemul_parse.so")
-        srcs = [os.path.join(_EMUL, "emul_parse.cpp"), os.path.join(_EMUL, "emul_lex.cpp")]
+        srcs = [os.path.join(_EMUL, "emul_parse.cpp"), os.path.join(_EMUL, "emul_lex.cpp"),
+                os.path.join(_EMUL, "emul_lex2.cpp")]
         deps = srcs + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".hpp", ".h"))]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so] + srcs)
@@ -78,8 +79,19 @@ def parse_lib():
                                        C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_uint32, C.POINTER(C.c_uint64)]
         L.emul_fast_hits.restype = C.c_uint64
+        L.emul_lex2_punts.restype = C.c_uint64
+        L.emul_set_lexer.argtypes = [C.c_int, C.c_uint32]
         _libs["parse"] = L
     return _libs["parse"]
+
+
+def set_lexer(version, seg_len=1024):
+    """1 = thread-per-chunk walker (lex_core.cuh), 2 = warp-cooperative lexer (lex2_core.cuh)."""
+    parse_lib().emul_set_lexer(version, seg_len)
+
+
+def lex2_punts():
+    return parse_lib().emul_lex2_punts()
 
 
 def set_fast(on):
@@ -116,7 +128,7 @@ def parse_batch(text, offs, chunk=32, stack_cap=4096):
     rc = L.emul_parse_batch(text.ctypes.data, offs.ctypes.data, nstmt, chunk, stack_cap, b.stmt.ctypes.data,
                             node.ctypes.data, len(node), C.byref(nn), err.ctypes.data, len(err), C.byref(ne),
                             ty.ctypes.data, st.ctypes.data, en.ctypes.data, kw.ctypes.data, tcap, C.byref(nt))
-    assert rc == 0, "emul_parse_batch overflow"
+    assert rc == 0, f"emul_parse_batch failed rc={rc} (-1 overflow, -2 scanned context states disagree)"
     b.node, b.err = node[:nn.value], err[:ne.value]
     b.tok_type, b.tok_start, b.tok_end, b.tok_kw = ty[:nt.value], st[:nt.value], en[:nt.value], kw[:nt.value]
     return b

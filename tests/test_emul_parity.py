@@ -15,6 +15,13 @@ APP_D = ["SELECT * FROM table WHERE 1 = 1", "", "  ", ";", "-- c", "SELECT 1d", 
          "SELECT $0", "SELECT 'abc", "select 1; 'oops", "\t1d", "select `你 好`, 'he''llo' -- x"]
 
 
+@pytest.fixture(autouse=True)
+def _default_lexer():
+    E.set_lexer(2, 1024)   # the warp-cooperative lexer with the device's segment size
+    yield
+    E.set_lexer(2, 1024)
+
+
 def check(stmts, chunk=32):
     text, offs = P.make_batch(stmts)
     got = E.parse_batch(text, offs, chunk=chunk)
@@ -25,8 +32,44 @@ def check(stmts, chunk=32):
 
 @pytest.mark.parametrize("chunk", [32, 7, 1])
 def test_corpus_and_known_vectors(chunk):
+    E.set_lexer(1)   # thread-per-chunk walker (the verify-mode lexer), any chunk size
     got = check(CORPUS + APP_D, chunk)
     assert (got.stmt["status"][:len(CORPUS)] == 0).all()  # tests/parser_test.rs:19-34
+
+
+@pytest.mark.parametrize("seg", [1024, 32, 96])
+def test_corpus_and_known_vectors_warp_lexer(seg):
+    E.set_lexer(2, seg)
+    got = check(CORPUS + APP_D + fuzz.EXTRA_SEEDS + fuzz.SIMPLE_SEEDS)
+    assert (got.stmt["status"][:len(CORPUS)] == 0).all()
+
+
+@pytest.mark.parametrize("lexer,seg", [(1, 0), (2, 64)])
+def test_synthetic_config_other_lexers(lexer, seg):
+    E.set_lexer(lexer, seg or 1024)
+    for config in (2, 3, 4):
+        text, offs = W.generate(config, 96 << 10, seed=3)
+        got = E.parse_batch(text, offs)
+        bad = P.compare_with_oracle(got, text, offs)
+        assert not bad, "\n".join(bad)
+
+
+def test_warp_lexer_hands_only_odd_statements_to_the_exact_walker():
+    p0 = E.lex2_punts()
+    for config in (2, 4):
+        text, offs = W.generate(config, 128 << 10)
+        E.parse_batch(text, offs)
+    assert E.lex2_punts() == p0          # valid text without hex / $n / @name: all native
+    text, offs = W.generate(3, 128 << 10)
+    E.parse_batch(text, offs)
+    assert 0 < E.lex2_punts() - p0 < 0.06 * (len(offs) - 1)   # the ~5 % malformed statements (not all are lex errors)
+
+
+def test_reference_panic_is_reported_not_reproduced():
+    # literal.rs:63 unreachable!(): `\\u` swallows the next char, leaving a lone trailing backslash
+    stmts = [b"select 'x\\u\\\\'", b"select 1"]
+    got = check(stmts)
+    assert got.stmt["status"].tolist() == [4, 0]
 
 
 @pytest.mark.parametrize("config", [2, 3, 4])
@@ -44,8 +87,21 @@ def test_synthetic_config(config):
 
 @pytest.mark.parametrize("seed,chunk", [(1, 32), (2, 32), (3, 5)])
 def test_mutation_fuzz(seed, chunk):
+    E.set_lexer(1)
     stmts = fuzz.fuzz_statements(CORPUS + fuzz.EXTRA_SEEDS, 1500, seed=seed)
     check(stmts, chunk)
+
+
+def stress_seeds():
+    text, offs = W.generate(3, 64 << 10, seed=98)
+    return [bytes(text[int(offs[i]):int(offs[i + 1])]) for i in range(len(offs) - 1)][:300]
+
+
+@pytest.mark.parametrize("seed,seg", [(300, 32), (301, 64), (302, 160), (303, 1024)])
+def test_mutation_fuzz_warp_lexer(seed, seg):
+    E.set_lexer(2, seg)
+    pool = [CORPUS + fuzz.EXTRA_SEEDS + fuzz.SIMPLE_SEEDS, simple_seeds(), stress_seeds()][seed % 3]
+    check(fuzz.fuzz_statements(pool, 4000, seed=seed, max_mut=4))
 
 
 def simple_seeds():

@@ -85,6 +85,30 @@ def test_fast_path_fuzz(ctx):
     assert ctx.slow_statements() == 0     # config 2 is parsed entirely by the straight-line parser
 
 
+def test_warp_lexer_exact_walker_split(ctx):
+    for config in (2, 4):
+        text, offs = W.generate(config, 1 << 20)
+        ctx.parse_batch(text, offs)
+        assert ctx.exact_lexed_statements() == 0
+    text, offs = W.generate(3, 1 << 20)
+    got = ctx.parse_batch(text, offs)
+    assert 0 < ctx.exact_lexed_statements() < 0.06 * (len(offs) - 1)
+    bad = P.compare_with_oracle(got, text, offs)
+    assert not bad, "\n".join(bad)
+    # hex literals, $n, @name, long tokens: valid text that only the exact walker lexes
+    stmts = ["select 0x1F, 0xg, $1 2, a" + "b" * 70 + ", 1", "set @cfg = 1", "select 1 <<= 2", "select 'x\\u\\\\'"]
+    got = check(ctx, stmts)
+    assert ctx.exact_lexed_statements() >= 3
+    assert got.stmt["status"].tolist()[-1] == 4
+
+
+@pytest.mark.parametrize("seed", [300, 301, 302])
+def test_mutation_fuzz_lexer_stress(ctx, seed):
+    text, offs = W.generate(3, 64 << 10, seed=98)
+    pool = [bytes(text[int(offs[i]):int(offs[i + 1])]) for i in range(len(offs) - 1)][:300]
+    check(ctx, fuzz.fuzz_statements(pool, 8000, seed=seed, max_mut=4))
+
+
 def test_full_token_stream_incl_whitespace_and_comments(ctx):
     from nutdb_b200 import gpu
     stmts = [s for s in CORPUS + [x.encode() for x in APP_D] + fuzz.fuzz_statements(CORPUS, 400, seed=9) if len(s)]
