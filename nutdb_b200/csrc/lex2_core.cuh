@@ -1,28 +1,30 @@
-// lex2_core.cuh -- the warp-cooperative lexer: one LANE per byte, 32 bytes per step.
+// lex2_core.cuh -- the mask-based lexer: one THREAD per 32-byte window, masks built by the warp.
 //
-// lex_core.cuh walks every byte through a branchy state machine in one thread; that is exact
-// for every input but costs ~60 warp-instructions per byte on the GPU (divergence).  This file
-// lexes the same language with mask arithmetic:
+// lex_core.cuh walks every byte through a branchy state machine; exact for every input, but ~60
+// warp-instructions per byte on the GPU.  Here a warp takes 32 consecutive windows (1 KB):
 //
-//   stage 1 (per lane)   byte -> class bits; 12 warp ballots turn them into 32-bit masks
-//   stage 2 (uniform)    the CONTEXT automaton (strings, quoted identifiers, comments) only steps at
-//                        its sparse event bytes (quotes, newlines, "--", "/*", "*/", statement
-//                        starts), iterating over the set bits of an event mask; string / quoted
-//                        identifier tokens are produced here, at their closing quote
-//   stage 3 (per lane)   code tokens: every lane decides from the masks of its own and the previous
-//                        window whether a token ENDS at its byte, finds the token's start by bit
-//                        scanning (a token longer than the 32-byte look-back is left to the exact
-//                        path), checks the reference's end-of-token rule and classifies keywords
-//   stage 4 (per lane)   token index = running count + popcount of the emitting lanes below
+//   stage 1 (warp)      for each window the 32 lanes classify one byte each and 14 ballots give the
+//                       window's class masks; lane j keeps the masks of window j (a bit transposition)
+//   stage 2 (thread)    the CONTEXT automaton (strings, quoted identifiers, comments) only steps at its
+//                       sparse event bytes (quotes, newlines, "--", "/*", "*/", statement starts): the
+//                       thread iterates over the set bits of its event mask -- first symbolically (a
+//                       transition FUNCTION over the 8 states, so entry states come from a scan), then
+//                       concretely; string / quoted-identifier tokens are found here at their closing quote
+//   stage 3 (thread)    code tokens: for every byte where a token can END the thread finds the start by
+//                       bit scanning its own and the previous window's masks (tokens longer than that
+//                       look-back go to the exact path), applies the reference's end-of-token rule and
+//                       looks up keywords
+//   carries (warp scan) entry state, open string (offset, escaped flag), statement start, token count
 //
 // Only VALID text is handled natively.  Whatever the reference would reject with a lex error
 // (tokenizer/mod.rs error sites) and a few rare valid forms (hex literals, `$n`, `@name`, runs of
-// three or more of `< > = !`, code tokens longer than 32 bytes) mark their STATEMENT for an exact
-// re-lex by the walker of lex_core.cuh into an extra token region -- per statement, so one odd
-// statement costs one thread a few hundred bytes of sequential work, not the batch its speed.
+// three or more of `< > = !`, code tokens longer than the look-back, more than 4 literals closing in
+// one window) mark their STATEMENT for an exact re-lex by the walker of lex_core.cuh into an extra
+// token region -- per statement, so one odd statement costs one thread a few hundred bytes of
+// sequential work, not the batch its speed.
 //
-// Every function is NUTDB_HD and lane-explicit, so tests/emul runs the identical logic on the
-// host by looping over the 32 lanes.
+// Everything is NUTDB_HD and window-explicit, so tests/emul runs the identical logic on the host by
+// looping over windows and passing the carries along sequentially.
 #pragma once
 #include "lex_core.cuh"
 
@@ -68,7 +70,7 @@ inline void build_lex2_tables(Lex2Tables& T) {
 
 // raw class masks of one 32-byte window (bit i = byte base+i); bytes at or beyond the batch end are 0
 struct Win {
-  uint32_t sq, dq, bt, nl, bs, dash, slash, star, L, D, DOT, OP;
+  uint32_t sq, dq, bt, nl, bs, dash, slash, star, L, D, DOT, OP, P, WS;
   uint32_t bnd;    // a statement starts at this byte; also set at position n (virtual end) if inside the window
   uint32_t valid;  // bytes that exist (< n)
 };
@@ -78,17 +80,6 @@ struct Next {
   uint8_t byte;   // 0 if there is none
   uint8_t bnd;    // a statement starts there (or it is the batch end)
   uint16_t cls;
-};
-
-struct Carry2 {
-  uint8_t s = A_C;        // context state after the previous window (transient states only if its last byte set them)
-  uint8_t esc = 0;        // previous window ended with an odd run of backslashes
-  uint8_t reopen = 0;     // previous window ended with a closing quote whose twin opens this window ('' / "")
-  uint8_t escaped = 0;    // string in progress has seen '' / "" / a backslash (mod.rs:122,137,157)
-  uint8_t prev = 0;       // last byte of the previous window
-  uint32_t str_start = 0; // absolute offset of the opening quote in progress
-  uint32_t stmt_start = 0;
-  uint32_t count = 0;     // tokens emitted so far
 };
 
 NUTDB_HD uint8_t decay(uint8_t s) { return s == A_CX ? (uint8_t)A_C : (s == A_BC0 ? (uint8_t)A_BC : s); }
@@ -184,31 +175,90 @@ NUTDB_HD uint32_t ctx_window_fn(const LexTables& T, const Win& w, const Events& 
   return run;
 }
 
-// ---- phase 2/3, stage 2: concrete walk of the context automaton over one window ----
-struct CtxOut {
+// positions preceded by an odd run of backslashes, for all 32 bytes at once
+NUTDB_HD uint32_t esc_mask32(uint32_t bs, uint8_t carry_in) {
+  uint32_t m = 0;
+  // runs are short and rare: walk the run starts
+  uint32_t starts = bs & ~(bs << 1);
+  if (carry_in && !(bs & 1u)) m |= 1u;  // the run ended with the previous window
+  while (starts) {
+    const int p = ctz32(starts);
+    starts &= starts - 1;
+    const uint32_t from = bs >> p;               // run begins at bit 0 of `from`
+    int len = ctz32(~from);                      // its length (ctz32(0) cannot happen: ~from has a zero only if from is all ones)
+    if (from == 0xFFFFFFFFu) len = 32;
+    const int total = len + ((p == 0 && carry_in) ? 1 : 0);  // continued from the previous window
+    const int end = p + len;                      // first byte after the run
+    if (end < 32 && (total & 1)) m |= 1u << end;
+  }
+  return m;
+}
+
+// ---- stage 2: concrete walk of the context automaton over one window (entry state known) ----
+#define NUTDB_L2_NCAP 4
+struct StrCarry {  // what later windows need to know about a string / quoted identifier still open
+  uint8_t has_open = 0;   // one was opened in this window (and that is the last opening)
+  uint8_t esc = 0;        // escaped-flag since that opening (or over the whole window if none)
+  uint32_t open_pos = 0;  // absolute offset of the opening quote
+};
+NUTDB_HD StrCarry str_then(const StrCarry& a, const StrCarry& b) {
+  if (b.has_open) return b;
+  StrCarry r = a;
+  r.esc = (uint8_t)(a.esc | b.esc);
+  return r;
+}
+struct WinCtx {
   uint32_t ct = 0;        // code bytes that may be (part of) a code token
   uint32_t in_str = 0;    // bytes lexed inside '..' / ".."
   uint32_t in_bt = 0;     // bytes lexed inside `..`
-  uint32_t close = 0;     // final closing quote of a string / quoted identifier: this lane emits the token
+  uint32_t close = 0;     // final closing quote of a string / quoted identifier: a token ends here
   uint32_t bad = 0;       // the statement containing this byte needs the exact path
   uint32_t bad_prev = 0;  // the statement ENDING right before this (statement start) byte needs the exact path
-  uint8_t cap_type = 0;   // token of `lane` if close has its bit
-  uint32_t cap_start = 0;
+  uint32_t escm = 0;
+  uint8_t s_out = A_C;
+  uint8_t ncap = 0;
+  uint8_t cap_pos[NUTDB_L2_NCAP];
+  uint8_t cap_type[NUTDB_L2_NCAP];     // token type; for a literal opened in an earlier window: 1 = '..', 2 = "..", 3 = `..`
+  uint8_t cap_carried[NUTDB_L2_NCAP];
+  uint32_t cap_start[NUTDB_L2_NCAP];   // absolute start of the payload (opened in this window)
+  uint8_t esc_first = 0;               // this window's escaped-flag contribution before a carried close
+  StrCarry sc;
+  uint32_t last_bnd1 = 0;              // 1 + absolute offset of the last statement start in the window, 0 if none
 };
 
-NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Next& nx, int lane, Carry2& c, CtxOut& o) {
+NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Next& nx, uint8_t s_in, uint8_t prev_byte,
+                         WinCtx& o) {
   uint32_t todo = ev.all, consumed = 0;
-  uint8_t s = c.s;
-  int s_pos = -1, p0 = 0, reopen_at = c.reopen ? 0 : -1;
+  uint8_t s = s_in;
+  // '' / "" split exactly at the window start: the closing quote was the previous window's last byte
+  const uint8_t b0q = (w.sq & 1u) ? (uint8_t)'\'' : ((w.dq & 1u) ? (uint8_t)'"' : (uint8_t)0);
+  int reopen_at = (s_in == A_C && b0q && prev_byte == b0q && !(w.bnd & 1u)) ? 0 : -1;
+  int s_pos = -1, p0 = 0;
   uint32_t m_code = 0, m_str = 0, m_bt = 0;
+  bool open_local = false;
+  uint32_t cur_start = 0;
+  uint8_t cur_esc = 0;
   auto assign = [&](int lo, int hi) {
     if (hi < lo) return;
     const uint32_t r = bits_range(lo, hi);
     if (s <= A_CX) m_code |= r;
     else if (s == A_SQ || s == A_DQ) {
       m_str |= r;
-      if (w.bs & r) c.escaped = 1;
+      if (w.bs & r) cur_esc = 1;
     } else if (s == A_BT) m_bt |= r;
+  };
+  auto record = [&](int e, uint8_t local_type, uint8_t kind) {
+    o.close |= 1u << e;
+    if (o.ncap >= NUTDB_L2_NCAP) {
+      o.bad |= 1u << e;
+      return;
+    }
+    o.cap_pos[o.ncap] = (uint8_t)e;
+    o.cap_carried[o.ncap] = open_local ? 0 : 1;
+    o.cap_type[o.ncap] = open_local ? local_type : kind;
+    o.cap_start[o.ncap] = cur_start + 1;
+    if (!open_local) o.esc_first = cur_esc;
+    o.ncap++;
   };
   while (todo) {
     const int e = ctz32(todo);
@@ -220,8 +270,9 @@ NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Ne
       s = A_C;
       s_pos = -100;
       reopen_at = -1;
-      c.escaped = 0;
-      c.stmt_start = base + (uint32_t)e;
+      cur_esc = 0;
+      open_local = true;  // nothing can be carried into a new statement
+      o.last_bnd1 = base + (uint32_t)e + 1u;
       p0 = e;
       if (!((ev.own >> e) & 1u)) continue;
     }
@@ -232,13 +283,20 @@ NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Ne
     const uint8_t a1 = a_next(a0, t);
     if (a0 <= A_CX) {
       if (t == EV_SQ || t == EV_DQ) {
-        if (reopen_at == e) c.escaped = 1;  // second half of '' / ""
+        if (reopen_at == e) cur_esc = 1;  // second half of '' / ""
         else {
-          c.str_start = base + (uint32_t)e;
-          c.escaped = 0;
+          open_local = true;
+          cur_start = base + (uint32_t)e;
+          cur_esc = 0;
+          o.sc.has_open = 1;
+          o.sc.open_pos = cur_start;
         }
       } else if (t == EV_BT) {
-        c.str_start = base + (uint32_t)e;
+        open_local = true;
+        cur_start = base + (uint32_t)e;
+        cur_esc = 0;
+        o.sc.has_open = 1;
+        o.sc.open_pos = cur_start;
       } else if ((t == EV_DD || t == EV_SLST) && a0 == A_C) {
         consumed |= 1u << e;  // second byte of "--" / "/*": not a token
       }
@@ -250,30 +308,24 @@ NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Ne
       if (twin) {
         reopen_at = e + 1;
       } else {
-        o.close |= 1u << e;
-        if (lane == e) {
-          o.cap_type = c.escaped ? (t == EV_SQ ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
-                                 : (uint8_t)NUTDB_TT_RawStringLiteral;
-          o.cap_start = c.str_start + 1;
-        }
+        record(e, cur_esc ? (t == EV_SQ ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
+                          : (uint8_t)NUTDB_TT_RawStringLiteral,
+               t == EV_SQ ? 1 : 2);
+        cur_esc = 0;
       }
     } else if (a0 == A_BT && t == EV_BT) {
-      o.close |= 1u << e;
-      // `` : Incomplete (tokenizer/mod.rs:323).  Decided from the previous byte, not from str_start: the
-      // counting pass (which flags statements) does not know carried offsets at a segment start.
-      if (e > 0 ? ((w.bt >> (e - 1)) & 1u) != 0 : c.prev == '`') o.bad |= 1u << e;
-      if (lane == e) {
-        o.cap_type = NUTDB_TT_DelimitedIdentifier;
-        o.cap_start = c.str_start + 1;
-      }
+      record(e, NUTDB_TT_DelimitedIdentifier, 3);
+      // `` : Incomplete (tokenizer/mod.rs:323): the previous byte is the opening backtick
+      if (e > 0 ? ((w.bt >> (e - 1)) & 1u) != 0 : prev_byte == '`') o.bad |= 1u << e;
+      cur_esc = 0;
     }
     s = a1;
     s_pos = e;
   }
   assign(p0, 31);
   if (s_pos < 31) s = decay(s);
-  c.s = s;
-  c.reopen = reopen_at == 32 ? 1 : 0;
+  o.s_out = s;
+  o.sc.esc = cur_esc;
   o.ct = m_code & ~consumed & w.valid;
   o.in_str = m_str & w.valid;
   o.in_bt = m_bt & w.valid;
@@ -302,42 +354,18 @@ NUTDB_HD int run_start(uint64_t cont, int pos) {
   return r == 0 ? -1 : r;  // position 0 always "stops" (nothing is known below it): the run may extend further back
 }
 
+// the code token (if any) that ENDS at byte i of the window; i is a code-token byte (bit of ct)
 template <class Src>
-NUTDB_HD LaneTok lane_token(const LexTables& T, Src& src, int lane, uint32_t base, uint8_t b, uint16_t k, const Win& w,
-                            const CtxOut& o, const Hist& h, const Next& nx, uint32_t esc_mask, uint8_t prev_byte) {
+NUTDB_HD LaneTok code_token_at(const LexTables& T, Src& src, int lane, uint32_t base, uint8_t b, uint16_t k, const Win& w,
+                               uint32_t ct, const Hist& h, const Next& nx, uint32_t esc_mask, uint8_t prev_byte) {
   LaneTok r;
   const uint32_t bit = 1u << lane;
-  if (!(w.valid & bit)) return r;
   const uint32_t pos = base + (uint32_t)lane;
   // the byte after this one
   const bool nbnd = lane < 31 ? ((w.bnd >> (lane + 1)) & 1u) != 0 : nx.bnd != 0;
   const uint8_t nb = lane < 31 ? (nbnd ? (uint8_t)0 : src.byte(pos + 1)) : (nbnd ? (uint8_t)0 : nx.byte);
-  r.eof = nbnd ? 1 : 0;
-  if (o.close & bit) {  // string / quoted identifier closed here (stage 2)
-    r.has = 1;
-    r.type = o.cap_type;
-    r.start = o.cap_start;
-    r.end = pos;
-    if (o.bad & bit) r.bad = 1;
-    return r;
-  }
-  if (o.in_str & bit) {  // raw CR / LF inside a string literal is an error unless escaped (mod.rs:147-170)
-    if (b == '\r') {
-      if (!(esc_mask & bit)) r.bad = 1;
-    } else if (b == '\n') {
-      const bool pesc = lane > 0 ? ((esc_mask >> (lane - 1)) & 1u) != 0 : false;
-      const uint8_t pb = lane > 0 ? src.byte(pos - 1) : prev_byte;
-      if (!(esc_mask & bit) && !(pb == '\r' && pesc)) r.bad = 1;
-    }
-    return r;
-  }
-  if (o.in_bt & bit) {
-    if (k & K_NL) r.bad = 1;
-    return r;
-  }
-  if (!(o.ct & bit)) return r;  // comment bytes, consumed second bytes of "--" and "/*"
   const uint16_t nk = nbnd ? (uint16_t)0 : (lane < 31 ? (uint16_t)0xFFFF : nx.cls);  // class of next byte (lane 31 only)
-  const uint32_t ctL = w.L & o.ct, ctD = w.D & o.ct, ctDOT = w.DOT & o.ct, ctOP = w.OP & o.ct;
+  const uint32_t ctL = w.L & ct, ctD = w.D & ct, ctDOT = w.DOT & ct, ctOP = w.OP & ct;
   const uint64_t L64 = ((uint64_t)ctL << 32) | h.L, D64 = ((uint64_t)ctD << 32) | h.D;
   const uint64_t DOT64 = ((uint64_t)ctDOT << 32) | h.DOT, OP64 = ((uint64_t)ctOP << 32) | h.OP;
   const uint64_t bnd64 = ((uint64_t)w.bnd << 32) | h.bnd;
@@ -363,12 +391,6 @@ NUTDB_HD LaneTok lane_token(const LexTables& T, Src& src, int lane, uint32_t bas
       r.type = NUTDB_TT_KeywordOrIdentifier;
       r.start = abs_st;
       r.end = pos + 1;
-      const uint32_t len = r.end - r.start;
-      if (len >= 2 && len <= 10) {
-        Src& sr = src;
-        const uint32_t s0 = r.start;
-        r.kw = keyword_lookup(T, len, [&sr, s0](uint32_t i) { return sr.byte(s0 + i); });
-      }
       return r;
     }
     if (L64 & span) { r.bad = 1; return r; }  // 1abc, 0x1F ...: error or hex -> exact path
@@ -495,10 +517,116 @@ NUTDB_HD LaneTok lane_token(const LexTables& T, Src& src, int lane, uint32_t bas
     r.end = pos + 1;
     return r;
   }
-  if (k & K_WS) return r;
-  if ((k & (K_SQ | K_DQ | K_BT)) && !(esc_mask & bit)) return r;  // an opening quote: stage 2 handles the literal
-  r.bad = 1;  // invalid character in code, '@', '$', an escaped quote outside a string ...
-  return r;
+  (void)bit;
+  (void)esc_mask;
+  return r;  // whitespace, opening quotes: no code token ends here (invalid bytes are caught by win_bad_mask)
+}
+
+// statements that need the exact path, as far as masks can tell (token-level checks add to this)
+template <class Src>
+NUTDB_HD uint32_t win_bad_mask(Src& src, const Win& w, const WinCtx& o, uint32_t base, uint8_t prev_byte) {
+  const uint32_t known = w.sq | w.dq | w.bt | w.WS | w.dash | w.slash | w.L | w.D | w.DOT | w.OP | w.P;
+  uint32_t bad = o.bad;
+  bad |= o.ct & w.valid & ~known;              // '@' '$' '#' '?' '\\' controls, non-ASCII in code
+  bad |= o.ct & (w.sq | w.dq) & o.escm;        // an escaped quote outside a string
+  bad |= o.in_bt & w.nl;                       // raw newline in `..` (tokenizer/mod.rs:336)
+  uint32_t nls = o.in_str & w.nl;              // raw CR / LF inside a string literal must be escaped (mod.rs:147-170)
+  while (nls) {
+    const int i = ctz32(nls);
+    nls &= nls - 1;
+    const uint32_t bit = 1u << i;
+    if (o.escm & bit) continue;
+    const uint8_t b = src.byte(base + (uint32_t)i);
+    if (b == '\n') {
+      const uint8_t pb = i > 0 ? src.byte(base + (uint32_t)i - 1u) : prev_byte;
+      const bool pesc = i > 0 ? ((o.escm >> (i - 1)) & 1u) != 0 : false;
+      if (pb == '\r' && pesc) continue;  // backslash CR LF
+    }
+    bad |= bit;
+  }
+  return bad;
+}
+
+// candidate positions: a code token can only end where one of these bits is set
+NUTDB_HD uint32_t win_candidates(const Win& w, const WinCtx& o, const Next& nx) {
+  const uint32_t nbnd = (w.bnd >> 1) | ((uint32_t)(nx.bnd != 0) << 31);
+  const uint32_t Wm = (w.L | w.D);
+  const uint32_t nextW = ((Wm >> 1) | ((uint32_t)((nx.cls & (K_L | K_D)) != 0) << 31)) & ~nbnd;
+  const uint32_t nextDash = ((w.dash >> 1) | ((uint32_t)(nx.byte == '-') << 31)) & ~nbnd;
+  const uint32_t nextStar = ((w.star >> 1) | ((uint32_t)(nx.byte == '*') << 31)) & ~nbnd;
+  uint32_t c = (Wm & ~nextW) | w.DOT | w.OP | w.P | (w.dash & ~nextDash) | (w.slash & ~nextStar);
+  return c & o.ct;
+}
+
+// Sink: void token(uint32_t index, uint8_t type, uint32_t start_rel, uint32_t end_rel, uint8_t kw);
+//       void stmt_begin(uint32_t abs_pos, uint32_t first_index); void stmt_end(uint32_t abs_last_byte, uint32_t end_index);
+// Returns the number of tokens of the window (EOF tokens included); `bad` gets the positions whose
+// statement needs the exact path.  With Emit = false nothing is written and no keyword is looked up.
+template <bool Emit, class Src, class Sink>
+NUTDB_HD uint32_t win_tokens(const LexTables& T, const Lex2Tables& K, Src& src, Sink& sink, const Win& w, const WinCtx& o,
+                             const Hist& h, const Next& nx, uint32_t base, uint8_t prev_byte, const StrCarry& sc_in,
+                             uint32_t stmt_start_in, uint32_t index, uint32_t& bad) {
+  bad = win_bad_mask(src, w, o, base, prev_byte);
+  const uint32_t eofm = ((w.bnd >> 1) | ((uint32_t)(nx.bnd != 0) << 31)) & w.valid;
+  uint32_t todo = win_candidates(w, o, nx) | o.close | eofm;
+  if (Emit) todo |= w.bnd & w.valid;
+  uint32_t n = 0, icap = 0;
+  uint32_t sst = stmt_start_in;
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const uint32_t bit = 1u << i;
+    const uint32_t pos = base + (uint32_t)i;
+    if (Emit && (w.bnd & w.valid & bit)) {
+      sst = pos;
+      sink.stmt_begin(pos, index + n);
+    }
+    if (o.close & bit) {
+      if (icap < o.ncap && o.cap_pos[icap] == i) {
+        if (Emit) {
+          uint8_t type = o.cap_type[icap];
+          uint32_t start = o.cap_start[icap];
+          if (o.cap_carried[icap]) {  // opened in an earlier window: offset and escaped flag come from the carry
+            start = sc_in.open_pos + 1u;
+            const bool escd = (sc_in.esc | o.esc_first) != 0;
+            type = type == 3 ? (uint8_t)NUTDB_TT_DelimitedIdentifier
+                             : (escd ? (type == 1 ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
+                                     : (uint8_t)NUTDB_TT_RawStringLiteral);
+          }
+          sink.token(index + n, type, start - sst, pos - sst, 0);
+        }
+        icap++;
+      }
+      n++;  // (closes beyond the capture array are flagged bad; they still count so both passes agree)
+    } else if (o.ct & bit) {
+      const uint8_t b = src.byte(pos);
+      const LaneTok t = code_token_at(T, src, i, base, b, K.cls[b], w, o.ct, h, nx, o.escm, prev_byte);
+      if (t.bad) bad |= bit;
+      if (t.has) {
+        if (Emit) {
+          uint8_t kw = t.kw;
+          if (t.type == NUTDB_TT_KeywordOrIdentifier) {
+            const uint32_t len = t.end - t.start;
+            if (len >= 2 && len <= 10) {
+              Src& sr = src;
+              const uint32_t s0 = t.start;
+              kw = keyword_lookup(T, len, [&sr, s0](uint32_t q) { return sr.byte(s0 + q); });
+            }
+          }
+          sink.token(index + n, t.type, t.start - sst, t.end - sst, kw);
+        }
+        n++;
+      }
+    }
+    if (eofm & bit) {
+      if (Emit) {
+        sink.token(index + n, NUTDB_TT_EOF, pos + 1u - sst, pos + 1u - sst, 0);
+        sink.stmt_end(pos, index + n + 1u);
+      }
+      n++;
+    }
+  }
+  return n;
 }
 
 }  // namespace nlex2

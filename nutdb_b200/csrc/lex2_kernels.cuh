@@ -56,49 +56,40 @@ __device__ __forceinline__ uint32_t bnd_word(const Lex2Shared& S, const uint32_t
   return r < L2_TILE ? S.bm[r >> 5] : bitmap[base >> 5];
 }
 
-// stage 1: raw class masks of the window at `base` (warp-wide)
-__device__ __forceinline__ void build_win(const Lex2Shared& S, const Tile2Src& src, const uint32_t* bitmap,
-                                          uint32_t tile_begin, uint32_t base, uint32_t n, int lane, uint8_t& b, uint16_t& k,
-                                          nlex2::Win& w) {
-  const uint32_t pos = base + (uint32_t)lane;
-  b = src.byte(pos);
-  k = pos < n ? S.K.cls[b] : (uint16_t)0;
+// ---- per-thread window set-up shared by the three kernels -------------------------------------------------
+// Lane j of a warp owns window j of the warp's 1 KB block.  stage 1: the warp classifies window jj (one byte
+// per lane), ballots give its class masks, lane jj keeps them.
+template <bool All>
+__device__ __forceinline__ void build_masks(const Lex2Shared& S, const Tile2Src& src, uint32_t blk, uint32_t n, int lane,
+                                            nlex2::Win& w) {
   const uint32_t full = 0xFFFFFFFFu;
-  w.valid = base + 32u <= n ? full : (n > base ? ((1u << (n - base)) - 1u) : 0u);
-  w.sq = __ballot_sync(full, k & nlex2::K_SQ);
-  w.dq = __ballot_sync(full, k & nlex2::K_DQ);
-  w.bt = __ballot_sync(full, k & nlex2::K_BT);
-  w.nl = __ballot_sync(full, k & nlex2::K_NL);
-  w.bs = __ballot_sync(full, k & nlex2::K_BS);
-  w.dash = __ballot_sync(full, k & nlex2::K_DASH);
-  w.slash = __ballot_sync(full, k & nlex2::K_SLASH);
-  w.star = __ballot_sync(full, k & nlex2::K_STAR);
-  w.L = __ballot_sync(full, k & nlex2::K_L);
-  w.D = __ballot_sync(full, k & nlex2::K_D);
-  w.DOT = __ballot_sync(full, k & nlex2::K_DOT);
-  w.OP = __ballot_sync(full, k & nlex2::K_OP);
-  uint32_t bnd = bnd_word(S, bitmap, tile_begin, base) & w.valid;
-  if (n >= base && n - base < 32u) bnd |= 1u << (n - base);  // the batch end terminates the last statement
-  w.bnd = bnd;
-}
-
-__device__ __forceinline__ nlex2::Next next_of(const Lex2Shared& S, const Tile2Src& src, const uint32_t* bitmap,
-                                               uint32_t tile_begin, uint32_t base, uint32_t n) {
-  nlex2::Next nx;
-  const uint32_t p = base + 32u;
-  if (p >= n) {
-    nx.byte = 0;
-    nx.bnd = 1;
-    nx.cls = 0;
-  } else {
-    nx.byte = src.byte(p);
-    nx.bnd = (uint8_t)(bnd_word(S, bitmap, tile_begin, p) & 1u);
-    nx.cls = S.K.cls[nx.byte];
+  w.sq = w.dq = w.bt = w.nl = w.bs = w.dash = w.slash = w.star = w.L = w.D = w.DOT = w.OP = w.P = w.WS = 0u;
+#pragma unroll 4
+  for (int jj = 0; jj < 32; jj++) {
+    const uint32_t pos = blk + 32u * (uint32_t)jj + (uint32_t)lane;
+    const uint16_t k = pos < n ? S.K.cls[src.byte(pos)] : (uint16_t)0;
+    const bool mine = lane == jj;
+    uint32_t m;
+    m = __ballot_sync(full, k & nlex2::K_SQ); if (mine) w.sq = m;
+    m = __ballot_sync(full, k & nlex2::K_DQ); if (mine) w.dq = m;
+    m = __ballot_sync(full, k & nlex2::K_BT); if (mine) w.bt = m;
+    m = __ballot_sync(full, k & nlex2::K_NL); if (mine) w.nl = m;
+    m = __ballot_sync(full, k & nlex2::K_BS); if (mine) w.bs = m;
+    m = __ballot_sync(full, k & nlex2::K_DASH); if (mine) w.dash = m;
+    m = __ballot_sync(full, k & nlex2::K_SLASH); if (mine) w.slash = m;
+    m = __ballot_sync(full, k & nlex2::K_STAR); if (mine) w.star = m;
+    if (All) {
+      m = __ballot_sync(full, k & nlex2::K_L); if (mine) w.L = m;
+      m = __ballot_sync(full, k & nlex2::K_D); if (mine) w.D = m;
+      m = __ballot_sync(full, k & nlex2::K_DOT); if (mine) w.DOT = m;
+      m = __ballot_sync(full, k & nlex2::K_OP); if (mine) w.OP = m;
+      m = __ballot_sync(full, k & nlex2::K_P); if (mine) w.P = m;
+      m = __ballot_sync(full, k & nlex2::K_WS); if (mine) w.WS = m;
+    }
   }
-  return nx;
 }
 
-// backslash parity and previous byte in front of a segment
+// backslash parity and previous byte in front of position pos (walks back over the run; never across a statement start)
 __device__ __forceinline__ void entry_esc(const Tile2Src& src, const uint32_t* bitmap, uint32_t pos, uint8_t& prev,
                                           uint8_t& esc) {
   prev = 0;
@@ -110,9 +101,72 @@ __device__ __forceinline__ void entry_esc(const Tile2Src& src, const uint32_t* b
   while (p > 0 && src.byte(p - 1) == '\\') {
     nrun++;
     p--;
-    if ((bitmap[p >> 5] >> (p & 31u)) & 1u) break;  // the run cannot extend over a statement start
+    if ((bitmap[p >> 5] >> (p & 31u)) & 1u) break;
   }
   esc = (uint8_t)(nrun & 1u);
+}
+
+struct WinSetup {
+  nlex2::Win w;
+  nlex2::Next nx;
+  nlex2::Events ev;
+  uint32_t base, escm;
+  uint8_t prev_byte;
+};
+
+// everything a thread knows about its window before any carry: masks, neighbours, escapes, events
+template <bool All, bool Virt>
+__device__ __forceinline__ void setup_window(const Lex2Shared& S, const Tile2Src& src, const uint32_t* bitmap,
+                                             uint32_t tile_begin, uint32_t blk, uint32_t n, int lane, WinSetup& u) {
+  const uint32_t full = 0xFFFFFFFFu;
+  build_masks<All>(S, src, blk, n, lane, u.w);
+  u.base = blk + 32u * (uint32_t)lane;
+  nlex2::Win& w = u.w;
+  w.valid = u.base + 32u <= n ? full : (n > u.base ? ((1u << (n - u.base)) - 1u) : 0u);
+  uint32_t bnd = u.base < n ? (bnd_word(S, bitmap, tile_begin, u.base) & w.valid) : 0u;
+  if (Virt && n >= u.base && n - u.base < 32u) bnd |= 1u << (n - u.base);  // the batch end terminates the last statement
+  w.bnd = bnd;
+  // next window's first byte
+  const uint32_t p = u.base + 32u;
+  if (p >= n) {
+    u.nx.byte = 0;
+    u.nx.bnd = 1;
+    u.nx.cls = 0;
+  } else {
+    u.nx.byte = src.byte(p);
+    u.nx.bnd = (uint8_t)(bnd_word(S, bitmap, tile_begin, p) & 1u);
+    u.nx.cls = S.K.cls[u.nx.byte];
+  }
+  // previous byte and backslash parity in front of the window
+  const uint32_t bs_prev = __shfl_up_sync(full, w.bs, 1);
+  uint8_t esc_in;
+  if (lane == 0) {
+    entry_esc(src, bitmap, u.base < n ? u.base : 0u, u.prev_byte, esc_in);
+  } else {
+    u.prev_byte = u.base <= n && u.base > 0 ? src.byte(u.base - 1u) : (uint8_t)0;
+    const int run = nlex2::clz32(~bs_prev);
+    esc_in = (uint8_t)(run >= 32 ? 0 : (run & 1));  // (a window of 32 backslashes: its statement is flagged, see below)
+  }
+  u.escm = nlex2::esc_mask32(w.bs, esc_in) & ~w.bnd;
+  u.ev = nlex2::make_events(w, u.escm, u.prev_byte);
+}
+
+__device__ __forceinline__ uint32_t warp_scan_vec8(uint32_t f, int lane, uint32_t& excl) {
+  const uint32_t full = 0xFFFFFFFFu;
+  uint32_t v = f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(full, v, d);
+    if (lane >= d) v = vec8_then(o, v);
+  }
+  excl = __shfl_up_sync(full, v, 1);
+  if (lane == 0) excl = NUTDB_VEC8_ID;
+  return v;
+}
+
+__device__ __forceinline__ uint32_t window_fn(const LexTables& T, const WinSetup& u) {
+  if (u.ev.all) return nlex2::ctx_window_fn(T, u.w, u.ev, NUTDB_VEC8_ID);
+  return vec8_then_row(NUTDB_VEC8_ID, T.a_row[EV_OTHER][0], T.a_row[EV_OTHER][1]);
 }
 
 __global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
@@ -126,36 +180,14 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restric
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text), tile_begin, n};
-  const uint32_t seg = tile_begin + (uint32_t)warp * L2_SEG;
+  const uint32_t blk = tile_begin + (uint32_t)warp * L2_SEG;
   uint32_t run = NUTDB_VEC8_ID;
-  if (seg < n) {
-    uint8_t prev, esc;
-    entry_esc(src, bitmap, seg, prev, esc);
-    const uint32_t end = min(seg + L2_SEG, n);
-    for (uint32_t base = seg; base < end; base += 32u) {
-      const uint32_t pos = base + (uint32_t)lane;
-      const uint8_t b = src.byte(pos);
-      const uint16_t k = pos < n ? S.K.cls[b] : (uint16_t)0;
-      const uint32_t full = 0xFFFFFFFFu;
-      nlex2::Win w;
-      w.valid = base + 32u <= n ? full : ((1u << (n - base)) - 1u);
-      w.sq = __ballot_sync(full, k & nlex2::K_SQ);
-      w.dq = __ballot_sync(full, k & nlex2::K_DQ);
-      w.bt = __ballot_sync(full, k & nlex2::K_BT);
-      w.nl = __ballot_sync(full, k & nlex2::K_NL);
-      w.bs = __ballot_sync(full, k & nlex2::K_BS);
-      w.dash = __ballot_sync(full, k & nlex2::K_DASH);
-      w.slash = __ballot_sync(full, k & nlex2::K_SLASH);
-      w.star = __ballot_sync(full, k & nlex2::K_STAR);
-      w.L = w.D = w.DOT = w.OP = 0;
-      w.bnd = bnd_word(S, bitmap, tile_begin, base) & w.valid;
-      const uint32_t escm = __ballot_sync(full, nlex2::lane_esc(w.bs, lane, esc)) & ~w.bnd;
-      const nlex2::Events ev = nlex2::make_events(w, escm, prev);
-      if (ev.all) run = nlex2::ctx_window_fn(S.T, w, ev, run);
-      else run = vec8_then_row(run, S.T.a_row[EV_OTHER][0], S.T.a_row[EV_OTHER][1]);
-      esc = nlex2::esc_carry_out(w.bs, esc);
-      prev = (uint8_t)__shfl_sync(full, (uint32_t)b, 31);
-    }
+  if (blk < n) {
+    WinSetup u;
+    setup_window<false, false>(S, src, bitmap, tile_begin, blk, n, lane, u);
+    const uint32_t f = u.base < n ? window_fn(S.T, u) : NUTDB_VEC8_ID;
+    uint32_t excl;
+    run = __shfl_sync(0xFFFFFFFFu, warp_scan_vec8(f, lane, excl), 31);
   }
   if (lane == 0) wfn[warp] = run;
   __syncthreads();
@@ -195,8 +227,20 @@ struct Lex2Out {
     const uint32_t s = find_stmt(pos);
     if (atomicExch(&punt_flag[s], 1u) == 0u) punt_list[atomicAdd(punt_count, 1u)] = s;
   }
+  // sink interface of nlex2::win_tokens
+  __device__ __forceinline__ void token(uint32_t i, uint8_t t, uint32_t s, uint32_t e, uint8_t k) const {
+    if (i < cap) {
+      type[i] = t;
+      start[i] = s;
+      end[i] = e;
+      kw[i] = k;
+    }
+  }
+  __device__ __forceinline__ void stmt_begin(uint32_t pos, uint32_t first) const { stmt_tok_begin[find_stmt(pos)] = first; }
+  __device__ __forceinline__ void stmt_end(uint32_t pos, uint32_t endi) const { stmt_tok_end[find_stmt(pos)] = endi; }
 };
 
+// Emit = false: token counts per window (wcount, one byte each) + per-warp carries + flags; Emit = true: tokens.
 template <bool Emit>
 __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restrict__ text,
                                                           const uint32_t* __restrict__ bitmap, uint32_t n,
@@ -205,124 +249,157 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
                                                           const uint32_t* __restrict__ localA,
                                                           const uint8_t* __restrict__ tileEntA, uint4* __restrict__ localC,
                                                           uint4* __restrict__ tileC, const uint4* __restrict__ tilePrefC,
-                                                          Lex2Out out) {
+                                                          uint8_t* __restrict__ wcount, Lex2Out out) {
   __shared__ Lex2Shared S;
   __shared__ uint4 wsum[L2_WARPS];
   const uint32_t tile_begin = blockIdx.x * L2_TILE;
   stage_tile2(text, bitmap, tile_begin, n, S, gT, gK);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t full = 0xFFFFFFFFu, lt = (1u << lane) - 1u;
+  const uint32_t full = 0xFFFFFFFFu;
   Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text), tile_begin, n};
-  const uint32_t seg = tile_begin + (uint32_t)warp * L2_SEG;
+  const uint32_t blk = tile_begin + (uint32_t)warp * L2_SEG;
   const uint32_t widx = blockIdx.x * L2_WARPS + warp;
-  nlex2::Carry2 c;
-  bool opened = false;
-  uint32_t nbnd_seen = 0;
-  if (seg < n) {
-    c.s = (uint8_t)vec8_apply(localA[widx], tileEntA[blockIdx.x]);
-    entry_esc(src, bitmap, seg, c.prev, c.esc);
-    c.str_start = NUTDB_NO_TOK;
-    c.stmt_start = 0;
-    if (Emit) {
-      const CSum pre = csum_unpack(CSumOp::then(tilePrefC[blockIdx.x], localC[widx]));
-      c.count = pre.count;
-      c.str_start = pre.tok_start;
-      c.escaped = pre.escaped;
-      c.stmt_start = pre.stmt_start;
-    }
-    // history: class masks of the 32 bytes in front of the segment (raw masks are exact there when we enter in code)
+  CSum wtotal = csum_identity();
+  if (blk < n) {
+    WinSetup u;
+    setup_window<true, true>(S, src, bitmap, tile_begin, blk, n, lane, u);
+    const bool live = u.base < n;
+    // entry state of every window: scan of the window functions on top of the warp's entry state
+    const uint32_t f = live ? window_fn(S.T, u) : NUTDB_VEC8_ID;
+    uint32_t excl;
+    warp_scan_vec8(f, lane, excl);
+    const uint8_t s_warp = (uint8_t)vec8_apply(localA[widx], tileEntA[blockIdx.x]);
+    const uint8_t s_in = (uint8_t)vec8_apply(excl, s_warp);
+    nlex2::WinCtx o;
+    if (live) nlex2::ctx_window(u.w, u.ev, u.base, u.nx, s_in, u.prev_byte, o);
+    o.escm = u.escm;
+    // history: code-token class masks of the previous window (lane 0: the 32 bytes in front of the block, whose
+    // raw classes are exact when the block is entered in code)
     nlex2::Hist h;
-    if (seg >= 32u && c.s <= A_CX) {
-      const uint32_t pos = seg - 32u + (uint32_t)lane;
-      const uint16_t k = S.K.cls[src.byte(pos)];
-      h.L = __ballot_sync(full, k & nlex2::K_L);
-      h.D = __ballot_sync(full, k & nlex2::K_D);
-      h.DOT = __ballot_sync(full, k & nlex2::K_DOT);
-      h.OP = __ballot_sync(full, k & nlex2::K_OP);
-      h.bnd = bitmap[(seg - 32u) >> 5];
-    } else if (seg >= 32u) {
-      h.bnd = bitmap[(seg - 32u) >> 5];
+    {
+      uint32_t rL = 0, rD = 0, rDOT = 0, rOP = 0;
+      if (blk >= 32u) {
+        const uint16_t k = S.K.cls[src.byte(blk - 32u + (uint32_t)lane)];
+        rL = __ballot_sync(full, k & nlex2::K_L);
+        rD = __ballot_sync(full, k & nlex2::K_D);
+        rDOT = __ballot_sync(full, k & nlex2::K_DOT);
+        rOP = __ballot_sync(full, k & nlex2::K_OP);
+      }
+      const bool code_entry = s_warp <= A_CX;
+      h.L = __shfl_up_sync(full, u.w.L & o.ct, 1);
+      h.D = __shfl_up_sync(full, u.w.D & o.ct, 1);
+      h.DOT = __shfl_up_sync(full, u.w.DOT & o.ct, 1);
+      h.OP = __shfl_up_sync(full, u.w.OP & o.ct, 1);
+      h.bnd = __shfl_up_sync(full, u.w.bnd, 1);
+      if (lane == 0) {
+        h.L = code_entry ? rL : 0u;
+        h.D = code_entry ? rD : 0u;
+        h.DOT = code_entry ? rDOT : 0u;
+        h.OP = code_entry ? rOP : 0u;
+        h.bnd = blk >= 32u ? bitmap[(blk - 32u) >> 5] : 0u;
+      }
     }
-    {  // '' / "" split exactly at the segment start
-      const uint8_t b0 = src.byte(seg);
-      const bool bnd0 = (bnd_word(S, bitmap, tile_begin, seg) & 1u) != 0;
-      c.reopen = (c.s == A_C && !bnd0 && (c.prev == '\'' || c.prev == '"') && b0 == c.prev) ? 1 : 0;
-    }
-    const uint32_t end = min(seg + L2_SEG, n);
-    for (uint32_t base = seg; base < end; base += 32u) {
-      uint8_t b;
-      uint16_t k;
-      nlex2::Win w;
-      build_win(S, src, bitmap, tile_begin, base, n, lane, b, k, w);
-      const nlex2::Next nx = next_of(S, src, bitmap, tile_begin, base, n);
-      const uint32_t escm = __ballot_sync(full, nlex2::lane_esc(w.bs, lane, c.esc)) & ~w.bnd;
-      const nlex2::Events ev = nlex2::make_events(w, escm, c.prev);
-      const uint32_t stmt_entry = c.stmt_start;
-      const uint32_t str_before = c.str_start;
-      nlex2::CtxOut o;
-      nlex2::ctx_window(w, ev, base, nx, lane, c, o);
-      if (c.str_start != str_before) opened = true;
-      nbnd_seen += (uint32_t)__popc(w.bnd & w.valid);
-      nlex2::LaneTok t = nlex2::lane_token(S.T, src, lane, base, b, k, w, o, h, nx, escm, c.prev);
-      const uint32_t tokmask = __ballot_sync(full, t.has);
-      const uint32_t eofmask = __ballot_sync(full, t.eof);
-      if (!Emit) {
-        const uint32_t badmask = __ballot_sync(full, t.bad) | o.bad;
-        if (badmask | o.bad_prev) {
-          if ((badmask >> lane) & 1u) out.punt(base + (uint32_t)lane);
-          if ((o.bad_prev >> lane) & 1u) out.punt(base + (uint32_t)lane - 1u);
+    nlex2::StrCarry sc_in;
+    uint32_t stmt_in = 0, index = 0, ntok = 0;
+    if (!Emit) {
+      uint32_t bad = 0;
+      if (live) ntok = nlex2::win_tokens<false>(S.T, S.K, src, out, u.w, o, h, u.nx, u.base, u.prev_byte, sc_in, 0u, 0u, bad);
+      if (live) {
+        if (u.w.bs == 0xFFFFFFFFu) bad |= 1u;  // backslash run longer than a window: parity not tracked
+        wcount[u.base >> 5] = (uint8_t)ntok;
+        uint32_t bb = bad;
+        while (bb) {
+          const int i = __ffs((int)bb) - 1;
+          bb &= bb - 1;
+          out.punt(u.base + (uint32_t)i);
         }
-      } else {
-        const uint32_t idx = c.count + (uint32_t)__popc(tokmask & lt) + (uint32_t)__popc(eofmask & lt);
-        // start of the statement this lane's token belongs to
-        const uint32_t below = w.bnd & w.valid & (lt | (1u << lane));
-        const uint32_t sst = below ? base + (uint32_t)(31 - __clz((int)below)) : stmt_entry;
-        if ((w.bnd & w.valid) & (1u << lane)) out.stmt_tok_begin[out.find_stmt(base + (uint32_t)lane)] = idx;
-        if (t.has && idx < out.cap) {
-          out.type[idx] = t.type;
-          out.start[idx] = t.start - sst;
-          out.end[idx] = t.end - sst;
-          out.kw[idx] = t.kw;
+        bb = o.bad_prev;
+        while (bb) {
+          const int i = __ffs((int)bb) - 1;
+          bb &= bb - 1;
+          out.punt(u.base + (uint32_t)i - 1u);
         }
-        if (t.eof) {
-          const uint32_t e = idx + (uint32_t)t.has;
-          if (e < out.cap) {
-            out.type[e] = NUTDB_TT_EOF;
-            out.start[e] = base + (uint32_t)lane + 1u - sst;
-            out.end[e] = base + (uint32_t)lane + 1u - sst;
-            out.kw[e] = 0;
+        // the batch ends exactly on a window boundary: no window carries the virtual end-of-batch statement start
+        if (u.base + 32u == n && (o.s_out == A_SQ || o.s_out == A_DQ || o.s_out == A_BT || o.s_out == A_BC0 || o.s_out == A_BC))
+          out.punt(n - 1u);
+      }
+      // warp totals: count, open string, last statement start (ordered reductions over the lanes)
+      uint32_t cnt = ntok, lb = o.last_bnd1;
+      uint32_t sc_open = o.sc.has_open, sc_esc = o.sc.esc, sc_pos = o.sc.open_pos;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t c2 = __shfl_up_sync(full, cnt, d), l2 = __shfl_up_sync(full, lb, d);
+        const uint32_t o2 = __shfl_up_sync(full, sc_open, d), e2 = __shfl_up_sync(full, sc_esc, d),
+                       p2 = __shfl_up_sync(full, sc_pos, d);
+        if (lane >= d) {
+          cnt += c2;
+          lb = max(lb, l2);
+          if (!sc_open) {  // str_then(earlier, mine)
+            sc_open = o2;
+            sc_esc |= e2;
+            sc_pos = p2;
           }
-          out.stmt_tok_end[out.find_stmt(base + (uint32_t)lane)] = e + 1u;
         }
       }
-      c.count += (uint32_t)__popc(tokmask) + (uint32_t)__popc(eofmask);
-      // next window's history and carries
-      h.L = w.L & o.ct;
-      h.D = w.D & o.ct;
-      h.DOT = w.DOT & o.ct;
-      h.OP = w.OP & o.ct;
-      h.bnd = w.bnd;
-      c.esc = nlex2::esc_carry_out(w.bs, c.esc);
-      c.prev = (uint8_t)__shfl_sync(full, (uint32_t)b, 31);
+      if (lane == 31) {
+        wtotal.count = cnt;
+        wtotal.nseg = lb ? 1u : 0u;
+        wtotal.stmt_start = lb ? lb - 1u : 0u;
+        wtotal.has_tok = (uint8_t)sc_open;
+        wtotal.tok_start = sc_pos;
+        wtotal.escaped = (uint8_t)sc_esc;
+        wsum[warp] = csum_pack(wtotal);
+      }
+    } else {
+      const CSum pre = csum_unpack(CSumOp::then(tilePrefC[blockIdx.x], localC[widx]));
+      // exclusive scans over the lanes, seeded with the warp's carry-in
+      uint32_t cnt = live ? (uint32_t)wcount[u.base >> 5] : 0u, lb = o.last_bnd1;
+      uint32_t sc_open = o.sc.has_open, sc_esc = o.sc.esc, sc_pos = o.sc.open_pos;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t c2 = __shfl_up_sync(full, cnt, d), l2 = __shfl_up_sync(full, lb, d);
+        const uint32_t o2 = __shfl_up_sync(full, sc_open, d), e2 = __shfl_up_sync(full, sc_esc, d),
+                       p2 = __shfl_up_sync(full, sc_pos, d);
+        if (lane >= d) {
+          cnt += c2;
+          lb = max(lb, l2);
+          if (!sc_open) {
+            sc_open = o2;
+            sc_esc |= e2;
+            sc_pos = p2;
+          }
+        }
+      }
+      const uint32_t own = live ? (uint32_t)wcount[u.base >> 5] : 0u;
+      uint32_t xcnt = __shfl_up_sync(full, cnt, 1), xlb = __shfl_up_sync(full, lb, 1);
+      uint32_t xo = __shfl_up_sync(full, sc_open, 1), xe = __shfl_up_sync(full, sc_esc, 1), xp = __shfl_up_sync(full, sc_pos, 1);
+      if (lane == 0) {
+        xcnt = 0;
+        xlb = 0;
+        xo = 0;
+        xe = 0;
+        xp = 0;
+      }
+      (void)own;
+      index = pre.count + xcnt;
+      stmt_in = xlb ? xlb - 1u : pre.stmt_start;
+      if (xo) {
+        sc_in.has_open = 1;
+        sc_in.esc = (uint8_t)xe;
+        sc_in.open_pos = xp;
+      } else {
+        sc_in.has_open = 0;
+        sc_in.esc = (uint8_t)(pre.escaped | xe);
+        sc_in.open_pos = pre.tok_start;
+      }
+      uint32_t bad = 0;
+      if (live) nlex2::win_tokens<true>(S.T, S.K, src, out, u.w, o, h, u.nx, u.base, u.prev_byte, sc_in, stmt_in, index, bad);
     }
-    // the batch ends exactly on a window boundary: no window carries the virtual end-of-batch statement
-    // start, so check here that the last statement did not end inside a string / quoted identifier / comment
-    if (!Emit && end == n && (n & 31u) == 0u && lane == 0 &&
-        (c.s == A_SQ || c.s == A_DQ || c.s == A_BT || c.s == A_BC0 || c.s == A_BC))
-      out.punt(n - 1u);
+  } else if (!Emit) {
+    if (lane == 31) wsum[warp] = csum_pack(wtotal);
   }
   if (!Emit) {
-    if (lane == 0) {
-      CSum s;
-      s.count = c.count;
-      s.nseg = nbnd_seen;
-      s.has_tok = opened ? 1 : 0;
-      s.tok_start = c.str_start;
-      s.escaped = c.escaped;
-      s.stmt_start = c.stmt_start;
-      wsum[warp] = csum_pack(s);
-    }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint4 acc = CSumOp::identity();

@@ -28,45 +28,6 @@ struct HSrc {
   uint8_t byte(uint32_t p) const { return e.byte(p); }
 };
 
-void build_win(const Env& e, uint32_t base, uint8_t* b, uint16_t* k, Win& w) {
-  std::memset(&w, 0, sizeof(w));
-  for (int lane = 0; lane < 32; lane++) {
-    uint32_t pos = base + lane;
-    b[lane] = e.byte(pos);
-    k[lane] = pos < e.n ? e.K->cls[b[lane]] : 0;
-    uint32_t bit = 1u << lane;
-    if (pos < e.n) w.valid |= bit;
-    if (k[lane] & K_SQ) w.sq |= bit;
-    if (k[lane] & K_DQ) w.dq |= bit;
-    if (k[lane] & K_BT) w.bt |= bit;
-    if (k[lane] & K_NL) w.nl |= bit;
-    if (k[lane] & K_BS) w.bs |= bit;
-    if (k[lane] & K_DASH) w.dash |= bit;
-    if (k[lane] & K_SLASH) w.slash |= bit;
-    if (k[lane] & K_STAR) w.star |= bit;
-    if (k[lane] & K_L) w.L |= bit;
-    if (k[lane] & K_D) w.D |= bit;
-    if (k[lane] & K_DOT) w.DOT |= bit;
-    if (k[lane] & K_OP) w.OP |= bit;
-  }
-  uint32_t bnd = e.bitmap[base >> 5] & w.valid;
-  if (e.n >= base && e.n - base < 32u) bnd |= 1u << (e.n - base);
-  w.bnd = bnd;
-}
-Next next_of(const Env& e, uint32_t base) {
-  Next nx;
-  uint32_t p = base + 32;
-  if (p >= e.n) {
-    nx.byte = 0;
-    nx.bnd = 1;
-    nx.cls = 0;
-  } else {
-    nx.byte = e.byte(p);
-    nx.bnd = e.bnd(p) ? 1 : 0;
-    nx.cls = e.K->cls[nx.byte];
-  }
-  return nx;
-}
 void entry_esc(const Env& e, uint32_t pos, uint8_t& prev, uint8_t& esc) {
   prev = 0;
   esc = 0;
@@ -81,11 +42,70 @@ void entry_esc(const Env& e, uint32_t pos, uint8_t& prev, uint8_t& esc) {
   }
   esc = (uint8_t)(nrun & 1u);
 }
-uint32_t esc_ballot(const Win& w, uint8_t carry) {
-  uint32_t m = 0;
-  for (int lane = 0; lane < 32; lane++)
-    if (lane_esc(w.bs, lane, carry)) m |= 1u << lane;
-  return m & ~w.bnd;
+
+struct WinSetup {
+  Win w;
+  Next nx;
+  Events ev;
+  uint32_t base, escm;
+  uint8_t prev_byte;
+};
+
+// the device's setup_window for window `base` of the block starting at `blk`
+void setup_window(const Env& e, uint32_t blk, uint32_t base, bool virt, WinSetup& u) {
+  Win& w = u.w;
+  std::memset(&w, 0, sizeof(w));
+  u.base = base;
+  for (int lane = 0; lane < 32; lane++) {
+    uint32_t pos = base + lane;
+    uint16_t k = pos < e.n ? e.K->cls[e.byte(pos)] : 0;
+    uint32_t bit = 1u << lane;
+    if (pos < e.n) w.valid |= bit;
+    if (k & K_SQ) w.sq |= bit;
+    if (k & K_DQ) w.dq |= bit;
+    if (k & K_BT) w.bt |= bit;
+    if (k & K_NL) w.nl |= bit;
+    if (k & K_BS) w.bs |= bit;
+    if (k & K_DASH) w.dash |= bit;
+    if (k & K_SLASH) w.slash |= bit;
+    if (k & K_STAR) w.star |= bit;
+    if (k & K_L) w.L |= bit;
+    if (k & K_D) w.D |= bit;
+    if (k & K_DOT) w.DOT |= bit;
+    if (k & K_OP) w.OP |= bit;
+    if (k & K_P) w.P |= bit;
+    if (k & K_WS) w.WS |= bit;
+  }
+  uint32_t bnd = base < e.n ? (e.bitmap[base >> 5] & w.valid) : 0u;
+  if (virt && e.n >= base && e.n - base < 32u) bnd |= 1u << (e.n - base);
+  w.bnd = bnd;
+  uint32_t p = base + 32;
+  if (p >= e.n) {
+    u.nx.byte = 0;
+    u.nx.bnd = 1;
+    u.nx.cls = 0;
+  } else {
+    u.nx.byte = e.byte(p);
+    u.nx.bnd = e.bnd(p) ? 1 : 0;
+    u.nx.cls = e.K->cls[u.nx.byte];
+  }
+  uint8_t esc_in;
+  if (base == blk) {  // lane 0 of the warp: look back through the text
+    entry_esc(e, base < e.n ? base : 0u, u.prev_byte, esc_in);
+  } else {            // other lanes: the previous window's backslash mask
+    u.prev_byte = base <= e.n && base > 0 ? e.byte(base - 1) : 0;
+    uint32_t bs_prev = 0;
+    for (int lane = 0; lane < 32; lane++)
+      if (base - 32 + lane < e.n && e.byte(base - 32 + lane) == '\\') bs_prev |= 1u << lane;
+    int run = clz32(~bs_prev);
+    esc_in = (uint8_t)(run >= 32 ? 0 : (run & 1));
+  }
+  u.escm = esc_mask32(w.bs, esc_in) & ~w.bnd;
+  u.ev = make_events(w, u.escm, u.prev_byte);
+}
+uint32_t window_fn(const LexTables& T, const WinSetup& u) {
+  if (u.ev.all) return ctx_window_fn(T, u.w, u.ev, NUTDB_VEC8_ID);
+  return vec8_then_row(NUTDB_VEC8_ID, T.a_row[EV_OTHER][0], T.a_row[EV_OTHER][1]);
 }
 
 struct Out {
@@ -117,132 +137,16 @@ struct Out {
       list->push_back(s);
     }
   }
+  void token(uint32_t i, uint8_t t, uint32_t s, uint32_t e, uint8_t k) {
+    if (i >= cap) { overflow = true; return; }
+    type[i] = t;
+    start[i] = s;
+    end[i] = e;
+    kw[i] = k;
+  }
+  void stmt_begin(uint32_t pos, uint32_t first) { stmt_tok_begin[find_stmt(pos)] = first; }
+  void stmt_end(uint32_t pos, uint32_t endi) { stmt_tok_end[find_stmt(pos)] = endi; }
 };
-
-// one segment; Emit=false: returns its CSum and flags statements; Emit=true: writes tokens
-template <bool Emit>
-CSum walk_segment(const Env& e, uint32_t seg, uint32_t seg_len, uint8_t entryA, const CSum& pre, Out& out) {
-  Carry2 c;
-  bool opened = false;
-  uint32_t nbnd_seen = 0;
-  c.s = entryA;
-  entry_esc(e, seg, c.prev, c.esc);
-  c.str_start = NUTDB_NO_TOK;
-  c.stmt_start = 0;
-  if (Emit) {
-    c.count = pre.count;
-    c.str_start = pre.tok_start;
-    c.escaped = pre.escaped;
-    c.stmt_start = pre.stmt_start;
-  }
-  Hist h;
-  if (seg >= 32) {
-    if (c.s <= A_CX)
-      for (int lane = 0; lane < 32; lane++) {
-        uint16_t k = e.K->cls[e.byte(seg - 32 + lane)];
-        uint32_t bit = 1u << lane;
-        if (k & K_L) h.L |= bit;
-        if (k & K_D) h.D |= bit;
-        if (k & K_DOT) h.DOT |= bit;
-        if (k & K_OP) h.OP |= bit;
-      }
-    h.bnd = e.bitmap[(seg - 32) >> 5];
-  }
-  {
-    uint8_t b0 = e.byte(seg);
-    bool bnd0 = e.bnd(seg);
-    c.reopen = (c.s == A_C && !bnd0 && (c.prev == '\'' || c.prev == '"') && b0 == c.prev) ? 1 : 0;
-  }
-  HSrc src{e};
-  uint32_t end = std::min(seg + seg_len, e.n);
-  for (uint32_t base = seg; base < end; base += 32) {
-    uint8_t b[32];
-    uint16_t k[32];
-    Win w;
-    build_win(e, base, b, k, w);
-    Next nx = next_of(e, base);
-    uint32_t escm = esc_ballot(w, c.esc);
-    Events ev = make_events(w, escm, c.prev);
-    uint32_t stmt_entry = c.stmt_start, str_before = c.str_start;
-    // stage 2 is warp-uniform: every lane runs it on identical inputs; only the capture differs
-    CtxOut outs[32];
-    Carry2 cnext = c;
-    for (int lane = 0; lane < 32; lane++) {
-      Carry2 cc = c;
-      ctx_window(w, ev, base, nx, lane, cc, outs[lane]);
-      if (lane == 0) cnext = cc;
-    }
-    const uint8_t prev_byte = c.prev;
-    c = cnext;
-    if (c.str_start != str_before) opened = true;
-    nbnd_seen += (uint32_t)popc32(w.bnd & w.valid);
-    LaneTok t[32];
-    uint32_t tokmask = 0, eofmask = 0, badmask = 0;
-    for (int lane = 0; lane < 32; lane++) {
-      t[lane] = lane_token(*e.T, src, lane, base, b[lane], k[lane], w, outs[lane], h, nx, escm, prev_byte);
-      if (t[lane].has) tokmask |= 1u << lane;
-      if (t[lane].eof) eofmask |= 1u << lane;
-      if (t[lane].bad) badmask |= 1u << lane;
-    }
-    const CtxOut& o = outs[0];
-    if (!Emit) {
-      badmask |= o.bad;
-      for (int lane = 0; lane < 32; lane++) {
-        if ((badmask >> lane) & 1u) out.punt(base + lane);
-        if ((o.bad_prev >> lane) & 1u) out.punt(base + lane - 1);
-      }
-    } else {
-      for (int lane = 0; lane < 32; lane++) {
-        uint32_t lt = (1u << lane) - 1u;
-        uint32_t idx = c.count + (uint32_t)popc32(tokmask & lt) + (uint32_t)popc32(eofmask & lt);
-        uint32_t below = w.bnd & w.valid & (lt | (1u << lane));
-        uint32_t sst = below ? base + (uint32_t)(31 - clz32(below)) : stmt_entry;
-        if ((w.bnd & w.valid) & (1u << lane)) out.stmt_tok_begin[out.find_stmt(base + lane)] = idx;
-        if (t[lane].has) {
-          if (idx < out.cap) {
-            out.type[idx] = t[lane].type;
-            out.start[idx] = t[lane].start - sst;
-            out.end[idx] = t[lane].end - sst;
-            out.kw[idx] = t[lane].kw;
-          } else {
-            out.overflow = true;
-          }
-        }
-        if (t[lane].eof) {
-          uint32_t ei = idx + t[lane].has;
-          if (ei < out.cap) {
-            out.type[ei] = NUTDB_TT_EOF;
-            out.start[ei] = base + lane + 1 - sst;
-            out.end[ei] = base + lane + 1 - sst;
-            out.kw[ei] = 0;
-          } else {
-            out.overflow = true;
-          }
-          out.stmt_tok_end[out.find_stmt(base + lane)] = ei + 1;
-        }
-      }
-    }
-    c.count += (uint32_t)popc32(tokmask) + (uint32_t)popc32(eofmask);
-    h.L = w.L & o.ct;
-    h.D = w.D & o.ct;
-    h.DOT = w.DOT & o.ct;
-    h.OP = w.OP & o.ct;
-    h.bnd = w.bnd;
-    c.esc = esc_carry_out(w.bs, c.esc);
-    c.prev = b[31];
-  }
-  if (!Emit && end == e.n && (e.n & 31u) == 0u &&
-      (c.s == A_SQ || c.s == A_DQ || c.s == A_BT || c.s == A_BC0 || c.s == A_BC))
-    out.punt(e.n - 1);
-  CSum s;
-  s.count = c.count;
-  s.nseg = nbnd_seen;
-  s.has_tok = opened ? 1 : 0;
-  s.tok_start = c.str_start;
-  s.escaped = c.escaped;
-  s.stmt_start = c.stmt_start;
-  return s;
-}
 
 struct StmtSrc {
   const uint8_t* text;
@@ -271,6 +175,7 @@ LexTables g_T;
 Lex2Tables g_K;
 bool g_init = false;
 uint64_t g_punts = 0;
+std::vector<uint32_t> g_xoff;
 }  // namespace
 
 extern "C" {
@@ -295,79 +200,122 @@ int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
       bitmap[p >> 5] |= 1u << (p & 31);
     }
   Env e{text, bitmap.data(), n, &g_T, &g_K};
-  uint32_t nseg = (n + seg_len - 1) / seg_len;
-  // phase 1: per-segment transition functions, then entry states
-  std::vector<uint32_t> fn(nseg);
-  for (uint32_t g = 0; g < nseg; g++) {
-    uint32_t seg = g * seg_len, end = std::min(seg + seg_len, n);
-    uint8_t prev, esc;
-    entry_esc(e, seg, prev, esc);
+  const uint32_t blk_len = seg_len;  // bytes per warp on the device (32 windows = 1024 there)
+  const uint32_t nblk = (n + blk_len - 1) / blk_len, nwin = (n + 31) / 32;
+  // phase 1: per-window transition functions -> per-block functions -> block entry states
+  std::vector<uint32_t> wfn(nwin), bfn(nblk);
+  for (uint32_t g = 0; g < nblk; g++) {
     uint32_t run = NUTDB_VEC8_ID;
-    for (uint32_t base = seg; base < end; base += 32) {
-      uint8_t b[32];
-      uint16_t k[32];
-      Win w;
-      build_win(e, base, b, k, w);
-      w.bnd = e.bitmap[base >> 5] & w.valid;  // the function kernel does not add the virtual end
-      w.L = w.D = w.DOT = w.OP = 0;
-      uint32_t escm = esc_ballot(w, esc);
-      Events ev = make_events(w, escm, prev);
-      if (ev.all) run = ctx_window_fn(g_T, w, ev, run);
-      else run = vec8_then_row(run, g_T.a_row[EV_OTHER][0], g_T.a_row[EV_OTHER][1]);
-      esc = esc_carry_out(w.bs, esc);
-      prev = b[31];
+    for (uint32_t base = g * blk_len; base < std::min((g + 1) * blk_len, n); base += 32) {
+      WinSetup u;
+      setup_window(e, g * blk_len, base, false, u);
+      wfn[base >> 5] = window_fn(g_T, u);
+      run = vec8_then(run, wfn[base >> 5]);
     }
-    fn[g] = run;
+    bfn[g] = run;
   }
-  std::vector<uint8_t> entA(nseg);
+  std::vector<uint8_t> entA(nblk);
   uint32_t pref = NUTDB_VEC8_ID;
-  for (uint32_t g = 0; g < nseg; g++) {
+  for (uint32_t g = 0; g < nblk; g++) {
     entA[g] = (uint8_t)vec8_apply(pref, A_C);
-    pref = vec8_then(pref, fn[g]);
+    pref = vec8_then(pref, bfn[g]);
   }
-  // phase 2: counts + flags
+  // phase 2 (count + flags) and phase 3 (emit): identical per-window work, carries passed along
   std::vector<uint8_t> flag(nstmt + 1, 0);
   std::vector<uint32_t> list;
   Out out{tok_type, tok_start, tok_end, tok_kw, 0, stmt_tok_begin, stmt_tok_end, offs, nstmt, &flag, &list};
-  std::vector<CSum> sums(nseg), pre(nseg);
-  CSum zero = csum_identity();
-  for (uint32_t g = 0; g < nseg; g++) sums[g] = walk_segment<false>(e, g * seg_len, seg_len, entA[g], zero, out);
-  CSum run = csum_identity();
-  for (uint32_t g = 0; g < nseg; g++) {
-    pre[g] = run;
-    run = csum_then(run, sums[g]);
-  }
-  uint32_t ntok_main = run.count;
-  // consistency of the scanned context states with a plain sequential walk (checks ctx_window_fn against ctx_window)
-  {
-    uint8_t s = A_C;
-    for (uint32_t g = 0; g < nseg; g++) {
-      if (s != entA[g]) return -2;
-      s = (uint8_t)vec8_apply(fn[g], s);
+  HSrc src{e};
+  std::vector<uint8_t> wcount(nwin);
+  uint32_t ntok_main = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    uint32_t count = 0, stmt_start = 0;
+    StrCarry sc;
+    Hist hprev;
+    if (pass == 1) {
+      if ((uint64_t)ntok_main > cap) return -1;
+      out.cap = ntok_main;
+    }
+    for (uint32_t g = 0; g < nblk; g++) {
+      uint8_t s = entA[g];
+      const uint32_t blk = g * blk_len;
+      for (uint32_t base = blk; base < std::min(blk + blk_len, n); base += 32) {
+        WinSetup u;
+        setup_window(e, blk, base, true, u);
+        WinCtx o;
+        ctx_window(u.w, u.ev, base, u.nx, s, u.prev_byte, o);
+        o.escm = u.escm;
+        // the symbolic function (phase 1) and the concrete walk must agree
+        // (not in the window holding the batch end: only the concrete walk sees the virtual statement start there)
+        if (base + 32 <= n && (uint8_t)vec8_apply(wfn[base >> 5], s) != o.s_out) return -2;
+        Hist h;
+        if (base == blk) {  // lane 0: raw classes of the 32 bytes in front of the block if it is entered in code
+          if (blk >= 32) {
+            if (entA[g] <= A_CX)
+              for (int lane = 0; lane < 32; lane++) {
+                uint16_t k = e.K->cls[e.byte(blk - 32 + lane)];
+                uint32_t bit = 1u << lane;
+                if (k & K_L) h.L |= bit;
+                if (k & K_D) h.D |= bit;
+                if (k & K_DOT) h.DOT |= bit;
+                if (k & K_OP) h.OP |= bit;
+              }
+            h.bnd = e.bitmap[(blk - 32) >> 5];
+          }
+        } else {
+          h = hprev;
+        }
+        uint32_t bad = 0;
+        if (pass == 0) {
+          StrCarry none;
+          uint32_t nt = win_tokens<false>(g_T, g_K, src, out, u.w, o, h, u.nx, base, u.prev_byte, none, 0u, 0u, bad);
+          if (u.w.bs == 0xFFFFFFFFu) bad |= 1u;
+          wcount[base >> 5] = (uint8_t)nt;
+          for (int i = 0; i < 32; i++) {
+            if ((bad >> i) & 1u) out.punt(base + i);
+            if ((o.bad_prev >> i) & 1u) out.punt(base + i - 1);
+          }
+          if (base + 32 == n && (o.s_out == A_SQ || o.s_out == A_DQ || o.s_out == A_BT || o.s_out == A_BC0 || o.s_out == A_BC))
+            out.punt(n - 1);
+          count += nt;
+        } else {
+          uint32_t nt = win_tokens<true>(g_T, g_K, src, out, u.w, o, h, u.nx, base, u.prev_byte, sc, stmt_start, count, bad);
+          if (nt != wcount[base >> 5]) return -3;
+          count += nt;
+        }
+        sc = str_then(sc, o.sc);
+        if (o.last_bnd1) stmt_start = o.last_bnd1 - 1;
+        hprev.L = u.w.L & o.ct;
+        hprev.D = u.w.D & o.ct;
+        hprev.DOT = u.w.DOT & o.ct;
+        hprev.OP = u.w.OP & o.ct;
+        hprev.bnd = u.w.bnd;
+        s = o.s_out;
+      }
+    }
+    if (pass == 0) {
+      ntok_main = count;
+      // exact path: counts of flagged statements (needed before the token arrays can be sized)
+      g_xoff.assign(list.size() + 1, 0);
+      for (size_t i = 0; i < list.size(); i++) {
+        uint32_t st = list[i];
+        StmtSrc ssrc{text, (uint32_t)(offs[st] - offs[0]), (uint32_t)(offs[st + 1] - offs[0])};
+        ExactSink sink{nullptr, nullptr, nullptr, nullptr, 0};
+        LexCarry c;
+        c.stmt_start = ssrc.begin;
+        c.tok_start = ssrc.begin;
+        Walker<false, StmtSrc, ExactSink> w(g_T, ssrc, sink, c);
+        w.counting = true;
+        for (uint32_t pos = ssrc.begin; pos < ssrc.end; pos++) w.step(pos, ssrc.byte(pos), pos == ssrc.begin, true);
+        w.flush_eof(ssrc.end);
+        g_xoff[i + 1] = g_xoff[i] + w.c.count;
+      }
+      if ((uint64_t)ntok_main + g_xoff[list.size()] > cap) return -1;
     }
   }
-  g_punts += list.size();
-  // exact path: counts of flagged statements
-  std::vector<uint32_t> xoff(list.size() + 1, 0);
-  for (size_t i = 0; i < list.size(); i++) {
-    uint32_t s = list[i];
-    StmtSrc src{text, (uint32_t)(offs[s] - offs[0]), (uint32_t)(offs[s + 1] - offs[0])};
-    ExactSink sink{nullptr, nullptr, nullptr, nullptr, 0};
-    LexCarry c;
-    c.stmt_start = src.begin;
-    c.tok_start = src.begin;
-    Walker<false, StmtSrc, ExactSink> w(g_T, src, sink, c);
-    w.counting = true;
-    for (uint32_t pos = src.begin; pos < src.end; pos++) w.step(pos, src.byte(pos), pos == src.begin, true);
-    w.flush_eof(src.end);
-    xoff[i + 1] = xoff[i] + w.c.count;
-  }
-  uint64_t ntok = (uint64_t)ntok_main + xoff[list.size()];
-  if (ntok > cap) return -1;
-  // phase 3: emit
-  out.cap = ntok_main;
-  for (uint32_t g = 0; g < nseg; g++) walk_segment<true>(e, g * seg_len, seg_len, entA[g], pre[g], out);
   if (out.overflow) return -1;
+  std::vector<uint32_t>& xoff = g_xoff;
+  uint64_t ntok = (uint64_t)ntok_main + xoff[list.size()];
+  g_punts += list.size();
   for (size_t i = 0; i < list.size(); i++) {
     uint32_t s = list[i];
     StmtSrc src{text, (uint32_t)(offs[s] - offs[0]), (uint32_t)(offs[s + 1] - offs[0])};
