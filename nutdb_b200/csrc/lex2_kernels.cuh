@@ -67,7 +67,7 @@ __device__ __forceinline__ void build_masks(const Lex2Shared& S, const Tile2Src&
 #pragma unroll 4
   for (int jj = 0; jj < 32; jj++) {
     const uint32_t pos = blk + 32u * (uint32_t)jj + (uint32_t)lane;
-    const uint16_t k = pos < n ? S.K.cls[src.byte(pos)] : (uint16_t)0;
+    const uint16_t k = pos < n ? S.K.cls[src.sm[pos - src.tile_begin]] : (uint16_t)0;  // always inside the tile
     const bool mine = lane == jj;
     uint32_t m;
     m = __ballot_sync(full, k & nlex2::K_SQ); if (mine) w.sq = m;
@@ -106,6 +106,41 @@ __device__ __forceinline__ void entry_esc(const Tile2Src& src, const uint32_t* b
   esc = (uint8_t)(nrun & 1u);
 }
 
+// class masks of every window, computed once by k_lex2_fn: 14 arrays of nwin words (structure of arrays)
+#define L2_NMASK 14
+__device__ __forceinline__ void store_masks(uint32_t* __restrict__ g, size_t stride, uint32_t win, const nlex2::Win& w) {
+  g[0 * stride + win] = w.sq;
+  g[1 * stride + win] = w.dq;
+  g[2 * stride + win] = w.bt;
+  g[3 * stride + win] = w.nl;
+  g[4 * stride + win] = w.bs;
+  g[5 * stride + win] = w.dash;
+  g[6 * stride + win] = w.slash;
+  g[7 * stride + win] = w.star;
+  g[8 * stride + win] = w.L;
+  g[9 * stride + win] = w.D;
+  g[10 * stride + win] = w.DOT;
+  g[11 * stride + win] = w.OP;
+  g[12 * stride + win] = w.P;
+  g[13 * stride + win] = w.WS;
+}
+__device__ __forceinline__ void load_masks(const uint32_t* __restrict__ g, size_t stride, uint32_t win, nlex2::Win& w) {
+  w.sq = g[0 * stride + win];
+  w.dq = g[1 * stride + win];
+  w.bt = g[2 * stride + win];
+  w.nl = g[3 * stride + win];
+  w.bs = g[4 * stride + win];
+  w.dash = g[5 * stride + win];
+  w.slash = g[6 * stride + win];
+  w.star = g[7 * stride + win];
+  w.L = g[8 * stride + win];
+  w.D = g[9 * stride + win];
+  w.DOT = g[10 * stride + win];
+  w.OP = g[11 * stride + win];
+  w.P = g[12 * stride + win];
+  w.WS = g[13 * stride + win];
+}
+
 struct WinSetup {
   nlex2::Win w;
   nlex2::Next nx;
@@ -115,12 +150,18 @@ struct WinSetup {
 };
 
 // everything a thread knows about its window before any carry: masks, neighbours, escapes, events
-template <bool All, bool Virt>
+template <bool Build, bool Virt>
 __device__ __forceinline__ void setup_window(const Lex2Shared& S, const Tile2Src& src, const uint32_t* bitmap,
-                                             uint32_t tile_begin, uint32_t blk, uint32_t n, int lane, WinSetup& u) {
+                                             uint32_t tile_begin, uint32_t blk, uint32_t n, int lane, uint32_t* gmask,
+                                             size_t mstride, WinSetup& u) {
   const uint32_t full = 0xFFFFFFFFu;
-  build_masks<All>(S, src, blk, n, lane, u.w);
   u.base = blk + 32u * (uint32_t)lane;
+  if (Build) {
+    build_masks<true>(S, src, blk, n, lane, u.w);
+    store_masks(gmask, mstride, u.base >> 5, u.w);
+  } else {
+    load_masks(gmask, mstride, u.base >> 5, u.w);
+  }
   nlex2::Win& w = u.w;
   w.valid = u.base + 32u <= n ? full : (n > u.base ? ((1u << (n - u.base)) - 1u) : 0u);
   uint32_t bnd = u.base < n ? (bnd_word(S, bitmap, tile_begin, u.base) & w.valid) : 0u;
@@ -172,7 +213,8 @@ __device__ __forceinline__ uint32_t window_fn(const LexTables& T, const WinSetup
 __global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
                                                         uint32_t n, const LexTables* __restrict__ gT,
                                                         const nlex2::Lex2Tables* __restrict__ gK,
-                                                        uint32_t* __restrict__ localA, uint32_t* __restrict__ tileA) {
+                                                        uint32_t* __restrict__ localA, uint32_t* __restrict__ tileA,
+                                                        uint32_t* __restrict__ gmask, size_t mstride) {
   __shared__ Lex2Shared S;
   __shared__ uint32_t wfn[L2_WARPS];
   const uint32_t tile_begin = blockIdx.x * L2_TILE;
@@ -184,7 +226,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restric
   uint32_t run = NUTDB_VEC8_ID;
   if (blk < n) {
     WinSetup u;
-    setup_window<false, false>(S, src, bitmap, tile_begin, blk, n, lane, u);
+    setup_window<true, false>(S, src, bitmap, tile_begin, blk, n, lane, gmask, mstride, u);
     const uint32_t f = u.base < n ? window_fn(S.T, u) : NUTDB_VEC8_ID;
     uint32_t excl;
     run = __shfl_sync(0xFFFFFFFFu, warp_scan_vec8(f, lane, excl), 31);
@@ -249,7 +291,8 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
                                                           const uint32_t* __restrict__ localA,
                                                           const uint8_t* __restrict__ tileEntA, uint4* __restrict__ localC,
                                                           uint4* __restrict__ tileC, const uint4* __restrict__ tilePrefC,
-                                                          uint8_t* __restrict__ wcount, Lex2Out out) {
+                                                          uint8_t* __restrict__ wcount, uint32_t* __restrict__ gmask,
+                                                          size_t mstride, Lex2Out out) {
   __shared__ Lex2Shared S;
   __shared__ uint4 wsum[L2_WARPS];
   const uint32_t tile_begin = blockIdx.x * L2_TILE;
@@ -263,7 +306,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
   CSum wtotal = csum_identity();
   if (blk < n) {
     WinSetup u;
-    setup_window<true, true>(S, src, bitmap, tile_begin, blk, n, lane, u);
+    setup_window<false, true>(S, src, bitmap, tile_begin, blk, n, lane, gmask, mstride, u);
     const bool live = u.base < n;
     // entry state of every window: scan of the window functions on top of the warp's entry state
     const uint32_t f = live ? window_fn(S.T, u) : NUTDB_VEC8_ID;

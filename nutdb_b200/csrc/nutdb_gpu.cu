@@ -392,6 +392,9 @@ struct DTok {
   const uint8_t* kwp;
   uint32_t n;
   __device__ __forceinline__ uint8_t type(uint32_t i) const { return i < n ? ty[i] : (uint8_t)NUTDB_TT_EOF; }
+  // the current token of a parser never lies beyond the statement's EOF token: no bounds check
+  __device__ __forceinline__ uint8_t type_at(uint32_t i) const { return ty[i]; }
+  __device__ __forceinline__ uint8_t kw_at(uint32_t i) const { return kwp[i]; }
   __device__ __forceinline__ uint8_t kw(uint32_t i) const { return i < n ? kwp[i] : (uint8_t)0; }
   __device__ __forceinline__ uint32_t start(uint32_t i) const { return i < n ? st[i] : 0u; }
   __device__ __forceinline__ uint32_t end(uint32_t i) const { return i < n ? en[i] : 0u; }
@@ -707,7 +710,7 @@ struct NutdbCtx {
   // device buffers (grow only)
   DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount;
+      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
   float ms[5] = {0, 0, 0, 0, 0};
@@ -814,7 +817,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount};
+                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
   HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
@@ -1028,16 +1031,19 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(entA, ntiles);
     ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
     ENSURE_DEV(winCount, (size_t)ntiles * (L2_TILE / 32) + 16);
+    const size_t mstride = (size_t)ntiles * (L2_TILE / 32);
+    ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
     Lex2Out lo{nullptr, nullptr, nullptr, nullptr, 0, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
                (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->puntList.p, dS + 3};
     LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2,
-                                                                  (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p));
+                                                                  (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p,
+                                                                  (uint32_t*)ctx->winMasks.p, mstride));
     LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
     LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
                                dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                                (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr,
-                               (uint8_t*)ctx->winCount.p, lo));
+                               (uint8_t*)ctx->winCount.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
     LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p,
                                                                         ntiles, (uint4*)(dS + 4)));
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
@@ -1079,7 +1085,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p,
-                              (uint8_t*)ctx->winCount.p, lo));
+                              (uint8_t*)ctx->winCount.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
     if (npunt > 0) {
       xs = ExactSink{lo.type, lo.start, lo.end, lo.kw, ntok};
       LAUNCH("k_lex_exact_emit", k_lex_exact<true><<<(npunt + 127) / 128, 128, 0, st>>>(

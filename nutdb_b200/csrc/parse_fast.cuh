@@ -32,6 +32,7 @@ struct FastParser {
   Nodes& nd;
   Text& text;
   uint32_t t = 0, n = 0, cap;
+  uint8_t ty = 0, kw = 0;  // the current token (index t), held in registers
   // the operand being built (right-most subtree)
   uint32_t cur_start = 0;
   uint8_t cur_kind = 0;
@@ -41,41 +42,61 @@ struct FastParser {
   uint32_t einfo[DEPTH];   // type | power << 2 | op << 6 | left kind << 12 | item count << 20
   uint32_t emark[DEPTH];   // E_OP: start of the left operand; brackets: node count at the opening
   uint32_t sp = 0;
+  // where the expression being parsed sits in its statement (one shared expression loop: lanes of a
+  // warp that are in different clauses still execute the same code)
+  enum : uint8_t { C_SEL_ITEM, C_WHERE, C_GROUP_ITEM, C_HAVING, C_ORDER_ITEM, C_INS_VALUE, C_COL_DEFAULT, C_TBL_PK_ITEM,
+                   C_TBL_ORDER_ITEM, C_TBL_PART };
+  enum : uint32_t { R_BAIL = 0, R_EXPR = 1, R_DONE = 2 };
+  uint8_t ctx = 0;
+  uint32_t m0 = 0, m1 = 0;          // open interior nodes: outer (ROWS / COLDEF) and inner (clause / ROW / attribute)
+  uint32_t width = 0, w = 0, row = 0, seen = 0, tseen = 0, aux = 0;
 
   NUTDB_HD FastParser(Tok& tk, Nodes& nodes, Text& tx) : tok(tk), nd(nodes), text(tx), cap(nodes.capacity()) {}
 
-  NUTDB_HD bool emit(uint8_t kind, uint8_t sub, uint16_t aux, uint32_t x) {
+  NUTDB_HD void load() {
+    ty = tok.type_at(t);
+    kw = tok.kw_at(t);
+  }
+  NUTDB_HD void adv() {
+    t++;
+    load();
+  }
+  NUTDB_HD void adv(uint32_t k) {
+    t += k;
+    load();
+  }
+  NUTDB_HD bool emit(uint8_t kind, uint8_t sub, uint16_t ax, uint32_t x) {
     if (n >= cap) return false;
     CNode c;
     c.kind = kind;
     c.sub = sub;
-    c.aux = aux;
+    c.aux = ax;
     c.x = x;
     nd.set(n++, c);
     return true;
   }
   NUTDB_HD static bool is_literal(uint8_t kind) { return kind >= NUTDB_NK_LIT_INT && kind <= NUTDB_NK_LIT_INTERVAL; }
-  NUTDB_HD bool is_kw(uint32_t i, uint32_t kw) { return tok.type(i) == NUTDB_TT_KeywordOrIdentifier && tok.kw(i) == kw; }
-  NUTDB_HD static bool ident_string(uint8_t ty) {  // must_parse_identifier_string (mod.rs:1682)
-    return ty == NUTDB_TT_KeywordOrIdentifier || ty == NUTDB_TT_DelimitedIdentifier;
+  NUTDB_HD bool is_kw(uint32_t k) const { return ty == NUTDB_TT_KeywordOrIdentifier && kw == k; }
+  NUTDB_HD bool next_is_kw(uint32_t d, uint32_t k) { return tok.type(t + d) == NUTDB_TT_KeywordOrIdentifier && tok.kw(t + d) == k; }
+  NUTDB_HD static bool ident_string(uint8_t y) {  // must_parse_identifier_string (mod.rs:1682)
+    return y == NUTDB_TT_KeywordOrIdentifier || y == NUTDB_TT_DelimitedIdentifier;
   }
   // integer_from_str! cannot fail for 1..safe digits; the lexer stores min(len, 255) in the kw byte
-  NUTDB_HD bool int_ok(uint32_t i, uint32_t width) {
-    const bool hex = tok.type(i) == NUTDB_TT_HexLiteral;
-    const uint32_t len = tok.kw(i);
-    const uint32_t safe = width == 0 ? 2u : width == 1 ? (hex ? 16u : 19u) : (hex ? 32u : 38u);
+  NUTDB_HD static bool int_ok(uint8_t y, uint32_t len, uint32_t width_) {
+    const bool hex = y == NUTDB_TT_HexLiteral;
+    const uint32_t safe = width_ == 0 ? 2u : width_ == 1 ? (hex ? 16u : 19u) : (hex ? 32u : 38u);
     return len >= 1 && len <= safe;
   }
   // an escaped string literal can only be rejected through a backslash-u escape (literal.rs:70-88)
-  NUTDB_HD bool string_ok(uint32_t i) {
-    if (tok.type(i) == NUTDB_TT_RawStringLiteral) return true;
+  NUTDB_HD bool string_ok(uint32_t i, uint8_t y) {
+    if (y == NUTDB_TT_RawStringLiteral) return true;
     const uint32_t s = tok.start(i), e = tok.end(i);
     for (uint32_t p = s; p + 1 < e; p++)
       if (text.byte(p) == '\\' && text.byte(p + 1) == 'u') return false;
     return true;
   }
-  NUTDB_HD static uint8_t str_sub(uint8_t ty) {
-    return ty == NUTDB_TT_RawStringLiteral ? 0 : (ty == NUTDB_TT_EscapedSQStringLiteral ? 1 : 2);
+  NUTDB_HD static uint8_t str_sub(uint8_t y) {
+    return y == NUTDB_TT_RawStringLiteral ? 0 : (y == NUTDB_TT_EscapedSQStringLiteral ? 1 : 2);
   }
 
   // pops the top E_OP entry: BinaryOp{op, left, right}; refuses whatever simplify.rs would fold
@@ -93,27 +114,25 @@ struct FastParser {
     return emit(NUTDB_NK_BINARY, (uint8_t)op, 0, cur_start);
   }
 
-  // must_parse_expr (mod.rs:1205): on success the expression's subtree is [cur_start, n)
+  // must_parse_expr (mod.rs:1205): on success the expression's subtree is [cur_start, n) and (ty, kw) is the
+  // token that ended it.  There is exactly ONE call site (try_parse).
   NUTDB_HD bool expr() {
-    const uint32_t base = sp;
     for (;;) {
       // ---------------- operand: must_parse_expr_prefix (mod.rs:1222-1347) ----------------
-      const uint8_t ty = tok.type(t);
       switch (ty) {
         case NUTDB_TT_KeywordOrIdentifier: {
-          const uint32_t kw = tok.kw(t);
           if (kw == KW_TRUE || kw == KW_FALSE) {
             cur_start = n;
             cur_kind = NUTDB_NK_LIT_BOOL;
             if (!emit(NUTDB_NK_LIT_BOOL, kw == KW_TRUE ? 1 : 0, 0, NUTDB_CN_NOTOK)) return false;
-            t++;
+            adv();
             break;
           }
           if (kw == KW_NULL) {
             cur_start = n;
             cur_kind = NUTDB_NK_LIT_NULL;
             if (!emit(NUTDB_NK_LIT_NULL, 0, 0, NUTDB_CN_NOTOK)) return false;
-            t++;
+            adv();
             break;
           }
           if (kw == KW_NOT || kw == KW_INTERVAL || kw == KW_IF || kw == KW_CASE) return false;
@@ -128,32 +147,38 @@ struct FastParser {
               if (!emit(NUTDB_NK_FNCALL, 7, 0, m)) return false;
               cur_start = m;
               cur_kind = NUTDB_NK_FNCALL;
-              t += 3;
+              adv(3);
               break;
             }
             if (sp >= DEPTH) return false;
             einfo[sp] = E_CALL;
             emark[sp] = m;
             sp++;
-            t += 2;
+            adv(2);
             continue;  // first argument
           }
-          // fallthrough to the identifier forms
+          if (ty2 == NUTDB_TT_Dot) goto qualified;
+          cur_start = n;
+          cur_kind = NUTDB_NK_IDENT;
+          if (!emit(NUTDB_NK_IDENT, 0, 0, t)) return false;
+          adv();
+          break;
         }
         case NUTDB_TT_DelimitedIdentifier: {  // must_parse_identifier_based_prefix (mod.rs:1506-1523)
           if (tok.type(t + 1) == NUTDB_TT_Dot) {
+          qualified:
             const uint8_t ty3 = tok.type(t + 2);
             if (!(ident_string(ty3) || ty3 == NUTDB_TT_Mul)) return false;
             cur_start = n;
             cur_kind = NUTDB_NK_IDENT;
             if (!emit(NUTDB_NK_QUAL, 0, 0, t)) return false;
             if (!emit(NUTDB_NK_IDENT, ty3 == NUTDB_TT_Mul ? 1 : 0, 1, t + 2)) return false;
-            t += 3;
+            adv(3);
           } else {
             cur_start = n;
             cur_kind = NUTDB_NK_IDENT;
             if (!emit(NUTDB_NK_IDENT, 0, 0, t)) return false;
-            t++;
+            adv();
           }
           break;
         }
@@ -161,30 +186,30 @@ struct FastParser {
           cur_start = n;
           cur_kind = NUTDB_NK_IDENT;
           if (!emit(NUTDB_NK_IDENT, 1, 0, t)) return false;
-          t++;
+          adv();
           break;
         case NUTDB_TT_RawStringLiteral:
         case NUTDB_TT_EscapedSQStringLiteral:
         case NUTDB_TT_EscapedDQStringLiteral:
-          if (!string_ok(t)) return false;
+          if (!string_ok(t, ty)) return false;
           cur_start = n;
           cur_kind = NUTDB_NK_LIT_STR;
           if (!emit(NUTDB_NK_LIT_STR, str_sub(ty), 0, t)) return false;
-          t++;
+          adv();
           break;
         case NUTDB_TT_FloatLiteral:
           cur_start = n;
           cur_kind = NUTDB_NK_LIT_FLOAT;
           if (!emit(NUTDB_NK_LIT_FLOAT, 0, 0, t)) return false;
-          t++;
+          adv();
           break;
         case NUTDB_TT_IntegerLiteral:
         case NUTDB_TT_HexLiteral:
-          if (!int_ok(t, 2)) return false;
+          if (!int_ok(ty, kw, 2)) return false;
           cur_start = n;
           cur_kind = NUTDB_NK_LIT_INT;
           if (!emit(NUTDB_NK_LIT_INT, 0, ty == NUTDB_TT_HexLiteral ? 1 : 0, t)) return false;
-          t++;
+          adv();
           break;
         case NUTDB_TT_Minus: {  // only a literal may follow (mod.rs:1259-1269)
           const uint8_t ty2 = tok.type(t + 1);
@@ -193,35 +218,33 @@ struct FastParser {
             cur_kind = NUTDB_NK_LIT_FLOAT;
             if (!emit(NUTDB_NK_LIT_FLOAT, 1, 0, t + 1)) return false;
           } else if (ty2 == NUTDB_TT_IntegerLiteral || ty2 == NUTDB_TT_HexLiteral) {
-            if (!int_ok(t + 1, 2)) return false;
+            if (!int_ok(ty2, tok.kw(t + 1), 2)) return false;
             cur_kind = NUTDB_NK_LIT_INT;
             if (!emit(NUTDB_NK_LIT_INT, 1, ty2 == NUTDB_TT_HexLiteral ? 1 : 0, t + 1)) return false;
           } else {
             return false;
           }
-          t += 2;
+          adv(2);
           break;
         }
         case NUTDB_TT_Plus:  // prefix plus is dropped (mod.rs:1270)
-          t++;
+          adv();
           continue;
         case NUTDB_TT_LParen: {  // (mod.rs:1229-1246); a subquery goes to the automaton
-          if (tok.type(t + 1) == NUTDB_TT_KeywordOrIdentifier && (tok.kw(t + 1) == KW_SELECT || tok.kw(t + 1) == KW_WITH))
-            return false;
+          if (next_is_kw(1, KW_SELECT) || next_is_kw(1, KW_WITH)) return false;
           if (sp >= DEPTH) return false;
           einfo[sp] = E_PAREN;
           emark[sp] = n;
           sp++;
-          t++;
+          adv();
           continue;
         }
         default: return false;
       }
       // ---------------- operators: token_power (mod.rs:1895-1927) + must_parse_expr_infix ----------------
       for (;;) {
-        const uint8_t oy = tok.type(t);
         uint32_t power = P_Terminator, op = 0;
-        switch (oy) {
+        switch (ty) {
           case NUTDB_TT_Eq: power = P_Comparison; op = 9; break;
           case NUTDB_TT_NotEq: power = P_Comparison; op = 10; break;
           case NUTDB_TT_Gt: power = P_Comparison; op = 5; break;
@@ -240,7 +263,7 @@ struct FastParser {
           case NUTDB_TT_Mod: power = P_MulDivMod; op = 4; break;
           case NUTDB_TT_LBracket: return false;  // index access
           case NUTDB_TT_KeywordOrIdentifier:
-            switch (tok.kw(t)) {
+            switch (kw) {
               case KW_AND: power = P_And; op = 11; break;
               case KW_OR: power = P_Or; op = 12; break;
               case KW_XOR: power = P_Xor; op = 13; break;
@@ -254,29 +277,29 @@ struct FastParser {
           default: break;
         }
         // everything of equal or higher power on the stack is complete (left-associative)
-        while (sp > base && (einfo[sp - 1] & 3u) == E_OP && ((einfo[sp - 1] >> 2) & 15u) >= power)
+        while (sp > 0 && (einfo[sp - 1] & 3u) == E_OP && ((einfo[sp - 1] >> 2) & 15u) >= power)
           if (!reduce()) return false;
         if (power != P_Terminator) {
           if (sp >= DEPTH) return false;
           einfo[sp] = E_OP | (power << 2) | (op << 6) | ((uint32_t)cur_kind << 12);
           emark[sp] = cur_start;
           sp++;
-          t++;
+          adv();
           break;  // right operand
         }
-        if (sp == base) return true;  // the expression is complete
+        if (sp == 0) return true;  // the expression is complete
         // inside brackets opened by this expression
         const uint32_t btype = einfo[sp - 1] & 3u;
-        if (oy == NUTDB_TT_Comma) {
+        if (ty == NUTDB_TT_Comma) {
           einfo[sp - 1] += 1u << 20;
-          t++;
+          adv();
           break;  // next item
         }
-        if (oy != NUTDB_TT_RParen) return false;
+        if (ty != NUTDB_TT_RParen) return false;
         const uint32_t items = (einfo[sp - 1] >> 20) + 1u;
         const uint32_t m = emark[sp - 1];
         sp--;
-        t++;
+        adv();
         if (btype == E_CALL) {
           if (!emit(NUTDB_NK_FNCALL, 7, 0, m)) return false;
           cur_start = m;
@@ -290,212 +313,149 @@ struct FastParser {
     }
   }
 
-  // must_parse_query_expr (mod.rs:571-579): expr [AS name]
-  NUTDB_HD bool query_expr() {
-    if (!expr()) return false;
-    if (is_kw(t, KW_AS)) {
+  NUTDB_HD bool alias() {  // [AS name] (mod.rs:563-578)
+    if (is_kw(KW_AS)) {
       if (!ident_string(tok.type(t + 1))) return false;
       if (!emit(NUTDB_NK_ALIAS, 0, 0, t + 1)) return false;
-      t += 2;
+      adv(2);
     }
     return true;
   }
-  NUTDB_HD bool query_expr_list() {
-    for (;;) {
-      if (!query_expr()) return false;
-      if (tok.type(t) != NUTDB_TT_Comma) return true;
-      t++;
-    }
-  }
-  NUTDB_HD bool expr_list() {
-    for (;;) {
-      if (!expr()) return false;
-      if (tok.type(t) != NUTDB_TT_Comma) return true;
-      t++;
-    }
-  }
-  NUTDB_HD bool int_literal(uint32_t width) {  // must_parse_integer_literal (mod.rs:1815) -> NK_NUM
-    const uint8_t ty = tok.type(t);
+  NUTDB_HD bool int_literal(uint32_t width_) {  // must_parse_integer_literal (mod.rs:1815) -> NK_NUM
     if (ty != NUTDB_TT_IntegerLiteral && ty != NUTDB_TT_HexLiteral) return false;
-    if (!int_ok(t, width)) return false;
+    if (!int_ok(ty, kw, width_)) return false;
     if (!emit(NUTDB_NK_NUM, 0, ty == NUTDB_TT_HexLiteral ? 1 : 0, t)) return false;
-    t++;
+    adv();
     return true;
   }
   NUTDB_HD bool string_literal() {  // must_parse_string_literal (mod.rs:1833) -> NK_STR
-    const uint8_t ty = tok.type(t);
     if (ty != NUTDB_TT_RawStringLiteral && ty != NUTDB_TT_EscapedSQStringLiteral && ty != NUTDB_TT_EscapedDQStringLiteral)
       return false;
-    if (!string_ok(t)) return false;
+    if (!string_ok(t, ty)) return false;
     if (!emit(NUTDB_NK_STR, str_sub(ty), 0, t)) return false;
-    t++;
+    adv();
     return true;
   }
 
-  // try_parse_select_stmt / must_parse_query_body (mod.rs:190-203, :279-325); t is after SELECT
-  NUTDB_HD bool select_stmt() {
-    if (is_kw(t, KW_DISTINCT)) return false;
-    const uint32_t body = n;
-    if (!query_expr_list()) return false;
-    if (!emit(NUTDB_NK_COLS, 0, 0, body)) return false;
-    if (is_kw(t, KW_FROM)) {  // must_parse_query_source (mod.rs:546-569): a plain table name here
-      t++;
+  // ---- SELECT (mod.rs:190-203, :279-544): what may follow once clause number `stage` is done ----
+  // stages: 1 WHERE, 2 GROUP BY, 3 HAVING, 4 ORDER BY, 5 LIMIT, then the end of the body
+  NUTDB_HD uint32_t select_advance(uint32_t stage) {
+    if (stage <= 1 && is_kw(KW_WHERE)) {
+      adv();
+      m1 = n;
+      ctx = C_WHERE;
+      return R_EXPR;
+    }
+    if (stage <= 2 && is_kw(KW_GROUP)) {
+      if (!next_is_kw(1, KW_BY)) return R_BAIL;
+      adv(2);
+      m1 = n;
+      ctx = C_GROUP_ITEM;
+      return R_EXPR;
+    }
+    if (stage <= 3 && is_kw(KW_HAVING)) {
+      adv();
+      m1 = n;
+      ctx = C_HAVING;
+      return R_EXPR;
+    }
+    if (stage <= 4 && is_kw(KW_ORDER)) {
+      if (!next_is_kw(1, KW_BY)) return R_BAIL;
+      adv(2);
+      m1 = n;
+      ctx = C_ORDER_ITEM;
+      return R_EXPR;
+    }
+    if (is_kw(KW_LIMIT)) {  // mod.rs:503-544
+      adv();
       const uint32_t m = n;
-      const uint8_t ty = tok.type(t);
-      if (!ident_string(ty)) return false;
+      uint32_t sub = 0, ax = 0;
+      if (!int_literal(1)) return R_BAIL;
+      if (ty == NUTDB_TT_Comma) {
+        adv();
+        sub = 1;
+        if (!int_literal(1)) return R_BAIL;
+      } else if (is_kw(KW_OFFSET)) {
+        adv();
+        sub = 2;
+        if (!int_literal(1)) return R_BAIL;
+      }
+      if (is_kw(KW_WITH)) {
+        if (!next_is_kw(1, KW_TIES)) return R_BAIL;
+        adv(2);
+        ax = 1;
+      }
+      if (!emit(NUTDB_NK_LIMIT, (uint8_t)sub, (uint16_t)ax, m)) return R_BAIL;
+    }
+    if (!emit(NUTDB_NK_QUERY_BODY, 0, 0, 0)) return R_BAIL;
+    if (ty == NUTDB_TT_KeywordOrIdentifier && (kw == KW_UNION || kw == KW_INTERSECT || kw == KW_EXCEPT))
+      return R_BAIL;  // set operations (mod.rs:250-267)
+    return emit(NUTDB_NK_STMT_SELECT, 0, 0, 0) ? R_DONE : R_BAIL;
+  }
+  // the select list is complete: [FROM name [AS a]] (must_parse_query_source, mod.rs:546-569: a plain table name here)
+  NUTDB_HD uint32_t select_after_items() {
+    if (!emit(NUTDB_NK_COLS, 0, 0, 0)) return R_BAIL;
+    if (is_kw(KW_FROM)) {
+      adv();
+      const uint32_t m = n;
+      if (!ident_string(ty)) return R_BAIL;
       if (ty == NUTDB_TT_KeywordOrIdentifier) {
-        const uint32_t kw = tok.kw(t);
         if (kw == KW_TRUE || kw == KW_FALSE || kw == KW_NULL || kw == KW_NOT || kw == KW_INTERVAL || kw == KW_IF ||
             kw == KW_CASE)
-          return false;
+          return R_BAIL;
+        if (tok.type(t + 1) == NUTDB_TT_LParen) return R_BAIL;  // table function
       }
-      if (!expr()) return false;
-      if (cur_kind != NUTDB_NK_IDENT || cur_start != m || n != m + 1) return false;  // only `name`
-      if (is_kw(t, KW_AS)) {
-        if (!ident_string(tok.type(t + 1))) return false;
-        if (!emit(NUTDB_NK_ALIAS, 0, 0, t + 1)) return false;
-        t += 2;
+      if (tok.type(t + 1) == NUTDB_TT_Dot) return R_BAIL;       // qualified: the automaton drops the qualifier
+      if (!emit(NUTDB_NK_IDENT, 0, 0, t)) return R_BAIL;
+      adv();
+      // the source is an expression: anything with infix power continues it (mod.rs:1212-1216)
+      switch (ty) {
+        case NUTDB_TT_Eq: case NUTDB_TT_NotEq: case NUTDB_TT_Gt: case NUTDB_TT_Lt: case NUTDB_TT_GtEq: case NUTDB_TT_LtEq:
+        case NUTDB_TT_BitOr: case NUTDB_TT_BitXor: case NUTDB_TT_BitAnd: case NUTDB_TT_BitLShift: case NUTDB_TT_BitRShift:
+        case NUTDB_TT_Plus: case NUTDB_TT_Minus: case NUTDB_TT_Mul: case NUTDB_TT_Div: case NUTDB_TT_Mod:
+        case NUTDB_TT_LBracket:
+          return R_BAIL;
+        case NUTDB_TT_KeywordOrIdentifier:
+          if (kw == KW_AND || kw == KW_OR || kw == KW_XOR || kw == KW_IN || kw == KW_LIKE || kw == KW_ILIKE ||
+              kw == KW_NOT || kw == KW_IS || kw == KW_BETWEEN)
+            return R_BAIL;
+          break;
+        default: break;
       }
-      if (!emit(NUTDB_NK_FROM, 0, 0, m)) return false;
+      if (!alias()) return R_BAIL;
+      if (!emit(NUTDB_NK_FROM, 0, 0, m)) return R_BAIL;
     }
-    if (tok.type(t) == NUTDB_TT_KeywordOrIdentifier) {
-      const uint32_t kw = tok.kw(t);
-      if (kw == KW_INNER || kw == KW_FULL || kw == KW_LEFT || kw == KW_RIGHT || kw == KW_JOIN) return false;
-    }
-    if (is_kw(t, KW_WHERE)) {
-      t++;
-      const uint32_t m = n;
-      if (!expr()) return false;
-      if (!emit(NUTDB_NK_WHERE, 0, 0, m)) return false;
-    }
-    if (is_kw(t, KW_GROUP)) {
-      if (!is_kw(t + 1, KW_BY)) return false;
-      t += 2;
-      const uint32_t m = n;
-      if (!query_expr_list()) return false;
-      if (!emit(NUTDB_NK_GROUPBY, 0, 0, m)) return false;
-    }
-    if (is_kw(t, KW_HAVING)) {
-      t++;
-      const uint32_t m = n;
-      if (!expr()) return false;
-      if (!emit(NUTDB_NK_HAVING, 0, 0, m)) return false;
-    }
-    if (is_kw(t, KW_ORDER)) {  // DESC only: the reference never accepts ASC (mod.rs:491-496)
-      if (!is_kw(t + 1, KW_BY)) return false;
-      t += 2;
-      const uint32_t m = n;
-      for (;;) {
-        if (!query_expr()) return false;
-        if (is_kw(t, KW_DESC)) {
-          if (!emit(NUTDB_NK_ORDER_DESC, 0, 0, NUTDB_CN_NOTOK)) return false;
-          t++;
-        }
-        if (tok.type(t) != NUTDB_TT_Comma) break;
-        t++;
-      }
-      if (!emit(NUTDB_NK_ORDERBY, 0, 0, m)) return false;
-    }
-    if (is_kw(t, KW_LIMIT)) {  // mod.rs:503-544
-      t++;
-      const uint32_t m = n;
-      uint32_t sub = 0, aux = 0;
-      if (!int_literal(1)) return false;
-      if (tok.type(t) == NUTDB_TT_Comma) {
-        t++;
-        sub = 1;
-        if (!int_literal(1)) return false;
-      } else if (is_kw(t, KW_OFFSET)) {
-        t++;
-        sub = 2;
-        if (!int_literal(1)) return false;
-      }
-      if (is_kw(t, KW_WITH)) {
-        if (!is_kw(t + 1, KW_TIES)) return false;
-        t += 2;
-        aux = 1;
-      }
-      if (!emit(NUTDB_NK_LIMIT, (uint8_t)sub, (uint16_t)aux, m)) return false;
-    }
-    if (!emit(NUTDB_NK_QUERY_BODY, 0, 0, body)) return false;
-    if (tok.type(t) == NUTDB_TT_KeywordOrIdentifier) {  // set operations (mod.rs:250-267)
-      const uint32_t kw = tok.kw(t);
-      if (kw == KW_UNION || kw == KW_INTERSECT || kw == KW_EXCEPT) return false;
-    }
-    return emit(NUTDB_NK_STMT_SELECT, 0, 0, 0);
+    if (ty == NUTDB_TT_KeywordOrIdentifier &&
+        (kw == KW_INNER || kw == KW_FULL || kw == KW_LEFT || kw == KW_RIGHT || kw == KW_JOIN))
+      return R_BAIL;
+    return select_advance(1);
   }
 
-  // try_parse_insert_stmt with VALUES (mod.rs:589-670); t is after INSERT
-  NUTDB_HD bool insert_stmt() {
-    if (!is_kw(t, KW_INTO)) return false;
-    t++;
-    if (!ident_string(tok.type(t))) return false;
-    if (!emit(NUTDB_NK_NAME, 0, 0, t)) return false;
-    t++;
-    if (tok.type(t) == NUTDB_TT_LParen) {
-      t++;
-      for (;;) {
-        if (!ident_string(tok.type(t))) return false;
-        if (!emit(NUTDB_NK_NAME, 0, 0, t)) return false;
-        t++;
-        if (tok.type(t) != NUTDB_TT_Comma) break;
-        t++;
-      }
-      if (tok.type(t) != NUTDB_TT_RParen) return false;
-      t++;
-    }
-    if (!is_kw(t, KW_VALUES)) return false;
-    t++;
-    const uint32_t rows = n;
-    uint32_t width = 0;
-    for (uint32_t r = 0;; r++) {
-      if (tok.type(t) != NUTDB_TT_LParen) return false;
-      t++;
-      const uint32_t m = n;
-      uint32_t w = 0;
-      for (;;) {
-        if (!expr()) return false;
-        w++;
-        if (tok.type(t) != NUTDB_TT_Comma) break;
-        t++;
-      }
-      if (!emit(NUTDB_NK_ROW, 0, 0, m)) return false;
-      if (r == 0) width = w;
-      else if (w != width) return false;  // Conflicts: the automaton reports it
-      if (tok.type(t) != NUTDB_TT_RParen) return false;
-      t++;
-      if (tok.type(t) != NUTDB_TT_Comma) break;
-      t++;
-    }
-    if (!emit(NUTDB_NK_ROWS, 0, 0, rows)) return false;
-    return emit(NUTDB_NK_STMT_INSERT, 0, 0, 0);
-  }
-
+  // ---- CREATE TABLE (mod.rs:689-805, :936-972) ----
   // must_parse_datatype (mod.rs:1688-1797) without Enum / Tuple / Map
   NUTDB_HD bool datatype() {
     uint32_t marks[4], subs[4], depth = 0;
     for (;;) {
-      if (tok.type(t) != NUTDB_TT_KeywordOrIdentifier) return false;
-      const uint32_t kw = tok.kw(t);
+      if (ty != NUTDB_TT_KeywordOrIdentifier) return false;
       if (kw < KW_INT8 || kw > KW_NULLABLE) return false;
       const uint32_t i = kw - KW_INT8;
-      t++;
+      adv();
       if (i == 26 || i == 30 || i == 31) {  // Array / Dictionary / Nullable (inner)
-        if (depth >= 4 || tok.type(t) != NUTDB_TT_LParen) return false;
+        if (depth >= 4 || ty != NUTDB_TT_LParen) return false;
         marks[depth] = n;
         subs[depth] = i == 26 ? 0u : (i == 30 ? 4u : 5u);
         depth++;
-        t++;
+        adv();
         continue;
       }
       if (i > 25) return false;
-      if (i == 16 || i == 17 || i == 21 || (i == 22 && tok.type(t) == NUTDB_TT_LParen)) {
-        if (tok.type(t) != NUTDB_TT_LParen) return false;
-        t++;
+      if (i == 16 || i == 17 || i == 21 || (i == 22 && ty == NUTDB_TT_LParen)) {
+        if (ty != NUTDB_TT_LParen) return false;
+        adv();
         const uint32_t m = n;
         if (!int_literal((i == 16 || i == 17) ? 0u : 1u)) return false;
-        if (tok.type(t) != NUTDB_TT_RParen) return false;
-        t++;
+        if (ty != NUTDB_TT_RParen) return false;
+        adv();
         if (!emit(NUTDB_NK_DT_PARAM, (uint8_t)i, 0, m)) return false;
       } else {
         if (!emit(NUTDB_NK_DT_SCALAR, (uint8_t)i, 0, NUTDB_CN_NOTOK)) return false;
@@ -504,102 +464,220 @@ struct FastParser {
     }
     while (depth > 0) {
       depth--;
-      if (tok.type(t) != NUTDB_TT_RParen) return false;
-      t++;
+      if (ty != NUTDB_TT_RParen) return false;
+      adv();
       if (!emit(NUTDB_NK_DT_COMPOUND, (uint8_t)subs[depth], 0, marks[depth])) return false;
     }
     return true;
   }
-
-  // try_parse_create_stmt for tables (mod.rs:689-805, :936-972); t is after CREATE
-  NUTDB_HD bool create_stmt() {
-    if (!is_kw(t, KW_TABLE)) return false;
-    t++;
-    uint32_t aux = 0;
-    if (is_kw(t, KW_IF)) {
-      if (!is_kw(t + 1, KW_NOT) || !is_kw(t + 2, KW_EXISTS)) return false;
-      t += 3;
-      aux = 1;
-    }
-    if (!ident_string(tok.type(t))) return false;
-    if (!emit(NUTDB_NK_NAME, 0, 0, t)) return false;
-    t++;
-    if (tok.type(t) != NUTDB_TT_LParen) return false;
-    t++;
-    for (;;) {
-      if (is_kw(t, KW_INDEX) || is_kw(t, KW_CONSTRAINT)) return false;
-      const uint32_t m = n;
-      if (!ident_string(tok.type(t))) return false;
-      if (!emit(NUTDB_NK_NAME, 0, 0, t)) return false;
-      t++;
-      if (!datatype()) return false;
-      uint32_t seen = 0;
-      while (tok.type(t) == NUTDB_TT_KeywordOrIdentifier) {
-        const uint32_t kw = tok.kw(t);
-        if (kw == KW_DEFAULT) {
-          if (seen & 1u) return false;
-          seen |= 1u;
-          t++;
-          const uint32_t d = n;
-          if (!expr()) return false;
-          if (!emit(NUTDB_NK_ATTR_DEFAULT, 0, 0, d)) return false;
-        } else if (kw == KW_COMMENT) {
-          if (seen & 2u) return false;
-          seen |= 2u;
-          t++;
-          if (!string_literal()) return false;
-        } else {
-          return false;
-        }
-      }
-      if (!emit(NUTDB_NK_COLDEF, 0, 0, m)) return false;
-      if (tok.type(t) != NUTDB_TT_Comma) break;
-      t++;
-    }
-    if (tok.type(t) != NUTDB_TT_RParen) return false;
-    t++;
-    uint32_t seen = 0;
-    while (tok.type(t) == NUTDB_TT_KeywordOrIdentifier) {
-      const uint32_t kw = tok.kw(t);
-      uint32_t bit, kind;
-      if (kw == KW_PRIMARY) { bit = 1; kind = NUTDB_NK_ATTR_PK; }
-      else if (kw == KW_ORDER) { bit = 2; kind = NUTDB_NK_ATTR_ORDER; }
-      else if (kw == KW_PARTITION) { bit = 4; kind = NUTDB_NK_ATTR_PART; }
-      else if (kw == KW_COMMENT) { bit = 8; kind = 0; }
-      else return false;
-      if (seen & bit) return false;
-      seen |= bit;
-      t++;
-      if (kind == 0) {
-        if (!string_literal()) return false;
+  // table attributes after the column list (mod.rs:746-803)
+  NUTDB_HD uint32_t table_attrs() {
+    while (ty == NUTDB_TT_KeywordOrIdentifier) {
+      uint32_t bit;
+      uint8_t next_ctx;
+      if (kw == KW_PRIMARY) { bit = 1; next_ctx = C_TBL_PK_ITEM; }
+      else if (kw == KW_ORDER) { bit = 2; next_ctx = C_TBL_ORDER_ITEM; }
+      else if (kw == KW_PARTITION) { bit = 4; next_ctx = C_TBL_PART; }
+      else if (kw == KW_COMMENT) { bit = 8; next_ctx = 0xFF; }
+      else return R_BAIL;
+      if (tseen & bit) return R_BAIL;  // Conflicts: the automaton reports it
+      tseen |= bit;
+      adv();
+      if (next_ctx == 0xFF) {
+        if (!string_literal()) return R_BAIL;
         continue;
       }
-      if (!is_kw(t, kind == NUTDB_NK_ATTR_PK ? (uint32_t)KW_KEY : (uint32_t)KW_BY)) return false;
-      t++;
-      const uint32_t m = n;
-      if (kind == NUTDB_NK_ATTR_PART) {
-        if (!expr()) return false;
-      } else {
-        if (!expr_list()) return false;
-      }
-      if (!emit((uint8_t)kind, 0, 0, m)) return false;
+      if (!is_kw(next_ctx == C_TBL_PK_ITEM ? (uint32_t)KW_KEY : (uint32_t)KW_BY)) return R_BAIL;
+      adv();
+      m1 = n;
+      ctx = next_ctx;
+      return R_EXPR;
     }
-    if (!emit(NUTDB_NK_TABLEDEF, 0, 0, 0)) return false;
-    return emit(NUTDB_NK_STMT_CREATE, 0, (uint16_t)aux, 0);
+    if (!emit(NUTDB_NK_TABLEDEF, 0, 0, 0)) return R_BAIL;
+    return emit(NUTDB_NK_STMT_CREATE, 0, (uint16_t)aux, 0) ? R_DONE : R_BAIL;
+  }
+  // attributes of the column in progress, then the next column or the end of the list (mod.rs:936-972, :722-733)
+  NUTDB_HD uint32_t column_attrs() {
+    for (;;) {
+      while (ty == NUTDB_TT_KeywordOrIdentifier) {
+        if (kw == KW_DEFAULT) {
+          if (seen & 1u) return R_BAIL;
+          seen |= 1u;
+          adv();
+          m1 = n;
+          ctx = C_COL_DEFAULT;
+          return R_EXPR;
+        }
+        if (kw != KW_COMMENT || (seen & 2u)) return R_BAIL;
+        seen |= 2u;
+        adv();
+        if (!string_literal()) return R_BAIL;
+      }
+      if (!emit(NUTDB_NK_COLDEF, 0, 0, m0)) return R_BAIL;
+      if (ty != NUTDB_TT_Comma) break;
+      adv();
+      if (!begin_column()) return R_BAIL;
+    }
+    if (ty != NUTDB_TT_RParen) return R_BAIL;
+    adv();
+    tseen = 0;
+    return table_attrs();
+  }
+  NUTDB_HD bool begin_column() {
+    if (is_kw(KW_INDEX) || is_kw(KW_CONSTRAINT)) return false;
+    m0 = n;
+    seen = 0;
+    if (!ident_string(ty)) return false;
+    if (!emit(NUTDB_NK_NAME, 0, 0, t)) return false;
+    adv();
+    return datatype();
+  }
+
+  // ---- statement prologues: everything before the first expression ----
+  NUTDB_HD uint32_t begin_select() {
+    if (is_kw(KW_DISTINCT)) return R_BAIL;
+    ctx = C_SEL_ITEM;
+    return R_EXPR;
+  }
+  NUTDB_HD uint32_t begin_insert() {  // try_parse_insert_stmt with VALUES (mod.rs:589-670)
+    if (!is_kw(KW_INTO)) return R_BAIL;
+    adv();
+    if (!ident_string(ty)) return R_BAIL;
+    if (!emit(NUTDB_NK_NAME, 0, 0, t)) return R_BAIL;
+    adv();
+    if (ty == NUTDB_TT_LParen) {
+      adv();
+      for (;;) {
+        if (!ident_string(ty)) return R_BAIL;
+        if (!emit(NUTDB_NK_NAME, 0, 0, t)) return R_BAIL;
+        adv();
+        if (ty != NUTDB_TT_Comma) break;
+        adv();
+      }
+      if (ty != NUTDB_TT_RParen) return R_BAIL;
+      adv();
+    }
+    if (!is_kw(KW_VALUES)) return R_BAIL;
+    adv();
+    m0 = n;
+    if (ty != NUTDB_TT_LParen) return R_BAIL;
+    adv();
+    m1 = n;
+    w = 0;
+    row = 0;
+    ctx = C_INS_VALUE;
+    return R_EXPR;
+  }
+  NUTDB_HD uint32_t begin_create() {
+    if (!is_kw(KW_TABLE)) return R_BAIL;
+    adv();
+    aux = 0;
+    if (is_kw(KW_IF)) {
+      if (!next_is_kw(1, KW_NOT) || !next_is_kw(2, KW_EXISTS)) return R_BAIL;
+      adv(3);
+      aux = 1;
+    }
+    if (!ident_string(ty)) return R_BAIL;
+    if (!emit(NUTDB_NK_NAME, 0, 0, t)) return R_BAIL;
+    adv();
+    if (ty != NUTDB_TT_LParen) return R_BAIL;
+    adv();
+    if (!begin_column()) return R_BAIL;
+    return column_attrs();
+  }
+
+  // what follows the expression that was just parsed in context `ctx`
+  NUTDB_HD uint32_t after_expr() {
+    switch (ctx) {
+      case C_SEL_ITEM:
+        if (!alias()) return R_BAIL;
+        if (ty == NUTDB_TT_Comma) {
+          adv();
+          return R_EXPR;
+        }
+        return select_after_items();
+      case C_WHERE:
+        if (!emit(NUTDB_NK_WHERE, 0, 0, m1)) return R_BAIL;
+        return select_advance(2);
+      case C_GROUP_ITEM:
+        if (!alias()) return R_BAIL;
+        if (ty == NUTDB_TT_Comma) {
+          adv();
+          return R_EXPR;
+        }
+        if (!emit(NUTDB_NK_GROUPBY, 0, 0, m1)) return R_BAIL;
+        return select_advance(3);
+      case C_HAVING:
+        if (!emit(NUTDB_NK_HAVING, 0, 0, m1)) return R_BAIL;
+        return select_advance(4);
+      case C_ORDER_ITEM:  // DESC only: the reference never accepts ASC (mod.rs:491-496)
+        if (!alias()) return R_BAIL;
+        if (is_kw(KW_DESC)) {
+          if (!emit(NUTDB_NK_ORDER_DESC, 0, 0, NUTDB_CN_NOTOK)) return R_BAIL;
+          adv();
+        }
+        if (ty == NUTDB_TT_Comma) {
+          adv();
+          return R_EXPR;
+        }
+        if (!emit(NUTDB_NK_ORDERBY, 0, 0, m1)) return R_BAIL;
+        return select_advance(5);
+      case C_INS_VALUE:  // must_parse_insert_rows (mod.rs:636-670)
+        w++;
+        if (ty == NUTDB_TT_Comma) {
+          adv();
+          return R_EXPR;
+        }
+        if (!emit(NUTDB_NK_ROW, 0, 0, m1)) return R_BAIL;
+        if (row == 0) width = w;
+        else if (w != width) return R_BAIL;  // Conflicts: the automaton reports it
+        if (ty != NUTDB_TT_RParen) return R_BAIL;
+        adv();
+        if (ty == NUTDB_TT_Comma) {
+          adv();
+          if (ty != NUTDB_TT_LParen) return R_BAIL;
+          adv();
+          m1 = n;
+          w = 0;
+          row++;
+          return R_EXPR;
+        }
+        if (!emit(NUTDB_NK_ROWS, 0, 0, m0)) return R_BAIL;
+        return emit(NUTDB_NK_STMT_INSERT, 0, 0, 0) ? R_DONE : R_BAIL;
+      case C_COL_DEFAULT:
+        if (!emit(NUTDB_NK_ATTR_DEFAULT, 0, 0, m1)) return R_BAIL;
+        return column_attrs();
+      case C_TBL_PK_ITEM:
+      case C_TBL_ORDER_ITEM:
+        if (ty == NUTDB_TT_Comma) {
+          adv();
+          return R_EXPR;
+        }
+        if (!emit(ctx == C_TBL_PK_ITEM ? (uint8_t)NUTDB_NK_ATTR_PK : (uint8_t)NUTDB_NK_ATTR_ORDER, 0, 0, m1)) return R_BAIL;
+        return table_attrs();
+      default:  // C_TBL_PART
+        if (!emit(NUTDB_NK_ATTR_PART, 0, 0, m1)) return R_BAIL;
+        return table_attrs();
+    }
   }
 
   // parse_stmt (mod.rs:128-180).  true: res describes a successful parse with n nodes emitted.
   NUTDB_HD bool try_parse(ParseResult& res) {
-    if (tok.type(0) != NUTDB_TT_KeywordOrIdentifier) return false;
-    const uint32_t kw = tok.kw(0);
-    t = 1;
-    bool ok;
-    if (kw == KW_SELECT) ok = select_stmt();
-    else if (kw == KW_INSERT) ok = insert_stmt();
-    else if (kw == KW_CREATE) ok = create_stmt();
+    t = 0;
+    load();
+    if (ty != NUTDB_TT_KeywordOrIdentifier) return false;
+    const uint32_t first = kw;
+    adv();
+    uint32_t r;
+    if (first == KW_SELECT) r = begin_select();
+    else if (first == KW_INSERT) r = begin_insert();
+    else if (first == KW_CREATE) r = begin_create();
     else return false;
-    if (!ok || sp != 0) return false;
-    const uint8_t ty = tok.type(t);
+    while (r == R_EXPR) {
+      if (!expr()) return false;
+      r = after_expr();
+    }
+    if (r != R_DONE || sp != 0) return false;
     if (ty != NUTDB_TT_EOF && ty != NUTDB_TT_SemiColon) return false;
     res.status = NUTDB_ST_OK;
     res.node_count = n;

@@ -33,6 +33,8 @@ struct HTokAdapter {
   HTok h;
   uint8_t type(uint32_t i) const { return h.type(i); }
   uint8_t kw(uint32_t i) const { return h.kwid(i); }
+  uint8_t type_at(uint32_t i) const { return h.type(i); }
+  uint8_t kw_at(uint32_t i) const { return h.kwid(i); }
   uint32_t start(uint32_t i) const { return h.start(i); }
   uint32_t end(uint32_t i) const { return h.end(i); }
 };
