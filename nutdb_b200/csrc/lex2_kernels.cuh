@@ -256,6 +256,8 @@ struct Lex2Out {
   uint32_t* punt_flag;   // per statement
   uint32_t* punt_list;   // statement indices
   uint32_t* punt_count;
+  const uint32_t* first_stmt;  // per 32-byte window: smallest non-empty statement starting in it
+  uint32_t nbytes;
   __device__ uint32_t find_stmt(uint32_t pos) const {  // the statement containing byte `pos`
     uint32_t lo = 0, hi = nstmt;
     while (lo < hi) {
@@ -278,8 +280,35 @@ struct Lex2Out {
       kw[i] = k;
     }
   }
-  __device__ __forceinline__ void stmt_begin(uint32_t pos, uint32_t first) const { stmt_tok_begin[find_stmt(pos)] = first; }
-  __device__ __forceinline__ void stmt_end(uint32_t pos, uint32_t endi) const { stmt_tok_end[find_stmt(pos)] = endi; }
+  // A statement starts at byte `pos` and its first token has index `first`.  first_stmt[pos / 32] is the
+  // smallest non-empty statement starting in that window (k_prep), so the statement is found by stepping over
+  // the few statements of the window (and over empty ones, which share their offset with their successor).
+  // The same lane closes the token range of the previous non-empty statement: its EOF token is first - 1.
+  __device__ __forceinline__ void stmt_begin(uint32_t pos, uint32_t first) const {
+    uint32_t c = first_stmt[pos >> 5];
+    while (off32[c] != pos || off32[c + 1] == pos) c++;
+    stmt_tok_begin[c] = first;
+    uint32_t p = c;
+    while (p > 0) {
+      p--;
+      if (off32[p + 1] != off32[p]) {
+        stmt_tok_end[p] = first;
+        break;
+      }
+    }
+  }
+  // only the last statement of the batch has no successor to close its range
+  __device__ __forceinline__ void stmt_end(uint32_t pos, uint32_t endi) const {
+    if (pos + 1u != nbytes) return;
+    uint32_t p = nstmt;
+    while (p > 0) {
+      p--;
+      if (off32[p + 1] != off32[p]) {
+        stmt_tok_end[p] = endi;
+        break;
+      }
+    }
+  }
 };
 
 // Emit = false: token counts per window (wcount, one byte each) + per-warp carries + flags; Emit = true: tokens.

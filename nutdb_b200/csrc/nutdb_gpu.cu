@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_vec8(const uint32_t* __re
 // k_prep
 // ------------------------------------------------------------------------------------------
 __global__ void k_prep(const uint64_t* __restrict__ off, uint64_t nstmt, uint32_t* __restrict__ off32,
-                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ bad) {
+                       uint32_t* __restrict__ bitmap, uint32_t* __restrict__ first_stmt, uint32_t* __restrict__ bad) {
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nstmt) return;
   const uint64_t base = off[0];
@@ -233,6 +233,7 @@ __global__ void k_prep(const uint64_t* __restrict__ off, uint64_t nstmt, uint32_
     else if (e > o) {
       uint32_t p = (uint32_t)(o - base);
       atomicOr(&bitmap[p >> 5], 1u << (p & 31u));
+      atomicMin(&first_stmt[p >> 5], (uint32_t)s);
     }
   }
 }
@@ -710,7 +711,7 @@ struct NutdbCtx {
   // device buffers (grow only)
   DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks;
+      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
   float ms[5] = {0, 0, 0, 0, 0};
@@ -817,7 +818,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks};
+                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
   HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
@@ -960,11 +961,14 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   // ---- lexer ----
   ENSURE_DEV(puntFlag, 4 * ((size_t)nstmt + 1));
   CK(cudaMemsetAsync(ctx->puntFlag.p, 0, 4 * ((size_t)nstmt + 1), st));
+  ENSURE_DEV(firstStmt, 4 * (nchunks + 1));
+  CK(cudaMemsetAsync(ctx->firstStmt.p, 0xFF, 4 * (nchunks + 1), st));
   CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 1), st));
   CK(cudaMemsetAsync(dS, 0, 64, st));
   {
     const uint32_t blocks = (uint32_t)(((uint64_t)nstmt + 1 + 255) / 256);
-    LAUNCH("k_prep", k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p, dS));
+    LAUNCH("k_prep", k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p,
+                                                  (uint32_t*)ctx->firstStmt.p, dS));
   }
   uint32_t ntok = 0;
   ctx->n_punt = 0;
@@ -1035,7 +1039,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
     Lex2Out lo{nullptr, nullptr, nullptr, nullptr, 0, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
-               (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->puntList.p, dS + 3};
+               (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->puntList.p, dS + 3,
+               (const uint32_t*)ctx->firstStmt.p, n};
     LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2,
                                                                   (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p,
                                                                   (uint32_t*)ctx->winMasks.p, mstride));

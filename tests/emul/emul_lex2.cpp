@@ -144,8 +144,34 @@ struct Out {
     end[i] = e;
     kw[i] = k;
   }
-  void stmt_begin(uint32_t pos, uint32_t first) { stmt_tok_begin[find_stmt(pos)] = first; }
-  void stmt_end(uint32_t pos, uint32_t endi) { stmt_tok_end[find_stmt(pos)] = endi; }
+  // same O(1) statement lookup as the device sink (first_stmt table built by k_prep)
+  const uint32_t* first_stmt = nullptr;
+  uint32_t nbytes = 0;
+  uint32_t off32(uint64_t s) const { return (uint32_t)(offs[s] - offs[0]); }
+  void stmt_begin(uint32_t pos, uint32_t first) {
+    uint32_t c = first_stmt[pos >> 5];
+    while (off32(c) != pos || off32(c + 1) == pos) c++;
+    stmt_tok_begin[c] = first;
+    uint32_t p = c;
+    while (p > 0) {
+      p--;
+      if (off32(p + 1) != off32(p)) {
+        stmt_tok_end[p] = first;
+        break;
+      }
+    }
+  }
+  void stmt_end(uint32_t pos, uint32_t endi) {
+    if (pos + 1u != nbytes) return;
+    uint64_t p = nstmt;
+    while (p > 0) {
+      p--;
+      if (off32(p + 1) != off32(p)) {
+        stmt_tok_end[p] = endi;
+        break;
+      }
+    }
+  }
 };
 
 struct StmtSrc {
@@ -224,6 +250,14 @@ int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
   std::vector<uint8_t> flag(nstmt + 1, 0);
   std::vector<uint32_t> list;
   Out out{tok_type, tok_start, tok_end, tok_kw, 0, stmt_tok_begin, stmt_tok_end, offs, nstmt, &flag, &list};
+  std::vector<uint32_t> first_stmt((n + 31) / 32 + 2, 0xFFFFFFFFu);
+  for (uint64_t st = 0; st < nstmt; st++)
+    if (offs[st + 1] > offs[st]) {
+      uint32_t p = (uint32_t)(offs[st] - offs[0]);
+      first_stmt[p >> 5] = std::min(first_stmt[p >> 5], (uint32_t)st);
+    }
+  out.first_stmt = first_stmt.data();
+  out.nbytes = n;
   HSrc src{e};
   std::vector<uint8_t> wcount(nwin);
   uint32_t ntok_main = 0;
