@@ -3,4 +3,4 @@
 Drop-in for the one hot path of nutdb/nutdb: `nutdb::parser::Parser::parse` (reference
 src/parser/mod.rs:26-29).  `gpu` binds the CUDA library, `workload` generates benchmark batches.
 """
-__all__ = ["gpu", "workload", "build", "parser", "dispatch"]
+__all__ = ["gpu", "workload", "build", "parser", "dispatch", "stream"]

@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
                                                           const uint32_t* __restrict__ localA,
                                                           const uint8_t* __restrict__ tileEntA, uint4* __restrict__ localC,
                                                           uint4* __restrict__ tileC, const uint4* __restrict__ tilePrefC,
-                                                          uint8_t* __restrict__ wcount, uint32_t* __restrict__ gmask,
-                                                          size_t mstride, Lex2Out out) {
+                                                          uint8_t* __restrict__ wcount, uint8_t* __restrict__ wstate,
+                                                          uint32_t* __restrict__ gmask, size_t mstride, Lex2Out out) {
   __shared__ Lex2Shared S;
   __shared__ uint4 wsum[L2_WARPS];
   const uint32_t tile_begin = blockIdx.x * L2_TILE;
@@ -338,11 +338,18 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
     setup_window<false, true>(S, src, bitmap, tile_begin, blk, n, lane, gmask, mstride, u);
     const bool live = u.base < n;
     // entry state of every window: scan of the window functions on top of the warp's entry state
-    const uint32_t f = live ? window_fn(S.T, u) : NUTDB_VEC8_ID;
-    uint32_t excl;
-    warp_scan_vec8(f, lane, excl);
+    // (the counting pass stores it, one byte per window, for the emitting pass)
     const uint8_t s_warp = (uint8_t)vec8_apply(localA[widx], tileEntA[blockIdx.x]);
-    const uint8_t s_in = (uint8_t)vec8_apply(excl, s_warp);
+    uint8_t s_in;
+    if (!Emit) {
+      const uint32_t f = live ? window_fn(S.T, u) : NUTDB_VEC8_ID;
+      uint32_t excl;
+      warp_scan_vec8(f, lane, excl);
+      s_in = (uint8_t)vec8_apply(excl, s_warp);
+      if (live) wstate[u.base >> 5] = s_in;
+    } else {
+      s_in = live ? wstate[u.base >> 5] : (uint8_t)A_C;
+    }
     nlex2::WinCtx o;
     if (live) nlex2::ctx_window(u.w, u.ev, u.base, u.nx, s_in, u.prev_byte, o);
     o.escm = u.escm;

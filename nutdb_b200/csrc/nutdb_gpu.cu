@@ -711,7 +711,7 @@ struct NutdbCtx {
   // device buffers (grow only)
   DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt;
+      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
   float ms[5] = {0, 0, 0, 0, 0};
@@ -818,7 +818,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt};
+                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
   HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
@@ -1035,6 +1035,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(entA, ntiles);
     ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
     ENSURE_DEV(winCount, (size_t)ntiles * (L2_TILE / 32) + 16);
+    ENSURE_DEV(winState, (size_t)ntiles * (L2_TILE / 32) + 16);
     const size_t mstride = (size_t)ntiles * (L2_TILE / 32);
     ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
@@ -1048,7 +1049,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
                                dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                                (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr,
-                               (uint8_t*)ctx->winCount.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
+                               (uint8_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
     LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p,
                                                                         ntiles, (uint4*)(dS + 4)));
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
@@ -1090,7 +1091,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p,
-                              (uint8_t*)ctx->winCount.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
+                              (uint8_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
     if (npunt > 0) {
       xs = ExactSink{lo.type, lo.start, lo.end, lo.kw, ntok};
       LAUNCH("k_lex_exact_emit", k_lex_exact<true><<<(npunt + 127) / 128, 128, 0, st>>>(

@@ -13,7 +13,7 @@ def split_statements(offs, nparts):
     total = int(offs[-1] - offs[0])
     cuts = [0]
     for p in range(1, nparts):
-        target = int(offs[0]) + total * p // nparts
+        target = np.uint64(int(offs[0]) + total * p // nparts)   # same dtype as offs: no O(n) conversion per cut
         s = int(np.searchsorted(offs, target, side="left"))
         cuts.append(min(max(s, cuts[-1]), n))
     cuts.append(n)

@@ -124,9 +124,9 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().nutdb_gpu_ctx_destroy(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.nutdb_gpu_ctx_destroy(self._h)
+        self._h = None
 
     __del__ = close
 

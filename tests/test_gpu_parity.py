@@ -178,3 +178,24 @@ def test_parser_parse_mirrors_the_reference_entry(ctx):
     for s, r in zip(fuzz.EXTRA_SEEDS + [b"select $0", b"select 'abc"], res):
         want = O.parse(s)
         assert (repr(r) == want.debug) if want.ok else (str(r) == want.error)
+
+
+def test_stream_parser_chunks_match_one_batch(ctx):
+    from nutdb_b200 import gpu, stream
+    text, offs = W.generate(3, 6 << 20)
+    whole = ctx.parse_batch(text, offs, flags=gpu.F_NO_TOKENS)
+    sp = stream.StreamParser(0, workers=3)
+    got = {}
+
+    def on_batch(first, b):
+        got[first] = (b.stmt.copy(), b.node.copy(), b.err.copy())
+
+    n = sp.parse(text, offs, on_batch, chunk_bytes=1 << 20)
+    sp.close()
+    assert n >= 5 and len(got) == n
+    nodes = np.concatenate([got[k][1] for k in sorted(got)])
+    status = np.concatenate([got[k][0]["status"] for k in sorted(got)])
+    ncount = np.concatenate([got[k][0]["node_count"] for k in sorted(got)])
+    assert np.array_equal(nodes, whole.node)
+    assert np.array_equal(status, whole.stmt["status"]) and np.array_equal(ncount, whole.stmt["node_count"])
+    assert sum(len(got[k][2]) for k in got) == whole.n_err
