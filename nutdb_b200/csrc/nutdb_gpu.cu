@@ -37,6 +37,8 @@ using namespace nlex;
 #define LEX_ROW (LEX_THREADS + 1)
 #define SCAN_THREADS 1024
 #define PARSE_THREADS 128
+#define FAST_THREADS 512     // statements per CTA in k_parse_fast (re-dealt among its warps)
+#define FAST_BINS 64
 #define PARSE_STACK 160      // words of local stack in the fast path
 #define FIN_THREADS 256
 #define NODE_SLACK 8u        // fast-path node range of a statement = its token count + NODE_SLACK
@@ -467,14 +469,43 @@ __device__ __forceinline__ void store_result(const npar::ParseResult& res, uint3
 // Pass 1, one thread per statement: the straight-line parser (parse_fast.cuh).  Statements it
 // declines go to the slow list.  Small code, no interpreter state: this is where a query log's
 // bulk is parsed.
-__global__ void __launch_bounds__(PARSE_THREADS) k_parse_fast(
+__global__ void __launch_bounds__(FAST_THREADS) k_parse_fast(
     const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, uint32_t nstmt, uint32_t ntok,
     const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end,
     const uint8_t* __restrict__ tok_kw, const uint32_t* __restrict__ stmt_tok_begin,
     const uint32_t* __restrict__ stmt_tok_end, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
     uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count, const uint32_t* __restrict__ punt,
     int lex_only) {
-  const uint32_t s = blockIdx.x * PARSE_THREADS + threadIdx.x;
+  // Lanes of a warp run independent parsers, so they only execute together where their statements look
+  // alike.  The block therefore re-deals its statements: a counting sort in shared memory by (first keyword,
+  // token-count bucket) puts statements of the same kind and similar length into the same warp.
+  __shared__ uint32_t bin_count[FAST_BINS], bin_base[FAST_BINS], order[FAST_THREADS];
+  uint32_t s = blockIdx.x * FAST_THREADS + threadIdx.x;
+  if (threadIdx.x < FAST_BINS) bin_count[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t key = FAST_BINS - 1, rank = 0;
+  if (s < nstmt) {
+    const uint32_t len0 = off32[s + 1] - off32[s];
+    if (len0 != 0) {
+      const uint32_t tb0 = stmt_tok_begin[s], tc0 = stmt_tok_end[s] - tb0;
+      const uint32_t k0 = tok_type[tb0] == NUTDB_TT_KeywordOrIdentifier ? tok_kw[tb0] : 0u;
+      const uint32_t kind = k0 == npar::KW_SELECT ? 0u : (k0 == npar::KW_INSERT ? 1u : (k0 == npar::KW_CREATE ? 2u : 3u));
+      key = kind * 16u + min(15u, tc0 >> 2);
+    }
+  }
+  rank = atomicAdd(&bin_count[key], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int b = 0; b < FAST_BINS; b++) {
+      bin_base[b] = acc;
+      acc += bin_count[b];
+    }
+  }
+  __syncthreads();
+  order[bin_base[key] + rank] = threadIdx.x;
+  __syncthreads();
+  s = blockIdx.x * FAST_THREADS + order[threadIdx.x];
   if (s >= nstmt) return;
   const uint32_t o = off32[s], len = off32[s + 1] - o;
   if (len == 0) {
@@ -1117,7 +1148,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
     const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
     ENSURE_DEV(slowList, 4 * ((size_t)nstmt + 1));
-    LAUNCH("k_parse_fast", k_parse_fast<<<pblocks, PARSE_THREADS, 0, st>>>(
+    LAUNCH("k_parse_fast", k_parse_fast<<<(nstmt + FAST_THREADS - 1) / FAST_THREADS, FAST_THREADS, 0, st>>>(
                                dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                (const uint8_t*)ctx->tokKw.p, (const uint32_t*)ctx->stmtTokBegin.p,
