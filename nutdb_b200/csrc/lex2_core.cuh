@@ -608,9 +608,14 @@ NUTDB_HD uint32_t win_tokens(const LexTables& T, const Lex2Tables& K, Src& src, 
           if (t.type == NUTDB_TT_KeywordOrIdentifier) {
             const uint32_t len = t.end - t.start;
             if (len >= 2 && len <= 10) {
-              Src& sr = src;
-              const uint32_t s0 = t.start;
-              kw = keyword_lookup(T, len, [&sr, s0](uint32_t q) { return sr.byte(s0 + q); });
+              const uint8_t* wp = src.span(t.start, len);  // the word as contiguous bytes (almost always)
+              if (wp) {
+                kw = keyword_lookup(T, len, [wp](uint32_t q) { return wp[q]; });
+              } else {
+                Src& sr = src;
+                const uint32_t s0 = t.start;
+                kw = keyword_lookup(T, len, [&sr, s0](uint32_t q) { return sr.byte(s0 + q); });
+              }
             }
           }
           sink.token(index + n, t.type, t.start - sst, t.end - sst, kw);

@@ -19,6 +19,9 @@ struct alignas(16) Lex2Shared {
   nlex2::Lex2Tables K;
 };
 
+// bytes outside the CTA's tile (look-back / look-ahead across a tile edge): rare, kept out of line
+__device__ __noinline__ uint8_t far_byte(const uint8_t* text, uint32_t p, uint32_t n) { return p < n ? text[p] : (uint8_t)0; }
+
 struct Tile2Src {
   const uint8_t* text;
   const uint8_t* sm;
@@ -26,7 +29,12 @@ struct Tile2Src {
   __device__ __forceinline__ uint8_t byte(uint32_t p) const {
     const uint32_t r = p - tile_begin;
     if (r < L2_TILE) return sm[r];
-    return p < n ? text[p] : (uint8_t)0;
+    return far_byte(text, p, n);
+  }
+  // [p, p + len) as one contiguous run of shared memory, or nullptr if it leaves the tile
+  __device__ __forceinline__ const uint8_t* span(uint32_t p, uint32_t len) const {
+    const uint32_t r = p - tile_begin;
+    return (r < L2_TILE && r + len <= L2_TILE) ? sm + r : nullptr;
   }
 };
 
@@ -106,6 +114,46 @@ __device__ __forceinline__ void entry_esc(const Tile2Src& src, const uint32_t* b
   esc = (uint8_t)(nrun & 1u);
 }
 
+// stage 1, per thread: the 32 bytes of the lane's own window -> 32 class words (16 bits each) through the
+// shared-memory class table, then a SWAR bit-matrix transposition (two 16x16 blocks side by side in 16
+// registers, 4 butterfly stages) turns "16 class bits per byte" into "32 byte bits per class".
+__device__ __forceinline__ void build_masks_transpose(const Lex2Shared& S, uint32_t tile_begin, uint32_t base, uint32_t valid,
+                                                      nlex2::Win& w) {
+  const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(S.text) + (base - tile_begin));
+  const uint4 q0 = wp[0], q1 = wp[1];
+  const uint32_t lo[4] = {q0.x, q0.y, q0.z, q0.w}, hi[4] = {q1.x, q1.y, q1.z, q1.w};
+  uint32_t A[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      A[4 * i + b] = (uint32_t)S.K.cls[(lo[i] >> (8 * b)) & 0xFFu] | ((uint32_t)S.K.cls[(hi[i] >> (8 * b)) & 0xFFu] << 16);
+  uint32_t m = 0x00FF00FFu;
+#pragma unroll
+  for (int j = 8; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+    for (int k = 0; k < 16; k = (k + j + 1) & ~j) {
+      const uint32_t t = ((A[k] >> j) ^ A[k + j]) & m;
+      A[k + j] ^= t;
+      A[k] ^= t << j;
+    }
+  }
+  w.sq = A[0] & valid;
+  w.dq = A[1] & valid;
+  w.bt = A[2] & valid;
+  w.nl = A[3] & valid;
+  w.bs = A[4] & valid;
+  w.dash = A[5] & valid;
+  w.slash = A[6] & valid;
+  w.star = A[7] & valid;
+  w.L = A[8] & valid;
+  w.D = A[9] & valid;
+  w.DOT = A[10] & valid;
+  w.OP = A[11] & valid;
+  w.P = A[12] & valid;
+  w.WS = A[13] & valid;
+}
+
 // class masks of every window, computed once by k_lex2_fn: 14 arrays of nwin words (structure of arrays)
 #define L2_NMASK 14
 __device__ __forceinline__ void store_masks(uint32_t* __restrict__ g, size_t stride, uint32_t win, const nlex2::Win& w) {
@@ -156,14 +204,14 @@ __device__ __forceinline__ void setup_window(const Lex2Shared& S, const Tile2Src
                                              size_t mstride, WinSetup& u) {
   const uint32_t full = 0xFFFFFFFFu;
   u.base = blk + 32u * (uint32_t)lane;
-  if (Build) {
-    build_masks<true>(S, src, blk, n, lane, u.w);
-    store_masks(gmask, mstride, u.base >> 5, u.w);
-  } else {
-    load_masks(gmask, mstride, u.base >> 5, u.w);
-  }
   nlex2::Win& w = u.w;
   w.valid = u.base + 32u <= n ? full : (n > u.base ? ((1u << (n - u.base)) - 1u) : 0u);
+  if (Build) {
+    build_masks_transpose(S, tile_begin, u.base, w.valid, w);
+    store_masks(gmask, mstride, u.base >> 5, w);
+  } else {
+    load_masks(gmask, mstride, u.base >> 5, w);
+  }
   uint32_t bnd = u.base < n ? (bnd_word(S, bitmap, tile_begin, u.base) & w.valid) : 0u;
   if (Virt && n >= u.base && n - u.base < 32u) bnd |= 1u << (n - u.base);  // the batch end terminates the last statement
   w.bnd = bnd;

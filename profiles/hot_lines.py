@@ -5,6 +5,7 @@ import csv, re, subprocess, sys, collections, os, tempfile
 
 rep, kre, mangled = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+skip = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # kernel instances (in report order) to skip
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nutdb_b200", "libnutdb_gpu.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -27,11 +28,13 @@ rows = list(csv.reader(out.splitlines()))
 hdr = None; base = None; acc = collections.Counter(); samples = collections.Counter(); total = 0; started = False
 for r in rows:
     if r and r[0] == "Kernel Name":
+        if skip > 0:
+            skip -= 1; hdr = None; continue
         if started: break
         started = True; continue
     if r and r[0] == "Address":
         hdr = r; continue
-    if hdr and len(r) == len(hdr):
+    if started and hdr and len(r) == len(hdr):
         a = int(r[0], 16)
         if base is None: base = a
         ie = float(r[hdr.index("Instructions Executed")]); sm = float(r[hdr.index("# Samples")])

@@ -26,6 +26,10 @@ struct Env {
 struct HSrc {
   const Env& e;
   uint8_t byte(uint32_t p) const { return e.byte(p); }
+  // mimic the device: contiguous only inside one 8 KB tile
+  const uint8_t* span(uint32_t p, uint32_t len) const {
+    return (p / 8192 == (p + len - 1) / 8192 && p + len <= e.n) ? e.text + p : nullptr;
+  }
 };
 
 void entry_esc(const Env& e, uint32_t pos, uint8_t& prev, uint8_t& esc) {
