@@ -354,172 +354,166 @@ NUTDB_HD int run_start(uint64_t cont, int pos) {
   return r == 0 ? -1 : r;  // position 0 always "stops" (nothing is known below it): the run may extend further back
 }
 
-// the code token (if any) that ENDS at byte i of the window; i is a code-token byte (bit of ct)
-template <class Src>
-NUTDB_HD LaneTok code_token_at(const LexTables& T, Src& src, int lane, uint32_t base, uint8_t b, uint16_t k, const Win& w,
-                               uint32_t ct, const Hist& h, const Next& nx, uint32_t esc_mask, uint8_t prev_byte) {
-  LaneTok r;
-  const uint32_t bit = 1u << lane;
-  const uint32_t pos = base + (uint32_t)lane;
-  // the byte after this one
-  const bool nbnd = lane < 31 ? ((w.bnd >> (lane + 1)) & 1u) != 0 : nx.bnd != 0;
-  const uint8_t nb = lane < 31 ? (nbnd ? (uint8_t)0 : src.byte(pos + 1)) : (nbnd ? (uint8_t)0 : nx.byte);
-  const uint16_t nk = nbnd ? (uint16_t)0 : (lane < 31 ? (uint16_t)0xFFFF : nx.cls);  // class of next byte (lane 31 only)
+// per-window constants of code-token recognition: the thread's own masks on top of the previous window's
+struct WinTok {
+  uint64_t L64, D64, DOT64, W64, bnd64, contW, contO;
+  uint32_t nbnd;     // bit i: byte i+1 starts a statement (or is the batch end)
+  uint32_t nextW, nextD, nextDOT, nextOP;  // bit i: byte i+1 has that class and belongs to the same statement
+};
+NUTDB_HD WinTok make_wintok(const Win& w, uint32_t ct, const Hist& h, const Next& nx) {
+  WinTok k;
   const uint32_t ctL = w.L & ct, ctD = w.D & ct, ctDOT = w.DOT & ct, ctOP = w.OP & ct;
-  const uint64_t L64 = ((uint64_t)ctL << 32) | h.L, D64 = ((uint64_t)ctD << 32) | h.D;
-  const uint64_t DOT64 = ((uint64_t)ctDOT << 32) | h.DOT, OP64 = ((uint64_t)ctOP << 32) | h.OP;
-  const uint64_t bnd64 = ((uint64_t)w.bnd << 32) | h.bnd;
-  const uint64_t W64 = L64 | D64;
-  const int p = 32 + lane;
-  auto next_is = [&](uint32_t mask, uint16_t cls) -> bool {  // next byte is of that class (same statement)
-    if (nbnd) return false;
-    return lane < 31 ? ((mask >> (lane + 1)) & 1u) != 0 : (nk & cls) != 0;
-  };
-  auto ident_end_ok = [&]() { return nbnd || (T.prop[nb] & PR_IDENT_END); };
-  auto num_end_ok = [&]() { return nbnd || (T.prop[nb] & PR_NUM_END); };
-  if (k & (K_L | K_D)) {
-    // raw class of the next byte is enough: inside code a word byte cannot change the context
-    if (next_is(w.L | w.D, K_L | K_D)) return r;  // the run continues
-    const uint64_t contW = W64 & (W64 << 1) & ~bnd64;
-    const int st = run_start(contW, p);
-    if (st < 0) { r.bad = 1; return r; }
-    const uint64_t span = ((p >= 63 ? ~0ull : ((2ull << p) - 1ull))) & ~((1ull << st) - 1ull);
-    const uint32_t abs_st = base + (uint32_t)st - 32u;
-    if (!((D64 >> st) & 1ull)) {  // identifier / keyword (tokenizer/mod.rs:262-282)
-      if (!ident_end_ok()) { r.bad = 1; return r; }
-      r.has = 1;
-      r.type = NUTDB_TT_KeywordOrIdentifier;
-      r.start = abs_st;
-      r.end = pos + 1;
-      return r;
-    }
-    if (L64 & span) { r.bad = 1; return r; }  // 1abc, 0x1F ...: error or hex -> exact path
-    const bool left_dot = st > 0 && ((DOT64 >> (st - 1)) & 1ull) && !((bnd64 >> st) & 1ull);
-    if (next_is(w.DOT, K_DOT)) {  // digits '.' ...: the token ends later
-      if (left_dot) r.bad = 1;    // second dot of one numeric token: error
-      return r;
-    }
-    if (!num_end_ok()) { r.bad = 1; return r; }
+  k.L64 = ((uint64_t)ctL << 32) | h.L;
+  k.D64 = ((uint64_t)ctD << 32) | h.D;
+  k.DOT64 = ((uint64_t)ctDOT << 32) | h.DOT;
+  const uint64_t OP64 = ((uint64_t)ctOP << 32) | h.OP;
+  k.bnd64 = ((uint64_t)w.bnd << 32) | h.bnd;
+  k.W64 = k.L64 | k.D64;
+  k.contW = k.W64 & (k.W64 << 1) & ~k.bnd64;
+  k.contO = OP64 & (OP64 << 1) & ~k.bnd64;
+  k.nbnd = (w.bnd >> 1) | ((uint32_t)(nx.bnd != 0) << 31);
+  // raw class of the next byte is enough: inside code a word / digit / dot / operator byte cannot change the context
+  k.nextW = (((w.L | w.D) >> 1) | ((uint32_t)((nx.cls & (K_L | K_D)) != 0) << 31)) & ~k.nbnd;
+  k.nextD = ((w.D >> 1) | ((uint32_t)((nx.cls & K_D) != 0) << 31)) & ~k.nbnd;
+  k.nextDOT = ((w.DOT >> 1) | ((uint32_t)((nx.cls & K_DOT) != 0) << 31)) & ~k.nbnd;
+  k.nextOP = ((w.OP >> 1) | ((uint32_t)((nx.cls & K_OP) != 0) << 31)) & ~k.nbnd;
+  return k;
+}
+template <class Src>
+NUTDB_HD uint8_t next_byte(Src& src, const WinTok& k, const Next& nx, uint32_t base, int i) {
+  if ((k.nbnd >> i) & 1u) return 0;
+  return i < 31 ? src.byte(base + (uint32_t)i + 1u) : nx.byte;
+}
+
+// word / number whose LAST byte is byte i of the window (i is the end of a run of [A-Za-z0-9_])
+template <class Src>
+NUTDB_HD LaneTok tok_word(const LexTables& T, Src& src, const WinTok& k, const Next& nx, uint32_t base, int i) {
+  LaneTok r;
+  const uint32_t pos = base + (uint32_t)i;
+  const int p = 32 + i;
+  const bool nbnd = ((k.nbnd >> i) & 1u) != 0;
+  const int st = run_start(k.contW, p);
+  if (st < 0) { r.bad = 1; return r; }
+  const uint32_t abs_st = base + (uint32_t)st - 32u;
+  if (!((k.D64 >> st) & 1ull)) {  // identifier / keyword (tokenizer/mod.rs:262-282)
+    if (!(nbnd || (T.prop[next_byte(src, k, nx, base, i)] & PR_IDENT_END))) { r.bad = 1; return r; }
     r.has = 1;
+    r.type = NUTDB_TT_KeywordOrIdentifier;
+    r.start = abs_st;
     r.end = pos + 1;
-    if (!left_dot) {  // integer literal (tokenizer/mod.rs:196-238)
-      r.type = NUTDB_TT_IntegerLiteral;
-      r.start = abs_st;
-      const uint32_t len = r.end - r.start;
-      r.kw = (uint8_t)(len > 255u ? 255u : len);
-      return r;
+    return r;
+  }
+  const uint64_t span = ((p >= 63 ? ~0ull : ((2ull << p) - 1ull))) & ~((1ull << st) - 1ull);
+  if (k.L64 & span) { r.bad = 1; return r; }  // 1abc, 0x1F ...: error or hex -> exact path
+  const bool left_dot = ((k.DOT64 >> (st - 1)) & 1ull) && !((k.bnd64 >> st) & 1ull);
+  if ((k.nextDOT >> i) & 1u) {  // digits '.' ...: the token ends later
+    if (left_dot) r.bad = 1;    // second dot of one numeric token: error
+    return r;
+  }
+  if (!(nbnd || (T.prop[next_byte(src, k, nx, base, i)] & PR_NUM_END))) { r.bad = 1; return r; }
+  r.has = 1;
+  r.end = pos + 1;
+  if (!left_dot) {  // integer literal (tokenizer/mod.rs:196-238)
+    r.type = NUTDB_TT_IntegerLiteral;
+    r.start = abs_st;
+    const uint32_t len = r.end - r.start;
+    r.kw = (uint8_t)(len > 255u ? 255u : len);
+    return r;
+  }
+  // float: [digits] '.' digits (tokenizer/mod.rs:246-258)
+  const int d = st - 1;
+  int fs = d;
+  if (d > 0 && ((k.W64 >> (d - 1)) & 1ull) && !((k.bnd64 >> d) & 1ull)) {
+    const int ls = run_start(k.contW, d - 1);
+    if (ls < 0) { r.bad = 1; return r; }
+    if ((k.D64 >> ls) & 1ull) {  // digits before the dot belong to the literal
+      fs = ls;
+      if (((k.DOT64 >> (ls - 1)) & 1ull) && !((k.bnd64 >> ls) & 1ull)) r.bad = 1;  // 1.2.3
     }
-    // float: [digits] '.' digits (tokenizer/mod.rs:246-258)
-    const int d = st - 1;
-    int fs = d;
-    if (d > 0 && ((W64 >> (d - 1)) & 1ull) && !((bnd64 >> d) & 1ull)) {
-      const int ls = run_start(contW, d - 1);
-      if (ls < 0) { r.bad = 1; return r; }
-      if ((D64 >> ls) & 1ull) {  // digits before the dot belong to the literal
-        fs = ls;
-        if (ls > 0 && ((DOT64 >> (ls - 1)) & 1ull) && !((bnd64 >> ls) & 1ull)) r.bad = 1;  // 1.2.3
-      }
-    } else if (d == 0) {
-      r.bad = 1;  // cannot see what precedes the dot
+  } else if (d == 0) {
+    r.bad = 1;  // cannot see what precedes the dot
+  }
+  r.type = NUTDB_TT_FloatLiteral;
+  r.start = base + (uint32_t)fs - 32u;
+  return r;
+}
+
+// byte i is a '.' in code
+template <class Src>
+NUTDB_HD LaneTok tok_dot(const LexTables& T, Src& src, const WinTok& k, const Next& nx, uint32_t base, int i) {
+  LaneTok r;
+  const uint32_t pos = base + (uint32_t)i;
+  const int p = 32 + i;
+  if ((k.nextD >> i) & 1u) return r;  // '.' digits: ends at the last digit
+  bool is_float = false;
+  int fs = p;
+  if (((k.W64 >> (p - 1)) & 1ull) && !((k.bnd64 >> p) & 1ull)) {
+    const int ls = run_start(k.contW, p - 1);
+    if (ls < 0) { r.bad = 1; return r; }
+    if ((k.D64 >> ls) & 1ull) {  // digits '.'  (a word with letters in it before the dot is flagged at its own end)
+      is_float = true;
+      fs = ls;
+      if (((k.DOT64 >> (ls - 1)) & 1ull) && !((k.bnd64 >> ls) & 1ull)) r.bad = 1;  // .5.
     }
+  }
+  r.has = 1;
+  r.end = pos + 1;
+  if (is_float) {
+    const bool nbnd = ((k.nbnd >> i) & 1u) != 0;
+    if (!(nbnd || (T.prop[next_byte(src, k, nx, base, i)] & PR_NUM_END))) { r.bad = 1; return r; }
     r.type = NUTDB_TT_FloatLiteral;
     r.start = base + (uint32_t)fs - 32u;
-    return r;
+  } else {
+    r.type = NUTDB_TT_Dot;  // no end check (tokenizer/mod.rs:248-250)
+    r.start = pos;
   }
-  if (k & K_DOT) {
-    if (next_is(w.D, K_D)) return r;  // '.' digits: ends at the last digit
-    bool is_float = false;
-    int fs = p;
-    if (((W64 >> (p - 1)) & 1ull) && !((bnd64 >> p) & 1ull)) {
-      const uint64_t contW = W64 & (W64 << 1) & ~bnd64;
-      const int ls = run_start(contW, p - 1);
-      if (ls < 0) { r.bad = 1; return r; }
-      if ((D64 >> ls) & 1ull) {  // digits '.'  (a word with letters in it before the dot is flagged by its own lane)
-        is_float = true;
-        fs = ls;
-        if (ls > 0 && ((DOT64 >> (ls - 1)) & 1ull) && !((bnd64 >> ls) & 1ull)) r.bad = 1;  // .5.
-      }
-    }
+  return r;
+}
+
+// byte i is one of < > = ! in code: at most two in a row are handled here (tokenizer/mod.rs:393-428)
+template <class Src>
+NUTDB_HD LaneTok tok_op(Src& src, const WinTok& k, const Next& nx, uint32_t base, int i, uint8_t prev_byte) {
+  LaneTok r;
+  const uint32_t pos = base + (uint32_t)i;
+  const int p = 32 + i;
+  const uint8_t b = src.byte(pos);
+  const int st = run_start(k.contO, p);
+  if (st < 0 || p - st >= 2) { r.bad = 1; return r; }
+  const bool more = ((k.nextOP >> i) & 1u) != 0;
+  auto pair_type = [](uint8_t c0, uint8_t c1) -> uint8_t {
+    if (c0 == '<') return c1 == '=' ? NUTDB_TT_LtEq : (c1 == '>' ? NUTDB_TT_NotEq : (c1 == '<' ? NUTDB_TT_BitLShift : 0));
+    if (c0 == '>') return c1 == '=' ? NUTDB_TT_GtEq : (c1 == '>' ? NUTDB_TT_BitRShift : 0);
+    if (c0 == '!') return c1 == '=' ? NUTDB_TT_NotEq : 0;
+    return 0;
+  };
+  auto single_type = [](uint8_t c0) -> uint8_t {
+    return c0 == '<' ? NUTDB_TT_Lt : (c0 == '>' ? NUTDB_TT_Gt : (c0 == '=' ? NUTDB_TT_Eq : 0xFF));
+  };
+  if (p - st == 0) {
+    if (more && pair_type(b, next_byte(src, k, nx, base, i))) return r;  // first half of a two-character operator
+    const uint8_t ty = single_type(b);
+    if (ty == 0xFF) { r.bad = 1; return r; }  // lone '!'
     r.has = 1;
-    r.end = pos + 1;
-    if (is_float) {
-      if (!num_end_ok()) { r.bad = 1; return r; }
-      r.type = NUTDB_TT_FloatLiteral;
-      r.start = base + (uint32_t)fs - 32u;
-    } else {
-      r.type = NUTDB_TT_Dot;  // no end check (tokenizer/mod.rs:248-250)
-      r.start = pos;
-    }
-    return r;
-  }
-  if (k & K_OP) {  // < > = ! : at most two in a row are handled here (tokenizer/mod.rs:393-428)
-    const uint64_t contO = OP64 & (OP64 << 1) & ~bnd64;
-    const int st = run_start(contO, p);
-    if (st < 0 || p - st >= 2) { r.bad = 1; return r; }
-    const bool more = next_is(w.OP, K_OP);
-    auto pair_type = [](uint8_t c0, uint8_t c1) -> uint8_t {
-      if (c0 == '<') return c1 == '=' ? NUTDB_TT_LtEq : (c1 == '>' ? NUTDB_TT_NotEq : (c1 == '<' ? NUTDB_TT_BitLShift : 0));
-      if (c0 == '>') return c1 == '=' ? NUTDB_TT_GtEq : (c1 == '>' ? NUTDB_TT_BitRShift : 0);
-      if (c0 == '!') return c1 == '=' ? NUTDB_TT_NotEq : 0;
-      return 0;
-    };
-    auto single_type = [](uint8_t c0) -> uint8_t {
-      return c0 == '<' ? NUTDB_TT_Lt : (c0 == '>' ? NUTDB_TT_Gt : (c0 == '=' ? NUTDB_TT_Eq : 0xFF));
-    };
-    if (p - st == 0) {
-      if (more) {
-        if (pair_type(b, nb)) return r;  // first half of a two-character operator
-      }
-      const uint8_t ty = single_type(b);
-      if (ty == 0xFF) { r.bad = 1; return r; }  // lone '!'
-      r.has = 1;
-      r.type = ty;
-      r.start = pos;
-      r.end = pos + 1;
-      return r;
-    }
-    if (more) { r.bad = 1; return r; }  // three or more
-    const uint8_t pb = lane > 0 ? src.byte(pos - 1) : prev_byte;
-    const uint8_t pt = pair_type(pb, b);
-    r.has = 1;
-    r.end = pos + 1;
-    if (pt) {
-      r.type = pt;
-      r.start = pos - 1;
-    } else {
-      const uint8_t ty = single_type(b);
-      if (ty == 0xFF) { r.bad = 1; r.has = 0; return r; }
-      r.type = ty;
-      r.start = pos;
-    }
-    return r;
-  }
-  if (k & K_P) {
-    r.has = 1;
-    r.type = T.single_tt[b];
+    r.type = ty;
     r.start = pos;
     r.end = pos + 1;
     return r;
   }
-  if (k & K_DASH) {
-    if (!nbnd && nb == '-') return r;  // "--" opens a comment at the next byte
-    r.has = 1;
-    r.type = NUTDB_TT_Minus;
+  if (more) { r.bad = 1; return r; }  // three or more
+  const uint8_t pb = i > 0 ? src.byte(pos - 1) : prev_byte;
+  const uint8_t pt = pair_type(pb, b);
+  r.has = 1;
+  r.end = pos + 1;
+  if (pt) {
+    r.type = pt;
+    r.start = pos - 1;
+  } else {
+    const uint8_t ty = single_type(b);
+    if (ty == 0xFF) { r.bad = 1; r.has = 0; return r; }
+    r.type = ty;
     r.start = pos;
-    r.end = pos + 1;
-    return r;
   }
-  if (k & K_SLASH) {
-    if (!nbnd && nb == '*') return r;  // "/*"
-    r.has = 1;
-    r.type = NUTDB_TT_Div;
-    r.start = pos;
-    r.end = pos + 1;
-    return r;
-  }
-  (void)bit;
-  (void)esc_mask;
-  return r;  // whitespace, opening quotes: no code token ends here (invalid bytes are caught by win_bad_mask)
+  return r;
 }
 
 // statements that need the exact path, as far as masks can tell (token-level checks add to this)
@@ -547,91 +541,153 @@ NUTDB_HD uint32_t win_bad_mask(Src& src, const Win& w, const WinCtx& o, uint32_t
   return bad;
 }
 
-// candidate positions: a code token can only end where one of these bits is set
-NUTDB_HD uint32_t win_candidates(const Win& w, const WinCtx& o, const Next& nx) {
-  const uint32_t nbnd = (w.bnd >> 1) | ((uint32_t)(nx.bnd != 0) << 31);
-  const uint32_t Wm = (w.L | w.D);
-  const uint32_t nextW = ((Wm >> 1) | ((uint32_t)((nx.cls & (K_L | K_D)) != 0) << 31)) & ~nbnd;
-  const uint32_t nextDash = ((w.dash >> 1) | ((uint32_t)(nx.byte == '-') << 31)) & ~nbnd;
-  const uint32_t nextStar = ((w.star >> 1) | ((uint32_t)(nx.byte == '*') << 31)) & ~nbnd;
-  uint32_t c = (Wm & ~nextW) | w.DOT | w.OP | w.P | (w.dash & ~nextDash) | (w.slash & ~nextStar);
-  return c & o.ct;
+// Tokens are extracted CLASS BY CLASS (all single-character tokens, then all words/numbers, ...), not in
+// position order: every loop below runs the same code in all lanes of a warp.  The index of a token only
+// needs the mask of ALL positions where a token ends ("has"), which the counting pass computes and stores.
+
+// single-character punctuation and lone '-' '/' need no look at anything but masks
+NUTDB_HD uint32_t simple_token_mask(const Win& w, const WinCtx& o, const Next& nx, const WinTok& k) {
+  const uint32_t nextDash = ((w.dash >> 1) | ((uint32_t)(nx.byte == '-') << 31)) & ~k.nbnd;
+  const uint32_t nextStar = ((w.star >> 1) | ((uint32_t)(nx.byte == '*') << 31)) & ~k.nbnd;
+  return o.ct & (w.P | (w.dash & ~nextDash) | (w.slash & ~nextStar));
+}
+
+// counting pass: positions where a token ENDS (code tokens and literal closes; EOF tokens are counted from
+// the boundary mask) and positions whose statement needs the exact path
+template <class Src>
+NUTDB_HD uint32_t win_has_mask(const LexTables& T, Src& src, const Win& w, const WinCtx& o, const Hist& h, const Next& nx,
+                               uint32_t base, uint8_t prev_byte, uint32_t& bad) {
+  bad = win_bad_mask(src, w, o, base, prev_byte);
+  const WinTok k = make_wintok(w, o.ct, h, nx);
+  uint32_t has = simple_token_mask(w, o, nx, k) | o.close;
+  uint32_t todo = o.ct & (w.L | w.D) & ~k.nextW;  // ends of word / number runs
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const LaneTok t = tok_word(T, src, k, nx, base, i);
+    has |= (uint32_t)t.has << i;
+    bad |= (uint32_t)t.bad << i;
+  }
+  todo = o.ct & w.DOT;
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const LaneTok t = tok_dot(T, src, k, nx, base, i);
+    has |= (uint32_t)t.has << i;
+    bad |= (uint32_t)t.bad << i;
+  }
+  todo = o.ct & w.OP;
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const LaneTok t = tok_op(src, k, nx, base, i, prev_byte);
+    has |= (uint32_t)t.has << i;
+    bad |= (uint32_t)t.bad << i;
+  }
+  return has;
+}
+NUTDB_HD uint32_t win_eof_mask(const Win& w, const Next& nx) {
+  return ((w.bnd >> 1) | ((uint32_t)(nx.bnd != 0) << 31)) & w.valid;
 }
 
 // Sink: void token(uint32_t index, uint8_t type, uint32_t start_rel, uint32_t end_rel, uint8_t kw);
 //       void stmt_begin(uint32_t abs_pos, uint32_t first_index); void stmt_end(uint32_t abs_last_byte, uint32_t end_index);
-// Returns the number of tokens of the window (EOF tokens included); `bad` gets the positions whose
-// statement needs the exact path.  With Emit = false nothing is written and no keyword is looked up.
-template <bool Emit, class Src, class Sink>
-NUTDB_HD uint32_t win_tokens(const LexTables& T, const Lex2Tables& K, Src& src, Sink& sink, const Win& w, const WinCtx& o,
-                             const Hist& h, const Next& nx, uint32_t base, uint8_t prev_byte, const StrCarry& sc_in,
-                             uint32_t stmt_start_in, uint32_t index, uint32_t& bad) {
-  bad = win_bad_mask(src, w, o, base, prev_byte);
-  const uint32_t eofm = ((w.bnd >> 1) | ((uint32_t)(nx.bnd != 0) << 31)) & w.valid;
-  uint32_t todo = win_candidates(w, o, nx) | o.close | eofm;
-  if (Emit) todo |= w.bnd & w.valid;
-  uint32_t n = 0, icap = 0;
-  uint32_t sst = stmt_start_in;
+// emitting pass: `has` is the mask stored by the counting pass, `index` the index of the window's first token
+template <class Src, class Sink>
+NUTDB_HD void win_emit(const LexTables& T, Src& src, Sink& sink, const Win& w, const WinCtx& o, const Hist& h, const Next& nx,
+                       uint32_t base, uint8_t prev_byte, const StrCarry& sc_in, uint32_t stmt_start_in, uint32_t index,
+                       uint32_t has) {
+  const uint32_t eofm = win_eof_mask(w, nx);
+  const WinTok k = make_wintok(w, o.ct, h, nx);
+  const uint32_t bnds = w.bnd & w.valid;
+  auto index_of = [&](int i) {  // tokens (and EOF tokens) that end before byte i
+    const uint32_t below = (1u << i) - 1u;
+    return index + (uint32_t)popc32(has & below) + (uint32_t)popc32(eofm & below);
+  };
+  auto stmt_of = [&](int i) {  // start of the statement byte i belongs to
+    const uint32_t bb = bnds & (i >= 31 ? 0xFFFFFFFFu : ((2u << i) - 1u));
+    return bb ? base + (uint32_t)(31 - clz32(bb)) : stmt_start_in;
+  };
+  // statement starts and ends
+  uint32_t todo = bnds;
   while (todo) {
     const int i = ctz32(todo);
     todo &= todo - 1;
-    const uint32_t bit = 1u << i;
-    const uint32_t pos = base + (uint32_t)i;
-    if (Emit && (w.bnd & w.valid & bit)) {
-      sst = pos;
-      sink.stmt_begin(pos, index + n);
-    }
-    if (o.close & bit) {
-      if (icap < o.ncap && o.cap_pos[icap] == i) {
-        if (Emit) {
-          uint8_t type = o.cap_type[icap];
-          uint32_t start = o.cap_start[icap];
-          if (o.cap_carried[icap]) {  // opened in an earlier window: offset and escaped flag come from the carry
-            start = sc_in.open_pos + 1u;
-            const bool escd = (sc_in.esc | o.esc_first) != 0;
-            type = type == 3 ? (uint8_t)NUTDB_TT_DelimitedIdentifier
-                             : (escd ? (type == 1 ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
-                                     : (uint8_t)NUTDB_TT_RawStringLiteral);
-          }
-          sink.token(index + n, type, start - sst, pos - sst, 0);
-        }
-        icap++;
-      }
-      n++;  // (closes beyond the capture array are flagged bad; they still count so both passes agree)
-    } else if (o.ct & bit) {
-      const uint8_t b = src.byte(pos);
-      const LaneTok t = code_token_at(T, src, i, base, b, K.cls[b], w, o.ct, h, nx, o.escm, prev_byte);
-      if (t.bad) bad |= bit;
-      if (t.has) {
-        if (Emit) {
-          uint8_t kw = t.kw;
-          if (t.type == NUTDB_TT_KeywordOrIdentifier) {
-            const uint32_t len = t.end - t.start;
-            if (len >= 2 && len <= 10) {
-              const uint8_t* wp = src.span(t.start, len);  // the word as contiguous bytes (almost always)
-              if (wp) {
-                kw = keyword_lookup(T, len, [wp](uint32_t q) { return wp[q]; });
-              } else {
-                Src& sr = src;
-                const uint32_t s0 = t.start;
-                kw = keyword_lookup(T, len, [&sr, s0](uint32_t q) { return sr.byte(s0 + q); });
-              }
-            }
-          }
-          sink.token(index + n, t.type, t.start - sst, t.end - sst, kw);
-        }
-        n++;
-      }
-    }
-    if (eofm & bit) {
-      if (Emit) {
-        sink.token(index + n, NUTDB_TT_EOF, pos + 1u - sst, pos + 1u - sst, 0);
-        sink.stmt_end(pos, index + n + 1u);
-      }
-      n++;
-    }
+    sink.stmt_begin(base + (uint32_t)i, index_of(i));
   }
-  return n;
+  todo = eofm;
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const uint32_t sst = stmt_of(i), e = index_of(i) + ((has >> i) & 1u);
+    sink.token(e, NUTDB_TT_EOF, base + (uint32_t)i + 1u - sst, base + (uint32_t)i + 1u - sst, 0);
+    sink.stmt_end(base + (uint32_t)i, e + 1u);
+  }
+  // single-character tokens
+  todo = simple_token_mask(w, o, nx, k);
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const uint32_t pos = base + (uint32_t)i, sst = stmt_of(i);
+    const uint8_t b = src.byte(pos);
+    const uint8_t type = b == '-' ? (uint8_t)NUTDB_TT_Minus : (b == '/' ? (uint8_t)NUTDB_TT_Div : T.single_tt[b]);
+    sink.token(index_of(i), type, pos - sst, pos + 1u - sst, 0);
+  }
+  // words and numbers
+  todo = o.ct & (w.L | w.D) & ~k.nextW & has;
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const LaneTok t = tok_word(T, src, k, nx, base, i);
+    const uint32_t sst = stmt_of(i);
+    uint8_t kw = t.kw;
+    if (t.type == NUTDB_TT_KeywordOrIdentifier) {
+      const uint32_t len = t.end - t.start;
+      if (len >= 2 && len <= 10) {
+        const uint8_t* wp = src.span(t.start, len);  // the word as contiguous bytes (almost always)
+        if (wp) {
+          kw = keyword_lookup(T, len, [wp](uint32_t q) { return wp[q]; });
+        } else {
+          Src& sr = src;
+          const uint32_t s0 = t.start;
+          kw = keyword_lookup(T, len, [&sr, s0](uint32_t q) { return sr.byte(s0 + q); });
+        }
+      }
+    }
+    sink.token(index_of(i), t.type, t.start - sst, t.end - sst, kw);
+  }
+  todo = o.ct & w.DOT & has;
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const LaneTok t = tok_dot(T, src, k, nx, base, i);
+    const uint32_t sst = stmt_of(i);
+    sink.token(index_of(i), t.type, t.start - sst, t.end - sst, 0);
+  }
+  todo = o.ct & w.OP & has;
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const LaneTok t = tok_op(src, k, nx, base, i, prev_byte);
+    const uint32_t sst = stmt_of(i);
+    sink.token(index_of(i), t.type, t.start - sst, t.end - sst, 0);
+  }
+  // strings and quoted identifiers, at their closing quote
+  for (uint32_t c = 0; c < o.ncap; c++) {
+    const int i = o.cap_pos[c];
+    const uint32_t pos = base + (uint32_t)i, sst = stmt_of(i);
+    uint8_t type = o.cap_type[c];
+    uint32_t start = o.cap_start[c];
+    if (o.cap_carried[c]) {  // opened in an earlier window: offset and escaped flag come from the carry
+      start = sc_in.open_pos + 1u;
+      const bool escd = (sc_in.esc | o.esc_first) != 0;
+      type = type == 3 ? (uint8_t)NUTDB_TT_DelimitedIdentifier
+                       : (escd ? (type == 1 ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
+                               : (uint8_t)NUTDB_TT_RawStringLiteral);
+    }
+    sink.token(index_of(i), type, start - sst, pos - sst, 0);
+  }
+  // (closes beyond the capture array are flagged for the exact path; their slots stay unwritten)
 }
 
 }  // namespace nlex2

@@ -319,7 +319,7 @@ struct Lex2Out {
     const uint32_t s = find_stmt(pos);
     if (atomicExch(&punt_flag[s], 1u) == 0u) punt_list[atomicAdd(punt_count, 1u)] = s;
   }
-  // sink interface of nlex2::win_tokens
+  // sink interface of nlex2::win_emit
   __device__ __forceinline__ void token(uint32_t i, uint8_t t, uint32_t s, uint32_t e, uint8_t k) const {
     if (i < cap) {
       type[i] = t;
@@ -359,7 +359,7 @@ struct Lex2Out {
   }
 };
 
-// Emit = false: token counts per window (wcount, one byte each) + per-warp carries + flags; Emit = true: tokens.
+// Emit = false: token-end mask per window (whas) + per-warp carries + flags; Emit = true: tokens.
 template <bool Emit>
 __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restrict__ text,
                                                           const uint32_t* __restrict__ bitmap, uint32_t n,
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
                                                           const uint32_t* __restrict__ localA,
                                                           const uint8_t* __restrict__ tileEntA, uint4* __restrict__ localC,
                                                           uint4* __restrict__ tileC, const uint4* __restrict__ tilePrefC,
-                                                          uint8_t* __restrict__ wcount, uint8_t* __restrict__ wstate,
+                                                          uint32_t* __restrict__ whas, uint8_t* __restrict__ wstate,
                                                           uint32_t* __restrict__ gmask, size_t mstride, Lex2Out out) {
   __shared__ Lex2Shared S;
   __shared__ uint4 wsum[L2_WARPS];
@@ -431,10 +431,11 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
     uint32_t stmt_in = 0, index = 0, ntok = 0;
     if (!Emit) {
       uint32_t bad = 0;
-      if (live) ntok = nlex2::win_tokens<false>(S.T, S.K, src, out, u.w, o, h, u.nx, u.base, u.prev_byte, sc_in, 0u, 0u, bad);
       if (live) {
+        const uint32_t has = nlex2::win_has_mask(S.T, src, u.w, o, h, u.nx, u.base, u.prev_byte, bad);
+        ntok = (uint32_t)__popc(has) + (uint32_t)__popc(nlex2::win_eof_mask(u.w, u.nx));
         if (u.w.bs == 0xFFFFFFFFu) bad |= 1u;  // backslash run longer than a window: parity not tracked
-        wcount[u.base >> 5] = (uint8_t)ntok;
+        whas[u.base >> 5] = has;
         uint32_t bb = bad;
         while (bb) {
           const int i = __ffs((int)bb) - 1;
@@ -481,7 +482,8 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
     } else {
       const CSum pre = csum_unpack(CSumOp::then(tilePrefC[blockIdx.x], localC[widx]));
       // exclusive scans over the lanes, seeded with the warp's carry-in
-      uint32_t cnt = live ? (uint32_t)wcount[u.base >> 5] : 0u, lb = o.last_bnd1;
+      const uint32_t has = live ? whas[u.base >> 5] : 0u;
+      uint32_t cnt = live ? (uint32_t)__popc(has) + (uint32_t)__popc(nlex2::win_eof_mask(u.w, u.nx)) : 0u, lb = o.last_bnd1;
       uint32_t sc_open = o.sc.has_open, sc_esc = o.sc.esc, sc_pos = o.sc.open_pos;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -498,7 +500,6 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
           }
         }
       }
-      const uint32_t own = live ? (uint32_t)wcount[u.base >> 5] : 0u;
       uint32_t xcnt = __shfl_up_sync(full, cnt, 1), xlb = __shfl_up_sync(full, lb, 1);
       uint32_t xo = __shfl_up_sync(full, sc_open, 1), xe = __shfl_up_sync(full, sc_esc, 1), xp = __shfl_up_sync(full, sc_pos, 1);
       if (lane == 0) {
@@ -508,7 +509,6 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
         xe = 0;
         xp = 0;
       }
-      (void)own;
       index = pre.count + xcnt;
       stmt_in = xlb ? xlb - 1u : pre.stmt_start;
       if (xo) {
@@ -520,8 +520,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
         sc_in.esc = (uint8_t)(pre.escaped | xe);
         sc_in.open_pos = pre.tok_start;
       }
-      uint32_t bad = 0;
-      if (live) nlex2::win_tokens<true>(S.T, S.K, src, out, u.w, o, h, u.nx, u.base, u.prev_byte, sc_in, stmt_in, index, bad);
+      if (live) nlex2::win_emit(S.T, src, out, u.w, o, h, u.nx, u.base, u.prev_byte, sc_in, stmt_in, index, has);
     }
   } else if (!Emit) {
     if (lane == 31) wsum[warp] = csum_pack(wtotal);

@@ -1065,7 +1065,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(tilePrefC, 16 * (size_t)ntiles);
     ENSURE_DEV(entA, ntiles);
     ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
-    ENSURE_DEV(winCount, (size_t)ntiles * (L2_TILE / 32) + 16);
+    ENSURE_DEV(winCount, 4 * ((size_t)ntiles * (L2_TILE / 32) + 16));
     ENSURE_DEV(winState, (size_t)ntiles * (L2_TILE / 32) + 16);
     const size_t mstride = (size_t)ntiles * (L2_TILE / 32);
     ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
@@ -1080,7 +1080,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
                                dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                                (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr,
-                               (uint8_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
+                               (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
     LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p,
                                                                         ntiles, (uint4*)(dS + 4)));
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
@@ -1122,7 +1122,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p,
-                              (uint8_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
+                              (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
     if (npunt > 0) {
       xs = ExactSink{lo.type, lo.start, lo.end, lo.kw, ntok};
       LAUNCH("k_lex_exact_emit", k_lex_exact<true><<<(npunt + 127) / 128, 128, 0, st>>>(

@@ -263,7 +263,7 @@ int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
   out.first_stmt = first_stmt.data();
   out.nbytes = n;
   HSrc src{e};
-  std::vector<uint8_t> wcount(nwin);
+  std::vector<uint32_t> whas(nwin);
   uint32_t ntok_main = 0;
   for (int pass = 0; pass < 2; pass++) {
     uint32_t count = 0, stmt_start = 0;
@@ -305,9 +305,11 @@ int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
         uint32_t bad = 0;
         if (pass == 0) {
           StrCarry none;
-          uint32_t nt = win_tokens<false>(g_T, g_K, src, out, u.w, o, h, u.nx, base, u.prev_byte, none, 0u, 0u, bad);
+          (void)none;
+          const uint32_t has = win_has_mask(g_T, src, u.w, o, h, u.nx, base, u.prev_byte, bad);
+          const uint32_t nt = (uint32_t)popc32(has) + (uint32_t)popc32(win_eof_mask(u.w, u.nx));
           if (u.w.bs == 0xFFFFFFFFu) bad |= 1u;
-          wcount[base >> 5] = (uint8_t)nt;
+          whas[base >> 5] = has;
           for (int i = 0; i < 32; i++) {
             if ((bad >> i) & 1u) out.punt(base + i);
             if ((o.bad_prev >> i) & 1u) out.punt(base + i - 1);
@@ -316,9 +318,9 @@ int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
             out.punt(n - 1);
           count += nt;
         } else {
-          uint32_t nt = win_tokens<true>(g_T, g_K, src, out, u.w, o, h, u.nx, base, u.prev_byte, sc, stmt_start, count, bad);
-          if (nt != wcount[base >> 5]) return -3;
-          count += nt;
+          const uint32_t has = whas[base >> 5];
+          win_emit(g_T, src, out, u.w, o, h, u.nx, base, u.prev_byte, sc, stmt_start, count, has);
+          count += (uint32_t)popc32(has) + (uint32_t)popc32(win_eof_mask(u.w, u.nx));
         }
         sc = str_then(sc, o.sc);
         if (o.last_bnd1) stmt_start = o.last_bnd1 - 1;
