@@ -480,6 +480,8 @@ __global__ void __launch_bounds__(FAST_THREADS) k_parse_fast(
   // alike.  The block therefore re-deals its statements: a counting sort in shared memory by (first keyword,
   // token-count bucket) puts statements of the same kind and similar length into the same warp.
   __shared__ uint32_t bin_count[FAST_BINS], bin_base[FAST_BINS], order[FAST_THREADS];
+  __shared__ npar::FastTables FT;
+  if (threadIdx.x < 128) npar::fast_tables_fill(FT, threadIdx.x);
   uint32_t s = blockIdx.x * FAST_THREADS + threadIdx.x;
   if (threadIdx.x < FAST_BINS) bin_count[threadIdx.x] = 0;
   __syncthreads();
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_parse_fast(
   DNodes nd{range, tc + NODE_SLACK};
   DText tx{text + o, len};
   npar::ParseResult res;
-  npar::FastParser<DTok, DNodes, DText> f(tk, nd, tx);
+  npar::FastParser<DTok, DNodes, DText> f(FT, tk, nd, tx);
   if (f.try_parse(res)) {
     store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
   } else {

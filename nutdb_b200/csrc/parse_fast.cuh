@@ -26,8 +26,81 @@
 
 namespace npar {
 
+// Lookup tables of the expression loop: what an operand token is, and the infix power / operator of a token
+// (token_power, mod.rs:1895-1927).  Lanes holding different token types then execute the SAME instructions.
+struct FastTables {
+  uint32_t opnd[48];   // by token type: class | kind << 8 | sub << 16 | aux << 24
+  uint16_t optok[48];  // by token type: power | op << 4 | bail << 12
+  uint16_t opkw[128];  // by keyword id: same encoding
+};
+enum : uint32_t { FO_BAIL = 0, FO_LEAF = 1, FO_WORD = 2, FO_DELIM = 3, FO_MINUS = 4, FO_PLUS = 5, FO_LPAREN = 6, FO_INT = 7,
+                  FO_ESTR = 8 };
+NUTDB_HD uint32_t fast_opnd_entry(uint32_t ty) {
+  switch (ty) {
+    case NUTDB_TT_KeywordOrIdentifier: return FO_WORD;
+    case NUTDB_TT_DelimitedIdentifier: return FO_DELIM;
+    case NUTDB_TT_Mul: return FO_LEAF | (NUTDB_NK_IDENT << 8) | (1u << 16);
+    case NUTDB_TT_RawStringLiteral: return FO_LEAF | (NUTDB_NK_LIT_STR << 8);
+    case NUTDB_TT_EscapedSQStringLiteral: return FO_ESTR | (NUTDB_NK_LIT_STR << 8) | (1u << 16);
+    case NUTDB_TT_EscapedDQStringLiteral: return FO_ESTR | (NUTDB_NK_LIT_STR << 8) | (2u << 16);
+    case NUTDB_TT_FloatLiteral: return FO_LEAF | (NUTDB_NK_LIT_FLOAT << 8);
+    case NUTDB_TT_IntegerLiteral: return FO_INT | (NUTDB_NK_LIT_INT << 8);
+    case NUTDB_TT_HexLiteral: return FO_INT | (NUTDB_NK_LIT_INT << 8) | (1u << 24);
+    case NUTDB_TT_Minus: return FO_MINUS;
+    case NUTDB_TT_Plus: return FO_PLUS;
+    case NUTDB_TT_LParen: return FO_LPAREN;
+    default: return FO_BAIL;
+  }
+}
+NUTDB_HD uint16_t fast_optok_entry(uint32_t ty) {
+  uint32_t power = P_Terminator, op = 0, bail = 0;
+  switch (ty) {
+    case NUTDB_TT_Eq: power = P_Comparison; op = 9; break;
+    case NUTDB_TT_NotEq: power = P_Comparison; op = 10; break;
+    case NUTDB_TT_Gt: power = P_Comparison; op = 5; break;
+    case NUTDB_TT_Lt: power = P_Comparison; op = 6; break;
+    case NUTDB_TT_GtEq: power = P_Comparison; op = 7; break;
+    case NUTDB_TT_LtEq: power = P_Comparison; op = 8; break;
+    case NUTDB_TT_BitOr: power = P_BitOr; op = 21; break;
+    case NUTDB_TT_BitXor: power = P_BitXor; op = 23; break;
+    case NUTDB_TT_BitAnd: power = P_BitAnd; op = 22; break;
+    case NUTDB_TT_BitLShift: power = P_BitShift; op = 24; break;
+    case NUTDB_TT_BitRShift: power = P_BitShift; op = 25; break;
+    case NUTDB_TT_Plus: power = P_PlusMinus; op = 0; break;
+    case NUTDB_TT_Minus: power = P_PlusMinus; op = 1; break;
+    case NUTDB_TT_Mul: power = P_MulDivMod; op = 2; break;
+    case NUTDB_TT_Div: power = P_MulDivMod; op = 3; break;
+    case NUTDB_TT_Mod: power = P_MulDivMod; op = 4; break;
+    case NUTDB_TT_LBracket: bail = 1; break;  // index access
+    default: break;
+  }
+  return (uint16_t)(power | (op << 4) | (bail << 12));
+}
+NUTDB_HD uint16_t fast_opkw_entry(uint32_t kw) {
+  uint32_t power = P_Terminator, op = 0, bail = 0;
+  switch (kw) {
+    case KW_AND: power = P_And; op = 11; break;
+    case KW_OR: power = P_Or; op = 12; break;
+    case KW_XOR: power = P_Xor; op = 13; break;
+    case KW_IN: power = P_Comparison; op = 18; break;
+    case KW_LIKE: power = P_Comparison; op = 14; break;
+    case KW_ILIKE: power = P_Comparison; op = 16; break;
+    case KW_NOT: case KW_IS: case KW_BETWEEN: bail = 1; break;
+    default: break;
+  }
+  return (uint16_t)(power | (op << 4) | (bail << 12));
+}
+NUTDB_HD void fast_tables_fill(FastTables& F, uint32_t i) {  // entry i of every table (i < 128)
+  if (i < 48) {
+    F.opnd[i] = fast_opnd_entry(i);
+    F.optok[i] = fast_optok_entry(i);
+  }
+  F.opkw[i] = fast_opkw_entry(i);
+}
+
 template <class Tok, class Nodes, class Text>
 struct FastParser {
+  const FastTables& F;
   Tok& tok;
   Nodes& nd;
   Text& text;
@@ -51,7 +124,8 @@ struct FastParser {
   uint32_t m0 = 0, m1 = 0;          // open interior nodes: outer (ROWS / COLDEF) and inner (clause / ROW / attribute)
   uint32_t width = 0, w = 0, row = 0, seen = 0, tseen = 0, aux = 0;
 
-  NUTDB_HD FastParser(Tok& tk, Nodes& nodes, Text& tx) : tok(tk), nd(nodes), text(tx), cap(nodes.capacity()) {}
+  NUTDB_HD FastParser(const FastTables& ft, Tok& tk, Nodes& nodes, Text& tx)
+      : F(ft), tok(tk), nd(nodes), text(tx), cap(nodes.capacity()) {}
 
   NUTDB_HD void load() {
     ty = tok.type_at(t);
@@ -119,37 +193,37 @@ struct FastParser {
   NUTDB_HD bool expr() {
     for (;;) {
       // ---------------- operand: must_parse_expr_prefix (mod.rs:1222-1347) ----------------
-      switch (ty) {
-        case NUTDB_TT_KeywordOrIdentifier: {
-          if (kw == KW_TRUE || kw == KW_FALSE) {
+      const uint32_t oi = F.opnd[ty];
+      const uint32_t ocls = oi & 15u;
+      if (ocls == FO_LEAF || ocls == FO_INT) {  // a literal (or `*`): one leaf, whatever its type
+        if (ocls == FO_INT && !int_ok(ty, kw, 2)) return false;
+        cur_start = n;
+        cur_kind = (uint8_t)(oi >> 8);
+        if (!emit((uint8_t)(oi >> 8), (uint8_t)(oi >> 16), (uint16_t)(oi >> 24), t)) return false;
+        adv();
+      } else if (ocls == FO_WORD || ocls == FO_DELIM) {
+        if (ocls == FO_WORD) {
+          if (kw == KW_TRUE || kw == KW_FALSE || kw == KW_NULL) {
             cur_start = n;
-            cur_kind = NUTDB_NK_LIT_BOOL;
-            if (!emit(NUTDB_NK_LIT_BOOL, kw == KW_TRUE ? 1 : 0, 0, NUTDB_CN_NOTOK)) return false;
+            cur_kind = kw == KW_NULL ? (uint8_t)NUTDB_NK_LIT_NULL : (uint8_t)NUTDB_NK_LIT_BOOL;
+            if (!emit(cur_kind, kw == KW_TRUE ? 1 : 0, 0, NUTDB_CN_NOTOK)) return false;
             adv();
-            break;
-          }
-          if (kw == KW_NULL) {
-            cur_start = n;
-            cur_kind = NUTDB_NK_LIT_NULL;
-            if (!emit(NUTDB_NK_LIT_NULL, 0, 0, NUTDB_CN_NOTOK)) return false;
-            adv();
-            break;
+            goto operators;
           }
           if (kw == KW_NOT || kw == KW_INTERVAL || kw == KW_IF || kw == KW_CASE) return false;
-          const uint8_t ty2 = tok.type(t + 1);
-          if (ty2 == NUTDB_TT_LParen) {  // function call (mod.rs:1303-1308, :1538-1556)
-            const uint8_t ty3 = tok.type(t + 2);
-            if (ty3 == NUTDB_TT_KeywordOrIdentifier && (tok.kw(t + 2) == KW_SELECT || tok.kw(t + 2) == KW_WITH))
-              return false;
-            const uint32_t m = n;
-            if (!emit(NUTDB_NK_FN_NAME, 0, 0, t)) return false;
-            if (ty3 == NUTDB_TT_RParen) {
-              if (!emit(NUTDB_NK_FNCALL, 7, 0, m)) return false;
-              cur_start = m;
-              cur_kind = NUTDB_NK_FNCALL;
-              adv(3);
-              break;
-            }
+        }
+        const uint8_t ty2 = tok.type(t + 1);
+        if (ty2 == NUTDB_TT_LParen && ocls == FO_WORD) {  // function call (mod.rs:1303-1308, :1538-1556)
+          const uint8_t ty3 = tok.type(t + 2);
+          if (ty3 == NUTDB_TT_KeywordOrIdentifier && (tok.kw(t + 2) == KW_SELECT || tok.kw(t + 2) == KW_WITH)) return false;
+          const uint32_t m = n;
+          if (!emit(NUTDB_NK_FN_NAME, 0, 0, t)) return false;
+          if (ty3 == NUTDB_TT_RParen) {
+            if (!emit(NUTDB_NK_FNCALL, 7, 0, m)) return false;
+            cur_start = m;
+            cur_kind = NUTDB_NK_FNCALL;
+            adv(3);
+          } else {
             if (sp >= DEPTH) return false;
             einfo[sp] = E_CALL;
             emark[sp] = m;
@@ -157,125 +231,60 @@ struct FastParser {
             adv(2);
             continue;  // first argument
           }
-          if (ty2 == NUTDB_TT_Dot) goto qualified;
+        } else if (ty2 == NUTDB_TT_Dot) {  // must_parse_identifier_based_prefix (mod.rs:1506-1523)
+          const uint8_t ty3 = tok.type(t + 2);
+          if (!(ident_string(ty3) || ty3 == NUTDB_TT_Mul)) return false;
+          cur_start = n;
+          cur_kind = NUTDB_NK_IDENT;
+          if (!emit(NUTDB_NK_QUAL, 0, 0, t)) return false;
+          if (!emit(NUTDB_NK_IDENT, ty3 == NUTDB_TT_Mul ? 1 : 0, 1, t + 2)) return false;
+          adv(3);
+        } else {
           cur_start = n;
           cur_kind = NUTDB_NK_IDENT;
           if (!emit(NUTDB_NK_IDENT, 0, 0, t)) return false;
           adv();
-          break;
         }
-        case NUTDB_TT_DelimitedIdentifier: {  // must_parse_identifier_based_prefix (mod.rs:1506-1523)
-          if (tok.type(t + 1) == NUTDB_TT_Dot) {
-          qualified:
-            const uint8_t ty3 = tok.type(t + 2);
-            if (!(ident_string(ty3) || ty3 == NUTDB_TT_Mul)) return false;
-            cur_start = n;
-            cur_kind = NUTDB_NK_IDENT;
-            if (!emit(NUTDB_NK_QUAL, 0, 0, t)) return false;
-            if (!emit(NUTDB_NK_IDENT, ty3 == NUTDB_TT_Mul ? 1 : 0, 1, t + 2)) return false;
-            adv(3);
-          } else {
-            cur_start = n;
-            cur_kind = NUTDB_NK_IDENT;
-            if (!emit(NUTDB_NK_IDENT, 0, 0, t)) return false;
-            adv();
-          }
-          break;
-        }
-        case NUTDB_TT_Mul:
-          cur_start = n;
-          cur_kind = NUTDB_NK_IDENT;
-          if (!emit(NUTDB_NK_IDENT, 1, 0, t)) return false;
-          adv();
-          break;
-        case NUTDB_TT_RawStringLiteral:
-        case NUTDB_TT_EscapedSQStringLiteral:
-        case NUTDB_TT_EscapedDQStringLiteral:
-          if (!string_ok(t, ty)) return false;
-          cur_start = n;
-          cur_kind = NUTDB_NK_LIT_STR;
-          if (!emit(NUTDB_NK_LIT_STR, str_sub(ty), 0, t)) return false;
-          adv();
-          break;
-        case NUTDB_TT_FloatLiteral:
-          cur_start = n;
+      } else if (ocls == FO_ESTR) {
+        if (!string_ok(t, ty)) return false;
+        cur_start = n;
+        cur_kind = NUTDB_NK_LIT_STR;
+        if (!emit(NUTDB_NK_LIT_STR, (uint8_t)(oi >> 16), 0, t)) return false;
+        adv();
+      } else if (ocls == FO_MINUS) {  // only a literal may follow (mod.rs:1259-1269)
+        const uint8_t ty2 = tok.type(t + 1);
+        cur_start = n;
+        if (ty2 == NUTDB_TT_FloatLiteral) {
           cur_kind = NUTDB_NK_LIT_FLOAT;
-          if (!emit(NUTDB_NK_LIT_FLOAT, 0, 0, t)) return false;
-          adv();
-          break;
-        case NUTDB_TT_IntegerLiteral:
-        case NUTDB_TT_HexLiteral:
-          if (!int_ok(ty, kw, 2)) return false;
-          cur_start = n;
+          if (!emit(NUTDB_NK_LIT_FLOAT, 1, 0, t + 1)) return false;
+        } else if (ty2 == NUTDB_TT_IntegerLiteral || ty2 == NUTDB_TT_HexLiteral) {
+          if (!int_ok(ty2, tok.kw(t + 1), 2)) return false;
           cur_kind = NUTDB_NK_LIT_INT;
-          if (!emit(NUTDB_NK_LIT_INT, 0, ty == NUTDB_TT_HexLiteral ? 1 : 0, t)) return false;
-          adv();
-          break;
-        case NUTDB_TT_Minus: {  // only a literal may follow (mod.rs:1259-1269)
-          const uint8_t ty2 = tok.type(t + 1);
-          cur_start = n;
-          if (ty2 == NUTDB_TT_FloatLiteral) {
-            cur_kind = NUTDB_NK_LIT_FLOAT;
-            if (!emit(NUTDB_NK_LIT_FLOAT, 1, 0, t + 1)) return false;
-          } else if (ty2 == NUTDB_TT_IntegerLiteral || ty2 == NUTDB_TT_HexLiteral) {
-            if (!int_ok(ty2, tok.kw(t + 1), 2)) return false;
-            cur_kind = NUTDB_NK_LIT_INT;
-            if (!emit(NUTDB_NK_LIT_INT, 1, ty2 == NUTDB_TT_HexLiteral ? 1 : 0, t + 1)) return false;
-          } else {
-            return false;
-          }
-          adv(2);
-          break;
+          if (!emit(NUTDB_NK_LIT_INT, 1, ty2 == NUTDB_TT_HexLiteral ? 1 : 0, t + 1)) return false;
+        } else {
+          return false;
         }
-        case NUTDB_TT_Plus:  // prefix plus is dropped (mod.rs:1270)
-          adv();
-          continue;
-        case NUTDB_TT_LParen: {  // (mod.rs:1229-1246); a subquery goes to the automaton
-          if (next_is_kw(1, KW_SELECT) || next_is_kw(1, KW_WITH)) return false;
-          if (sp >= DEPTH) return false;
-          einfo[sp] = E_PAREN;
-          emark[sp] = n;
-          sp++;
-          adv();
-          continue;
-        }
-        default: return false;
+        adv(2);
+      } else if (ocls == FO_PLUS) {  // prefix plus is dropped (mod.rs:1270)
+        adv();
+        continue;
+      } else if (ocls == FO_LPAREN) {  // (mod.rs:1229-1246); a subquery goes to the automaton
+        if (next_is_kw(1, KW_SELECT) || next_is_kw(1, KW_WITH)) return false;
+        if (sp >= DEPTH) return false;
+        einfo[sp] = E_PAREN;
+        emark[sp] = n;
+        sp++;
+        adv();
+        continue;
+      } else {
+        return false;
       }
+    operators:
       // ---------------- operators: token_power (mod.rs:1895-1927) + must_parse_expr_infix ----------------
       for (;;) {
-        uint32_t power = P_Terminator, op = 0;
-        switch (ty) {
-          case NUTDB_TT_Eq: power = P_Comparison; op = 9; break;
-          case NUTDB_TT_NotEq: power = P_Comparison; op = 10; break;
-          case NUTDB_TT_Gt: power = P_Comparison; op = 5; break;
-          case NUTDB_TT_Lt: power = P_Comparison; op = 6; break;
-          case NUTDB_TT_GtEq: power = P_Comparison; op = 7; break;
-          case NUTDB_TT_LtEq: power = P_Comparison; op = 8; break;
-          case NUTDB_TT_BitOr: power = P_BitOr; op = 21; break;
-          case NUTDB_TT_BitXor: power = P_BitXor; op = 23; break;
-          case NUTDB_TT_BitAnd: power = P_BitAnd; op = 22; break;
-          case NUTDB_TT_BitLShift: power = P_BitShift; op = 24; break;
-          case NUTDB_TT_BitRShift: power = P_BitShift; op = 25; break;
-          case NUTDB_TT_Plus: power = P_PlusMinus; op = 0; break;
-          case NUTDB_TT_Minus: power = P_PlusMinus; op = 1; break;
-          case NUTDB_TT_Mul: power = P_MulDivMod; op = 2; break;
-          case NUTDB_TT_Div: power = P_MulDivMod; op = 3; break;
-          case NUTDB_TT_Mod: power = P_MulDivMod; op = 4; break;
-          case NUTDB_TT_LBracket: return false;  // index access
-          case NUTDB_TT_KeywordOrIdentifier:
-            switch (kw) {
-              case KW_AND: power = P_And; op = 11; break;
-              case KW_OR: power = P_Or; op = 12; break;
-              case KW_XOR: power = P_Xor; op = 13; break;
-              case KW_IN: power = P_Comparison; op = 18; break;
-              case KW_LIKE: power = P_Comparison; op = 14; break;
-              case KW_ILIKE: power = P_Comparison; op = 16; break;
-              case KW_NOT: case KW_IS: case KW_BETWEEN: return false;
-              default: break;
-            }
-            break;
-          default: break;
-        }
+        const uint32_t e = ty == NUTDB_TT_KeywordOrIdentifier ? F.opkw[kw] : F.optok[ty];
+        if (e >> 12) return false;  // NOT / IS / BETWEEN / index access: the automaton
+        const uint32_t power = e & 15u, op = (e >> 4) & 63u;
         // everything of equal or higher power on the stack is complete (left-associative)
         while (sp > 0 && (einfo[sp - 1] & 3u) == E_OP && ((einfo[sp - 1] >> 2) & 15u) >= power)
           if (!reduce()) return false;

@@ -133,7 +133,13 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
       // same order as the device: the straight-line parser first, the exact automaton if it declines
       bool fast = false;
       if (g_use_fast) {
-        npar::FastParser<HTokAdapter, HNodes, HText> f(tk, nd, tx);
+        static npar::FastTables FT;
+        static bool ft_init = false;
+        if (!ft_init) {
+          for (uint32_t q = 0; q < 128; q++) npar::fast_tables_fill(FT, q);
+          ft_init = true;
+        }
+        npar::FastParser<HTokAdapter, HNodes, HText> f(FT, tk, nd, tx);
         fast = f.try_parse(res);
       }
       if (fast) {
