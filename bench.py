@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4])
@@ -337,9 +337,10 @@ def main():
         ksum = sum(kernel_ms.values())
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp):  # dram bytes per input byte from the committed ncu --set full capture, scaled to this launch
             try:
-                traffic = json.load(open(tp)).get(dom)
+                ent = json.load(open(tp)).get(dom)
+                traffic = int(ent["dram_bytes_per_input_byte"] * n_in) if ent else None
             except Exception:
                 traffic = None
         achieved = alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9
@@ -358,6 +359,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_launch": alg[dom], "kernel_ms": kernel_ms[dom],
+                         "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per input byte x bytes of this launch)",
                          "kernel_share_of_step": kernel_ms[dom] / ksum},
             "roofline_pipeline": {"alg_bytes": b_alg, "B_alg_over_N_in": b_alg / n_in, "T": T, "M": M, "S": n_stmt,
                                   "achieved": b_alg / (dev_ms * 1e-3) / 1e9, "frac": b_alg / (dev_ms * 1e-3) / 1e9 / peak,
