@@ -565,9 +565,32 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
     uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, uint32_t nstmt,
     const uint32_t* __restrict__ punt) {
   __shared__ npar::ParseTables P;
+  __shared__ uint32_t skey[PARSE_THREADS], sorder[PARSE_THREADS];
   stage_parse_tables(gP, &P);
+  // Re-deal the CTA's statements so that a warp gets statements of the same SHAPE (same token count and the
+  // same leading token types: query logs repeat a few templates): the lanes' interpreters then run in step.
+  {
+    const uint32_t i0 = blockIdx.x * PARSE_THREADS + threadIdx.x;
+    uint32_t key = 0xFFFFFFFFu;
+    if (i0 < nslow) {
+      const uint32_t s0 = slow_list[i0];
+      const uint32_t tb0 = stmt[s0].tok_begin, tc0 = stmt[s0].tok_count;
+      uint32_t h = 0;
+      const uint32_t m = min(tc0, 24u);
+      for (uint32_t q = 0; q < m; q++) h = h * 31u + tok_type[tb0 + q];
+      key = (min(tc0, 0xFFFFu) << 15) | (h & 0x7FFFu);
+    }
+    skey[threadIdx.x] = key;
+    __syncthreads();
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < PARSE_THREADS; j++) {
+      const uint32_t kj = skey[j];
+      rank += (kj < key || (kj == key && j < threadIdx.x)) ? 1u : 0u;
+    }
+    sorder[rank] = threadIdx.x;
+  }
   __syncthreads();
-  const uint32_t i = blockIdx.x * PARSE_THREADS + threadIdx.x;
+  const uint32_t i = blockIdx.x * PARSE_THREADS + sorder[threadIdx.x];
   if (i >= nslow) return;
   const uint32_t s = slow_list[i];
   const uint32_t o = off32[s], len = off32[s + 1] - o;
