@@ -362,6 +362,18 @@ typedef struct {
 } NutdbBatchDevice;
 int nutdb_gpu_batch_device(const NutdbBatch *batch, NutdbBatchDevice *out);
 
+/* Statement splitter for raw buffers (query logs).  The reference has no multi-statement entry
+ * (Parser::parse stops after one statement, src/parser/mod.rs:165-172); this produces the `stmt_off`
+ * that nutdb_gpu_parse_batch consumes.  The buffer is read as ONE character stream with the
+ * tokenizer's rules for '..' / ".." literals (doubled quotes, backslash escapes), `..` identifiers,
+ * `--` and block comments (tokenizer/mod.rs:115-184, 313-345, 430-468); every ';' outside of them ends a
+ * statement.  Statement i is [stmt_off[i], stmt_off[i+1]) and includes its ';'; white space between
+ * statements leads the next one; text after the last ';' is a final statement unless it is only white
+ * space.  *stmt_off (n_stmt + 1 entries, stmt_off[0] = 0) is pinned host memory owned by the context,
+ * valid until the next call on it.  len < 2^31.  NUTDB_F_DEVICE_INPUT: `sql` is a device pointer. */
+int nutdb_gpu_split_statements(NutdbCtx *ctx, const uint8_t *sql, uint64_t len, uint32_t flags,
+                               const uint64_t **stmt_off, uint64_t *n_stmt);
+
 /* Single-statement convenience = Parser::parse(sql) (batch of one). */
 int nutdb_gpu_parse(NutdbCtx *ctx, const uint8_t *sql, uint64_t len, NutdbBatch *out);
 

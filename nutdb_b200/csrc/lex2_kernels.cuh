@@ -538,6 +538,96 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
   }
 }
 
+// ---- statement splitter: every ';' in code context ends a statement -----------------
+// bit i: byte i of the thread's window is ';'
+__device__ __forceinline__ uint32_t semicolon_mask(const Lex2Shared& S, uint32_t tile_begin, uint32_t base, uint32_t valid) {
+  const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(S.text) + (base - tile_begin));
+  const uint4 q0 = wp[0], q1 = wp[1];
+  const uint32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t x = v[i] ^ 0x3B3B3B3Bu;                                   // zero byte <=> ';'
+    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 in every zero byte
+    m |= (((z >> 7) * 0x00204081u) >> 21 & 0xFu) << (4 * i);                 // gather the four flags
+  }
+  return m & valid;
+}
+
+// Emit = false: number of code-context ';' per warp block / tile; Emit = true: offsets[1 + k] = position after the k-th
+template <bool Emit>
+__global__ void __launch_bounds__(L2_THREADS) k_split(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
+                                                      uint32_t n, const LexTables* __restrict__ gT,
+                                                      const nlex2::Lex2Tables* __restrict__ gK,
+                                                      const uint32_t* __restrict__ localA, const uint8_t* __restrict__ tileEntA,
+                                                      uint32_t* __restrict__ gmask, size_t mstride, uint2* __restrict__ localS,
+                                                      uint2* __restrict__ tileS, const uint2* __restrict__ tilePrefS,
+                                                      uint64_t* __restrict__ offsets) {
+  __shared__ Lex2Shared S;
+  __shared__ uint32_t wsum[L2_WARPS];
+  const uint32_t tile_begin = blockIdx.x * L2_TILE;
+  stage_tile2(text, bitmap, tile_begin, n, S, gT, gK);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t full = 0xFFFFFFFFu;
+  Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text), tile_begin, n};
+  const uint32_t blk = tile_begin + (uint32_t)warp * L2_SEG;
+  const uint32_t widx = blockIdx.x * L2_WARPS + warp;
+  uint32_t total = 0;
+  if (blk < n) {
+    WinSetup u;
+    setup_window<false, false>(S, src, bitmap, tile_begin, blk, n, lane, gmask, mstride, u);
+    const bool live = u.base < n;
+    const uint32_t f = live ? window_fn(S.T, u) : NUTDB_VEC8_ID;
+    uint32_t excl;
+    warp_scan_vec8(f, lane, excl);
+    const uint8_t s_warp = (uint8_t)vec8_apply(localA[widx], tileEntA[blockIdx.x]);
+    const uint8_t s_in = (uint8_t)vec8_apply(excl, s_warp);
+    nlex2::WinCtx o;
+    if (live) nlex2::ctx_window(u.w, u.ev, u.base, u.nx, s_in, u.prev_byte, o);
+    const uint32_t semis = live ? (o.ct & semicolon_mask(S, tile_begin, u.base, u.w.valid)) : 0u;
+    uint32_t cnt = (uint32_t)__popc(semis);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t c2 = __shfl_up_sync(full, cnt, d);
+      if (lane >= d) cnt += c2;
+    }
+    total = __shfl_sync(full, cnt, 31);
+    if (Emit) {
+      uint32_t idx = tilePrefS[blockIdx.x].x + localS[widx].x + cnt - (uint32_t)__popc(semis);
+      uint32_t todo = semis;
+      while (todo) {
+        const int i = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        offsets[1u + idx++] = (uint64_t)u.base + (uint64_t)i + 1ull;
+      }
+    }
+  }
+  if (!Emit) {
+    if (lane == 0) wsum[warp] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      for (int i = 0; i < L2_WARPS; i++) {
+        localS[blockIdx.x * L2_WARPS + i] = make_uint2(acc, 0u);
+        acc += wsum[i];
+      }
+      tileS[blockIdx.x] = make_uint2(acc, 0u);
+    }
+  }
+}
+
+// is there anything but whitespace in [from, n)?
+__global__ void k_tail_content(const uint8_t* __restrict__ text, uint32_t from, uint32_t n, uint32_t* __restrict__ flag) {
+  for (uint32_t p = from + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const uint8_t b = text[p];
+    if (!(b == ' ' || b == '\t' || b == '\n' || b == '\r')) {
+      atomicOr(flag, 1u);
+      return;
+    }
+  }
+}
+
 // ---- exact path for flagged statements: one thread per statement runs the walker of lex_core.cuh ----
 struct StmtSrc {
   const uint8_t* text;

@@ -767,9 +767,9 @@ struct NutdbCtx {
   // device buffers (grow only)
   DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState;
+      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
-  HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry;
+  HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry, hSplit;
   float ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
   uint32_t n_slow = 0;  // statements of the last batch that needed the exact automaton
@@ -874,11 +874,12 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState};
+                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
+                 &c->splitTile, &c->splitPref, &c->splitOff};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
   HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
-                  &c->hRetry};
+                  &c->hRetry, &c->hSplit};
   for (HostBuf* b : h)
     if (b->p) cudaFreeHost(b->p);
 }
@@ -1321,6 +1322,90 @@ int nutdb_gpu_parse(NutdbCtx* ctx, const uint8_t* sql, uint64_t len, NutdbBatch*
   const uint64_t off[2] = {0, len};
   static const uint8_t empty[1] = {0};
   return nutdb_gpu_parse_batch(ctx, sql ? sql : empty, off, 1, 0, out);
+}
+
+int nutdb_gpu_split_statements(NutdbCtx* ctx, const uint8_t* sql, uint64_t len, uint32_t flags, const uint64_t** stmt_off,
+                               uint64_t* n_stmt) {
+  if (!ctx) return NUTDB_E_CUDA;
+  if (!stmt_off || !n_stmt || (len > 0 && !sql) || len >= 0x7FFFFFFFull) {
+    ctx->err = "bad argument (null pointer, or 2^31 bytes or more)";
+    return NUTDB_E_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ctx->launches = 0;
+  ctx->recs.clear();
+  ctx->ev_used = 0;
+  const uint32_t n = (uint32_t)len;
+  const uint32_t ntiles = (n + L2_TILE - 1) / L2_TILE;
+  const size_t nchunks = (size_t)ntiles * (L2_TILE / 32);
+  uint32_t* hS = (uint32_t*)ctx->hSmall.p;
+  uint32_t* dS = (uint32_t*)ctx->small.p;
+  uint64_t nsemi = 0;
+  bool tail = false;
+  if (n > 0) {
+    const uint8_t* dText;
+    if ((flags & NUTDB_F_DEVICE_INPUT) && (reinterpret_cast<uintptr_t>(sql) & 15u) == 0) {
+      dText = sql;
+    } else {
+      ENSURE_DEV(text, (size_t)ntiles * L2_TILE + 16);
+      CK(cudaMemcpyAsync(ctx->text.p, sql, n, (flags & NUTDB_F_DEVICE_INPUT) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+      dText = (const uint8_t*)ctx->text.p;
+    }
+    const size_t nwarps = (size_t)ntiles * L2_WARPS;
+    ENSURE_DEV(bitmap, 4 * (nchunks + 1));
+    ENSURE_DEV(localA, 4 * nwarps);
+    ENSURE_DEV(tileA, 4 * (size_t)ntiles);
+    ENSURE_DEV(entA, ntiles);
+    ENSURE_DEV(winMasks, 4 * nchunks * L2_NMASK + 64);
+    ENSURE_DEV(splitLocal, 8 * nwarps);
+    ENSURE_DEV(splitTile, 8 * (size_t)ntiles);
+    ENSURE_DEV(splitPref, 8 * (size_t)ntiles);
+    // the whole buffer is ONE character stream: only byte 0 starts a "statement" for the context automaton
+    CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 1), st));
+    const uint32_t one = 1u;
+    CK(cudaMemcpyAsync(ctx->bitmap.p, &one, 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dS, 0, 64, st));
+    const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
+    LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2, (uint32_t*)ctx->localA.p,
+                                                                  (uint32_t*)ctx->tileA.p, (uint32_t*)ctx->winMasks.p, nchunks));
+    LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
+    LAUNCH("k_split_count", k_split<false><<<ntiles, L2_THREADS, 0, st>>>(
+                                dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
+                                (uint32_t*)ctx->winMasks.p, nchunks, (uint2*)ctx->splitLocal.p, (uint2*)ctx->splitTile.p, nullptr,
+                                nullptr));
+    LAUNCH("k_scan_S", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->splitTile.p, (uint2*)ctx->splitPref.p,
+                                                                         ntiles, (uint2*)(dS + 8)));
+    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nsemi = hS[8];
+    ENSURE_DEV(splitOff, 8 * (nsemi + 2));
+    ENSURE_HOST(hSplit, 8 * (nsemi + 3));
+    LAUNCH("k_split_emit", k_split<true><<<ntiles, L2_THREADS, 0, st>>>(
+                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
+                               (uint32_t*)ctx->winMasks.p, nchunks, (uint2*)ctx->splitLocal.p, nullptr,
+                               (const uint2*)ctx->splitPref.p, (uint64_t*)ctx->splitOff.p));
+    CK(cudaMemcpyAsync((uint64_t*)ctx->hSplit.p + 1, (uint64_t*)ctx->splitOff.p + 1, 8 * nsemi, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t* off = (uint64_t*)ctx->hSplit.p;
+    off[0] = 0;
+    const uint64_t last = nsemi ? off[nsemi] : 0;
+    if (last < n) {  // text after the last ';' is a statement of its own unless it is only whitespace
+      k_tail_content<<<64, 256, 0, st>>>(dText, (uint32_t)last, n, dS + 12);
+      ctx->launches++;
+      CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      tail = hS[12] != 0;
+    }
+    if (tail) off[nsemi + 1] = n;
+  } else {
+    ENSURE_HOST(hSplit, 64);
+    ((uint64_t*)ctx->hSplit.p)[0] = 0;
+  }
+  CK(cudaGetLastError());
+  *stmt_off = (const uint64_t*)ctx->hSplit.p;
+  *n_stmt = nsemi + (tail ? 1 : 0);
+  return NUTDB_OK;
 }
 
 int nutdb_gpu_last_timing(const NutdbCtx* ctx, float ms[5]) {

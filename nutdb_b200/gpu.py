@@ -61,6 +61,9 @@ def lib():
     L.nutdb_gpu_batch_device.argtypes = [C.POINTER(NutdbBatch), C.POINTER(NutdbBatchDevice)]
     L.nutdb_gpu_parse.restype = C.c_int
     L.nutdb_gpu_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(NutdbBatch)]
+    L.nutdb_gpu_split_statements.restype = C.c_int
+    L.nutdb_gpu_split_statements.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                                             C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.nutdb_gpu_last_timing.restype = C.c_int
     L.nutdb_gpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float * 5)]
     L.nutdb_gpu_last_launches.restype = C.c_int
@@ -146,6 +149,18 @@ class Context:
         o = np.ascontiguousarray(offs, np.uint64)
         assert t.dtype == np.uint8 and o.ndim == 1 and len(o) >= 1
         return self.parse_batch_raw(t.ctypes.data, o.ctypes.data, len(o) - 1, flags, copy)
+
+    def split_statements(self, text, flags=0):
+        """Raw buffer -> uint64 offsets (n+1) of its statements: every ';' outside literals / comments ends one."""
+        if isinstance(text, (bytes, bytearray, memoryview)):
+            t = np.frombuffer(text, np.uint8)
+        else:
+            t = np.ascontiguousarray(text)
+        off, n = C.c_void_p(), C.c_uint64(0)
+        rc = lib().nutdb_gpu_split_statements(self._h, t.ctypes.data if len(t) else None, len(t), flags, C.byref(off), C.byref(n))
+        if rc != 0:
+            raise NutdbGpuError(f"nutdb_gpu_split_statements failed ({rc}): {self.last_error()}")
+        return _view(off.value, n.value + 1, np.uint64).copy()
 
     def timing(self):
         ms = (C.c_float * 5)()

@@ -210,6 +210,33 @@ std::vector<uint32_t> g_xoff;
 
 extern "C" {
 
+// Sequential statement splitter: the context automaton of lex_core.cuh run byte by byte over the whole buffer
+// (the definition the scan-based GPU splitter has to reproduce).  Returns n_stmt; offs gets n_stmt + 1 entries.
+int64_t emul_split(const uint8_t* text, uint64_t n, uint64_t* offs, uint64_t cap) {
+  uint64_t k = 0;
+  offs[k++] = 0;
+  uint8_t A = A_C, prev = 0, esc = 0;
+  for (uint64_t pos = 0; pos < n; pos++) {
+    const uint8_t b = text[pos];
+    const uint8_t ev = a_event(b, prev, esc != 0);
+    if (A <= A_CX && b == ';') {
+      if (k >= cap) return -1;
+      offs[k++] = pos + 1;
+    }
+    A = a_next(A, ev);
+    esc = (b == '\\' && !esc) ? 1 : 0;
+    prev = b;
+  }
+  bool tail = false;
+  for (uint64_t pos = offs[k - 1]; pos < n; pos++)
+    if (!(text[pos] == ' ' || text[pos] == '\t' || text[pos] == '\n' || text[pos] == '\r')) tail = true;
+  if (tail) {
+    if (k >= cap) return -1;
+    offs[k++] = n;
+  }
+  return (int64_t)k - 1;
+}
+
 uint64_t emul_lex2_punts(void) { return g_punts; }
 
 // Tokens of every statement (no Whitespace / Comment) + per-STATEMENT token ranges.

@@ -132,3 +132,15 @@ def parse_batch(text, offs, chunk=32, stack_cap=4096):
     b.node, b.err = node[:nn.value], err[:ne.value]
     b.tok_type, b.tok_start, b.tok_end, b.tok_kw = ty[:nt.value], st[:nt.value], en[:nt.value], kw[:nt.value]
     return b
+
+
+def split(text):
+    """Sequential reference of the statement splitter -> uint64 offsets (n + 1)."""
+    L = parse_lib()
+    L.emul_split.restype = C.c_int64
+    L.emul_split.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    t = np.frombuffer(bytes(text), np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text)
+    offs = np.zeros(len(t) + 2, np.uint64)
+    n = L.emul_split(t.ctypes.data, len(t), offs.ctypes.data, len(offs))
+    assert n >= 0
+    return offs[:n + 1].copy()

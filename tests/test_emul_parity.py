@@ -165,3 +165,12 @@ def test_keyword_hash_matches_keyword_table():
         assert E.keyword(w) == k and E.keyword(w.upper()) == k and E.keyword(w.capitalize()) == k
     for w in ["selec", "selectt", "a", "tables", "fro", "x" * 10, "nulls", "byy"]:
         assert E.keyword(w) == 0
+
+
+def test_sequential_splitter_reference():
+    # the definition the GPU splitter is tested against (tests/test_gpu_parity.py::test_statement_splitter)
+    assert E.split(b"select ';' , \";\" , `;` ; select 2 -- ; x\n; /* ; */ select 3;  \n").tolist() == [0, 24, 42, 60]
+    assert E.split(b"").tolist() == [0] and E.split(b"select 1").tolist() == [0, 8]
+    assert E.split(b"select 1;\n\n\t ").tolist() == [0, 9]
+    text, offs = W.generate(2, 64 << 10)
+    assert np.array_equal(E.split(text[:int(offs[-1])])[1:], offs[1:] - 1)

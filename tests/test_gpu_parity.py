@@ -199,3 +199,27 @@ def test_stream_parser_chunks_match_one_batch(ctx):
     assert np.array_equal(nodes, whole.node)
     assert np.array_equal(status, whole.stmt["status"]) and np.array_equal(ncount, whole.stmt["node_count"])
     assert sum(len(got[k][2]) for k in got) == whole.n_err
+
+
+def test_statement_splitter(ctx):
+    import emul_lib as E
+    # a query log as one buffer: the generators end every statement with ";\n"
+    for config in (2, 3, 4):
+        text, offs = W.generate(config, 3 << 20)
+        buf = text[:int(offs[-1])]
+        got = ctx.split_statements(buf)
+        want = E.split(buf)
+        assert np.array_equal(got, want)
+        if config != 3:   # valid statements: one ';' each, at the end (malformed ones of config 3 may hide or add some)
+            assert len(got) == len(offs) and np.array_equal(got[1:], offs[1:] - 1)
+        # and the split batch parses like the original one
+        b1 = ctx.parse_batch(buf, got)
+        b0 = ctx.parse_batch(text, offs)
+        if config != 3:
+            assert np.array_equal(b1.stmt["status"], b0.stmt["status"])
+            assert np.array_equal(b1.node["kind"], b0.node["kind"])
+    cases = [b"", b";", b" ;; ", b"select 1", b"select ';' , \";\" , `;` ; select 2 -- ; x\n; /* ; */ select 3;  \n",
+             b"select 'it''s; ok'; select 'a\\'; b'; select 4", b"select 1 /* open ; comment", b"select 'open ; string",
+             b"a;" * 5000, b"-- only a comment; really\n", b"select 1;\n\n\t "]
+    for c in cases + fuzz.fuzz_statements([b"; ".join(CORPUS[:4])], 200, seed=5, max_mut=6):
+        assert np.array_equal(ctx.split_statements(c), E.split(c)), c
