@@ -34,7 +34,9 @@ using namespace nlex;
 
 enum : uint16_t {
   K_SQ = 1, K_DQ = 2, K_BT = 4, K_NL = 8, K_BS = 16, K_DASH = 32, K_SLASH = 64, K_STAR = 128,
-  K_L = 256, K_D = 512, K_DOT = 1024, K_OP = 2048, K_P = 4096, K_WS = 8192, K_X = 16384
+  K_L = 256, K_D = 512, K_DOT = 1024, K_OP = 2048, K_P = 4096, K_WS = 8192,
+  K_IE = 16384,  // may follow an identifier (tokenizer/mod.rs:486-503)
+  K_NE = 32768   // may follow a numeric literal / query parameter (tokenizer/mod.rs:506-543)
 };
 
 struct Lex2Tables {
@@ -43,7 +45,7 @@ struct Lex2Tables {
 
 inline void build_lex2_tables(Lex2Tables& T) {
   for (int i = 0; i < 256; i++) {
-    uint16_t k = K_X;
+    uint16_t k = 0;  // '@' '$' '#' '?' '\\' controls, DEL, bytes >= 0x80: no class (invalid in code or left to the exact path)
     uint8_t c = (uint8_t)i;
     if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_') k = K_L;
     else if (c >= '0' && c <= '9') k = K_D;
@@ -54,7 +56,7 @@ inline void build_lex2_tables(Lex2Tables& T) {
         case '`': k = K_BT; break;
         case '\n': case '\r': k = K_NL | K_WS; break;
         case ' ': case '\t': k = K_WS; break;
-        case '\\': k = K_BS | K_X; break;
+        case '\\': k = K_BS; break;
         case '-': k = K_DASH; break;
         case '/': k = K_SLASH; break;
         case '*': k = K_STAR | K_P; break;
@@ -62,15 +64,21 @@ inline void build_lex2_tables(Lex2Tables& T) {
         case '<': case '>': case '=': case '!': k = K_OP; break;
         case '(': case ')': case '[': case ']': case '{': case '}': case ',': case ':': case '+': case '%':
         case '&': case '|': case '^': case '~': case ';': k = K_P; break;
-        default: break;  // '@' '$' '#' '?' controls, DEL, every byte >= 0x80: invalid in code or left to the exact path
+        default: break;
       }
+    {
+      const char* ident_end = "+-*/%&|^><=!.,;[](){}\t\n\r ";
+      const char* num_end = "+-*/%&|^><=!,:;])}\t\n\r ";
+      if (c != 0 && std::strchr(ident_end, c)) k |= K_IE;
+      if (c != 0 && std::strchr(num_end, c)) k |= K_NE;
+    }
     T.cls[i] = k;
   }
 }
 
 // raw class masks of one 32-byte window (bit i = byte base+i); bytes at or beyond the batch end are 0
 struct Win {
-  uint32_t sq, dq, bt, nl, bs, dash, slash, star, L, D, DOT, OP, P, WS;
+  uint32_t sq, dq, bt, nl, bs, dash, slash, star, L, D, DOT, OP, P, WS, IE, NE;
   uint32_t bnd;    // a statement starts at this byte; also set at position n (virtual end) if inside the window
   uint32_t valid;  // bytes that exist (< n)
 };
@@ -359,6 +367,8 @@ struct WinTok {
   uint64_t L64, D64, DOT64, W64, bnd64, contW, contO;
   uint32_t nbnd;     // bit i: byte i+1 starts a statement (or is the batch end)
   uint32_t nextW, nextD, nextDOT, nextOP;  // bit i: byte i+1 has that class and belongs to the same statement
+  uint32_t endI, endN;   // bit i: byte i+1 may follow an identifier / a number (or the statement ends there)
+  uint32_t EI, EX;       // ends of runs of [A-Za-z0-9_]: identifiers decided by masks alone / numbers and odd cases
 };
 NUTDB_HD WinTok make_wintok(const Win& w, uint32_t ct, const Hist& h, const Next& nx) {
   WinTok k;
@@ -377,6 +387,23 @@ NUTDB_HD WinTok make_wintok(const Win& w, uint32_t ct, const Hist& h, const Next
   k.nextD = ((w.D >> 1) | ((uint32_t)((nx.cls & K_D) != 0) << 31)) & ~k.nbnd;
   k.nextDOT = ((w.DOT >> 1) | ((uint32_t)((nx.cls & K_DOT) != 0) << 31)) & ~k.nbnd;
   k.nextOP = ((w.OP >> 1) | ((uint32_t)((nx.cls & K_OP) != 0) << 31)) & ~k.nbnd;
+  k.endI = ((w.IE >> 1) | ((uint32_t)((nx.cls & K_IE) != 0) << 31)) | k.nbnd;
+  k.endN = ((w.NE >> 1) | ((uint32_t)((nx.cls & K_NE) != 0) << 31)) | k.nbnd;
+  // Word runs end where the next byte is no word byte.  Runs that start with a letter inside the look-back
+  // are identifiers and need nothing but masks; runs that start with a digit (numbers), at the very first
+  // look-back position (start unknown) or that a statement start cuts in two go through tok_word().
+  const uint32_t E = ct & (w.L | w.D) & ~k.nextW;
+  if (k.W64 & (k.W64 << 1) & k.bnd64) {
+    k.EX = E;
+  } else {
+    const uint64_t starts = k.W64 & ~(k.W64 << 1);
+    const uint64_t sel = starts & (k.D64 | 1ull);
+    const uint64_t sum = k.W64 + sel;  // the carry runs through each selected run and lands right behind it
+    uint64_t ends = (sum & ~k.W64) >> 1;
+    if (sum < k.W64) ends |= 1ull << 63;  // a selected run ends with the window's last byte
+    k.EX = E & (uint32_t)(ends >> 32);
+  }
+  k.EI = E & ~k.EX;
   return k;
 }
 template <class Src>
@@ -391,12 +418,11 @@ NUTDB_HD LaneTok tok_word(const LexTables& T, Src& src, const WinTok& k, const N
   LaneTok r;
   const uint32_t pos = base + (uint32_t)i;
   const int p = 32 + i;
-  const bool nbnd = ((k.nbnd >> i) & 1u) != 0;
   const int st = run_start(k.contW, p);
   if (st < 0) { r.bad = 1; return r; }
   const uint32_t abs_st = base + (uint32_t)st - 32u;
   if (!((k.D64 >> st) & 1ull)) {  // identifier / keyword (tokenizer/mod.rs:262-282)
-    if (!(nbnd || (T.prop[next_byte(src, k, nx, base, i)] & PR_IDENT_END))) { r.bad = 1; return r; }
+    if (!((k.endI >> i) & 1u)) { r.bad = 1; return r; }
     r.has = 1;
     r.type = NUTDB_TT_KeywordOrIdentifier;
     r.start = abs_st;
@@ -410,7 +436,7 @@ NUTDB_HD LaneTok tok_word(const LexTables& T, Src& src, const WinTok& k, const N
     if (left_dot) r.bad = 1;    // second dot of one numeric token: error
     return r;
   }
-  if (!(nbnd || (T.prop[next_byte(src, k, nx, base, i)] & PR_NUM_END))) { r.bad = 1; return r; }
+  if (!((k.endN >> i) & 1u)) { r.bad = 1; return r; }
   r.has = 1;
   r.end = pos + 1;
   if (!left_dot) {  // integer literal (tokenizer/mod.rs:196-238)
@@ -459,8 +485,7 @@ NUTDB_HD LaneTok tok_dot(const LexTables& T, Src& src, const WinTok& k, const Ne
   r.has = 1;
   r.end = pos + 1;
   if (is_float) {
-    const bool nbnd = ((k.nbnd >> i) & 1u) != 0;
-    if (!(nbnd || (T.prop[next_byte(src, k, nx, base, i)] & PR_NUM_END))) { r.bad = 1; return r; }
+    if (!((k.endN >> i) & 1u)) { r.bad = 1; return r; }
     r.type = NUTDB_TT_FloatLiteral;
     r.start = base + (uint32_t)fs - 32u;
   } else {
@@ -560,7 +585,9 @@ NUTDB_HD uint32_t win_has_mask(const LexTables& T, Src& src, const Win& w, const
   bad = win_bad_mask(src, w, o, base, prev_byte);
   const WinTok k = make_wintok(w, o.ct, h, nx);
   uint32_t has = simple_token_mask(w, o, nx, k) | o.close;
-  uint32_t todo = o.ct & (w.L | w.D) & ~k.nextW;  // ends of word / number runs
+  has |= k.EI & k.endI;    // identifiers / keywords: the byte after must be allowed to follow one
+  bad |= k.EI & ~k.endI;
+  uint32_t todo = k.EX;    // numbers, runs with unknown start
   while (todo) {
     const int i = ctz32(todo);
     todo &= todo - 1;
@@ -633,8 +660,32 @@ NUTDB_HD void win_emit(const LexTables& T, Src& src, Sink& sink, const Win& w, c
     const uint8_t type = b == '-' ? (uint8_t)NUTDB_TT_Minus : (b == '/' ? (uint8_t)NUTDB_TT_Div : T.single_tt[b]);
     sink.token(index_of(i), type, pos - sst, pos + 1u - sst, 0);
   }
-  // words and numbers
-  todo = o.ct & (w.L | w.D) & ~k.nextW & has;
+  // identifiers / keywords: the start is the highest run start at or below the end
+  {
+    const uint64_t starts = k.W64 & ~(k.W64 << 1);
+    todo = k.EI & has;
+    while (todo) {
+      const int i = ctz32(todo);
+      todo &= todo - 1;
+      const int p = 32 + i;
+      const int st = 63 - clz64(starts & (p >= 63 ? ~0ull : ((2ull << p) - 1ull)));
+      const uint32_t start = base + (uint32_t)st - 32u, end = base + (uint32_t)i + 1u, sst = stmt_of(i);
+      const uint32_t len = end - start;
+      uint8_t kw = 0;
+      if (len >= 2 && len <= 10) {
+        const uint8_t* wp = src.span(start, len);  // the word as contiguous bytes (almost always)
+        if (wp) {
+          kw = keyword_lookup(T, len, [wp](uint32_t q) { return wp[q]; });
+        } else {
+          Src& sr = src;
+          kw = keyword_lookup(T, len, [&sr, start](uint32_t q) { return sr.byte(start + q); });
+        }
+      }
+      sink.token(index_of(i), NUTDB_TT_KeywordOrIdentifier, start - sst, end - sst, kw);
+    }
+  }
+  // numbers (and the odd word runs)
+  todo = k.EX & has;
   while (todo) {
     const int i = ctz32(todo);
     todo &= todo - 1;
@@ -644,14 +695,9 @@ NUTDB_HD void win_emit(const LexTables& T, Src& src, Sink& sink, const Win& w, c
     if (t.type == NUTDB_TT_KeywordOrIdentifier) {
       const uint32_t len = t.end - t.start;
       if (len >= 2 && len <= 10) {
-        const uint8_t* wp = src.span(t.start, len);  // the word as contiguous bytes (almost always)
-        if (wp) {
-          kw = keyword_lookup(T, len, [wp](uint32_t q) { return wp[q]; });
-        } else {
-          Src& sr = src;
-          const uint32_t s0 = t.start;
-          kw = keyword_lookup(T, len, [&sr, s0](uint32_t q) { return sr.byte(s0 + q); });
-        }
+        Src& sr = src;
+        const uint32_t s0 = t.start;
+        kw = keyword_lookup(T, len, [&sr, s0](uint32_t q) { return sr.byte(s0 + q); });
       }
     }
     sink.token(index_of(i), t.type, t.start - sst, t.end - sst, kw);

@@ -71,7 +71,7 @@ template <bool All>
 __device__ __forceinline__ void build_masks(const Lex2Shared& S, const Tile2Src& src, uint32_t blk, uint32_t n, int lane,
                                             nlex2::Win& w) {
   const uint32_t full = 0xFFFFFFFFu;
-  w.sq = w.dq = w.bt = w.nl = w.bs = w.dash = w.slash = w.star = w.L = w.D = w.DOT = w.OP = w.P = w.WS = 0u;
+  w.sq = w.dq = w.bt = w.nl = w.bs = w.dash = w.slash = w.star = w.L = w.D = w.DOT = w.OP = w.P = w.WS = w.IE = w.NE = 0u;
 #pragma unroll 4
   for (int jj = 0; jj < 32; jj++) {
     const uint32_t pos = blk + 32u * (uint32_t)jj + (uint32_t)lane;
@@ -152,10 +152,12 @@ __device__ __forceinline__ void build_masks_transpose(const Lex2Shared& S, uint3
   w.OP = A[11] & valid;
   w.P = A[12] & valid;
   w.WS = A[13] & valid;
+  w.IE = A[14] & valid;
+  w.NE = A[15] & valid;
 }
 
 // class masks of every window, computed once by k_lex2_fn: 14 arrays of nwin words (structure of arrays)
-#define L2_NMASK 14
+#define L2_NMASK 16
 __device__ __forceinline__ void store_masks(uint32_t* __restrict__ g, size_t stride, uint32_t win, const nlex2::Win& w) {
   g[0 * stride + win] = w.sq;
   g[1 * stride + win] = w.dq;
@@ -171,6 +173,8 @@ __device__ __forceinline__ void store_masks(uint32_t* __restrict__ g, size_t str
   g[11 * stride + win] = w.OP;
   g[12 * stride + win] = w.P;
   g[13 * stride + win] = w.WS;
+  g[14 * stride + win] = w.IE;
+  g[15 * stride + win] = w.NE;
 }
 __device__ __forceinline__ void load_masks(const uint32_t* __restrict__ g, size_t stride, uint32_t win, nlex2::Win& w) {
   w.sq = g[0 * stride + win];
@@ -187,6 +191,8 @@ __device__ __forceinline__ void load_masks(const uint32_t* __restrict__ g, size_
   w.OP = g[11 * stride + win];
   w.P = g[12 * stride + win];
   w.WS = g[13 * stride + win];
+  w.IE = g[14 * stride + win];
+  w.NE = g[15 * stride + win];
 }
 
 struct WinSetup {

@@ -79,6 +79,8 @@ void setup_window(const Env& e, uint32_t blk, uint32_t base, bool virt, WinSetup
     if (k & K_OP) w.OP |= bit;
     if (k & K_P) w.P |= bit;
     if (k & K_WS) w.WS |= bit;
+    if (k & K_IE) w.IE |= bit;
+    if (k & K_NE) w.NE |= bit;
   }
   uint32_t bnd = base < e.n ? (e.bitmap[base >> 5] & w.valid) : 0u;
   if (virt && e.n >= base && e.n - base < 32u) bnd |= 1u << (e.n - base);
