@@ -12,8 +12,9 @@
 #define L2_SEG 1024                     // bytes per warp
 #define L2_TILE (L2_WARPS * L2_SEG)     // bytes per block
 
+#define L2_HALO 32  // bytes in front of and behind the tile that are staged too (look-back / look-ahead of edge windows)
 struct alignas(16) Lex2Shared {
-  alignas(16) uint32_t text[L2_TILE / 4];  // filled with 16-byte stores
+  alignas(16) uint32_t text[(L2_TILE + 2 * L2_HALO) / 4];  // [tile_begin - 32, tile_end + 32), filled with 16-byte stores
   uint32_t bm[L2_TILE / 32];
   LexTables T;
   nlex2::Lex2Tables K;
@@ -26,15 +27,16 @@ struct Tile2Src {
   const uint8_t* text;
   const uint8_t* sm;
   uint32_t tile_begin, n;
+  // sm points at the tile's first byte; the halo lies at sm[-32..-1] and sm[L2_TILE..L2_TILE+31]
   __device__ __forceinline__ uint8_t byte(uint32_t p) const {
-    const uint32_t r = p - tile_begin;
-    if (r < L2_TILE) return sm[r];
+    const uint32_t r = p - tile_begin + L2_HALO;
+    if (r < L2_TILE + 2 * L2_HALO) return sm[(int)r - L2_HALO];
     return far_byte(text, p, n);
   }
-  // [p, p + len) as one contiguous run of shared memory, or nullptr if it leaves the tile
+  // [p, p + len) as one contiguous run of shared memory, or nullptr if it leaves the staged range
   __device__ __forceinline__ const uint8_t* span(uint32_t p, uint32_t len) const {
-    const uint32_t r = p - tile_begin;
-    return (r < L2_TILE && r + len <= L2_TILE) ? sm + r : nullptr;
+    const uint32_t r = p - tile_begin + L2_HALO;
+    return (r < L2_TILE + 2 * L2_HALO && r + len <= L2_TILE + 2 * L2_HALO) ? sm + ((int)r - L2_HALO) : nullptr;
   }
 };
 
@@ -44,14 +46,21 @@ __device__ __forceinline__ void stage_tile2(const uint8_t* text, const uint32_t*
   {
     const uint32_t* a = reinterpret_cast<const uint32_t*>(gK);
     uint32_t* b = reinterpret_cast<uint32_t*>(&S.K);
-    for (uint32_t i = threadIdx.x; i < sizeof(nlex2::Lex2Tables) / 4; i += blockDim.x) b[i] = a[i];
+    for (uint32_t i = threadIdx.x; i < sizeof(nlex2::Lex2Tables) / 4; i += L2_THREADS) b[i] = a[i];
   }
   const uint4* src = reinterpret_cast<const uint4*>(text + tile_begin);
-  uint4* dst = reinterpret_cast<uint4*>(S.text);
+  uint4* dst = reinterpret_cast<uint4*>(S.text) + L2_HALO / 16;
 #pragma unroll
   for (uint32_t k = threadIdx.x; k < L2_TILE / 16; k += L2_THREADS) {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (tile_begin + 16u * k < n) v = __ldg(src + k);
+    dst[k] = v;
+  }
+  if (threadIdx.x < 2 * L2_HALO / 16) {  // the halo: two 16-byte pieces on either side (zero outside the batch)
+    const int k = threadIdx.x < L2_HALO / 16 ? (int)threadIdx.x - L2_HALO / 16 : (int)(L2_TILE / 16) + (int)threadIdx.x - L2_HALO / 16;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const long long p = (long long)tile_begin + 16ll * k;
+    if (p >= 0 && p < (long long)n) v = __ldg(src + k);
     dst[k] = v;
   }
   S.bm[threadIdx.x] = bitmap[(tile_begin >> 5) + threadIdx.x];
@@ -119,7 +128,7 @@ __device__ __forceinline__ void entry_esc(const Tile2Src& src, const uint32_t* b
 // registers, 4 butterfly stages) turns "16 class bits per byte" into "32 byte bits per class".
 __device__ __forceinline__ void build_masks_transpose(const Lex2Shared& S, uint32_t tile_begin, uint32_t base, uint32_t valid,
                                                       nlex2::Win& w) {
-  const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(S.text) + (base - tile_begin));
+  const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(S.text) + L2_HALO + (base - tile_begin));
   const uint4 q0 = wp[0], q1 = wp[1];
   const uint32_t lo[4] = {q0.x, q0.y, q0.z, q0.w}, hi[4] = {q1.x, q1.y, q1.z, q1.w};
   uint32_t A[16];
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restric
   stage_tile2(text, bitmap, tile_begin, n, S, gT, gK);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text), tile_begin, n};
+  Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text) + L2_HALO, tile_begin, n};
   const uint32_t blk = tile_begin + (uint32_t)warp * L2_SEG;
   uint32_t run = NUTDB_VEC8_ID;
   if (blk < n) {
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t full = 0xFFFFFFFFu;
-  Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text), tile_begin, n};
+  Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text) + L2_HALO, tile_begin, n};
   const uint32_t blk = tile_begin + (uint32_t)warp * L2_SEG;
   const uint32_t widx = blockIdx.x * L2_WARPS + warp;
   CSum wtotal = csum_identity();
@@ -547,7 +556,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
 // ---- statement splitter: every ';' in code context ends a statement -----------------
 // bit i: byte i of the thread's window is ';'
 __device__ __forceinline__ uint32_t semicolon_mask(const Lex2Shared& S, uint32_t tile_begin, uint32_t base, uint32_t valid) {
-  const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(S.text) + (base - tile_begin));
+  const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(S.text) + L2_HALO + (base - tile_begin));
   const uint4 q0 = wp[0], q1 = wp[1];
   const uint32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
   uint32_t m = 0;
@@ -576,7 +585,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_split(const uint8_t* __restrict_
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t full = 0xFFFFFFFFu;
-  Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text), tile_begin, n};
+  Tile2Src src{text, reinterpret_cast<const uint8_t*>(S.text) + L2_HALO, tile_begin, n};
   const uint32_t blk = tile_begin + (uint32_t)warp * L2_SEG;
   const uint32_t widx = blockIdx.x * L2_WARPS + warp;
   uint32_t total = 0;
