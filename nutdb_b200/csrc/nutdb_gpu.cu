@@ -28,6 +28,7 @@
 
 #include "lex_tables.hpp"
 #include "parse_fast.cuh"
+#include "parse_fast_tables.hpp"
 
 using namespace nlex;
 
@@ -37,7 +38,13 @@ using namespace nlex;
 #define LEX_ROW (LEX_THREADS + 1)
 #define SCAN_THREADS 1024
 #define PARSE_THREADS 128
-#define FAST_THREADS 512     // statements per CTA in k_parse_fast (re-dealt among its warps)
+#ifndef FAST_THREADS
+#define FAST_THREADS 512
+#endif
+#ifndef FAST_MINBLOCKS
+#define FAST_MINBLOCKS 3
+#endif
+//#define FAST_THREADS_DOC     // statements per CTA in k_parse_fast (re-dealt among its warps)
 #define FAST_BINS 64
 #define PARSE_STACK 160      // words of local stack in the fast path
 #define FIN_THREADS 256
@@ -401,6 +408,27 @@ struct DTok {
   __device__ __forceinline__ uint8_t kw(uint32_t i) const { return i < n ? kwp[i] : (uint8_t)0; }
   __device__ __forceinline__ uint32_t start(uint32_t i) const { return i < n ? st[i] : 0u; }
   __device__ __forceinline__ uint32_t end(uint32_t i) const { return i < n ? en[i] : 0u; }
+  __device__ __forceinline__ uint32_t pair_at(uint32_t i) const { return (uint32_t)ty[i] | ((uint32_t)kwp[i] << 8); }
+};
+// The same view for k_parse_fast, whose CTA has staged the (type, keyword) pairs of its statements' tokens in
+// shared memory: `rel` is the statement's first token relative to the staged window; tokens outside the window
+// (a statement lexed into the extra region, or a CTA with more than FAST_TOKCAP tokens) come from global memory.
+#ifndef FAST_TOKCAP
+#define FAST_TOKCAP 16384u
+#endif
+#define FAST_DYN_SMEM (FAST_STACK_DEPTH * FAST_THREADS * 8)
+struct DTokS {
+  const uint16_t* sm;
+  uint32_t rel;
+  DTok g;
+  __device__ __forceinline__ uint32_t pair_at(uint32_t i) const {
+    const uint32_t j = rel + i;
+    return j < FAST_TOKCAP ? (uint32_t)sm[j] : g.pair_at(i);
+  }
+  __device__ __forceinline__ uint8_t type(uint32_t i) const { return i < g.n ? (uint8_t)pair_at(i) : (uint8_t)NUTDB_TT_EOF; }
+  __device__ __forceinline__ uint8_t kw(uint32_t i) const { return i < g.n ? (uint8_t)(pair_at(i) >> 8) : (uint8_t)0; }
+  __device__ __forceinline__ uint32_t start(uint32_t i) const { return g.start(i); }
+  __device__ __forceinline__ uint32_t end(uint32_t i) const { return g.end(i); }
 };
 struct DNodes {
   uint2* p;
@@ -469,31 +497,82 @@ __device__ __forceinline__ void store_result(const npar::ParseResult& res, uint3
 // Pass 1, one thread per statement: the straight-line parser (parse_fast.cuh).  Statements it
 // declines go to the slow list.  Small code, no interpreter state: this is where a query log's
 // bulk is parsed.
-__global__ void __launch_bounds__(FAST_THREADS) k_parse_fast(
+__global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
     const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, uint32_t nstmt, uint32_t ntok,
     const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end,
     const uint8_t* __restrict__ tok_kw, const uint32_t* __restrict__ stmt_tok_begin,
     const uint32_t* __restrict__ stmt_tok_end, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
     uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count, const uint32_t* __restrict__ punt,
-    int lex_only) {
+    int lex_only, uint32_t tok_alloc, const npar::FastTables* __restrict__ gF) {
   // Lanes of a warp run independent parsers, so they only execute together where their statements look
   // alike.  The block therefore re-deals its statements: a counting sort in shared memory by (first keyword,
   // token-count bucket) puts statements of the same kind and similar length into the same warp.
   __shared__ uint32_t bin_count[FAST_BINS], bin_base[FAST_BINS], order[FAST_THREADS];
   __shared__ npar::FastTables FT;
-  if (threadIdx.x < 128) npar::fast_tables_fill(FT, threadIdx.x);
+  __shared__ __align__(16) uint16_t stok[FAST_TOKCAP];
+  __shared__ uint32_t tok_lo, tok_hi;
+  extern __shared__ __align__(16) npar::FastStackEntry fstack[];  // operator stacks: entry i of thread x at [i * FAST_THREADS + x]
+  {  // the grammar table (built on the host, parse_fast_tables.hpp)
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(gF);
+    uint32_t* b = reinterpret_cast<uint32_t*>(&FT);
+    for (uint32_t i = threadIdx.x; i < sizeof(npar::FastTables) / 4; i += FAST_THREADS) b[i] = a[i];
+  }
   uint32_t s = blockIdx.x * FAST_THREADS + threadIdx.x;
   if (threadIdx.x < FAST_BINS) bin_count[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    tok_lo = 0xFFFFFFFFu;
+    tok_hi = 0u;
+  }
+  __syncthreads();
+  // The CTA's statements are consecutive, so their tokens are one contiguous run of the token arrays (except the
+  // few lexed into the extra region).  Stage that run's (type, keyword) pairs in shared memory with coalesced
+  // 16-byte loads: the parsers below then never wait on a global load for a token.
+  uint32_t tb0 = 0xFFFFFFFFu, tc0 = 0;
+  if (s < nstmt && off32[s + 1] != off32[s]) {
+    tb0 = stmt_tok_begin[s];
+    tc0 = stmt_tok_end[s] - tb0;
+  }
+  {
+    const uint32_t wmin = __reduce_min_sync(0xFFFFFFFFu, tb0);
+    if ((threadIdx.x & 31u) == 0 && wmin != 0xFFFFFFFFu) atomicMin(&tok_lo, wmin);
+  }
+  __syncthreads();
+  const uint32_t lo16 = tok_lo == 0xFFFFFFFFu ? 0u : (tok_lo & ~15u);
+  {  // the end of the run: the furthest token of any statement that starts inside the window
+    const uint32_t te0 = (tb0 != 0xFFFFFFFFu && tb0 - lo16 < FAST_TOKCAP) ? tb0 + tc0 : 0u;
+    const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, te0);
+    if ((threadIdx.x & 31u) == 0 && wmax != 0u) atomicMax(&tok_hi, wmax);
+  }
+  __syncthreads();
+  if (!lex_only) {
+    const uint32_t hi = min(max(tok_hi, lo16), lo16 + FAST_TOKCAP);
+    for (uint32_t v = threadIdx.x; v * 16u < hi - lo16; v += FAST_THREADS) {
+      const uint32_t base = lo16 + v * 16u;
+      if (base + 16u > tok_alloc) break;
+      const uint4 a = *reinterpret_cast<const uint4*>(tok_type + base);
+      const uint4 b = *reinterpret_cast<const uint4*>(tok_kw + base);
+      uint4 x, y;
+      x.x = __byte_perm(a.x, b.x, 0x5140);
+      x.y = __byte_perm(a.x, b.x, 0x7362);
+      x.z = __byte_perm(a.y, b.y, 0x5140);
+      x.w = __byte_perm(a.y, b.y, 0x7362);
+      y.x = __byte_perm(a.z, b.z, 0x5140);
+      y.y = __byte_perm(a.z, b.z, 0x7362);
+      y.z = __byte_perm(a.w, b.w, 0x5140);
+      y.w = __byte_perm(a.w, b.w, 0x7362);
+      uint4* d = reinterpret_cast<uint4*>(stok + v * 16u);
+      d[0] = x;
+      d[1] = y;
+    }
+  }
   __syncthreads();
   uint32_t key = FAST_BINS - 1, rank = 0;
-  if (s < nstmt) {
-    const uint32_t len0 = off32[s + 1] - off32[s];
-    if (len0 != 0) {
-      const uint32_t tb0 = stmt_tok_begin[s], tc0 = stmt_tok_end[s] - tb0;
-      const uint32_t k0 = tok_type[tb0] == NUTDB_TT_KeywordOrIdentifier ? tok_kw[tb0] : 0u;
-      const uint32_t kind = k0 == npar::KW_SELECT ? 0u : (k0 == npar::KW_INSERT ? 1u : (k0 == npar::KW_CREATE ? 2u : 3u));
-      key = kind * 16u + min(15u, tc0 >> 2);
-    }
+  if (tb0 != 0xFFFFFFFFu) {
+    const uint32_t j0 = tb0 - lo16;
+    const uint32_t p0 = (j0 < FAST_TOKCAP && !lex_only) ? (uint32_t)stok[j0] : ((uint32_t)tok_type[tb0] | ((uint32_t)tok_kw[tb0] << 8));
+    const uint32_t k0 = (p0 & 0xFFu) == NUTDB_TT_KeywordOrIdentifier ? (p0 >> 8) : 0u;
+    const uint32_t kind = k0 == npar::KW_SELECT ? 0u : (k0 == npar::KW_INSERT ? 1u : (k0 == npar::KW_CREATE ? 2u : 3u));
+    key = kind * 16u + min(15u, tc0 >> 2);
   }
   rank = atomicAdd(&bin_count[key], 1u);
   __syncthreads();
@@ -534,12 +613,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_parse_fast(
     stmt[s] = S;
     return;
   }
-  DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
+  DTokS tk{stok, tb - lo16, DTok{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc}};
   uint2* range = scratch + node_slot(s, tb, nstmt, punt);
   DNodes nd{range, tc + NODE_SLACK};
   DText tx{text + o, len};
   npar::ParseResult res;
-  npar::FastParser<DTok, DNodes, DText> f(FT, tk, nd, tx);
+  npar::FastParser<DTokS, DNodes, DText> f(&FT, tk, nd, tx, fstack + threadIdx.x, FAST_THREADS);
   if (f.try_parse(res)) {
     store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
   } else {
@@ -762,6 +841,7 @@ struct NutdbCtx {
   std::string err;
   LexTables* dLex = nullptr;
   npar::ParseTables* dPar = nullptr;
+  npar::FastTables* dFast = nullptr;
   nlex2::Lex2Tables* dLex2 = nullptr;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
@@ -913,12 +993,25 @@ NutdbCtx* nutdb_gpu_ctx_create(int device) {
        cudaMemcpy(ctx->dLex, &lt, sizeof(lt), cudaMemcpyHostToDevice) == cudaSuccess &&
        cudaMemcpy(ctx->dPar, &npar::PARSE_TABLES, sizeof(npar::ParseTables), cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) {
+    static_assert(sizeof(npar::FastTables) % 4 == 0, "FastTables is staged word by word");
+    npar::FastTables ft;
+    try {
+      npar::fast_tables_build(ft);
+    } catch (...) {
+      ok = false;
+    }
+    ok = ok && cudaMalloc(&ctx->dFast, sizeof(ft)) == cudaSuccess &&
+         cudaMemcpy(ctx->dFast, &ft, sizeof(ft), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  if (ok) {
     nlex2::Lex2Tables l2;
     nlex2::build_lex2_tables(l2);
     ok = cudaMalloc(&ctx->dLex2, sizeof(l2)) == cudaSuccess &&
          cudaMemcpy(ctx->dLex2, &l2, sizeof(l2), cudaMemcpyHostToDevice) == cudaSuccess;
   }
   if (ok) ok = ensure_dev(ctx, ctx->small, 256) == NUTDB_OK && ensure_host(ctx, ctx->hSmall, 256) == NUTDB_OK;
+  // k_parse_fast: staged tokens (static) + operator stacks (dynamic) exceed the 48 KB default
+  if (ok) ok = cudaFuncSetAttribute(k_parse_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_DYN_SMEM) == cudaSuccess;
   if (!ok) {
     nutdb_gpu_ctx_destroy(ctx);
     return nullptr;
@@ -933,6 +1026,7 @@ void nutdb_gpu_ctx_destroy(NutdbCtx* ctx) {
   free_all(ctx);
   if (ctx->dLex) cudaFree(ctx->dLex);
   if (ctx->dPar) cudaFree(ctx->dPar);
+  if (ctx->dFast) cudaFree(ctx->dFast);
   if (ctx->dLex2) cudaFree(ctx->dLex2);
   for (int i = 0; i < 6; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1174,12 +1268,13 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
     const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
     ENSURE_DEV(slowList, 4 * ((size_t)nstmt + 1));
-    LAUNCH("k_parse_fast", k_parse_fast<<<(nstmt + FAST_THREADS - 1) / FAST_THREADS, FAST_THREADS, 0, st>>>(
+    LAUNCH("k_parse_fast", k_parse_fast<<<(nstmt + FAST_THREADS - 1) / FAST_THREADS, FAST_THREADS, FAST_DYN_SMEM, st>>>(
                                dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                (const uint8_t*)ctx->tokKw.p, (const uint32_t*)ctx->stmtTokBegin.p,
                                (const uint32_t*)ctx->stmtTokEnd.p, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
-                               (uint32_t*)ctx->slowList.p, dS + 2, (const uint32_t*)ctx->puntFlag.p, lex_only ? 1 : 0));
+                               (uint32_t*)ctx->slowList.p, dS + 2, (const uint32_t*)ctx->puntFlag.p, lex_only ? 1 : 0,
+                               (uint32_t)min((size_t)0xFFFFFFF0u, (size_t)ntok + 16), ctx->dFast));
     CK(cudaMemcpyAsync(hS, dS, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t nslow = hS[2];

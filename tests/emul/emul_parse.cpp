@@ -6,6 +6,7 @@
 
 #include "../../nutdb_b200/csrc/lex_tables.hpp"
 #include "../../nutdb_b200/csrc/parse_fast.cuh"
+#include "../../nutdb_b200/csrc/parse_fast_tables.hpp"
 
 using namespace nlex;
 
@@ -35,6 +36,7 @@ struct HTokAdapter {
   uint8_t kw(uint32_t i) const { return h.kwid(i); }
   uint8_t type_at(uint32_t i) const { return h.type(i); }
   uint8_t kw_at(uint32_t i) const { return h.kwid(i); }
+  uint32_t pair_at(uint32_t i) const { return (uint32_t)h.type(i) | ((uint32_t)h.kwid(i) << 8); }
   uint32_t start(uint32_t i) const { return h.start(i); }
   uint32_t end(uint32_t i) const { return h.end(i); }
 };
@@ -136,10 +138,11 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
         static npar::FastTables FT;
         static bool ft_init = false;
         if (!ft_init) {
-          for (uint32_t q = 0; q < 128; q++) npar::fast_tables_fill(FT, q);
+          npar::fast_tables_build(FT);
           ft_init = true;
         }
-        npar::FastParser<HTokAdapter, HNodes, HText> f(FT, tk, nd, tx);
+        npar::FastStackEntry fstack[FAST_STACK_DEPTH];
+        npar::FastParser<HTokAdapter, HNodes, HText> f(&FT, tk, nd, tx, fstack, 1);
         fast = f.try_parse(res);
       }
       if (fast) {
