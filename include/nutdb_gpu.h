@@ -362,6 +362,14 @@ typedef struct {
 } NutdbBatchDevice;
 int nutdb_gpu_batch_device(const NutdbBatch *batch, NutdbBatchDevice *out);
 
+/* 64-bit checksum of everything the batch holds on the device (statement records, the four token arrays, nodes,
+ * error records), computed on the device:
+ *     H = sum over arrays A, 32-bit words (or bytes, for the two byte arrays) w at index i of
+ *         mix(mix(i + (A + 1) * 0x9E3779B97F4A7C15) ^ w)    (mod 2^64; mix = the splitmix64 finaliser)
+ * with A = 0 stmt, 1 tok_type, 2 tok_start, 3 tok_end, 4 tok_kw, 5 node, 6 err.  Used to compare the outputs of
+ * the same log parsed on different numbers of GPUs without moving them to the host. */
+int nutdb_gpu_batch_hash(const NutdbBatch *batch, uint64_t *out);
+
 /* Statement splitter for raw buffers (query logs).  The reference has no multi-statement entry
  * (Parser::parse stops after one statement, src/parser/mod.rs:165-172); this produces the `stmt_off`
  * that nutdb_gpu_parse_batch consumes.  The buffer is read as ONE character stream with the

@@ -675,7 +675,9 @@ NUTDB_HD void win_emit(const LexTables& T, Src& src, Sink& sink, const Win& w, c
       if (len >= 2 && len <= 10) {
         const uint8_t* wp = src.span(start, len);  // the word as contiguous bytes (almost always)
         if (wp) {
-          kw = keyword_lookup(T, len, [wp](uint32_t q) { return wp[q]; });
+          uint32_t w0, w1, w2;
+          load_word12(wp, len, w0, w1, w2);
+          kw = keyword_lookup_words(T, len, w0, w1, w2);
         } else {
           Src& sr = src;
           kw = keyword_lookup(T, len, [&sr, start](uint32_t q) { return sr.byte(start + q); });

@@ -159,7 +159,7 @@ struct LexTables {
   uint32_t kw_mul[4];            // perfect hash multipliers
   uint8_t kw_slot[NUTDB_KW_SLOTS];  // keyword id or 0
   uint8_t kw_len[NUTDB_KW_COUNT + 1];
-  uint8_t kw_text[NUTDB_KW_COUNT + 1][12];  // lower case, zero padded
+  alignas(4) uint8_t kw_text[NUTDB_KW_COUNT + 1][12];  // lower case ([a-z0-9] only), zero padded; read as 3 words
 };
 
 NUTDB_HD uint8_t b_class(const LexTables& T, uint8_t b, uint8_t prev) {
@@ -239,6 +239,47 @@ NUTDB_HD uint8_t keyword_lookup(const LexTables& T, uint32_t len, Get get) {
   for (uint32_t i = 0; i < len; i++)
     if (ascii_lower(get(i)) != T.kw_text[id][i]) return 0;
   return id;
+}
+
+// The same look-up on the word held in registers: w0..w2 are its first 12 bytes (little endian; bytes at and
+// beyond `len` are arbitrary).  Folding with `| 0x20` instead of ascii_lower is exact here: the word consists
+// of [A-Za-z0-9_] and a keyword of [a-z0-9], so c | 0x20 == k exactly when c equals k ignoring ASCII case
+// ('_' becomes 0x7F, which no keyword contains).
+NUTDB_HD uint8_t keyword_lookup_words(const LexTables& T, uint32_t len, uint32_t w0, uint32_t w1, uint32_t w2) {
+  if (len < 2 || len > 10) return 0;
+  const uint32_t L0 = w0 | 0x20202020u, L1 = w1 | 0x20202020u, L2 = w2 | 0x20202020u;
+  const uint64_t lo = (uint64_t)L0 | ((uint64_t)L1 << 32);
+  const uint32_t il = len - 1, ip = len - 2;
+  const uint32_t c0 = L0 & 255u, c1 = (L0 >> 8) & 255u;
+  const uint32_t cl = il < 8 ? (uint32_t)(lo >> (8 * il)) & 255u : (L2 >> (8 * (il - 8))) & 255u;
+  const uint32_t cp = ip < 8 ? (uint32_t)(lo >> (8 * ip)) & 255u : (L2 >> (8 * (ip - 8))) & 255u;
+  const uint32_t h = (c0 * T.kw_mul[0] + c1 * T.kw_mul[1] + cl * T.kw_mul[2] + cp * T.kw_mul[3] + len) & (NUTDB_KW_SLOTS - 1);
+  const uint8_t id = T.kw_slot[h];
+  if (id == 0 || T.kw_len[id] != len) return 0;
+  const uint32_t m0 = len >= 4 ? 0xFFFFFFFFu : ((1u << (8 * len)) - 1u);
+  const uint32_t m1 = len >= 8 ? 0xFFFFFFFFu : (len <= 4 ? 0u : ((1u << (8 * (len - 4))) - 1u));
+  const uint32_t m2 = len <= 8 ? 0u : ((1u << (8 * (len - 8))) - 1u);
+  const uint32_t* k = reinterpret_cast<const uint32_t*>(T.kw_text[id]);
+  return ((L0 & m0) == k[0] && (L1 & m1) == k[1] && (L2 & m2) == k[2]) ? id : (uint8_t)0;
+}
+// the first 12 bytes of a word that lies contiguously in memory at p (device: shared memory, read as aligned
+// words -- up to 15 bytes around the word are touched, always inside the staged tile and its neighbours)
+NUTDB_HD void load_word12(const uint8_t* p, uint32_t len, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+#ifdef __CUDA_ARCH__
+  const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+  const uint32_t x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3];
+  const uint32_t sh = 8u * a;
+  w0 = __funnelshift_r(x0, x1, sh);
+  w1 = __funnelshift_r(x1, x2, sh);
+  w2 = __funnelshift_r(x2, x3, sh);
+#else
+  uint32_t w[3] = {0, 0, 0};
+  for (uint32_t i = 0; i < len && i < 12; i++) w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+  w0 = w[0];
+  w1 = w[1];
+  w2 = w[2];
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -95,6 +95,11 @@ inline void build_lex_tables(LexTables& T) {
   // keywords + perfect hash: slot = (c0*m0 + c1*m1 + c[n-1]*m2 + c[n-2]*m3 + n) mod 512, all 115 words distinct
   for (int k = 0; k < NUTDB_KW_COUNT; k++) {
     size_t n = std::strlen(KEYWORD_TEXT[k]);
+    for (size_t i = 0; i < n; i++) {  // keyword_lookup_words folds case with `| 0x20`: exact for [a-z0-9] only
+      const char c = KEYWORD_TEXT[k][i];
+      if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9')) || n < 2 || n > 10)
+        throw std::runtime_error("keyword outside [a-z0-9]{2,10}");
+    }
     T.kw_len[k + 1] = (uint8_t)n;
     std::memcpy(T.kw_text[k + 1], KEYWORD_TEXT[k], n);
   }

@@ -416,7 +416,7 @@ struct DTok {
 #ifndef FAST_TOKCAP
 #define FAST_TOKCAP 16384u
 #endif
-#define FAST_DYN_SMEM (FAST_STACK_DEPTH * FAST_THREADS * 8)
+#define FAST_DYN_SMEM (FAST_TOKCAP * 2 + FAST_STACK_DEPTH * FAST_THREADS * 8)
 struct DTokS {
   const uint16_t* sm;
   uint32_t rel;
@@ -509,9 +509,12 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
   // token-count bucket) puts statements of the same kind and similar length into the same warp.
   __shared__ uint32_t bin_count[FAST_BINS], bin_base[FAST_BINS], order[FAST_THREADS];
   __shared__ npar::FastTables FT;
-  __shared__ __align__(16) uint16_t stok[FAST_TOKCAP];
   __shared__ uint32_t tok_lo, tok_hi;
-  extern __shared__ __align__(16) npar::FastStackEntry fstack[];  // operator stacks: entry i of thread x at [i * FAST_THREADS + x]
+  // dynamic shared memory: the staged (type, keyword) pairs of the CTA's tokens, then the operator stacks
+  // (entry i of thread x at fstack[i * FAST_THREADS + x])
+  extern __shared__ __align__(16) unsigned char fast_smem[];
+  uint16_t* const stok = reinterpret_cast<uint16_t*>(fast_smem);
+  npar::FastStackEntry* const fstack = reinterpret_cast<npar::FastStackEntry*>(fast_smem + FAST_TOKCAP * 2);
   {  // the grammar table (built on the host, parse_fast_tables.hpp)
     const uint32_t* a = reinterpret_cast<const uint32_t*>(gF);
     uint32_t* b = reinterpret_cast<uint32_t*>(&FT);
@@ -845,7 +848,7 @@ struct NutdbCtx {
   nlex2::Lex2Tables* dLex2 = nullptr;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
-  DevBuf text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+  DevBuf hashAcc, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
@@ -950,7 +953,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->hashAcc, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1403,6 +1406,60 @@ void nutdb_gpu_batch_free(NutdbCtx* ctx, NutdbBatch* batch) {
   // releasing a batch only invalidates the caller's view.
   if (ctx) ctx->batch_live = false;
   if (batch) std::memset(batch, 0, sizeof(*batch));
+}
+
+}  // extern "C"
+
+// ---- 64-bit checksum of a batch's device-resident outputs (nutdb_gpu_batch_hash) ----
+__host__ __device__ __forceinline__ uint64_t hash_mix64(uint64_t z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t hash_term(uint32_t array, uint64_t index, uint32_t value) {
+  return hash_mix64(hash_mix64(index + (uint64_t)(array + 1u) * 0x9E3779B97F4A7C15ull) ^ (uint64_t)value);
+}
+// array 0..: stmt words, tok_type bytes, tok_start, tok_end, tok_kw bytes, node words, err words.  One launch per array.
+template <typename T>
+__global__ void __launch_bounds__(256) k_hash(const T* __restrict__ a, uint64_t n, uint32_t array,
+                                              unsigned long long* __restrict__ out) {
+  uint64_t acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    acc += hash_term(array, i, (uint32_t)a[i]);
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+  if ((threadIdx.x & 31u) == 0 && acc != 0) atomicAdd(out, (unsigned long long)acc);
+}
+
+extern "C" {
+
+int nutdb_gpu_batch_hash(const NutdbBatch* batch, uint64_t* out) {
+  if (!batch || !out || !batch->impl) return NUTDB_E_ARG;
+  NutdbCtx* ctx = (NutdbCtx*)batch->impl;
+  if (!ctx->batch_live) return NUTDB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  {
+    const int rc = ensure_dev(ctx, ctx->hashAcc, 8);
+    if (rc != NUTDB_OK) return rc;
+  }
+  unsigned long long* acc = (unsigned long long*)ctx->hashAcc.p;
+  CK(cudaMemsetAsync(acc, 0, 8, st));
+  const int grid = 148 * 8;
+  const NutdbBatchDevice& v = ctx->dev_view;
+  if (batch->n_stmt) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.stmt, batch->n_stmt * (sizeof(NutdbStmt) / 4), 0, acc);
+  if (batch->n_tok) {
+    k_hash<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.tok_type, batch->n_tok, 1, acc);
+    k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.tok_start, batch->n_tok, 2, acc);
+    k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.tok_end, batch->n_tok, 3, acc);
+    k_hash<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.tok_kw, batch->n_tok, 4, acc);
+  }
+  if (batch->n_node) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.node, batch->n_node * (sizeof(NutdbNode) / 4), 5, acc);
+  if (batch->n_err) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.err, batch->n_err * (sizeof(NutdbError) / 4), 6, acc);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->hSmall.p, acc, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *out = *(const uint64_t*)ctx->hSmall.p;
+  return NUTDB_OK;
 }
 
 int nutdb_gpu_batch_device(const NutdbBatch* batch, NutdbBatchDevice* out) {

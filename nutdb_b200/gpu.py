@@ -59,6 +59,8 @@ def lib():
     L.nutdb_gpu_batch_free.argtypes = [C.c_void_p, C.POINTER(NutdbBatch)]
     L.nutdb_gpu_batch_device.restype = C.c_int
     L.nutdb_gpu_batch_device.argtypes = [C.POINTER(NutdbBatch), C.POINTER(NutdbBatchDevice)]
+    L.nutdb_gpu_batch_hash.restype = C.c_int
+    L.nutdb_gpu_batch_hash.argtypes = [C.POINTER(NutdbBatch), C.POINTER(C.c_uint64)]
     L.nutdb_gpu_parse.restype = C.c_int
     L.nutdb_gpu_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(NutdbBatch)]
     L.nutdb_gpu_split_statements.restype = C.c_int
@@ -114,6 +116,36 @@ class Batch:
         if rc != 0:
             raise NutdbGpuError("batch is no longer live")
         return {n: getattr(d, n) for n, _ in NutdbBatchDevice._fields_}
+
+    def device_hash(self):
+        """64-bit checksum of the batch's device-resident outputs (nutdb_gpu_batch_hash)."""
+        h = C.c_uint64(0)
+        rc = lib().nutdb_gpu_batch_hash(C.byref(self.raw), C.byref(h))
+        if rc != 0:
+            raise NutdbGpuError(f"nutdb_gpu_batch_hash failed ({rc}): batch is no longer live?")
+        return int(h.value)
+
+
+def host_hash(batch):
+    """The checksum of nutdb_gpu_batch_hash computed with numpy from a Batch's host arrays (test helper)."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def mix(z):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+    total = np.uint64(0)
+    arrays = [np.ascontiguousarray(batch.stmt).view(np.uint32), batch.tok_type, batch.tok_start, batch.tok_end,
+              batch.tok_kw, np.ascontiguousarray(batch.node).view(np.uint32), np.ascontiguousarray(batch.err).view(np.uint32)]
+    with np.errstate(over="ignore"):
+        for a, w in enumerate(arrays):
+            w = np.asarray(w).reshape(-1)
+            if w.size == 0:
+                continue
+            i = np.arange(w.size, dtype=np.uint64) + np.uint64(((a + 1) * 0x9E3779B97F4A7C15) & int(M))
+            total = total + np.sum(mix(mix(i) ^ w.astype(np.uint64)), dtype=np.uint64)
+    return int(total)
 
 
 class Context:

@@ -223,3 +223,25 @@ def test_statement_splitter(ctx):
              b"a;" * 5000, b"-- only a comment; really\n", b"select 1;\n\n\t "]
     for c in cases + fuzz.fuzz_statements([b"; ".join(CORPUS[:4])], 200, seed=5, max_mut=6):
         assert np.array_equal(ctx.split_statements(c), E.split(c)), c
+
+
+def test_device_hash_matches_host_arrays_and_is_shard_invariant(ctx):
+    """nutdb_gpu_batch_hash: equal to the same sum computed from the host copies; the sum of the chunk checksums of a
+    log does not depend on how the chunks are dealt to contexts (config 5's cross-GPU-count check)."""
+    from nutdb_b200 import gpu
+    for config in (2, 3):
+        text, offs = W.generate(config, 1 << 20)
+        got = ctx.parse_batch(text, offs)
+        assert got.device_hash() == gpu.host_hash(got)
+    # the same two chunks on one context in either order, and a changed byte changes the checksum
+    chunks = [W.generate(2, 256 << 10, seed=0x5EED0005 + c) for c in range(2)]
+    h = []
+    for order in ((0, 1), (1, 0)):
+        tot = 0
+        for c in order:
+            tot = (tot + ctx.parse_batch(*chunks[c]).device_hash()) & 0xFFFFFFFFFFFFFFFF
+        h.append(tot)
+    assert h[0] == h[1]
+    t2 = chunks[0][0].copy()
+    t2[10] = ord("x") if t2[10] != ord("x") else ord("y")
+    assert ctx.parse_batch(t2, chunks[0][1]).device_hash() != ctx.parse_batch(*chunks[0]).device_hash()
