@@ -689,7 +689,28 @@ __global__ void __launch_bounds__(128) k_lex_exact(const uint8_t* __restrict__ t
   const uint32_t first = c.count;
   Walker<false, StmtSrc, ExactSink> w(T, src, sink, c);
   w.counting = !Emit;
-  for (uint32_t pos = src.begin; pos < src.end; pos++) w.step(pos, src.byte(pos), pos == src.begin, true);
+  // One thread walks one statement: a byte at a time from global memory would cost a full memory latency per
+  // byte.  The statement is read as aligned 16-byte blocks, the next block in flight while this one is walked.
+  if (src.begin < src.end) {
+    const uint8_t* p0 = text + src.begin;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 15u);
+    const uint8_t* blk = p0 - mis;             // (the aligned block of a valid byte lies inside the same allocation)
+    const uint8_t* const last = text + src.end - 1u;
+    uint4 cur = __ldg(reinterpret_cast<const uint4*>(blk));
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (blk + 16 <= last) nxt = __ldg(reinterpret_cast<const uint4*>(blk + 16));
+    uint32_t k = mis;
+    for (uint32_t pos = src.begin; pos < src.end; pos++, k++) {
+      if (k == 16u) {
+        k = 0u;
+        blk += 16;
+        cur = nxt;
+        if (blk + 16 <= last) nxt = __ldg(reinterpret_cast<const uint4*>(blk + 16));
+      }
+      const uint32_t word = k < 8u ? (k < 4u ? cur.x : cur.y) : (k < 12u ? cur.z : cur.w);
+      w.step(pos, (uint8_t)((word >> (8u * (k & 3u))) & 255u), pos == src.begin, true);
+    }
+  }
   w.flush_eof(src.end);
   if (Emit) {
     stmt_tok_begin[s] = first;

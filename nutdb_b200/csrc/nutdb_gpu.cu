@@ -206,6 +206,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const typename Op::
   if (threadIdx.x == 0 && total_out) *total_out = total;
 }
 
+// The statements flagged for the exact lexer, as an ASCENDING list (the flags are raised by whichever warp sees
+// the reason first, so an atomically appended list would make token positions in the extra region -- and with them
+// tok_begin of those statements -- depend on scheduling).  Two passes over punt_flag around a scan of block counts.
+#define PUNT_PER_THREAD 16u
+#define PUNT_THREADS 256u
+template <bool Scatter>
+__global__ void __launch_bounds__(PUNT_THREADS) k_punt_list(const uint32_t* __restrict__ punt_flag, uint32_t nstmt,
+                                                            uint2* __restrict__ block_count,
+                                                            const uint2* __restrict__ block_pref,
+                                                            uint32_t* __restrict__ list) {
+  __shared__ uint2 ws[32];
+  const uint32_t s0 = (blockIdx.x * PUNT_THREADS + threadIdx.x) * PUNT_PER_THREAD;
+  uint32_t bits = 0;
+  for (uint32_t k = 0; k < PUNT_PER_THREAD; k++)
+    if (s0 + k < nstmt && punt_flag[s0 + k] != 0u) bits |= 1u << k;
+  uint2 incl, total;
+  const uint2 excl = block_scan<U2AddOp>(make_uint2((uint32_t)__popc(bits), 0u), ws, incl, total);
+  if (!Scatter) {
+    if (threadIdx.x == 0) block_count[blockIdx.x] = total;
+  } else {
+    uint32_t at = block_pref[blockIdx.x].x + excl.x;
+    while (bits) {
+      const uint32_t k = (uint32_t)__ffs((int)bits) - 1u;
+      bits &= bits - 1u;
+      list[at++] = s0 + k;
+    }
+  }
+}
+
 // vec8 variant: stores only the ENTRY STATE of each tile (the automaton starts in state 0)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_vec8(const uint32_t* __restrict__ in, uint8_t* __restrict__ entry,
                                                             uint32_t n) {
@@ -848,7 +877,7 @@ struct NutdbCtx {
   nlex2::Lex2Tables* dLex2 = nullptr;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
-  DevBuf hashAcc, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+  DevBuf hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
@@ -953,7 +982,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->hashAcc, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1219,6 +1248,18 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     if (npunt > 0) {
       ENSURE_DEV(puntCounts, 8 * (size_t)npunt);
       ENSURE_DEV(puntOffs, 8 * (size_t)npunt);
+      {  // the flagged statements in ascending order (deterministic extra-region layout)
+        const uint32_t nb = (nstmt + PUNT_THREADS * PUNT_PER_THREAD - 1) / (PUNT_THREADS * PUNT_PER_THREAD);
+        ENSURE_DEV(puntBlockCount, 8 * (size_t)nb);
+        ENSURE_DEV(puntBlockPref, 8 * (size_t)nb);
+        LAUNCH("k_punt_count", k_punt_list<false><<<nb, PUNT_THREADS, 0, st>>>(
+                                   (const uint32_t*)ctx->puntFlag.p, nstmt, (uint2*)ctx->puntBlockCount.p, nullptr, nullptr));
+        LAUNCH("k_scan_PB", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>(
+                                (const uint2*)ctx->puntBlockCount.p, (uint2*)ctx->puntBlockPref.p, nb, nullptr));
+        LAUNCH("k_punt_scatter", k_punt_list<true><<<nb, PUNT_THREADS, 0, st>>>(
+                                     (const uint32_t*)ctx->puntFlag.p, nstmt, nullptr, (const uint2*)ctx->puntBlockPref.p,
+                                     (uint32_t*)ctx->puntList.p));
+      }
       LAUNCH("k_lex_exact_count", k_lex_exact<false><<<(npunt + 127) / 128, 128, 0, st>>>(
                                       dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p,
                                       npunt, (uint2*)ctx->puntCounts.p, nullptr, 0u, xs, nullptr, nullptr, nullptr));
