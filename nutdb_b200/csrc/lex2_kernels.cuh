@@ -317,8 +317,7 @@ struct Lex2Out {
   const uint32_t* off32;
   uint32_t nstmt;
   uint32_t* punt_flag;   // per statement
-  uint32_t* punt_list;   // statement indices
-  uint32_t* punt_count;
+  uint32_t* punt_count;  // [0] flagged statements, [1] bound on their tokens
   const uint32_t* first_stmt;  // per 32-byte window: smallest non-empty statement starting in it
   uint32_t nbytes;
   __device__ uint32_t find_stmt(uint32_t pos) const {  // the statement containing byte `pos`
@@ -332,7 +331,11 @@ struct Lex2Out {
   }
   __device__ void punt(uint32_t pos) const {
     const uint32_t s = find_stmt(pos);
-    if (atomicExch(&punt_flag[s], 1u) == 0u) punt_list[atomicAdd(punt_count, 1u)] = s;
+    if (atomicExch(&punt_flag[s], 1u) == 0u) {
+      atomicAdd(punt_count, 1u);
+      // a bound on the tokens the exact lexer can produce for it (a token per byte + EOF): sizes the extra region
+      atomicAdd(punt_count + 1, off32[s + 1] - off32[s] + 1u);
+    }
   }
   // sink interface of nlex2::win_emit
   __device__ __forceinline__ void token(uint32_t i, uint8_t t, uint32_t s, uint32_t e, uint8_t k) const {
@@ -350,12 +353,13 @@ struct Lex2Out {
   __device__ __forceinline__ void stmt_begin(uint32_t pos, uint32_t first) const {
     uint32_t c = first_stmt[pos >> 5];
     while (off32[c] != pos || off32[c + 1] == pos) c++;
-    stmt_tok_begin[c] = first;
+    // (a statement flagged for the exact lexer gets its token range from k_lex_exact, which runs beside this pass)
+    if (punt_flag[c] == 0u) stmt_tok_begin[c] = first;
     uint32_t p = c;
     while (p > 0) {
       p--;
       if (off32[p + 1] != off32[p]) {
-        stmt_tok_end[p] = first;
+        if (punt_flag[p] == 0u) stmt_tok_end[p] = first;
         break;
       }
     }
@@ -367,7 +371,7 @@ struct Lex2Out {
     while (p > 0) {
       p--;
       if (off32[p + 1] != off32[p]) {
-        stmt_tok_end[p] = endi;
+        if (punt_flag[p] == 0u) stmt_tok_end[p] = endi;
         break;
       }
     }

@@ -874,6 +874,8 @@ struct NutdbCtx {
   LexTables* dLex = nullptr;
   npar::ParseTables* dPar = nullptr;
   npar::FastTables* dFast = nullptr;
+  cudaStream_t stream2 = nullptr;  // the exact-lexer chain runs here beside the emit pass
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   nlex2::Lex2Tables* dLex2 = nullptr;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
@@ -955,21 +957,22 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   return NUTDB_OK;
 }
 // LAUNCH(name, kernel<<<...>>>(...)): counts the launch and, in profiling mode, brackets it with events
-#define LAUNCH(name, ...)                                  \
+#define LAUNCH_ON(stream_, name, ...)                      \
   do {                                                     \
     NutdbCtx::KRec r_{name, nullptr, nullptr};             \
     if (ctx->profiling) {                                  \
       r_.a = ctx->take_event();                            \
       r_.b = ctx->take_event();                            \
-      cudaEventRecord(r_.a, st);                           \
+      cudaEventRecord(r_.a, stream_);                      \
     }                                                      \
     __VA_ARGS__;                                           \
     ctx->launches++;                                       \
     if (ctx->profiling) {                                  \
-      cudaEventRecord(r_.b, st);                           \
+      cudaEventRecord(r_.b, stream_);                      \
       ctx->recs.push_back(r_);                             \
     }                                                      \
   } while (0)
+#define LAUNCH(name, ...) LAUNCH_ON(st, name, __VA_ARGS__)
 #define ENSURE_DEV(buf, bytes)                      \
   do {                                              \
     int rc_ = ensure_dev(ctx, ctx->buf, (bytes));   \
@@ -1002,6 +1005,14 @@ extern "C" {
 
 const char* nutdb_gpu_version(void) { return "nutdb-gpu 0.1 (sm_100a)"; }
 
+// A stream whose grids are dispatched ahead of the main stream's: the exact-lexer chain is a series of tiny dependent
+// kernels, and at equal priority each of them would queue behind all 131K blocks of the emit pass it runs beside.
+static bool create_priority_stream(cudaStream_t* s) {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return false;
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest) == cudaSuccess;
+}
+
 NutdbCtx* nutdb_gpu_ctx_create(int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -1012,7 +1023,10 @@ NutdbCtx* nutdb_gpu_ctx_create(int device) {
   NutdbCtx* ctx = new (std::nothrow) NutdbCtx();
   if (!ctx) return nullptr;
   ctx->device = device;
-  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            create_priority_stream(&ctx->stream2) &&
+            cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 6 && ok; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   LexTables lt;
   try {
@@ -1063,6 +1077,9 @@ void nutdb_gpu_ctx_destroy(NutdbCtx* ctx) {
   for (int i = 0; i < 6; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+  if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1223,7 +1240,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
     Lex2Out lo{nullptr, nullptr, nullptr, nullptr, 0, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
-               (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->puntList.p, dS + 3,
+               (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, dS + 14,
                (const uint32_t*)ctx->firstStmt.p, n};
     LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2,
                                                                   (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p,
@@ -1241,59 +1258,70 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
       ctx->err = "statement offsets must ascend";
       return NUTDB_E_ARG;
     }
-    const uint32_t ntok_main = hS[4], npunt = hS[3];
-    uint32_t n_extra = 0;
+    const uint32_t ntok_main = hS[4], npunt = hS[14];
+    const uint64_t extra_bound = npunt ? hS[15] : 0u;  // tokens the flagged statements can have at most
     ctx->n_punt = npunt;
-    ExactSink xs{nullptr, nullptr, nullptr, nullptr, 0};
-    if (npunt > 0) {
-      ENSURE_DEV(puntCounts, 8 * (size_t)npunt);
-      ENSURE_DEV(puntOffs, 8 * (size_t)npunt);
-      {  // the flagged statements in ascending order (deterministic extra-region layout)
-        const uint32_t nb = (nstmt + PUNT_THREADS * PUNT_PER_THREAD - 1) / (PUNT_THREADS * PUNT_PER_THREAD);
-        ENSURE_DEV(puntBlockCount, 8 * (size_t)nb);
-        ENSURE_DEV(puntBlockPref, 8 * (size_t)nb);
-        LAUNCH("k_punt_count", k_punt_list<false><<<nb, PUNT_THREADS, 0, st>>>(
-                                   (const uint32_t*)ctx->puntFlag.p, nstmt, (uint2*)ctx->puntBlockCount.p, nullptr, nullptr));
-        LAUNCH("k_scan_PB", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>(
-                                (const uint2*)ctx->puntBlockCount.p, (uint2*)ctx->puntBlockPref.p, nb, nullptr));
-        LAUNCH("k_punt_scatter", k_punt_list<true><<<nb, PUNT_THREADS, 0, st>>>(
-                                     (const uint32_t*)ctx->puntFlag.p, nstmt, nullptr, (const uint2*)ctx->puntBlockPref.p,
-                                     (uint32_t*)ctx->puntList.p));
-      }
-      LAUNCH("k_lex_exact_count", k_lex_exact<false><<<(npunt + 127) / 128, 128, 0, st>>>(
-                                      dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p,
-                                      npunt, (uint2*)ctx->puntCounts.p, nullptr, 0u, xs, nullptr, nullptr, nullptr));
-      LAUNCH("k_scan_P", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->puntCounts.p,
-                                                                           (uint2*)ctx->puntOffs.p, npunt, (uint2*)(dS + 10)));
-      CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      n_extra = hS[10];
-    }
-    if ((uint64_t)ntok_main + n_extra >= 0xFFFFFFF0ull) {
+    if ((uint64_t)ntok_main + extra_bound >= 0xFFFFFFF0ull) {
       ctx->err = "too many tokens in one batch";
       return NUTDB_E_ARG;
     }
-    ntok = ntok_main + n_extra;
-    ENSURE_DEV(tokType, (size_t)ntok + 16);
-    ENSURE_DEV(tokKw, (size_t)ntok + 16);
-    ENSURE_DEV(tokStart, 4 * ((size_t)ntok + 4));
-    ENSURE_DEV(tokEnd, 4 * ((size_t)ntok + 4));
+    // The token arrays are sized with that bound, so the emit pass does not have to wait for the exact lexer's
+    // count: the (small, latency-bound) exact-lexer chain runs on a second stream beside it.
+    const size_t tok_cap = (size_t)ntok_main + extra_bound;
+    ENSURE_DEV(tokType, tok_cap + 16);
+    ENSURE_DEV(tokKw, tok_cap + 16);
+    ENSURE_DEV(tokStart, 4 * (tok_cap + 4));
+    ENSURE_DEV(tokEnd, 4 * (tok_cap + 4));
     lo.type = (uint8_t*)ctx->tokType.p;
     lo.start = (uint32_t*)ctx->tokStart.p;
     lo.end = (uint32_t*)ctx->tokEnd.p;
     lo.kw = (uint8_t*)ctx->tokKw.p;
     lo.cap = ntok_main;
+    uint32_t n_extra = 0;
+    if (npunt > 0) {
+      cudaStream_t s2 = ctx->profiling ? st : ctx->stream2;  // (per-kernel timing serialises everything on one stream)
+      ENSURE_DEV(puntCounts, 8 * (size_t)npunt);
+      ENSURE_DEV(puntOffs, 8 * (size_t)npunt);
+      const uint32_t nb = (nstmt + PUNT_THREADS * PUNT_PER_THREAD - 1) / (PUNT_THREADS * PUNT_PER_THREAD);
+      ENSURE_DEV(puntBlockCount, 8 * (size_t)nb);
+      ENSURE_DEV(puntBlockPref, 8 * (size_t)nb);
+      if (s2 != st) {
+        CK(cudaEventRecord(ctx->evFork, st));
+        CK(cudaStreamWaitEvent(s2, ctx->evFork, 0));
+      }
+      // the flagged statements in ascending order (deterministic extra-region layout)
+      LAUNCH_ON(s2, "k_punt_count", k_punt_list<false><<<nb, PUNT_THREADS, 0, s2>>>(
+                                        (const uint32_t*)ctx->puntFlag.p, nstmt, (uint2*)ctx->puntBlockCount.p, nullptr, nullptr));
+      LAUNCH_ON(s2, "k_scan_PB", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, s2>>>(
+                                     (const uint2*)ctx->puntBlockCount.p, (uint2*)ctx->puntBlockPref.p, nb, nullptr));
+      LAUNCH_ON(s2, "k_punt_scatter", k_punt_list<true><<<nb, PUNT_THREADS, 0, s2>>>(
+                                          (const uint32_t*)ctx->puntFlag.p, nstmt, nullptr, (const uint2*)ctx->puntBlockPref.p,
+                                          (uint32_t*)ctx->puntList.p));
+      ExactSink xs{nullptr, nullptr, nullptr, nullptr, 0};
+      LAUNCH_ON(s2, "k_lex_exact_count", k_lex_exact<false><<<(npunt + 127) / 128, 128, 0, s2>>>(
+                                             dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p,
+                                             npunt, (uint2*)ctx->puntCounts.p, nullptr, 0u, xs, nullptr, nullptr, nullptr));
+      LAUNCH_ON(s2, "k_scan_P", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, s2>>>(
+                                    (const uint2*)ctx->puntCounts.p, (uint2*)ctx->puntOffs.p, npunt, (uint2*)(dS + 10)));
+      xs = ExactSink{lo.type, lo.start, lo.end, lo.kw, (uint32_t)tok_cap};
+      LAUNCH_ON(s2, "k_lex_exact_emit", k_lex_exact<true><<<(npunt + 127) / 128, 128, 0, s2>>>(
+                                            dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p,
+                                            npunt, nullptr, (const uint2*)ctx->puntOffs.p, ntok_main, xs,
+                                            (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
+                                            (uint32_t*)ctx->puntFlag.p));
+      if (s2 != st) CK(cudaEventRecord(ctx->evJoin, s2));
+    }
     LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p,
                               (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
     if (npunt > 0) {
-      xs = ExactSink{lo.type, lo.start, lo.end, lo.kw, ntok};
-      LAUNCH("k_lex_exact_emit", k_lex_exact<true><<<(npunt + 127) / 128, 128, 0, st>>>(
-                                     dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p, npunt,
-                                     nullptr, (const uint2*)ctx->puntOffs.p, ntok_main, xs, (uint32_t*)ctx->stmtTokBegin.p,
-                                     (uint32_t*)ctx->stmtTokEnd.p, (uint32_t*)ctx->puntFlag.p));
+      if (!ctx->profiling) CK(cudaStreamWaitEvent(st, ctx->evJoin, 0));
+      CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      n_extra = hS[10];
     }
+    ntok = ntok_main + n_extra;
   } else {
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
