@@ -206,6 +206,53 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const typename Op::
   if (threadIdx.x == 0 && total_out) *total_out = total;
 }
 
+// The same scans in two grid-wide passes for long inputs (one entry per 8 KB tile: 131K entries per GiB): a
+// single block walking them took ~0.25 ms per scan.  Pass 1: the aggregate of each run of SCAN_THREADS entries;
+// pass 2: every block reduces the aggregates before it and scans its own run.  n <= SCAN_THREADS^2.
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_totals(const typename Op::T* __restrict__ in, uint32_t n,
+                                                               typename Op::T* __restrict__ block_total) {
+  typedef typename Op::T T;
+  __shared__ T ws[32];
+  const uint32_t i = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  T incl, total;
+  block_scan<Op>(i < n ? in[i] : Op::identity(), ws, incl, total);
+  if (threadIdx.x == 0) block_total[blockIdx.x] = total;
+}
+template <class Op>
+__device__ __forceinline__ typename Op::T scan2_prefix(const typename Op::T* __restrict__ block_total, typename Op::T* ws,
+                                                       typename Op::T v, typename Op::T& total_all) {
+  typedef typename Op::T T;
+  T incl, before;
+  block_scan<Op>(threadIdx.x < blockIdx.x ? block_total[threadIdx.x] : Op::identity(), ws, incl, before);
+  T total;
+  const T excl = block_scan<Op>(v, ws, incl, total);
+  total_all = Op::then(before, total);
+  return Op::then(before, excl);
+}
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_apply(const typename Op::T* __restrict__ in,
+                                                              typename Op::T* __restrict__ out, uint32_t n,
+                                                              const typename Op::T* __restrict__ block_total,
+                                                              typename Op::T* __restrict__ total_out) {
+  typedef typename Op::T T;
+  __shared__ T ws[32];
+  const uint32_t i = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  T all;
+  const T g = scan2_prefix<Op>(block_total, ws, i < n ? in[i] : Op::identity(), all);
+  if (i < n) out[i] = g;
+  if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = all;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_vec8_apply(const uint32_t* __restrict__ in,
+                                                                   uint8_t* __restrict__ entry, uint32_t n,
+                                                                   const uint32_t* __restrict__ block_total) {
+  __shared__ uint32_t ws[32];
+  const uint32_t i = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  uint32_t all;
+  const uint32_t g = scan2_prefix<Vec8Op>(block_total, ws, i < n ? in[i] : NUTDB_VEC8_ID, all);
+  if (i < n) entry[i] = (uint8_t)vec8_apply(g, 0u);
+}
+
 // The statements flagged for the exact lexer, as an ASCENDING list (the flags are raised by whichever warp sees
 // the reason first, so an atomically appended list would make token positions in the extra region -- and with them
 // tok_begin of those statements -- depend on scheduling).  Two passes over punt_flag around a scan of block counts.
@@ -879,7 +926,7 @@ struct NutdbCtx {
   nlex2::Lex2Tables* dLex2 = nullptr;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
-  DevBuf hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+  DevBuf scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
@@ -985,7 +1032,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1245,13 +1292,31 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2,
                                                                   (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p,
                                                                   (uint32_t*)ctx->winMasks.p, mstride));
-    LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
+    const uint32_t sblocks = (ntiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const bool scan2 = ntiles > 2 * SCAN_THREADS && sblocks <= SCAN_THREADS;  // long batch: two-pass grid-wide scans
+    if (scan2) {
+      ENSURE_DEV(scanTotals, 16 * (size_t)sblocks);
+      LAUNCH("k_scan_A", k_scan2_totals<Vec8Op><<<sblocks, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, ntiles,
+                                                                                  (uint32_t*)ctx->scanTotals.p));
+      LAUNCH("k_scan_A2", k_scan2_vec8_apply<<<sblocks, SCAN_THREADS, 0, st>>>(
+                              (const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles, (const uint32_t*)ctx->scanTotals.p));
+    } else {
+      LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
+    }
     LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
                                dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                                (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr,
                                (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
-    LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p,
-                                                                        ntiles, (uint4*)(dS + 4)));
+    if (scan2) {
+      LAUNCH("k_scan_C", k_scan2_totals<CSumOp><<<sblocks, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, ntiles,
+                                                                                  (uint4*)ctx->scanTotals.p));
+      LAUNCH("k_scan_C2", k_scan2_apply<CSumOp><<<sblocks, SCAN_THREADS, 0, st>>>(
+                              (const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p, ntiles, (const uint4*)ctx->scanTotals.p,
+                              (uint4*)(dS + 4)));
+    } else {
+      LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p,
+                                                                          ntiles, (uint4*)(dS + 4)));
+    }
     CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (hS[0]) {

@@ -250,3 +250,11 @@ def test_device_hash_matches_host_arrays_and_is_shard_invariant(ctx):
     t2 = chunks[0][0].copy()
     t2[10] = ord("x") if t2[10] != ord("x") else ord("y")
     assert ctx.parse_batch(t2, chunks[0][1]).device_hash() != ctx.parse_batch(*chunks[0]).device_hash()
+
+
+def test_long_batch_uses_the_two_pass_scans(ctx):
+    """Batches beyond 16 MiB switch the per-tile scans to their two-pass grid-wide form: same results as the oracle."""
+    text, offs = W.generate(3, 20 << 20, seed=77)
+    got = ctx.parse_batch(text, offs)
+    bad = P.compare_with_oracle(got, text, offs)
+    assert not bad, "\n".join(bad[:5])
