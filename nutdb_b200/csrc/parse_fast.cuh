@@ -122,11 +122,46 @@ struct FastParser {
     const uint32_t safe = width_ == 0 ? 2u : width_ == 1 ? (hex ? 16u : 19u) : (hex ? 32u : 38u);
     return len >= 1 && len <= safe;
   }
-  // an escaped string literal can only be rejected through a backslash-u escape (literal.rs:70-88)
-  NUTDB_HD bool string_ok(uint32_t i) {
-    const uint32_t s = tok.start(i), e = tok.end(i);
-    for (uint32_t p = s; p + 1 < e; p++)
-      if (text.byte(p) == '\\' && text.byte(p + 1) == 'u') return false;
+  // Would unescaping this escaped string literal succeed (literal.rs:45-102)?  Only a backslash-u escape can be
+  // rejected (InvalidEscapedUnicode), and a lone trailing backslash makes the reference panic (literal.rs:63); both
+  // go to the automaton, which reports them.  Byte-wise is exact: every character that matters is ASCII, and the
+  // continuation bytes of a skipped multi-byte character are inert.  `quote` doubles as an escape ('' / "").
+  NUTDB_HD bool string_ok(uint32_t i, uint32_t quote) {
+    uint32_t p = tok.start(i);
+    const uint32_t e = tok.end(i);
+    while (p < e) {
+      const uint32_t c = text.byte(p++);
+      if (c == quote) {
+        p++;  // chars.next()
+        continue;
+      }
+      if (c != '\\') continue;
+      if (p >= e) return false;  // the reference panics here
+      if (text.byte(p++) != 'u') continue;
+      if (p >= e || text.byte(p++) != '{') continue;  // plain 'u'; the character after it is dropped
+      bool ok = true, any = false, first = true;
+      uint64_t v = 0;
+      while (p < e) {  // take_while(|&ch| ch != '}') then u32::from_str_radix(.., 16) and char::from_u32
+        const uint32_t h = text.byte(p++);
+        if (h == '}') break;
+        if (first && h == '+') {
+          first = false;
+          continue;
+        }
+        first = false;
+        uint32_t d;
+        if (h >= '0' && h <= '9') d = h - '0';
+        else if (h >= 'a' && h <= 'f') d = h - 'a' + 10;
+        else if (h >= 'A' && h <= 'F') d = h - 'A' + 10;
+        else {
+          ok = false;
+          continue;
+        }
+        any = true;
+        if (v <= 0xFFFFFFFFull) v = v * 16 + d;
+      }
+      if (!ok || !any || v > 0x10FFFF || (v >= 0xD800 && v <= 0xDFFF)) return false;
+    }
     return true;
   }
 
@@ -230,7 +265,7 @@ struct FastParser {
           }
           const uint32_t check = (hi >> 5) & 7u;
           if (check == FK_STR) {
-            if (!string_ok(t)) return false;
+            if (!string_ok(t, ty == NUTDB_TT_EscapedSQStringLiteral ? '\'' : '"')) return false;
           } else if (check != FK_NONE) {
             if (!int_ok(ty, kw, check - FK_INT_W0)) return false;
           }

@@ -6,6 +6,9 @@ import csv, re, subprocess, sys, collections, os, tempfile
 rep, kre, mangled = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 skip = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # kernel instances (in report order) to skip
+name_has = sys.argv[6] if len(sys.argv) > 6 else ""    # e.g. "(bool)1": only instances whose demangled name contains this
+# (the source page lists every instance twice; template instances share one base name, so a wrong `skip` silently
+#  pairs one instance's counters with another's line table -- select by name)
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nutdb_b200", "libnutdb_gpu.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -28,6 +31,9 @@ rows = list(csv.reader(out.splitlines()))
 hdr = None; base = None; acc = collections.Counter(); samples = collections.Counter(); total = 0; started = False
 for r in rows:
     if r and r[0] == "Kernel Name":
+        if name_has and name_has not in r[1]:
+            if started: break
+            hdr = None; continue
         if skip > 0:
             skip -= 1; hdr = None; continue
         if started: break
