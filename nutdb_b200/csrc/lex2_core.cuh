@@ -735,7 +735,18 @@ NUTDB_HD void win_emit(const LexTables& T, Src& src, Sink& sink, const Win& w, c
     }
     sink.token(index_of(i), type, start - sst, pos - sst, 0);
   }
-  // (closes beyond the capture array are flagged for the exact path; their slots stay unwritten)
+  // Closes beyond the capture array: their statement is flagged for the exact path, which gives it a token range of
+  // its own; the slots counted for it here are referenced by nobody, but every output byte has to be a function of
+  // the input alone (reproducible arrays, nutdb_gpu_batch_hash), so they get a fixed filler.
+  if (o.ncap >= NUTDB_L2_NCAP) {
+    uint32_t rest = o.close & has;
+    for (uint32_t c = 0; c < o.ncap; c++) rest &= ~(1u << o.cap_pos[c]);
+    while (rest) {
+      const int i = ctz32(rest);
+      rest &= rest - 1;
+      sink.token(index_of(i), NUTDB_TT_POISON, 0u, 0u, 0);
+    }
+  }
 }
 
 }  // namespace nlex2

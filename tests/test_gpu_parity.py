@@ -238,6 +238,17 @@ def test_device_hash_matches_host_arrays_and_is_shard_invariant(ctx):
         # whose region of the token arrays is laid out in statement order, not in discovery order)
         again = ctx.parse_batch(text, offs)
         assert again.device_hash() == h and np.array_equal(again.stmt, got.stmt)
+    # ... and do not depend on what the context parsed before (no stale bytes in any output array)
+    from nutdb_b200 import gpu as G
+    text, offs = W.generate(3, 1 << 20, seed=5)
+    fresh = G.Context(0)
+    try:
+        h_fresh = fresh.parse_batch(text, offs).device_hash()
+    finally:
+        fresh.close()
+    ctx.parse_batch(*W.generate(4, 1 << 20, seed=6))
+    ctx.parse_batch(*W.generate(3, 2 << 20, seed=7))
+    assert ctx.parse_batch(text, offs).device_hash() == h_fresh
     # the same two chunks on one context in either order, and a changed byte changes the checksum
     chunks = [W.generate(2, 256 << 10, seed=0x5EED0005 + c) for c in range(2)]
     h = []
