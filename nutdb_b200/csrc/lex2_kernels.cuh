@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restric
                                                         uint32_t n, const LexTables* __restrict__ gT,
                                                         const nlex2::Lex2Tables* __restrict__ gK,
                                                         uint32_t* __restrict__ localA, uint32_t* __restrict__ tileA,
-                                                        uint32_t* __restrict__ gmask, size_t mstride) {
+                                                        uint32_t* __restrict__ gmask, size_t mstride,
+                                                        uint32_t* __restrict__ winfn /* may be null */) {
   __shared__ Lex2Shared S;
   __shared__ uint32_t wfn[L2_WARPS];
   const uint32_t tile_begin = blockIdx.x * L2_TILE;
@@ -293,6 +294,9 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restric
     const uint32_t f = u.base < n ? window_fn(S.T, u) : NUTDB_VEC8_ID;
     uint32_t excl;
     run = __shfl_sync(0xFFFFFFFFu, warp_scan_vec8(f, lane, excl), 31);
+    // the composed function of the windows before this one in the warp: the counting pass applies it to the warp's
+    // entry state instead of walking the events a second time
+    if (winfn && u.base < n) winfn[u.base >> 5] = excl;
   }
   if (lane == 0) wfn[warp] = run;
   __syncthreads();
@@ -388,7 +392,8 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
                                                           const uint8_t* __restrict__ tileEntA, uint4* __restrict__ localC,
                                                           uint4* __restrict__ tileC, const uint4* __restrict__ tilePrefC,
                                                           uint32_t* __restrict__ whas, uint8_t* __restrict__ wstate,
-                                                          uint32_t* __restrict__ gmask, size_t mstride, Lex2Out out) {
+                                                          uint32_t* __restrict__ gmask, size_t mstride, Lex2Out out,
+                                                          const uint32_t* __restrict__ winfn) {
   __shared__ Lex2Shared S;
   __shared__ uint4 wsum[L2_WARPS];
   const uint32_t tile_begin = blockIdx.x * L2_TILE;
@@ -409,9 +414,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
     const uint8_t s_warp = (uint8_t)vec8_apply(localA[widx], tileEntA[blockIdx.x]);
     uint8_t s_in;
     if (!Emit) {
-      const uint32_t f = live ? window_fn(S.T, u) : NUTDB_VEC8_ID;
-      uint32_t excl;
-      warp_scan_vec8(f, lane, excl);
+      const uint32_t excl = live ? winfn[u.base >> 5] : NUTDB_VEC8_ID;  // from k_lex2_fn
       s_in = (uint8_t)vec8_apply(excl, s_warp);
       if (live) wstate[u.base >> 5] = s_in;
     } else {

@@ -926,7 +926,7 @@ struct NutdbCtx {
   nlex2::Lex2Tables* dLex2 = nullptr;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
-  DevBuf scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+  DevBuf winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
@@ -1032,7 +1032,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1285,13 +1285,14 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(winState, (size_t)ntiles * (L2_TILE / 32) + 16);
     const size_t mstride = (size_t)ntiles * (L2_TILE / 32);
     ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
+    ENSURE_DEV(winFn, 4 * mstride + 64);
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
     Lex2Out lo{nullptr, nullptr, nullptr, nullptr, 0, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
                (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, dS + 14,
                (const uint32_t*)ctx->firstStmt.p, n};
     LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2,
                                                                   (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p,
-                                                                  (uint32_t*)ctx->winMasks.p, mstride));
+                                                                  (uint32_t*)ctx->winMasks.p, mstride, (uint32_t*)ctx->winFn.p));
     const uint32_t sblocks = (ntiles + SCAN_THREADS - 1) / SCAN_THREADS;
     const bool scan2 = ntiles > 2 * SCAN_THREADS && sblocks <= SCAN_THREADS;  // long batch: two-pass grid-wide scans
     if (scan2) {
@@ -1306,7 +1307,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
                                dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                                (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr,
-                               (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
+                               (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
+                               (const uint32_t*)ctx->winFn.p));
     if (scan2) {
       LAUNCH("k_scan_C", k_scan2_totals<CSumOp><<<sblocks, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, ntiles,
                                                                                   (uint4*)ctx->scanTotals.p));
@@ -1379,7 +1381,8 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p,
-                              (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo));
+                              (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
+                               (const uint32_t*)ctx->winFn.p));
     if (npunt > 0) {
       if (!ctx->profiling) CK(cudaStreamWaitEvent(st, ctx->evJoin, 0));
       CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
@@ -1654,7 +1657,7 @@ int nutdb_gpu_split_statements(NutdbCtx* ctx, const uint8_t* sql, uint64_t len, 
     CK(cudaMemsetAsync(dS, 0, 64, st));
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
     LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2, (uint32_t*)ctx->localA.p,
-                                                                  (uint32_t*)ctx->tileA.p, (uint32_t*)ctx->winMasks.p, nchunks));
+                                                                  (uint32_t*)ctx->tileA.p, (uint32_t*)ctx->winMasks.p, nchunks, nullptr));
     LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
     LAUNCH("k_split_count", k_split<false><<<ntiles, L2_THREADS, 0, st>>>(
                                 dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p, (const uint8_t*)ctx->entA.p,
