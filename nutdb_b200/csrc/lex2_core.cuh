@@ -225,10 +225,11 @@ struct WinCtx {
   uint32_t escm = 0;
   uint8_t s_out = A_C;
   uint8_t ncap = 0;
-  uint8_t cap_pos[NUTDB_L2_NCAP];
-  uint8_t cap_type[NUTDB_L2_NCAP];     // token type; for a literal opened in an earlier window: 1 = '..', 2 = "..", 3 = `..`
-  uint8_t cap_carried[NUTDB_L2_NCAP];
-  uint32_t cap_start[NUTDB_L2_NCAP];   // absolute start of the payload (opened in this window)
+  // the literals / quoted identifiers that CLOSE in this window, 16 bits each (two per word):
+  //   closing offset[0:5) opening offset[5:10) carried[10] type code[11:13)
+  // type code, opened in this window: 0 raw, 1 escaped '..', 2 escaped "..", 3 `..`;
+  // opened in an earlier window (carried): the kind 1 = '..', 2 = "..", 3 = `..`
+  uint32_t capw[NUTDB_L2_NCAP / 2] = {0, 0};
   uint8_t esc_first = 0;               // this window's escaped-flag contribution before a carried close
   StrCarry sc;
   uint32_t last_bnd1 = 0;              // 1 + absolute offset of the last statement start in the window, 0 if none
@@ -255,16 +256,15 @@ NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Ne
       if (w.bs & r) cur_esc = 1;
     } else if (s == A_BT) m_bt |= r;
   };
-  auto record = [&](int e, uint8_t local_type, uint8_t kind) {
+  auto record = [&](int e, uint8_t local_code, uint8_t kind) {
     o.close |= 1u << e;
     if (o.ncap >= NUTDB_L2_NCAP) {
       o.bad |= 1u << e;
       return;
     }
-    o.cap_pos[o.ncap] = (uint8_t)e;
-    o.cap_carried[o.ncap] = open_local ? 0 : 1;
-    o.cap_type[o.ncap] = open_local ? local_type : kind;
-    o.cap_start[o.ncap] = cur_start + 1;
+    const uint32_t c = (uint32_t)e | (((cur_start - base) & 31u) << 5) | (open_local ? 0u : 1u << 10) |
+                       ((uint32_t)(open_local ? local_code : kind) << 11);
+    o.capw[o.ncap >> 1] |= c << (16u * (o.ncap & 1u));
     if (!open_local) o.esc_first = cur_esc;
     o.ncap++;
   };
@@ -316,13 +316,11 @@ NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Ne
       if (twin) {
         reopen_at = e + 1;
       } else {
-        record(e, cur_esc ? (t == EV_SQ ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
-                          : (uint8_t)NUTDB_TT_RawStringLiteral,
-               t == EV_SQ ? 1 : 2);
+        record(e, cur_esc ? (t == EV_SQ ? 1 : 2) : 0, t == EV_SQ ? 1 : 2);
         cur_esc = 0;
       }
     } else if (a0 == A_BT && t == EV_BT) {
-      record(e, NUTDB_TT_DelimitedIdentifier, 3);
+      record(e, 3, 3);
       // `` : Incomplete (tokenizer/mod.rs:323): the previous byte is the opening backtick
       if (e > 0 ? ((w.bt >> (e - 1)) & 1u) != 0 : prev_byte == '`') o.bad |= 1u << e;
       cur_esc = 0;
@@ -337,6 +335,38 @@ NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Ne
   o.ct = m_code & ~consumed & w.valid;
   o.in_str = m_str & w.valid;
   o.in_bt = m_bt & w.valid;
+}
+
+// What the emitting pass needs of a window's context walk, packed by the counting pass so that the walk is done once:
+//   w0 = ct, w1 = close,
+//   w2 = ncap[0:3) has_open[3] sc.esc[4] esc_first[5] open offset[6:11) last statement start offset + 1 [11:17),
+//   w3 / w4 = WinCtx::capw.
+struct WinCtxPacked {
+  uint32_t w[5];
+};
+NUTDB_HD WinCtxPacked ctx_pack(const WinCtx& o, uint32_t base) {
+  WinCtxPacked p;
+  p.w[0] = o.ct;
+  p.w[1] = o.close;
+  p.w[2] = (uint32_t)o.ncap | ((uint32_t)o.sc.has_open << 3) | ((uint32_t)(o.sc.esc != 0) << 4) |
+           ((uint32_t)(o.esc_first != 0) << 5) | (((o.sc.open_pos - base) & 31u) << 6) |
+           ((o.last_bnd1 ? o.last_bnd1 - base : 0u) << 11);
+  p.w[3] = o.capw[0];
+  p.w[4] = o.capw[1];
+  return p;
+}
+NUTDB_HD void ctx_unpack(const WinCtxPacked& p, uint32_t base, WinCtx& o) {
+  o.ct = p.w[0];
+  o.close = p.w[1];
+  o.ncap = (uint8_t)(p.w[2] & 7u);
+  o.sc.has_open = (uint8_t)((p.w[2] >> 3) & 1u);
+  o.sc.esc = (uint8_t)((p.w[2] >> 4) & 1u);
+  o.esc_first = (uint8_t)((p.w[2] >> 5) & 1u);
+  o.sc.open_pos = base + ((p.w[2] >> 6) & 31u);
+  const uint32_t lb = (p.w[2] >> 11) & 63u;
+  o.last_bnd1 = lb ? base + lb : 0u;
+  o.capw[0] = p.w[3];
+  o.capw[1] = p.w[4];
 }
 
 // ---- stage 3: what token (if any) ENDS at this lane's byte ----
@@ -722,15 +752,19 @@ NUTDB_HD void win_emit(const LexTables& T, Src& src, Sink& sink, const Win& w, c
   }
   // strings and quoted identifiers, at their closing quote
   for (uint32_t c = 0; c < o.ncap; c++) {
-    const int i = o.cap_pos[c];
+    const uint32_t cw = (o.capw[c >> 1] >> (16u * (c & 1u))) & 0xFFFFu;
+    const int i = (int)(cw & 31u);
     const uint32_t pos = base + (uint32_t)i, sst = stmt_of(i);
-    uint8_t type = o.cap_type[c];
-    uint32_t start = o.cap_start[c];
-    if (o.cap_carried[c]) {  // opened in an earlier window: offset and escaped flag come from the carry
+    const uint32_t code = (cw >> 11) & 3u;
+    uint8_t type = code == 0 ? (uint8_t)NUTDB_TT_RawStringLiteral
+                   : code == 1 ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral
+                   : code == 2 ? (uint8_t)NUTDB_TT_EscapedDQStringLiteral : (uint8_t)NUTDB_TT_DelimitedIdentifier;
+    uint32_t start = base + ((cw >> 5) & 31u) + 1u;
+    if ((cw >> 10) & 1u) {  // opened in an earlier window: offset and escaped flag come from the carry
       start = sc_in.open_pos + 1u;
       const bool escd = (sc_in.esc | o.esc_first) != 0;
-      type = type == 3 ? (uint8_t)NUTDB_TT_DelimitedIdentifier
-                       : (escd ? (type == 1 ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
+      type = code == 3 ? (uint8_t)NUTDB_TT_DelimitedIdentifier
+                       : (escd ? (code == 1 ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral : (uint8_t)NUTDB_TT_EscapedDQStringLiteral)
                                : (uint8_t)NUTDB_TT_RawStringLiteral);
     }
     sink.token(index_of(i), type, start - sst, pos - sst, 0);
@@ -740,7 +774,7 @@ NUTDB_HD void win_emit(const LexTables& T, Src& src, Sink& sink, const Win& w, c
   // the input alone (reproducible arrays, nutdb_gpu_batch_hash), so they get a fixed filler.
   if (o.ncap >= NUTDB_L2_NCAP) {
     uint32_t rest = o.close & has;
-    for (uint32_t c = 0; c < o.ncap; c++) rest &= ~(1u << o.cap_pos[c]);
+    for (uint32_t c = 0; c < o.ncap; c++) rest &= ~(1u << ((o.capw[c >> 1] >> (16u * (c & 1u))) & 31u));
     while (rest) {
       const int i = ctz32(rest);
       rest &= rest - 1;

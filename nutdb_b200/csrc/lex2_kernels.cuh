@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
                                                           const uint32_t* __restrict__ localA,
                                                           const uint8_t* __restrict__ tileEntA, uint4* __restrict__ localC,
                                                           uint4* __restrict__ tileC, const uint4* __restrict__ tilePrefC,
-                                                          uint32_t* __restrict__ whas, uint8_t* __restrict__ wstate,
+                                                          uint32_t* __restrict__ whas, uint32_t* __restrict__ wctx,
                                                           uint32_t* __restrict__ gmask, size_t mstride, Lex2Out out,
                                                           const uint32_t* __restrict__ winfn) {
   __shared__ Lex2Shared S;
@@ -416,12 +416,25 @@ __global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restr
     if (!Emit) {
       const uint32_t excl = live ? winfn[u.base >> 5] : NUTDB_VEC8_ID;  // from k_lex2_fn
       s_in = (uint8_t)vec8_apply(excl, s_warp);
-      if (live) wstate[u.base >> 5] = s_in;
     } else {
-      s_in = live ? wstate[u.base >> 5] : (uint8_t)A_C;
+      s_in = (uint8_t)A_C;
     }
+    // the concrete walk of the window's events is done once, by the counting pass; the emitting pass reads what it
+    // needs of the result (5 words per window)
     nlex2::WinCtx o;
-    if (live) nlex2::ctx_window(u.w, u.ev, u.base, u.nx, s_in, u.prev_byte, o);
+    if (live) {
+      if (!Emit) {
+        nlex2::ctx_window(u.w, u.ev, u.base, u.nx, s_in, u.prev_byte, o);
+        const nlex2::WinCtxPacked pk = nlex2::ctx_pack(o, u.base);
+#pragma unroll
+        for (int q = 0; q < 5; q++) wctx[(size_t)q * mstride + (u.base >> 5)] = pk.w[q];
+      } else {
+        nlex2::WinCtxPacked pk;
+#pragma unroll
+        for (int q = 0; q < 5; q++) pk.w[q] = wctx[(size_t)q * mstride + (u.base >> 5)];
+        nlex2::ctx_unpack(pk, u.base, o);
+      }
+    }
     o.escm = u.escm;
     // history: code-token class masks of the previous window (lane 0: the 32 bytes in front of the block, whose
     // raw classes are exact when the block is entered in code)

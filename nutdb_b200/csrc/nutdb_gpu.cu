@@ -926,7 +926,7 @@ struct NutdbCtx {
   nlex2::Lex2Tables* dLex2 = nullptr;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
-  DevBuf winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+  DevBuf winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
@@ -1032,7 +1032,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1282,10 +1282,10 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(entA, ntiles);
     ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
     ENSURE_DEV(winCount, 4 * ((size_t)ntiles * (L2_TILE / 32) + 16));
-    ENSURE_DEV(winState, (size_t)ntiles * (L2_TILE / 32) + 16);
     const size_t mstride = (size_t)ntiles * (L2_TILE / 32);
     ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
     ENSURE_DEV(winFn, 4 * mstride + 64);
+    ENSURE_DEV(winCtx, 4 * mstride * 5 + 64);
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
     Lex2Out lo{nullptr, nullptr, nullptr, nullptr, 0, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
                (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, dS + 14,
@@ -1307,7 +1307,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
                                dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                                (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr,
-                               (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
+                               (uint32_t*)ctx->winCount.p, (uint32_t*)ctx->winCtx.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
                                (const uint32_t*)ctx->winFn.p));
     if (scan2) {
       LAUNCH("k_scan_C", k_scan2_totals<CSumOp><<<sblocks, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, ntiles,
@@ -1381,7 +1381,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p,
-                              (uint32_t*)ctx->winCount.p, (uint8_t*)ctx->winState.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
+                              (uint32_t*)ctx->winCount.p, (uint32_t*)ctx->winCtx.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
                                (const uint32_t*)ctx->winFn.p));
     if (npunt > 0) {
       if (!ctx->profiling) CK(cudaStreamWaitEvent(st, ctx->evJoin, 0));

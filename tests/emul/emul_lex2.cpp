@@ -348,7 +348,11 @@ int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
           count += nt;
         } else {
           const uint32_t has = whas[base >> 5];
-          win_emit(g_T, src, out, u.w, o, h, u.nx, base, u.prev_byte, sc, stmt_start, count, has);
+          // the device's emitting pass does not walk the events again: it unpacks what the counting pass stored
+          WinCtx o2;
+          ctx_unpack(ctx_pack(o, base), base, o2);
+          o2.escm = o.escm;
+          win_emit(g_T, src, out, u.w, o2, h, u.nx, base, u.prev_byte, sc, stmt_start, count, has);
           count += (uint32_t)popc32(has) + (uint32_t)popc32(win_eof_mask(u.w, u.nx));
         }
         sc = str_then(sc, o.sc);
