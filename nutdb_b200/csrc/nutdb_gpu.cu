@@ -45,7 +45,7 @@ using namespace nlex;
 #define FAST_MINBLOCKS 3
 #endif
 //#define FAST_THREADS_DOC     // statements per CTA in k_parse_fast (re-dealt among its warps)
-#define FAST_BINS 64
+#define FAST_BINS 256         // 4 statement kinds x 64 token counts
 #define PARSE_STACK 160      // words of local stack in the fast path
 #define FIN_THREADS 256
 #define NODE_SLACK 8u        // fast-path node range of a statement = its token count + NODE_SLACK
@@ -651,15 +651,28 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
     const uint32_t p0 = (j0 < FAST_TOKCAP && !lex_only) ? (uint32_t)stok[j0] : ((uint32_t)tok_type[tb0] | ((uint32_t)tok_kw[tb0] << 8));
     const uint32_t k0 = (p0 & 0xFFu) == NUTDB_TT_KeywordOrIdentifier ? (p0 >> 8) : 0u;
     const uint32_t kind = k0 == npar::KW_SELECT ? 0u : (k0 == npar::KW_INSERT ? 1u : (k0 == npar::KW_CREATE ? 2u : 3u));
-    key = kind * 16u + min(15u, tc0 >> 2);
+    key = kind * 64u + min(63u, tc0);  // equal token counts in a warp: its lanes finish together
   }
   rank = atomicAdd(&bin_count[key], 1u);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t acc = 0;
-    for (int b = 0; b < FAST_BINS; b++) {
-      bin_base[b] = acc;
-      acc += bin_count[b];
+  {  // exclusive prefix over the bins (first FAST_BINS threads: warp scans + the warp totals)
+    __shared__ uint32_t bin_wtot[FAST_BINS / 32];
+    uint32_t v = 0, incl = 0;
+    if (threadIdx.x < FAST_BINS) {
+      v = bin_count[threadIdx.x];
+      incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o2 = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((threadIdx.x & 31u) >= (uint32_t)d) incl += o2;
+      }
+      if ((threadIdx.x & 31u) == 31u) bin_wtot[threadIdx.x >> 5] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < FAST_BINS) {
+      uint32_t before = 0;
+      for (uint32_t q = 0; q < (threadIdx.x >> 5); q++) before += bin_wtot[q];
+      bin_base[threadIdx.x] = before + incl - v;
     }
   }
   __syncthreads();
