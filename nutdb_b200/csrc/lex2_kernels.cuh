@@ -8,6 +8,17 @@
 #pragma once
 
 #define L2_THREADS 256
+// resident CTAs per SM the walk kernels are compiled for (register cap): measured best, counting pass 5 (48
+// registers), emitting pass 4 (64)
+#ifndef L2_COUNT_MINBLOCKS
+#define L2_COUNT_MINBLOCKS 5
+#endif
+#ifndef L2_EMIT_MINBLOCKS
+#define L2_EMIT_MINBLOCKS 4
+#endif
+#ifndef L2_FN_MINBLOCKS
+#define L2_FN_MINBLOCKS 8
+#endif
 #define L2_WARPS (L2_THREADS / 32)
 #define L2_SEG 1024                     // bytes per warp
 #define L2_TILE (L2_WARPS * L2_SEG)     // bytes per block
@@ -273,7 +284,7 @@ __device__ __forceinline__ uint32_t window_fn(const LexTables& T, const WinSetup
   return vec8_then_row(NUTDB_VEC8_ID, T.a_row[EV_OTHER][0], T.a_row[EV_OTHER][1]);
 }
 
-__global__ void __launch_bounds__(L2_THREADS) k_lex2_fn(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
+__global__ void __launch_bounds__(L2_THREADS, L2_FN_MINBLOCKS) k_lex2_fn(const uint8_t* __restrict__ text, const uint32_t* __restrict__ bitmap,
                                                         uint32_t n, const LexTables* __restrict__ gT,
                                                         const nlex2::Lex2Tables* __restrict__ gK,
                                                         uint32_t* __restrict__ localA, uint32_t* __restrict__ tileA,
@@ -384,7 +395,7 @@ struct Lex2Out {
 
 // Emit = false: token-end mask per window (whas) + per-warp carries + flags; Emit = true: tokens.
 template <bool Emit>
-__global__ void __launch_bounds__(L2_THREADS) k_lex2_walk(const uint8_t* __restrict__ text,
+__global__ void __launch_bounds__(L2_THREADS, Emit ? L2_EMIT_MINBLOCKS : L2_COUNT_MINBLOCKS) k_lex2_walk(const uint8_t* __restrict__ text,
                                                           const uint32_t* __restrict__ bitmap, uint32_t n,
                                                           const LexTables* __restrict__ gT,
                                                           const nlex2::Lex2Tables* __restrict__ gK,
