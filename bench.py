@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=64 << 20, help="bytes of SQL per pipelined chunk on the host path")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="contexts (threads) the host path pipelines chunks over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -380,10 +381,10 @@ def main():
         h_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
         flags = gpu.F_NO_TOKENS  # the reference API never exposes tokens (mod.rs:27 returns Statement only)
 
-        # host-resident batch -> chunked, double-buffered through 3 contexts (nutdb_b200.stream):
+        # host-resident batch -> chunked, pipelined through --e2e-workers contexts (nutdb_b200.stream):
         # uploads, kernels and downloads of different chunks overlap
         from nutdb_b200 import stream
-        sp = stream.StreamParser(local, workers=3)
+        sp = stream.StreamParser(local, workers=args.e2e_workers)
         h_text_np, h_offs_np = h_text.numpy(), h_offs.numpy().view(np.uint64)
         acc = {}
 
@@ -491,7 +492,7 @@ def main():
                            "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
                            "ms_per_step": e2e_ms_max, "statements_per_s": tot_stmts / (e2e_ms_max * 1e-3),
                            "api": "nutdb_b200.stream.StreamParser: nutdb_gpu_parse_batch(pinned host text, host offsets, "
-                                  "NUTDB_F_NO_TOKENS) per chunk on 3 contexts -> pinned host stmt/node/err arrays",
+                                  f"NUTDB_F_NO_TOKENS) per chunk on {args.e2e_workers} contexts -> pinned host stmt/node/err arrays",
                            "chunk_bytes": args.e2e_chunk}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(text, offs)
