@@ -493,6 +493,11 @@ struct DTok {
 #define FAST_TOKCAP 16384u
 #endif
 #define FAST_DYN_SMEM (FAST_TOKCAP * 2 + FAST_STACK_DEPTH * FAST_THREADS * 8)
+// k_parse_fast is tuned for FAST_MINBLOCKS resident CTAs per SM: tables + sort arrays + dynamic part + the 1 KB the
+// driver reserves per CTA must fit 227 KB that many times (one CTA less costs ~25 % of the kernel's speed)
+static_assert(FAST_MINBLOCKS * (sizeof(npar::FastTables) + 4 * (2 * FAST_BINS + FAST_THREADS + 16) + FAST_DYN_SMEM + 1024) <=
+                  227 * 1024,
+              "k_parse_fast: shared memory per CTA too large for the intended occupancy");
 struct DTokS {
   const uint16_t* sm;
   uint32_t rel;
@@ -521,6 +526,7 @@ struct DNodes {
   __device__ __forceinline__ void set(uint32_t i, const npar::CNode& x) {
     p[i] = make_uint2((uint32_t)x.kind | ((uint32_t)x.sub << 8) | ((uint32_t)x.aux << 16), x.x);
   }
+  __device__ __forceinline__ void set_raw(uint32_t i, uint32_t header, uint32_t x) { p[i] = make_uint2(header, x); }
   __device__ __forceinline__ uint32_t capacity() const { return cap; }
 };
 // First compact-node slot of statement s.  Token ranges of natively lexed statements ascend with s, so

@@ -83,17 +83,18 @@ enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DT
 enum : uint32_t { FE_NONE = 0, FE_LEAF_TOK, FE_LEAF_NOTOK, FE_NODE_M0, FE_NODE_M1, FE_NODE_ZERO };
 enum : uint32_t { FK_NONE = 0, FK_INT_W0, FK_INT_W1, FK_INT_W2, FK_STR };
 enum : uint32_t { FL_NONE = 0, FL_NODOT, FL_NODOT_NOLP };
-static const uint32_t FAST_MAX_REC = 224;
+static const uint32_t FAST_MAX_REC = 128;
 static const uint32_t FAST_HI_UNCOMMON = 0x03FFFFE0u;  // every hi field except pre / post / setcur
 
+// Token-indexed tables take ONE index for both kinds of token: the token type, or 64 + keyword id for a word.
 struct FastTables {
-  uint16_t optok[48];   // by token type: power | op << 4 | bail << 12   (token_power, mod.rs:1895-1927)
-  uint16_t opkw[128];   // by keyword id: same encoding
-  uint8_t tycls[48];    // token type -> FastClass
-  uint8_t kwcls[128];   // keyword id -> FastClass
+  uint16_t op[192];     // power | op << 4 | bail << 12   (token_power, mod.rs:1895-1927)
+  uint8_t cls[192];     // -> FastClass
   uint8_t trans[FS_COUNT][FC_COUNT];  // -> record index (0 = bail)
   uint32_t rec_lo[FAST_MAX_REC], rec_hi[FAST_MAX_REC];
+  uint32_t rec_hdr[FAST_MAX_REC];  // first word of the compact node a record emits: kind | sub << 8 | aux bit << 16
 };
+NUTDB_HD uint32_t fast_token_index(uint32_t ty, uint32_t kw) { return ty == NUTDB_TT_KeywordOrIdentifier ? 64u + kw : ty; }
 
 template <class Tok, class Nodes, class Text>
 struct FastParser {
@@ -198,9 +199,10 @@ struct FastParser {
       if (n > cap) return false;  // (a store beyond the range was skipped: the automaton redoes the statement)
       p = tok.pair_at(t);  // the current token never lies beyond the statement's EOF token
       const uint32_t ty = p & 255u, kw = p >> 8;
+      const uint32_t ti = fast_token_index(ty, kw);
       if (st == FS_X_OPER) {
         // ---------------- operators: token_power (mod.rs:1895-1927) + must_parse_expr_infix ----------------
-        const uint32_t e = ty == NUTDB_TT_KeywordOrIdentifier ? F->opkw[kw] : F->optok[ty];
+        const uint32_t e = F->op[ti];
         if (e >> 12) return false;  // NOT / IS / BETWEEN / index access: the automaton
         const uint32_t power = e & 15u, op = (e >> 4) & 63u;
         // everything of equal or higher power on the stack is complete (left-associative)
@@ -250,7 +252,7 @@ struct FastParser {
         }
         st = FS_AFTER + ctx;  // the expression is complete: the same token decides what follows it
       }
-      const uint32_t cls = ty == NUTDB_TT_KeywordOrIdentifier ? F->kwcls[kw] : F->tycls[ty];
+      const uint32_t cls = F->cls[ti];
       const uint32_t ri = F->trans[st][cls];
       const uint32_t lo = F->rec_lo[ri];
       const uint32_t act = lo & 15u;
@@ -287,8 +289,8 @@ struct FastParser {
         if (em != FE_NONE) {
           const uint32_t x = em == FE_LEAF_TOK ? t : em == FE_LEAF_NOTOK ? NUTDB_CN_NOTOK : em == FE_NODE_M0 ? m0
                              : em == FE_NODE_M1 ? m1 : 0u;
-          const uint32_t ax = ((lo >> 27) & 1u) | ((lo >> 28) & auxr);
-          FAST_EMIT(kind, (lo >> 23) & 15u, ax, x);
+          if (n < cap) nd.set_raw(n, F->rec_hdr[ri] | (((lo >> 28) & auxr) << 16), x);
+          n++;
         }
         t += (lo >> 11) & 1u;
         if (hi & 4u) m0 = n;

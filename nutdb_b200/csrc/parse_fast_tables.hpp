@@ -79,8 +79,10 @@ class FastTableBuilder {
   void finish() {
     if (recs_.size() > FAST_MAX_REC) throw std::runtime_error("fast parser: too many transition records");
     for (size_t i = 0; i < recs_.size(); i++) {
-      F.rec_lo[i] = recs_[i].first;
+      const uint32_t lo = recs_[i].first;
+      F.rec_lo[i] = lo;
       F.rec_hi[i] = recs_[i].second;
+      F.rec_hdr[i] = ((lo >> 15) & 255u) | (((lo >> 23) & 15u) << 8) | (((lo >> 27) & 1u) << 16);
     }
   }
 
@@ -207,13 +209,13 @@ inline uint8_t fast_keyword_class(uint32_t kw) {
 inline void fast_tables_build(FastTables& F) {
   static_assert(FS_COUNT <= 128 && FC_COUNT <= 64, "state / class fields");
   FastTableBuilder B(F);
-  for (uint32_t i = 0; i < 48; i++) {
-    F.optok[i] = fast_optok_entry(i);
-    F.tycls[i] = fast_type_class(i);
+  for (uint32_t i = 0; i < 64; i++) {
+    F.op[i] = fast_optok_entry(i);
+    F.cls[i] = fast_type_class(i);
   }
   for (uint32_t i = 0; i < 128; i++) {
-    F.opkw[i] = fast_opkw_entry(i);
-    F.kwcls[i] = fast_keyword_class(i);
+    F.op[64 + i] = fast_opkw_entry(i);
+    F.cls[64 + i] = fast_keyword_class(i);
   }
   auto R = [] { return FastRec(); };
   const FastRec skip_to_operand = R().adv().to(FS_X_OPND);

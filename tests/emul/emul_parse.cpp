@@ -48,6 +48,14 @@ struct HNodes {
     if (i >= v.size()) v.resize(i + 1);
     v[i] = x;
   }
+  void set_raw(uint32_t i, uint32_t header, uint32_t x) {
+    npar::CNode c;
+    c.kind = (uint8_t)(header & 0xFF);
+    c.sub = (uint8_t)((header >> 8) & 0xFF);
+    c.aux = (uint16_t)(header >> 16);
+    c.x = x;
+    set(i, c);
+  }
   uint32_t capacity() const { return cap; }
 };
 struct HCompact {
