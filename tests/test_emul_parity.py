@@ -140,6 +140,25 @@ def test_config2_is_entirely_fast_path():
     assert E.fast_hits() == len(offs) - 1
 
 
+def test_config3_mostly_fast_path_with_unicode_escapes_validated_in_place():
+    # config 3's strings are full of backslash-u escapes: the table-driven parser validates them itself
+    # (literal.rs:70-88) and only hands the malformed 5 % (and the odd construct) to the automaton
+    text, offs = W.generate(3, 256 << 10)
+    E.fast_hits()
+    got = E.parse_batch(text, offs)
+    assert E.fast_hits() > 0.9 * (len(offs) - 1)
+    bad = P.compare_with_oracle(got, text, offs)
+    assert not bad, "\n".join(bad[:5])
+
+
+def test_unicode_escape_edge_cases():
+    check([b"select 'a\\u{41}'", b"select 'a\\u{110000}'", b"select 'a\\u{}'", b"select 'a\\u{+41}' from t",
+           b"select 'a\\u{D800}'", b"select 'a\\u{DFFF}', 'b\\u{E000}'", b'select "q\\u{1F600" from t',
+           b"select 'a\\uz' , '\\u{zz}'", b"select '\\u{41', 1", b"select 'it''s \\u{e9}'", b"select '\\\\u{zz}'",
+           b"select '\\u{+}'", b"select '\\u{FFFFFFFFF}'", b"select '\\u{0041}\\u{10FFFF}' where 'x\\u' = 1",
+           "select 'é\\u{é}'".encode(), "select '\\é\\u{41}é'".encode()])
+
+
 def test_extra_seeds_unmutated():
     check(fuzz.EXTRA_SEEDS)
 
