@@ -460,8 +460,31 @@ NUTDB_HD LaneTok tok_word(const LexTables& T, Src& src, const WinTok& k, const N
     return r;
   }
   const uint64_t span = ((p >= 63 ? ~0ull : ((2ull << p) - 1ull))) & ~((1ull << st) - 1ull);
-  if (k.L64 & span) { r.bad = 1; return r; }  // 1abc, 0x1F ...: error or hex -> exact path
   const bool left_dot = ((k.DOT64 >> (st - 1)) & 1ull) && !((k.bnd64 >> st) & 1ull);
+  if (k.L64 & span) {
+    // A digit-led run with letters in it is an error (1abc) -- or a hex literal: "0" then x / X then hex digits
+    // (tokenizer/mod.rs:201-208; the span is the digits, and there is NO end-of-token check).  Only the plain form
+    // is lexed here: every character after "0x" a hex digit and no '.' on either side; "0x1G" (a hex literal
+    // followed by an identifier), "0x1.5" and ".0x1" split differently and go to the exact path.
+    if (p > st && !left_dot && !((k.nextDOT >> i) & 1u) && src.byte(abs_st) == '0' && (src.byte(abs_st + 1u) | 0x20) == 'x') {
+      bool all_hex = true;
+      for (uint32_t q = abs_st + 2u; q <= pos; q++) {
+        const uint8_t c = src.byte(q);
+        all_hex = all_hex && ((c >= '0' && c <= '9') || ((c | 0x20) >= 'a' && (c | 0x20) <= 'f'));
+      }
+      if (all_hex) {
+        r.has = 1;
+        r.type = NUTDB_TT_HexLiteral;
+        r.start = abs_st + 2u;
+        r.end = pos + 1u;
+        const uint32_t len = r.end - r.start;
+        r.kw = (uint8_t)(len > 255u ? 255u : len);
+        return r;
+      }
+    }
+    r.bad = 1;
+    return r;
+  }
   if ((k.nextDOT >> i) & 1u) {  // digits '.' ...: the token ends later
     if (left_dot) r.bad = 1;    // second dot of one numeric token: error
     return r;
