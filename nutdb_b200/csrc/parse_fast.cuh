@@ -9,8 +9,9 @@
 //   CREATE TABLE [IF NOT EXISTS] name (name type [DEFAULT e | COMMENT s].. ,..)
 //          [PRIMARY KEY es | ORDER BY es | PARTITION BY e | COMMENT s]..
 //
-// with expressions over identifiers, literals, the binary operators, AND/OR/XOR, IN/LIKE/ILIKE,
-// parenthesised groups / tuples and function calls (operator-precedence parsing with an explicit
+// with expressions over identifiers, literals, the binary operators, AND/OR/XOR, [NOT] IN/LIKE/ILIKE,
+// [NOT] BETWEEN .. AND .., IS [NOT] NULL, prefix NOT, parenthesised groups / tuples and function calls
+// (operator-precedence parsing with an explicit
 // operator stack -- the iterative form of must_parse_expr_tdop, reference mod.rs:1209-1220: an
 // operator is reduced when one of equal or lower power arrives, so every operator is
 // left-associative exactly as in the reference).
@@ -28,7 +29,7 @@
 //
 // It is ALL-OR-NOTHING: on anything outside that subset -- any error, any construct that needs
 // constant folding (simplify.rs), literal validation beyond a length check, joins, set
-// operations, subqueries, CASE/IF/NOT/IS/BETWEEN, arrays, maps ... -- try_parse() returns false
+// operations, subqueries, CASE/IF/INTERVAL, NOT EXISTS, arrays, maps ... -- try_parse() returns false
 // without side effects the caller keeps, and the statement is parsed from scratch by the exact
 // automaton.  For a statement it accepts, it emits precisely the nodes the automaton would.
 #pragma once
@@ -75,7 +76,7 @@ enum FastState : uint8_t {
   FS_COUNT
 };
 
-enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT };
+enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT };
 
 // ---- transition record: two words ----
 // lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28]
@@ -104,9 +105,13 @@ struct FastParser {
   Text text;
   FastStackEntry* stk;  // the caller's memory (shared memory on the device): entry i of this thread at stk[i * stride]
   uint32_t stride;
-  // operator / bracket stack entries: x = type | power << 2 | op << 6 | left kind << 12 | item count << 20
-  // (E_DT: x = type | compound sub << 2), y = start of the left operand (E_OP) / node count at the opening
-  enum : uint32_t { E_OP = 0, E_PAREN = 1, E_CALL = 2, E_DT = 3 };
+  // operator / bracket stack entries: x = type | power << 3 | op << 7 | left kind << 13 | item count << 21
+  // (E_DT: x = type | compound sub << 3), y = start of the left operand (operators) / node count at the opening.
+  // The power of an entry is the min_power its right operand is parsed with (must_parse_expr_tdop, mod.rs:1209):
+  // an arriving operator of equal or lower power completes it.  E_NOT = prefix NOT, E_BTW1 / E_BTW2 = [NOT] BETWEEN
+  // before / after its AND (op = FnName Between 3 / NotBetween 4).
+  enum : uint32_t { E_OP = 0, E_PAREN = 1, E_CALL = 2, E_DT = 3, E_NOT = 4, E_BTW1 = 5, E_BTW2 = 6 };
+  enum : uint32_t { SPEC_NONE = 0, SPEC_BAIL = 1, SPEC_NOT = 2, SPEC_IS = 3, SPEC_BETWEEN = 4 };  // FastTables::op >> 12
   static const uint32_t DEPTH = FAST_STACK_DEPTH;
 
   NUTDB_HD FastParser(const FastTables* ft, const Tok& tk, const Nodes& nodes, const Text& tx, FastStackEntry* stack,
@@ -203,27 +208,89 @@ struct FastParser {
       if (st == FS_X_OPER) {
         // ---------------- operators: token_power (mod.rs:1895-1927) + must_parse_expr_infix ----------------
         const uint32_t e = F->op[ti];
-        if (e >> 12) return false;  // NOT / IS / BETWEEN / index access: the automaton
+        const uint32_t spec = e >> 12;
+        if (spec == SPEC_BAIL) return false;  // index access: the automaton
         const uint32_t power = e & 15u, op = (e >> 4) & 63u;
         // everything of equal or higher power on the stack is complete (left-associative)
+        bool took_and = false;
         while (sp > 0) {
           const FastStackEntry top = stk[(sp - 1) * stride];
-          if ((top.x & 3u) != E_OP || ((top.x >> 2) & 15u) < power) break;
-          // BinaryOp{op, left, right}; refuse whatever simplify.rs would fold
-          const uint32_t bop = (top.x >> 6) & 63u, lkind = (top.x >> 12) & 255u;
-          if (bop == 9 || bop == 10) {  // simplified_eq / simplified_neq
-            if (is_literal(lkind) && is_literal(cur_kind)) return false;
-          } else if (bop >= 11 && bop <= 13) {  // simplified_and / or / xor
-            if (lkind == NUTDB_NK_LIT_BOOL || cur_kind == NUTDB_NK_LIT_BOOL) return false;
+          const uint32_t type = top.x & 7u;
+          if (((top.x >> 3) & 15u) < power) break;  // (brackets carry power 0: only a terminator gets past this)
+          if (type == E_OP) {
+            // BinaryOp{op, left, right}; refuse whatever simplify.rs would fold
+            const uint32_t bop = (top.x >> 7) & 63u, lkind = (top.x >> 13) & 255u;
+            if (bop == 9 || bop == 10) {  // simplified_eq / simplified_neq
+              if (is_literal(lkind) && is_literal(cur_kind)) return false;
+            } else if (bop >= 11 && bop <= 13) {  // simplified_and / or / xor
+              if (lkind == NUTDB_NK_LIT_BOOL || cur_kind == NUTDB_NK_LIT_BOOL) return false;
+            }
+            sp--;
+            cur_start = top.y;
+            cur_kind = NUTDB_NK_BINARY;
+            FAST_EMIT(NUTDB_NK_BINARY, bop, 0, cur_start);
+          } else if (type - 1u < 3u) {  // E_PAREN / E_CALL / E_DT: the terminator belongs to the bracket
+            break;
+          } else if (type == E_NOT) {  // simplified_not (simplify.rs): a boolean literal would be flipped
+            if (cur_kind == NUTDB_NK_LIT_BOOL) return false;
+            sp--;
+            cur_kind = NUTDB_NK_UNARY;
+            FAST_EMIT(NUTDB_NK_UNARY, 1, 0, cur_start);
+          } else if (type == E_BTW1) {  // `left BETWEEN x` must continue with AND (mod.rs:1445-1449)
+            if (!(ty == NUTDB_TT_KeywordOrIdentifier && kw == KW_AND)) return false;
+            stk[(sp - 1) * stride].x = (top.x & ~7u) | E_BTW2;
+            took_and = true;
+            break;
+          } else {  // E_BTW2: FnCall{Between | NotBetween, [left, x, y]}
+            sp--;
+            cur_start = top.y;
+            cur_kind = NUTDB_NK_FNCALL;
+            FAST_EMIT(NUTDB_NK_FNCALL, (top.x >> 7) & 63u, 0, cur_start);
           }
-          sp--;
-          cur_start = top.y;
-          cur_kind = NUTDB_NK_BINARY;
-          FAST_EMIT(NUTDB_NK_BINARY, bop, 0, cur_start);
+        }
+        if (took_and) {
+          t++;
+          st = FS_X_OPND;  // the upper bound
+          continue;
+        }
+        if (spec != SPEC_NONE) {
+          const uint32_t p1 = tok.pair_at(t + 1);  // (the current token is a word, so t + 1 is at most the EOF token)
+          const uint32_t kw1 = (p1 & 255u) == NUTDB_TT_KeywordOrIdentifier ? (p1 >> 8) : 0u;
+          if (spec == SPEC_IS) {  // IS [NOT] NULL (mod.rs:1430-1438): simplified_is_null folds literals
+            uint32_t sub = 2, used = 2;
+            if (kw1 == KW_NOT) {
+              const uint32_t p2 = tok.pair_at(t + 2);
+              if (!((p2 & 255u) == NUTDB_TT_KeywordOrIdentifier && (p2 >> 8) == KW_NULL)) return false;
+              sub = 3;
+              used = 3;
+            } else if (kw1 != KW_NULL) {
+              return false;
+            }
+            if (is_literal(cur_kind)) return false;
+            cur_kind = NUTDB_NK_UNARY;
+            FAST_EMIT(NUTDB_NK_UNARY, sub, 0, cur_start);
+            t += used;
+            continue;  // still after an operand
+          }
+          if (sp >= DEPTH) return false;
+          if (spec == SPEC_BETWEEN) {
+            stk[sp * stride] = FastStackEntry{E_BTW1 | (P_Between << 3) | (3u << 7), cur_start};
+            t += 1;
+          } else {  // NOT IN / LIKE / ILIKE / BETWEEN (mod.rs:1399-1427); NOT EXISTS goes to the automaton
+            if (kw1 == KW_BETWEEN) stk[sp * stride] = FastStackEntry{E_BTW1 | (P_Between << 3) | (4u << 7), cur_start};
+            else if (kw1 == KW_IN || kw1 == KW_LIKE || kw1 == KW_ILIKE)
+              stk[sp * stride] = FastStackEntry{E_OP | (P_Comparison << 3) | ((kw1 == KW_IN ? 19u : kw1 == KW_LIKE ? 15u : 17u) << 7) |
+                                                    (cur_kind << 13), cur_start};
+            else return false;
+            t += 2;
+          }
+          sp++;
+          st = FS_X_OPND;
+          continue;
         }
         if (power != P_Terminator) {
           if (sp >= DEPTH) return false;
-          stk[sp * stride] = FastStackEntry{E_OP | (power << 2) | (op << 6) | (cur_kind << 12), cur_start};
+          stk[sp * stride] = FastStackEntry{E_OP | (power << 3) | (op << 7) | (cur_kind << 13), cur_start};
           sp++;
           t++;
           st = FS_X_OPND;  // right operand
@@ -231,7 +298,7 @@ struct FastParser {
         }
         if (sp != 0) {  // inside brackets opened by this expression
           if (ty == NUTDB_TT_Comma) {
-            stk[(sp - 1) * stride].x += 1u << 20;
+            stk[(sp - 1) * stride].x += 1u << 21;
             t++;
             st = FS_X_OPND;  // next item
             continue;
@@ -239,11 +306,11 @@ struct FastParser {
           if (ty != NUTDB_TT_RParen) return false;
           const FastStackEntry br = stk[(--sp) * stride];
           t++;
-          if ((br.x & 3u) == E_CALL) {
+          if ((br.x & 7u) == E_CALL) {
             FAST_EMIT(NUTDB_NK_FNCALL, 7, 0, br.y);
             cur_start = br.y;
             cur_kind = NUTDB_NK_FNCALL;
-          } else if ((br.x >> 20) != 0u) {  // one item in parentheses is the item itself (mod.rs:1236-1242)
+          } else if ((br.x >> 21) != 0u) {  // one item in parentheses is the item itself (mod.rs:1236-1242)
             FAST_EMIT(NUTDB_NK_COLLECTION, 0, 0, br.y);
             cur_start = br.y;
             cur_kind = NUTDB_NK_COLLECTION;
@@ -342,6 +409,12 @@ struct FastParser {
         sp++;
         t++;
         st = FS_X_OPND;
+      } else if (act == FA_NOT) {  // prefix NOT applies to the next PREFIX expression only (mod.rs:1294-1296): `not a = b`
+        if (sp >= DEPTH) return false;  // is `(not a) = b` -- so the entry is completed by whatever token comes next
+        stk[sp * stride] = FastStackEntry{E_NOT | (15u << 3), 0u};
+        sp++;
+        t++;
+        st = FS_X_OPND;
       } else if (act == FA_NEG) {  // only a literal may follow a prefix minus here (mod.rs:1259-1269)
         const uint32_t p1 = tok.pair_at(t + 1);
         const uint32_t ty1 = p1 & 255u;
@@ -363,7 +436,7 @@ struct FastParser {
         const uint32_t ty1 = tok.pair_at(t + 1) & 255u;
         if (i == 26 || i == 30 || i == 31) {  // Array / Dictionary / Nullable (inner)
           if (ty1 != NUTDB_TT_LParen || sp >= DEPTH) return false;
-          stk[sp * stride] = FastStackEntry{E_DT | ((i == 26 ? 0u : (i == 30 ? 4u : 5u)) << 2), n};
+          stk[sp * stride] = FastStackEntry{E_DT | ((i == 26 ? 0u : (i == 30 ? 4u : 5u)) << 3), n};
           sp++;
           t += 2;  // the inner type follows (state FS_DT stays)
         } else {
@@ -388,7 +461,7 @@ struct FastParser {
       } else if (act == FA_DTEND) {  // the closing parentheses of compound types
         if (ty != NUTDB_TT_RParen) return false;
         const FastStackEntry d = stk[(--sp) * stride];
-        FAST_EMIT(NUTDB_NK_DT_COMPOUND, d.x >> 2, 0, d.y);
+        FAST_EMIT(NUTDB_NK_DT_COMPOUND, d.x >> 3, 0, d.y);
         t++;
         st = sp ? (uint32_t)FS_DT_END : (uint32_t)FS_COL_ATTRS;
       } else if (act == FA_ROWEND) {  // `)` of a VALUES row: must_parse_insert_rows (mod.rs:636-670)

@@ -135,7 +135,10 @@ inline uint16_t fast_opkw_entry(uint32_t kw) {
     case KW_IN: power = P_Comparison; op = 18; break;
     case KW_LIKE: power = P_Comparison; op = 14; break;
     case KW_ILIKE: power = P_Comparison; op = 16; break;
-    case KW_NOT: case KW_IS: case KW_BETWEEN: bail = 1; break;
+    // handled by the operator phase itself (FastParser::SPEC_*): NOT IN/LIKE/ILIKE/BETWEEN, IS [NOT] NULL, BETWEEN
+    case KW_NOT: power = P_Not; bail = 2; break;
+    case KW_IS: power = P_Comparison; bail = 3; break;
+    case KW_BETWEEN: power = P_Between; bail = 4; break;
     default: break;
   }
   return (uint16_t)(power | (op << 4) | (bail << 12));
@@ -233,7 +236,8 @@ inline void fast_tables_build(FastTables& F) {
     B.on(st, FC_TRUE, R().cur().leaf0(NUTDB_NK_LIT_BOOL, 1).adv().to(FS_X_OPER));
     B.on(st, FC_FALSE, R().cur().leaf0(NUTDB_NK_LIT_BOOL, 0).adv().to(FS_X_OPER));
     B.on(st, FC_NULL, R().cur().leaf0(NUTDB_NK_LIT_NULL, 0).adv().to(FS_X_OPER));
-    B.bail(st, {FC_NOT, FC_IF, FC_BADPFX});  // NOT / IF / INTERVAL / CASE expressions: the automaton
+    B.on(st, FC_NOT, R().act(FA_NOT));
+    B.bail(st, {FC_IF, FC_BADPFX});  // IF / INTERVAL / CASE expressions: the automaton
     B.ident(st, R().act(FA_IDENT));
     B.on(st, FC_MINUS, R().act(FA_NEG));
     B.on(st, FC_PLUS, R().adv().to(FS_X_OPND));  // prefix plus is dropped (mod.rs:1270)

@@ -159,6 +159,46 @@ def test_unicode_escape_edge_cases():
            "select 'é\\u{é}'".encode(), "select '\\é\\u{41}é'".encode()])
 
 
+PREDICATES = [b"select a from t where b is null and c is not null",
+              b"select a from t where a not in (1,2,3) or b not like 'x%' and c not ilike 'y'",
+              b"select a from t where a between 1 and 10 and b not between x + 1 and y * 2 or c",
+              b"select not a, not a = b, not (a and b), not not a from t where not a is null",
+              b"select a from t order by a is null desc, b between 1 and 2 limit 5",
+              b"insert into t values (not a, b is null, c between 1 and 2), (1 not in (2), not 2, d not like e)",
+              b"select a + b between c - d and e * f is not null from t",
+              b"select f(a is null, not b, c between 1 and 2), (a is null), (not a, b) from t group by a is null having not a",
+              b"select a from t where a between b and c and d between e and f or not g between h and i"]
+PREDICATES_AUTOMATON = [b"select a between 1 and 2 between 3 and 4, a is null is not null, 1 is null, null is null from t",
+                        b"select a from t where a between 1 or 2 and 3", b"select a from t where a between 1",
+                        b"select not true, not false, not 1, a and not true from t",
+                        b"select a not exists (1), a not between 1 and 2 and 3, a is nul, a is not 5, a not 5 from t",
+                        b"select a from t where x not in (select 1) and y between (1) and (2)",
+                        b"select a from t where a = 1 is null, b = not c, not a between 1 and 2, a between not 1 and 2",
+                        b"select not f(x), not (a, b), not a.b, not -1, not 'x', not a[1] from t"]
+
+
+def test_predicates_in_the_fast_path():
+    """IS [NOT] NULL, [NOT] IN / LIKE / ILIKE / BETWEEN and prefix NOT (mod.rs:1294-1296, :1399-1449): parsed by the
+    table-driven parser unless folding (simplify.rs) or an error is involved; same nodes as the automaton either way."""
+    E.fast_hits()
+    got = check(PREDICATES)
+    assert E.fast_hits() == len(PREDICATES) and (got.stmt["status"] == 0).all()
+    check(PREDICATES_AUTOMATON)
+    text, offs = P.make_batch(PREDICATES)
+    a = E.parse_batch(text, offs)
+    E.set_fast(False)
+    try:
+        b = E.parse_batch(text, offs)
+    finally:
+        E.set_fast(True)
+    assert np.array_equal(a.node, b.node) and np.array_equal(a.stmt, b.stmt)
+
+
+@pytest.mark.parametrize("seed", [71, 72, 73])
+def test_mutation_fuzz_predicates(seed):
+    check(fuzz.fuzz_statements(PREDICATES + PREDICATES_AUTOMATON, 4000, seed=seed, max_mut=3))
+
+
 def test_extra_seeds_unmutated():
     check(fuzz.EXTRA_SEEDS)
 

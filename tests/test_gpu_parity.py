@@ -269,3 +269,15 @@ def test_long_batch_uses_the_two_pass_scans(ctx):
     got = ctx.parse_batch(text, offs)
     bad = P.compare_with_oracle(got, text, offs)
     assert not bad, "\n".join(bad[:5])
+
+
+def test_predicates_and_hex_literals(ctx):
+    """Constructs added to the native paths late in round 1: IS [NOT] NULL, [NOT] IN/LIKE/ILIKE/BETWEEN, prefix NOT
+    (table-driven parser) and plain hex literals (mask lexer), unmutated and mutated."""
+    import test_emul_parity as T
+    hexs = [b"select 0x1F, 0X2a, 0x, 0x0 from t where a = 0xdeadBEEF limit 0x10",
+            b"select 0x1G, 0xzz, 00x1, 0x1.5, .0x1, 1.0x2, 0x1_2, x0x1, 0x1x", b"select a from t limit 0x, 0xFFFFFFFFFFFFFFFFF"]
+    seeds = T.PREDICATES + T.PREDICATES_AUTOMATON + hexs
+    check(ctx, seeds)
+    for seed in (81, 82):
+        check(ctx, fuzz.fuzz_statements(seeds, 20000, seed=seed, max_mut=3))
