@@ -238,6 +238,10 @@ struct WinCtx {
 NUTDB_HD void ctx_window(const Win& w, const Events& ev, uint32_t base, const Next& nx, uint8_t s_in, uint8_t prev_byte,
                          WinCtx& o) {
   uint32_t todo = ev.all, consumed = 0;
+  // A newline only matters to a line comment (a_next: every other state maps it to itself or to what it decays to
+  // anyway), and a line comment needs a "--" in this window or an open one on entry: otherwise the newline events
+  // that are not statement starts are skipped.
+  if (s_in != A_LC && ev.dd == 0) todo &= ~(w.nl & ~w.bnd);
   uint8_t s = s_in;
   // '' / "" split exactly at the window start: the closing quote was the previous window's last byte
   const uint8_t b0q = (w.sq & 1u) ? (uint8_t)'\'' : ((w.dq & 1u) ? (uint8_t)'"' : (uint8_t)0);
