@@ -37,7 +37,9 @@ using namespace nlex;
 #define LEX_TILE (LEX_THREADS * LEX_CHUNK)
 #define LEX_ROW (LEX_THREADS + 1)
 #define SCAN_THREADS 1024
-#define PARSE_THREADS 128
+#ifndef PARSE_THREADS
+#define PARSE_THREADS 1024  // statements per CTA of the automaton: a large CTA gives its shape sort more equal statements per warp
+#endif
 #ifndef FAST_THREADS
 #define FAST_THREADS 512
 #endif
