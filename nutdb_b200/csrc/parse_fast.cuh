@@ -3,7 +3,7 @@
 // The bytecode automaton in parse_core.cuh is exact for the whole grammar but pays an
 // interpreter's price (fetch/dispatch/stack per grammar step).  This file parses the COMMON shapes:
 //
-//   SELECT items [FROM name [AS a]] [WHERE e] [GROUP BY items] [HAVING e] [ORDER BY item [DESC],..]
+//   SELECT [DISTINCT] items [FROM name [AS a] {[INNER|LEFT|RIGHT|FULL ..] JOIN name [AS a] ON e | USING (names)}] [WHERE e] [GROUP BY items] [HAVING e] [ORDER BY item [DESC],..]
 //          [LIMIT n [, m | OFFSET m] [WITH TIES]]
 //   INSERT INTO name [(names)] VALUES (exprs) {, (exprs)}
 //   CREATE TABLE [IF NOT EXISTS] name (name type [DEFAULT e | COMMENT s].. ,..)
@@ -54,17 +54,19 @@ enum FastClass : uint8_t {
   FC_FROM, FC_WHERE, FC_GROUP, FC_BY, FC_HAVING, FC_ORDER, FC_LIMIT, FC_OFFSET, FC_WITH, FC_TIES, FC_AS, FC_DESC,
   FC_INTO, FC_VALUES, FC_TABLE, FC_EXISTS, FC_DEFAULT, FC_COMMENT, FC_PRIMARY, FC_KEY, FC_PARTITION, FC_DISTINCT,
   FC_SETOP, FC_JOIN, FC_INDEXCON, FC_SELECT, FC_DTYPE,
+  FC_ON, FC_USING, FC_INNER, FC_FULL, FC_LEFT, FC_RIGHT, FC_OUTER, FC_KSEMI, FC_KANTI,
   FC_COUNT
 };
 static const uint32_t FC_FIRST_WORD = FC_WORD;
 
 // where the expression being parsed sits in its statement; the state after an expression is FS_AFTER + context
 enum FastCtx : uint8_t { C_SEL_ITEM = 0, C_WHERE, C_GROUP_ITEM, C_HAVING, C_ORDER_ITEM, C_INS_VALUE, C_COL_DEFAULT,
-                         C_TBL_PK_ITEM, C_TBL_ORDER_ITEM, C_TBL_PART, C_COUNT };
+                         C_TBL_PK_ITEM, C_TBL_ORDER_ITEM, C_TBL_PART, C_JOIN_ON, C_COUNT };
 
 enum FastState : uint8_t {
   FS_X_OPND = 0, FS_X_OPER, FS_AFTER, FS_AFTER_END = FS_AFTER + C_COUNT - 1,
-  FS_SEL0, FS_SEL_ALIAS, FS_SEL_ITEM2, FS_FROM, FS_SRC, FS_SRC2, FS_SRC_ALIAS, FS_SRC3,
+  FS_SEL0, FS_SEL_D, FS_SEL_ALIAS, FS_SEL_ITEM2, FS_FROM, FS_SRC, FS_SRC2, FS_SRC_ALIAS, FS_SRC3,
+  FS_J_KW, FS_J_OUTER, FS_J_LEFT, FS_J_RIGHT, FS_J_SRC, FS_J_SRC2, FS_J_ALIAS, FS_J_ONUSING, FS_J_U_LP, FS_J_U_ID, FS_J_U_SEP,
   FS_CL1, FS_CL2, FS_CL3, FS_CL4, FS_CL5, FS_GROUP_BY, FS_ORDER_BY, FS_GRP_ALIAS, FS_GRP_ITEM2,
   FS_ORD_ALIAS, FS_ORD_ITEM2, FS_ORD_ITEM3,
   FS_LIM1, FS_LIM2, FS_LIM3A, FS_LIM4A, FS_LIM3B, FS_LIM4B, FS_TIES0, FS_TIES1, FS_TIES2, FS_BODY, FS_END_SEL,
@@ -79,13 +81,14 @@ enum FastState : uint8_t {
 enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT };
 
 // ---- transition record: two words ----
-// lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28]
+// lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28] subreg[29]
 // hi: pre[0:2) post[2:4) setcur[4] check[5:8) look[8:10) setctx[10] ctx[11:15) bit[15:23) clr[23] inccnt[24] setaux[25]
+//     setjr[26] jr[27:30)   (jr = the join type, kept in a register until the JOIN node is emitted: subreg)
 enum : uint32_t { FE_NONE = 0, FE_LEAF_TOK, FE_LEAF_NOTOK, FE_NODE_M0, FE_NODE_M1, FE_NODE_ZERO };
 enum : uint32_t { FK_NONE = 0, FK_INT_W0, FK_INT_W1, FK_INT_W2, FK_STR };
 enum : uint32_t { FL_NONE = 0, FL_NODOT, FL_NODOT_NOLP };
-static const uint32_t FAST_MAX_REC = 128;
-static const uint32_t FAST_HI_UNCOMMON = 0x03FFFFE0u;  // every hi field except pre / post / setcur
+static const uint32_t FAST_MAX_REC = 160;
+static const uint32_t FAST_HI_UNCOMMON = 0x3FFFFFE0u;  // every hi field except pre / post / setcur
 
 // Token-indexed tables take ONE index for both kinds of token: the token type, or 64 + keyword id for a word.
 struct FastTables {
@@ -187,7 +190,7 @@ struct FastParser {
     uint32_t t = 1, n = 0, sp = 0;
     uint32_t cur_start = 0, cur_kind = 0;  // the operand just completed (right-most subtree)
     uint32_t m0 = 0, m1 = 0;               // open interior nodes: outer (ROWS / COLDEF) and inner (clause / ROW / attribute)
-    uint32_t ctx = C_SEL_ITEM, seen = 0, cnt = 0, width = 0, auxr = 0;
+    uint32_t ctx = C_SEL_ITEM, seen = 0, cnt = 0, width = 0, auxr = 0, jreg = 0;
 #define FAST_EMIT(kind_, sub_, aux_, x_)          \
   do {                                            \
     if (n < cap) {                                \
@@ -345,6 +348,7 @@ struct FastParser {
           if (hi & (1u << 24)) cnt++;
           if (hi & (1u << 25)) auxr = 1;
           if (hi & (1u << 10)) ctx = (hi >> 11) & 15u;
+          if (hi & (1u << 26)) jreg = (hi >> 27) & 7u;
         }
         if (hi & 1u) m0 = n;
         if (hi & 2u) m1 = n;
@@ -356,7 +360,7 @@ struct FastParser {
         if (em != FE_NONE) {
           const uint32_t x = em == FE_LEAF_TOK ? t : em == FE_LEAF_NOTOK ? NUTDB_CN_NOTOK : em == FE_NODE_M0 ? m0
                              : em == FE_NODE_M1 ? m1 : 0u;
-          if (n < cap) nd.set_raw(n, F->rec_hdr[ri] | (((lo >> 28) & auxr) << 16), x);
+          if (n < cap) nd.set_raw(n, F->rec_hdr[ri] | (((lo >> 28) & auxr) << 16) | ((lo & (1u << 29)) ? jreg << 8 : 0u), x);
           n++;
         }
         t += (lo >> 11) & 1u;

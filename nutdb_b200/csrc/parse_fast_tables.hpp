@@ -41,6 +41,8 @@ struct FastRec {
   FastRec& clr() { hi |= 1u << 23; return *this; }
   FastRec& inc() { hi |= 1u << 24; return *this; }
   FastRec& setaux() { hi |= 1u << 25; return *this; }
+  FastRec& setjr(uint32_t v) { hi |= (1u << 26) | (v << 27); return *this; }
+  FastRec& subreg() { lo |= 1u << 29; return *this; }
 };
 
 class FastTableBuilder {
@@ -202,7 +204,16 @@ inline uint8_t fast_keyword_class(uint32_t kw) {
     case KW_PARTITION: return FC_PARTITION;
     case KW_DISTINCT: return FC_DISTINCT;
     case KW_UNION: case KW_INTERSECT: case KW_EXCEPT: return FC_SETOP;
-    case KW_INNER: case KW_FULL: case KW_LEFT: case KW_RIGHT: case KW_JOIN: return FC_JOIN;
+    case KW_JOIN: return FC_JOIN;
+    case KW_INNER: return FC_INNER;
+    case KW_FULL: return FC_FULL;
+    case KW_LEFT: return FC_LEFT;
+    case KW_RIGHT: return FC_RIGHT;
+    case KW_OUTER: return FC_OUTER;
+    case KW_SEMI: return FC_KSEMI;
+    case KW_ANTI: return FC_KANTI;
+    case KW_ON: return FC_ON;
+    case KW_USING: return FC_USING;
     case KW_INDEX: case KW_CONSTRAINT: return FC_INDEXCON;
     case KW_SELECT: return FC_SELECT;
     default: return FC_WORD;  // an identifier, or a keyword that plays no part in this subset
@@ -224,8 +235,11 @@ inline void fast_tables_build(FastTables& F) {
   const FastRec skip_to_operand = R().adv().to(FS_X_OPND);
 
   // ---- operand position: must_parse_expr_prefix (mod.rs:1222-1347) ----
-  for (uint32_t st : {(uint32_t)FS_X_OPND, (uint32_t)FS_SEL0}) {
-    if (st == FS_SEL0) B.bail(st, {FC_DISTINCT});  // must_parse_query_clause_distinct: the automaton
+  // SELECT [DISTINCT]: must_parse_query_clause_distinct (mod.rs:349-360); DISTINCT ON (..) goes to the automaton.
+  // The DISTINCT node has no children (its own index is its subtree start); the select list's node starts after it.
+  B.on(FS_SEL0, FC_DISTINCT, R().pre_m1().node_m1(NUTDB_NK_DISTINCT).adv().post_m0().to(FS_SEL_D));
+  B.bail(FS_SEL_D, {FC_ON});
+  for (uint32_t st : {(uint32_t)FS_X_OPND, (uint32_t)FS_SEL0, (uint32_t)FS_SEL_D}) {
     B.on(st, FC_INT, R().cur().check(FK_INT_W2).leaf(NUTDB_NK_LIT_INT).adv().to(FS_X_OPER));
     B.on(st, FC_HEX, R().cur().check(FK_INT_W2).leaf(NUTDB_NK_LIT_INT, 0, 1).adv().to(FS_X_OPER));
     B.on(st, FC_FLOAT, R().cur().leaf(NUTDB_NK_LIT_FLOAT).adv().to(FS_X_OPER));
@@ -247,7 +261,7 @@ inline void fast_tables_build(FastTables& F) {
 
   // ---- SELECT list (mod.rs:279-330), aliases (:563-578) ----
   const FastRec alias = R().leaf(NUTDB_NK_ALIAS).adv();
-  const FastRec cols = R().node0(NUTDB_NK_COLS).to(FS_FROM);
+  const FastRec cols = R().node_m0(NUTDB_NK_COLS).to(FS_FROM);
   B.on(FS_AFTER + C_SEL_ITEM, FC_AS, R().adv().to(FS_SEL_ALIAS));
   B.ident(FS_SEL_ALIAS, FastRec(alias).to(FS_SEL_ITEM2));
   for (uint32_t st : {(uint32_t)(FS_AFTER + C_SEL_ITEM), (uint32_t)FS_SEL_ITEM2}) {
@@ -276,7 +290,36 @@ inline void fast_tables_build(FastTables& F) {
   B.otherwise(FS_SRC2, R().node_m1(NUTDB_NK_FROM).to(FS_CL1));
   B.ident(FS_SRC_ALIAS, FastRec(alias).to(FS_SRC3));
   B.otherwise(FS_SRC3, R().node_m1(NUTDB_NK_FROM).to(FS_CL1));
-  B.bail(FS_CL1, {FC_JOIN});
+  // joins (try_parse_query_clause_join, mod.rs:376-431): [INNER | FULL [OUTER] | LEFT|RIGHT [SEMI|ANTI|OUTER]] JOIN
+  // source (ON expr | USING (identifiers)); the join type waits in a register for the JOIN node
+  const uint32_t JOINS = FS_CL1;
+  B.on(JOINS, FC_INNER, R().adv().setjr(0).to(FS_J_KW));
+  B.on(JOINS, FC_FULL, R().adv().setjr(1).to(FS_J_OUTER));
+  B.on(JOINS, FC_LEFT, R().adv().setjr(2).to(FS_J_LEFT));
+  B.on(JOINS, FC_RIGHT, R().adv().setjr(3).to(FS_J_RIGHT));
+  B.on(JOINS, FC_JOIN, R().adv().setjr(0).post_m1().to(FS_J_SRC));
+  B.on(FS_J_LEFT, FC_KSEMI, R().adv().setjr(4).to(FS_J_KW));
+  B.on(FS_J_LEFT, FC_KANTI, R().adv().setjr(6).to(FS_J_KW));
+  B.on(FS_J_RIGHT, FC_KSEMI, R().adv().setjr(5).to(FS_J_KW));
+  B.on(FS_J_RIGHT, FC_KANTI, R().adv().setjr(7).to(FS_J_KW));
+  for (uint32_t st : {(uint32_t)FS_J_LEFT, (uint32_t)FS_J_RIGHT, (uint32_t)FS_J_OUTER}) B.on(st, FC_OUTER, R().adv().to(FS_J_KW));
+  for (uint32_t st : {(uint32_t)FS_J_LEFT, (uint32_t)FS_J_RIGHT, (uint32_t)FS_J_OUTER, (uint32_t)FS_J_KW})
+    B.on(st, FC_JOIN, R().adv().post_m1().to(FS_J_SRC));
+  B.bail(FS_J_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX});
+  B.words(FS_J_SRC, R().look(FL_NODOT_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
+  B.on(FS_J_SRC, FC_DELIM, R().look(FL_NODOT).leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
+  B.on(FS_J_SRC2, FC_AS, R().adv().to(FS_J_ALIAS));
+  B.ident(FS_J_ALIAS, FastRec(alias).to(FS_J_ONUSING));
+  for (uint32_t st : {(uint32_t)FS_J_SRC2, (uint32_t)FS_J_ONUSING}) {
+    B.on(st, FC_ON, R().adv().ctx(C_JOIN_ON).to(FS_X_OPND));
+    B.on(st, FC_USING, R().adv().to(FS_J_U_LP));
+  }
+  B.otherwise(FS_AFTER + C_JOIN_ON, R().node_m1(NUTDB_NK_JOIN).subreg().to(JOINS));
+  B.on(FS_J_U_LP, FC_LPAREN, R().adv().to(FS_J_U_ID));
+  B.ident(FS_J_U_ID, R().look(FL_NODOT).leaf(NUTDB_NK_IDENT).adv().to(FS_J_U_SEP));  // must_parse_identifier (mod.rs:1525)
+  B.on(FS_J_U_ID, FC_MUL, R().leaf(NUTDB_NK_IDENT, 1).adv().to(FS_J_U_SEP));
+  B.on(FS_J_U_SEP, FC_COMMA, R().adv().to(FS_J_U_ID));
+  B.on(FS_J_U_SEP, FC_RPAREN, R().node_m1(NUTDB_NK_JOIN, 0, 1).subreg().adv().to(JOINS));
   clauses(FS_CL1, 1);
   clauses(FS_CL2, 2);
   clauses(FS_CL3, 3);

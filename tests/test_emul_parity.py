@@ -177,6 +177,43 @@ PREDICATES_AUTOMATON = [b"select a between 1 and 2 between 3 and 4, a is null is
                         b"select not f(x), not (a, b), not a.b, not -1, not 'x', not a[1] from t"]
 
 
+JOINS = [b"select distinct a, b from t where c = 1", b"select distinct * from t order by a desc limit 3",
+         b"select a from t join u on t.x = u.x where a > 1",
+         b"select a from t as x inner join u as y on x.i = y.i left join v using (i, j) right outer join w on a = 2",
+         b"select a from t full outer join u using (*) left semi join v on a left anti join w on b right semi join x on c "
+         b"right anti join y on d full join z on e",
+         b"select a from t left outer join `u v` as q on q.a = t.a and q.b is not null group by a order by a limit 1",
+         b"select a from t join u on a join v on b where c", b"select a from t join u as true on x"]
+JOINS_AUTOMATON = [b"select distinct on (a) a, b from t", b"select a from t join u", b"select a from t join u on",
+                   b"select a from t left u on x", b"select a from t join u.v on x", b"select a from t join f(x) on y",
+                   b"select a from t join (select 1) as s on y", b"select a from t join u using (a.b)",
+                   b"select a from t join u using ()", b"select a from t join u using (a,)", b"select a join u on x",
+                   b"select distinct", b"select a from t join u on x = y, z", b"select a from t inner outer join u on x",
+                   b"select a from t left semi outer join u on x", b"select a from t join u on x using (y)",
+                   b"select a from t join u on 1 = 2"]
+
+
+def test_distinct_and_joins_in_the_fast_path():
+    """SELECT DISTINCT and the join clause (mod.rs:349-360, :376-431) as rows of the table-driven parser."""
+    E.fast_hits()
+    got = check(JOINS)
+    assert E.fast_hits() == len(JOINS) and (got.stmt["status"] == 0).all()
+    check(JOINS_AUTOMATON)
+    text, offs = P.make_batch(JOINS)
+    a = E.parse_batch(text, offs)
+    E.set_fast(False)
+    try:
+        b = E.parse_batch(text, offs)
+    finally:
+        E.set_fast(True)
+    assert np.array_equal(a.node, b.node) and np.array_equal(a.stmt, b.stmt)
+
+
+@pytest.mark.parametrize("seed", [74, 75])
+def test_mutation_fuzz_joins(seed):
+    check(fuzz.fuzz_statements(JOINS + JOINS_AUTOMATON, 4000, seed=seed, max_mut=3))
+
+
 def test_predicates_in_the_fast_path():
     """IS [NOT] NULL, [NOT] IN / LIKE / ILIKE / BETWEEN and prefix NOT (mod.rs:1294-1296, :1399-1449): parsed by the
     table-driven parser unless folding (simplify.rs) or an error is involved; same nodes as the automaton either way."""
