@@ -10,7 +10,7 @@
 //          [PRIMARY KEY es | ORDER BY es | PARTITION BY e | COMMENT s]..
 //
 // with expressions over identifiers, literals, the binary operators, AND/OR/XOR, [NOT] IN/LIKE/ILIKE,
-// [NOT] BETWEEN .. AND .., IS [NOT] NULL, prefix NOT, parenthesised groups / tuples and function calls
+// [NOT] BETWEEN .. AND .., IS [NOT] NULL, prefix NOT, CASE .. END, parenthesised groups / tuples and function calls
 // (operator-precedence parsing with an explicit
 // operator stack -- the iterative form of must_parse_expr_tdop, reference mod.rs:1209-1220: an
 // operator is reduced when one of equal or lower power arrives, so every operator is
@@ -29,7 +29,7 @@
 //
 // It is ALL-OR-NOTHING: on anything outside that subset -- any error, any construct that needs
 // constant folding (simplify.rs), literal validation beyond a length check, joins, set
-// operations, subqueries, CASE/IF/INTERVAL, NOT EXISTS, arrays, maps ... -- try_parse() returns false
+// operations, subqueries, IF/INTERVAL, NOT EXISTS, arrays, maps ... -- try_parse() returns false
 // without side effects the caller keeps, and the statement is parsed from scratch by the exact
 // automaton.  For a statement it accepts, it emits precisely the nodes the automaton would.
 #pragma once
@@ -54,7 +54,7 @@ enum FastClass : uint8_t {
   FC_FROM, FC_WHERE, FC_GROUP, FC_BY, FC_HAVING, FC_ORDER, FC_LIMIT, FC_OFFSET, FC_WITH, FC_TIES, FC_AS, FC_DESC,
   FC_INTO, FC_VALUES, FC_TABLE, FC_EXISTS, FC_DEFAULT, FC_COMMENT, FC_PRIMARY, FC_KEY, FC_PARTITION, FC_DISTINCT,
   FC_SETOP, FC_JOIN, FC_INDEXCON, FC_SELECT, FC_DTYPE,
-  FC_ON, FC_USING, FC_INNER, FC_FULL, FC_LEFT, FC_RIGHT, FC_OUTER, FC_KSEMI, FC_KANTI,
+  FC_ON, FC_USING, FC_INNER, FC_FULL, FC_LEFT, FC_RIGHT, FC_OUTER, FC_KSEMI, FC_KANTI, FC_CASE,
   FC_COUNT
 };
 static const uint32_t FC_FIRST_WORD = FC_WORD;
@@ -78,7 +78,7 @@ enum FastState : uint8_t {
   FS_COUNT
 };
 
-enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT };
+enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT, FA_CASE };
 
 // ---- transition record: two words ----
 // lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28] subreg[29]
@@ -113,7 +113,9 @@ struct FastParser {
   // The power of an entry is the min_power its right operand is parsed with (must_parse_expr_tdop, mod.rs:1209):
   // an arriving operator of equal or lower power completes it.  E_NOT = prefix NOT, E_BTW1 / E_BTW2 = [NOT] BETWEEN
   // before / after its AND (op = FnName Between 3 / NotBetween 4).
-  enum : uint32_t { E_OP = 0, E_PAREN = 1, E_CALL = 2, E_DT = 3, E_NOT = 4, E_BTW1 = 5, E_BTW2 = 6 };
+  // E_CASE = CASE [scrutinee] WHEN .. THEN .. [ELSE ..] END: x = type | position << 7 | FnName << 9 (position: 0 after
+  // the scrutinee, 1 after a condition, 2 after a result, 3 after the ELSE expression)
+  enum : uint32_t { E_OP = 0, E_PAREN = 1, E_CALL = 2, E_DT = 3, E_NOT = 4, E_BTW1 = 5, E_BTW2 = 6, E_CASE = 7 };
   enum : uint32_t { SPEC_NONE = 0, SPEC_BAIL = 1, SPEC_NOT = 2, SPEC_IS = 3, SPEC_BETWEEN = 4 };  // FastTables::op >> 12
   static const uint32_t DEPTH = FAST_STACK_DEPTH;
 
@@ -232,7 +234,7 @@ struct FastParser {
             cur_start = top.y;
             cur_kind = NUTDB_NK_BINARY;
             FAST_EMIT(NUTDB_NK_BINARY, bop, 0, cur_start);
-          } else if (type - 1u < 3u) {  // E_PAREN / E_CALL / E_DT: the terminator belongs to the bracket
+          } else if (type - 1u < 3u || type == E_CASE) {  // E_PAREN / E_CALL / E_DT / E_CASE: the terminator belongs to the bracket
             break;
           } else if (type == E_NOT) {  // simplified_not (simplify.rs): a boolean literal would be flipped
             if (cur_kind == NUTDB_NK_LIT_BOOL) return false;
@@ -300,6 +302,29 @@ struct FastParser {
           continue;
         }
         if (sp != 0) {  // inside brackets opened by this expression
+          const FastStackEntry br0 = stk[(sp - 1) * stride];
+          if ((br0.x & 7u) == E_CASE) {  // must_parse_case_when_body (mod.rs:1585-1618)
+            const uint32_t at = (br0.x >> 7) & 3u, k = ty == NUTDB_TT_KeywordOrIdentifier ? kw : 0u;
+            uint32_t next;
+            if ((at == 0 || at == 2) && k == KW_WHEN) next = 1;
+            else if (at == 1 && k == KW_THEN) next = 2;
+            else if (at == 2 && k == KW_ELSE) next = 3;
+            else if (at >= 2 && k == KW_END) {  // without ELSE the default is NULL
+              if (at == 2) FAST_EMIT(NUTDB_NK_LIT_NULL, 0, 0, NUTDB_CN_NOTOK);
+              sp--;
+              t++;
+              cur_start = br0.y;
+              cur_kind = NUTDB_NK_FNCALL;
+              FAST_EMIT(NUTDB_NK_FNCALL, (br0.x >> 9) & 7u, 0, br0.y);
+              continue;
+            } else {
+              return false;
+            }
+            stk[(sp - 1) * stride].x = (br0.x & ~(3u << 7)) | (next << 7);
+            t++;
+            st = FS_X_OPND;
+            continue;
+          }
           if (ty == NUTDB_TT_Comma) {
             stk[(sp - 1) * stride].x += 1u << 21;
             t++;
@@ -412,6 +437,14 @@ struct FastParser {
         stk[sp * stride] = FastStackEntry{E_PAREN, n};
         sp++;
         t++;
+        st = FS_X_OPND;
+      } else if (act == FA_CASE) {  // CASE WHEN .. = FnName::MultiIf (1), CASE scrutinee WHEN .. = FnName::CaseWhen (2)
+        if (sp >= DEPTH) return false;
+        const uint32_t p1 = tok.pair_at(t + 1);
+        const bool multi = (p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && (p1 >> 8) == KW_WHEN;
+        stk[sp * stride] = FastStackEntry{E_CASE | ((multi ? 1u : 0u) << 7) | ((multi ? 1u : 2u) << 9), n};
+        sp++;
+        t += multi ? 2u : 1u;
         st = FS_X_OPND;
       } else if (act == FA_NOT) {  // prefix NOT applies to the next PREFIX expression only (mod.rs:1294-1296): `not a = b`
         if (sp >= DEPTH) return false;  // is `(not a) = b` -- so the entry is completed by whatever token comes next

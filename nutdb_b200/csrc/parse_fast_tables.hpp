@@ -178,7 +178,8 @@ inline uint8_t fast_keyword_class(uint32_t kw) {
     case KW_NULL: return FC_NULL;
     case KW_NOT: return FC_NOT;
     case KW_IF: return FC_IF;
-    case KW_INTERVAL: case KW_CASE: return FC_BADPFX;
+    case KW_INTERVAL: return FC_BADPFX;
+    case KW_CASE: return FC_CASE;
     case KW_AND: case KW_OR: case KW_XOR: case KW_IN: case KW_LIKE: case KW_ILIKE: return FC_KWBINOP;
     case KW_IS: case KW_BETWEEN: return FC_ISBETWEEN;
     case KW_FROM: return FC_FROM;
@@ -251,6 +252,7 @@ inline void fast_tables_build(FastTables& F) {
     B.on(st, FC_FALSE, R().cur().leaf0(NUTDB_NK_LIT_BOOL, 0).adv().to(FS_X_OPER));
     B.on(st, FC_NULL, R().cur().leaf0(NUTDB_NK_LIT_NULL, 0).adv().to(FS_X_OPER));
     B.on(st, FC_NOT, R().act(FA_NOT));
+    B.on(st, FC_CASE, R().act(FA_CASE));
     B.bail(st, {FC_IF, FC_BADPFX});  // IF / INTERVAL / CASE expressions: the automaton
     B.ident(st, R().act(FA_IDENT));
     B.on(st, FC_MINUS, R().act(FA_NEG));
@@ -281,7 +283,7 @@ inline void fast_tables_build(FastTables& F) {
   B.on(FS_FROM, FC_FROM, R().adv().post_m1().to(FS_SRC));
   B.bail(FS_FROM, {FC_JOIN});
   clauses(FS_FROM, 1);
-  B.bail(FS_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX});
+  B.bail(FS_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_CASE});
   B.words(FS_SRC, R().look(FL_NODOT_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));  // no table function, no qualifier
   B.on(FS_SRC, FC_DELIM, R().look(FL_NODOT).leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));
   // the source is an expression: anything with infix power continues it (mod.rs:1212-1216)
@@ -305,7 +307,7 @@ inline void fast_tables_build(FastTables& F) {
   for (uint32_t st : {(uint32_t)FS_J_LEFT, (uint32_t)FS_J_RIGHT, (uint32_t)FS_J_OUTER}) B.on(st, FC_OUTER, R().adv().to(FS_J_KW));
   for (uint32_t st : {(uint32_t)FS_J_LEFT, (uint32_t)FS_J_RIGHT, (uint32_t)FS_J_OUTER, (uint32_t)FS_J_KW})
     B.on(st, FC_JOIN, R().adv().post_m1().to(FS_J_SRC));
-  B.bail(FS_J_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX});
+  B.bail(FS_J_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_CASE});
   B.words(FS_J_SRC, R().look(FL_NODOT_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
   B.on(FS_J_SRC, FC_DELIM, R().look(FL_NODOT).leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
   B.on(FS_J_SRC2, FC_AS, R().adv().to(FS_J_ALIAS));

@@ -193,6 +193,42 @@ JOINS_AUTOMATON = [b"select distinct on (a) a, b from t", b"select a from t join
                    b"select a from t join u on 1 = 2"]
 
 
+CASES = [b"select case when a > 1 then 'x' when a < 0 then 'y' else 'z' end from t",
+         b"select case a when 1 then 'one' when 2 then 'two' end as w, b from t",
+         b"select sum(case when a = b then 1 else 0 end), case x when y then case when p then q end else r end from t "
+         b"where case when a then b end is not null",
+         b"select a from t order by case when a then 1 else 2 end desc limit 1",
+         b"insert into t values (case when a then 1 end, case b when 1 then 2 else 3 end)",
+         b"select case when a then (b, c) when f(x) then g(case when y then z end) end from t",
+         b"select case when a between 1 and 2 then b not in (1, 2) else not c end from t",
+         b"select case case when a then b end when c then d end from t"]
+CASES_AUTOMATON = [b"select case when a then b", b"select case a when b", b"select case end", b"select case when a then b else c",
+                   b"select case when a then b else c else d end", b"select case a then b end", b"select case when 1 = 1 then 2 end",
+                   b"select case when a then b end + 1, -case when a then b end from t", b"select case from t",
+                   b"select case when a then b end end", b"select case when when then end"]
+
+
+def test_case_expressions_in_the_fast_path():
+    """CASE [x] WHEN .. THEN .. [ELSE ..] END (must_parse_case_when_body, mod.rs:1585-1618) on the operator stack."""
+    E.fast_hits()
+    got = check(CASES)
+    assert E.fast_hits() == len(CASES) and (got.stmt["status"] == 0).all()
+    check(CASES_AUTOMATON)
+    text, offs = P.make_batch(CASES)
+    a = E.parse_batch(text, offs)
+    E.set_fast(False)
+    try:
+        b = E.parse_batch(text, offs)
+    finally:
+        E.set_fast(True)
+    assert np.array_equal(a.node, b.node) and np.array_equal(a.stmt, b.stmt)
+
+
+@pytest.mark.parametrize("seed", [76, 77])
+def test_mutation_fuzz_case_expressions(seed):
+    check(fuzz.fuzz_statements(CASES + CASES_AUTOMATON, 4000, seed=seed, max_mut=3))
+
+
 def test_distinct_and_joins_in_the_fast_path():
     """SELECT DISTINCT and the join clause (mod.rs:349-360, :376-431) as rows of the table-driven parser."""
     E.fast_hits()
