@@ -48,8 +48,8 @@ struct FastStackEntry {
 // ---- token classes: everything the grammar states distinguish ----
 enum FastClass : uint8_t {
   FC_OTHER = 0, FC_EOF, FC_SEMI, FC_COMMA, FC_LPAREN, FC_RPAREN, FC_MUL, FC_PLUS, FC_MINUS, FC_BINOP, FC_LBRACKET,
-  FC_INT, FC_HEX, FC_FLOAT, FC_RAWSTR, FC_ESQ, FC_EDQ, FC_DELIM,
-  // words (token type KeywordOrIdentifier), by keyword id
+  FC_INT, FC_HEX, FC_FLOAT, FC_RAWSTR, FC_ESQ, FC_EDQ, FC_DELIM, FC_DOT,
+  // words (token type KeywordOrIdentifier), by keyword id: every class from FC_WORD on is a word class
   FC_WORD, FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_KWBINOP, FC_ISBETWEEN,
   FC_FROM, FC_WHERE, FC_GROUP, FC_BY, FC_HAVING, FC_ORDER, FC_LIMIT, FC_OFFSET, FC_WITH, FC_TIES, FC_AS, FC_DESC,
   FC_INTO, FC_VALUES, FC_TABLE, FC_EXISTS, FC_DEFAULT, FC_COMMENT, FC_PRIMARY, FC_KEY, FC_PARTITION, FC_DISTINCT,
@@ -65,8 +65,8 @@ enum FastCtx : uint8_t { C_SEL_ITEM = 0, C_WHERE, C_GROUP_ITEM, C_HAVING, C_ORDE
 
 enum FastState : uint8_t {
   FS_X_OPND = 0, FS_X_OPER, FS_AFTER, FS_AFTER_END = FS_AFTER + C_COUNT - 1,
-  FS_SEL0, FS_SEL_D, FS_SEL_ALIAS, FS_SEL_ITEM2, FS_FROM, FS_SRC, FS_SRC2, FS_SRC_ALIAS, FS_SRC3,
-  FS_J_KW, FS_J_OUTER, FS_J_LEFT, FS_J_RIGHT, FS_J_SRC, FS_J_SRC2, FS_J_ALIAS, FS_J_ONUSING, FS_J_U_LP, FS_J_U_ID, FS_J_U_SEP,
+  FS_SEL0, FS_SEL_D, FS_SEL_ALIAS, FS_SEL_ITEM2, FS_FROM, FS_SRC, FS_SRC2, FS_SRC_Q, FS_SRC2B, FS_SRC_ALIAS, FS_SRC3,
+  FS_J_KW, FS_J_OUTER, FS_J_LEFT, FS_J_RIGHT, FS_J_SRC, FS_J_SRC2, FS_J_SRC_Q, FS_J_SRC2B, FS_J_ALIAS, FS_J_ONUSING, FS_J_U_LP, FS_J_U_ID, FS_J_U_SEP,
   FS_CL1, FS_CL2, FS_CL3, FS_CL4, FS_CL5, FS_GROUP_BY, FS_ORDER_BY, FS_GRP_ALIAS, FS_GRP_ITEM2,
   FS_ORD_ALIAS, FS_ORD_ITEM2, FS_ORD_ITEM3,
   FS_LIM1, FS_LIM2, FS_LIM3A, FS_LIM4A, FS_LIM3B, FS_LIM4B, FS_TIES0, FS_TIES1, FS_TIES2, FS_BODY, FS_END_SEL,
@@ -84,11 +84,12 @@ enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DT
 // lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28] subreg[29]
 // hi: pre[0:2) post[2:4) setcur[4] check[5:8) look[8:10) setctx[10] ctx[11:15) bit[15:23) clr[23] inccnt[24] setaux[25]
 //     setjr[26] jr[27:30)   (jr = the join type, kept in a register until the JOIN node is emitted: subreg)
+//     popnode[30]           (the node emitted last is withdrawn: the qualifier of `db.table`)
 enum : uint32_t { FE_NONE = 0, FE_LEAF_TOK, FE_LEAF_NOTOK, FE_NODE_M0, FE_NODE_M1, FE_NODE_ZERO };
 enum : uint32_t { FK_NONE = 0, FK_INT_W0, FK_INT_W1, FK_INT_W2, FK_STR };
-enum : uint32_t { FL_NONE = 0, FL_NODOT, FL_NODOT_NOLP };
+enum : uint32_t { FL_NONE = 0, FL_NODOT, FL_NODOT_NOLP, FL_NOLP };
 static const uint32_t FAST_MAX_REC = 160;
-static const uint32_t FAST_HI_UNCOMMON = 0x3FFFFFE0u;  // every hi field except pre / post / setcur
+static const uint32_t FAST_HI_UNCOMMON = 0x7FFFFFE0u;  // every hi field except pre / post / setcur
 
 // Token-indexed tables take ONE index for both kinds of token: the token type, or 64 + keyword id for a word.
 struct FastTables {
@@ -358,7 +359,7 @@ struct FastParser {
           const uint32_t look = (hi >> 8) & 3u;
           if (look) {  // (the current token is not EOF here, so t + 1 exists)
             const uint32_t ty1 = tok.pair_at(t + 1) & 255u;
-            if (ty1 == NUTDB_TT_Dot || (look == FL_NODOT_NOLP && ty1 == NUTDB_TT_LParen)) return false;
+            if ((look != FL_NOLP && ty1 == NUTDB_TT_Dot) || (look >= FL_NODOT_NOLP && ty1 == NUTDB_TT_LParen)) return false;
           }
           const uint32_t check = (hi >> 5) & 7u;
           if (check == FK_STR) {
@@ -374,6 +375,7 @@ struct FastParser {
           if (hi & (1u << 25)) auxr = 1;
           if (hi & (1u << 10)) ctx = (hi >> 11) & 15u;
           if (hi & (1u << 26)) jreg = (hi >> 27) & 7u;
+          if (hi & (1u << 30)) n--;
         }
         if (hi & 1u) m0 = n;
         if (hi & 2u) m1 = n;

@@ -43,6 +43,7 @@ struct FastRec {
   FastRec& setaux() { hi |= 1u << 25; return *this; }
   FastRec& setjr(uint32_t v) { hi |= (1u << 26) | (v << 27); return *this; }
   FastRec& subreg() { lo |= 1u << 29; return *this; }
+  FastRec& popnode() { hi |= 1u << 30; return *this; }
 };
 
 class FastTableBuilder {
@@ -167,6 +168,7 @@ inline uint8_t fast_type_class(uint32_t ty) {
     case NUTDB_TT_EscapedSQStringLiteral: return FC_ESQ;
     case NUTDB_TT_EscapedDQStringLiteral: return FC_EDQ;
     case NUTDB_TT_DelimitedIdentifier: return FC_DELIM;
+    case NUTDB_TT_Dot: return FC_DOT;
     default: return FC_OTHER;
   }
 }
@@ -222,7 +224,7 @@ inline uint8_t fast_keyword_class(uint32_t kw) {
 }
 
 inline void fast_tables_build(FastTables& F) {
-  static_assert(FS_COUNT <= 128 && FC_COUNT <= 64, "state / class fields");
+  static_assert(FS_COUNT <= 128 && FC_COUNT <= 255, "state / class fields");
   FastTableBuilder B(F);
   for (uint32_t i = 0; i < 64; i++) {
     F.op[i] = fast_optok_entry(i);
@@ -284,12 +286,17 @@ inline void fast_tables_build(FastTables& F) {
   B.bail(FS_FROM, {FC_JOIN});
   clauses(FS_FROM, 1);
   B.bail(FS_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_CASE});
-  B.words(FS_SRC, R().look(FL_NODOT_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));  // no table function, no qualifier
-  B.on(FS_SRC, FC_DELIM, R().look(FL_NODOT).leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));
+  B.words(FS_SRC, R().look(FL_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));  // no table function
+  B.on(FS_SRC, FC_DELIM, R().leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));
+  // `db.table`: the reference keeps the table and DROPS the qualifier (mod.rs:549-562): the node just emitted is withdrawn
+  B.on(FS_SRC2, FC_DOT, R().adv().popnode().to(FS_SRC_Q));
+  B.ident(FS_SRC_Q, R().leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2B));
   // the source is an expression: anything with infix power continues it (mod.rs:1212-1216)
-  B.bail(FS_SRC2, {FC_BINOP, FC_MUL, FC_PLUS, FC_MINUS, FC_LBRACKET, FC_KWBINOP, FC_NOT, FC_ISBETWEEN});
-  B.on(FS_SRC2, FC_AS, R().adv().to(FS_SRC_ALIAS));
-  B.otherwise(FS_SRC2, R().node_m1(NUTDB_NK_FROM).to(FS_CL1));
+  for (uint32_t st : {(uint32_t)FS_SRC2, (uint32_t)FS_SRC2B}) {
+    B.bail(st, {FC_BINOP, FC_MUL, FC_PLUS, FC_MINUS, FC_LBRACKET, FC_KWBINOP, FC_NOT, FC_ISBETWEEN, FC_DOT});
+    B.on(st, FC_AS, R().adv().to(FS_SRC_ALIAS));
+    B.otherwise(st, R().node_m1(NUTDB_NK_FROM).to(FS_CL1));
+  }
   B.ident(FS_SRC_ALIAS, FastRec(alias).to(FS_SRC3));
   B.otherwise(FS_SRC3, R().node_m1(NUTDB_NK_FROM).to(FS_CL1));
   // joins (try_parse_query_clause_join, mod.rs:376-431): [INNER | FULL [OUTER] | LEFT|RIGHT [SEMI|ANTI|OUTER]] JOIN
@@ -308,11 +315,13 @@ inline void fast_tables_build(FastTables& F) {
   for (uint32_t st : {(uint32_t)FS_J_LEFT, (uint32_t)FS_J_RIGHT, (uint32_t)FS_J_OUTER, (uint32_t)FS_J_KW})
     B.on(st, FC_JOIN, R().adv().post_m1().to(FS_J_SRC));
   B.bail(FS_J_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_CASE});
-  B.words(FS_J_SRC, R().look(FL_NODOT_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
-  B.on(FS_J_SRC, FC_DELIM, R().look(FL_NODOT).leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
-  B.on(FS_J_SRC2, FC_AS, R().adv().to(FS_J_ALIAS));
+  B.words(FS_J_SRC, R().look(FL_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
+  B.on(FS_J_SRC, FC_DELIM, R().leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2));
+  B.on(FS_J_SRC2, FC_DOT, R().adv().popnode().to(FS_J_SRC_Q));
+  B.ident(FS_J_SRC_Q, R().leaf(NUTDB_NK_IDENT).adv().to(FS_J_SRC2B));
+  for (uint32_t st : {(uint32_t)FS_J_SRC2, (uint32_t)FS_J_SRC2B}) B.on(st, FC_AS, R().adv().to(FS_J_ALIAS));
   B.ident(FS_J_ALIAS, FastRec(alias).to(FS_J_ONUSING));
-  for (uint32_t st : {(uint32_t)FS_J_SRC2, (uint32_t)FS_J_ONUSING}) {
+  for (uint32_t st : {(uint32_t)FS_J_SRC2, (uint32_t)FS_J_SRC2B, (uint32_t)FS_J_ONUSING}) {
     B.on(st, FC_ON, R().adv().ctx(C_JOIN_ON).to(FS_X_OPND));
     B.on(st, FC_USING, R().adv().to(FS_J_U_LP));
   }

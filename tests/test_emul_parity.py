@@ -229,6 +229,29 @@ def test_mutation_fuzz_case_expressions(seed):
     check(fuzz.fuzz_statements(CASES + CASES_AUTOMATON, 4000, seed=seed, max_mut=3))
 
 
+QUALIFIED = [b"select a from db.t where x = 1", b"select a from `d b`.`t t` as q join db2.u as r on q.a = r.a",
+             b"select a from db. t", b"select a from db.true", b"select a from t join d.u using (x)",
+             b"select a from t where a.b = c.d and e.* is null", b"select a from db.t limit 1;"]
+QUALIFIED_AUTOMATON = [b"select a from db.t.u", b"select a from db.*", b"select a from db.", b"select a from db.t (1)",
+                       b"select a from db.f(1)", b"select a from t.>= 1", b"select a from t where . >= 1",
+                       b"select a from db.t + 1", b"select a from true.t", b"select a from t join d.u.v on x",
+                       b"select a from d.t as", b"select . from t", b"select a.b.c from t", b"insert into d.t values (1)"]
+
+
+def test_qualified_table_names_in_the_fast_path():
+    """`db.table` as a source: the reference keeps the table and drops the qualifier (mod.rs:549-562)."""
+    E.fast_hits()
+    got = check(QUALIFIED)
+    assert E.fast_hits() == len(QUALIFIED) and (got.stmt["status"] == 0).all()
+    check(QUALIFIED_AUTOMATON)
+    assert (check([b"select a from t where . >= 1", b"select . from t"]).stmt["status"] != 0).all()
+
+
+@pytest.mark.parametrize("seed", [78])
+def test_mutation_fuzz_qualified_names(seed):
+    check(fuzz.fuzz_statements(QUALIFIED + QUALIFIED_AUTOMATON + JOINS, 5000, seed=seed, max_mut=3))
+
+
 def test_distinct_and_joins_in_the_fast_path():
     """SELECT DISTINCT and the join clause (mod.rs:349-360, :376-431) as rows of the table-driven parser."""
     E.fast_hits()

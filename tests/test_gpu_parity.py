@@ -277,7 +277,7 @@ def test_predicates_and_hex_literals(ctx):
     import test_emul_parity as T
     hexs = [b"select 0x1F, 0X2a, 0x, 0x0 from t where a = 0xdeadBEEF limit 0x10",
             b"select 0x1G, 0xzz, 00x1, 0x1.5, .0x1, 1.0x2, 0x1_2, x0x1, 0x1x", b"select a from t limit 0x, 0xFFFFFFFFFFFFFFFFF"]
-    seeds = T.PREDICATES + T.PREDICATES_AUTOMATON + T.JOINS + T.JOINS_AUTOMATON + T.CASES + T.CASES_AUTOMATON + hexs
+    seeds = T.PREDICATES + T.PREDICATES_AUTOMATON + T.JOINS + T.JOINS_AUTOMATON + T.CASES + T.CASES_AUTOMATON + T.QUALIFIED + T.QUALIFIED_AUTOMATON + hexs
     check(ctx, seeds)
     for seed in (81, 82):
         check(ctx, fuzz.fuzz_statements(seeds, 20000, seed=seed, max_mut=3))
