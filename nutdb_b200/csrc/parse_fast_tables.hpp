@@ -234,6 +234,11 @@ inline void fast_tables_build(FastTables& F) {
     F.op[64 + i] = fast_opkw_entry(i);
     F.cls[64 + i] = fast_keyword_class(i);
   }
+  // FastTableBuilder::words() / ident() rely on the word classes being exactly [FC_FIRST_WORD, FC_COUNT)
+  for (uint32_t i = 0; i < 64; i++)
+    if (F.cls[i] >= FC_FIRST_WORD) throw std::runtime_error("fast parser: a token-type class lies in the word-class range");
+  for (uint32_t i = 0; i < 128; i++)
+    if (F.cls[64 + i] < FC_FIRST_WORD) throw std::runtime_error("fast parser: a keyword class lies below the word-class range");
   auto R = [] { return FastRec(); };
   const FastRec skip_to_operand = R().adv().to(FS_X_OPND);
 
