@@ -19,7 +19,7 @@ import test_emul_parity as T
 pools['predicates'] = T.PREDICATES + T.PREDICATES_AUTOMATON + T.JOINS + T.JOINS_AUTOMATON + T.CASES + T.CASES_AUTOMATON + T.QUALIFIED + T.QUALIFIED_AUTOMATON + fuzz.SIMPLE_SEEDS[:40]
 t0 = time.time(); total = 0; nbad = 0
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0
-sd = 5000
+sd = int(sys.argv[2]) if len(sys.argv) > 2 else 5000  # first seed: pass another base to cover new ground
 while time.time() - t0 < budget:
     for name, pool in pools.items():
         st = fuzz.fuzz_statements(pool, 20000, seed=sd, max_mut=4)
