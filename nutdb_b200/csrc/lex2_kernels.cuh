@@ -702,52 +702,55 @@ struct ExactSink {
 template <bool Emit>
 __global__ void __launch_bounds__(128) k_lex_exact(const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32,
                                                    const LexTables* __restrict__ gT, const uint32_t* __restrict__ punt_list,
-                                                   uint32_t npunt, uint2* __restrict__ counts /* x = tokens, y = 0 */,
-                                                   const uint2* __restrict__ offsets, uint32_t extra_base, ExactSink sink,
-                                                   uint32_t* __restrict__ stmt_tok_begin, uint32_t* __restrict__ stmt_tok_end,
-                                                   uint32_t* __restrict__ punt_flag) {
+                                                   const uint32_t* __restrict__ npunt_dev, uint2* __restrict__ counts /* x = tokens, y = 0 */,
+                                                   const uint2* __restrict__ offsets, const uint32_t* __restrict__ extra_base_dev,
+                                                   ExactSink sink, uint32_t* __restrict__ stmt_tok_begin,
+                                                   uint32_t* __restrict__ stmt_tok_end, uint32_t* __restrict__ punt_flag) {
   __shared__ LexTables T;
+  const uint32_t npunt = *npunt_dev;  // (the list's length is only known on the device: a fixed grid strides over it)
+  if (blockIdx.x * blockDim.x >= npunt) return;
   stage_tables(gT, &T);
   __syncthreads();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npunt) return;
-  const uint32_t s = punt_list[i];
-  StmtSrc src{text, off32[s], off32[s + 1]};
-  LexCarry c;
-  c.stmt_start = src.begin;
-  c.tok_start = src.begin;
-  c.count = Emit ? extra_base + offsets[i].x : 0u;
-  const uint32_t first = c.count;
-  Walker<false, StmtSrc, ExactSink> w(T, src, sink, c);
-  w.counting = !Emit;
-  // One thread walks one statement: a byte at a time from global memory would cost a full memory latency per
-  // byte.  The statement is read as aligned 16-byte blocks, the next block in flight while this one is walked.
-  if (src.begin < src.end) {
-    const uint8_t* p0 = text + src.begin;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 15u);
-    const uint8_t* blk = p0 - mis;             // (the aligned block of a valid byte lies inside the same allocation)
-    const uint8_t* const last = text + src.end - 1u;
-    uint4 cur = __ldg(reinterpret_cast<const uint4*>(blk));
-    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-    if (blk + 16 <= last) nxt = __ldg(reinterpret_cast<const uint4*>(blk + 16));
-    uint32_t k = mis;
-    for (uint32_t pos = src.begin; pos < src.end; pos++, k++) {
-      if (k == 16u) {
-        k = 0u;
-        blk += 16;
-        cur = nxt;
-        if (blk + 16 <= last) nxt = __ldg(reinterpret_cast<const uint4*>(blk + 16));
+  const uint32_t extra_base = Emit ? *extra_base_dev : 0u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npunt; i += gridDim.x * blockDim.x) {
+    const uint32_t s = punt_list[i];
+    StmtSrc src{text, off32[s], off32[s + 1]};
+    LexCarry c;
+    c.stmt_start = src.begin;
+    c.tok_start = src.begin;
+    c.count = Emit ? extra_base + offsets[i].x : 0u;
+    const uint32_t first = c.count;
+    Walker<false, StmtSrc, ExactSink> w(T, src, sink, c);
+    w.counting = !Emit;
+    // One thread walks one statement: a byte at a time from global memory would cost a full memory latency per
+    // byte.  The statement is read as aligned 16-byte blocks, the next block in flight while this one is walked.
+    if (src.begin < src.end) {
+      const uint8_t* p0 = text + src.begin;
+      const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 15u);
+      const uint8_t* blk = p0 - mis;             // (the aligned block of a valid byte lies inside the same allocation)
+      const uint8_t* const last = text + src.end - 1u;
+      uint4 cur = __ldg(reinterpret_cast<const uint4*>(blk));
+      uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+      if (blk + 16 <= last) nxt = __ldg(reinterpret_cast<const uint4*>(blk + 16));
+      uint32_t k = mis;
+      for (uint32_t pos = src.begin; pos < src.end; pos++, k++) {
+        if (k == 16u) {
+          k = 0u;
+          blk += 16;
+          cur = nxt;
+          if (blk + 16 <= last) nxt = __ldg(reinterpret_cast<const uint4*>(blk + 16));
+        }
+        const uint32_t word = k < 8u ? (k < 4u ? cur.x : cur.y) : (k < 12u ? cur.z : cur.w);
+        w.step(pos, (uint8_t)((word >> (8u * (k & 3u))) & 255u), pos == src.begin, true);
       }
-      const uint32_t word = k < 8u ? (k < 4u ? cur.x : cur.y) : (k < 12u ? cur.z : cur.w);
-      w.step(pos, (uint8_t)((word >> (8u * (k & 3u))) & 255u), pos == src.begin, true);
     }
-  }
-  w.flush_eof(src.end);
-  if (Emit) {
-    stmt_tok_begin[s] = first;
-    stmt_tok_end[s] = w.c.count;
-    punt_flag[s] = i + 1u;  // position in the extra region's order: keeps the parser's node ranges disjoint
-  } else {
-    counts[i] = make_uint2(w.c.count, 0u);
+    w.flush_eof(src.end);
+    if (Emit) {
+      stmt_tok_begin[s] = first;
+      stmt_tok_end[s] = w.c.count;
+      punt_flag[s] = i + 1u;  // position in the extra region's order: keeps the parser's node ranges disjoint
+    } else {
+      counts[i] = make_uint2(w.c.count, 0u);
+    }
   }
 }

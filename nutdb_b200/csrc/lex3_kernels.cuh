@@ -1,0 +1,548 @@
+// lex3_kernels.cuh -- k_lex3: the whole lexer in ONE pass over the text (logic: lex3_core.cuh).
+//
+// Stages 1-3 of the pipeline in a single persistent kernel: the text is read once, nothing but the token arrays
+// and 12 bytes per 32-byte window (token index + token-end masks, from which the parser derives every statement's
+// token range) is written.
+//
+//   * persistent CTAs (one 8 KB tile per iteration, tiles handed out by an atomic ticket, so a tile's predecessors
+//     are always running or finished -- the forward-progress guarantee the look-back needs);
+//   * the next tile is staged while this one is lexed: one thread issues a bulk asynchronous copy
+//     (cp.async.bulk global -> shared, completion counted on an mbarrier), two buffers;
+//   * two DECOUPLED LOOK-BACK scans chained inside the kernel: (a) the context automaton's transition function
+//     (8 nibbles; ends early as soon as the composed function is constant, which a statement start makes it),
+//     (b) token count + open-literal carry + statement start;
+//   * thread per WINDOW for masks / context walk / token records, then thread per TOKEN for type, keyword hash,
+//     end-of-token checks and coalesced stores (records staged in shared memory).
+#pragma once
+#include "lex3_core.cuh"
+
+#define L3_THREADS 256
+#define L3_WARPS (L3_THREADS / 32)
+#define L3_WIN L3_THREADS                 // windows per tile
+#define L3_TILE (L3_WIN * 32)             // bytes per tile
+#define L3_HALO 32
+#define L3_RCAP 2560                      // token records staged per round (a tile holds ~1600 on query logs)
+#ifndef L3_MINBLOCKS
+#define L3_MINBLOCKS 3
+#endif
+
+struct alignas(16) Lex3Shared {
+  alignas(16) uint8_t text[2][L3_HALO + L3_TILE + L3_HALO];
+  alignas(16) uint32_t bm[2][L3_WIN + 4];  // statement-start bitmap words of the tile and of the window after it
+  alignas(8) unsigned long long bar[2];
+  LexTables T;
+  uint32_t bndm[L3_WIN + 1];               // statement starts per window incl. the virtual one at the batch end
+  uint32_t sst_in[L3_WIN];                 // start of the statement that is open where the window begins
+  uint32_t rec0[L3_RCAP], rec1[L3_RCAP];
+  uint32_t wfn[L3_WARPS];
+  uint4 wsum[L3_WARPS];
+  uint32_t ticket[2];
+  uint32_t s_tile_in;
+  uint4 c_tile_pre;
+};
+
+// descriptors of the two look-back scans (one entry per tile; `epoch` distinguishes launches, so nothing is cleared)
+struct Lex3Desc {
+  unsigned long long* fn;  // (epoch << 34) | (status << 32) | function;  status 1 = the tile's own function, 2 = inclusive
+  uint32_t* cstatus;       // (epoch << 2) | status
+  uint4* cagg;             // x = tokens, y = 1 + last statement start (0: none), z = offset of the open quote,
+  uint4* cinc;             //   w = bit 0: a literal was opened (z valid), bit 1: escaped flag
+};
+
+struct Lex3Out {
+  uint8_t* type;
+  uint32_t* start;
+  uint32_t* end;
+  uint8_t* kw;
+  uint32_t cap;            // capacity of the token arrays (tokens beyond it are counted, not stored)
+  uint32_t* win_idx;       // per window: index of the first token that ends in it (+1 entry: the total)
+  uint32_t* win_has;       // per window: bytes where a token ends
+  uint32_t* win_eof;       // per window: bytes after which an EOF token follows
+  const uint32_t* off32;
+  uint32_t nstmt;
+  uint32_t* punt_flag;     // per statement: needs the exact lexer
+  uint32_t* counters;      // [0] flagged statements, [1] bound on their tokens, [2] total tokens, [3] tile ticket
+  const uint32_t* first_stmt;
+  uint32_t* dbg;           // optional (tests): per tile {entry state, first token index, statement start, open quote}
+  __device__ void punt_stmt_at(uint32_t sst) const {  // the (non-empty) statement that starts at byte sst
+    uint32_t c = first_stmt[sst >> 5];
+    while (off32[c] != sst || off32[c + 1] == sst) c++;
+    if (atomicExch(&punt_flag[c], 1u) == 0u) {
+      atomicAdd(counters, 1u);
+      atomicAdd(counters + 1, off32[c + 1] - off32[c] + 1u);
+    }
+  }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One thread stages tile t (text with a 32-byte halo on both sides + its bitmap words) into buffer b.
+// `padded` = bytes readable behind the text (the library's own buffer is padded; a caller's device buffer is not).
+__device__ __forceinline__ void l3_issue_load(Lex3Shared& S, int b, uint32_t t, const uint8_t* text, const uint32_t* bitmap,
+                                              uint32_t n, uint32_t n_readable) {
+  const uint32_t tile_begin = t * L3_TILE;
+  const uint32_t lo = tile_begin >= L3_HALO ? tile_begin - L3_HALO : 0u;
+  uint32_t hi = tile_begin + L3_TILE + L3_HALO;
+  if (hi > n_readable) hi = n_readable & ~15u;  // whole 16-byte pieces only; the ragged rest is loaded by threads
+  const uint32_t bytes_text = hi > lo ? hi - lo : 0u;
+  const uint32_t bytes_bm = (L3_WIN + 4) * 4u;    // (the bitmap has that many words behind every tile)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(&S.bar[b], bytes_text + bytes_bm);
+  if (bytes_text) bulk_g2s(&S.text[b][L3_HALO + lo - tile_begin], text + lo, bytes_text, &S.bar[b]);
+  bulk_g2s(&S.bm[b][0], bitmap + (tile_begin >> 5), bytes_bm, &S.bar[b]);
+}
+
+struct Tile3Src {
+  const uint8_t* text;
+  const uint8_t* sm;  // the tile's first byte in shared memory; the halo lies at sm[-32..-1] and sm[L3_TILE..+31]
+  uint32_t tile_begin, n;
+  __device__ __forceinline__ uint8_t byte(uint32_t p) const {
+    const uint32_t r = p - tile_begin + L3_HALO;
+    if (r < L3_TILE + 2 * L3_HALO) return sm[(int)r - L3_HALO];
+    return far_byte(text, p, n);
+  }
+  __device__ __forceinline__ const uint8_t* span(uint32_t p, uint32_t len) const {
+    const uint32_t r = p - tile_begin + L3_HALO;
+    // (load_word12 reads aligned words around the span: keep 16 bytes clear of the staged range's ends)
+    return (r >= 4u && r + len + 16u <= L3_TILE + 2 * L3_HALO) ? sm + ((int)r - L3_HALO) : nullptr;
+  }
+};
+
+__device__ __forceinline__ uint4 c3_then(const uint4& a, const uint4& b) {
+  uint4 r;
+  r.x = a.x + b.x;
+  r.y = b.y ? b.y : a.y;
+  if (b.w & 1u) {
+    r.z = b.z;
+    r.w = b.w;
+  } else {
+    r.z = a.z;
+    r.w = a.w | (b.w & 2u);
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 c3_shfl_up(const uint4& v, int d) {
+  return make_uint4(__shfl_up_sync(0xFFFFFFFFu, v.x, d), __shfl_up_sync(0xFFFFFFFFu, v.y, d),
+                    __shfl_up_sync(0xFFFFFFFFu, v.z, d), __shfl_up_sync(0xFFFFFFFFu, v.w, d));
+}
+__device__ __forceinline__ bool vec8_is_const(uint32_t f) { return f == (f & 7u) * 0x11111111u; }
+// A load the compiler may not hoist out of (or delete together with) a polling loop: a plain / __ldcg load is
+// loop-invariant to it, and a loop without side effects "must terminate", so the epoch test would be removed.
+__device__ __forceinline__ unsigned long long ld_poll_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_poll_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(L3_THREADS, L3_MINBLOCKS) k_lex3(const uint8_t* __restrict__ text,
+                                                                    const uint32_t* __restrict__ bitmap, uint32_t n,
+                                                                    uint32_t n_readable, uint32_t ntiles,
+                                                                    const LexTables* __restrict__ gT, Lex3Desc desc,
+                                                                    uint32_t epoch, Lex3Out out,
+                                                                    const uint32_t* __restrict__ gate) {
+  if (*gate) return;  // invalid statement offsets (k_prep): nothing downstream may trust them
+  extern __shared__ __align__(16) unsigned char l3_smem[];
+  Lex3Shared& S = *reinterpret_cast<Lex3Shared*>(l3_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t full = 0xFFFFFFFFu;
+  stage_tables(gT, &S.T);
+  if (threadIdx.x == 0) {
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t t0 = atomicAdd(out.counters + 3, 1u);
+    S.ticket[0] = t0;
+    if (t0 < ntiles) l3_issue_load(S, 0, t0, text, bitmap, n, n_readable);
+  }
+  __syncthreads();
+  uint32_t phase0 = 0u, phase1 = 0u;
+  for (int b = 0;; b ^= 1) {
+    const uint32_t tile = S.ticket[b];
+    if (tile >= ntiles) break;
+    if (threadIdx.x == 0) {  // claim and stage the next tile while this one is lexed
+      const uint32_t tn = atomicAdd(out.counters + 3, 1u);
+      S.ticket[b ^ 1] = tn;
+      if (tn < ntiles) l3_issue_load(S, b ^ 1, tn, text, bitmap, n, n_readable);
+    }
+    const uint32_t tile_begin = tile * L3_TILE;
+    mbar_wait(&S.bar[b], b ? phase1 : phase0);
+    if (b) phase1 ^= 1u;
+    else phase0 ^= 1u;
+    uint8_t* const sm = &S.text[b][L3_HALO];
+    // what the bulk copy could not bring: the front halo of tile 0, and everything behind the last whole 16-byte
+    // piece of a caller's unpadded buffer (loaded bytewise up to n, zero beyond)
+    if (tile_begin == 0 && threadIdx.x < L3_HALO) sm[(int)threadIdx.x - L3_HALO] = 0;
+    if (tile_begin + L3_TILE + L3_HALO > n_readable) {
+      const uint32_t from = n_readable & ~15u;
+      for (uint32_t p = max(from, tile_begin >= L3_HALO ? tile_begin - L3_HALO : 0u) + threadIdx.x; p < tile_begin + L3_TILE + L3_HALO;
+           p += L3_THREADS)
+        sm[(int)(p - tile_begin)] = p < n ? text[p] : (uint8_t)0;
+      __syncthreads();
+    } else if (tile_begin == 0) {
+      __syncthreads();
+    }
+    const uint32_t* const bm = S.bm[b];
+    Tile3Src src{text, sm, tile_begin, n};
+    const uint32_t base = tile_begin + 32u * threadIdx.x;
+    const uint32_t blk = tile_begin + 1024u * (uint32_t)warp;
+    // ---------------- stage 1: class masks, escapes, context events, transition function ----------------
+    nlex2::Win w;
+    nlex3::Ops op;
+    w.valid = base + 32u <= n ? full : (n > base ? ((1u << (n - base)) - 1u) : 0u);
+    {
+      const uint4* wp = reinterpret_cast<const uint4*>(sm + 32u * threadIdx.x);
+      const uint4 q0 = wp[0], q1 = wp[1];
+      const uint32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      uint32_t p[8];
+      nlex3::bit_planes(v, p);
+      nlex3::classify_planes(p, w.valid, w, op);
+    }
+    {
+      uint32_t bnd = base < n ? (bm[threadIdx.x] & w.valid) : 0u;
+      if (n >= base && n - base < 32u) bnd |= 1u << (n - base);  // the batch end terminates the last statement
+      w.bnd = bnd;
+    }
+    nlex2::Next nx;
+    {
+      const uint32_t p = base + 32u;
+      if (p >= n) {
+        nx.byte = 0;
+        nx.bnd = 1;
+        nx.cls = 0;
+      } else {
+        nx.byte = sm[32u * threadIdx.x + 32u];
+        nx.bnd = (uint8_t)(bm[threadIdx.x + 1] & 1u);
+        nx.cls = 0;
+      }
+    }
+    uint8_t prev_byte, prev2_byte, esc_in;
+    {
+      const uint32_t bs_prev = __shfl_up_sync(full, w.bs, 1);
+      if (lane == 0) {
+        prev_byte = 0;
+        esc_in = 0;
+        if (base > 0 && base <= n) {
+          prev_byte = sm[(int)(32u * threadIdx.x) - 1];
+          if (!(w.bnd & 1u)) {  // backslash parity in front of the warp's block: walk back over the run
+            uint32_t nrun = 0, p = base;
+            while (p > 0 && src.byte(p - 1) == '\\') {
+              nrun++;
+              p--;
+              if ((bitmap[p >> 5] >> (p & 31u)) & 1u) break;
+            }
+            esc_in = (uint8_t)(nrun & 1u);
+          }
+        }
+      } else {
+        prev_byte = base <= n && base > 0 ? sm[(int)(32u * threadIdx.x) - 1] : (uint8_t)0;
+        const int run = nlex2::clz32(~bs_prev);
+        esc_in = (uint8_t)(run >= 32 ? 0 : (run & 1));  // (32 backslashes in a row: the statement is flagged below)
+      }
+      prev2_byte = base <= n && base > 1 ? sm[(int)(32u * threadIdx.x) - 2] : (uint8_t)0;
+    }
+    const uint32_t escm = nlex2::esc_mask32(w.bs, esc_in) & ~w.bnd;
+    const nlex2::Events ev = nlex2::make_events(w, escm, prev_byte);
+    uint32_t fnv = NUTDB_VEC8_ID;
+    if (base < n)
+      fnv = ev.all ? nlex2::ctx_window_fn(S.T, w, ev, NUTDB_VEC8_ID)
+                   : vec8_then_row(NUTDB_VEC8_ID, S.T.a_row[EV_OTHER][0], S.T.a_row[EV_OTHER][1]);
+    uint32_t fexcl;
+    {
+      const uint32_t incl = warp_scan_vec8(fnv, lane, fexcl);
+      if (lane == 31) S.wfn[warp] = incl;
+    }
+    if (threadIdx.x == 0)  // the byte behind the tile starts a statement (or is the end of the batch)
+      S.bndm[L3_WIN] = (tile_begin + L3_TILE < n ? (bm[L3_WIN] & 1u) : 0u) | (tile_begin + L3_TILE == n ? 1u : 0u);
+    S.bndm[threadIdx.x] = w.bnd;
+    __syncthreads();
+    // ---------------- look-back (a): entry state of the tile ----------------
+    if (warp == 0) {
+      uint32_t agg = NUTDB_VEC8_ID;
+#pragma unroll
+      for (int i = 0; i < L3_WARPS; i++) agg = vec8_then(agg, S.wfn[i]);
+      if (lane == 0) {
+        uint32_t s_in = A_C;
+        if (tile > 0) {
+          // publish the tile's own function first: successors can compose it without waiting for our look-back
+          if (!vec8_is_const(agg)) {
+            __stcg(desc.fn + tile, ((unsigned long long)epoch << 34) | (1ull << 32) | agg);
+            uint32_t acc = NUTDB_VEC8_ID;  // functions of the tiles (p, tile) composed
+            uint32_t p = tile;
+            for (;;) {
+              p--;
+              unsigned long long d;
+              do {
+                d = ld_poll_u64(desc.fn + p);
+              } while ((d >> 34) != epoch);
+              acc = vec8_then((uint32_t)d, acc);
+              if (((d >> 32) & 3ull) == 2ull || vec8_is_const(acc) || p == 0) break;
+            }
+            s_in = vec8_apply(acc, A_C);
+          }
+        }
+        const uint32_t s_out = vec8_apply(agg, vec8_is_const(agg) ? 0u : s_in);
+        __stcg(desc.fn + tile, ((unsigned long long)epoch << 34) | (2ull << 32) | (s_out * 0x11111111u));
+        if (tile > 0 && vec8_is_const(agg)) {
+          // our exit state does not depend on the entry state, but the windows before the tile's first statement
+          // start do: look back now, after successors were served
+          uint32_t acc = NUTDB_VEC8_ID;
+          uint32_t p = tile;
+          for (;;) {
+            p--;
+            unsigned long long d;
+            do {
+              d = ld_poll_u64(desc.fn + p);
+            } while ((d >> 34) != epoch);
+            acc = vec8_then((uint32_t)d, acc);
+            if (((d >> 32) & 3ull) == 2ull || vec8_is_const(acc) || p == 0) break;
+          }
+          s_in = vec8_apply(acc, A_C);
+        }
+        S.s_tile_in = s_in;
+      }
+    }
+    __syncthreads();
+    uint8_t s_warp;
+    {
+      uint32_t pre = NUTDB_VEC8_ID;
+      for (int i = 0; i < warp; i++) pre = vec8_then(pre, S.wfn[i]);
+      s_warp = (uint8_t)vec8_apply(pre, S.s_tile_in);
+    }
+    const uint8_t s_in = (uint8_t)vec8_apply(fexcl, s_warp);
+    // ---------------- stage 2: concrete context walk, token masks ----------------
+    nlex2::WinCtx o;
+    const bool live = base < n;
+    if (live) nlex2::ctx_window(w, ev, base, nx, s_in, prev_byte, o);
+    o.escm = escm;
+    nlex3::Hist3 h;
+    {
+      h.L = __shfl_up_sync(full, w.L & o.ct, 1);
+      h.D = __shfl_up_sync(full, w.D & o.ct, 1);
+      h.DOT = __shfl_up_sync(full, w.DOT & o.ct, 1);
+      h.bnd = __shfl_up_sync(full, w.bnd, 1);
+      // lane 0: the 32 bytes in front of the warp's block; their raw classes are exact where it matters (a run of
+      // word characters / dots that reaches the block) when the block is entered in code
+      uint32_t rL = 0, rD = 0, rDOT = 0;
+      if (blk >= 32u) {
+        const uint8_t c = sm[(int)(blk - tile_begin) - 32 + lane];
+        const uint8_t pr = S.T.prop[c];
+        rL = __ballot_sync(full, (pr & PR_WORD) && !(pr & PR_DIGIT));
+        rD = __ballot_sync(full, pr & PR_DIGIT);
+        rDOT = __ballot_sync(full, c == '.');
+      }
+      if (lane == 0) {
+        const bool code_entry = s_warp <= A_CX;
+        h.L = code_entry ? rL : 0u;
+        h.D = code_entry ? rD : 0u;
+        h.DOT = code_entry ? rDOT : 0u;
+        h.bnd = blk >= 32u ? (warp == 0 ? bitmap[(blk - 32u) >> 5] : bm[(blk - 32u - tile_begin) >> 5]) : 0u;
+      }
+    }
+    nlex3::TokMasks m;
+    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+    if (live) {
+      nlex3::win_tokens3(w, op, o, h, nx, prev_byte, prev2_byte, m);
+      uint32_t bad = m.bad | nlex2::win_bad_mask(src, w, o, base, prev_byte);
+      if (w.bs == 0xFFFFFFFFu) bad |= 1u;  // a backslash run longer than a window: parity not tracked
+      // flag statements: find the start of the statement each flagged byte belongs to
+      uint32_t bb = bad;
+      const uint32_t bnds = w.bnd & w.valid;
+      // (the statement open at the window start is only known after look-back (b): remember the request)
+      uint32_t bad_carry = 0;
+      while (bb) {
+        const int i = __ffs((int)bb) - 1;
+        bb &= bb - 1;
+        const uint32_t below = bnds & (i >= 31 ? 0xFFFFFFFFu : ((2u << i) - 1u));
+        if (below) out.punt_stmt_at(base + (uint32_t)(31 - __clz((int)below)));
+        else bad_carry = 1;
+      }
+      bb = o.bad_prev;  // the statement that ENDS right before this (statement start) byte
+      while (bb) {
+        const int i = __ffs((int)bb) - 1;
+        bb &= bb - 1;
+        const uint32_t below = bnds & ((1u << i) - 1u);
+        if (below) out.punt_stmt_at(base + (uint32_t)(31 - __clz((int)below)));
+        else bad_carry = 1;
+      }
+      // the batch ends exactly on a window boundary inside a literal / comment: no window carries the virtual start
+      if (base + 32u == n && (o.s_out == A_SQ || o.s_out == A_DQ || o.s_out == A_BT || o.s_out == A_BC0 || o.s_out == A_BC)) {
+        if (bnds) out.punt_stmt_at(base + (uint32_t)(31 - __clz((int)bnds)));
+        else bad_carry = 1;
+      }
+      mine.x = (uint32_t)__popc(m.has) + (uint32_t)__popc(m.eofm);
+      mine.y = o.last_bnd1;
+      mine.z = o.sc.open_pos;
+      mine.w = (uint32_t)(o.sc.has_open != 0) | ((uint32_t)(o.sc.esc != 0) << 1) | (bad_carry << 2);
+    }
+    // ---------------- scan of (count, statement start, open literal) over the tile ----------------
+    uint4 incl = mine;
+    incl.w &= 3u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint4 o2 = c3_shfl_up(incl, d);
+      if (lane >= d) incl = c3_then(o2, incl);
+    }
+    uint4 excl = c3_shfl_up(incl, 1);
+    if (lane == 0) excl = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 31) S.wsum[warp] = incl;
+    __syncthreads();
+    // ---------------- look-back (b): tokens / statement start / open literal before the tile ----------------
+    if (warp == 0) {
+      uint4 agg = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int i = 0; i < L3_WARPS; i++) agg = c3_then(agg, S.wsum[i]);
+      uint4 pre = make_uint4(0u, 0u, 0u, 0u);
+      if (tile > 0) {
+        if (lane == 0) {
+          __stcg(desc.cagg + tile, agg);
+          __threadfence();
+          *(volatile uint32_t*)(desc.cstatus + tile) = (epoch << 2) | 1u;
+        }
+        // 32 predecessors per step: each lane waits for one descriptor; the nearest inclusive one ends the walk
+        uint32_t p0 = tile;  // the window [p0 - 32, p0) is inspected next
+        for (;;) {
+          const bool has_p = p0 > (uint32_t)lane;
+          const uint32_t p = has_p ? p0 - 1u - (uint32_t)lane : 0u;
+          uint32_t st = 0;
+          if (has_p) {
+            do {
+              st = ld_poll_u32(desc.cstatus + p);
+            } while ((st >> 2) != epoch || (st & 3u) == 0u);
+            st &= 3u;
+          }
+          __threadfence();
+          const uint32_t incl_mask = __ballot_sync(full, has_p && st == 2u);
+          const int stop = incl_mask ? __ffs((int)incl_mask) - 1 : (has_p ? 32 : 31);  // nearest inclusive lane
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (has_p && lane <= stop) v = __ldcg((st == 2u ? desc.cinc : desc.cagg) + p);
+          // ordered composition: lane `stop` (farthest) first ... lane 0 (nearest) last, then what we have so far
+          uint4 part = make_uint4(0u, 0u, 0u, 0u);
+          const int last = incl_mask ? stop : 31;
+          for (int q = last; q >= 0; q--) {
+            const uint4 x = make_uint4(__shfl_sync(full, v.x, q), __shfl_sync(full, v.y, q), __shfl_sync(full, v.z, q),
+                                       __shfl_sync(full, v.w, q));
+            part = c3_then(part, x);
+          }
+          pre = c3_then(part, pre);
+          if (incl_mask || p0 <= 32u) break;
+          p0 -= 32u;
+        }
+      }
+      if (lane == 0) {
+        const uint4 inc = c3_then(pre, agg);
+        __stcg(desc.cinc + tile, inc);
+        __threadfence();
+        *(volatile uint32_t*)(desc.cstatus + tile) = (epoch << 2) | 2u;
+        S.c_tile_pre = pre;
+        if (tile + 1 == ntiles) {
+          out.counters[2] = inc.x;
+          out.win_idx[(size_t)ntiles * L3_WIN] = inc.x;
+        }
+      }
+    }
+    __syncthreads();
+    uint4 cin;  // everything before this thread's window
+    {
+      uint4 pre = S.c_tile_pre;
+      for (int i = 0; i < warp; i++) pre = c3_then(pre, S.wsum[i]);
+      cin = c3_then(pre, excl);
+    }
+    if (out.dbg && threadIdx.x == 0) {
+      out.dbg[4 * tile + 0] = S.s_tile_in;
+      out.dbg[4 * tile + 1] = cin.x;
+      out.dbg[4 * tile + 2] = cin.y;
+      out.dbg[4 * tile + 3] = cin.z | (cin.w << 30);
+    }
+    const uint32_t sst_open = cin.y ? cin.y - 1u : 0u;
+    S.sst_in[threadIdx.x] = sst_open;
+    if (live && (mine.w & 4u)) out.punt_stmt_at(sst_open);
+    if (base <= n) {  // (the window that starts exactly at the batch end holds the last statement's token-range end)
+      out.win_idx[base >> 5] = cin.x;
+      out.win_has[base >> 5] = m.has;
+      out.win_eof[base >> 5] = m.eofm;
+    }
+    // ---------------- stage 3: token records (thread per window) -> tokens (thread per token) ----------------
+    const uint32_t tile_first = S.c_tile_pre.x;  // index of the tile's first token
+    uint32_t tile_count;
+    {
+      uint4 t = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 0; i < L3_WARPS; i++) t.x += S.wsum[i].x;
+      tile_count = t.x;
+    }
+    nlex2::StrCarry sc_in;
+    sc_in.has_open = (uint8_t)(cin.w & 1u);
+    sc_in.esc = (uint8_t)((cin.w >> 1) & 1u);
+    sc_in.open_pos = cin.z;
+    for (uint32_t r0 = 0; r0 < tile_count; r0 += L3_RCAP) {
+      if (r0) __syncthreads();  // the previous round's records have been consumed
+      if (live && mine.x) {
+        const uint32_t local = cin.x - tile_first;  // index of the window's first token inside the tile
+        if (local < r0 + L3_RCAP && local + mine.x > r0) {
+          auto rec = [&](uint32_t idx, uint32_t start_abs, uint32_t end_abs, uint32_t flags) {
+            const uint32_t k = idx - r0;
+            if (k < L3_RCAP) {
+              S.rec0[k] = start_abs;
+              S.rec1[k] = (end_abs - tile_begin) | (flags << NUTDB_R3_FLAG_SHIFT);
+            }
+          };
+          nlex3::win_records3(o, m, base, sc_in, local, rec);
+        }
+      }
+      __syncthreads();
+      const uint32_t cnt = min(tile_count - r0, (uint32_t)L3_RCAP);
+      for (uint32_t k = threadIdx.x; k < cnt; k += L3_THREADS) {
+        const uint32_t start_abs = S.rec0[k], r1 = S.rec1[k];
+        const uint32_t end_rel = r1 & ((1u << NUTDB_R3_FLAG_SHIFT) - 1u), flags = r1 >> NUTDB_R3_FLAG_SHIFT;
+        const uint32_t last = end_rel - 1u;  // the token's last byte, tile relative
+        const uint32_t wv = last >> 5, i = last & 31u;
+        const uint32_t bb = S.bndm[wv] & (i >= 31u ? 0xFFFFFFFFu : ((2u << i) - 1u));
+        const uint32_t sst = bb ? tile_begin + 32u * wv + (uint32_t)(31 - __clz((int)bb)) : S.sst_in[wv];
+        const bool next_bnd = i < 31u ? ((S.bndm[wv] >> (i + 1u)) & 1u) != 0 : (S.bndm[wv + 1] & 1u) != 0;
+        nlex3::Tok3 tk;
+        nlex3::token_finish3(S.T, src, start_abs, tile_begin + end_rel, flags, sst, next_bnd, tk);
+        if (tk.punt) {
+          out.punt_stmt_at(sst);
+          tk.type = NUTDB_TT_POISON;  // (the slot belongs to a flagged statement: a fixed filler)
+          tk.start = tk.end = 0;
+          tk.kw = 0;
+        }
+        const uint32_t gi = tile_first + r0 + k;
+        if (gi < out.cap) {
+          out.type[gi] = tk.type;
+          out.start[gi] = tk.start;
+          out.end[gi] = tk.end;
+          out.kw[gi] = tk.kw;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with buffer b and the per-window tables before the next tile reuses them
+  }
+}

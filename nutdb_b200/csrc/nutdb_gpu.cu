@@ -19,6 +19,7 @@
 // 32 different banks.  No CPU fallback anywhere: without a device every entry point fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -191,9 +192,11 @@ __device__ __forceinline__ typename Op::T block_scan(typename Op::T v, typename 
 template <class Op>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const typename Op::T* __restrict__ in,
                                                              typename Op::T* __restrict__ out, uint32_t n,
-                                                             typename Op::T* __restrict__ total_out) {
+                                                             typename Op::T* __restrict__ total_out,
+                                                             const uint32_t* __restrict__ n_dev = nullptr) {
   typedef typename Op::T T;
   __shared__ T ws[32];
+  if (n_dev) n = min(n, *n_dev);  // the number of entries is only known on the device
   const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
   T f = Op::identity();
@@ -264,8 +267,13 @@ template <bool Scatter>
 __global__ void __launch_bounds__(PUNT_THREADS) k_punt_list(const uint32_t* __restrict__ punt_flag, uint32_t nstmt,
                                                             uint2* __restrict__ block_count,
                                                             const uint2* __restrict__ block_pref,
-                                                            uint32_t* __restrict__ list) {
+                                                            uint32_t* __restrict__ list,
+                                                            const uint32_t* __restrict__ npunt_dev) {
   __shared__ uint2 ws[32];
+  if (*npunt_dev == 0u) {  // nothing flagged (the usual case): the list is empty
+    if (!Scatter && threadIdx.x == 0) block_count[blockIdx.x] = make_uint2(0u, 0u);
+    return;
+  }
   const uint32_t s0 = (blockIdx.x * PUNT_THREADS + threadIdx.x) * PUNT_PER_THREAD;
   uint32_t bits = 0;
   for (uint32_t k = 0; k < PUNT_PER_THREAD; k++)
@@ -303,20 +311,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_vec8(const uint32_t* __re
 // ------------------------------------------------------------------------------------------
 // k_prep
 // ------------------------------------------------------------------------------------------
-__global__ void k_prep(const uint64_t* __restrict__ off, uint64_t nstmt, uint32_t* __restrict__ off32,
+__global__ void k_prep(const uint64_t* __restrict__ off, uint64_t nstmt, uint64_t nbytes, uint32_t* __restrict__ off32,
                        uint32_t* __restrict__ bitmap, uint32_t* __restrict__ first_stmt, uint32_t* __restrict__ bad) {
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nstmt) return;
   const uint64_t base = off[0];
   const uint64_t o = off[s];
-  if (o < base) {
+  // every offset must lie inside the batch [off[0], off[n]]: an interior offset beyond it would index the bitmap
+  // (sized for the batch) out of bounds
+  if (o < base || o - base > nbytes) {
     atomicOr(bad, 1u);
+    off32[s] = 0u;
     return;
   }
   off32[s] = (uint32_t)(o - base);
   if (s < nstmt) {
     const uint64_t e = off[s + 1];
-    if (e < o) atomicOr(bad, 1u);
+    if (e < o || e - base > nbytes) atomicOr(bad, 1u);
     else if (e > o) {
       uint32_t p = (uint32_t)(o - base);
       atomicOr(&bitmap[p >> 5], 1u << (p & 31u));
@@ -469,6 +480,7 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_D(const uint8_t* __restrict
 
 #include "lex2_core.cuh"
 #include "lex2_kernels.cuh"
+#include "lex3_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // parser kernels
@@ -578,16 +590,48 @@ __device__ __forceinline__ void store_result(const npar::ParseResult& res, uint3
   }
 }
 
+// Token range of a statement.  The single-pass lexer does not know statements: it stores, per 32-byte window, the index
+// of the first token ending in it and the masks of bytes where a token / an EOF token ends; the number of tokens that
+// end before byte `pos` follows from those.  Statements lexed by the exact walker have explicit ranges.
+struct StmtToks {
+  const uint32_t* win_idx;
+  const uint32_t* win_has;
+  const uint32_t* win_eof;
+  const uint32_t* punt;            // per statement: 0, or 1 + position in the exact lexer's region
+  const uint32_t* x_begin;         // per statement, valid where punt != 0
+  const uint32_t* x_end;
+  __device__ __forceinline__ uint32_t index_at(uint32_t pos) const {
+    const uint32_t w = pos >> 5, b = pos & 31u;
+    uint32_t r = win_idx[w];
+    if (b) {
+      const uint32_t below = (1u << b) - 1u;
+      r += (uint32_t)__popc(win_has[w] & below) + (uint32_t)__popc(win_eof[w] & below);
+    }
+    return r;
+  }
+  __device__ __forceinline__ void range(uint32_t s, uint32_t o, uint32_t e, uint32_t& tb, uint32_t& tc) const {
+    if (!win_idx || punt[s]) {
+      tb = x_begin[s];
+      tc = x_end[s] - tb;
+    } else {
+      tb = index_at(o);
+      tc = index_at(e) - tb;
+    }
+  }
+};
+
 // Pass 1, one thread per statement: the straight-line parser (parse_fast.cuh).  Statements it
 // declines go to the slow list.  Small code, no interpreter state: this is where a query log's
 // bulk is parsed.
 __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
     const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, uint32_t nstmt, uint32_t ntok,
     const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end,
-    const uint8_t* __restrict__ tok_kw, const uint32_t* __restrict__ stmt_tok_begin,
-    const uint32_t* __restrict__ stmt_tok_end, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
+    const uint8_t* __restrict__ tok_kw, StmtToks stoks, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
     uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count, const uint32_t* __restrict__ punt,
-    int lex_only, uint32_t tok_alloc, const npar::FastTables* __restrict__ gF) {
+    int lex_only, uint32_t tok_alloc, const npar::FastTables* __restrict__ gF, const uint32_t* __restrict__ ntok_main_dev,
+    const uint32_t* __restrict__ ntok_extra_dev, const uint32_t* __restrict__ gate) {
+  if (*gate) return;  // invalid statement offsets: nothing downstream of k_prep may trust them
+  if (ntok_main_dev) ntok = *ntok_main_dev + *ntok_extra_dev;  // tokens of the main region + of the exact lexer's region
   // Lanes of a warp run independent parsers, so they only execute together where their statements look
   // alike.  The block therefore re-deals its statements: a counting sort in shared memory by (first keyword,
   // token-count bucket) puts statements of the same kind and similar length into the same warp.
@@ -615,10 +659,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
   // few lexed into the extra region).  Stage that run's (type, keyword) pairs in shared memory with coalesced
   // 16-byte loads: the parsers below then never wait on a global load for a token.
   uint32_t tb0 = 0xFFFFFFFFu, tc0 = 0;
-  if (s < nstmt && off32[s + 1] != off32[s]) {
-    tb0 = stmt_tok_begin[s];
-    tc0 = stmt_tok_end[s] - tb0;
-  }
+  if (s < nstmt && off32[s + 1] != off32[s]) stoks.range(s, off32[s], off32[s + 1], tb0, tc0);
   {
     const uint32_t wmin = __reduce_min_sync(0xFFFFFFFFu, tb0);
     if ((threadIdx.x & 31u) == 0 && wmin != 0xFFFFFFFFu) atomicMin(&tok_lo, wmin);
@@ -701,7 +742,8 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
     stmt[s] = S;
     return;
   }
-  const uint32_t tb = stmt_tok_begin[s], tc = stmt_tok_end[s] - tb;
+  uint32_t tb, tc;
+  stoks.range(s, o, o + len, tb, tc);
   if (lex_only) {
     NutdbStmt S;
     S.status = NUTDB_ST_OK;
@@ -742,7 +784,9 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
     const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw,
     const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch,
     uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, uint32_t nstmt,
-    const uint32_t* __restrict__ punt) {
+    const uint32_t* __restrict__ punt, const uint32_t* __restrict__ nslow_dev) {
+  if (nslow_dev) nslow = *nslow_dev;  // the slow list's length is only known on the device
+  if (blockIdx.x * PARSE_THREADS >= nslow) return;
   __shared__ npar::ParseTables P;
   __shared__ uint32_t skey[PARSE_THREADS], sorder[PARSE_THREADS];
   stage_parse_tables(gP, &P);
@@ -945,9 +989,15 @@ struct NutdbCtx {
   cudaStream_t stream2 = nullptr;  // the exact-lexer chain runs here beside the emit pass
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   nlex2::Lex2Tables* dLex2 = nullptr;
+  uint32_t epoch = 0;       // launch number of k_lex3 (tags its look-back descriptors)
+  int sm_count = 148;
+  size_t tok_cap_min = 0;   // token capacity a previous batch turned out to need
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
-  DevBuf winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+  bool debug_tiles = false;
+  uint32_t dbg_ntiles = 0;
+  DevBuf dbgTiles;
+  DevBuf winIdx, winHas, winEof, descFn, descStatus, descAgg, descInc, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
@@ -1009,6 +1059,13 @@ int ensure_dev(NutdbCtx* ctx, DevBuf& b, size_t bytes) {
   b.cap = want;
   return NUTDB_OK;
 }
+// grow-only buffer whose NEW storage starts zeroed (look-back descriptors: stale epochs must not look current)
+int ensure_dev_zeroed(NutdbCtx* ctx, DevBuf& b, size_t bytes, cudaStream_t st) {
+  if (bytes <= b.cap) return NUTDB_OK;
+  const int rc = ensure_dev(ctx, b, bytes);
+  if (rc != NUTDB_OK) return rc;
+  return cudaMemsetAsync(b.p, 0, b.cap, st) == cudaSuccess ? NUTDB_OK : NUTDB_E_CUDA;
+}
 int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   if (bytes <= b.cap) return NUTDB_OK;
   if (b.p) cudaFreeHost(b.p);
@@ -1053,7 +1110,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descStatus, &c->descAgg, &c->descInc, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1126,6 +1183,11 @@ NutdbCtx* nutdb_gpu_ctx_create(int device) {
   if (ok) ok = ensure_dev(ctx, ctx->small, 256) == NUTDB_OK && ensure_host(ctx, ctx->hSmall, 256) == NUTDB_OK;
   // k_parse_fast: staged tokens (static) + operator stacks (dynamic) exceed the 48 KB default
   if (ok) ok = cudaFuncSetAttribute(k_parse_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_DYN_SMEM) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(k_lex3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Lex3Shared)) == cudaSuccess;
+  if (ok) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
+  }
   if (!ok) {
     nutdb_gpu_ctx_destroy(ctx);
     return nullptr;
@@ -1200,7 +1262,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
 
   CK(cudaEventRecord(ctx->ev[0], st));
   ENSURE_DEV(off32, 4 * ((size_t)nstmt + 1));
-  ENSURE_DEV(bitmap, 4 * (nchunks + 1));
+  ENSURE_DEV(bitmap, 4 * (nchunks + 8));
   ENSURE_DEV(stmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
   ENSURE_DEV(stmtTokBegin, 4 * ((size_t)nstmt + 1));
   ENSURE_DEV(stmtTokEnd, 4 * ((size_t)nstmt + 1));
@@ -1227,15 +1289,19 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   CK(cudaEventRecord(ctx->ev[1], st));
 
   // ---- lexer ----
+  uint32_t tok_cap = 0;
+  int attempt = 0;
+  const uint32_t n_readable = n;  // bytes of dText that may be read: bulk copies move whole 16-byte pieces below this
+run_again:
   ENSURE_DEV(puntFlag, 4 * ((size_t)nstmt + 1));
   CK(cudaMemsetAsync(ctx->puntFlag.p, 0, 4 * ((size_t)nstmt + 1), st));
-  ENSURE_DEV(firstStmt, 4 * (nchunks + 1));
-  CK(cudaMemsetAsync(ctx->firstStmt.p, 0xFF, 4 * (nchunks + 1), st));
-  CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 1), st));
-  CK(cudaMemsetAsync(dS, 0, 64, st));
+  ENSURE_DEV(firstStmt, 4 * (nchunks + 8));
+  CK(cudaMemsetAsync(ctx->firstStmt.p, 0xFF, 4 * (nchunks + 8), st));
+  CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 8), st));
+  CK(cudaMemsetAsync(dS, 0, 128, st));
   {
     const uint32_t blocks = (uint32_t)(((uint64_t)nstmt + 1 + 255) / 256);
-    LAUNCH("k_prep", k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p,
+    LAUNCH("k_prep", k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint64_t)n, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p,
                                                   (uint32_t*)ctx->firstStmt.p, dS));
   }
   uint32_t ntok = 0;
@@ -1293,163 +1359,140 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
                             (const uint32_t*)ctx->localB.p, (const uint8_t*)ctx->entB.p, (const uint4*)ctx->localC.p,
                             (const uint4*)ctx->tilePrefC.p, sink));
   } else if (n > 0) {
-    // ---- warp-cooperative lexer (lex2_core.cuh) + exact walker for the statements it flags ----
-    const size_t nwarps = (size_t)ntiles * L2_WARPS;
-    ENSURE_DEV(localA, 4 * nwarps);
-    ENSURE_DEV(localC, 16 * nwarps);
-    ENSURE_DEV(tileA, 4 * (size_t)ntiles);
-    ENSURE_DEV(tileC, 16 * (size_t)ntiles);
-    ENSURE_DEV(tilePrefC, 16 * (size_t)ntiles);
-    ENSURE_DEV(entA, ntiles);
+    // ---- single-pass lexer (lex3_core.cuh) + exact walker for the statements it flags ----
+    // Everything up to the dense node layout is issued without the host looking at a device-side count: token arrays
+    // are sized by an estimate (grow-only; an overflow is detected at the one synchronisation and the batch re-run),
+    // list lengths are read by the kernels themselves.
+    const uint32_t ntiles3 = (n + L3_TILE - 1) / L3_TILE;
+    const size_t nwin = (size_t)ntiles3 * L3_WIN;
+    ENSURE_DEV(winIdx, 4 * (nwin + 8));
+    ENSURE_DEV(winHas, 4 * (nwin + 8));
+    ENSURE_DEV(winEof, 4 * (nwin + 8));
+    {
+      const int rc = ensure_dev_zeroed(ctx, ctx->descFn, 8 * (size_t)ntiles3, st);
+      if (rc != NUTDB_OK) return rc;
+      const int rc2 = ensure_dev_zeroed(ctx, ctx->descStatus, 4 * (size_t)ntiles3, st);
+      if (rc2 != NUTDB_OK) return rc2;
+    }
+    ENSURE_DEV(descAgg, 16 * (size_t)ntiles3);
+    ENSURE_DEV(descInc, 16 * (size_t)ntiles3);
     ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
-    ENSURE_DEV(winCount, 4 * ((size_t)ntiles * (L2_TILE / 32) + 16));
-    const size_t mstride = (size_t)ntiles * (L2_TILE / 32);
-    ENSURE_DEV(winMasks, 4 * mstride * L2_NMASK + 64);
-    ENSURE_DEV(winFn, 4 * mstride + 64);
-    ENSURE_DEV(winCtx, 4 * mstride * 5 + 64);
+    ENSURE_DEV(puntCounts, 8 * ((size_t)nstmt + 1));
+    ENSURE_DEV(puntOffs, 8 * ((size_t)nstmt + 1));
+    const uint32_t nb = (nstmt + PUNT_THREADS * PUNT_PER_THREAD - 1) / (PUNT_THREADS * PUNT_PER_THREAD);
+    ENSURE_DEV(puntBlockCount, 8 * ((size_t)nb + 1));
+    ENSURE_DEV(puntBlockPref, 8 * ((size_t)nb + 1));
+    {
+      // ~0.2 tokens per byte on query logs; dense text ("((((") overflows the estimate once and grows the buffers
+      size_t want = (size_t)n / 4 + 2 * (size_t)nstmt + 4096;
+      if (want > 0xFFFFFFE0ull) want = 0xFFFFFFE0ull;
+      if (want < ctx->tok_cap_min) want = ctx->tok_cap_min;
+      ENSURE_DEV(tokType, want + 16);
+      ENSURE_DEV(tokKw, want + 16);
+      ENSURE_DEV(tokStart, 4 * (want + 4));
+      ENSURE_DEV(tokEnd, 4 * (want + 4));
+      tok_cap = (uint32_t)std::min<size_t>({(size_t)0xFFFFFFE0u, ctx->tokType.cap - 16, ctx->tokKw.cap - 16,
+                                            ctx->tokStart.cap / 4 - 4, ctx->tokEnd.cap / 4 - 4});
+    }
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
-    Lex2Out lo{nullptr, nullptr, nullptr, nullptr, 0, (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
-               (const uint32_t*)ctx->off32.p, nstmt, (uint32_t*)ctx->puntFlag.p, dS + 14,
-               (const uint32_t*)ctx->firstStmt.p, n};
-    LAUNCH("k_lex2_fn", k_lex2_fn<<<ntiles, L2_THREADS, 0, st>>>(dText, bm, n, ctx->dLex, ctx->dLex2,
-                                                                  (uint32_t*)ctx->localA.p, (uint32_t*)ctx->tileA.p,
-                                                                  (uint32_t*)ctx->winMasks.p, mstride, (uint32_t*)ctx->winFn.p));
-    const uint32_t sblocks = (ntiles + SCAN_THREADS - 1) / SCAN_THREADS;
-    const bool scan2 = ntiles > 2 * SCAN_THREADS && sblocks <= SCAN_THREADS;  // long batch: two-pass grid-wide scans
-    if (scan2) {
-      ENSURE_DEV(scanTotals, 16 * (size_t)sblocks);
-      LAUNCH("k_scan_A", k_scan2_totals<Vec8Op><<<sblocks, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, ntiles,
-                                                                                  (uint32_t*)ctx->scanTotals.p));
-      LAUNCH("k_scan_A2", k_scan2_vec8_apply<<<sblocks, SCAN_THREADS, 0, st>>>(
-                              (const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles, (const uint32_t*)ctx->scanTotals.p));
-    } else {
-      LAUNCH("k_scan_A", k_scan_vec8<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)ctx->tileA.p, (uint8_t*)ctx->entA.p, ntiles));
+    uint32_t* counters = dS + 14;  // [0] flagged statements, [1] bound on their tokens, [2] main-region tokens, [3] tile ticket
+    Lex3Desc desc{(unsigned long long*)ctx->descFn.p, (uint32_t*)ctx->descStatus.p, (uint4*)ctx->descAgg.p, (uint4*)ctx->descInc.p};
+    Lex3Out lo3{(uint8_t*)ctx->tokType.p, (uint32_t*)ctx->tokStart.p, (uint32_t*)ctx->tokEnd.p, (uint8_t*)ctx->tokKw.p, tok_cap,
+                (uint32_t*)ctx->winIdx.p, (uint32_t*)ctx->winHas.p, (uint32_t*)ctx->winEof.p, (const uint32_t*)ctx->off32.p, nstmt,
+                (uint32_t*)ctx->puntFlag.p, counters, (const uint32_t*)ctx->firstStmt.p, nullptr};
+    if (ctx->debug_tiles) {
+      ENSURE_DEV(dbgTiles, 16 * (size_t)ntiles3 + 16);
+      lo3.dbg = (uint32_t*)ctx->dbgTiles.p;
+      ctx->dbg_ntiles = ntiles3;
     }
-    LAUNCH("k_lex2_count", k_lex2_walk<false><<<ntiles, L2_THREADS, 0, st>>>(
-                               dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
-                               (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, (uint4*)ctx->tileC.p, nullptr,
-                               (uint32_t*)ctx->winCount.p, (uint32_t*)ctx->winCtx.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
-                               (const uint32_t*)ctx->winFn.p));
-    if (scan2) {
-      LAUNCH("k_scan_C", k_scan2_totals<CSumOp><<<sblocks, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, ntiles,
-                                                                                  (uint4*)ctx->scanTotals.p));
-      LAUNCH("k_scan_C2", k_scan2_apply<CSumOp><<<sblocks, SCAN_THREADS, 0, st>>>(
-                              (const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p, ntiles, (const uint4*)ctx->scanTotals.p,
-                              (uint4*)(dS + 4)));
-    } else {
-      LAUNCH("k_scan_C", k_scan_tiles<CSumOp><<<1, SCAN_THREADS, 0, st>>>((const uint4*)ctx->tileC.p, (uint4*)ctx->tilePrefC.p,
-                                                                          ntiles, (uint4*)(dS + 4)));
+    ctx->epoch = (ctx->epoch + 1u) & 0x3FFFFFFFu;
+    if (ctx->epoch == 0u) ctx->epoch = 1u;
+    {
+      const uint32_t grid = std::min<uint32_t>(ntiles3, (uint32_t)ctx->sm_count * L3_MINBLOCKS);
+      LAUNCH("k_lex3", k_lex3<<<grid, L3_THREADS, sizeof(Lex3Shared), st>>>(dText, bm, n, n_readable, ntiles3, ctx->dLex, desc,
+                                                                            ctx->epoch, lo3, dS));
     }
-    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (hS[0]) {
-      ctx->err = "statement offsets must ascend";
-      return NUTDB_E_ARG;
-    }
-    const uint32_t ntok_main = hS[4], npunt = hS[14];
-    const uint64_t extra_bound = npunt ? hS[15] : 0u;  // tokens the flagged statements can have at most
-    ctx->n_punt = npunt;
-    if ((uint64_t)ntok_main + extra_bound >= 0xFFFFFFF0ull) {
-      ctx->err = "too many tokens in one batch";
-      return NUTDB_E_ARG;
-    }
-    // The token arrays are sized with that bound, so the emit pass does not have to wait for the exact lexer's
-    // count: the (small, latency-bound) exact-lexer chain runs on a second stream beside it.
-    const size_t tok_cap = (size_t)ntok_main + extra_bound;
-    ENSURE_DEV(tokType, tok_cap + 16);
-    ENSURE_DEV(tokKw, tok_cap + 16);
-    ENSURE_DEV(tokStart, 4 * (tok_cap + 4));
-    ENSURE_DEV(tokEnd, 4 * (tok_cap + 4));
-    lo.type = (uint8_t*)ctx->tokType.p;
-    lo.start = (uint32_t*)ctx->tokStart.p;
-    lo.end = (uint32_t*)ctx->tokEnd.p;
-    lo.kw = (uint8_t*)ctx->tokKw.p;
-    lo.cap = ntok_main;
-    uint32_t n_extra = 0;
-    if (npunt > 0) {
-      cudaStream_t s2 = ctx->profiling ? st : ctx->stream2;  // (per-kernel timing serialises everything on one stream)
-      ENSURE_DEV(puntCounts, 8 * (size_t)npunt);
-      ENSURE_DEV(puntOffs, 8 * (size_t)npunt);
-      const uint32_t nb = (nstmt + PUNT_THREADS * PUNT_PER_THREAD - 1) / (PUNT_THREADS * PUNT_PER_THREAD);
-      ENSURE_DEV(puntBlockCount, 8 * (size_t)nb);
-      ENSURE_DEV(puntBlockPref, 8 * (size_t)nb);
-      if (s2 != st) {
-        CK(cudaEventRecord(ctx->evFork, st));
-        CK(cudaStreamWaitEvent(s2, ctx->evFork, 0));
-      }
-      // the flagged statements in ascending order (deterministic extra-region layout)
-      LAUNCH_ON(s2, "k_punt_count", k_punt_list<false><<<nb, PUNT_THREADS, 0, s2>>>(
-                                        (const uint32_t*)ctx->puntFlag.p, nstmt, (uint2*)ctx->puntBlockCount.p, nullptr, nullptr));
-      LAUNCH_ON(s2, "k_scan_PB", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, s2>>>(
-                                     (const uint2*)ctx->puntBlockCount.p, (uint2*)ctx->puntBlockPref.p, nb, nullptr));
-      LAUNCH_ON(s2, "k_punt_scatter", k_punt_list<true><<<nb, PUNT_THREADS, 0, s2>>>(
-                                          (const uint32_t*)ctx->puntFlag.p, nstmt, nullptr, (const uint2*)ctx->puntBlockPref.p,
-                                          (uint32_t*)ctx->puntList.p));
-      ExactSink xs{nullptr, nullptr, nullptr, nullptr, 0};
-      LAUNCH_ON(s2, "k_lex_exact_count", k_lex_exact<false><<<(npunt + 127) / 128, 128, 0, s2>>>(
-                                             dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p,
-                                             npunt, (uint2*)ctx->puntCounts.p, nullptr, 0u, xs, nullptr, nullptr, nullptr));
-      LAUNCH_ON(s2, "k_scan_P", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, s2>>>(
-                                    (const uint2*)ctx->puntCounts.p, (uint2*)ctx->puntOffs.p, npunt, (uint2*)(dS + 10)));
-      xs = ExactSink{lo.type, lo.start, lo.end, lo.kw, (uint32_t)tok_cap};
-      LAUNCH_ON(s2, "k_lex_exact_emit", k_lex_exact<true><<<(npunt + 127) / 128, 128, 0, s2>>>(
-                                            dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p,
-                                            npunt, nullptr, (const uint2*)ctx->puntOffs.p, ntok_main, xs,
-                                            (uint32_t*)ctx->stmtTokBegin.p, (uint32_t*)ctx->stmtTokEnd.p,
-                                            (uint32_t*)ctx->puntFlag.p));
-      if (s2 != st) CK(cudaEventRecord(ctx->evJoin, s2));
-    }
-    LAUNCH("k_lex2_emit", k_lex2_walk<true><<<ntiles, L2_THREADS, 0, st>>>(
-                              dText, bm, n, ctx->dLex, ctx->dLex2, (const uint32_t*)ctx->localA.p,
-                              (const uint8_t*)ctx->entA.p, (uint4*)ctx->localC.p, nullptr, (const uint4*)ctx->tilePrefC.p,
-                              (uint32_t*)ctx->winCount.p, (uint32_t*)ctx->winCtx.p, (uint32_t*)ctx->winMasks.p, mstride, lo,
-                               (const uint32_t*)ctx->winFn.p));
-    if (npunt > 0) {
-      if (!ctx->profiling) CK(cudaStreamWaitEvent(st, ctx->evJoin, 0));
-      CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      n_extra = hS[10];
-    }
-    ntok = ntok_main + n_extra;
-  } else {
-    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (hS[0]) {
-      ctx->err = "statement offsets must ascend";
-      return NUTDB_E_ARG;
-    }
+    // the flagged statements in ascending order (deterministic layout of the extra token region), then the exact walker
+    LAUNCH("k_punt_count", k_punt_list<false><<<nb, PUNT_THREADS, 0, st>>>((const uint32_t*)ctx->puntFlag.p, nstmt,
+                                                                           (uint2*)ctx->puntBlockCount.p, nullptr, nullptr, counters));
+    LAUNCH("k_scan_PB", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->puntBlockCount.p,
+                                                                          (uint2*)ctx->puntBlockPref.p, nb, nullptr));
+    LAUNCH("k_punt_scatter", k_punt_list<true><<<nb, PUNT_THREADS, 0, st>>>((const uint32_t*)ctx->puntFlag.p, nstmt, nullptr,
+                                                                            (const uint2*)ctx->puntBlockPref.p,
+                                                                            (uint32_t*)ctx->puntList.p, counters));
+    const uint32_t xgrid = std::min<uint32_t>((nstmt + 127) / 128, 4096u);
+    ExactSink xs{nullptr, nullptr, nullptr, nullptr, 0};
+    LAUNCH("k_lex_exact_count", k_lex_exact<false><<<xgrid, 128, 0, st>>>(
+                                    dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p, counters,
+                                    (uint2*)ctx->puntCounts.p, nullptr, nullptr, xs, nullptr, nullptr, nullptr));
+    LAUNCH("k_scan_P", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->puntCounts.p, (uint2*)ctx->puntOffs.p,
+                                                                         nstmt, (uint2*)(dS + 10), counters));
+    xs = ExactSink{lo3.type, lo3.start, lo3.end, lo3.kw, tok_cap};
+    LAUNCH("k_lex_exact_emit", k_lex_exact<true><<<xgrid, 128, 0, st>>>(
+                                   dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p, counters, nullptr,
+                                   (const uint2*)ctx->puntOffs.p, counters + 2, xs, (uint32_t*)ctx->stmtTokBegin.p,
+                                   (uint32_t*)ctx->stmtTokEnd.p, (uint32_t*)ctx->puntFlag.p));
   }
   CK(cudaEventRecord(ctx->ev[2], st));
 
   // ---- parser ----
   uint64_t n_node = 0, n_err = 0;
+  const bool native_lex = n > 0 && !lex_only;
   if (nstmt > 0) {
-    const size_t scratch_nodes = (size_t)ntok + (size_t)NODE_SLACK * ((size_t)nstmt + ctx->n_punt) + 4;
+    // compact-node scratch: a disjoint range of tok_count + NODE_SLACK slots per statement (see node_slot)
+    const size_t scratch_nodes = (native_lex ? (size_t)tok_cap : (size_t)ntok) + (size_t)NODE_SLACK * 2 * ((size_t)nstmt + 1) + 4;
     if (!lex_only) ENSURE_DEV(scratch, 8 * scratch_nodes);
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
-    const uint32_t pblocks = (nstmt + PARSE_THREADS - 1) / PARSE_THREADS;
     ENSURE_DEV(slowList, 4 * ((size_t)nstmt + 1));
+    StmtToks stoks{native_lex ? (const uint32_t*)ctx->winIdx.p : nullptr, (const uint32_t*)ctx->winHas.p,
+                   (const uint32_t*)ctx->winEof.p, (const uint32_t*)ctx->puntFlag.p, (const uint32_t*)ctx->stmtTokBegin.p,
+                   (const uint32_t*)ctx->stmtTokEnd.p};
     LAUNCH("k_parse_fast", k_parse_fast<<<(nstmt + FAST_THREADS - 1) / FAST_THREADS, FAST_THREADS, FAST_DYN_SMEM, st>>>(
                                dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
-                               (const uint8_t*)ctx->tokKw.p, (const uint32_t*)ctx->stmtTokBegin.p,
-                               (const uint32_t*)ctx->stmtTokEnd.p, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
+                               (const uint8_t*)ctx->tokKw.p, stoks, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
                                (uint32_t*)ctx->slowList.p, dS + 2, (const uint32_t*)ctx->puntFlag.p, lex_only ? 1 : 0,
-                               (uint32_t)min((size_t)0xFFFFFFF0u, (size_t)ntok + 16), ctx->dFast));
-    CK(cudaMemcpyAsync(hS, dS, 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const uint32_t nslow = hS[2];
-    ctx->n_slow = nslow;
-    if (nslow > 0) {
-      LAUNCH("k_parse", k_parse<<<(nslow + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
-                            dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, nslow,
+                               native_lex ? tok_cap : (uint32_t)min((size_t)0xFFFFFFF0u, (size_t)ntok + 16), ctx->dFast,
+                               native_lex ? dS + 16 : nullptr, native_lex ? dS + 10 : nullptr, dS));
+    if (!lex_only)
+      LAUNCH("k_parse", k_parse<<<(nstmt + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
+                            dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, 0u,
                             (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
                             (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar,
                             (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, nstmt,
-                            (const uint32_t*)ctx->puntFlag.p));
-      CK(cudaMemcpyAsync(hS, dS, 16, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+                            (const uint32_t*)ctx->puntFlag.p, dS + 2));
+    const uint32_t stiles = (nstmt + FIN_THREADS - 1) / FIN_THREADS;
+    ENSURE_DEV(tileS, 8 * (size_t)stiles);
+    ENSURE_DEV(tilePrefS, 8 * (size_t)stiles);
+    LAUNCH("k_stmt_sums", k_stmt_sums<<<stiles, FIN_THREADS, 0, st>>>((const NutdbStmt*)ctx->stmt.p, nstmt, (uint2*)ctx->tileS.p));
+    LAUNCH("k_scan_S", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->tileS.p, (uint2*)ctx->tilePrefS.p, stiles,
+                                                      (uint2*)(dS + 8)));
+    // ---- the one synchronisation of the call: counts the host needs to size what follows ----
+    CK(cudaMemcpyAsync(hS, dS, 128, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hS[0]) {
+      ctx->err = "statement offsets must ascend and lie inside the batch";
+      return NUTDB_E_ARG;
     }
+    if (native_lex) {
+      const uint64_t ntok_main = hS[16], n_extra = hS[10];
+      ctx->n_punt = hS[14];
+      if (ntok_main + n_extra >= 0xFFFFFFE0ull) {
+        ctx->err = "too many tokens in one batch";
+        return NUTDB_E_ARG;
+      }
+      if (ntok_main + n_extra > tok_cap) {  // the estimate was too small: grow and run the batch again
+        if (attempt >= 2) {
+          ctx->err = "token buffers kept overflowing";
+          return NUTDB_E_NOMEM;
+        }
+        ctx->tok_cap_min = (size_t)(ntok_main + n_extra) + (size_t)(ntok_main + n_extra) / 16 + 1024;
+        attempt++;
+        goto run_again;
+      }
+      ntok = (uint32_t)(ntok_main + n_extra);
+    }
+    ctx->n_slow = hS[2];
     const uint32_t nretry = hS[1];
     if (nretry > 0) {
       // deep statements: per-statement stack and node ranges sized from their token counts
@@ -1480,15 +1523,12 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
           (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
           (const uint2*)ctx->retryList.p, nretry, (const uint64_t*)ctx->retryNodeOff.p,
           (const uint64_t*)ctx->retryStackOff.p, (uint2*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p));
+      LAUNCH("k_stmt_sums", k_stmt_sums<<<stiles, FIN_THREADS, 0, st>>>((const NutdbStmt*)ctx->stmt.p, nstmt, (uint2*)ctx->tileS.p));
+      LAUNCH("k_scan_S", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->tileS.p, (uint2*)ctx->tilePrefS.p,
+                                                                           stiles, (uint2*)(dS + 8)));
+      CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
     }
-    const uint32_t stiles = (nstmt + FIN_THREADS - 1) / FIN_THREADS;
-    ENSURE_DEV(tileS, 8 * (size_t)stiles);
-    ENSURE_DEV(tilePrefS, 8 * (size_t)stiles);
-    LAUNCH("k_stmt_sums", k_stmt_sums<<<stiles, FIN_THREADS, 0, st>>>((const NutdbStmt*)ctx->stmt.p, nstmt, (uint2*)ctx->tileS.p));
-    LAUNCH("k_scan_S", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->tileS.p, (uint2*)ctx->tilePrefS.p, stiles,
-                                                      (uint2*)(dS + 8)));
-    CK(cudaMemcpyAsync(hS, dS, 64, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     n_node = hS[8];
     n_err = hS[9];
     ENSURE_DEV(nodes, 16 * (n_node + 1));
@@ -1498,6 +1538,9 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
                                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                                (const uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->nodes.p,
                                                (uint4*)ctx->errs.p));
+  } else {
+    CK(cudaMemcpyAsync(hS, dS, 128, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
   }
   CK(cudaEventRecord(ctx->ev[3], st));
 
@@ -1725,6 +1768,17 @@ int nutdb_gpu_last_timing(const NutdbCtx* ctx, float ms[5]) {
 }
 
 int nutdb_gpu_last_launches(const NutdbCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+// test hook (not in the public header): per-tile carries of the single-pass lexer's two look-back scans
+int nutdb_gpu_debug_tiles(NutdbCtx* ctx, int enable, uint32_t* out, uint32_t cap_tiles) {
+  if (!ctx) return -1;
+  ctx->debug_tiles = enable != 0;
+  if (!out || !ctx->dbgTiles.p) return 0;
+  const uint32_t nt = std::min(cap_tiles, ctx->dbg_ntiles);
+  cudaSetDevice(ctx->device);
+  if (cudaMemcpy(out, ctx->dbgTiles.p, 16 * (size_t)nt, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int)nt;
+}
 
 void nutdb_gpu_set_profiling(NutdbCtx* ctx, int on) {
   if (ctx) ctx->profiling = on != 0;

@@ -18,6 +18,10 @@ extern "C" int64_t emul_lex2(const uint8_t* text, uint32_t n, const uint64_t* of
                              uint8_t* tok_type, uint32_t* tok_start, uint32_t* tok_end, uint8_t* tok_kw, uint32_t cap,
                              uint32_t* stmt_tok_begin, uint32_t* stmt_tok_end);
 
+extern "C" int64_t emul_lex3(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_t nstmt, uint32_t seg_len,
+                             uint8_t* tok_type, uint32_t* tok_start, uint32_t* tok_end, uint8_t* tok_kw, uint32_t cap,
+                             uint32_t* stmt_tok_begin, uint32_t* stmt_tok_end);
+
 namespace {
 struct HTok {
   const uint8_t* ty;
@@ -81,7 +85,7 @@ struct HText {
 }  // namespace
 
 static int g_use_fast = 1;
-static int g_lexer = 2;          // 1 = thread-per-chunk walker, 2 = warp-cooperative lexer
+static int g_lexer = 3;          // 1 = thread-per-chunk walker, 2 = three-pass mask lexer, 3 = single-pass lexer
 static uint32_t g_seg_len = 1024;
 static uint64_t g_fast_hits = 0;
 
@@ -106,7 +110,9 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
   std::vector<uint32_t> sb(nstmt + 1), se(nstmt + 1);
   uint32_t nseg = 0;
   int64_t nt;
-  if (g_lexer == 2) {
+  if (g_lexer == 3) {
+    nt = emul_lex3(base, n, offs, nstmt, g_seg_len, tok_type, tok_start, tok_end, tok_kw, tok_cap, sb.data(), se.data());
+  } else if (g_lexer == 2) {
     nt = emul_lex2(base, n, offs, nstmt, g_seg_len, tok_type, tok_start, tok_end, tok_kw, tok_cap, sb.data(), se.data());
   } else {
     nt = emul_lex(base, n, offs, nstmt, 0, chunk, tok_type, tok_start, tok_end, tok_kw, tok_cap, sb.data(), se.data(), &nseg);
@@ -136,7 +142,7 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
       res.err_pos = res.err_a = res.err_b = res.err_c = 0;
     } else {
       // lexer 1 indexes token ranges by non-empty statement ordinal, lexer 2 by statement
-      uint32_t b = g_lexer == 2 ? sb[s] : sb[seg], e = g_lexer == 2 ? se[s] : se[seg];
+      uint32_t b = g_lexer >= 2 ? sb[s] : sb[seg], e = g_lexer >= 2 ? se[s] : se[seg];
       seg++;
       HTokAdapter tk{HTok{tok_type + b, tok_start + b, tok_end + b, tok_kw + b, e - b}};
       HNodes nd{tmp, 2 * (e - b) + 8};

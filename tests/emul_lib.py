@@ -68,7 +68,7 @@ def parse_lib():
     if "parse" not in _libs:
         so = os.path.join(_EMUL, "libemul_parse.so")
         srcs = [os.path.join(_EMUL, "emul_parse.cpp"), os.path.join(_EMUL, "emul_lex.cpp"),
-                os.path.join(_EMUL, "emul_lex2.cpp")]
+                os.path.join(_EMUL, "emul_lex2.cpp"), os.path.join(_EMUL, "emul_lex3.cpp")]
         deps = srcs + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".hpp", ".h"))]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so] + srcs)
@@ -80,18 +80,32 @@ def parse_lib():
                                        C.c_uint32, C.POINTER(C.c_uint64)]
         L.emul_fast_hits.restype = C.c_uint64
         L.emul_lex2_punts.restype = C.c_uint64
+        L.emul_lex3_punts.restype = C.c_uint64
+        L.emul_lex3_check_classes.restype = C.c_int
+        L.emul_lex3_check_classes.argtypes = [C.c_void_p]
         L.emul_set_lexer.argtypes = [C.c_int, C.c_uint32]
         _libs["parse"] = L
     return _libs["parse"]
 
 
 def set_lexer(version, seg_len=1024):
-    """1 = thread-per-chunk walker (lex_core.cuh), 2 = warp-cooperative lexer (lex2_core.cuh)."""
+    """1 = thread-per-chunk walker (lex_core.cuh), 2 = three-pass mask lexer (lex2_core.cuh), 3 = single-pass lexer
+    (lex3_core.cuh, the product's)."""
     parse_lib().emul_set_lexer(version, seg_len)
 
 
 def lex2_punts():
     return parse_lib().emul_lex2_punts()
+
+
+def lex3_punts():
+    return parse_lib().emul_lex3_punts()
+
+
+def lex3_check_classes(bytes32):
+    b = np.frombuffer(bytes(bytes32), np.uint8).copy()
+    assert len(b) == 32
+    return parse_lib().emul_lex3_check_classes(b.ctypes.data)
 
 
 def set_fast(on):

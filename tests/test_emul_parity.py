@@ -17,9 +17,9 @@ APP_D = ["SELECT * FROM table WHERE 1 = 1", "", "  ", ";", "-- c", "SELECT 1d", 
 
 @pytest.fixture(autouse=True)
 def _default_lexer():
-    E.set_lexer(2, 1024)   # the warp-cooperative lexer with the device's segment size
+    E.set_lexer(3, 1024)   # the single-pass lexer with the device's warp-block size
     yield
-    E.set_lexer(2, 1024)
+    E.set_lexer(3, 1024)
 
 
 def check(stmts, chunk=32):
@@ -37,14 +37,14 @@ def test_corpus_and_known_vectors(chunk):
     assert (got.stmt["status"][:len(CORPUS)] == 0).all()  # tests/parser_test.rs:19-34
 
 
-@pytest.mark.parametrize("seg", [1024, 32, 96])
-def test_corpus_and_known_vectors_warp_lexer(seg):
-    E.set_lexer(2, seg)
+@pytest.mark.parametrize("lexer,seg", [(3, 1024), (3, 32), (3, 96), (2, 1024), (2, 96)])
+def test_corpus_and_known_vectors_warp_lexer(lexer, seg):
+    E.set_lexer(lexer, seg)
     got = check(CORPUS + APP_D + fuzz.EXTRA_SEEDS + fuzz.SIMPLE_SEEDS)
     assert (got.stmt["status"][:len(CORPUS)] == 0).all()
 
 
-@pytest.mark.parametrize("lexer,seg", [(1, 0), (2, 64)])
+@pytest.mark.parametrize("lexer,seg", [(1, 0), (2, 64), (3, 64)])
 def test_synthetic_config_other_lexers(lexer, seg):
     E.set_lexer(lexer, seg or 1024)
     for config in (2, 3, 4):
@@ -55,14 +55,14 @@ def test_synthetic_config_other_lexers(lexer, seg):
 
 
 def test_warp_lexer_hands_only_odd_statements_to_the_exact_walker():
-    p0 = E.lex2_punts()
+    p0 = E.lex3_punts()
     for config in (2, 4):
         text, offs = W.generate(config, 128 << 10)
         E.parse_batch(text, offs)
-    assert E.lex2_punts() == p0          # valid text without hex / $n / @name: all native
+    assert E.lex3_punts() == p0          # valid text without $n / @name: all native
     text, offs = W.generate(3, 128 << 10)
     E.parse_batch(text, offs)
-    assert 0 < E.lex2_punts() - p0 < 0.06 * (len(offs) - 1)   # the ~5 % malformed statements (not all are lex errors)
+    assert 0 < E.lex3_punts() - p0 < 0.06 * (len(offs) - 1)   # the ~5 % malformed statements (not all are lex errors)
 
 
 def test_reference_panic_is_reported_not_reproduced():
@@ -97,9 +97,9 @@ def stress_seeds():
     return [bytes(text[int(offs[i]):int(offs[i + 1])]) for i in range(len(offs) - 1)][:300]
 
 
-@pytest.mark.parametrize("seed,seg", [(300, 32), (301, 64), (302, 160), (303, 1024)])
+@pytest.mark.parametrize("seed,seg", [(300, 32), (301, 64), (302, 160), (303, 1024), (304, 1024), (305, 1024), (306, 96)])
 def test_mutation_fuzz_warp_lexer(seed, seg):
-    E.set_lexer(2, seg)
+    E.set_lexer(3, seg)
     pool = [CORPUS + fuzz.EXTRA_SEEDS + fuzz.SIMPLE_SEEDS, simple_seeds(), stress_seeds()][seed % 3]
     check(fuzz.fuzz_statements(pool, 4000, seed=seed, max_mut=4))
 
