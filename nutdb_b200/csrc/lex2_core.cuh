@@ -599,8 +599,8 @@ NUTDB_HD LaneTok tok_op(Src& src, const WinTok& k, const Next& nx, uint32_t base
 }
 
 // statements that need the exact path, as far as masks can tell (token-level checks add to this)
-template <class Src>
-NUTDB_HD uint32_t win_bad_mask(Src& src, const Win& w, const WinCtx& o, uint32_t base, uint8_t prev_byte) {
+template <class Src, class Ctx>
+NUTDB_HD uint32_t win_bad_mask(Src& src, const Win& w, const Ctx& o, uint32_t base, uint8_t prev_byte) {
   const uint32_t known = w.sq | w.dq | w.bt | w.WS | w.dash | w.slash | w.L | w.D | w.DOT | w.OP | w.P;
   uint32_t bad = o.bad;
   bad |= o.ct & w.valid & ~known;              // '@' '$' '#' '?' '\\' controls, non-ASCII in code

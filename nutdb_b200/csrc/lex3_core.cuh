@@ -110,9 +110,130 @@ NUTDB_HD void classify_planes(const uint32_t p[8], uint32_t valid, Win& w, Ops& 
   w.P = (r2 & ((h01 & (b1 ^ b0)) | h10 | (h11 & l00))) | (r3 & h10 & b1) | (r5 & ((h10 & l11) | (h11 & (b1 ^ b0)))) |
         (r7 & ((h10 & l11) | (h11 & ~l11)));
   w.OP = op.LT | op.GT | op.EQ | op.BANG;
-  w.IE = 0;
-  w.NE = 0;
+  // what may follow an identifier (tokenizer/mod.rs:486-503) / a numeric literal (:506-543)
+  const uint32_t colon = r3 & h10 & l10, tilde = r7 & h11 & l10, lparen = r2 & h10 & l00, lbracket = r5 & h10 & l11,
+                 lbrace = r7 & h10 & l11;
+  const uint32_t common = w.WS | w.OP | w.dash | w.slash;
+  w.IE = common | w.DOT | (w.P & ~(colon | tilde));
+  w.NE = common | (w.P & ~(lparen | lbracket | lbrace | tilde));
   w.valid = valid;
+}
+
+// ---- concrete walk of the context automaton over one window (entry state known) ------------------------------
+// lex2's ctx_window with the literals that close in the window described by MASKS instead of a capture array, so
+// any number of them may close in one window: `openm` = opening quotes seen in this window, `close` = final closing
+// quotes, `escd` = closes of escaped literals opened here.  A close without an opening quote below it belongs to the
+// literal that was open on entry (at most one per window): its offset and escaped flag come from the carry.
+struct WinCtx3 {
+  uint32_t ct = 0;        // code bytes that may be (part of) a code token
+  uint32_t in_str = 0;    // bytes lexed inside '..' / ".."
+  uint32_t in_bt = 0;     // bytes lexed inside `..`
+  uint32_t close = 0, openm = 0, escd = 0;
+  uint32_t csq = 0, cdq = 0;  // closes by quote character (the rest of `close` are backticks)
+  uint32_t bad = 0;       // the statement containing this byte needs the exact path
+  uint32_t bad_prev = 0;  // the statement ENDING right before this (statement start) byte needs the exact path
+  uint32_t escm = 0;
+  uint8_t s_out = A_C;
+  uint8_t esc_first = 0;  // this window's escaped-flag contribution before a carried close
+  StrCarry sc;
+  uint32_t last_bnd1 = 0;  // 1 + absolute offset of the last statement start in the window, 0 if none
+};
+
+NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const Next& nx, uint8_t s_in, uint8_t prev_byte,
+                          WinCtx3& o) {
+  uint32_t todo = ev.all, consumed = 0;
+  // A newline only matters to a line comment, and a line comment needs a "--" in this window or an open one on entry
+  if (s_in != A_LC && ev.dd == 0) todo &= ~(w.nl & ~w.bnd);
+  uint8_t s = s_in;
+  // '' / "" split exactly at the window start: the closing quote was the previous window's last byte
+  const uint8_t b0q = (w.sq & 1u) ? (uint8_t)'\'' : ((w.dq & 1u) ? (uint8_t)'"' : (uint8_t)0);
+  int reopen_at = (s_in == A_C && b0q && prev_byte == b0q && !(w.bnd & 1u)) ? 0 : -1;
+  int s_pos = -1, p0 = 0;
+  uint32_t m_code = 0, m_str = 0, m_bt = 0;
+  bool open_local = false;
+  uint8_t cur_esc = 0;
+  auto assign = [&](int lo, int hi) {
+    if (hi < lo) return;
+    const uint32_t r = bits_range(lo, hi);
+    if (s <= A_CX) m_code |= r;
+    else if (s == A_SQ || s == A_DQ) {
+      m_str |= r;
+      if (w.bs & r) cur_esc = 1;
+    } else if (s == A_BT) m_bt |= r;
+  };
+  while (todo) {
+    const int e = ctz32(todo);
+    todo &= todo - 1;
+    const uint32_t bit = 1u << e;
+    if (w.bnd & bit) {
+      assign(p0, e - 1);
+      const uint8_t sa = (e == s_pos + 1) ? s : decay(s);
+      if (sa == A_SQ || sa == A_DQ || sa == A_BT || sa == A_BC0 || sa == A_BC) o.bad_prev |= bit;
+      s = A_C;
+      s_pos = -100;
+      reopen_at = -1;
+      cur_esc = 0;
+      open_local = true;  // nothing can be carried into a new statement
+      o.last_bnd1 = base + (uint32_t)e + 1u;
+      p0 = e;
+      if (!(ev.own & bit)) continue;
+    }
+    assign(p0, e);
+    p0 = e + 1;
+    const uint8_t a0 = (e == s_pos + 1) ? s : decay(s);
+    const uint8_t t = event_type(w, ev, e);
+    const uint8_t a1 = a_next(a0, t);
+    if (a0 <= A_CX) {
+      if (t == EV_SQ || t == EV_DQ || t == EV_BT) {
+        if (t != EV_BT && reopen_at == e) {
+          cur_esc = 1;  // second half of '' / ""
+        } else {
+          open_local = true;
+          cur_esc = 0;
+          o.openm |= bit;
+          o.sc.has_open = 1;
+          o.sc.open_pos = base + (uint32_t)e;
+        }
+      } else if ((t == EV_DD || t == EV_SLST) && a0 == A_C) {
+        consumed |= bit;  // second byte of "--" / "/*": not a token
+      }
+    } else if ((a0 == A_SQ && t == EV_SQ) || (a0 == A_DQ && t == EV_DQ)) {
+      const uint32_t same = t == EV_SQ ? w.sq : w.dq;
+      bool twin;
+      if (e < 31) twin = ((same >> (e + 1)) & 1u) && !((w.bnd >> (e + 1)) & 1u);
+      else twin = !nx.bnd && nx.byte == (t == EV_SQ ? '\'' : '"');
+      if (twin) {
+        reopen_at = e + 1;
+      } else {
+        o.close |= bit;
+        if (t == EV_SQ) o.csq |= bit;
+        else o.cdq |= bit;
+        if (cur_esc) {
+          if (open_local) o.escd |= bit;
+          else o.esc_first = 1;
+        }
+        cur_esc = 0;
+      }
+    } else if (a0 == A_BT && t == EV_BT) {
+      o.close |= bit;
+      // `` : Incomplete (tokenizer/mod.rs:323): the previous byte is the opening backtick
+      if (e > 0 ? ((w.bt >> (e - 1)) & 1u) != 0 : prev_byte == '`') o.bad |= bit;
+      cur_esc = 0;
+    }
+    s = a1;
+    s_pos = e;
+  }
+  assign(p0, 31);
+  if (s_pos < 31) s = decay(s);
+  o.s_out = s;
+  o.sc.esc = cur_esc;
+  o.ct = m_code & ~consumed & w.valid;
+  o.in_str = m_str & w.valid;
+  o.in_bt = m_bt & w.valid;
+}
+// the first literal that closes in the window was opened in an earlier one
+NUTDB_HD bool has_carried_close(const WinCtx3& o) {
+  return o.close != 0u && (o.openm & ((o.close & (0u - o.close)) - 1u)) == 0u;
 }
 
 // ---- code tokens by mask arithmetic ------------------------------------------------------------------------
@@ -125,7 +246,7 @@ struct TokMasks {
   uint32_t bad = 0;    // the statement containing this byte needs the exact lexer
   uint32_t bad_prev = 0;  // ... and so does the statement that ends right before this byte
   uint64_t TS = 0;     // first bytes of code tokens over [previous window | this window]
-  uint64_t L64 = 0, DOT64 = 0;
+  uint64_t L64 = 0, DOT64 = 0, N64 = 0;  // letters, dots, digits | dots (restricted to code bytes), same 64 positions
 };
 
 NUTDB_HD int ctz64(uint64_t x) {
@@ -153,7 +274,8 @@ NUTDB_HD uint8_t pair_type(uint8_t c0, uint8_t c1) {
 
 // prev / prev2: the two bytes in front of the window (0 if none); they only matter for operator pairs, whose bytes
 // cannot be the tail of a literal or comment, so their raw values are enough.
-NUTDB_HD void win_tokens3(const Win& w, const Ops& op, const WinCtx& o, const Hist3& h, const Next& nx, uint8_t prev,
+// nx.cls: bit 0 = the next window's first byte may follow an identifier, bit 1 = ... a numeric literal.
+NUTDB_HD void win_tokens3(const Win& w, const Ops& op, const WinCtx3& o, const Hist3& h, const Next& nx, uint8_t prev,
                           uint8_t prev2, TokMasks& m) {
   const uint32_t ct = o.ct;
   const uint32_t cL = w.L & ct, cD = w.D & ct, cDOT = w.DOT & ct;
@@ -220,8 +342,16 @@ NUTDB_HD void win_tokens3(const Win& w, const Ops& op, const WinCtx& o, const Hi
   m.TS = TSw | ((uint64_t)(simple | (cOP & ~pair2)) << 32) | (((pair2 & 1u) && !pm1) ? (1ull << 31) : 0ull);
   m.L64 = L64;
   m.DOT64 = DOT64;
-  // statements for the exact lexer, as far as masks can tell (token_finish3 adds the end-of-token checks)
+  m.N64 = D64 | DOT64;
+  // statements for the exact lexer.  End-of-token checks: an identifier must be followed by one of the characters of
+  // tokenizer/mod.rs:486-503, a numeric literal (a digit-led run -- a plain hex literal has no such check, but one
+  // followed by an odd character is rare enough for the exact lexer -- or "12.") by one of :506-543.
+  const uint32_t okI = ((w.IE >> 1) | ((uint32_t)(nx.cls & 1u) << 31)) | nbnd;
+  const uint32_t okN = ((w.NE >> 1) | ((uint32_t)((nx.cls >> 1) & 1u) << 31)) | nbnd;
+  const uint32_t dledhi = (uint32_t)(dled >> 32);
   uint32_t bad = overlap | (cBANG & ~first_of_pair);
+  bad |= E & ~dledhi & ~okI;
+  bad |= ((has_word & dledhi) | (has_dot & (uint32_t)(joinL >> 32))) & ~okN;
   // a token that began before the look-back window
   if (((h.L | h.D | h.DOT) == 0xFFFFFFFFu) && !(w.bnd & 1u) && ((cL | cD | cDOT) & 1u)) bad |= 1u;
   m.bad = bad;
@@ -229,54 +359,73 @@ NUTDB_HD void win_tokens3(const Win& w, const Ops& op, const WinCtx& o, const Hi
 }
 
 // ---- token records -----------------------------------------------------------------------------------------
-// flags of a record: [0:2) number of dots in the token (saturated), [2] a letter in the token, [3:6) explicit type
-enum : uint32_t { R3_CODE = 0, R3_RAW = 1, R3_ESQ = 2, R3_EDQ = 3, R3_BT = 4, R3_EOF = 5, R3_FILL = 6 };
-#define NUTDB_R3_FLAG_SHIFT 14   // word 1 of a record = end offset relative to the tile (1..8192) | flags << 14
+// word 0 of a record = first byte of the token (absolute); word 1 = end offset relative to the tile (1..8192) |
+// kind << 14 | number of dots (saturated at 2) << 17 | a letter in the token << 19
+enum : uint32_t {
+  R3_GENERIC = 0,  // type follows from the first byte (words, one digit, punctuation, operators)
+  R3_RAW = 1, R3_ESQ = 2, R3_EDQ = 3, R3_BT = 4, R3_EOF = 5, R3_FILL = 6,
+  R3_NUM = 7       // digit- or dot-led token of more than one byte
+};
+#define NUTDB_R3_KIND_SHIFT 14
 
-// Rec: void operator()(uint32_t index, uint32_t start_abs, uint32_t end_abs, uint32_t flags)
-// index = index of the window's first token; returns the index after its last one.
+// Rec: void operator()(uint32_t index, uint32_t start_abs, uint32_t end_abs, uint32_t flags /* kind | dots << 3 | letter << 5 */)
+// index = index of the window's first token.
 template <class Rec>
-NUTDB_HD uint32_t win_records3(const WinCtx& o, const TokMasks& m, uint32_t base, const StrCarry& sc_in, uint32_t index, Rec& rec) {
-  uint32_t todo = m.has | m.eofm, c = 0;
+NUTDB_HD void win_records3(const WinCtx3& o, const TokMasks& m, uint32_t base, const StrCarry& sc_in, uint32_t index, Rec& rec) {
+  const uint32_t TShi = (uint32_t)(m.TS >> 32), Nhi = (uint32_t)(m.N64 >> 32);
+  uint32_t todo = m.has, n = 0;
   while (todo) {
     const int i = ctz32(todo);
     todo &= todo - 1;
     const uint32_t bit = 1u << i, end = base + (uint32_t)i + 1u;
-    if (m.has & bit) {
-      if (o.close & bit) {
-        if (c < o.ncap) {  // a literal / quoted identifier closes here (ctx_window recorded it)
-          const uint32_t cw = (o.capw[c >> 1] >> (16u * (c & 1u))) & 0xFFFFu;
-          const uint32_t code = (cw >> 11) & 3u;
-          uint32_t start = base + ((cw >> 5) & 31u) + 1u, kind;
-          if ((cw >> 10) & 1u) {  // opened in an earlier window: offset and escaped flag come from the carry
-            start = sc_in.open_pos + 1u;
-            const bool escd = (sc_in.esc | o.esc_first) != 0;
-            kind = code == 3 ? (uint32_t)R3_BT : (escd ? (code == 1 ? (uint32_t)R3_ESQ : (uint32_t)R3_EDQ) : (uint32_t)R3_RAW);
-          } else {
-            kind = code == 0 ? (uint32_t)R3_RAW : code == 1 ? (uint32_t)R3_ESQ : code == 2 ? (uint32_t)R3_EDQ : (uint32_t)R3_BT;
-          }
-          rec(index, start, end, kind << 3);
-          c++;
-        } else {  // beyond the capture array: the statement is flagged; a fixed filler keeps the arrays reproducible
-          rec(index, 0u, end, (uint32_t)R3_FILL << 3);
-        }
-      } else {
-        const int p = 32 + i;
-        const uint64_t below = p >= 63 ? ~0ull : ((2ull << p) - 1ull);
-        const uint64_t ts = m.TS & below;
-        const int st = ts ? 63 - clz64(ts) : p;
-        const uint64_t span = below & ~((1ull << st) - 1ull);
-        const int nd = popc64(m.DOT64 & span);
-        rec(index, base + (uint32_t)st - 32u, end, (uint32_t)(nd > 2 ? 2 : nd) | ((m.L64 & span) ? 4u : 0u));
+    const uint32_t idx = index + n + (uint32_t)popc32(m.eofm & (bit - 1u));  // EOF tokens of statements that ended before
+    n++;
+    if (o.close & bit) {  // a literal / quoted identifier closes here
+      const uint32_t opens = o.openm & (bit - 1u);
+      uint32_t start;
+      bool escd;
+      if (opens) {
+        start = base + (uint32_t)(31 - clz32(opens)) + 1u;
+        escd = (o.escd & bit) != 0;
+      } else {  // opened in an earlier window: offset and escaped flag come from the carry
+        start = sc_in.open_pos + 1u;
+        escd = (sc_in.esc | o.esc_first) != 0;
       }
-      index++;
+      const uint32_t kind = (o.csq & bit) ? (escd ? (uint32_t)R3_ESQ : (uint32_t)R3_RAW)
+                            : (o.cdq & bit) ? (escd ? (uint32_t)R3_EDQ : (uint32_t)R3_RAW) : (uint32_t)R3_BT;
+      rec(idx, start, end, kind);
+      continue;
     }
-    if (m.eofm & bit) {
-      rec(index, end, end, (uint32_t)R3_EOF << 3);
-      index++;
+    const uint32_t incl = i >= 31 ? 0xFFFFFFFFu : ((2u << i) - 1u);
+    const uint32_t ts = TShi & incl;
+    if (ts) {  // the token starts in this window
+      const int st = 31 - clz32(ts);
+      uint32_t flags = R3_GENERIC;
+      if (((Nhi >> st) & 1u) && st < i) {
+        const uint32_t span = incl & ~((1u << st) - 1u);
+        const int nd = popc32((uint32_t)(m.DOT64 >> 32) & span);
+        flags = (uint32_t)R3_NUM | ((uint32_t)(nd > 2 ? 2 : nd) << 3) | (((uint32_t)(m.L64 >> 32) & span) ? 32u : 0u);
+      }
+      rec(idx, base + (uint32_t)st, end, flags);
+    } else {  // ... in the previous one
+      const uint32_t tl = (uint32_t)m.TS;
+      const int st = tl ? 31 - clz32(tl) : 31;
+      const uint64_t span = (((uint64_t)incl << 32) | 0xFFFFFFFFull) & ~((1ull << st) - 1ull);
+      uint32_t flags = R3_GENERIC;
+      if ((m.N64 >> st) & 1ull) {
+        const int nd = popc64(m.DOT64 & span);
+        flags = (uint32_t)R3_NUM | ((uint32_t)(nd > 2 ? 2 : nd) << 3) | ((m.L64 & span) ? 32u : 0u);
+      }
+      rec(idx, base - 32u + (uint32_t)st, end, flags);
     }
   }
-  return index;
+  todo = m.eofm;  // the EOF token of a statement follows the token (if any) that ends at the statement's last byte
+  while (todo) {
+    const int i = ctz32(todo);
+    todo &= todo - 1;
+    const uint32_t bit = 1u << i, end = base + (uint32_t)i + 1u;
+    rec(index + (uint32_t)popc32(m.has & (bit | (bit - 1u))) + (uint32_t)popc32(m.eofm & (bit - 1u)), end, end, (uint32_t)R3_EOF);
+  }
 }
 
 // ---- one thread per token ----------------------------------------------------------------------------------
@@ -284,87 +433,68 @@ struct Tok3 {
   uint8_t type = NUTDB_TT_POISON, kw = 0, punt = 0;
   uint32_t start = 0, end = 0;  // statement relative
 };
-// Src: uint8_t byte(abs), const uint8_t* span(abs, len).  sst = first byte of the token's statement; next_bnd = the
-// byte after the token starts another statement (or is the end of the batch).
+// Src: uint8_t at(abs) for bytes of the token itself (always staged), const uint8_t* span(abs, len).
+// sst = first byte of the token's statement.
 template <class Src>
-NUTDB_HD void token_finish3(const LexTables& T, Src& src, uint32_t start, uint32_t end, uint32_t flags, uint32_t sst,
-                            bool next_bnd, Tok3& r) {
-  const uint32_t kind = (flags >> 3) & 7u;
-  if (kind != R3_CODE) {
-    if (kind == R3_EOF) {
-      r.type = NUTDB_TT_EOF;
-      r.start = r.end = end - sst;
-    } else if (kind == R3_FILL) {
-      r.type = NUTDB_TT_POISON;
-    } else {  // payload between the quotes
-      r.type = kind == R3_RAW ? (uint8_t)NUTDB_TT_RawStringLiteral
-               : kind == R3_ESQ ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral
-               : kind == R3_EDQ ? (uint8_t)NUTDB_TT_EscapedDQStringLiteral : (uint8_t)NUTDB_TT_DelimitedIdentifier;
-      r.start = start - sst;
-      r.end = end - 1u - sst;
-    }
-    return;
-  }
-  const uint32_t len = end - start, ndots = flags & 3u;
-  const bool letter = (flags & 4u) != 0;
-  const uint8_t b0 = src.byte(start);
-  const uint8_t nb = next_bnd ? (uint8_t)0 : src.byte(end);
-  const bool end_ident = next_bnd || (T.prop[nb] & PR_IDENT_END);  // tokenizer/mod.rs:486-503
-  const bool end_num = next_bnd || (T.prop[nb] & PR_NUM_END);      // tokenizer/mod.rs:506-543
+NUTDB_HD void token_finish3(const LexTables& T, Src& src, uint32_t start, uint32_t end, uint32_t flags, uint32_t sst, Tok3& r) {
+  const uint32_t kind = flags & 7u, len = end - start;
   r.start = start - sst;
   r.end = end - sst;
-  const uint8_t pr = T.prop[b0];
-  if (pr & PR_DIGIT) {
-    if (letter) {
-      // "0" x|X hex-digits* (tokenizer/mod.rs:201-208): the span is the digits, there is no end-of-token check.
-      // Only the plain form is lexed here; "0x1G", "0x1.5", "1x" ... go to the exact lexer.
-      bool ok = ndots == 0 && len >= 2 && b0 == '0' && (src.byte(start + 1u) | 0x20) == 'x';
-      for (uint32_t q = start + 2u; ok && q < end; q++) ok = (T.prop[src.byte(q)] & PR_HEX) != 0;
+  if (kind == R3_GENERIC) {
+    const uint8_t b0 = src.at(start);
+    uint8_t t = T.tt0[b0];
+    if (t == NUTDB_TT_KeywordOrIdentifier) {  // tokenizer/mod.rs:262-282
+      if (len >= 2 && len <= 10) {
+        const uint8_t* wp = src.span(start, len);
+        if (wp) {
+          uint32_t w0, w1, w2;
+          load_word12(wp, len, w0, w1, w2);
+          r.kw = keyword_lookup_words(T, len, w0, w1, w2);
+        } else {
+          Src& sr = src;
+          r.kw = keyword_lookup(T, len, [&sr, start](uint32_t q) { return sr.at(start + q); });
+        }
+      }
+    } else if (t == NUTDB_TT_IntegerLiteral) {
+      r.kw = 1;  // one digit
+    } else if (len == 2) {  // the only other generic tokens of two bytes: <= >= != <> << >>
+      t = pair_type(b0, src.at(start + 1u));
+      if (!t) t = NUTDB_TT_POISON;
+    } else if (t == 0xFF) {
+      t = NUTDB_TT_POISON;  // (a lone '!': its statement has been flagged by win_tokens3)
+    }
+    r.type = t;
+  } else if (kind == R3_NUM) {
+    const uint32_t ndots = (flags >> 3) & 3u;
+    const uint8_t b0 = src.at(start);
+    if (flags & 32u) {
+      // "0" x|X hex-digits* (tokenizer/mod.rs:201-208): the span is the digits.  Only the plain form is lexed here;
+      // "0x1G", "0x1.5", "1x", ".0x1" ... go to the exact lexer.
+      bool ok = ndots == 0 && b0 == '0' && (src.at(start + 1u) | 0x20) == 'x';
+      for (uint32_t q = start + 2u; ok && q < end; q++) ok = (T.prop[src.at(q)] & PR_HEX) != 0;
       if (!ok) { r.punt = 1; return; }
       r.type = NUTDB_TT_HexLiteral;
       r.start += 2u;
       r.kw = (uint8_t)(len - 2u > 255u ? 255u : len - 2u);
     } else if (ndots == 0) {  // tokenizer/mod.rs:196-238
-      if (!end_num) { r.punt = 1; return; }
       r.type = NUTDB_TT_IntegerLiteral;
       r.kw = (uint8_t)(len > 255u ? 255u : len);
-    } else {  // digits '.' digits* (tokenizer/mod.rs:246-258)
-      if (ndots != 1 || !end_num) { r.punt = 1; return; }
+    } else if (ndots == 1) {  // digits '.' digits* | '.' digits (tokenizer/mod.rs:246-258)
       r.type = NUTDB_TT_FloatLiteral;
-    }
-  } else if (pr & PR_WORD) {  // identifier / keyword (tokenizer/mod.rs:262-282)
-    if (!end_ident) { r.punt = 1; return; }
-    r.type = NUTDB_TT_KeywordOrIdentifier;
-    if (len >= 2 && len <= 10) {
-      const uint8_t* wp = src.span(start, len);
-      if (wp) {
-        uint32_t w0, w1, w2;
-        load_word12(wp, len, w0, w1, w2);
-        r.kw = keyword_lookup_words(T, len, w0, w1, w2);
-      } else {
-        Src& sr = src;
-        r.kw = keyword_lookup(T, len, [&sr, start](uint32_t q) { return sr.byte(start + q); });
-      }
-    }
-  } else if (b0 == '.') {
-    if (len == 1) {
-      r.type = NUTDB_TT_Dot;  // no end check (tokenizer/mod.rs:248-250)
     } else {
-      if (letter || ndots != 1 || !end_num) { r.punt = 1; return; }
-      r.type = NUTDB_TT_FloatLiteral;
+      r.punt = 1;
     }
-  } else if (len == 1) {
-    const uint8_t t = b0 == '-' ? (uint8_t)NUTDB_TT_Minus
-                      : b0 == '/' ? (uint8_t)NUTDB_TT_Div
-                      : b0 == '<' ? (uint8_t)NUTDB_TT_Lt
-                      : b0 == '>' ? (uint8_t)NUTDB_TT_Gt
-                      : b0 == '=' ? (uint8_t)NUTDB_TT_Eq : T.single_tt[b0];
-    if (t == 0xFF) { r.punt = 1; return; }
-    r.type = t;
-  } else {
-    const uint8_t t = len == 2 ? pair_type(b0, src.byte(start + 1u)) : (uint8_t)0;
-    if (!t) { r.punt = 1; return; }
-    r.type = t;
+  } else if (kind == R3_EOF) {
+    r.type = NUTDB_TT_EOF;
+    r.start = r.end = end - sst;
+  } else if (kind == R3_FILL) {
+    r.type = NUTDB_TT_POISON;
+    r.start = r.end = 0;
+  } else {  // payload between the quotes
+    r.type = kind == R3_RAW ? (uint8_t)NUTDB_TT_RawStringLiteral
+             : kind == R3_ESQ ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral
+             : kind == R3_EDQ ? (uint8_t)NUTDB_TT_EscapedDQStringLiteral : (uint8_t)NUTDB_TT_DelimitedIdentifier;
+    r.end = end - 1u - sst;
   }
 }
 

@@ -154,6 +154,7 @@ struct LexTables {
   uint8_t base_cls[256];   // class ignoring the pair rule
   uint8_t prop[256];
   uint8_t single_tt[256];  // token type of single-char tokens, 0xFF otherwise
+  uint8_t tt0[256];        // token type by FIRST byte: words 0, digits Integer, '.', '-', '/', '<', '>', '=', single_tt; else 0xFF
   uint32_t a_row[EV_COUNT][2];   // transition function of each event, one state per BYTE (lo: states 0-3, hi: 4-7)
   uint32_t b_row[CL_COUNT][2];
   uint32_t kw_mul[4];            // perfect hash multipliers

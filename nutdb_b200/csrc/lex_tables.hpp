@@ -77,6 +77,14 @@ inline void build_lex_tables(LexTables& T) {
     T.base_cls[i] = cl;
     T.prop[i] = pr;
     T.single_tt[i] = tt;
+    T.tt0[i] = (pr & PR_DIGIT) ? (uint8_t)NUTDB_TT_IntegerLiteral
+               : (pr & PR_WORD) ? (uint8_t)NUTDB_TT_KeywordOrIdentifier
+               : c == '.' ? (uint8_t)NUTDB_TT_Dot
+               : c == '-' ? (uint8_t)NUTDB_TT_Minus
+               : c == '/' ? (uint8_t)NUTDB_TT_Div
+               : c == '<' ? (uint8_t)NUTDB_TT_Lt
+               : c == '>' ? (uint8_t)NUTDB_TT_Gt
+               : c == '=' ? (uint8_t)NUTDB_TT_Eq : tt;
   }
   for (int ev = 0; ev < EV_COUNT; ev++) {
     uint32_t lo = 0, hi = 0;

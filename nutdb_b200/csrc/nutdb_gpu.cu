@@ -994,10 +994,11 @@ struct NutdbCtx {
   size_t tok_cap_min = 0;   // token capacity a previous batch turned out to need
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
-  bool debug_tiles = false;
+  bool debug_tiles = false, debug_timing = false;
+  DevBuf dbgTim;
   uint32_t dbg_ntiles = 0;
   DevBuf dbgTiles;
-  DevBuf winIdx, winHas, winEof, descFn, descStatus, descAgg, descInc, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
+  DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
@@ -1110,7 +1111,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descStatus, &c->descAgg, &c->descInc, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1368,14 +1369,10 @@ run_again:
     ENSURE_DEV(winIdx, 4 * (nwin + 8));
     ENSURE_DEV(winHas, 4 * (nwin + 8));
     ENSURE_DEV(winEof, 4 * (nwin + 8));
-    {
-      const int rc = ensure_dev_zeroed(ctx, ctx->descFn, 8 * (size_t)ntiles3, st);
+    for (DevBuf* d : {&ctx->descFn, &ctx->descA, &ctx->descI, &ctx->descB, &ctx->descC}) {  // (fn, counts, their prefix, statement start, open quote)  // look-back descriptors: tags start at epoch 0
+      const int rc = ensure_dev_zeroed(ctx, *d, 8 * (size_t)ntiles3, st);
       if (rc != NUTDB_OK) return rc;
-      const int rc2 = ensure_dev_zeroed(ctx, ctx->descStatus, 4 * (size_t)ntiles3, st);
-      if (rc2 != NUTDB_OK) return rc2;
     }
-    ENSURE_DEV(descAgg, 16 * (size_t)ntiles3);
-    ENSURE_DEV(descInc, 16 * (size_t)ntiles3);
     ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
     ENSURE_DEV(puntCounts, 8 * ((size_t)nstmt + 1));
     ENSURE_DEV(puntOffs, 8 * ((size_t)nstmt + 1));
@@ -1396,19 +1393,30 @@ run_again:
     }
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
     uint32_t* counters = dS + 14;  // [0] flagged statements, [1] bound on their tokens, [2] main-region tokens, [3] tile ticket
-    Lex3Desc desc{(unsigned long long*)ctx->descFn.p, (uint32_t*)ctx->descStatus.p, (uint4*)ctx->descAgg.p, (uint4*)ctx->descInc.p};
+    Lex3Desc desc{(unsigned long long*)ctx->descFn.p, (unsigned long long*)ctx->descA.p, (unsigned long long*)ctx->descI.p, (unsigned long long*)ctx->descB.p,
+                  (unsigned long long*)ctx->descC.p};
     Lex3Out lo3{(uint8_t*)ctx->tokType.p, (uint32_t*)ctx->tokStart.p, (uint32_t*)ctx->tokEnd.p, (uint8_t*)ctx->tokKw.p, tok_cap,
                 (uint32_t*)ctx->winIdx.p, (uint32_t*)ctx->winHas.p, (uint32_t*)ctx->winEof.p, (const uint32_t*)ctx->off32.p, nstmt,
-                (uint32_t*)ctx->puntFlag.p, counters, (const uint32_t*)ctx->firstStmt.p, nullptr};
+                (uint32_t*)ctx->puntFlag.p, counters, (const uint32_t*)ctx->firstStmt.p, nullptr, nullptr};
     if (ctx->debug_tiles) {
       ENSURE_DEV(dbgTiles, 16 * (size_t)ntiles3 + 16);
       lo3.dbg = (uint32_t*)ctx->dbgTiles.p;
       ctx->dbg_ntiles = ntiles3;
     }
-    ctx->epoch = (ctx->epoch + 1u) & 0x3FFFFFFFu;
+    if (ctx->debug_timing) {
+      ENSURE_DEV(dbgTim, 24 * 8 * (size_t)ntiles3 + 16);
+      CK(cudaMemsetAsync(ctx->dbgTim.p, 0, 24 * 8 * (size_t)ntiles3, st));
+      lo3.tim = (unsigned long long*)ctx->dbgTim.p;
+      ctx->dbg_ntiles = ntiles3;
+    }
+    ctx->epoch = (ctx->epoch + 1u) & 0x0FFFFFFFu;  // (the tags hold 28 bits of it)
     if (ctx->epoch == 0u) ctx->epoch = 1u;
     {
-      const uint32_t grid = std::min<uint32_t>(ntiles3, (uint32_t)ctx->sm_count * L3_MINBLOCKS);
+#ifndef L3_GRID_PER_SM
+#define L3_GRID_PER_SM L3_MINBLOCKS
+#endif
+      // (+ block 0, the scanner of the token counts)
+      const uint32_t grid = 1u + std::min<uint32_t>(ntiles3, (uint32_t)ctx->sm_count * L3_GRID_PER_SM);
       LAUNCH("k_lex3", k_lex3<<<grid, L3_THREADS, sizeof(Lex3Shared), st>>>(dText, bm, n, n_readable, ntiles3, ctx->dLex, desc,
                                                                             ctx->epoch, lo3, dS));
     }
@@ -1768,6 +1776,17 @@ int nutdb_gpu_last_timing(const NutdbCtx* ctx, float ms[5]) {
 }
 
 int nutdb_gpu_last_launches(const NutdbCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+// profiling hook (not in the public header): 24 clock64 stamps per tile of the last k_lex3 launch
+int nutdb_gpu_debug_timing(NutdbCtx* ctx, int enable, unsigned long long* out, uint32_t cap_tiles) {
+  if (!ctx) return -1;
+  ctx->debug_timing = enable != 0;
+  if (!out || !ctx->dbgTim.p) return 0;
+  const uint32_t nt = std::min(cap_tiles, ctx->dbg_ntiles);
+  cudaSetDevice(ctx->device);
+  if (cudaMemcpy(out, ctx->dbgTim.p, 24 * 8 * (size_t)nt, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int)nt;
+}
 
 // test hook (not in the public header): per-tile carries of the single-pass lexer's two look-back scans
 int nutdb_gpu_debug_tiles(NutdbCtx* ctx, int enable, uint32_t* out, uint32_t cap_tiles) {

@@ -26,6 +26,7 @@ struct Env3 {
 struct HSrc3 {
   const Env3& e;
   uint8_t byte(uint32_t p) const { return e.byte(p); }
+  uint8_t at(uint32_t p) const { return e.byte(p); }
   const uint8_t* span(uint32_t p, uint32_t len) const {
     return (p / 8192 == (p + len - 1) / 8192 && p + len <= e.n) ? e.text + p : nullptr;  // like the device: inside one tile
   }
@@ -169,7 +170,8 @@ int64_t emul_lex3(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
     } else {
       nx.byte = e.byte(base + 32);
       nx.bnd = e.bnd(base + 32) ? 1 : 0;
-      nx.cls = 0;
+      const uint8_t pr = T.prop[nx.byte];
+      nx.cls = (uint16_t)(((pr & PR_IDENT_END) ? 1u : 0u) | ((pr & PR_NUM_END) ? 2u : 0u));
     }
     uint8_t prev_byte = 0, prev2_byte = 0, esc_in = 0;
     if (base == blk) {
@@ -196,8 +198,8 @@ int64_t emul_lex3(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
     uint32_t fnv = NUTDB_VEC8_ID;
     if (live)
       fnv = ev.all ? ctx_window_fn(T, w, ev, NUTDB_VEC8_ID) : vec8_then_row(NUTDB_VEC8_ID, T.a_row[EV_OTHER][0], T.a_row[EV_OTHER][1]);
-    WinCtx o;
-    if (live) ctx_window(w, ev, base, nx, s_state, prev_byte, o);
+    WinCtx3 o;
+    if (live) ctx_window3(w, ev, base, nx, s_state, prev_byte, o);
     o.escm = escm;
     if (live && base + 32 <= n && (uint8_t)vec8_apply(fnv, s_state) != o.s_out) return -2;
     Hist3 h;
@@ -243,9 +245,8 @@ int64_t emul_lex3(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
         if (recs.size() <= idx) recs.resize(idx + 1);
         recs[idx] = Rec3{start_abs, end_abs, flags};
       };
-      const uint32_t after = win_records3(o, m, base, sc, count, rec);
-      if (after != count + (uint32_t)popc32(m.has) + (uint32_t)popc32(m.eofm)) return -3;
-      count = after;
+      win_records3(o, m, base, sc, count, rec);
+      count += (uint32_t)popc32(m.has) + (uint32_t)popc32(m.eofm);
       sc = str_then(sc, o.sc);
       if (o.last_bnd1) stmt_start1 = o.last_bnd1;
       hprev.L = w.L & o.ct;
@@ -265,9 +266,8 @@ int64_t emul_lex3(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
     const uint32_t last = r.end - 1u, wv = last >> 5, i = last & 31u;
     const uint32_t bb = win_bnd[wv] & (i >= 31u ? 0xFFFFFFFFu : ((2u << i) - 1u));
     const uint32_t sst = bb ? 32u * wv + (uint32_t)(31 - clz32(bb)) : sst_in[wv];
-    const bool next_bnd = i < 31u ? ((win_bnd[wv] >> (i + 1u)) & 1u) != 0 : (r.end >= n || (win_bnd[wv + 1] & 1u) != 0);
     Tok3 tk;
-    token_finish3(T, src, r.start, r.end, r.flags, sst, next_bnd, tk);
+    token_finish3(T, src, r.start, r.end, r.flags, sst, tk);
     if (tk.punt) {
       punt_stmt_at(sst);
       tk.type = NUTDB_TT_POISON;
