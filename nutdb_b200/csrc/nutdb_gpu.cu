@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_D(const uint8_t* __restrict
 #include "lex2_core.cuh"
 #include "lex2_kernels.cuh"
 #include "lex3_kernels.cuh"
+#include "lex4_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------
 // parser kernels
@@ -600,22 +601,35 @@ struct StmtToks {
   const uint32_t* punt;            // per statement: 0, or 1 + position in the exact lexer's region
   const uint32_t* x_begin;         // per statement, valid where punt != 0
   const uint32_t* x_end;
-  __device__ __forceinline__ uint32_t index_at(uint32_t pos) const {
-    const uint32_t w = pos >> 5, b = pos & 31u;
-    uint32_t r = win_idx[w];
+  const uint32_t* cut_stmt;        // first statement of each lexer range (k_cuts); a range's windows sit `range` slots up
+  const uint32_t* nranges;
+  __device__ __forceinline__ uint32_t range_of(uint32_t s) const {
+    uint32_t lo = 0, hi = *nranges;  // last range with cut_stmt[r] <= s
+    while (hi - lo > 1u) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (cut_stmt[mid] <= s) lo = mid;
+      else hi = mid;
+    }
+    return lo;
+  }
+  __device__ __forceinline__ uint32_t index_at(uint32_t pos, uint32_t r) const {
+    const size_t w = (size_t)(pos >> 5) + r;
+    const uint32_t b = pos & 31u;
+    uint32_t x = win_idx[w];
     if (b) {
       const uint32_t below = (1u << b) - 1u;
-      r += (uint32_t)__popc(win_has[w] & below) + (uint32_t)__popc(win_eof[w] & below);
+      x += (uint32_t)__popc(win_has[w] & below) + (uint32_t)__popc(win_eof[w] & below);
     }
-    return r;
+    return x;
   }
   __device__ __forceinline__ void range(uint32_t s, uint32_t o, uint32_t e, uint32_t& tb, uint32_t& tc) const {
     if (!win_idx || punt[s]) {
       tb = x_begin[s];
       tc = x_end[s] - tb;
     } else {
-      tb = index_at(o);
-      tc = index_at(e) - tb;
+      const uint32_t r = range_of(s);
+      tb = index_at(o, r);
+      tc = index_at(e, r) - tb;
     }
   }
 };
@@ -992,12 +1006,15 @@ struct NutdbCtx {
   uint32_t epoch = 0;       // launch number of k_lex3 (tags its look-back descriptors)
   int sm_count = 148;
   size_t tok_cap_min = 0;   // token capacity a previous batch turned out to need
+  uint32_t tok_cap_num = 4; // segment capacity of k_lex4 in sixteenths of a token per byte (doubles on overflow)
+  bool force_lookback = false, last_lookback = false;
   uint32_t n_punt = 0;  // statements of the last batch lexed by the exact walker
   // device buffers (grow only)
   bool debug_tiles = false, debug_timing = false;
   DevBuf dbgTim;
   uint32_t dbg_ntiles = 0;
   DevBuf dbgTiles;
+  DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
       tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
@@ -1111,7 +1128,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->rangeByte, &c->rangeStmt, &c->rangeTokBase, &c->rangeCount, &c->rangeDense, &c->tokTypeD, &c->tokStartD, &c->tokEndD, &c->tokKwD, &c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1185,6 +1202,7 @@ NutdbCtx* nutdb_gpu_ctx_create(int device) {
   // k_parse_fast: staged tokens (static) + operator stacks (dynamic) exceed the 48 KB default
   if (ok) ok = cudaFuncSetAttribute(k_parse_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_DYN_SMEM) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(k_lex3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Lex3Shared)) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(k_lex4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Lex4Shared)) == cudaSuccess;
   if (ok) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
@@ -1263,7 +1281,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
 
   CK(cudaEventRecord(ctx->ev[0], st));
   ENSURE_DEV(off32, 4 * ((size_t)nstmt + 1));
-  ENSURE_DEV(bitmap, 4 * (nchunks + 8));
+  ENSURE_DEV(bitmap, 4 * (nchunks + 520));  // (k_lex4's tiles start at a range, not at a multiple of 8 KB: one tile of slack)
   ENSURE_DEV(stmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
   ENSURE_DEV(stmtTokBegin, 4 * ((size_t)nstmt + 1));
   ENSURE_DEV(stmtTokEnd, 4 * ((size_t)nstmt + 1));
@@ -1292,13 +1310,16 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
   // ---- lexer ----
   uint32_t tok_cap = 0;
   int attempt = 0;
+  bool use_lookback = ctx->force_lookback;  // k_lex3 instead of k_lex4 (a statement too long to cut the batch around)
+  // bytes per range of k_lex4: at most L4_MAX_RANGES ranges, at least one tile each
+  const uint32_t range_target = std::max<uint32_t>(L3_TILE, (n + L4_MAX_RANGES - 1) / L4_MAX_RANGES + 127u) & ~127u;
   const uint32_t n_readable = n;  // bytes of dText that may be read: bulk copies move whole 16-byte pieces below this
 run_again:
   ENSURE_DEV(puntFlag, 4 * ((size_t)nstmt + 1));
   CK(cudaMemsetAsync(ctx->puntFlag.p, 0, 4 * ((size_t)nstmt + 1), st));
   ENSURE_DEV(firstStmt, 4 * (nchunks + 8));
   CK(cudaMemsetAsync(ctx->firstStmt.p, 0xFF, 4 * (nchunks + 8), st));
-  CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 8), st));
+  CK(cudaMemsetAsync(ctx->bitmap.p, 0, 4 * (nchunks + 520), st));
   CK(cudaMemsetAsync(dS, 0, 128, st));
   {
     const uint32_t blocks = (uint32_t)(((uint64_t)nstmt + 1 + 255) / 256);
@@ -1364,26 +1385,31 @@ run_again:
     // Everything up to the dense node layout is issued without the host looking at a device-side count: token arrays
     // are sized by an estimate (grow-only; an overflow is detected at the one synchronisation and the batch re-run),
     // list lengths are read by the kernels themselves.
+    // k_lex4 lexes ranges of whole statements independently; k_lex3 (one token stream, look-back scans between tiles)
+    // takes over when a statement is too long to cut the batch around it.
     const uint32_t ntiles3 = (n + L3_TILE - 1) / L3_TILE;
-    const size_t nwin = (size_t)ntiles3 * L3_WIN;
+    const size_t nwin = (size_t)ntiles3 * L3_WIN + L4_MAX_RANGES + 8;  // (+ one slot per range, see k_lex4)
     ENSURE_DEV(winIdx, 4 * (nwin + 8));
     ENSURE_DEV(winHas, 4 * (nwin + 8));
     ENSURE_DEV(winEof, 4 * (nwin + 8));
-    for (DevBuf* d : {&ctx->descFn, &ctx->descA, &ctx->descI, &ctx->descB, &ctx->descC}) {  // (fn, counts, their prefix, statement start, open quote)  // look-back descriptors: tags start at epoch 0
-      const int rc = ensure_dev_zeroed(ctx, *d, 8 * (size_t)ntiles3, st);
-      if (rc != NUTDB_OK) return rc;
-    }
+    ENSURE_DEV(rangeByte, 4 * (L4_MAX_RANGES + 2));
+    ENSURE_DEV(rangeStmt, 4 * (L4_MAX_RANGES + 2));
+    ENSURE_DEV(rangeTokBase, 4 * (L4_MAX_RANGES + 2));
+    ENSURE_DEV(rangeCount, 8 * (L4_MAX_RANGES + 2));
+    ENSURE_DEV(rangeDense, 8 * (L4_MAX_RANGES + 2));
     ENSURE_DEV(puntList, 4 * ((size_t)nstmt + 1));
     ENSURE_DEV(puntCounts, 8 * ((size_t)nstmt + 1));
     ENSURE_DEV(puntOffs, 8 * ((size_t)nstmt + 1));
     const uint32_t nb = (nstmt + PUNT_THREADS * PUNT_PER_THREAD - 1) / (PUNT_THREADS * PUNT_PER_THREAD);
     ENSURE_DEV(puntBlockCount, 8 * ((size_t)nb + 1));
     ENSURE_DEV(puntBlockPref, 8 * ((size_t)nb + 1));
+    // ~0.2 tokens per byte on query logs; dense text ("((((") overflows the estimate once and grows the buffers
+    const uint32_t cap_num = ctx->tok_cap_num;  // sixteenths of a token per byte
     {
-      // ~0.2 tokens per byte on query logs; dense text ("((((") overflows the estimate once and grows the buffers
-      size_t want = (size_t)n / 4 + 2 * (size_t)nstmt + 4096;
-      if (want > 0xFFFFFFE0ull) want = 0xFFFFFFE0ull;
+      size_t want = (size_t)n * cap_num / 16 + 2 * (size_t)nstmt + 64 * (size_t)L4_MAX_RANGES + 4096;
+      if (want > (size_t)n + nstmt + 64 * (size_t)L4_MAX_RANGES + 4096) want = (size_t)n + nstmt + 64 * (size_t)L4_MAX_RANGES + 4096;
       if (want < ctx->tok_cap_min) want = ctx->tok_cap_min;
+      if (want > 0xFFFFFFE0ull) want = 0xFFFFFFE0ull;
       ENSURE_DEV(tokType, want + 16);
       ENSURE_DEV(tokKw, want + 16);
       ENSURE_DEV(tokStart, 4 * (want + 4));
@@ -1392,26 +1418,53 @@ run_again:
                                             ctx->tokStart.cap / 4 - 4, ctx->tokEnd.cap / 4 - 4});
     }
     const uint32_t* bm = (const uint32_t*)ctx->bitmap.p;
-    uint32_t* counters = dS + 14;  // [0] flagged statements, [1] bound on their tokens, [2] main-region tokens, [3] tile ticket
-    Lex3Desc desc{(unsigned long long*)ctx->descFn.p, (unsigned long long*)ctx->descA.p, (unsigned long long*)ctx->descI.p, (unsigned long long*)ctx->descB.p,
-                  (unsigned long long*)ctx->descC.p};
+    // counters: [0] flagged statements, [1] bound on their tokens, [2] start of the exact lexer's token region (k_lex3: the
+    // number of main-region tokens), [3] tile / range ticket, [4] a segment overflowed
+    uint32_t* counters = dS + 14;
+    uint32_t* cuts_info = dS + 20;  // {ranges, end of the last segment, longest range in bytes}
     Lex3Out lo3{(uint8_t*)ctx->tokType.p, (uint32_t*)ctx->tokStart.p, (uint32_t*)ctx->tokEnd.p, (uint8_t*)ctx->tokKw.p, tok_cap,
                 (uint32_t*)ctx->winIdx.p, (uint32_t*)ctx->winHas.p, (uint32_t*)ctx->winEof.p, (const uint32_t*)ctx->off32.p, nstmt,
                 (uint32_t*)ctx->puntFlag.p, counters, (const uint32_t*)ctx->firstStmt.p, nullptr, nullptr};
-    if (ctx->debug_tiles) {
-      ENSURE_DEV(dbgTiles, 16 * (size_t)ntiles3 + 16);
-      lo3.dbg = (uint32_t*)ctx->dbgTiles.p;
-      ctx->dbg_ntiles = ntiles3;
-    }
-    if (ctx->debug_timing) {
-      ENSURE_DEV(dbgTim, 24 * 8 * (size_t)ntiles3 + 16);
-      CK(cudaMemsetAsync(ctx->dbgTim.p, 0, 24 * 8 * (size_t)ntiles3, st));
-      lo3.tim = (unsigned long long*)ctx->dbgTim.p;
-      ctx->dbg_ntiles = ntiles3;
-    }
-    ctx->epoch = (ctx->epoch + 1u) & 0x0FFFFFFFu;  // (the tags hold 28 bits of it)
-    if (ctx->epoch == 0u) ctx->epoch = 1u;
-    {
+    const uint32_t* extra_base_ptr;
+    if (!use_lookback) {
+      LAUNCH("k_cuts", k_cuts<<<1, 1024, 0, st>>>((const uint32_t*)ctx->off32.p, nstmt, n, range_target, cap_num,
+                                                  (uint32_t*)ctx->rangeByte.p, (uint32_t*)ctx->rangeStmt.p,
+                                                  (uint32_t*)ctx->rangeTokBase.p, cuts_info, dS));
+      Lex4Ranges rg{(const uint32_t*)ctx->rangeByte.p, (const uint32_t*)ctx->rangeTokBase.p, (uint2*)ctx->rangeCount.p, cuts_info};
+      const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>(L4_MAX_RANGES, (n + range_target - 1) / range_target),
+                                               (uint32_t)ctx->sm_count * L4_MINBLOCKS);
+      LAUNCH("k_lex4", k_lex4<<<grid, L4_THREADS, sizeof(Lex4Shared), st>>>(dText, bm, n, n_readable, ctx->dLex, rg, lo3, dS));
+      // (dense positions of the segments, for callers that want the token arrays)
+      LAUNCH("k_scan_R", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->rangeCount.p, (uint2*)ctx->rangeDense.p,
+                                                                           L4_MAX_RANGES, (uint2*)(dS + 24), cuts_info));
+      extra_base_ptr = cuts_info + 1;
+    } else {
+      for (DevBuf* d : {&ctx->descFn, &ctx->descA, &ctx->descI, &ctx->descB, &ctx->descC}) {  // look-back descriptors: tags start at epoch 0
+        const int rc = ensure_dev_zeroed(ctx, *d, 8 * (size_t)ntiles3, st);
+        if (rc != NUTDB_OK) return rc;
+      }
+      Lex3Desc desc{(unsigned long long*)ctx->descFn.p, (unsigned long long*)ctx->descA.p, (unsigned long long*)ctx->descI.p,
+                    (unsigned long long*)ctx->descB.p, (unsigned long long*)ctx->descC.p};
+      if (ctx->debug_tiles) {
+        ENSURE_DEV(dbgTiles, 16 * (size_t)ntiles3 + 16);
+        lo3.dbg = (uint32_t*)ctx->dbgTiles.p;
+        ctx->dbg_ntiles = ntiles3;
+      }
+      if (ctx->debug_timing) {
+        ENSURE_DEV(dbgTim, 24 * 8 * (size_t)ntiles3 + 16);
+        CK(cudaMemsetAsync(ctx->dbgTim.p, 0, 24 * 8 * (size_t)ntiles3, st));
+        lo3.tim = (unsigned long long*)ctx->dbgTim.p;
+        ctx->dbg_ntiles = ntiles3;
+      }
+      ctx->epoch = (ctx->epoch + 1u) & 0x0FFFFFFFu;  // (the tags hold 28 bits of it)
+      if (ctx->epoch == 0u) ctx->epoch = 1u;
+      // one range: the whole batch, window slots unshifted, tokens dense from 0
+      const uint32_t one[8] = {0u, n, 0u, nstmt, 0u, tok_cap, 1u, 0u};
+      std::memcpy(hS + 40, one, sizeof(one));
+      CK(cudaMemcpyAsync(ctx->rangeByte.p, hS + 40, 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->rangeStmt.p, hS + 42, 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->rangeTokBase.p, hS + 44, 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(cuts_info, hS + 46, 4, cudaMemcpyHostToDevice, st));
 #ifndef L3_GRID_PER_SM
 #define L3_GRID_PER_SM L3_MINBLOCKS
 #endif
@@ -1419,6 +1472,7 @@ run_again:
       const uint32_t grid = 1u + std::min<uint32_t>(ntiles3, (uint32_t)ctx->sm_count * L3_GRID_PER_SM);
       LAUNCH("k_lex3", k_lex3<<<grid, L3_THREADS, sizeof(Lex3Shared), st>>>(dText, bm, n, n_readable, ntiles3, ctx->dLex, desc,
                                                                             ctx->epoch, lo3, dS));
+      extra_base_ptr = counters + 2;
     }
     // the flagged statements in ascending order (deterministic layout of the extra token region), then the exact walker
     LAUNCH("k_punt_count", k_punt_list<false><<<nb, PUNT_THREADS, 0, st>>>((const uint32_t*)ctx->puntFlag.p, nstmt,
@@ -1438,7 +1492,7 @@ run_again:
     xs = ExactSink{lo3.type, lo3.start, lo3.end, lo3.kw, tok_cap};
     LAUNCH("k_lex_exact_emit", k_lex_exact<true><<<xgrid, 128, 0, st>>>(
                                    dText, (const uint32_t*)ctx->off32.p, ctx->dLex, (const uint32_t*)ctx->puntList.p, counters, nullptr,
-                                   (const uint2*)ctx->puntOffs.p, counters + 2, xs, (uint32_t*)ctx->stmtTokBegin.p,
+                                   (const uint2*)ctx->puntOffs.p, extra_base_ptr, xs, (uint32_t*)ctx->stmtTokBegin.p,
                                    (uint32_t*)ctx->stmtTokEnd.p, (uint32_t*)ctx->puntFlag.p));
   }
   CK(cudaEventRecord(ctx->ev[2], st));
@@ -1454,14 +1508,14 @@ run_again:
     ENSURE_DEV(slowList, 4 * ((size_t)nstmt + 1));
     StmtToks stoks{native_lex ? (const uint32_t*)ctx->winIdx.p : nullptr, (const uint32_t*)ctx->winHas.p,
                    (const uint32_t*)ctx->winEof.p, (const uint32_t*)ctx->puntFlag.p, (const uint32_t*)ctx->stmtTokBegin.p,
-                   (const uint32_t*)ctx->stmtTokEnd.p};
+                   (const uint32_t*)ctx->stmtTokEnd.p, (const uint32_t*)ctx->rangeStmt.p, dS + 20};
     LAUNCH("k_parse_fast", k_parse_fast<<<(nstmt + FAST_THREADS - 1) / FAST_THREADS, FAST_THREADS, FAST_DYN_SMEM, st>>>(
                                dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                (const uint8_t*)ctx->tokKw.p, stoks, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
                                (uint32_t*)ctx->slowList.p, dS + 2, (const uint32_t*)ctx->puntFlag.p, lex_only ? 1 : 0,
                                native_lex ? tok_cap : (uint32_t)min((size_t)0xFFFFFFF0u, (size_t)ntok + 16), ctx->dFast,
-                               native_lex ? dS + 16 : nullptr, native_lex ? dS + 10 : nullptr, dS));
+                               native_lex ? (use_lookback ? dS + 16 : dS + 21) : nullptr, native_lex ? dS + 10 : nullptr, dS));
     if (!lex_only)
       LAUNCH("k_parse", k_parse<<<(nstmt + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
                             dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, 0u,
@@ -1483,22 +1537,29 @@ run_again:
       return NUTDB_E_ARG;
     }
     if (native_lex) {
-      const uint64_t ntok_main = hS[16], n_extra = hS[10];
+      // k_lex4: hS[21] = end of the segments (where the exact lexer's region begins), hS[24] = tokens in them;
+      // k_lex3: hS[16] = tokens of the main region = start of the exact lexer's region
+      const uint64_t seg_end = use_lookback ? hS[16] : hS[21], n_main = use_lookback ? hS[16] : hS[24], n_extra = hS[10];
       ctx->n_punt = hS[14];
-      if (ntok_main + n_extra >= 0xFFFFFFE0ull) {
+      if (seg_end + n_extra >= 0xFFFFFFE0ull) {
         ctx->err = "too many tokens in one batch";
         return NUTDB_E_ARG;
       }
-      if (ntok_main + n_extra > tok_cap) {  // the estimate was too small: grow and run the batch again
-        if (attempt >= 2) {
+      const bool seg_overflow = !use_lookback && hS[18] != 0;
+      const bool giant = !use_lookback && (uint64_t)hS[22] > std::max<uint64_t>(4u << 20, 8ull * range_target);
+      if (seg_overflow || giant || seg_end + n_extra > tok_cap) {  // an estimate was too small / the cuts do not fit: run again
+        if (attempt >= 4) {
           ctx->err = "token buffers kept overflowing";
           return NUTDB_E_NOMEM;
         }
-        ctx->tok_cap_min = (size_t)(ntok_main + n_extra) + (size_t)(ntok_main + n_extra) / 16 + 1024;
+        if (giant) use_lookback = true;  // a statement too long to cut around: one token stream, look-back scans
+        else if (seg_overflow) ctx->tok_cap_num = std::min<uint32_t>(16u, ctx->tok_cap_num * 2u);
+        if (seg_end + n_extra > tok_cap) ctx->tok_cap_min = (size_t)(seg_end + n_extra) + (size_t)(seg_end + n_extra) / 16 + 1024;
         attempt++;
         goto run_again;
       }
-      ntok = (uint32_t)(ntok_main + n_extra);
+      ntok = (uint32_t)(n_main + n_extra);
+      ctx->last_lookback = use_lookback;
     }
     ctx->n_slow = hS[2];
     const uint32_t nretry = hS[1];
@@ -1550,6 +1611,29 @@ run_again:
     CK(cudaMemcpyAsync(hS, dS, 128, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
+  // k_lex4 left gaps between the ranges' token segments: callers that see the token arrays get dense ones
+  const uint8_t* dTokType = (const uint8_t*)ctx->tokType.p;
+  const uint8_t* dTokKw = (const uint8_t*)ctx->tokKw.p;
+  const uint32_t* dTokStart = (const uint32_t*)ctx->tokStart.p;
+  const uint32_t* dTokEnd = (const uint32_t*)ctx->tokEnd.p;
+  if (native_lex && !use_lookback && nstmt > 0 && !(flags & NUTDB_F_NO_TOKENS)) {
+    ENSURE_DEV(tokTypeD, (size_t)ntok + 16);
+    ENSURE_DEV(tokKwD, (size_t)ntok + 16);
+    ENSURE_DEV(tokStartD, 4 * ((size_t)ntok + 4));
+    ENSURE_DEV(tokEndD, 4 * ((size_t)ntok + 4));
+    const uint32_t slices = 8;
+    LAUNCH("k_tok_compact", k_tok_compact<<<(L4_MAX_RANGES + 1) * slices, 256, 0, st>>>(
+                                dTokType, dTokStart, dTokEnd, dTokKw, (uint8_t*)ctx->tokTypeD.p, (uint32_t*)ctx->tokStartD.p,
+                                (uint32_t*)ctx->tokEndD.p, (uint8_t*)ctx->tokKwD.p, (const uint32_t*)ctx->rangeTokBase.p,
+                                (const uint2*)ctx->rangeCount.p, (const uint2*)ctx->rangeDense.p, dS + 20, dS + 10, slices));
+    LAUNCH("k_stmt_tok_remap", k_stmt_tok_remap<<<(nstmt + 255) / 256, 256, 0, st>>>(
+                                   (NutdbStmt*)ctx->stmt.p, nstmt, (const uint32_t*)ctx->rangeStmt.p, (const uint32_t*)ctx->rangeTokBase.p,
+                                   (const uint2*)ctx->rangeCount.p, (const uint2*)ctx->rangeDense.p, dS + 20));
+    dTokType = (const uint8_t*)ctx->tokTypeD.p;
+    dTokKw = (const uint8_t*)ctx->tokKwD.p;
+    dTokStart = (const uint32_t*)ctx->tokStartD.p;
+    dTokEnd = (const uint32_t*)ctx->tokEndD.p;
+  }
   CK(cudaEventRecord(ctx->ev[3], st));
 
   // ---- output ----
@@ -1573,10 +1657,10 @@ run_again:
       ENSURE_HOST(hTokStart, 4 * ((size_t)ntok + 4));
       ENSURE_HOST(hTokEnd, 4 * ((size_t)ntok + 4));
       if (ntok) {
-        CK(cudaMemcpyAsync(ctx->hTokType.p, ctx->tokType.p, ntok, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->hTokKw.p, ctx->tokKw.p, ntok, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->hTokStart.p, ctx->tokStart.p, 4 * (size_t)ntok, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->hTokEnd.p, ctx->tokEnd.p, 4 * (size_t)ntok, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->hTokType.p, dTokType, ntok, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->hTokKw.p, dTokKw, ntok, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->hTokStart.p, dTokStart, 4 * (size_t)ntok, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->hTokEnd.p, dTokEnd, 4 * (size_t)ntok, cudaMemcpyDeviceToHost, st));
       }
       out->tok_type = (const uint8_t*)ctx->hTokType.p;
       out->tok_kw = (const uint8_t*)ctx->hTokKw.p;
@@ -1599,10 +1683,10 @@ run_again:
     ctx->kernel_ms.emplace_back(r.name, ms);
   }
   ctx->dev_view.stmt = ctx->stmt.p;
-  ctx->dev_view.tok_type = ctx->tokType.p;
-  ctx->dev_view.tok_start = ctx->tokStart.p;
-  ctx->dev_view.tok_end = ctx->tokEnd.p;
-  ctx->dev_view.tok_kw = ctx->tokKw.p;
+  ctx->dev_view.tok_type = dTokType;
+  ctx->dev_view.tok_start = dTokStart;
+  ctx->dev_view.tok_end = dTokEnd;
+  ctx->dev_view.tok_kw = dTokKw;
   ctx->dev_view.node = ctx->nodes.p;
   ctx->dev_view.err = ctx->errs.p;
   ctx->batch_live = true;
@@ -1776,6 +1860,21 @@ int nutdb_gpu_last_timing(const NutdbCtx* ctx, float ms[5]) {
 }
 
 int nutdb_gpu_last_launches(const NutdbCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+// test hook (not in the public header): the first statements of the last batch that the table-driven parser declined
+int nutdb_gpu_debug_slow_list(NutdbCtx* ctx, uint32_t* out, uint32_t cap) {
+  if (!ctx || !ctx->slowList.p) return 0;
+  const uint32_t k = std::min<uint32_t>(cap, ctx->n_slow);
+  cudaSetDevice(ctx->device);
+  if (k && cudaMemcpy(out, ctx->slowList.p, 4 * (size_t)k, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int)k;
+}
+
+// test hook (not in the public header): lex every batch with k_lex3 (look-back scans) instead of k_lex4 (ranges)
+void nutdb_gpu_debug_force_lookback(NutdbCtx* ctx, int on) {
+  if (ctx) ctx->force_lookback = on != 0;
+}
+int nutdb_gpu_debug_last_lookback(const NutdbCtx* ctx) { return ctx && ctx->last_lookback ? 1 : 0; }
 
 // profiling hook (not in the public header): 24 clock64 stamps per tile of the last k_lex3 launch
 int nutdb_gpu_debug_timing(NutdbCtx* ctx, int enable, unsigned long long* out, uint32_t cap_tiles) {
