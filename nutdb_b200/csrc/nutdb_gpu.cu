@@ -603,6 +603,7 @@ struct StmtToks {
   const uint32_t* x_end;
   const uint32_t* cut_stmt;        // first statement of each lexer range (k_cuts); a range's windows sit `range` slots up
   const uint32_t* nranges;
+  uint32_t tok_cap;                // capacity of the token arrays
   __device__ __forceinline__ uint32_t range_of(uint32_t s) const {
     uint32_t lo = 0, hi = *nranges;  // last range with cut_stmt[r] <= s
     while (hi - lo > 1u) {
@@ -630,6 +631,11 @@ struct StmtToks {
       const uint32_t r = range_of(s);
       tb = index_at(o, r);
       tc = index_at(e, r) - tb;
+    }
+    // (a batch whose token estimate was too small is run again -- but this attempt must stay inside the arrays)
+    if (tb >= tok_cap || tc > tok_cap - tb) {
+      tb = 0;
+      tc = 0;
     }
   }
 };
@@ -1508,7 +1514,8 @@ run_again:
     ENSURE_DEV(slowList, 4 * ((size_t)nstmt + 1));
     StmtToks stoks{native_lex ? (const uint32_t*)ctx->winIdx.p : nullptr, (const uint32_t*)ctx->winHas.p,
                    (const uint32_t*)ctx->winEof.p, (const uint32_t*)ctx->puntFlag.p, (const uint32_t*)ctx->stmtTokBegin.p,
-                   (const uint32_t*)ctx->stmtTokEnd.p, (const uint32_t*)ctx->rangeStmt.p, dS + 20};
+                   (const uint32_t*)ctx->stmtTokEnd.p, (const uint32_t*)ctx->rangeStmt.p, dS + 20,
+                   native_lex ? tok_cap : 0xFFFFFFFFu};
     LAUNCH("k_parse_fast", k_parse_fast<<<(nstmt + FAST_THREADS - 1) / FAST_THREADS, FAST_THREADS, FAST_DYN_SMEM, st>>>(
                                dText, (const uint32_t*)ctx->off32.p, nstmt, ntok, (const uint8_t*)ctx->tokType.p,
                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
