@@ -435,8 +435,10 @@ struct Tok3 {
 };
 // Src: uint8_t at(abs) for bytes of the token itself (always staged), const uint8_t* span(abs, len).
 // sst = first byte of the token's statement.
+// Returns true for a word of 2..10 bytes: it may be a keyword, r.kw is still to be looked up (token_keyword3) -- the
+// device does that in a second pass over the listed words so that all lanes of a warp run the hash together.
 template <class Src>
-NUTDB_HD void token_finish3(const LexTables& T, Src& src, uint32_t start, uint32_t end, uint32_t flags, uint32_t sst, Tok3& r) {
+NUTDB_HD bool token_finish3(const LexTables& T, Src& src, uint32_t start, uint32_t end, uint32_t flags, uint32_t sst, Tok3& r) {
   const uint32_t kind = flags & 7u, len = end - start;
   r.start = start - sst;
   r.end = end - sst;
@@ -444,17 +446,8 @@ NUTDB_HD void token_finish3(const LexTables& T, Src& src, uint32_t start, uint32
     const uint8_t b0 = src.at(start);
     uint8_t t = T.tt0[b0];
     if (t == NUTDB_TT_KeywordOrIdentifier) {  // tokenizer/mod.rs:262-282
-      if (len >= 2 && len <= 10) {
-        const uint8_t* wp = src.span(start, len);
-        if (wp) {
-          uint32_t w0, w1, w2;
-          load_word12(wp, len, w0, w1, w2);
-          r.kw = keyword_lookup_words(T, len, w0, w1, w2);
-        } else {
-          Src& sr = src;
-          r.kw = keyword_lookup(T, len, [&sr, start](uint32_t q) { return sr.at(start + q); });
-        }
-      }
+      r.type = t;
+      return len >= 2 && len <= 10;
     } else if (t == NUTDB_TT_IntegerLiteral) {
       r.kw = 1;  // one digit
     } else if (len == 2) {  // the only other generic tokens of two bytes: <= >= != <> << >>
@@ -472,7 +465,7 @@ NUTDB_HD void token_finish3(const LexTables& T, Src& src, uint32_t start, uint32
       // "0x1G", "0x1.5", "1x", ".0x1" ... go to the exact lexer.
       bool ok = ndots == 0 && b0 == '0' && (src.at(start + 1u) | 0x20) == 'x';
       for (uint32_t q = start + 2u; ok && q < end; q++) ok = (T.prop[src.at(q)] & PR_HEX) != 0;
-      if (!ok) { r.punt = 1; return; }
+      if (!ok) { r.punt = 1; return false; }
       r.type = NUTDB_TT_HexLiteral;
       r.start += 2u;
       r.kw = (uint8_t)(len - 2u > 255u ? 255u : len - 2u);
@@ -496,6 +489,19 @@ NUTDB_HD void token_finish3(const LexTables& T, Src& src, uint32_t start, uint32
              : kind == R3_EDQ ? (uint8_t)NUTDB_TT_EscapedDQStringLiteral : (uint8_t)NUTDB_TT_DelimitedIdentifier;
     r.end = end - 1u - sst;
   }
+  return false;
+}
+// keyword id of a word of 2..10 bytes (the shared-memory perfect hash)
+template <class Src>
+NUTDB_HD uint8_t token_keyword3(const LexTables& T, Src& src, uint32_t start, uint32_t len) {
+  const uint8_t* wp = src.span(start, len);
+  if (wp) {
+    uint32_t w0, w1, w2;
+    load_word12(wp, len, w0, w1, w2);
+    return keyword_lookup_words(T, len, w0, w1, w2);
+  }
+  Src& sr = src;
+  return keyword_lookup(T, len, [&sr, start](uint32_t q) { return sr.at(start + q); });
 }
 
 }  // namespace nlex3

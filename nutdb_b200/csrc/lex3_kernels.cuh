@@ -526,9 +526,9 @@ __global__ void __launch_bounds__(L3_THREADS, L3_MINBLOCKS) k_lex3(const uint8_t
       L3_STAMP(3);
       uint8_t s_warp;
       {
-        uint32_t pre = NUTDB_VEC8_ID;
-        for (int i = 0; i < warp; i++) pre = vec8_then(pre, S.wfn[i]);
-        s_warp = (uint8_t)vec8_apply(pre, S.s_tile_in);
+        uint32_t st = S.s_tile_in;
+        for (int i = 0; i < warp; i++) st = vec8_apply(S.wfn[i], st);
+        s_warp = (uint8_t)st;
       }
       const uint8_t s_in = (uint8_t)vec8_apply(fexcl, s_warp);
       // ---------------- stage 2: concrete context walk, token masks ----------------
@@ -683,15 +683,8 @@ __global__ void __launch_bounds__(L3_THREADS, L3_MINBLOCKS) k_lex3(const uint8_t
         const uint32_t bb = S.bndm[wv] & (i >= 31u ? 0xFFFFFFFFu : ((2u << i) - 1u));
         const uint32_t sst = bb ? tile_begin + 32u * wv + (uint32_t)(31 - __clz((int)bb)) : S.sst_in[wv];
         nlex3::Tok3 tk;
-        nlex3::token_finish3(S.T, src, start_abs, tile_begin + end_rel, flags, sst, tk);
-#ifdef L3_EXP_B2  // experiment: the per-token work twice (is the kernel bound by its arithmetic?)
-        {
-          nlex3::Tok3 t2;
-          nlex3::token_finish3(S.T, src, start_abs + (tk.kw == 255u ? 1u : 0u), tile_begin + end_rel, flags, sst + (tk.type == 77u ? 1u : 0u), t2);
-          tk.kw |= (uint8_t)(t2.kw & tk.kw);
-          tk.start |= t2.start & tk.start;
-        }
-#endif
+        if (nlex3::token_finish3(S.T, src, start_abs, tile_begin + end_rel, flags, sst, tk))
+          tk.kw = nlex3::token_keyword3(S.T, src, start_abs, tile_begin + end_rel - start_abs);
         if (tk.punt) {
           out.punt_stmt_at(sst);
           tk.type = NUTDB_TT_POISON;  // (the slot belongs to a flagged statement: a fixed filler)

@@ -36,6 +36,8 @@ struct alignas(16) Lex4Shared {
   uint32_t bndm[L3_WIN + 1];
   uint32_t sst_in[L3_WIN];
   uint32_t rec0[L3_RCAP], rec1[L3_RCAP];
+  uint16_t wlist[L3_RCAP];  // records of the words that may be keywords (pass 2 of the token stage)
+  uint32_t nwords;
   uint32_t wfn[L3_WARPS];
   uint4 wsum[L3_WARPS];
   uint32_t range;      // ticket
@@ -188,9 +190,9 @@ __global__ void __launch_bounds__(L4_THREADS, L4_MINBLOCKS) k_lex4(const uint8_t
       __syncthreads();  // ---- A: wfn
       uint8_t s_warp;
       {
-        uint32_t pre = NUTDB_VEC8_ID;
-        for (int i = 0; i < warp; i++) pre = vec8_then(pre, S.wfn[i]);
-        s_warp = (uint8_t)vec8_apply(pre, S.car_state);
+        uint32_t st = S.car_state;  // (applying the warps' functions one after the other is far cheaper than composing them)
+        for (int i = 0; i < warp; i++) st = vec8_apply(S.wfn[i], st);
+        s_warp = (uint8_t)st;
       }
       const uint8_t s_in = (uint8_t)vec8_apply(fexcl, s_warp);
       // ---------------- stage 2: concrete context walk, token masks ----------------
@@ -282,14 +284,13 @@ __global__ void __launch_bounds__(L4_THREADS, L4_MINBLOCKS) k_lex4(const uint8_t
       uint32_t new_state = 0;
       uint4 new_car = make_uint4(0u, 0u, 0u, 0u);
       if (threadIdx.x == 0) {
-        uint32_t agg = NUTDB_VEC8_ID;
         new_car = S.car;
+        new_state = S.car_state;
 #pragma unroll
         for (int i = 0; i < L3_WARPS; i++) {
-          agg = vec8_then(agg, S.wfn[i]);
+          new_state = vec8_apply(S.wfn[i], new_state);
           new_car = c3_then(new_car, S.wsum[i]);
         }
-        new_state = vec8_apply(agg, S.car_state);
       }
       const uint32_t sst_open = cin.y ? cin.y - 1u : 0u;
       S.sst_in[threadIdx.x] = sst_open;
@@ -320,29 +321,56 @@ __global__ void __launch_bounds__(L4_THREADS, L4_MINBLOCKS) k_lex4(const uint8_t
         }
         __syncthreads();  // ---- E: records
         const uint32_t cnt = min(tile_count - r0, (uint32_t)L3_RCAP);
-        for (uint32_t q = threadIdx.x; q < cnt; q += L4_THREADS) {
-          const uint32_t start_abs = S.rec0[q], r1 = S.rec1[q];
-          const uint32_t end_rel = r1 & ((1u << NUTDB_R3_KIND_SHIFT) - 1u), flags = r1 >> NUTDB_R3_KIND_SHIFT;
-          const uint32_t last = end_rel - 1u;  // the token's last byte, tile relative
-          const uint32_t wv = last >> 5, i = last & 31u;
-          const uint32_t bb = S.bndm[wv] & (i >= 31u ? 0xFFFFFFFFu : ((2u << i) - 1u));
-          const uint32_t sst = bb ? tile_begin + 32u * wv + (uint32_t)(31 - __clz((int)bb)) : S.sst_in[wv];
-          nlex3::Tok3 tk;
-          nlex3::token_finish3(S.T, src, start_abs, tile_begin + end_rel, flags, sst, tk);
-          if (tk.punt) {
-            out.punt_stmt_at(sst);
-            tk.type = NUTDB_TT_POISON;  // (the slot belongs to a flagged statement: a fixed filler)
-            tk.start = tk.end = 0;
-            tk.kw = 0;
+        if (threadIdx.x == 0) S.nwords = 0u;
+        __syncthreads();
+        // pass 1: every token -- type, statement-relative span; words that can be keywords are listed for pass 2
+        for (uint32_t q0 = 0; q0 < cnt; q0 += L4_THREADS) {
+          const uint32_t q = q0 + threadIdx.x;
+          bool is_word = false;
+          if (q < cnt) {
+            const uint32_t start_abs = S.rec0[q], r1 = S.rec1[q];
+            const uint32_t end_rel = r1 & ((1u << NUTDB_R3_KIND_SHIFT) - 1u), flags = r1 >> NUTDB_R3_KIND_SHIFT;
+            const uint32_t last = end_rel - 1u;  // the token's last byte, tile relative
+            const uint32_t wv = last >> 5, i = last & 31u;
+            const uint32_t bb = S.bndm[wv] & (i >= 31u ? 0xFFFFFFFFu : ((2u << i) - 1u));
+            const uint32_t sst = bb ? tile_begin + 32u * wv + (uint32_t)(31 - __clz((int)bb)) : S.sst_in[wv];
+            nlex3::Tok3 tk;
+            is_word = nlex3::token_finish3(S.T, src, start_abs, tile_begin + end_rel, flags, sst, tk);
+            if (tk.punt) {
+              out.punt_stmt_at(sst);
+              tk.type = NUTDB_TT_POISON;  // (the slot belongs to a flagged statement: a fixed filler)
+              tk.start = tk.end = 0;
+              tk.kw = 0;
+            }
+            const uint32_t li = tile_first + r0 + q;  // index inside the range's segment
+            if (li < seg_cap) {
+              const uint32_t gi = seg_base + li;
+              out.type[gi] = tk.type;
+              out.start[gi] = tk.start;
+              out.end[gi] = tk.end;
+              if (!is_word) out.kw[gi] = tk.kw;
+            } else {
+              is_word = false;
+            }
           }
-          const uint32_t li = tile_first + r0 + q;  // index inside the range's segment
-          if (li < seg_cap) {
-            const uint32_t gi = seg_base + li;
-            out.type[gi] = tk.type;
-            out.start[gi] = tk.start;
-            out.end[gi] = tk.end;
-            out.kw[gi] = tk.kw;
+          const uint32_t wm = __ballot_sync(full, is_word);
+          if (wm) {
+            uint32_t wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&S.nwords, (uint32_t)__popc(wm));
+            wbase = __shfl_sync(full, wbase, 0);
+            if (is_word) S.wlist[wbase + (uint32_t)__popc(wm & ((1u << lane) - 1u))] = (uint16_t)q;
           }
+        }
+        __syncthreads();
+        // pass 2: keyword ids (perfect hash), all lanes on the same code
+        const uint32_t nw = S.nwords;
+        for (uint32_t j = threadIdx.x; j < nw; j += L4_THREADS) {
+          const uint32_t q = S.wlist[j];
+          const uint32_t start_abs = S.rec0[q], end_abs = tile_begin + (S.rec1[q] & ((1u << NUTDB_R3_KIND_SHIFT) - 1u));
+          const uint32_t len = end_abs - start_abs;
+          uint32_t w0, w1, w2;
+          load_word12(src.span(start_abs, len), len, w0, w1, w2);
+          out.kw[seg_base + tile_first + r0 + q] = keyword_lookup_words(S.T, len, w0, w1, w2);
         }
       }
       __syncthreads();  // ---- F: everyone is done with buffer b, the per-window tables and the carries

@@ -267,7 +267,7 @@ int64_t emul_lex3(const uint8_t* text, uint32_t n, const uint64_t* offs, uint64_
     const uint32_t bb = win_bnd[wv] & (i >= 31u ? 0xFFFFFFFFu : ((2u << i) - 1u));
     const uint32_t sst = bb ? 32u * wv + (uint32_t)(31 - clz32(bb)) : sst_in[wv];
     Tok3 tk;
-    token_finish3(T, src, r.start, r.end, r.flags, sst, tk);
+    if (token_finish3(T, src, r.start, r.end, r.flags, sst, tk)) tk.kw = token_keyword3(T, src, r.start, r.end - r.start);
     if (tk.punt) {
       punt_stmt_at(sst);
       tk.type = NUTDB_TT_POISON;
