@@ -141,11 +141,19 @@ def alg_counts(text, offs, sample_bytes=16 << 20):
     return {"bytes": nb, "stmts": k, "T": int(b.t_alg), "M": int(b.m_alg)}
 
 
+def workload_config(config, n_in, n_stmt):
+    """The `config` object of the JSON line: what the workload is, nothing measured -- identical for both arms."""
+    return {"workload": WORKLOADS[config], "bytes_per_gpu": int(n_in), "statements_per_gpu": int(n_stmt),
+            "sharding": "statement ranges, one shard per GPU, outputs stay sharded",
+            "l2": "input (1 GiB class) and every intermediate array are larger than the 126 MB L2; no flush needed"}
+
+
 def run_reference(args, rank, world):
+    """CPU arm: the restated reference parser (oracle port; the Rust reference cannot be built in this image) on all
+    host cores.  Same workload and `config` as our arm; every step parses a bounded prefix of it."""
     if rank != 0:
         return
-    # the CPU arm parses a bounded sample per step, so it only generates the head of the workload
-    text, offs = make_workload(args.config, min(args.bytes, 256 << 20))
+    text, offs = make_workload(args.config, args.bytes)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     cores = os.cpu_count() or 1
@@ -163,14 +171,15 @@ def run_reference(args, rank, world):
         O.bench(text, offs[:k + 1], cores, reps=1)
     dt = (time.perf_counter() - t0) / args.steps
     v = nb / dt / 1e9
+    sample = (f"first {nb} bytes / {k} statements of the workload per step, {cores} threads; C++ restatement of the "
+              "reference parser (oracle port: no Rust toolchain in this image, so NOT the Rust parser itself)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "statements_per_s": k / dt,
-            "config": {"workload": WORKLOADS[args.config], "bytes_per_step": nb, "statements_per_step": k},
-            "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
-                             "sample": f"first {nb} bytes / {k} statements of the workload per step, {cores} threads; "
-                                       "C++ restatement of the reference parser (no Rust toolchain in this image)"},
+            "config": workload_config(args.config, total, len(offs) - 1),
+            "sample_per_step": {"bytes": nb, "statements": k},
+            "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -283,6 +292,129 @@ def run_log(args, rank, world, local, barrier):
     ctx.close()
 
 
+def device_run(ctx, text, offs, local, steps, warmup, barrier):
+    """Device-resident timing of one workload: input pre-staged in HBM, outputs left on the device.  CUDA events on the
+    library's stream around `steps` calls, then a separate pass with events around every launch."""
+    import torch
+    from nutdb_b200 import gpu
+    n_stmt = len(offs) - 1
+    d_text = torch.from_numpy(text).cuda()
+    d_offs = torch.from_numpy(offs.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    dev_flags = gpu.F_DEVICE_INPUT | gpu.F_NO_HOST_COPY
+
+    def step_device():
+        return ctx.parse_batch_raw(d_text.data_ptr(), d_offs.data_ptr(), n_stmt, dev_flags, copy=False)
+
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    for _ in range(warmup):
+        b = step_device()
+    out = {"n_tok": int(b.n_tok), "n_node": int(b.n_node), "n_err": int(b.n_err), "launches": ctx.launches(),
+           "n_slow": int(ctx.slow_statements()), "n_punt": int(ctx.exact_lexed_statements())}
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lib_stream)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_device()
+    e1.record(lib_stream)
+    barrier()
+    out["wall_ms"] = (time.perf_counter() - t0) * 1e3 / steps
+    out["dev_ms"] = e0.elapsed_time(e1) / steps
+    # ---- per-kernel timing (events around every launch, separate pass) ----
+    ctx.set_profiling(True)
+    acc = {}
+    reps = max(2, min(steps, 3))
+    for _ in range(reps):
+        step_device()
+        for name, ms in ctx.kernel_timing():
+            acc.setdefault(name, []).append(ms)
+    ctx.set_profiling(False)
+    out["kernel_ms"] = {k: sum(v) / reps for k, v in acc.items()}
+    del d_text, d_offs
+    return out
+
+
+def roofline_numbers(text, offs, dev, T_pulled, peak):
+    """Algorithmic bytes (DESIGN.md "Roofline accounting") of the pipeline and of its dominant kernel."""
+    n_in, n_stmt = int(offs[-1]), len(offs) - 1
+    cnt = alg_counts(text, offs)
+    scale = n_in / cnt["bytes"]
+    T = T_pulled if T_pulled is not None else int(cnt["T"] * scale)
+    M = int(cnt["M"] * scale)
+    b_alg = n_in + 9 * T + 16 * M + 16 * n_stmt
+    parse_b = 9 * T + 16 * M + 16 * n_stmt
+    alg = {"k_lex_A": n_in, "k_lex_B": n_in, "k_lex_C": n_in, "k_lex_D": n_in + 9 * T,
+           "k_lex4": n_in + 9 * T, "k_lex3": n_in + 9 * T,
+           "k_parse_fast": parse_b, "k_parse": parse_b, "k_parse_retry": parse_b, "k_parse_coop": parse_b,
+           "k_finalize": 16 * M + 16 * n_stmt}
+    kernel_ms = dev["kernel_ms"]
+    dom = max((k for k in kernel_ms if k in alg), key=lambda k: kernel_ms[k])
+    ksum = sum(kernel_ms.values())
+    return {"dominant": dom, "alg": alg, "ksum": ksum, "achieved": alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9,
+            "pipeline": {"alg_bytes": b_alg, "B_alg_over_N_in": b_alg / n_in, "T": T, "M": M, "S": n_stmt,
+                         "achieved": b_alg / (dev["dev_ms"] * 1e-3) / 1e9,
+                         "frac": b_alg / (dev["dev_ms"] * 1e-3) / 1e9 / peak,
+                         "sum_kernel_ms": ksum, "kernels_ms": {k: round(v, 4) for k, v in kernel_ms.items()}}}
+
+
+def extra_config(ctx, config, nbytes, local, barrier, peak):
+    """One of the other BASELINE.json configurations on this GPU: device-resident value, pipeline roofline fraction,
+    how many statements took the slower paths, and whether a sample of the output equals the oracle's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity as P
+    text, offs = make_workload(config, nbytes)
+    n_in, n_stmt = int(offs[-1]), len(offs) - 1
+    dev = device_run(ctx, text, offs, local, 5, 3, barrier)
+    rf = roofline_numbers(text, offs, dev, None, peak)
+    k = max(1, int(np.searchsorted(offs, np.uint64(2 << 20), side="right")) - 1)
+    sample_text = np.concatenate([text[:int(offs[k])], np.zeros(64, np.uint8)])
+    got = ctx.parse_batch(sample_text, offs[:k + 1])
+    bad = P.compare_with_oracle(got, sample_text, offs[:k + 1])
+    if bad:
+        print(f"config {config}: ORACLE MISMATCH: {bad[:3]}", file=sys.stderr, flush=True)
+    return {"workload": WORKLOADS[config], "bytes": n_in, "statements": n_stmt, "steps": 5, "warmup": 3,
+            "value": n_in / (dev["dev_ms"] * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": dev["dev_ms"],
+            "statements_per_s": n_stmt / (dev["dev_ms"] * 1e-3),
+            "tokens": dev["n_tok"], "nodes": dev["n_node"], "error_statements": dev["n_err"],
+            "automaton_share": dev["n_slow"] / max(1, n_stmt), "exact_lexed_share": dev["n_punt"] / max(1, n_stmt),
+            "roofline_pipeline_frac": rf["pipeline"]["frac"], "dominant_kernel": rf["dominant"],
+            "kernels_ms": rf["pipeline"]["kernels_ms"],
+            "oracle_sample": {"statements": k, "bytes": int(offs[k]), "bit_exact": not bad}}
+
+
+def single_call_latency(ctx):
+    """The reference's own bench shape (benches/parser_bench.rs:5-6,48: one statement per Parser::parse call, the 31-byte
+    and the 1,131-byte string): wall time of one nutdb_gpu_parse call (host text in, host AST out) next to the oracle
+    port on one host thread."""
+    import ctypes as C
+    from nutdb_b200 import gpu, workload as W
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    stmts = W.corpus_statements()
+    out = {}
+    for name, s in (("short sql", stmts[-1]), ("long sql", stmts[-2])):
+        raw = gpu.NutdbBatch()
+        L = gpu.lib()
+        for _ in range(20):
+            L.nutdb_gpu_parse(ctx._h, s, len(s), C.byref(raw))
+        ts = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            rc = L.nutdb_gpu_parse(ctx._h, s, len(s), C.byref(raw))
+            ts.append(time.perf_counter() - t0)
+        assert rc == 0 and raw.n_stmt == 1
+        reps = 20000
+        offs = np.arange(reps + 1, dtype=np.uint64) * np.uint64(len(s))
+        text = np.frombuffer(s * reps + b"\0" * 64, np.uint8)
+        t, _, _ = O.bench(text, offs, 1, reps=3)
+        out[name] = {"bytes": len(s), "gpu_call_us_median": statistics.median(ts) * 1e6, "gpu_call_us_min": min(ts) * 1e6,
+                     "gpu_launches_per_call": ctx.launches(), "cpu_port_single_thread_ns": t / reps * 1e9}
+    out["note"] = ("one nutdb_gpu_parse call per statement is launch-latency bound: the GPU path is a batch engine; "
+                   "cpu_port = C++ oracle port, not the Rust parser")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -295,6 +427,8 @@ def main():
     ap.add_argument("--bytes", type=int, default=1 << 30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the 256 MiB runs of configs 1, 3, 4 and the latency probe")
+    ap.add_argument("--extra-bytes", type=int, default=256 << 20)
     ap.add_argument("--e2e-chunk", type=int, default=64 << 20, help="bytes of SQL per pipelined chunk on the host path")
     ap.add_argument("--e2e-workers", type=int, default=4, help="contexts (threads) the host path pipelines chunks over")
     args = ap.parse_args()
@@ -332,50 +466,15 @@ def main():
     text, offs = make_workload(args.config, args.bytes, seed_offset=rank)
     n_in, n_stmt = int(offs[-1]), len(offs) - 1
     ctx = gpu.Context(local)
-    d_text = torch.from_numpy(text).cuda()
-    d_offs = torch.from_numpy(offs.view(np.int64)).cuda()
-    torch.cuda.synchronize()
-    dev_flags = gpu.F_DEVICE_INPUT | gpu.F_NO_HOST_COPY
-
-    def step_device():
-        return ctx.parse_batch_raw(d_text.data_ptr(), d_offs.data_ptr(), n_stmt, dev_flags, copy=False)
-
-    # ---- device-resident timing ----
-    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    for _ in range(args.warmup):
-        b = step_device()
-    n_tok, n_node, n_err = int(b.n_tok), int(b.n_node), int(b.n_err)
-    launches_per_step = ctx.launches()
-    n_slow = int(ctx.slow_statements())
-    n_punt = int(ctx.exact_lexed_statements())
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(lib_stream)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_device()
-    e1.record(lib_stream)
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    dev_ms = e0.elapsed_time(e1) / args.steps
+    dev = device_run(ctx, text, offs, local, args.steps, args.warmup, barrier)
     clocks = sampler.stop()
-
-    # ---- per-kernel timing (events around every launch, separate pass) ----
-    ctx.set_profiling(True)
-    acc = {}
-    for _ in range(max(2, min(args.steps, 3))):
-        step_device()
-        for name, ms in ctx.kernel_timing():
-            acc.setdefault(name, []).append(ms)
-    ctx.set_profiling(False)
-    kernel_ms = {k: sum(v) / len(v) * (len(v) / max(2, min(args.steps, 3))) for k, v in acc.items()}
+    dev_ms, wall_ms, kernel_ms = dev["dev_ms"], dev["wall_ms"], dev["kernel_ms"]
     T_pulled = None
 
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
-    h_stmt_sum = None
     if not args.no_e2e:
         h_text = torch.from_numpy(text).pin_memory()
         h_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
@@ -392,6 +491,7 @@ def main():
             acc["n_node"] = acc.get("n_node", 0) + int(bb.n_node)
             acc["n_err"] = acc.get("n_err", 0) + int(bb.n_err)
             acc["last_status"] = int(bb.stmt["status"][-1]) if bb.n_stmt else 0
+            acc["last_kind"] = int(bb.cnode["kind"][-1]) if bb.n_node else 0
 
         def step_host():
             acc.clear()
@@ -399,7 +499,7 @@ def main():
 
         # untimed: exact T (tokens the reference pulls) and the ok count from one plain host-buffer call
         hb0 = ctx.parse_batch_raw(h_text.data_ptr(), h_offs.data_ptr(), n_stmt, flags, copy=False)
-        acc0 = {"tok_used": int(hb0.stmt["tok_used"].astype(np.int64).sum()), "ok": int((hb0.stmt["status"] == 0).sum())}
+        T_pulled = int(hb0.stmt["tok_used"].astype(np.int64).sum())
         del hb0
         for _ in range(2):
             step_host()
@@ -410,15 +510,8 @@ def main():
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         sp.close()
-
-        class _HB:
-            pass
-        hb = _HB()
-        hb.n_node, hb.n_err = acc["n_node"], acc["n_err"]
-        T_pulled = acc0["tok_used"]
-        ok_stmts = acc0["ok"]
         h2d = n_in + 8 * (n_stmt + 1)
-        d2h = 24 * n_stmt + 16 * int(hb.n_node) + 32 * int(hb.n_err)
+        d2h = 24 * n_stmt + 8 * int(acc["n_node"]) + 32 * int(acc["n_err"])   # NutdbStmt, NutdbCNode (wire), NutdbError
         e2e = {"ms": e2e_ms, "h2d": h2d, "d2h": d2h}
         del h_text, h_offs
 
@@ -445,18 +538,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        cnt = alg_counts(text, offs)
-        scale = n_in / cnt["bytes"]
-        T = T_pulled if T_pulled is not None else int(cnt["T"] * scale)
-        M = int(cnt["M"] * scale)
-        b_alg = n_in + 9 * T + 16 * M + 16 * n_stmt
-        # algorithmic bytes of each kernel (DESIGN.md "Roofline accounting")
-        alg = {"k_lex_A": n_in, "k_lex_B": n_in, "k_lex_C": n_in, "k_lex_D": n_in + 9 * T,
-               "k_lex2_fn": n_in, "k_lex2_count": n_in, "k_lex2_emit": n_in + 9 * T,
-               "k_parse_fast": 9 * T + 16 * M + 16 * n_stmt, "k_parse": 9 * T + 16 * M + 16 * n_stmt,
-               "k_finalize": 16 * M + 16 * n_stmt}
-        dom = max((k for k in kernel_ms if k in alg), key=lambda k: kernel_ms[k])
-        ksum = sum(kernel_ms.values())
+        rf = roofline_numbers(text, offs, dev, T_pulled, peak)
+        dom = rf["dominant"]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):  # dram bytes per input byte from the committed ncu --set full capture, scaled to this launch
@@ -465,37 +548,42 @@ def main():
                 traffic = int(ent["dram_bytes_per_input_byte"] * n_in) if ent else None
             except Exception:
                 traffic = None
-        achieved = alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": tot_bytes / (dev_ms_max * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "wall_ms_per_step": wall_ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "statements_per_s": tot_stmts / (dev_ms_max * 1e-3),
-            "config": {"workload": WORKLOADS[args.config], "bytes_per_gpu": n_in, "statements_per_gpu": n_stmt,
-                       "tokens_per_gpu": n_tok, "nodes_per_gpu": n_node, "error_statements_per_gpu": n_err,
-                       "automaton_statements_per_gpu": n_slow, "exact_lexed_statements_per_gpu": n_punt,
-                       "sharding": "statement ranges, one shard per GPU, outputs stay sharded",
-                       "l2": "input (1 GiB class) and every intermediate array are larger than the 126 MB L2; no flush needed"},
-            "gpu_launches": launches_per_step * args.steps,
+            "config": workload_config(args.config, n_in, n_stmt),
+            "counts": {"tokens_per_gpu": dev["n_tok"], "nodes_per_gpu": dev["n_node"], "error_statements_per_gpu": dev["n_err"],
+                       "automaton_statements_per_gpu": dev["n_slow"], "exact_lexed_statements_per_gpu": dev["n_punt"]},
+            "gpu_launches": dev["launches"] * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "alg_bytes_per_launch": alg[dom], "kernel_ms": kernel_ms[dom],
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": rf["achieved"], "peak": peak, "unit": "GB/s",
+                         "frac": rf["achieved"] / peak, "traffic": traffic, "peak_source": peak_src,
+                         "alg_bytes_per_launch": rf["alg"][dom], "kernel_ms": kernel_ms[dom],
                          "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per input byte x bytes of this launch)",
-                         "kernel_share_of_step": kernel_ms[dom] / ksum},
-            "roofline_pipeline": {"alg_bytes": b_alg, "B_alg_over_N_in": b_alg / n_in, "T": T, "M": M, "S": n_stmt,
-                                  "achieved": b_alg / (dev_ms * 1e-3) / 1e9, "frac": b_alg / (dev_ms * 1e-3) / 1e9 / peak,
-                                  "sum_kernel_ms": ksum, "kernels_ms": {k: round(v, 4) for k, v in kernel_ms.items()}},
+                         "kernel_share_of_step": kernel_ms[dom] / rf["ksum"]},
+            "roofline_pipeline": rf["pipeline"],
         }
         if e2e:
             line["e2e"] = {"value": tot_bytes / (e2e_ms_max * 1e-3) / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
                            "ms_per_step": e2e_ms_max, "statements_per_s": tot_stmts / (e2e_ms_max * 1e-3),
                            "api": "nutdb_b200.stream.StreamParser: nutdb_gpu_parse_batch(pinned host text, host offsets, "
-                                  f"NUTDB_F_NO_TOKENS) per chunk on {args.e2e_workers} contexts -> pinned host stmt/node/err arrays",
+                                  f"NUTDB_F_NO_TOKENS) per chunk on {args.e2e_workers} contexts -> pinned host stmt / wire-node "
+                                  "(NutdbCNode, 8 B) / err arrays",
                            "chunk_bytes": args.e2e_chunk}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(text, offs)
+        del text, offs
+        if world == 1 and not args.no_extra_configs:
+            # the other single-GPU configurations of BASELINE.json, 256 MiB each (device-resident value, share of the
+            # slower paths, parity of a sample with the oracle), and the reference's own criterion bench shape
+            line["configs"] = {}
+            for c in (1, 3, 4):
+                if c != args.config:
+                    line["configs"][str(c)] = extra_config(ctx, c, args.extra_bytes, local, barrier, peak)
+            line["latency"] = single_call_latency(ctx)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -130,6 +130,22 @@ typedef struct {
   uint32_t b;
 } NutdbNode;
 
+/* The WIRE form of a node: 8 bytes, what the device produces and what crosses PCIe (NutdbBatch.cnode).  Same order
+ * (post-order per statement), same kind / sub.  It carries everything NutdbNode does -- a re-hydrator walks it with a
+ * stack (an interior node's children are the stack entries at or above its subtree start) and never needs `parent`:
+ *   interior : aux = flag bits, x = subtree_start
+ *   leaf     : aux = flag bit 0 | span length << 1, x = span start; the span is [x, x + length).  A length of
+ *              NUTDB_CN_LONG (32767) means "32767 bytes or more": the true length is in the batch's long_len table
+ *              under this node's index in long_idx (both sorted by node index; rare -- a 32 KB string literal).
+ * nutdb_batch_expand_nodes() turns them into NutdbNode records on the host. */
+typedef struct {
+  uint8_t kind;
+  uint8_t sub;
+  uint16_t aux;
+  uint32_t x;
+} NutdbCNode;
+#define NUTDB_CN_LONG 32767u
+
 #define NUTDB_NO_PARENT 0xFFFFFFFFu
 #define NUTDB_NK_FIRST_INTERIOR 32
 
@@ -323,9 +339,13 @@ typedef struct {
   const uint32_t *tok_start;/* [n_tok]  payload span start, statement-relative */
   const uint32_t *tok_end;  /* [n_tok] */
   const uint8_t *tok_kw;    /* [n_tok]  KeywordOrIdentifier: keyword id or 0; Integer/HexLiteral: digit count (max 255); else 0 */
-  const NutdbNode *node;    /* [n_node] */
+  const NutdbNode *node;    /* [n_node] expanded nodes: NULL in batches produced by the library (see cnode) */
   const NutdbError *err;    /* [n_err]  sorted by .stmt */
   void *impl;               /* opaque */
+  const NutdbCNode *cnode;  /* [n_node] wire nodes */
+  uint64_t n_long;          /* leaves whose span is NUTDB_CN_LONG bytes or more */
+  const uint32_t *long_idx; /* [n_long] their node indices, ascending */
+  const uint32_t *long_len; /* [n_long] their span lengths */
 } NutdbBatch;
 
 typedef struct NutdbCtx NutdbCtx;
@@ -356,7 +376,11 @@ int nutdb_gpu_parse_batch(NutdbCtx *ctx, const uint8_t *sql, const uint64_t *stm
                           uint64_t n_stmt, uint32_t flags, NutdbBatch *out);
 void nutdb_gpu_batch_free(NutdbCtx *ctx, NutdbBatch *batch);
 
-/* Device-side views of the last batch (valid until batch_free). */
+/* Expands the wire nodes of a batch into NutdbNode records (byte spans, child counts, parent links): pure host
+ * arithmetic, no parsing.  `out` must hold n_node records.  Returns 0, or NUTDB_E_ARG. */
+int nutdb_batch_expand_nodes(const NutdbBatch *batch, NutdbNode *out);
+
+/* Device-side views of the last batch (valid until batch_free); `node` points at the WIRE nodes (NutdbCNode). */
 typedef struct {
   const void *stmt, *tok_type, *tok_start, *tok_end, *tok_kw, *node, *err;
 } NutdbBatchDevice;

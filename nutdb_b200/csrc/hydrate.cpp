@@ -963,13 +963,67 @@ const NutdbError* find_error(const NutdbBatch* b, uint64_t i) {
 
 }  // namespace
 
+// Wire nodes (NutdbCNode) of one statement -> NutdbNode records: spans from (start, length), child counts and parent
+// links by walking each interior node's children backwards from the node before it (post-order: a child's subtree
+// ends right before its next sibling's begins).
+static uint32_t long_leaf_len(const NutdbBatch* b, uint32_t node_index) {
+  uint64_t lo = 0, hi = b->n_long;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) / 2;
+    if (b->long_idx[mid] < node_index) lo = mid + 1;
+    else hi = mid;
+  }
+  return (lo < b->n_long && b->long_idx[lo] == node_index) ? b->long_len[lo] : NUTDB_CN_LONG;
+}
+static void expand_stmt_nodes(const NutdbBatch* b, uint64_t begin, uint32_t count, NutdbNode* out) {
+  const NutdbCNode* c = b->cnode + begin;
+  auto subtree_start = [&](uint32_t r) -> uint32_t {
+    if (c[r].kind >= NUTDB_NK_FIRST_INTERIOR) return c[r].x;
+    return (c[r].kind == NUTDB_NK_IDENT && (c[r].aux & 1)) ? r - 1 : r;
+  };
+  for (uint32_t j = 0; j < count; j++) {
+    NutdbNode& o = out[j];
+    o.kind = c[j].kind;
+    o.sub = c[j].sub;
+    if (c[j].kind >= NUTDB_NK_FIRST_INTERIOR) {
+      o.aux = c[j].aux;
+      o.a = c[j].x;
+      uint32_t nchild = 0;
+      int64_t r = (int64_t)j - 1;
+      while (r >= (int64_t)c[j].x) {
+        out[r].parent = j;
+        nchild++;
+        r = (int64_t)subtree_start((uint32_t)r) - 1;
+      }
+      o.b = nchild;
+    } else {
+      o.aux = c[j].aux & 1u;
+      uint32_t len = c[j].aux >> 1;
+      if (len == NUTDB_CN_LONG) len = long_leaf_len(b, (uint32_t)(begin + j));
+      o.a = c[j].x;
+      o.b = c[j].x + len;
+      if (c[j].kind == NUTDB_NK_IDENT && (c[j].aux & 1) && j > 0) out[j - 1].parent = j;
+    }
+    if (j + 1 == count) o.parent = NUTDB_NO_PARENT;
+  }
+}
+
 extern "C" {
 
 size_t nutdb_fmt_debug(const NutdbBatch* batch, uint64_t i, const uint8_t* sql, size_t len, char* buf, size_t cap) {
   if (!batch || !batch->stmt || i >= batch->n_stmt) return 0;
   const NutdbStmt& s = batch->stmt[i];
-  if (s.status != NUTDB_ST_OK || s.node_count == 0 || !batch->node) return deliver(std::string(), buf, cap);
-  H h{batch->node + s.node_begin, s.node_count, sql, len, std::string()};
+  if (s.status != NUTDB_ST_OK || s.node_count == 0 || (!batch->node && !batch->cnode)) return deliver(std::string(), buf, cap);
+  std::vector<NutdbNode> expanded;
+  const NutdbNode* nodes;
+  if (batch->node) {
+    nodes = batch->node + s.node_begin;
+  } else {  // the library's batches carry wire nodes: expand this statement's
+    expanded.resize(s.node_count);
+    expand_stmt_nodes(batch, s.node_begin, s.node_count, expanded.data());
+    nodes = expanded.data();
+  }
+  H h{nodes, s.node_count, sql, len, std::string()};
   h.statement(s.node_count - 1);
   return deliver(h.o, buf, cap);
 }
@@ -984,6 +1038,15 @@ size_t nutdb_fmt_error(const NutdbBatch* batch, uint64_t i, const uint8_t* sql, 
   else if (e->cls == NUTDB_ST_REFERENCE_PANIC) r = "the reference panics on this input (unreachable!() at literal.rs:63)";
   else r = "nesting exceeds the device parser's limits";
   return deliver(r, buf, cap);
+}
+
+int nutdb_batch_expand_nodes(const NutdbBatch* batch, NutdbNode* out) {
+  if (!batch || !out || (batch->n_node && !batch->cnode) || (batch->n_stmt && !batch->stmt)) return NUTDB_E_ARG;
+  for (uint64_t i = 0; i < batch->n_stmt; i++) {
+    const NutdbStmt& s = batch->stmt[i];
+    if (s.status == NUTDB_ST_OK && s.node_count) expand_stmt_nodes(batch, s.node_begin, s.node_count, out + s.node_begin);
+  }
+  return NUTDB_OK;
 }
 
 }  // extern "C"

@@ -62,9 +62,8 @@ __device__ __forceinline__ void l4_issue_load(Lex4Shared& S, int b, uint32_t til
 __global__ void __launch_bounds__(L4_THREADS, L4_MINBLOCKS) k_lex4(const uint8_t* __restrict__ text,
                                                                     const uint32_t* __restrict__ bitmap, uint32_t n,
                                                                     uint32_t n_readable, const LexTables* __restrict__ gT,
-                                                                    Lex4Ranges rg, Lex3Out out,
-                                                                    const uint32_t* __restrict__ gate) {
-  if (*gate) return;  // invalid statement offsets (k_prep): nothing downstream may trust them
+                                                                    Lex4Ranges rg, Lex3Out out, uint32_t* gate) {
+  if (*gate & 1u) return;  // invalid statement offsets (k_prep): nothing downstream may trust them
   extern __shared__ __align__(16) unsigned char l3_smem[];
   Lex4Shared& S = *reinterpret_cast<Lex4Shared*>(l3_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -382,7 +381,10 @@ __global__ void __launch_bounds__(L4_THREADS, L4_MINBLOCKS) k_lex4(const uint8_t
           // (a range that ends on a window boundary: that window -- the last statement's token-range end -- may lie
           // behind the last tile)
           if ((re & 31u) == 0u) out.win_idx[(size_t)(re >> 5) + r] = seg_base + new_car.x;
-          if (new_car.x > seg_cap) atomicOr(out.counters + 4, 1u);  // the segment was too small: the batch is run again
+          if (new_car.x > seg_cap) {  // the segment was too small: the batch is run again, and the kernels behind
+            atomicOr(out.counters + 4, 1u);  // this one skip the attempt (bit 1 of the gate): its token ranges
+            atomicOr(gate, 2u);              // run into the neighbouring segments
+          }
         }
       }
       // (the carries are read after barrier A / C of the next tile, or after the barrier that follows the next ticket)

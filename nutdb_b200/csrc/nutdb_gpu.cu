@@ -922,7 +922,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
                                                           const uint32_t* __restrict__ tok_start,
                                                           const uint32_t* __restrict__ tok_end,
                                                           const uint32_t* __restrict__ punt,
-                                                          uint32_t* __restrict__ node_out, uint4* __restrict__ err_out) {
+                                                          uint2* __restrict__ node_out, uint4* __restrict__ err_out,
+                                                          uint32_t* __restrict__ long_count, uint2* __restrict__ long_out,
+                                                          uint32_t long_cap) {
   __shared__ uint2 ws[32];
   __shared__ uint32_t lbegin[FIN_THREADS + 1];
   __shared__ uint32_t ltok[FIN_THREADS];
@@ -972,13 +974,26 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
       else hi = mid;
     }
     // `lo` owns node j (statements without nodes share their offset with the next one and are skipped
-    // by "last k"); its nodes are [lbegin[lo], lbegin[lo+1]) of this block's range
-    const uint32_t first = lbegin[lo];
-    const uint32_t count = lbegin[lo + 1] - first;
-    CompactSrc cn{lsrc[lo]};
-    DTok tk{nullptr, tok_start + ltok[lo], tok_end + ltok[lo], nullptr, 0xFFFFFFFFu};
-    ExpandOut out{node_out + 4 * ((size_t)base.x + first)};
-    npar::expand_node(cn, j - first, count, tk, out);
+    // by "last k"); its nodes are [lbegin[lo], lbegin[lo+1]) of this block's range.
+    // The WIRE node (NutdbCNode): interior nodes as the parser left them (header, subtree start); a leaf's token
+    // index becomes its byte span (start, length in the upper 15 bits of aux).
+    const uint2 c = lsrc[lo][j - lbegin[lo]];
+    uint32_t w0 = c.x, w1 = c.y;
+    if ((c.x & 0xFFu) < NUTDB_NK_FIRST_INTERIOR) {
+      uint32_t a = 0, len = 0;
+      if (c.y != NUTDB_CN_NOTOK) {
+        a = tok_start[ltok[lo] + c.y];
+        len = tok_end[ltok[lo] + c.y] - a;
+      }
+      if (len >= NUTDB_CN_LONG) {  // (a 32 KB literal: its length goes to a side table the host sorts)
+        const uint32_t q = atomicAdd(long_count, 1u);
+        if (q < long_cap) long_out[q] = make_uint2(base.x + j, len);
+        len = NUTDB_CN_LONG;
+      }
+      w0 = (c.x & 0x0001FFFFu) | (len << 17);
+      w1 = a;
+    }
+    node_out[(size_t)base.x + j] = make_uint2(w0, w1);
   }
 }
 
@@ -1019,7 +1034,11 @@ struct NutdbCtx {
   bool debug_tiles = false, debug_timing = false;
   DevBuf dbgTim;
   uint32_t dbg_ntiles = 0;
+  bool debug_sync = false;  // NUTDB_GPU_DEBUG_SYNC=1: synchronise after every launch and name the kernel that failed
   DevBuf dbgTiles;
+  DevBuf longNodes;
+  HostBuf hLong;
+  std::vector<uint32_t> long_idx, long_len;
   DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
@@ -1116,6 +1135,14 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
     }                                                      \
     __VA_ARGS__;                                           \
     ctx->launches++;                                       \
+    if (ctx->debug_sync) {                                 \
+      const cudaError_t e_ = cudaStreamSynchronize(stream_); \
+      if (e_ != cudaSuccess) {                             \
+        ctx->err = std::string(name) + ": " + cudaGetErrorString(e_); \
+        fprintf(stderr, "nutdb_gpu: %s failed: %s\n", name, cudaGetErrorString(e_)); \
+        return NUTDB_E_CUDA;                               \
+      }                                                    \
+    }                                                      \
     if (ctx->profiling) {                                  \
       cudaEventRecord(r_.b, stream_);                      \
       ctx->recs.push_back(r_);                             \
@@ -1134,7 +1161,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->rangeByte, &c->rangeStmt, &c->rangeTokBase, &c->rangeCount, &c->rangeDense, &c->tokTypeD, &c->tokStartD, &c->tokEndD, &c->tokKwD, &c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->longNodes, &c->rangeByte, &c->rangeStmt, &c->rangeTokBase, &c->rangeCount, &c->rangeDense, &c->tokTypeD, &c->tokStartD, &c->tokEndD, &c->tokKwD, &c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1142,7 +1169,7 @@ void free_all(NutdbCtx* c) {
                  &c->splitTile, &c->splitPref, &c->splitOff};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
-  HostBuf* h[] = {&c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
+  HostBuf* h[] = {&c->hLong, &c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
                   &c->hRetry, &c->hSplit};
   for (HostBuf* b : h)
     if (b->p) cudaFreeHost(b->p);
@@ -1212,6 +1239,7 @@ NutdbCtx* nutdb_gpu_ctx_create(int device) {
   if (ok) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
+    if (const char* e = std::getenv("NUTDB_GPU_DEBUG_SYNC")) ctx->debug_sync = e[0] == '1';
   }
   if (!ok) {
     nutdb_gpu_ctx_destroy(ctx);
@@ -1539,7 +1567,7 @@ run_again:
     // ---- the one synchronisation of the call: counts the host needs to size what follows ----
     CK(cudaMemcpyAsync(hS, dS, 128, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (hS[0]) {
+    if (hS[0] & 1u) {
       ctx->err = "statement offsets must ascend and lie inside the batch";
       return NUTDB_E_ARG;
     }
@@ -1554,6 +1582,7 @@ run_again:
       }
       const bool seg_overflow = !use_lookback && hS[18] != 0;
       const bool giant = !use_lookback && (uint64_t)hS[22] > std::max<uint64_t>(4u << 20, 8ull * range_target);
+      if (ctx->debug_sync) fprintf(stderr, "nutdb_gpu: attempt %d n=%u nstmt=%u tok_cap=%u seg_end=%llu n_main=%llu n_extra=%llu overflow=%u longest=%u cap_num=%u lookback=%d\n", attempt, n, nstmt, tok_cap, (unsigned long long)seg_end, (unsigned long long)n_main, (unsigned long long)n_extra, hS[18], hS[22], ctx->tok_cap_num, (int)use_lookback);
       if (seg_overflow || giant || seg_end + n_extra > tok_cap) {  // an estimate was too small / the cuts do not fit: run again
         if (attempt >= 4) {
           ctx->err = "token buffers kept overflowing";
@@ -1607,13 +1636,15 @@ run_again:
     }
     n_node = hS[8];
     n_err = hS[9];
-    ENSURE_DEV(nodes, 16 * (n_node + 1));
+    ENSURE_DEV(nodes, 8 * (n_node + 1));
     ENSURE_DEV(errs, 32 * (n_err + 1));
+    const uint32_t long_cap = n / NUTDB_CN_LONG + 16u;  // (a long leaf spans that many bytes of its own)
+    ENSURE_DEV(longNodes, 8 * (size_t)long_cap);
     LAUNCH("k_finalize", k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
                                                (const uint2*)ctx->scratch.p, (const uint2*)ctx->retryNodes.p,
                                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
-                                               (const uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->nodes.p,
-                                               (uint4*)ctx->errs.p));
+                                               (const uint32_t*)ctx->puntFlag.p, (uint2*)ctx->nodes.p,
+                                               (uint4*)ctx->errs.p, dS + 26, (uint2*)ctx->longNodes.p, long_cap));
   } else {
     CK(cudaMemcpyAsync(hS, dS, 128, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1650,13 +1681,14 @@ run_again:
   out->n_err = n_err;
   if (!(flags & NUTDB_F_NO_HOST_COPY)) {
     ENSURE_HOST(hStmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
-    ENSURE_HOST(hNode, 16 * (n_node + 1));
+    ENSURE_HOST(hNode, 8 * (n_node + 1));
     ENSURE_HOST(hErr, 32 * (n_err + 1));
     if (nstmt) CK(cudaMemcpyAsync(ctx->hStmt.p, ctx->stmt.p, sizeof(NutdbStmt) * (size_t)nstmt, cudaMemcpyDeviceToHost, st));
-    if (n_node) CK(cudaMemcpyAsync(ctx->hNode.p, ctx->nodes.p, 16 * n_node, cudaMemcpyDeviceToHost, st));
+    if (n_node) CK(cudaMemcpyAsync(ctx->hNode.p, ctx->nodes.p, 8 * n_node, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hS + 48, dS + 26, 4, cudaMemcpyDeviceToHost, st));  // long leaves (almost always none)
     if (n_err) CK(cudaMemcpyAsync(ctx->hErr.p, ctx->errs.p, 32 * n_err, cudaMemcpyDeviceToHost, st));
     out->stmt = (const NutdbStmt*)ctx->hStmt.p;
-    out->node = (const NutdbNode*)ctx->hNode.p;
+    out->cnode = (const NutdbCNode*)ctx->hNode.p;
     out->err = (const NutdbError*)ctx->hErr.p;
     if (!(flags & NUTDB_F_NO_TOKENS)) {
       ENSURE_HOST(hTokType, (size_t)ntok + 16);
@@ -1678,6 +1710,24 @@ run_again:
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
+  if (!(flags & NUTDB_F_NO_HOST_COPY) && n_node && hS[48]) {  // leaves of 32 KB and more: their lengths, by node index
+    const uint32_t nl = std::min<uint32_t>(hS[48], n / NUTDB_CN_LONG + 16u);
+    ENSURE_HOST(hLong, 8 * (size_t)nl);
+    CK(cudaMemcpy(ctx->hLong.p, ctx->longNodes.p, 8 * (size_t)nl, cudaMemcpyDeviceToHost));
+    std::vector<std::pair<uint32_t, uint32_t>> v(nl);
+    const uint32_t* hp = (const uint32_t*)ctx->hLong.p;
+    for (uint32_t i = 0; i < nl; i++) v[i] = {hp[2 * i], hp[2 * i + 1]};
+    std::sort(v.begin(), v.end());
+    ctx->long_idx.resize(nl);
+    ctx->long_len.resize(nl);
+    for (uint32_t i = 0; i < nl; i++) {
+      ctx->long_idx[i] = v[i].first;
+      ctx->long_len[i] = v[i].second;
+    }
+    out->n_long = nl;
+    out->long_idx = ctx->long_idx.data();
+    out->long_len = ctx->long_len.data();
+  }
   cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&ctx->ms[2], ctx->ev[2], ctx->ev[3]);
@@ -1753,7 +1803,7 @@ int nutdb_gpu_batch_hash(const NutdbBatch* batch, uint64_t* out) {
     k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.tok_end, batch->n_tok, 3, acc);
     k_hash<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.tok_kw, batch->n_tok, 4, acc);
   }
-  if (batch->n_node) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.node, batch->n_node * (sizeof(NutdbNode) / 4), 5, acc);
+  if (batch->n_node) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.node, batch->n_node * (sizeof(NutdbCNode) / 4), 5, acc);
   if (batch->n_err) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.err, batch->n_err * (sizeof(NutdbError) / 4), 6, acc);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->hSmall.p, acc, 8, cudaMemcpyDeviceToHost, st));

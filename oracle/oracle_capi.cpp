@@ -168,7 +168,7 @@ struct OraBatch {
   std::vector<NutdbStmt> stmt;
   std::vector<NutdbNode> node;
   std::vector<NutdbError> err;
-  std::vector<uint8_t> tok_type;
+  std::vector<uint8_t> tok_type, tok_kw;  // tok_kw: keyword id of a KeywordOrIdentifier token (keyword.rs), else 0
   std::vector<uint32_t> tok_start, tok_end;
   uint64_t t_alg = 0, m_alg = 0;
 };
@@ -199,6 +199,7 @@ void* ora_parse_batch(const char* text, const uint64_t* offs, uint64_t n, int nt
   }
   b->node.reserve(nn);
   b->tok_type.reserve(nt);
+  b->tok_kw.reserve(nt);
   b->tok_start.reserve(nt);
   b->tok_end.reserve(nt);
   for (uint64_t i = 0; i < n; i++) {
@@ -214,6 +215,9 @@ void* ora_parse_batch(const char* text, const uint64_t* offs, uint64_t n, int nt
       b->tok_type.push_back(p.t);
       b->tok_start.push_back((uint32_t)p.span.start);
       b->tok_end.push_back((uint32_t)p.span.end);
+      b->tok_kw.push_back(p.t == NUTDB_TT_KeywordOrIdentifier
+                              ? (uint8_t)keyword_id(sv(text + offs[i] + p.span.start, p.span.end - p.span.start))
+                              : (uint8_t)0);
     }
     if (res[i].status != NUTDB_ST_OK) {
       NutdbError e = res[i].rec;
@@ -238,6 +242,7 @@ const NutdbStmt* ora_batch_stmt(void* h) { return ((OraBatch*)h)->stmt.data(); }
 const NutdbNode* ora_batch_node(void* h) { return ((OraBatch*)h)->node.data(); }
 const NutdbError* ora_batch_err(void* h) { return ((OraBatch*)h)->err.data(); }
 const uint8_t* ora_batch_tok_type(void* h) { return ((OraBatch*)h)->tok_type.data(); }
+const uint8_t* ora_batch_tok_kw(void* h) { return ((OraBatch*)h)->tok_kw.data(); }
 const uint32_t* ora_batch_tok_start(void* h) { return ((OraBatch*)h)->tok_start.data(); }
 const uint32_t* ora_batch_tok_end(void* h) { return ((OraBatch*)h)->tok_end.data(); }
 

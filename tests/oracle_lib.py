@@ -36,6 +36,9 @@ ERR_DT = np.dtype([("stmt", "<u4"), ("cls", "<u2"), ("code", "<u2"), ("line", "<
                    ("pos", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
 
 
+TT_KEYWORD_OR_IDENTIFIER = 0   # include/nutdb_gpu.h NUTDB_TT_KeywordOrIdentifier (token.rs:6)
+
+
 def build():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
 
@@ -82,7 +85,7 @@ def lib():
     L.ora_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     L.ora_batch_free.argtypes = [C.c_void_p]
     L.ora_batch_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 5
-    for f in ("stmt", "node", "err", "tok_type", "tok_start", "tok_end"):
+    for f in ("stmt", "node", "err", "tok_type", "tok_kw", "tok_start", "tok_end"):
         getattr(L, "ora_batch_" + f).restype = C.c_void_p
         getattr(L, "ora_batch_" + f).argtypes = [C.c_void_p]
     L.ora_bench.restype = C.c_double
@@ -115,6 +118,45 @@ def tokenize(sql):
         err = dict(type=et.value, site=es.value, pos=ep.value, line=el.value, col=ec.value,
                    ctx=ctx.value.decode("utf-8", "replace"))
     return toks, err
+
+
+def tokenize_arrays(sql):
+    """tokenize() without the per-token Python objects: (types u8, starts u32, ends u32, error | None)."""
+    L = lib()
+    raw = _b(sql)
+    cap = len(raw) + 2
+    ty = np.zeros(cap, np.uint8)
+    st = np.zeros(cap, np.uint32)
+    en = np.zeros(cap, np.uint32)
+    et, es = C.c_int(0), C.c_int(0)
+    ep, el, ec = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    ctx = C.create_string_buffer(256)
+    n = L.ora_tokenize(raw, len(raw), ty.ctypes.data, st.ctypes.data, en.ctypes.data, cap, C.byref(et), C.byref(es),
+                       C.byref(ep), C.byref(el), C.byref(ec), ctx, 256)
+    err = dict(type=et.value, site=es.value, pos=ep.value) if es.value else None
+    return ty[:n], st[:n], en[:n], err
+
+
+TT_SEMICOLON, TT_WHITESPACE, TT_EOF = 13, 38, 39   # include/nutdb_gpu.h (token.rs ordinals)
+
+
+def split_statements(buf):
+    """Expected output of the raw-buffer statement splitter, derived from the REFERENCE TOKENIZER (not from the
+    product's context automaton): one sequential tokenizer walk over the whole buffer (tokenizer/mod.rs:66-112); every
+    SemiColon token ends a statement (the statement includes it); what follows the last one is a final statement
+    unless it is only Whitespace tokens.  Returns (offsets u64, valid_upto): the tokenizer stops at its first error, so
+    only the offsets up to `valid_upto` are defined by it (valid_upto = len(buf) + 1 when the buffer lexes cleanly)."""
+    raw = _b(buf)
+    ty, st, en, err = tokenize_arrays(raw)
+    semi = en[ty == TT_SEMICOLON].astype(np.uint64)
+    offs = np.concatenate([np.zeros(1, np.uint64), semi])
+    if err is not None:   # (the error may be reported at EOF for a token that began earlier: pinned up to the last good token)
+        return offs, int(en[-1]) if len(en) else 0
+    last = int(semi[-1]) if len(semi) else 0
+    tail = (en > last) & (ty != TT_WHITESPACE) & (ty != TT_EOF)
+    if tail.any() or (last < len(raw) and not len(ty)):
+        offs = np.concatenate([offs, np.array([len(raw)], np.uint64)])
+    return offs, len(raw) + 1
 
 
 def get_pos(sql, cursor):
@@ -201,6 +243,7 @@ def parse_batch(text, offs, nthreads=0):
         b.node = arr(L.ora_batch_node(h), n_node, NODE_DT)
         b.err = arr(L.ora_batch_err(h), n_err, ERR_DT)
         b.tok_type = arr(L.ora_batch_tok_type(h), n_tok, np.uint8)
+        b.tok_kw = arr(L.ora_batch_tok_kw(h), n_tok, np.uint8)
         b.tok_start = arr(L.ora_batch_tok_start(h), n_tok, np.uint32)
         b.tok_end = arr(L.ora_batch_tok_end(h), n_tok, np.uint32)
         b.t_alg, b.m_alg = t_alg, m_alg

@@ -61,16 +61,26 @@ def compare_with_oracle(got, text, offs, stmts=None, check_tokens=True):
                    f": {sql(i)!r}")
         return bad
     if check_tokens:
-        # tokens the reference pulled == the first tok_used tokens of each statement
-        for i in range(n):
-            u = int(ws["tok_used"][i])
-            if int(offs[i + 1]) == int(offs[i]):
-                continue
-            gb, wb = int(gs["tok_begin"][i]), int(ws["tok_begin"][i])
-            if not (np.array_equal(got.tok_type[gb:gb + u], want.tok_type[wb:wb + u]) and
-                    np.array_equal(got.tok_start[gb:gb + u], want.tok_start[wb:wb + u]) and
-                    np.array_equal(got.tok_end[gb:gb + u], want.tok_end[wb:wb + u])):
-                bad.append(f"stmt {i}: pulled tokens differ: {sql(i)!r}")
-                if len(bad) > 3:
-                    break
+        # tokens the reference pulled == the first tok_used tokens of each statement (one gather per array, no
+        # per-statement loop: the 1 GiB-class workloads are compared with tokens too)
+        u = ws["tok_used"].astype(np.int64)
+        u[(offs[1:] == offs[:-1])] = 0
+        tot = int(u.sum())
+        if tot:
+            first = np.cumsum(u) - u                       # position of each statement's first pulled token in the gather
+            rel = np.arange(tot, dtype=np.int64) - np.repeat(first, u)
+            gi = np.repeat(gs["tok_begin"].astype(np.int64), u) + rel
+            wi = np.repeat(ws["tok_begin"].astype(np.int64), u) + rel
+            if gi.max(initial=-1) >= len(got.tok_type):
+                bad.append("pulled tokens run past the token arrays")
+                return bad
+            word = want.tok_type[wi] == O.TT_KEYWORD_OR_IDENTIFIER
+            diff = ((got.tok_type[gi] != want.tok_type[wi]) | (got.tok_start[gi] != want.tok_start[wi]) |
+                    (got.tok_end[gi] != want.tok_end[wi]) | (word & (got.tok_kw[gi] != want.tok_kw[wi])))
+            for k in np.nonzero(diff)[0][:4]:
+                i = int(np.searchsorted(first, k, side="right") - 1)
+                j = int(k - first[i])
+                bad.append(f"stmt {i}: pulled token {j} differs: got ({got.tok_type[gi[k]]}, {got.tok_start[gi[k]]}, "
+                           f"{got.tok_end[gi[k]]}, kw {got.tok_kw[gi[k]]}) oracle ({want.tok_type[wi[k]]}, "
+                           f"{want.tok_start[wi[k]]}, {want.tok_end[wi[k]]}, kw {want.tok_kw[wi[k]]}): {sql(i)!r}")
     return bad

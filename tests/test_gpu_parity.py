@@ -63,7 +63,7 @@ def test_empty_and_degenerate_batches(ctx):
 def test_synthetic_config(ctx, config):
     text, offs = W.generate(config, 4 << 20)
     got = ctx.parse_batch(text, offs)
-    bad = P.compare_with_oracle(got, text, offs, check_tokens=(config != 2))
+    bad = P.compare_with_oracle(got, text, offs)
     assert not bad, "\n".join(bad)
 
 
@@ -124,6 +124,28 @@ def test_full_token_stream_incl_whitespace_and_comments(ctx):
             assert g[len(want)] == (40, err["pos"], err["site"]), s
 
 
+def test_full_token_stream_on_the_lexer_stress_set(ctx):
+    """NUTDB_F_ALL_TOKENS over 4 MiB of config 3 (strings, quoted identifiers, comments, 5 % malformed): every token
+    of every statement incl. Whitespace / Comment, and the poison token at the reference's error position / site."""
+    from nutdb_b200 import gpu
+    text, offs = W.generate(3, 4 << 20, seed=21)
+    got = ctx.parse_batch(text, offs, flags=gpu.F_ALL_TOKENS)
+    n_err = 0
+    for i in range(len(offs) - 1):
+        s = bytes(text[int(offs[i]):int(offs[i + 1])])
+        ty, st, en, err = O.tokenize_arrays(s)
+        b = int(got.stmt["tok_begin"][i])
+        k = len(ty)
+        assert np.array_equal(got.tok_type[b:b + k], ty) and np.array_equal(got.tok_start[b:b + k], st) and \
+            np.array_equal(got.tok_end[b:b + k], en), s
+        if err is not None:
+            n_err += 1
+            assert (int(got.tok_type[b + k]), int(got.tok_start[b + k]), int(got.tok_end[b + k])) == (40, err["pos"], err["site"]), s
+        else:
+            assert int(got.stmt["tok_count"][i]) >= k, s
+    assert n_err > 100
+
+
 def test_deep_nesting_takes_the_retry_path(ctx):
     d = 256
     stmts = ["select " + "(" * d + "1" + ")" * d, "select " + "(select " * d + "1" + ")" * d,
@@ -141,7 +163,7 @@ def test_device_input_and_no_host_copy(ctx):
     do = torch.from_numpy(offs.astype(np.int64)).cuda()
     torch.cuda.synchronize()
     got = ctx.parse_batch_raw(dt.data_ptr(), do.data_ptr(), len(offs) - 1, gpu.F_DEVICE_INPUT)
-    bad = P.compare_with_oracle(got, text, offs, check_tokens=False)
+    bad = P.compare_with_oracle(got, text, offs)
     assert not bad, "\n".join(bad)
     # misaligned device text pointer
     dt2 = torch.zeros(len(text) + 3, dtype=torch.uint8, device="cuda")
@@ -159,6 +181,11 @@ def test_bad_arguments(ctx):
     from nutdb_b200 import gpu
     with pytest.raises(gpu.NutdbGpuError):
         ctx.parse_batch(b"select 1", np.array([0, 8, 4], np.uint64))
+    # an interior offset far beyond the batch: ascending pairs, but outside [off[0], off[n]] (must be NUTDB_E_ARG,
+    # not an out-of-bounds write into the statement-start bitmap)
+    with pytest.raises(gpu.NutdbGpuError):
+        ctx.parse_batch(b"select 1, 2", np.array([0, 1000000000, 1000000001, 10], np.uint64))
+    check(ctx, ["select 1", "select 2"])   # the context is still usable
 
 
 def test_parser_parse_mirrors_the_reference_entry(ctx):
@@ -201,15 +228,28 @@ def test_stream_parser_chunks_match_one_batch(ctx):
     assert sum(len(got[k][2]) for k in got) == whole.n_err
 
 
+def check_split(ctx, buf):
+    """Splitter output vs the offsets the reference tokenizer defines (oracle_lib.split_statements): identical when
+    the buffer lexes cleanly, identical up to the tokenizer's first error otherwise."""
+    got = ctx.split_statements(buf)
+    want, upto = O.split_statements(buf)
+    if upto > len(buf):
+        assert np.array_equal(got, want), bytes(buf[:200])
+    else:   # the reference tokenizer stops at its first error: the offsets in front of it are pinned
+        k = int(np.searchsorted(got, upto, side="right"))
+        kw = int(np.searchsorted(want, upto, side="right"))
+        assert np.array_equal(got[:k], want[:kw]), bytes(buf[:200])
+    return got
+
+
 def test_statement_splitter(ctx):
     import emul_lib as E
     # a query log as one buffer: the generators end every statement with ";\n"
     for config in (2, 3, 4):
         text, offs = W.generate(config, 3 << 20)
         buf = text[:int(offs[-1])]
-        got = ctx.split_statements(buf)
-        want = E.split(buf)
-        assert np.array_equal(got, want)
+        got = check_split(ctx, buf)
+        assert np.array_equal(got, E.split(buf))   # (sequential run of the kernels' own context automaton)
         if config != 3:   # valid statements: one ';' each, at the end (malformed ones of config 3 may hide or add some)
             assert len(got) == len(offs) and np.array_equal(got[1:], offs[1:] - 1)
         # and the split batch parses like the original one
@@ -218,10 +258,19 @@ def test_statement_splitter(ctx):
         if config != 3:
             assert np.array_equal(b1.stmt["status"], b0.stmt["status"])
             assert np.array_equal(b1.node["kind"], b0.node["kind"])
+    # config 3 without its malformed statements lexes cleanly end to end: the whole log is pinned by the tokenizer
+    text, offs = W.generate(3, 3 << 20, seed=11)
+    st = O.parse_batch(text, offs).stmt["status"]
+    keep = [bytes(text[int(offs[i]):int(offs[i + 1])]) for i in np.nonzero(st == 0)[0]]
+    buf = np.frombuffer(b"".join(keep), np.uint8)
+    want, upto = O.split_statements(buf)
+    assert upto > len(buf) and len(want) > 1000
+    assert np.array_equal(ctx.split_statements(buf), want)
     cases = [b"", b";", b" ;; ", b"select 1", b"select ';' , \";\" , `;` ; select 2 -- ; x\n; /* ; */ select 3;  \n",
              b"select 'it''s; ok'; select 'a\\'; b'; select 4", b"select 1 /* open ; comment", b"select 'open ; string",
              b"a;" * 5000, b"-- only a comment; really\n", b"select 1;\n\n\t "]
     for c in cases + fuzz.fuzz_statements([b"; ".join(CORPUS[:4])], 200, seed=5, max_mut=6):
+        check_split(ctx, np.frombuffer(c, np.uint8))
         assert np.array_equal(ctx.split_statements(c), E.split(c)), c
 
 
