@@ -187,56 +187,111 @@ def run_reference(args, rank, world):
 def run_log(args, rank, world, local, barrier):
     """a fixed statement log (default 64 GiB, 1 GiB chunks of the config-2 generator) parsed
     by N GPUs -- STRONG scaling.  Chunks are dealt in contiguous ranges, generated on the host and pre-staged in HBM
-    before the timed region; outputs stay sharded on the GPUs (no gather: a device-resident consumer reads them in
-    place).  After timing, a 64-bit checksum of every chunk's outputs is computed on the device and summed over chunks
-    and ranks: it must not depend on N."""
+    before the timed regions.  Two timed regions: `value` = all kernels of every chunk with the outputs left sharded
+    on the GPUs (CUDA events); `gather` = the same log through the C dispatcher (nutdb_gpu_mctx_parse_shards) with
+    every chunk's statement records, wire nodes and error records GATHERED to pinned host memory inside the timed
+    region, each GPU over its own PCIe link.  After timing, a 64-bit checksum of every chunk's outputs is computed on
+    the device and summed over chunks and ranks: it must not depend on N.
+
+    --single-process: one process drives all N GPUs through one dispatcher (the C-ABI multi-GPU path a Rust host
+    would use); --gather device0 then gathers into GPU 0's memory over NVLink instead."""
     import concurrent.futures as cf
     import torch
     import torch.distributed as dist
     from nutdb_b200 import gpu, workload as W
     chunk_bytes = min(args.bytes, 1 << 30)
-    n_chunks = max(world, args.log_bytes // chunk_bytes)
-    mine = list(range(rank * n_chunks // world, (rank + 1) * n_chunks // world))
-    ctx = gpu.Context(local)
+    single = args.single_process
+    ndev = args.gpus if single else 1            # devices this process drives
+    nparts = args.gpus if single else world      # GPUs sharing the log
+    part0 = 0 if single else rank
+    n_chunks = max(nparts, args.log_bytes // chunk_bytes)
+    devs = list(range(ndev)) if single else [local]
+    mine = []                                     # (chunk, device index in devs)
+    for d in range(ndev):
+        part = part0 + d
+        mine += [(c, d) for c in range(part * n_chunks // nparts, (part + 1) * n_chunks // nparts)]
+    ctxs = [gpu.Context(dv) for dv in devs]
     staged = []
 
-    def gen(c):
-        return c, W.generate(2, chunk_bytes, seed=W.SEEDS[5] + c)
+    def gen(cd):
+        return cd, W.generate(2, chunk_bytes, seed=W.SEEDS[5] + cd[0])
 
     first_host = None
     with cf.ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1) // max(1, world)))) as ex:
-        for c, (text, offs) in ex.map(gen, mine):
+        for (c, d), (text, offs) in ex.map(gen, mine):
             if first_host is None and args.verify:
                 k = int(np.searchsorted(offs, np.uint64(2 << 20), side="right")) - 1
                 first_host = (text[:int(offs[k])].copy(), offs[:k + 1].copy())
-            staged.append((c, torch.from_numpy(text).cuda(), torch.from_numpy(offs.view(np.int64)).cuda(), len(offs) - 1,
+            dv = torch.device("cuda", devs[d])
+            staged.append((c, d, torch.from_numpy(text).to(dv), torch.from_numpy(offs.view(np.int64)).to(dv), len(offs) - 1,
                            int(offs[-1])))
-    torch.cuda.synchronize()
-    my_bytes = sum(x[4] for x in staged)
-    my_stmts = sum(x[3] for x in staged)
+    for dv in devs:
+        torch.cuda.synchronize(dv)
+    my_bytes = sum(x[5] for x in staged)
+    my_stmts = sum(x[4] for x in staged)
     flags = gpu.F_DEVICE_INPUT | gpu.F_NO_HOST_COPY
 
     def one_pass(hashes=None):
-        for c, dt, do, ns, nb in staged:
-            b = ctx.parse_batch_raw(dt.data_ptr(), do.data_ptr(), ns, flags, copy=False)
+        for c, d, dt, do, ns, nb in staged:
+            b = ctxs[d].parse_batch_raw(dt.data_ptr(), do.data_ptr(), ns, flags, copy=False)
             if hashes is not None:
                 hashes.append((c, b.device_hash()))
 
-    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    # ---- device-resident: kernels only, outputs stay sharded (one context per device; devices one after the other in
+    # the single-process mode, so that number is only meaningful per device there) ----
+    streams = [torch.cuda.ExternalStream(cx.stream(), device=torch.device("cuda", dv)) for cx, dv in zip(ctxs, devs)]
     for _ in range(args.warmup):
         one_pass()
-    launches = ctx.launches() * len(staged)
-    sampler = ClockSampler(local)
+    launches = sum(ctxs[d].launches() for c, d, *_ in staged)
+    sampler = ClockSampler(devs[0])
     sampler.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(lib_stream)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in devs]
+    for (e0, e1), st in zip(ev, streams):
+        e0.record(st)
     for _ in range(args.steps):
         one_pass()
-    e1.record(lib_stream)
+    for (e0, e1), st in zip(ev, streams):
+        e1.record(st)
+    for dv in devs:
+        torch.cuda.synchronize(dv)
     barrier()
-    dev_ms = e0.elapsed_time(e1) / args.steps
+    dev_ms = max(e0.elapsed_time(e1) for e0, e1 in ev) / args.steps
     clocks = sampler.stop()
+
+    # ---- with the gather: the C dispatcher, outputs to pinned host memory (or GPU 0) inside the timed region ----
+    gather = None
+    if args.gather != "none":
+        m = gpu.MultiContext(devs, args.e2e_workers)
+        gflags = gpu.F_NO_TOKENS | (gpu.MF_GATHER_DEVICE0 if args.gather == "device0" else 0)
+        shards = [(d, dt.data_ptr(), do.data_ptr(), ns, gpu.F_DEVICE_INPUT, 0) for c, d, dt, do, ns, nb in staged]
+        acc = {}
+        lock = threading.Lock()
+
+        def consume(ch):   # the consumer's read of a gathered chunk
+            r = ch.raw
+            with lock:
+                acc["bytes"] = acc.get("bytes", 0) + 24 * r.n_stmt + 8 * r.n_node + 32 * r.n_err
+                acc["stmts"] = acc.get("stmts", 0) + r.n_stmt
+                if not ch.on_device and r.n_stmt:
+                    acc["last"] = int(ch.batch.stmt["status"][-1]) + int(ch.batch.cnode["kind"][-1])
+
+        for _ in range(2):
+            acc.clear()
+            m.parse_shards(shards, consume, gflags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            acc.clear()
+            m.parse_shards(shards, consume, gflags)
+        for dv in devs:
+            torch.cuda.synchronize(dv)
+        barrier()
+        g_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        assert acc["stmts"] == my_stmts
+        gather = {"ms": g_ms, "bytes": acc["bytes"]}
+        m.close()
+
     # ---- checksum of all outputs (untimed) ----
     hs = []
     one_pass(hs)
@@ -254,7 +309,7 @@ def run_log(args, rank, world, local, barrier):
     if args.verify and first_host is not None:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import parity as P
-        got = ctx.parse_batch(first_host[0], first_host[1])
+        got = ctxs[0].parse_batch(first_host[0], first_host[1])
         bad = P.compare_with_oracle(got, first_host[0], first_host[1])
         verified = not bad
         if bad:
@@ -271,25 +326,41 @@ def run_log(args, rank, world, local, barrier):
     tot_bytes = allred(float(my_bytes), dist.ReduceOp.SUM)
     tot_stmts = allred(float(my_stmts), dist.ReduceOp.SUM)
     ok_all = allred(0.0 if verified is False else 1.0, dist.ReduceOp.MIN)
+    g_ms_max = allred(gather["ms"], dist.ReduceOp.MAX) if gather else None
+    g_bytes = allred(float(gather["bytes"]), dist.ReduceOp.SUM) if gather else None
     if world > 1:  # the checksum: a wrapping 64-bit sum over ranks
         t = torch.tensor([total - (1 << 64) if total >= (1 << 63) else total], dtype=torch.int64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         total = int(t.item()) & M64
     if rank == 0:
-        line = {"metric": METRIC, "value": tot_bytes / (dev_ms_max * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
+        peak, _ = peaks()
+        line = {"metric": METRIC, "value": tot_bytes / (dev_ms_max * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": nparts,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "statements_per_s": tot_stmts / (dev_ms_max * 1e-3),
                 "config": {"workload": WORKLOADS[5], "log_bytes": int(tot_bytes), "chunk_bytes": chunk_bytes,
                            "chunks": n_chunks, "statements": int(tot_stmts),
-                           "timed_region": "all kernels of every chunk, inputs resident in HBM, outputs left sharded on the "
-                                           "GPUs (no gather)",
+                           "processes": "one process, one dispatcher over all GPUs" if single else "one process per GPU (torchrun)",
+                           "timed_region": "value: all kernels of every chunk, inputs resident in HBM, outputs left sharded on "
+                                           "the GPUs; gather: see there",
                            "l2": "each chunk and its intermediates exceed the 126 MB L2; no flush needed"},
                 "gpu_launches": launches * args.steps, "clocks": clocks,
                 "output_hash": f"{total:016x}",
                 "oracle_sample_ok": None if not args.verify else bool(ok_all)}
+        if single and ndev > 1:
+            line["value_note"] = "single-process mode drives the devices one after the other in the kernel-only region: `value` is per device; the gather region runs them concurrently"
+        if gather:
+            line["gather"] = {"value": tot_bytes / (g_ms_max * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": g_ms_max,
+                              "statements_per_s": tot_stmts / (g_ms_max * 1e-3),
+                              "to": "pinned host memory, each GPU over its own PCIe link" if args.gather == "host"
+                                    else "GPU 0 memory over NVLink (cudaMemcpyPeerAsync)",
+                              "gathered_bytes_per_step": int(g_bytes),
+                              "gather_rate_gbs": g_bytes / (g_ms_max * 1e-3) / 1e9,
+                              "api": f"nutdb_gpu_mctx_parse_shards, {args.e2e_workers} contexts per GPU, NUTDB_F_NO_TOKENS; "
+                                     "timed by the host clock between device synchronisations (several streams per GPU)"}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for cx in ctxs:
+        cx.close()
 
 
 def device_run(ctx, text, offs, local, steps, warmup, barrier):
@@ -423,6 +494,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--log-bytes", type=int, default=64 << 30, help="config 5: total bytes of the statement log")
+    ap.add_argument("--gather", default="host", choices=["host", "device0", "none"], help="config 5: where the outputs are gathered")
+    ap.add_argument("--single-process", action="store_true", help="config 5: one process drives all --gpus devices through one dispatcher")
     ap.add_argument("--verify", action="store_true", help="config 5: check a sample of every rank's first chunk against the oracle")
     ap.add_argument("--bytes", type=int, default=1 << 30)
     ap.add_argument("--no-cpu-baseline", action="store_true")

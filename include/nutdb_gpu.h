@@ -364,8 +364,8 @@ enum {
   NUTDB_E_NOMEM = -3
 };
 
-/* Create a context bound to one CUDA device (one process per GPU; the multi-GPU dispatcher
- * lives above this ABI).  Returns NULL on failure. */
+/* Create a context bound to one CUDA device (one process per GPU, or several contexts under the dispatcher
+ * below: nutdb_gpu_mctx_*).  Returns NULL on failure. */
 NutdbCtx *nutdb_gpu_ctx_create(int device);
 void nutdb_gpu_ctx_destroy(NutdbCtx *ctx);
 const char *nutdb_gpu_last_error(const NutdbCtx *ctx);
@@ -429,6 +429,59 @@ uint64_t nutdb_gpu_last_exact_lexed_statements(const NutdbCtx *ctx);
 /* The cudaStream_t every kernel and copy of this context is issued on (for callers that want to
  * order their own work or record their own events against it). */
 void *nutdb_gpu_ctx_stream(const NutdbCtx *ctx);
+
+/* ----------------------------------------------------------------------------------------
+ * Multi-GPU batch dispatcher (north_star: "a multi-GPU batch dispatcher"; statements are independent --
+ * Parser::parse keeps no state across calls, src/parser/mod.rs:21-37 -- so a batch shards by statement ranges).
+ * One dispatcher drives `n_devices` GPUs of one box from one process: `workers_per_device` contexts per device, one
+ * host thread each.  A call parses SHARDS (statement ranges) on their devices and GATHERS each shard's outputs --
+ * statement records, wire nodes, error records, and the token arrays unless NUTDB_F_NO_TOKENS -- to one place: pinned
+ * host memory (each device copies over its own PCIe link) or, with NUTDB_MF_GATHER_DEVICE0, the memory of the first
+ * device (cudaMemcpyPeerAsync: NVLink).  No collective is involved: nothing is reduced.  The consumer gets one
+ * callback per shard, from the worker thread that finished it (concurrently from several threads unless
+ * NUTDB_MF_SERIAL_CALLBACKS); the views are valid until the callback returns.  Indices inside a chunk (tok_begin,
+ * node_begin, err.stmt) are chunk-local; `first_stmt` is the chunk's first statement in the caller's numbering.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct NutdbMCtx NutdbMCtx;
+
+typedef struct {
+  int device_index;        /* position in the dispatcher's device list */
+  const uint8_t *sql;      /* text; a device pointer on that device with NUTDB_F_DEVICE_INPUT in `flags` */
+  const uint64_t *stmt_off;/* n_stmt + 1 ascending offsets into sql (same memory space as sql) */
+  uint64_t n_stmt;
+  uint32_t flags;          /* 0 or NUTDB_F_DEVICE_INPUT */
+  uint64_t first_stmt;     /* handed through to the chunk */
+} NutdbMShard;
+
+typedef struct {
+  uint64_t shard;          /* index into the shard list */
+  uint64_t first_stmt;
+  int device;              /* CUDA ordinal that parsed it */
+  int on_device;           /* 0: batch pointers are pinned host memory; 1: memory of the dispatcher's first device */
+  NutdbBatch batch;        /* counts, stmt, cnode, err (+ tokens); long_idx / long_len are always host memory */
+} NutdbMChunk;
+
+typedef void (*nutdb_chunk_fn)(void *user, const NutdbMChunk *chunk);
+
+#define NUTDB_MF_GATHER_DEVICE0 0x100u   /* gather to the first device's memory instead of pinned host memory */
+#define NUTDB_MF_SERIAL_CALLBACKS 0x200u /* never run two callbacks at the same time */
+
+NutdbMCtx *nutdb_gpu_mctx_create(const int *devices, int n_devices, int workers_per_device);
+void nutdb_gpu_mctx_destroy(NutdbMCtx *m);
+const char *nutdb_gpu_mctx_last_error(const NutdbMCtx *m);
+int nutdb_gpu_mctx_device_count(const NutdbMCtx *m);
+/* Parses the shards on their devices (each device's shards in list order) and gathers.  flags: NUTDB_F_NO_TOKENS,
+ * NUTDB_MF_*.  Returns NUTDB_OK or the first error (nutdb_gpu_mctx_last_error). */
+int nutdb_gpu_mctx_parse_shards(NutdbMCtx *m, const NutdbMShard *shards, uint64_t n_shards, uint32_t flags,
+                                nutdb_chunk_fn fn, void *user);
+/* One HOST batch (the arguments of nutdb_gpu_parse_batch; any size): cut at statement boundaries into chunks of about
+ * `chunk_bytes`, contiguous ranges of chunks dealt to the devices balanced by bytes, parsed and gathered as above. */
+int nutdb_gpu_mctx_parse_stream(NutdbMCtx *m, const uint8_t *sql, const uint64_t *stmt_off, uint64_t n_stmt,
+                                uint64_t chunk_bytes, uint32_t flags, nutdb_chunk_fn fn, void *user);
+
+/* Plain device-to-host copy through the library's CUDA runtime (for hosts without one of their own: reading a chunk
+ * that was gathered into device memory, or a nutdb_gpu_batch_device view). */
+int nutdb_gpu_copy_to_host(void *dst, const void *src_device, uint64_t bytes);
 
 /* Host-side helpers (pure CPU formatting of results; no parsing):
  * Rust `{:?}` text of statement i's AST, and `Display` text of its error, written

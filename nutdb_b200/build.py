@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 GPU_SO = os.path.join(HERE, "libnutdb_gpu.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
-GPU_SOURCES = ["nutdb_gpu.cu", "hydrate.cpp"]
+GPU_SOURCES = ["nutdb_gpu.cu", "hydrate.cpp", "dispatch.cpp"]
 
 
 def _stale(target, deps):

@@ -1679,13 +1679,14 @@ run_again:
   out->n_tok = ntok;
   out->n_node = n_node;
   out->n_err = n_err;
+  hS[48] = 0;
+  if (n_node) CK(cudaMemcpyAsync(hS + 48, dS + 26, 4, cudaMemcpyDeviceToHost, st));  // long leaves (almost always none)
   if (!(flags & NUTDB_F_NO_HOST_COPY)) {
     ENSURE_HOST(hStmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
     ENSURE_HOST(hNode, 8 * (n_node + 1));
     ENSURE_HOST(hErr, 32 * (n_err + 1));
     if (nstmt) CK(cudaMemcpyAsync(ctx->hStmt.p, ctx->stmt.p, sizeof(NutdbStmt) * (size_t)nstmt, cudaMemcpyDeviceToHost, st));
     if (n_node) CK(cudaMemcpyAsync(ctx->hNode.p, ctx->nodes.p, 8 * n_node, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hS + 48, dS + 26, 4, cudaMemcpyDeviceToHost, st));  // long leaves (almost always none)
     if (n_err) CK(cudaMemcpyAsync(ctx->hErr.p, ctx->errs.p, 32 * n_err, cudaMemcpyDeviceToHost, st));
     out->stmt = (const NutdbStmt*)ctx->hStmt.p;
     out->cnode = (const NutdbCNode*)ctx->hNode.p;
@@ -1710,7 +1711,7 @@ run_again:
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  if (!(flags & NUTDB_F_NO_HOST_COPY) && n_node && hS[48]) {  // leaves of 32 KB and more: their lengths, by node index
+  if (n_node && hS[48]) {  // leaves of 32 KB and more: their lengths, by node index (a host table whatever the flags)
     const uint32_t nl = std::min<uint32_t>(hS[48], n / NUTDB_CN_LONG + 16u);
     ENSURE_HOST(hLong, 8 * (size_t)nl);
     CK(cudaMemcpy(ctx->hLong.p, ctx->longNodes.p, 8 * (size_t)nl, cudaMemcpyDeviceToHost));

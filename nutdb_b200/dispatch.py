@@ -34,6 +34,13 @@ def totals(batch):
 
 def rebase(stmt, err, bases):
     """Turn shard-local indices into batch-global ones. bases = exclusive prefix [stmt, tok, node, err]."""
+    # the records hold 32-bit indices: a batch-global prefix beyond 2^32 (about 16 GiB of SQL in tokens) cannot be
+    # expressed in them -- such batches keep chunk-local records plus the prefix (what nutdb_gpu_mctx_* delivers)
+    top = [int(bases[1]) + (int(stmt["tok_begin"].max()) if len(stmt) else 0),
+           int(bases[2]) + (int(stmt["node_begin"].max()) if len(stmt) else 0),
+           int(bases[0]) + (int(err["stmt"].max()) if len(err) else 0)]
+    if max(top) >= 1 << 32:
+        raise OverflowError("batch-global indices exceed 32 bits: keep the records shard-local and carry the prefix")
     stmt = stmt.copy()
     stmt["tok_begin"] += np.uint32(bases[1])
     stmt["node_begin"] += np.uint32(bases[2])

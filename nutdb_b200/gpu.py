@@ -27,6 +27,20 @@ class NutdbBatch(C.Structure):
                 ("cnode", C.c_void_p), ("n_long", C.c_uint64), ("long_idx", C.c_void_p), ("long_len", C.c_void_p)]
 
 
+class NutdbMShard(C.Structure):
+    _fields_ = [("device_index", C.c_int), ("sql", C.c_void_p), ("stmt_off", C.c_void_p), ("n_stmt", C.c_uint64),
+                ("flags", C.c_uint32), ("first_stmt", C.c_uint64)]
+
+
+class NutdbMChunk(C.Structure):
+    _fields_ = [("shard", C.c_uint64), ("first_stmt", C.c_uint64), ("device", C.c_int), ("on_device", C.c_int),
+                ("batch", NutdbBatch)]
+
+
+CHUNK_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(NutdbMChunk))
+MF_GATHER_DEVICE0, MF_SERIAL_CALLBACKS = 0x100, 0x200
+
+
 class NutdbBatchDevice(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("stmt", "tok_type", "tok_start", "tok_end", "tok_kw", "node", "err")]
 
@@ -82,6 +96,19 @@ def lib():
     L.nutdb_gpu_last_slow_statements.argtypes = [C.c_void_p]
     L.nutdb_gpu_last_exact_lexed_statements.restype = C.c_uint64
     L.nutdb_gpu_last_exact_lexed_statements.argtypes = [C.c_void_p]
+    L.nutdb_gpu_mctx_create.restype = C.c_void_p
+    L.nutdb_gpu_mctx_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.nutdb_gpu_mctx_destroy.argtypes = [C.c_void_p]
+    L.nutdb_gpu_mctx_last_error.restype = C.c_char_p
+    L.nutdb_gpu_mctx_last_error.argtypes = [C.c_void_p]
+    L.nutdb_gpu_mctx_device_count.argtypes = [C.c_void_p]
+    L.nutdb_gpu_mctx_parse_shards.restype = C.c_int
+    L.nutdb_gpu_mctx_parse_shards.argtypes = [C.c_void_p, C.POINTER(NutdbMShard), C.c_uint64, C.c_uint32, CHUNK_FN, C.c_void_p]
+    L.nutdb_gpu_mctx_parse_stream.restype = C.c_int
+    L.nutdb_gpu_mctx_parse_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                              CHUNK_FN, C.c_void_p]
+    L.nutdb_gpu_copy_to_host.restype = C.c_int
+    L.nutdb_gpu_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.nutdb_gpu_ctx_stream.restype = C.c_void_p
     L.nutdb_gpu_ctx_stream.argtypes = [C.c_void_p]
     for f in ("nutdb_fmt_debug", "nutdb_fmt_error"):
@@ -249,3 +276,76 @@ class Context:
     def stream(self):
         """cudaStream_t (as int) that all work of this context is issued on."""
         return lib().nutdb_gpu_ctx_stream(self._h)
+
+
+def copy_to_host(ptr, count, dtype):
+    """count elements of `dtype` at device pointer `ptr` -> numpy array (nutdb_gpu_copy_to_host)."""
+    a = np.zeros(int(count), dtype)
+    if count:
+        rc = lib().nutdb_gpu_copy_to_host(a.ctypes.data, ptr, a.nbytes)
+        if rc != 0:
+            raise NutdbGpuError(f"nutdb_gpu_copy_to_host failed ({rc})")
+    return a
+
+
+class Chunk:
+    """One gathered shard handed to a dispatcher callback: `batch` views the gather slot (only valid inside the
+    callback; with on_device the array pointers are device-0 memory and only the counts / raw pointers are usable)."""
+
+    def __init__(self, c):
+        self.shard, self.first_stmt, self.device, self.on_device = int(c.shard), int(c.first_stmt), int(c.device), bool(c.on_device)
+        raw = NutdbBatch()
+        C.memmove(C.byref(raw), C.byref(c.batch), C.sizeof(NutdbBatch))
+        self.raw = raw
+        self.batch = None if self.on_device else Batch(None, raw, False)
+
+
+class MultiContext:
+    """nutdb_gpu_mctx_*: one process driving several GPUs (or several pipelined contexts on one)."""
+
+    def __init__(self, devices=(0,), workers_per_device=3):
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = lib().nutdb_gpu_mctx_create(devs, len(devices), workers_per_device)
+        if not self._h:
+            raise NutdbGpuError(f"cannot create a nutdb GPU dispatcher on CUDA devices {list(devices)}. There is no CPU fallback.")
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.nutdb_gpu_mctx_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def _callback(self, on_chunk, errs):
+        def cb(_user, cptr):
+            try:
+                on_chunk(Chunk(cptr.contents))
+            except BaseException as e:  # noqa: BLE001 - re-raised by the caller of the dispatcher
+                errs.append(e)
+        return CHUNK_FN(cb)
+
+    def _finish(self, rc, errs, what):
+        if errs:
+            raise errs[0]
+        if rc != 0:
+            raise NutdbGpuError(f"{what} failed ({rc}): {lib().nutdb_gpu_mctx_last_error(self._h).decode()}")
+
+    def parse_stream(self, text, offs, on_chunk, chunk_bytes=64 << 20, flags=F_NO_TOKENS):
+        """One host batch -> on_chunk(Chunk) per chunk, in completion order, from the dispatcher's worker threads."""
+        t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text)
+        o = np.ascontiguousarray(offs, np.uint64)
+        errs = []
+        cb = self._callback(on_chunk, errs)
+        rc = lib().nutdb_gpu_mctx_parse_stream(self._h, t.ctypes.data, o.ctypes.data, len(o) - 1, int(chunk_bytes), flags, cb, None)
+        self._finish(rc, errs, "nutdb_gpu_mctx_parse_stream")
+
+    def parse_shards(self, shards, on_chunk, flags=F_NO_TOKENS):
+        """shards: [(device_index, sql_ptr, off_ptr, n_stmt, shard_flags, first_stmt)] (raw pointers: host or device)."""
+        arr = (NutdbMShard * len(shards))()
+        for i, (d, sp, op, n, f, first) in enumerate(shards):
+            arr[i] = NutdbMShard(d, sp, op, n, f, first)
+        errs = []
+        cb = self._callback(on_chunk, errs)
+        rc = lib().nutdb_gpu_mctx_parse_shards(self._h, arr, len(shards), flags, cb, None)
+        self._finish(rc, errs, "nutdb_gpu_mctx_parse_shards")

@@ -9,7 +9,7 @@ skip = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # kernel instances (in repo
 name_has = sys.argv[6] if len(sys.argv) > 6 else ""    # e.g. "(bool)1": only instances whose demangled name contains this
 # (the source page lists every instance twice; template instances share one base name, so a wrong `skip` silently
 #  pairs one instance's counters with another's line table -- select by name)
-so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nutdb_b200", "libnutdb_gpu.so")
+so = os.environ.get("NUTDB_SO") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nutdb_b200", "libnutdb_gpu.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.startswith("nutdb_gpu.") and f.endswith(".cubin")][0]

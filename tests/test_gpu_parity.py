@@ -330,3 +330,96 @@ def test_predicates_and_hex_literals(ctx):
     check(ctx, seeds)
     for seed in (81, 82):
         check(ctx, fuzz.fuzz_statements(seeds, 20000, seed=seed, max_mut=3))
+
+
+def _collect(devices, text, offs, flags, chunk_bytes, workers=2):
+    """Runs the C dispatcher and returns its chunks' arrays re-assembled in statement order."""
+    from nutdb_b200 import gpu
+    m = gpu.MultiContext(devices, workers)
+    got = {}
+
+    def on_chunk(c):
+        if c.on_device:   # gathered into device-0 memory: read it back through the library's CUDA runtime
+            r = c.raw
+            got[c.first_stmt] = dict(stmt=gpu.copy_to_host(r.stmt, r.n_stmt, gpu.STMT_DT),
+                                     cnode=gpu.copy_to_host(r.cnode, r.n_node, gpu.CNODE_DT),
+                                     err=gpu.copy_to_host(r.err, r.n_err, gpu.ERR_DT), device=c.device, node=None, tok=None)
+        else:
+            b = c.batch
+            got[c.first_stmt] = dict(stmt=b.stmt.copy(), cnode=b.cnode.copy(), err=b.err.copy(), device=c.device,
+                                     node=b.node.copy(),
+                                     tok=None if flags & gpu.F_NO_TOKENS else
+                                     (b.tok_type.copy(), b.tok_start.copy(), b.tok_end.copy(), b.tok_kw.copy()))
+    try:
+        m.parse_stream(text, offs, on_chunk, chunk_bytes, flags)
+    finally:
+        m.close()
+    return got
+
+
+def _check_dispatcher(ctx, devices, gather_flags):
+    from nutdb_b200 import gpu
+    text, offs = W.generate(3, 6 << 20, seed=31)
+    whole = ctx.parse_batch(text, offs)
+    assert not P.compare_with_oracle(whole, text, offs)
+    got = _collect(devices, text, offs, gather_flags, 1 << 20)
+    keys = sorted(got)
+    assert len(keys) >= 5 and keys[0] == 0
+    assert len({got[k]["device"] for k in keys}) == len(set(devices))
+    # chunk-local records + first_stmt == the one-batch result
+    stmt = np.concatenate([got[k]["stmt"] for k in keys])
+    assert len(stmt) == whole.n_stmt
+    for f in ("status", "tok_count", "node_count", "tok_used"):
+        assert np.array_equal(stmt[f], whole.stmt[f]), f
+    assert np.array_equal(np.concatenate([got[k]["cnode"] for k in keys]), whole.cnode)
+    err = np.concatenate([got[k]["err"] for k in keys])
+    err_stmt = np.concatenate([got[k]["err"]["stmt"].astype(np.int64) + k for k in keys])
+    assert np.array_equal(err_stmt, whole.err["stmt"].astype(np.int64))
+    for f in ("cls", "code", "line", "col", "pos", "a", "b", "c"):
+        assert np.array_equal(err[f], whole.err[f]), f
+    if got[keys[0]]["node"] is not None:
+        assert np.array_equal(np.concatenate([got[k]["node"] for k in keys]), whole.node)
+    if got[keys[0]]["tok"] is not None:   # token arrays: each chunk's pulled tokens against the one-batch arrays
+        for k in keys:
+            s, (ty, st, en, kw) = got[k]["stmt"], got[k]["tok"]
+            for j in (0, len(s) // 2, len(s) - 1):
+                a, n = int(s["tok_begin"][j]), int(s["tok_count"][j])
+                wa = int(whole.stmt["tok_begin"][k + j])
+                assert np.array_equal(ty[a:a + n], whole.tok_type[wa:wa + n]) and np.array_equal(st[a:a + n], whole.tok_start[wa:wa + n])
+                assert np.array_equal(en[a:a + n], whole.tok_end[wa:wa + n]) and np.array_equal(kw[a:a + n], whole.tok_kw[wa:wa + n])
+
+
+def test_dispatcher_two_pipelined_device_slots_on_one_gpu(ctx):
+    """nutdb_gpu_mctx_*: the dispatcher's logic (cuts, per-device queues, gather slots, callbacks) with the one GPU
+    listed twice -- host gather with and without tokens, and the gather into device memory."""
+    from nutdb_b200 import gpu
+    _check_dispatcher(ctx, (0, 0), gpu.F_NO_TOKENS)
+    _check_dispatcher(ctx, (0, 0), 0)
+    _check_dispatcher(ctx, (0,), gpu.F_NO_TOKENS | gpu.MF_GATHER_DEVICE0 | gpu.MF_SERIAL_CALLBACKS)
+
+
+def test_dispatcher_two_gpus(ctx):
+    """Two GPUs of one box driven by one process: host gather over each GPU's PCIe link, and the gather into GPU 0's
+    memory over NVLink (cudaMemcpyPeerAsync); both against the one-GPU result (itself checked against the oracle)."""
+    import torch
+    from nutdb_b200 import gpu
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _check_dispatcher(ctx, (0, 1), gpu.F_NO_TOKENS)
+    _check_dispatcher(ctx, (0, 1), 0)
+    _check_dispatcher(ctx, (0, 1), gpu.F_NO_TOKENS | gpu.MF_GATHER_DEVICE0)
+
+
+def test_dispatcher_errors(ctx):
+    from nutdb_b200 import gpu
+    m = gpu.MultiContext((0,), 1)
+    try:
+        with pytest.raises(gpu.NutdbGpuError):
+            m.parse_stream(b"select 1", np.array([0, 8, 4], np.uint64), lambda c: None)
+        seen = []
+        m.parse_stream(b"select 1;select 2", np.array([0, 9, 17], np.uint64), lambda c: seen.append(int(c.batch.n_stmt)))
+        assert sum(seen) == 2
+        with pytest.raises(ZeroDivisionError):   # an exception in the consumer surfaces in the caller
+            m.parse_stream(b"select 1", np.array([0, 8], np.uint64), lambda c: 1 // 0)
+    finally:
+        m.close()
