@@ -372,7 +372,9 @@ def device_run(ctx, text, offs, local, steps, warmup, barrier):
     d_text = torch.from_numpy(text).cuda()
     d_offs = torch.from_numpy(offs.view(np.int64)).cuda()
     torch.cuda.synchronize()
-    dev_flags = gpu.F_DEVICE_INPUT | gpu.F_NO_HOST_COPY
+    # (NUTDB_F_NO_TOKENS: the reference's entry returns the AST only -- mod.rs:27 -- so the token arrays stay an
+    # intermediate in the lexer's own segmented layout instead of being compacted for a caller)
+    dev_flags = gpu.F_DEVICE_INPUT | gpu.F_NO_HOST_COPY | gpu.F_NO_TOKENS
 
     def step_device():
         return ctx.parse_batch_raw(d_text.data_ptr(), d_offs.data_ptr(), n_stmt, dev_flags, copy=False)

@@ -351,7 +351,9 @@ typedef struct {
 typedef struct NutdbCtx NutdbCtx;
 
 /* flags for nutdb_gpu_parse_batch */
-#define NUTDB_F_NO_TOKENS 1u /* do not copy the token arrays back to the host (reference never exposes tokens) */
+#define NUTDB_F_NO_TOKENS 1u /* the caller does not want the token arrays (the reference never exposes tokens): no host copy, and the
+                                device copies stay in the lexer's segmented layout (statement i's tokens are still
+                                [tok_begin, tok_begin + tok_count) of them, but the arrays have gaps between the lexer's ranges) */
 #define NUTDB_F_DEVICE_INPUT 2u /* `sql` and `stmt_off` are device pointers on the ctx's device */
 #define NUTDB_F_NO_HOST_COPY 4u /* leave every output on the device (use nutdb_gpu_batch_device) */
 #define NUTDB_F_ALL_TOKENS 8u /* lexer verify mode: token arrays also hold Whitespace / Comment tokens (the full stream of
@@ -420,9 +422,12 @@ int nutdb_gpu_last_launches(const NutdbCtx *ctx);
  * last call and, for 0 <= i < that number, the kernel's name and duration in milliseconds. */
 void nutdb_gpu_set_profiling(NutdbCtx *ctx, int on);
 int nutdb_gpu_kernel_timing(const NutdbCtx *ctx, int i, const char **name, float *ms);
-/* Statements of the last batch that the straight-line parser declined and the exact automaton
- * parsed (everything malformed, plus constructs outside the common shapes). */
+/* Statements of the last batch that both table-driven passes declined and the exact automaton
+ * parsed (everything malformed, plus constructs outside the tables' grammar). */
 uint64_t nutdb_gpu_last_slow_statements(const NutdbCtx *ctx);
+/* Statements of the last batch parsed by the second (wide) table-driven pass: deep nesting, arrays, maps, index
+ * access, IF, subqueries. */
+uint64_t nutdb_gpu_last_wide_statements(const NutdbCtx *ctx);
 /* Statements of the last batch that the warp-cooperative lexer handed to the exact walker (every
  * statement with a lex error, hex literals, `$n`, `@name`, code tokens longer than 32 bytes ...). */
 uint64_t nutdb_gpu_last_exact_lexed_statements(const NutdbCtx *ctx);

@@ -796,6 +796,66 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
   }
 }
 
+// Pass 1b, one thread per statement the first pass declined: the WIDE instantiation of the table-driven parser
+// (parse_fast.cuh) -- array / map literals, index access, prefix ~, IF .. END, parenthesised subqueries, and any nesting
+// depth: its operator stack is the top end of the statement's own compact-node range (the nodes grow from the bottom),
+// so a deep statement needs neither a local-memory stack nor a second run.  Tokens come straight from global memory
+// (these statements are long: a lane walks its own run of the arrays, the L1 serves it).  What it declines too goes to
+// the exact automaton.
+#define WIDE_THREADS 128
+__global__ void __launch_bounds__(WIDE_THREADS) k_parse_wide(
+    const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint32_t* __restrict__ slow_list,
+    const uint32_t* __restrict__ nslow_dev, const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start,
+    const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw, const npar::FastTables* __restrict__ gF,
+    NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch, uint32_t* __restrict__ slow2_list,
+    uint32_t* __restrict__ slow2_count, uint32_t nstmt, const uint32_t* __restrict__ punt) {
+  const uint32_t nslow = *nslow_dev;
+  if (blockIdx.x * WIDE_THREADS >= nslow) return;
+  __shared__ npar::FastTables FT;
+  __shared__ uint32_t skey[WIDE_THREADS], sorder[WIDE_THREADS];
+  {
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(gF);
+    uint32_t* b = reinterpret_cast<uint32_t*>(&FT);
+    for (uint32_t i = threadIdx.x; i < sizeof(npar::FastTables) / 4; i += WIDE_THREADS) b[i] = a[i];
+  }
+  {  // same shapes into the same warp (see k_parse)
+    const uint32_t i0 = blockIdx.x * WIDE_THREADS + threadIdx.x;
+    uint32_t key = 0xFFFFFFFFu;
+    if (i0 < nslow) {
+      const uint32_t s0 = slow_list[i0];
+      const uint32_t tb0 = stmt[s0].tok_begin, tc0 = stmt[s0].tok_count;
+      uint32_t h = 0;
+      const uint32_t m = min(tc0, 12u);
+      for (uint32_t q = 0; q < m; q++) h = h * 31u + tok_type[tb0 + q];
+      key = (min(tc0, 0xFFFFu) << 15) | (h & 0x7FFFu);
+    }
+    skey[threadIdx.x] = key;
+    __syncthreads();
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < WIDE_THREADS; j++) {
+      const uint32_t kj = skey[j];
+      rank += (kj < key || (kj == key && j < threadIdx.x)) ? 1u : 0u;
+    }
+    sorder[rank] = threadIdx.x;
+  }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * WIDE_THREADS + sorder[threadIdx.x];
+  if (i >= nslow) return;
+  const uint32_t s = slow_list[i];
+  const uint32_t o = off32[s], len = off32[s + 1] - o;
+  const uint32_t tb = stmt[s].tok_begin, tc = stmt[s].tok_count;
+  DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
+  uint2* range = scratch + node_slot(s, tb, nstmt, punt);
+  const uint32_t cap = tc + NODE_SLACK;
+  DNodes nd{range, cap};
+  DText tx{text + o, len};
+  npar::ParseResult res;
+  static_assert(sizeof(npar::FastStackEntry) == sizeof(uint2), "the wide parser's stack shares the node range");
+  npar::FastParser<DTok, DNodes, DText, true> f(&FT, tk, nd, tx, reinterpret_cast<npar::FastStackEntry*>(range) + (cap - 1), -1);
+  if (f.try_parse(res)) store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
+  else slow2_list[atomicAdd(slow2_count, 1u)] = s;
+}
+
 // Pass 2, one thread per statement of the slow list: the exact bytecode automaton (parse_core.cuh)
 // for the whole grammar, every error and constant folding.
 __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
@@ -806,13 +866,19 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
     uint2* __restrict__ retry_list, uint32_t* __restrict__ retry_count, uint32_t nstmt,
     const uint32_t* __restrict__ punt, const uint32_t* __restrict__ nslow_dev) {
   if (nslow_dev) nslow = *nslow_dev;  // the slow list's length is only known on the device
-  if (blockIdx.x * PARSE_THREADS >= nslow) return;
+  // The interpreters of a warp's lanes diverge, so a warp costs the SUM of its lanes' work.  A short list (a few long
+  // statements among many the tables parsed) is therefore spread out: one statement every `spread` threads, up to one
+  // statement per warp, over the blocks the launch has anyway (one thread per statement of the batch).
+  uint32_t spread = 1;
+  while (spread < 32u && (uint64_t)nslow * spread * 2u <= (uint64_t)gridDim.x * PARSE_THREADS) spread <<= 1;
+  if ((uint64_t)blockIdx.x * PARSE_THREADS >= (uint64_t)nslow * spread) return;
   __shared__ npar::ParseTables P;
   __shared__ uint32_t skey[PARSE_THREADS], sorder[PARSE_THREADS];
   stage_parse_tables(gP, &P);
-  // Re-deal the CTA's statements so that a warp gets statements of the same SHAPE (same token count and the
-  // same leading token types: query logs repeat a few templates): the lanes' interpreters then run in step.
-  {
+  uint32_t i;
+  if (spread == 1u) {
+    // Re-deal the CTA's statements so that a warp gets statements of the same SHAPE (same token count and the
+    // same leading token types: query logs repeat a few templates): the lanes' interpreters then run in step.
     const uint32_t i0 = blockIdx.x * PARSE_THREADS + threadIdx.x;
     uint32_t key = 0xFFFFFFFFu;
     if (i0 < nslow) {
@@ -831,9 +897,13 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(
       rank += (kj < key || (kj == key && j < threadIdx.x)) ? 1u : 0u;
     }
     sorder[rank] = threadIdx.x;
+    __syncthreads();
+    i = blockIdx.x * PARSE_THREADS + sorder[threadIdx.x];
+  } else {
+    __syncthreads();
+    const uint32_t slot = blockIdx.x * PARSE_THREADS + threadIdx.x;
+    i = (slot % spread) == 0u ? slot / spread : 0xFFFFFFFFu;
   }
-  __syncthreads();
-  const uint32_t i = blockIdx.x * PARSE_THREADS + sorder[threadIdx.x];
   if (i >= nslow) return;
   const uint32_t s = slow_list[i];
   const uint32_t o = off32[s], len = off32[s + 1] - o;
@@ -856,11 +926,13 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse_retry(
     const uint32_t* __restrict__ tok_start, const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw,
     const npar::ParseTables* __restrict__ gP, NutdbStmt* __restrict__ stmt, const uint2* __restrict__ retry_list,
     uint32_t nretry, const uint64_t* __restrict__ node_off, const uint64_t* __restrict__ stack_off,
-    uint2* __restrict__ retry_nodes, uint32_t* __restrict__ retry_stack) {
+    uint2* __restrict__ retry_nodes, uint32_t* __restrict__ retry_stack, uint32_t spread) {
   __shared__ npar::ParseTables P;
   stage_parse_tables(gP, &P);
   __syncthreads();
-  const uint32_t i = blockIdx.x * PARSE_THREADS + threadIdx.x;
+  const uint32_t slot = blockIdx.x * PARSE_THREADS + threadIdx.x;  // (a short list is spread out: see k_parse)
+  if (slot % spread) return;
+  const uint32_t i = slot / spread;
   if (i >= nretry) return;
   const uint32_t s = retry_list[i].x;
   const uint32_t o = off32[s], len = off32[s + 1] - o;
@@ -1042,12 +1114,13 @@ struct NutdbCtx {
   DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
+      tileS, tilePrefS, nodes, errs, small, slowList, slowList2, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry, hSplit;
   float ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
   uint32_t n_slow = 0;  // statements of the last batch that needed the exact automaton
+  uint32_t n_wide = 0;  // ... that the wide table-driven pass parsed
   // optional per-kernel timing (nutdb_gpu_set_profiling): events around every launch
   bool profiling = false;
   struct KRec {
@@ -1165,7 +1238,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
+                 &c->small, &c->slowList, &c->slowList2, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
                  &c->splitTile, &c->splitPref, &c->splitOff};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
@@ -1540,6 +1613,7 @@ run_again:
     if (!lex_only) ENSURE_DEV(scratch, 8 * scratch_nodes);
     ENSURE_DEV(retryList, 8 * ((size_t)nstmt + 1));
     ENSURE_DEV(slowList, 4 * ((size_t)nstmt + 1));
+    ENSURE_DEV(slowList2, 4 * ((size_t)nstmt + 1));
     StmtToks stoks{native_lex ? (const uint32_t*)ctx->winIdx.p : nullptr, (const uint32_t*)ctx->winHas.p,
                    (const uint32_t*)ctx->winEof.p, (const uint32_t*)ctx->puntFlag.p, (const uint32_t*)ctx->stmtTokBegin.p,
                    (const uint32_t*)ctx->stmtTokEnd.p, (const uint32_t*)ctx->rangeStmt.p, dS + 20,
@@ -1552,12 +1626,18 @@ run_again:
                                native_lex ? tok_cap : (uint32_t)min((size_t)0xFFFFFFF0u, (size_t)ntok + 16), ctx->dFast,
                                native_lex ? (use_lookback ? dS + 16 : dS + 21) : nullptr, native_lex ? dS + 10 : nullptr, dS));
     if (!lex_only)
+      LAUNCH("k_parse_wide", k_parse_wide<<<(nstmt + WIDE_THREADS - 1) / WIDE_THREADS, WIDE_THREADS, 0, st>>>(
+                                 dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, dS + 2,
+                                 (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
+                                 (const uint8_t*)ctx->tokKw.p, ctx->dFast, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
+                                 (uint32_t*)ctx->slowList2.p, dS + 27, nstmt, (const uint32_t*)ctx->puntFlag.p));
+    if (!lex_only)
       LAUNCH("k_parse", k_parse<<<(nstmt + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
-                            dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, 0u,
+                            dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList2.p, 0u,
                             (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
                             (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar,
                             (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p, (uint2*)ctx->retryList.p, dS + 1, nstmt,
-                            (const uint32_t*)ctx->puntFlag.p, dS + 2));
+                            (const uint32_t*)ctx->puntFlag.p, dS + 27));
     const uint32_t stiles = (nstmt + FIN_THREADS - 1) / FIN_THREADS;
     ENSURE_DEV(tileS, 8 * (size_t)stiles);
     ENSURE_DEV(tilePrefS, 8 * (size_t)stiles);
@@ -1597,7 +1677,8 @@ run_again:
       ntok = (uint32_t)(n_main + n_extra);
       ctx->last_lookback = use_lookback;
     }
-    ctx->n_slow = hS[2];
+    ctx->n_slow = hS[27];           // statements the exact automaton parsed
+    ctx->n_wide = hS[2] - hS[27];   // statements the wide table-driven pass parsed
     const uint32_t nretry = hS[1];
     if (nretry > 0) {
       // deep statements: per-statement stack and node ranges sized from their token counts
@@ -1623,11 +1704,13 @@ run_again:
       CK(cudaMemcpyAsync(ctx->retryNodeOff.p, noff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->retryStackOff.p, soff.data(), 8 * ((size_t)nretry + 1), cudaMemcpyHostToDevice, st));
       CK(cudaStreamSynchronize(st));  // noff/soff are stack vectors
-      LAUNCH("k_parse_retry", k_parse_retry<<<(nretry + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
+      uint32_t rspread = 1;
+      while (rspread < 32u && (uint64_t)nretry * rspread * 2u <= (uint64_t)ctx->sm_count * 1024u) rspread <<= 1;
+      LAUNCH("k_parse_retry", k_parse_retry<<<(uint32_t)(((uint64_t)nretry * rspread + PARSE_THREADS - 1) / PARSE_THREADS), PARSE_THREADS, 0, st>>>(
           dText, (const uint32_t*)ctx->off32.p, (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p,
           (const uint32_t*)ctx->tokEnd.p, (const uint8_t*)ctx->tokKw.p, ctx->dPar, (NutdbStmt*)ctx->stmt.p,
           (const uint2*)ctx->retryList.p, nretry, (const uint64_t*)ctx->retryNodeOff.p,
-          (const uint64_t*)ctx->retryStackOff.p, (uint2*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p));
+          (const uint64_t*)ctx->retryStackOff.p, (uint2*)ctx->retryNodes.p, (uint32_t*)ctx->retryStack.p, rspread));
       LAUNCH("k_stmt_sums", k_stmt_sums<<<stiles, FIN_THREADS, 0, st>>>((const NutdbStmt*)ctx->stmt.p, nstmt, (uint2*)ctx->tileS.p));
       LAUNCH("k_scan_S", k_scan_tiles<U2AddOp><<<1, SCAN_THREADS, 0, st>>>((const uint2*)ctx->tileS.p, (uint2*)ctx->tilePrefS.p,
                                                                            stiles, (uint2*)(dS + 8)));
@@ -1921,10 +2004,10 @@ int nutdb_gpu_last_launches(const NutdbCtx* ctx) { return ctx ? ctx->launches : 
 
 // test hook (not in the public header): the first statements of the last batch that the table-driven parser declined
 int nutdb_gpu_debug_slow_list(NutdbCtx* ctx, uint32_t* out, uint32_t cap) {
-  if (!ctx || !ctx->slowList.p) return 0;
+  if (!ctx || !ctx->slowList2.p) return 0;
   const uint32_t k = std::min<uint32_t>(cap, ctx->n_slow);
   cudaSetDevice(ctx->device);
-  if (k && cudaMemcpy(out, ctx->slowList.p, 4 * (size_t)k, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (k && cudaMemcpy(out, ctx->slowList2.p, 4 * (size_t)k, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int)k;
 }
 
@@ -1968,6 +2051,7 @@ int nutdb_gpu_kernel_timing(const NutdbCtx* ctx, int i, const char** name, float
   return (int)ctx->kernel_ms.size();
 }
 uint64_t nutdb_gpu_last_slow_statements(const NutdbCtx* ctx) { return ctx ? ctx->n_slow : 0; }
+uint64_t nutdb_gpu_last_wide_statements(const NutdbCtx* ctx) { return ctx ? ctx->n_wide : 0; }
 uint64_t nutdb_gpu_last_exact_lexed_statements(const NutdbCtx* ctx) { return ctx ? ctx->n_punt : 0; }
 void* nutdb_gpu_ctx_stream(const NutdbCtx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 

@@ -27,6 +27,13 @@
 //
 // The whole parser is a few hundred instructions, resident in the instruction cache.
 //
+// Two instantiations share this code and the table.  The NARROW one (WIDE = false) is the first pass over every
+// statement: operator stack of FAST_STACK_DEPTH entries in shared memory, the subset above.  The WIDE one is the second
+// pass over what the first declined: its stack lives at the top end of the statement's own compact-node range (nodes
+// grow up from the bottom, the stack down from the top; any nesting depth the token count allows), and it also takes
+// array literals [..], map literals {k: v, ..}, index access x[i], prefix ~, IF .. THEN .. ELSE .. END and parenthesised
+// subqueries (select ..) -- the constructs of the reference's corpus and of deeply nested statements.
+//
 // It is ALL-OR-NOTHING: on anything outside that subset -- any error, any construct that needs
 // constant folding (simplify.rs), literal validation beyond a length check, joins, set
 // operations, subqueries, IF/INTERVAL, NOT EXISTS, arrays, maps ... -- try_parse() returns false
@@ -48,6 +55,7 @@ struct FastStackEntry {
 // ---- token classes: everything the grammar states distinguish ----
 enum FastClass : uint8_t {
   FC_OTHER = 0, FC_EOF, FC_SEMI, FC_COMMA, FC_LPAREN, FC_RPAREN, FC_MUL, FC_PLUS, FC_MINUS, FC_BINOP, FC_LBRACKET,
+  FC_LBRACE, FC_BITNOT,
   FC_INT, FC_HEX, FC_FLOAT, FC_RAWSTR, FC_ESQ, FC_EDQ, FC_DELIM, FC_DOT,
   // words (token type KeywordOrIdentifier), by keyword id: every class from FC_WORD on is a word class
   FC_WORD, FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_KWBINOP, FC_ISBETWEEN,
@@ -78,7 +86,9 @@ enum FastState : uint8_t {
   FS_COUNT
 };
 
-enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT, FA_CASE };
+enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT, FA_CASE,
+                          // the wide instantiation only (the narrow one declines them):
+                          FA_IF, FA_ARRAY, FA_MAP, FA_BITNOT, FA_SUBQ_END };
 
 // ---- transition record: two words ----
 // lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28] subreg[29]
@@ -101,27 +111,34 @@ struct FastTables {
 };
 NUTDB_HD uint32_t fast_token_index(uint32_t ty, uint32_t kw) { return ty == NUTDB_TT_KeywordOrIdentifier ? 64u + kw : ty; }
 
-template <class Tok, class Nodes, class Text>
+template <class Tok, class Nodes, class Text, bool WIDE = false>
 struct FastParser {
   const FastTables* F;
   Tok tok;
   Nodes nd;
   Text text;
-  FastStackEntry* stk;  // the caller's memory (shared memory on the device): entry i of this thread at stk[i * stride]
-  uint32_t stride;
-  // operator / bracket stack entries: x = type | power << 3 | op << 7 | left kind << 13 | item count << 21
-  // (E_DT: x = type | compound sub << 3), y = start of the left operand (operators) / node count at the opening.
+  FastStackEntry* stk;  // the caller's memory: entry i of this thread at stk[i * stride] (narrow: shared memory, strided
+  int32_t stride;       // over the CTA's threads; wide: stride -1 from the last slot of the statement's node range)
+  // operator / bracket stack entries: x = type | power << 4 | op << 8 | left kind << 14 | item count << 22
+  // (E_DT: x = type | compound sub << 4), y = start of the left operand (operators) / node count at the opening.
   // The power of an entry is the min_power its right operand is parsed with (must_parse_expr_tdop, mod.rs:1209):
-  // an arriving operator of equal or lower power completes it.  E_NOT = prefix NOT, E_BTW1 / E_BTW2 = [NOT] BETWEEN
-  // before / after its AND (op = FnName Between 3 / NotBetween 4).
-  // E_CASE = CASE [scrutinee] WHEN .. THEN .. [ELSE ..] END: x = type | position << 7 | FnName << 9 (position: 0 after
-  // the scrutinee, 1 after a condition, 2 after a result, 3 after the ELSE expression)
-  enum : uint32_t { E_OP = 0, E_PAREN = 1, E_CALL = 2, E_DT = 3, E_NOT = 4, E_BTW1 = 5, E_BTW2 = 6, E_CASE = 7 };
+  // an arriving operator of equal or lower power completes it.  E_NOT / E_BITNOT = prefix NOT / ~, E_BTW1 / E_BTW2 =
+  // [NOT] BETWEEN before / after its AND (op = FnName Between 3 / NotBetween 4).  Everything from E_PAREN on is a
+  // BRACKET: power 0, closed by its own terminator.
+  // E_CASE = CASE [scrutinee] WHEN .. THEN .. [ELSE ..] END: x = type | position << 8 | FnName << 10 (position: 0 after
+  // the scrutinee, 1 after a condition, 2 after a result, 3 after the ELSE expression).
+  // Wide only: E_IF (x = type | position << 8: 0 after the condition, 1 after THEN's value, 2 after ELSE's),
+  // E_BRACKET = [items], E_MAP = {k: v, ..} (position << 8: 0 after a key, 1 after a value), E_INDEX = left[ (y = start of
+  // left), E_SUBQ = (select ..: x = type | ctx << 8 | join register << 12, y = the outer query's base; the entry below
+  // it holds the outer m0 / m1).
+  enum : uint32_t { E_OP = 0, E_NOT = 1, E_BITNOT = 2, E_BTW1 = 3, E_BTW2 = 4, E_PAREN = 5, E_CALL = 6, E_DT = 7, E_CASE = 8,
+                    E_IF = 9, E_BRACKET = 10, E_MAP = 11, E_INDEX = 12, E_SUBQ = 13 };
   enum : uint32_t { SPEC_NONE = 0, SPEC_BAIL = 1, SPEC_NOT = 2, SPEC_IS = 3, SPEC_BETWEEN = 4 };  // FastTables::op >> 12
-  static const uint32_t DEPTH = FAST_STACK_DEPTH;
+  enum : uint32_t { X_POWER = 4, X_OP = 8, X_LKIND = 14, X_COUNT = 22, X_COUNT_MAX = 1023 };
+  static const uint32_t DEPTH = WIDE ? 0x7FFFFFFFu : (uint32_t)FAST_STACK_DEPTH;  // (wide: bounded by the node range, see try_parse)
 
   NUTDB_HD FastParser(const FastTables* ft, const Tok& tk, const Nodes& nodes, const Text& tx, FastStackEntry* stack,
-                      uint32_t stack_stride)
+                      int32_t stack_stride)
       : F(ft), tok(tk), nd(nodes), text(tx), stk(stack), stride(stack_stride) {}
 
   NUTDB_HD static bool is_literal(uint32_t kind) { return kind >= NUTDB_NK_LIT_INT && kind <= NUTDB_NK_LIT_INTERVAL; }
@@ -194,6 +211,8 @@ struct FastParser {
     uint32_t cur_start = 0, cur_kind = 0;  // the operand just completed (right-most subtree)
     uint32_t m0 = 0, m1 = 0;               // open interior nodes: outer (ROWS / COLDEF) and inner (clause / ROW / attribute)
     uint32_t ctx = C_SEL_ITEM, seen = 0, cnt = 0, width = 0, auxr = 0, jreg = 0;
+    uint32_t qbase = 0;                    // first node of the query being parsed (wide: moves with subqueries)
+#define FAST_STK(i_) stk[(int32_t)(i_) * stride]
 #define FAST_EMIT(kind_, sub_, aux_, x_)          \
   do {                                            \
     if (n < cap) {                                \
@@ -207,7 +226,9 @@ struct FastParser {
     n++;                                          \
   } while (0)
     for (;;) {
-      if (n > cap) return false;  // (a store beyond the range was skipped: the automaton redoes the statement)
+      // (a store beyond the range was skipped: the automaton redoes the statement.  Wide: the stack comes down from
+      // the top of the same range; one turn of the loop emits / pushes at most three entries)
+      if (WIDE ? (n + sp + 4u > cap) : (n > cap)) return false;
       p = tok.pair_at(t);  // the current token never lies beyond the statement's EOF token
       const uint32_t ty = p & 255u, kw = p >> 8;
       const uint32_t ti = fast_token_index(ty, kw);
@@ -215,17 +236,17 @@ struct FastParser {
         // ---------------- operators: token_power (mod.rs:1895-1927) + must_parse_expr_infix ----------------
         const uint32_t e = F->op[ti];
         const uint32_t spec = e >> 12;
-        if (spec == SPEC_BAIL) return false;  // index access: the automaton
+        if (!WIDE && spec == SPEC_BAIL) return false;  // index access: the wide pass / the automaton
         const uint32_t power = e & 15u, op = (e >> 4) & 63u;
         // everything of equal or higher power on the stack is complete (left-associative)
         bool took_and = false;
         while (sp > 0) {
-          const FastStackEntry top = stk[(sp - 1) * stride];
-          const uint32_t type = top.x & 7u;
-          if (((top.x >> 3) & 15u) < power) break;  // (brackets carry power 0: only a terminator gets past this)
+          const FastStackEntry top = FAST_STK(sp - 1);
+          const uint32_t type = top.x & 15u;
+          if (((top.x >> X_POWER) & 15u) < power) break;  // (brackets carry power 0: only a terminator gets past this)
           if (type == E_OP) {
             // BinaryOp{op, left, right}; refuse whatever simplify.rs would fold
-            const uint32_t bop = (top.x >> 7) & 63u, lkind = (top.x >> 13) & 255u;
+            const uint32_t bop = (top.x >> X_OP) & 63u, lkind = (top.x >> X_LKIND) & 255u;
             if (bop == 9 || bop == 10) {  // simplified_eq / simplified_neq
               if (is_literal(lkind) && is_literal(cur_kind)) return false;
             } else if (bop >= 11 && bop <= 13) {  // simplified_and / or / xor
@@ -235,23 +256,27 @@ struct FastParser {
             cur_start = top.y;
             cur_kind = NUTDB_NK_BINARY;
             FAST_EMIT(NUTDB_NK_BINARY, bop, 0, cur_start);
-          } else if (type - 1u < 3u || type == E_CASE) {  // E_PAREN / E_CALL / E_DT / E_CASE: the terminator belongs to the bracket
+          } else if (type >= E_PAREN) {  // a bracket: the terminator belongs to it
             break;
           } else if (type == E_NOT) {  // simplified_not (simplify.rs): a boolean literal would be flipped
             if (cur_kind == NUTDB_NK_LIT_BOOL) return false;
             sp--;
             cur_kind = NUTDB_NK_UNARY;
             FAST_EMIT(NUTDB_NK_UNARY, 1, 0, cur_start);
+          } else if (type == E_BITNOT) {  // UnaryOp{BitNot} (mod.rs:1290-1292): never folded
+            sp--;
+            cur_kind = NUTDB_NK_UNARY;
+            FAST_EMIT(NUTDB_NK_UNARY, 0, 0, cur_start);
           } else if (type == E_BTW1) {  // `left BETWEEN x` must continue with AND (mod.rs:1445-1449)
             if (!(ty == NUTDB_TT_KeywordOrIdentifier && kw == KW_AND)) return false;
-            stk[(sp - 1) * stride].x = (top.x & ~7u) | E_BTW2;
+            FAST_STK(sp - 1).x = (top.x & ~15u) | E_BTW2;
             took_and = true;
             break;
           } else {  // E_BTW2: FnCall{Between | NotBetween, [left, x, y]}
             sp--;
             cur_start = top.y;
             cur_kind = NUTDB_NK_FNCALL;
-            FAST_EMIT(NUTDB_NK_FNCALL, (top.x >> 7) & 63u, 0, cur_start);
+            FAST_EMIT(NUTDB_NK_FNCALL, (top.x >> X_OP) & 63u, 0, cur_start);
           }
         }
         if (took_and) {
@@ -260,6 +285,13 @@ struct FastParser {
           continue;
         }
         if (spec != SPEC_NONE) {
+          if (WIDE && spec == SPEC_BAIL) {  // left[index] (mod.rs:1372-1382): BinaryOp{IndexAccess}, closed by `]`
+            FAST_STK(sp) = FastStackEntry{E_INDEX, cur_start};
+            sp++;
+            t++;
+            st = FS_X_OPND;
+            continue;
+          }
           const uint32_t p1 = tok.pair_at(t + 1);  // (the current token is a word, so t + 1 is at most the EOF token)
           const uint32_t kw1 = (p1 & 255u) == NUTDB_TT_KeywordOrIdentifier ? (p1 >> 8) : 0u;
           if (spec == SPEC_IS) {  // IS [NOT] NULL (mod.rs:1430-1438): simplified_is_null folds literals
@@ -280,13 +312,13 @@ struct FastParser {
           }
           if (sp >= DEPTH) return false;
           if (spec == SPEC_BETWEEN) {
-            stk[sp * stride] = FastStackEntry{E_BTW1 | (P_Between << 3) | (3u << 7), cur_start};
+            FAST_STK(sp) = FastStackEntry{E_BTW1 | (P_Between << X_POWER) | (3u << X_OP), cur_start};
             t += 1;
           } else {  // NOT IN / LIKE / ILIKE / BETWEEN (mod.rs:1399-1427); NOT EXISTS goes to the automaton
-            if (kw1 == KW_BETWEEN) stk[sp * stride] = FastStackEntry{E_BTW1 | (P_Between << 3) | (4u << 7), cur_start};
+            if (kw1 == KW_BETWEEN) FAST_STK(sp) = FastStackEntry{E_BTW1 | (P_Between << X_POWER) | (4u << X_OP), cur_start};
             else if (kw1 == KW_IN || kw1 == KW_LIKE || kw1 == KW_ILIKE)
-              stk[sp * stride] = FastStackEntry{E_OP | (P_Comparison << 3) | ((kw1 == KW_IN ? 19u : kw1 == KW_LIKE ? 15u : 17u) << 7) |
-                                                    (cur_kind << 13), cur_start};
+              FAST_STK(sp) = FastStackEntry{E_OP | (P_Comparison << X_POWER) | ((kw1 == KW_IN ? 19u : kw1 == KW_LIKE ? 15u : 17u) << X_OP) |
+                                                (cur_kind << X_LKIND), cur_start};
             else return false;
             t += 2;
           }
@@ -296,16 +328,20 @@ struct FastParser {
         }
         if (power != P_Terminator) {
           if (sp >= DEPTH) return false;
-          stk[sp * stride] = FastStackEntry{E_OP | (power << 3) | (op << 7) | (cur_kind << 13), cur_start};
+          FAST_STK(sp) = FastStackEntry{E_OP | (power << X_POWER) | (op << X_OP) | (cur_kind << X_LKIND), cur_start};
           sp++;
           t++;
           st = FS_X_OPND;  // right operand
           continue;
         }
-        if (sp != 0) {  // inside brackets opened by this expression
-          const FastStackEntry br0 = stk[(sp - 1) * stride];
-          if ((br0.x & 7u) == E_CASE) {  // must_parse_case_when_body (mod.rs:1585-1618)
-            const uint32_t at = (br0.x >> 7) & 3u, k = ty == NUTDB_TT_KeywordOrIdentifier ? kw : 0u;
+        // a terminator.  Inside a bracket opened by this expression it belongs to the bracket; a subquery's frame is
+        // not such a bracket: the expression of the inner query is complete and the grammar table decides
+        if (sp != 0 && !(WIDE && (FAST_STK(sp - 1).x & 15u) == E_SUBQ)) {
+          const FastStackEntry br0 = FAST_STK(sp - 1);
+          const uint32_t btype = br0.x & 15u;
+          const uint32_t k = ty == NUTDB_TT_KeywordOrIdentifier ? kw : 0u;
+          if (btype == E_CASE) {  // must_parse_case_when_body (mod.rs:1585-1618)
+            const uint32_t at = (br0.x >> 8) & 3u;
             uint32_t next;
             if ((at == 0 || at == 2) && k == KW_WHEN) next = 1;
             else if (at == 1 && k == KW_THEN) next = 2;
@@ -316,30 +352,92 @@ struct FastParser {
               t++;
               cur_start = br0.y;
               cur_kind = NUTDB_NK_FNCALL;
-              FAST_EMIT(NUTDB_NK_FNCALL, (br0.x >> 9) & 7u, 0, br0.y);
+              FAST_EMIT(NUTDB_NK_FNCALL, (br0.x >> 10) & 7u, 0, br0.y);
               continue;
             } else {
               return false;
             }
-            stk[(sp - 1) * stride].x = (br0.x & ~(3u << 7)) | (next << 7);
+            FAST_STK(sp - 1).x = (br0.x & ~(3u << 8)) | (next << 8);
             t++;
             st = FS_X_OPND;
             continue;
           }
+          if (WIDE) {
+            if (btype == E_IF) {  // must_parse_if_body (mod.rs:1571-1582): IF c THEN a ELSE b END = FnName::If
+              const uint32_t at = (br0.x >> 8) & 3u;
+              if ((at == 0 && k == KW_THEN) || (at == 1 && k == KW_ELSE)) {
+                FAST_STK(sp - 1).x = (br0.x & ~(3u << 8)) | ((at + 1u) << 8);
+                t++;
+                st = FS_X_OPND;
+                continue;
+              }
+              if (at == 2 && k == KW_END) {
+                sp--;
+                t++;
+                cur_start = br0.y;
+                cur_kind = NUTDB_NK_FNCALL;
+                FAST_EMIT(NUTDB_NK_FNCALL, 0, 0, br0.y);
+                continue;
+              }
+              return false;
+            }
+            if (btype == E_MAP) {  // must_parse_map (mod.rs:1558-1568): key : value {, key : value} }
+              const uint32_t at = (br0.x >> 8) & 1u;
+              if ((at == 0 && ty == NUTDB_TT_Colon) || (at == 1 && ty == NUTDB_TT_Comma)) {
+                FAST_STK(sp - 1).x = br0.x ^ (1u << 8);
+                t++;
+                st = FS_X_OPND;
+                continue;
+              }
+              if (at == 1 && ty == NUTDB_TT_RBrace) {
+                sp--;
+                t++;
+                cur_start = br0.y;
+                cur_kind = NUTDB_NK_COLLECTION;
+                FAST_EMIT(NUTDB_NK_COLLECTION, 1, 0, br0.y);
+                continue;
+              }
+              return false;
+            }
+            if (btype == E_BRACKET) {  // [items] (mod.rs:1247-1251): Collection{Array}
+              if (ty == NUTDB_TT_Comma) {
+                t++;
+                st = FS_X_OPND;
+                continue;
+              }
+              if (ty != NUTDB_TT_RBracket) return false;
+              sp--;
+              t++;
+              cur_start = br0.y;
+              cur_kind = NUTDB_NK_COLLECTION;
+              FAST_EMIT(NUTDB_NK_COLLECTION, 2, 0, br0.y);
+              continue;
+            }
+            if (btype == E_INDEX) {  // left[index]: exactly one expression, then `]`
+              if (ty != NUTDB_TT_RBracket) return false;
+              sp--;
+              t++;
+              cur_start = br0.y;
+              cur_kind = NUTDB_NK_BINARY;
+              FAST_EMIT(NUTDB_NK_BINARY, 20, 0, br0.y);
+              continue;
+            }
+          }
           if (ty == NUTDB_TT_Comma) {
-            stk[(sp - 1) * stride].x += 1u << 21;
+            if (((br0.x >> X_COUNT) & X_COUNT_MAX) == X_COUNT_MAX) return false;  // (the item counter is full)
+            FAST_STK(sp - 1).x += 1u << X_COUNT;
             t++;
             st = FS_X_OPND;  // next item
             continue;
           }
           if (ty != NUTDB_TT_RParen) return false;
-          const FastStackEntry br = stk[(--sp) * stride];
+          const FastStackEntry br = FAST_STK(--sp);
           t++;
-          if ((br.x & 7u) == E_CALL) {
+          if ((br.x & 15u) == E_CALL) {
             FAST_EMIT(NUTDB_NK_FNCALL, 7, 0, br.y);
             cur_start = br.y;
             cur_kind = NUTDB_NK_FNCALL;
-          } else if ((br.x >> 21) != 0u) {  // one item in parentheses is the item itself (mod.rs:1236-1242)
+          } else if ((br.x >> X_COUNT) != 0u) {  // one item in parentheses is the item itself (mod.rs:1236-1242)
             FAST_EMIT(NUTDB_NK_COLLECTION, 0, 0, br.y);
             cur_start = br.y;
             cur_kind = NUTDB_NK_COLLECTION;
@@ -386,7 +484,7 @@ struct FastParser {
         const uint32_t em = (lo >> 12) & 7u;
         if (em != FE_NONE) {
           const uint32_t x = em == FE_LEAF_TOK ? t : em == FE_LEAF_NOTOK ? NUTDB_CN_NOTOK : em == FE_NODE_M0 ? m0
-                             : em == FE_NODE_M1 ? m1 : 0u;
+                             : em == FE_NODE_M1 ? m1 : (WIDE ? qbase : 0u);
           if (n < cap) nd.set_raw(n, F->rec_hdr[ri] | (((lo >> 28) & auxr) << 16) | ((lo & (1u << 29)) ? jreg << 8 : 0u), x);
           n++;
         }
@@ -411,7 +509,7 @@ struct FastParser {
             st = FS_X_OPER;
           } else {
             if (sp >= DEPTH) return false;
-            stk[sp * stride] = FastStackEntry{E_CALL, m};
+            FAST_STK(sp) = FastStackEntry{E_CALL, m};
             sp++;
             t += 2;
             st = FS_X_OPND;  // first argument
@@ -432,11 +530,24 @@ struct FastParser {
           t++;
           st = FS_X_OPER;
         }
-      } else if (act == FA_OPEN) {  // (mod.rs:1229-1246); a subquery goes to the automaton
+      } else if (act == FA_OPEN) {  // (mod.rs:1229-1246)
         const uint32_t p1 = tok.pair_at(t + 1);
-        if ((p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && ((p1 >> 8) == KW_SELECT || (p1 >> 8) == KW_WITH)) return false;
+        if ((p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && ((p1 >> 8) == KW_SELECT || (p1 >> 8) == KW_WITH)) {
+          // a subquery (must_parse_subquery, mod.rs:206-241): narrow -> the wide pass; WITH -> the automaton
+          if (!WIDE || (p1 >> 8) == KW_WITH) return false;
+          FAST_STK(sp) = FastStackEntry{m0, m1};
+          FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12), qbase};
+          sp += 2;
+          qbase = n;
+          m0 = n;
+          m1 = n;
+          ctx = C_SEL_ITEM;
+          t += 2;  // `(` and SELECT
+          st = FS_SEL0;
+          continue;
+        }
         if (sp >= DEPTH) return false;
-        stk[sp * stride] = FastStackEntry{E_PAREN, n};
+        FAST_STK(sp) = FastStackEntry{E_PAREN, n};
         sp++;
         t++;
         st = FS_X_OPND;
@@ -444,13 +555,13 @@ struct FastParser {
         if (sp >= DEPTH) return false;
         const uint32_t p1 = tok.pair_at(t + 1);
         const bool multi = (p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && (p1 >> 8) == KW_WHEN;
-        stk[sp * stride] = FastStackEntry{E_CASE | ((multi ? 1u : 0u) << 7) | ((multi ? 1u : 2u) << 9), n};
+        FAST_STK(sp) = FastStackEntry{E_CASE | ((multi ? 1u : 0u) << 8) | ((multi ? 1u : 2u) << 10), n};
         sp++;
         t += multi ? 2u : 1u;
         st = FS_X_OPND;
       } else if (act == FA_NOT) {  // prefix NOT applies to the next PREFIX expression only (mod.rs:1294-1296): `not a = b`
         if (sp >= DEPTH) return false;  // is `(not a) = b` -- so the entry is completed by whatever token comes next
-        stk[sp * stride] = FastStackEntry{E_NOT | (15u << 3), 0u};
+        FAST_STK(sp) = FastStackEntry{E_NOT | (15u << X_POWER), 0u};
         sp++;
         t++;
         st = FS_X_OPND;
@@ -475,7 +586,7 @@ struct FastParser {
         const uint32_t ty1 = tok.pair_at(t + 1) & 255u;
         if (i == 26 || i == 30 || i == 31) {  // Array / Dictionary / Nullable (inner)
           if (ty1 != NUTDB_TT_LParen || sp >= DEPTH) return false;
-          stk[sp * stride] = FastStackEntry{E_DT | ((i == 26 ? 0u : (i == 30 ? 4u : 5u)) << 3), n};
+          FAST_STK(sp) = FastStackEntry{E_DT | ((i == 26 ? 0u : (i == 30 ? 4u : 5u)) << 4), n};
           sp++;
           t += 2;  // the inner type follows (state FS_DT stays)
         } else {
@@ -498,9 +609,10 @@ struct FastParser {
           st = sp ? (uint32_t)FS_DT_END : (uint32_t)FS_COL_ATTRS;
         }
       } else if (act == FA_DTEND) {  // the closing parentheses of compound types
-        if (ty != NUTDB_TT_RParen) return false;
-        const FastStackEntry d = stk[(--sp) * stride];
-        FAST_EMIT(NUTDB_NK_DT_COMPOUND, d.x >> 3, 0, d.y);
+        if (ty != NUTDB_TT_RParen || sp == 0) return false;
+        const FastStackEntry d = FAST_STK(--sp);
+        if ((d.x & 15u) != E_DT) return false;
+        FAST_EMIT(NUTDB_NK_DT_COMPOUND, d.x >> 4, 0, d.y);
         t++;
         st = sp ? (uint32_t)FS_DT_END : (uint32_t)FS_COL_ATTRS;
       } else if (act == FA_ROWEND) {  // `)` of a VALUES row: must_parse_insert_rows (mod.rs:636-670)
@@ -520,11 +632,45 @@ struct FastParser {
         res.err_has_pos = false;
         res.err_pos = res.err_a = res.err_b = res.err_c = 0;
         return true;
+      } else if (WIDE && act == FA_IF) {  // IF c THEN a ELSE b END in operand position (mod.rs:1297-1299)
+        FAST_STK(sp) = FastStackEntry{E_IF, n};
+        sp++;
+        t++;
+        st = FS_X_OPND;
+      } else if (WIDE && act == FA_ARRAY) {  // [items]: at least one (must_parse_expr_list)
+        FAST_STK(sp) = FastStackEntry{E_BRACKET, n};
+        sp++;
+        t++;
+        st = FS_X_OPND;
+      } else if (WIDE && act == FA_MAP) {  // {key : value, ..}
+        FAST_STK(sp) = FastStackEntry{E_MAP, n};
+        sp++;
+        t++;
+        st = FS_X_OPND;
+      } else if (WIDE && act == FA_BITNOT) {  // prefix ~ applies to the next PREFIX expression only, like NOT
+        FAST_STK(sp) = FastStackEntry{E_BITNOT | (15u << X_POWER), 0u};
+        sp++;
+        t++;
+        st = FS_X_OPND;
+      } else if (WIDE && act == FA_SUBQ_END) {  // `)` right after a query body: the subquery's own parenthesis
+        if (sp < 2u || (FAST_STK(sp - 1).x & 15u) != E_SUBQ) return false;
+        const FastStackEntry f1 = FAST_STK(sp - 1), f0 = FAST_STK(sp - 2);
+        sp -= 2;
+        cur_start = qbase;
+        cur_kind = NUTDB_NK_QUERY_BODY;
+        ctx = (f1.x >> 8) & 15u;
+        jreg = (f1.x >> 12) & 7u;
+        qbase = f1.y;
+        m0 = f0.x;
+        m1 = f0.y;
+        t++;
+        st = FS_X_OPER;  // the outer expression goes on behind it
       } else {
         return false;
       }
     }
 #undef FAST_EMIT
+#undef FAST_STK
   }
 };
 

@@ -124,7 +124,7 @@ inline uint16_t fast_optok_entry(uint32_t ty) {
     case NUTDB_TT_Mul: power = P_MulDivMod; op = 2; break;
     case NUTDB_TT_Div: power = P_MulDivMod; op = 3; break;
     case NUTDB_TT_Mod: power = P_MulDivMod; op = 4; break;
-    case NUTDB_TT_LBracket: bail = 1; break;  // index access
+    case NUTDB_TT_LBracket: power = P_Access; bail = 1; break;  // index access: the wide pass (the narrow one declines)
     default: break;
   }
   return (uint16_t)(power | (op << 4) | (bail << 12));
@@ -161,6 +161,8 @@ inline uint8_t fast_type_class(uint32_t ty) {
     case NUTDB_TT_Div: case NUTDB_TT_Mod:
       return FC_BINOP;
     case NUTDB_TT_LBracket: return FC_LBRACKET;
+    case NUTDB_TT_LBrace: return FC_LBRACE;
+    case NUTDB_TT_BitNot: return FC_BITNOT;
     case NUTDB_TT_IntegerLiteral: return FC_INT;
     case NUTDB_TT_HexLiteral: return FC_HEX;
     case NUTDB_TT_FloatLiteral: return FC_FLOAT;
@@ -260,7 +262,12 @@ inline void fast_tables_build(FastTables& F) {
     B.on(st, FC_NULL, R().cur().leaf0(NUTDB_NK_LIT_NULL, 0).adv().to(FS_X_OPER));
     B.on(st, FC_NOT, R().act(FA_NOT));
     B.on(st, FC_CASE, R().act(FA_CASE));
-    B.bail(st, {FC_IF, FC_BADPFX});  // IF / INTERVAL / CASE expressions: the automaton
+    B.bail(st, {FC_BADPFX});  // INTERVAL: the automaton
+    // the wide pass only (these actions make the narrow pass decline): IF .. END, [array], {map}, prefix ~
+    B.on(st, FC_IF, R().act(FA_IF));
+    B.on(st, FC_LBRACKET, R().act(FA_ARRAY));
+    B.on(st, FC_LBRACE, R().act(FA_MAP));
+    B.on(st, FC_BITNOT, R().act(FA_BITNOT));
     B.ident(st, R().act(FA_IDENT));
     B.on(st, FC_MINUS, R().act(FA_NEG));
     B.on(st, FC_PLUS, R().adv().to(FS_X_OPND));  // prefix plus is dropped (mod.rs:1270)
@@ -378,6 +385,7 @@ inline void fast_tables_build(FastTables& F) {
   }
   B.otherwise(FS_BODY, R().node0(NUTDB_NK_QUERY_BODY).to(FS_END_SEL));
   B.bail(FS_END_SEL, {FC_SETOP});  // set operations (mod.rs:250-267)
+  B.on(FS_END_SEL, FC_RPAREN, R().act(FA_SUBQ_END));  // the `)` of a parenthesised subquery (wide pass)
   B.otherwise(FS_END_SEL, R().node0(NUTDB_NK_STMT_SELECT).to(FS_FINAL));
   // statement-final position (mod.rs:165-172)
   B.on(FS_FINAL, {FC_EOF, FC_SEMI}, R().act(FA_ACCEPT));

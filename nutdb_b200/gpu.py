@@ -94,6 +94,8 @@ def lib():
     L.nutdb_gpu_kernel_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     L.nutdb_gpu_last_slow_statements.restype = C.c_uint64
     L.nutdb_gpu_last_slow_statements.argtypes = [C.c_void_p]
+    L.nutdb_gpu_last_wide_statements.restype = C.c_uint64
+    L.nutdb_gpu_last_wide_statements.argtypes = [C.c_void_p]
     L.nutdb_gpu_last_exact_lexed_statements.restype = C.c_uint64
     L.nutdb_gpu_last_exact_lexed_statements.argtypes = [C.c_void_p]
     L.nutdb_gpu_mctx_create.restype = C.c_void_p
@@ -255,6 +257,9 @@ class Context:
 
     def slow_statements(self):
         return lib().nutdb_gpu_last_slow_statements(self._h)
+
+    def wide_statements(self):
+        return lib().nutdb_gpu_last_wide_statements(self._h)
 
     def exact_lexed_statements(self):
         return lib().nutdb_gpu_last_exact_lexed_statements(self._h)

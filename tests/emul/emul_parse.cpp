@@ -84,10 +84,10 @@ struct HText {
 };
 }  // namespace
 
-static int g_use_fast = 1;
+static int g_use_fast = 2;        // 0 = automaton only, 1 = narrow table-driven pass first, 2 = narrow, then wide
 static int g_lexer = 3;          // 1 = thread-per-chunk walker, 2 = three-pass mask lexer, 3 = single-pass lexer
 static uint32_t g_seg_len = 1024;
-static uint64_t g_fast_hits = 0;
+static uint64_t g_fast_hits = 0, g_wide_hits = 0;
 
 extern "C" {
 
@@ -97,7 +97,8 @@ void emul_set_lexer(int version, uint32_t seg_len) {
   g_seg_len = seg_len;
 }
 uint64_t emul_fast_hits(void) { return g_fast_hits; }
-void emul_reset_fast_hits(void) { g_fast_hits = 0; }
+uint64_t emul_wide_hits(void) { return g_wide_hits; }
+void emul_reset_fast_hits(void) { g_fast_hits = g_wide_hits = 0; }
 
 // Parses every statement.  Outputs: stmt[nstmt] (NutdbStmt), nodes (compact, caller cap), errors.
 // Returns 0, or -1 on capacity overflow.
@@ -158,6 +159,35 @@ int emul_parse_batch(const uint8_t* text, const uint64_t* offs, uint64_t nstmt, 
         npar::FastStackEntry fstack[FAST_STACK_DEPTH];
         npar::FastParser<HTokAdapter, HNodes, HText> f(&FT, tk, nd, tx, fstack, 1);
         fast = f.try_parse(res);
+        if (!fast && g_use_fast >= 2) {
+          // the wide pass: nodes and operator stack share one range of tok_count + NODE_SLACK slots (nodes from the
+          // bottom, the stack from the top), exactly the device's layout
+          const uint32_t wcap = (e - b) + 8;
+          std::vector<npar::CNode> range(wcap);
+          struct WNodes {
+            npar::CNode* p;
+            uint32_t cap;
+            npar::CNode get(uint32_t i) const { return p[i]; }
+            void set(uint32_t i, const npar::CNode& x) { p[i] = x; }
+            void set_raw(uint32_t i, uint32_t header, uint32_t x) {
+              npar::CNode c;
+              c.kind = (uint8_t)(header & 0xFF);
+              c.sub = (uint8_t)((header >> 8) & 0xFF);
+              c.aux = (uint16_t)(header >> 16);
+              c.x = x;
+              p[i] = c;
+            }
+            uint32_t capacity() const { return cap; }
+          } wn{range.data(), wcap};
+          static_assert(sizeof(npar::CNode) == sizeof(npar::FastStackEntry), "the wide stack shares the node range");
+          npar::FastParser<HTokAdapter, WNodes, HText, true> w(&FT, tk, wn, tx,
+                                                                reinterpret_cast<npar::FastStackEntry*>(range.data()) + (wcap - 1), -1);
+          fast = w.try_parse(res);
+          if (fast) {
+            g_wide_hits++;
+            tmp.assign(range.begin(), range.begin() + res.node_count);
+          }
+        }
       }
       if (fast) {
         g_fast_hits++;

@@ -109,7 +109,14 @@ def lex3_check_classes(bytes32):
 
 
 def set_fast(on):
-    parse_lib().emul_set_fast(1 if on else 0)
+    """0 / False: the automaton alone; 1: the narrow table-driven pass first; 2 / True: narrow, then wide (the device's order)."""
+    parse_lib().emul_set_fast(2 if on is True else int(on))
+
+
+def wide_hits():
+    L = parse_lib()
+    L.emul_wide_hits.restype = C.c_uint64
+    return L.emul_wide_hits()
 
 
 def fast_hits(reset=True):
