@@ -271,10 +271,10 @@ def run_log(args, rank, world, local, barrier):
         def consume(ch):   # the consumer's read of a gathered chunk
             r = ch.raw
             with lock:
-                acc["bytes"] = acc.get("bytes", 0) + 24 * r.n_stmt + 8 * r.n_node + 32 * r.n_err
+                acc["bytes"] = acc.get("bytes", 0) + 24 * r.n_stmt + 4 * r.n_node + 32 * r.n_err
                 acc["stmts"] = acc.get("stmts", 0) + r.n_stmt
                 if not ch.on_device and r.n_stmt:
-                    acc["last"] = int(ch.batch.stmt["status"][-1]) + int(ch.batch.cnode["kind"][-1])
+                    acc["last"] = int(ch.batch.stmt["status"][-1]) + int(ch.batch.pnode[-1] & 127)
 
         for _ in range(2):
             acc.clear()
@@ -566,7 +566,7 @@ def main():
             acc["n_node"] = acc.get("n_node", 0) + int(bb.n_node)
             acc["n_err"] = acc.get("n_err", 0) + int(bb.n_err)
             acc["last_status"] = int(bb.stmt["status"][-1]) if bb.n_stmt else 0
-            acc["last_kind"] = int(bb.cnode["kind"][-1]) if bb.n_node else 0
+            acc["last_kind"] = int(bb.pnode[-1] & 127) if bb.n_node else 0
 
         def step_host():
             acc.clear()
@@ -586,7 +586,7 @@ def main():
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         sp.close()
         h2d = n_in + 8 * (n_stmt + 1)
-        d2h = 24 * n_stmt + 8 * int(acc["n_node"]) + 32 * int(acc["n_err"])   # NutdbStmt, NutdbCNode (wire), NutdbError
+        d2h = 24 * n_stmt + 4 * int(acc["n_node"]) + 32 * int(acc["n_err"])   # NutdbStmt, wire nodes (32-bit), NutdbError
         e2e = {"ms": e2e_ms, "h2d": h2d, "d2h": d2h}
         del h_text, h_offs
 
@@ -646,7 +646,7 @@ def main():
                            "ms_per_step": e2e_ms_max, "statements_per_s": tot_stmts / (e2e_ms_max * 1e-3),
                            "api": "nutdb_b200.stream.StreamParser: nutdb_gpu_parse_batch(pinned host text, host offsets, "
                                   f"NUTDB_F_NO_TOKENS) per chunk on {args.e2e_workers} contexts -> pinned host stmt / wire-node "
-                                  "(NutdbCNode, 8 B) / err arrays",
+                                  "(32-bit words) / err arrays",
                            "chunk_bytes": args.e2e_chunk}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(text, offs)

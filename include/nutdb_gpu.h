@@ -130,21 +130,39 @@ typedef struct {
   uint32_t b;
 } NutdbNode;
 
-/* The WIRE form of a node: 8 bytes, what the device produces and what crosses PCIe (NutdbBatch.cnode).  Same order
- * (post-order per statement), same kind / sub.  It carries everything NutdbNode does -- a re-hydrator walks it with a
- * stack (an interior node's children are the stack entries at or above its subtree start) and never needs `parent`:
- *   interior : aux = flag bits, x = subtree_start
- *   leaf     : aux = flag bit 0 | span length << 1, x = span start; the span is [x, x + length).  A length of
- *              NUTDB_CN_LONG (32767) means "32767 bytes or more": the true length is in the batch's long_len table
- *              under this node's index in long_idx (both sorted by node index; rare -- a 32 KB string literal).
- * nutdb_batch_expand_nodes() turns them into NutdbNode records on the host. */
+/* The WIRE form of a node: ONE 32-bit word -- what the device produces and what crosses PCIe (NutdbBatch.pnode).  Same
+ * order (post-order per statement), same kind / sub.  It carries everything NutdbNode does: a re-hydrator walks a
+ * statement's words front to back with a running byte position `pos` (0 at the statement's start) and a stack, and
+ * never needs `parent`:
+ *   bits 0-6 kind, 7-11 sub, 12 = bit 0 of aux, then
+ *   interior : bits 13-31 = subtree SIZE: the subtree is the `size` nodes in front of this one, so subtree_start =
+ *              index - size.  NUTDB_PN_SIZE_EXT: see the side table.
+ *   leaf     : bits 13-22 = gap, bits 23-31 = length: the span is [pos + gap, pos + gap + length) and pos moves to its
+ *              end (leaves come in text order).  length == NUTDB_PN_LEN_SPECIAL marks the two special forms:
+ *              gap == NUTDB_PN_GAP_NOSPAN: the leaf has no source span (a = b = 0; pos does not move);
+ *              gap == NUTDB_PN_GAP_EXT: see the side table.
+ * Side table (NutdbBatch.ext, sorted by batch-global node index; rare: a literal of 511 bytes or more, a kilobyte of
+ * comment in front of a token, a subtree of half a million nodes): the exact fields of a node that does not fit --
+ * hdr = kind | sub << 8 | aux << 16; leaf: a = span start, b = span length (pos moves to a + b); interior: a = subtree
+ * start (statement relative).
+ * nutdb_batch_expand_nodes() turns a batch's wire nodes into NutdbNode records on the host. */
+#define NUTDB_PN_SUB_SHIFT 7
+#define NUTDB_PN_FLAG_SHIFT 12
+#define NUTDB_PN_SIZE_SHIFT 13
+#define NUTDB_PN_SIZE_MAX 0x7FFFEu
+#define NUTDB_PN_SIZE_EXT 0x7FFFFu
+#define NUTDB_PN_GAP_SHIFT 13
+#define NUTDB_PN_GAP_MAX 1021u
+#define NUTDB_PN_GAP_EXT 1022u
+#define NUTDB_PN_GAP_NOSPAN 1023u
+#define NUTDB_PN_LEN_SHIFT 23
+#define NUTDB_PN_LEN_MAX 510u
+#define NUTDB_PN_LEN_SPECIAL 511u
 typedef struct {
-  uint8_t kind;
-  uint8_t sub;
-  uint16_t aux;
-  uint32_t x;
-} NutdbCNode;
-#define NUTDB_CN_LONG 32767u
+  uint32_t index; /* node index in the batch */
+  uint32_t hdr;   /* kind | sub << 8 | aux << 16 */
+  uint32_t a, b;
+} NutdbNodeExt;
 
 #define NUTDB_NO_PARENT 0xFFFFFFFFu
 #define NUTDB_NK_FIRST_INTERIOR 32
@@ -339,13 +357,12 @@ typedef struct {
   const uint32_t *tok_start;/* [n_tok]  payload span start, statement-relative */
   const uint32_t *tok_end;  /* [n_tok] */
   const uint8_t *tok_kw;    /* [n_tok]  KeywordOrIdentifier: keyword id or 0; Integer/HexLiteral: digit count (max 255); else 0 */
-  const NutdbNode *node;    /* [n_node] expanded nodes: NULL in batches produced by the library (see cnode) */
+  const NutdbNode *node;    /* [n_node] expanded nodes: NULL in batches produced by the library (see pnode) */
   const NutdbError *err;    /* [n_err]  sorted by .stmt */
   void *impl;               /* opaque */
-  const NutdbCNode *cnode;  /* [n_node] wire nodes */
-  uint64_t n_long;          /* leaves whose span is NUTDB_CN_LONG bytes or more */
-  const uint32_t *long_idx; /* [n_long] their node indices, ascending */
-  const uint32_t *long_len; /* [n_long] their span lengths */
+  const uint32_t *pnode;    /* [n_node] wire nodes (NUTDB_PN_*) */
+  uint64_t n_ext;           /* nodes whose fields did not fit the wire word */
+  const NutdbNodeExt *ext;  /* [n_ext] sorted by .index; host memory whatever the flags */
 } NutdbBatch;
 
 typedef struct NutdbCtx NutdbCtx;
@@ -382,7 +399,7 @@ void nutdb_gpu_batch_free(NutdbCtx *ctx, NutdbBatch *batch);
  * arithmetic, no parsing.  `out` must hold n_node records.  Returns 0, or NUTDB_E_ARG. */
 int nutdb_batch_expand_nodes(const NutdbBatch *batch, NutdbNode *out);
 
-/* Device-side views of the last batch (valid until batch_free); `node` points at the WIRE nodes (NutdbCNode). */
+/* Device-side views of the last batch (valid until batch_free); `node` points at the WIRE nodes (32-bit words). */
 typedef struct {
   const void *stmt, *tok_type, *tok_start, *tok_end, *tok_kw, *node, *err;
 } NutdbBatchDevice;
@@ -463,7 +480,7 @@ typedef struct {
   uint64_t first_stmt;
   int device;              /* CUDA ordinal that parsed it */
   int on_device;           /* 0: batch pointers are pinned host memory; 1: memory of the dispatcher's first device */
-  NutdbBatch batch;        /* counts, stmt, cnode, err (+ tokens); long_idx / long_len are always host memory */
+  NutdbBatch batch;        /* counts, stmt, pnode, err (+ tokens); ext is always host memory */
 } NutdbMChunk;
 
 typedef void (*nutdb_chunk_fn)(void *user, const NutdbMChunk *chunk);

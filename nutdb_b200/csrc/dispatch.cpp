@@ -26,7 +26,7 @@
 namespace {
 
 struct Slot {  // gather buffers of one worker, grow-only
-  void* p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // stmt, cnode, err, tok_type, tok_start, tok_end, tok_kw
+  void* p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // stmt, pnode, err, tok_type, tok_start, tok_end, tok_kw
   size_t cap[7] = {0, 0, 0, 0, 0, 0, 0};
   bool on_device = false;
 };
@@ -146,7 +146,7 @@ void work(Run& r, Worker& w) {
     // ---- gather: one copy per array from the producing device to the gather point ----
     Slot& s = to_dev0 ? w.dev0 : w.host;
     const void* src[7] = {dv.stmt, dv.node, dv.err, dv.tok_type, dv.tok_start, dv.tok_end, dv.tok_kw};
-    const size_t bytes[7] = {sizeof(NutdbStmt) * (size_t)b.n_stmt, sizeof(NutdbCNode) * (size_t)b.n_node,
+    const size_t bytes[7] = {sizeof(NutdbStmt) * (size_t)b.n_stmt, sizeof(uint32_t) * (size_t)b.n_node,
                              sizeof(NutdbError) * (size_t)b.n_err, want_tokens ? (size_t)b.n_tok : 0,
                              want_tokens ? 4 * (size_t)b.n_tok : 0, want_tokens ? 4 * (size_t)b.n_tok : 0,
                              want_tokens ? (size_t)b.n_tok : 0};
@@ -182,7 +182,7 @@ void work(Run& r, Worker& w) {
     c.batch.n_node = b.n_node;
     c.batch.n_err = b.n_err;
     c.batch.stmt = (const NutdbStmt*)(bytes[0] ? s.p[0] : nullptr);
-    c.batch.cnode = (const NutdbCNode*)(bytes[1] ? s.p[1] : nullptr);
+    c.batch.pnode = (const uint32_t*)(bytes[1] ? s.p[1] : nullptr);
     c.batch.err = (const NutdbError*)(bytes[2] ? s.p[2] : nullptr);
     if (want_tokens && b.n_tok) {
       c.batch.tok_type = (const uint8_t*)s.p[3];
@@ -190,9 +190,8 @@ void work(Run& r, Worker& w) {
       c.batch.tok_end = (const uint32_t*)s.p[5];
       c.batch.tok_kw = (const uint8_t*)s.p[6];
     }
-    c.batch.n_long = b.n_long;
-    c.batch.long_idx = b.long_idx;
-    c.batch.long_len = b.long_len;
+    c.batch.n_ext = b.n_ext;
+    c.batch.ext = b.ext;
     if (r.fn) {
       if (r.flags & NUTDB_MF_SERIAL_CALLBACKS) {
         std::lock_guard<std::mutex> g(r.cb_mu);

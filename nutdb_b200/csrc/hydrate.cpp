@@ -963,49 +963,86 @@ const NutdbError* find_error(const NutdbBatch* b, uint64_t i) {
 
 }  // namespace
 
-// Wire nodes (NutdbCNode) of one statement -> NutdbNode records: spans from (start, length), child counts and parent
-// links by walking each interior node's children backwards from the node before it (post-order: a child's subtree
-// ends right before its next sibling's begins).
-static uint32_t long_leaf_len(const NutdbBatch* b, uint32_t node_index) {
-  uint64_t lo = 0, hi = b->n_long;
+// Wire nodes (32-bit words, NUTDB_PN_*) of one statement -> NutdbNode records: spans from the running position and
+// the (gap, length) fields, subtree starts from the sizes, child counts and parent links by walking each interior
+// node's children backwards from the node before it (post-order: a child's subtree ends right before its next
+// sibling's begins).
+static const NutdbNodeExt* find_ext(const NutdbBatch* b, uint32_t node_index) {
+  uint64_t lo = 0, hi = b->n_ext;
   while (lo < hi) {
     const uint64_t mid = (lo + hi) / 2;
-    if (b->long_idx[mid] < node_index) lo = mid + 1;
+    if (b->ext[mid].index < node_index) lo = mid + 1;
     else hi = mid;
   }
-  return (lo < b->n_long && b->long_idx[lo] == node_index) ? b->long_len[lo] : NUTDB_CN_LONG;
+  return (lo < b->n_ext && b->ext[lo].index == node_index) ? &b->ext[lo] : nullptr;
 }
-static void expand_stmt_nodes(const NutdbBatch* b, uint64_t begin, uint32_t count, NutdbNode* out) {
-  const NutdbCNode* c = b->cnode + begin;
+// false: a malformed stream (an escape without its side-table entry, a subtree that starts before the statement)
+static bool expand_stmt_nodes(const NutdbBatch* b, uint64_t begin, uint32_t count, NutdbNode* out) {
+  const uint32_t* w = b->pnode + begin;
+  uint32_t pos = 0;
+  // pass 1: kind / sub / aux, spans (leaves), subtree starts (interior nodes: kept in .a)
+  for (uint32_t j = 0; j < count; j++) {
+    NutdbNode& o = out[j];
+    const uint32_t x = w[j];
+    o.kind = (uint8_t)(x & 127u);
+    o.sub = (uint8_t)((x >> NUTDB_PN_SUB_SHIFT) & 31u);
+    o.aux = (uint16_t)((x >> NUTDB_PN_FLAG_SHIFT) & 1u);
+    o.parent = NUTDB_NO_PARENT;
+    if (o.kind >= NUTDB_NK_FIRST_INTERIOR) {
+      const uint32_t size = x >> NUTDB_PN_SIZE_SHIFT;
+      if (size == NUTDB_PN_SIZE_EXT) {
+        const NutdbNodeExt* e = find_ext(b, (uint32_t)(begin + j));
+        if (!e) return false;
+        o.kind = (uint8_t)(e->hdr & 255u);
+        o.sub = (uint8_t)((e->hdr >> 8) & 255u);
+        o.aux = (uint16_t)(e->hdr >> 16);
+        o.a = e->a;
+      } else {
+        if (size > j) return false;
+        o.a = j - size;
+      }
+      o.b = 0;
+    } else {
+      const uint32_t gap = (x >> NUTDB_PN_GAP_SHIFT) & 1023u, len = x >> NUTDB_PN_LEN_SHIFT;
+      if (len == NUTDB_PN_LEN_SPECIAL && gap == NUTDB_PN_GAP_NOSPAN) {
+        o.a = o.b = 0;
+      } else if (len == NUTDB_PN_LEN_SPECIAL && gap == NUTDB_PN_GAP_EXT) {
+        const NutdbNodeExt* e = find_ext(b, (uint32_t)(begin + j));
+        if (!e) return false;
+        o.kind = (uint8_t)(e->hdr & 255u);
+        o.sub = (uint8_t)((e->hdr >> 8) & 255u);
+        o.aux = (uint16_t)((e->hdr >> 16) & 1u);
+        o.a = e->a;
+        o.b = e->a + e->b;
+        pos = o.b;
+      } else {
+        o.a = pos + gap;
+        o.b = o.a + len;
+        pos = o.b;
+      }
+    }
+  }
+  // pass 2: child counts and parent links
   auto subtree_start = [&](uint32_t r) -> uint32_t {
-    if (c[r].kind >= NUTDB_NK_FIRST_INTERIOR) return c[r].x;
-    return (c[r].kind == NUTDB_NK_IDENT && (c[r].aux & 1)) ? r - 1 : r;
+    if (out[r].kind >= NUTDB_NK_FIRST_INTERIOR) return out[r].a;
+    return (out[r].kind == NUTDB_NK_IDENT && (out[r].aux & 1) && r > 0) ? r - 1 : r;
   };
   for (uint32_t j = 0; j < count; j++) {
     NutdbNode& o = out[j];
-    o.kind = c[j].kind;
-    o.sub = c[j].sub;
-    if (c[j].kind >= NUTDB_NK_FIRST_INTERIOR) {
-      o.aux = c[j].aux;
-      o.a = c[j].x;
+    if (o.kind >= NUTDB_NK_FIRST_INTERIOR) {
       uint32_t nchild = 0;
       int64_t r = (int64_t)j - 1;
-      while (r >= (int64_t)c[j].x) {
+      while (r >= (int64_t)o.a) {
         out[r].parent = j;
         nchild++;
         r = (int64_t)subtree_start((uint32_t)r) - 1;
       }
       o.b = nchild;
-    } else {
-      o.aux = c[j].aux & 1u;
-      uint32_t len = c[j].aux >> 1;
-      if (len == NUTDB_CN_LONG) len = long_leaf_len(b, (uint32_t)(begin + j));
-      o.a = c[j].x;
-      o.b = c[j].x + len;
-      if (c[j].kind == NUTDB_NK_IDENT && (c[j].aux & 1) && j > 0) out[j - 1].parent = j;
+    } else if (o.kind == NUTDB_NK_IDENT && (o.aux & 1) && j > 0) {
+      out[j - 1].parent = j;
     }
-    if (j + 1 == count) o.parent = NUTDB_NO_PARENT;
   }
+  return true;
 }
 
 extern "C" {
@@ -1013,14 +1050,14 @@ extern "C" {
 size_t nutdb_fmt_debug(const NutdbBatch* batch, uint64_t i, const uint8_t* sql, size_t len, char* buf, size_t cap) {
   if (!batch || !batch->stmt || i >= batch->n_stmt) return 0;
   const NutdbStmt& s = batch->stmt[i];
-  if (s.status != NUTDB_ST_OK || s.node_count == 0 || (!batch->node && !batch->cnode)) return deliver(std::string(), buf, cap);
+  if (s.status != NUTDB_ST_OK || s.node_count == 0 || (!batch->node && !batch->pnode)) return deliver(std::string(), buf, cap);
   std::vector<NutdbNode> expanded;
   const NutdbNode* nodes;
   if (batch->node) {
     nodes = batch->node + s.node_begin;
   } else {  // the library's batches carry wire nodes: expand this statement's
     expanded.resize(s.node_count);
-    expand_stmt_nodes(batch, s.node_begin, s.node_count, expanded.data());
+    if (!expand_stmt_nodes(batch, s.node_begin, s.node_count, expanded.data())) return deliver(std::string(), buf, cap);
     nodes = expanded.data();
   }
   H h{nodes, s.node_count, sql, len, std::string()};
@@ -1041,10 +1078,11 @@ size_t nutdb_fmt_error(const NutdbBatch* batch, uint64_t i, const uint8_t* sql, 
 }
 
 int nutdb_batch_expand_nodes(const NutdbBatch* batch, NutdbNode* out) {
-  if (!batch || !out || (batch->n_node && !batch->cnode) || (batch->n_stmt && !batch->stmt)) return NUTDB_E_ARG;
+  if (!batch || !out || (batch->n_node && !batch->pnode) || (batch->n_stmt && !batch->stmt)) return NUTDB_E_ARG;
   for (uint64_t i = 0; i < batch->n_stmt; i++) {
     const NutdbStmt& s = batch->stmt[i];
-    if (s.status == NUTDB_ST_OK && s.node_count) expand_stmt_nodes(batch, s.node_begin, s.node_count, out + s.node_begin);
+    if (s.status == NUTDB_ST_OK && s.node_count && !expand_stmt_nodes(batch, s.node_begin, s.node_count, out + s.node_begin))
+      return NUTDB_E_ARG;
   }
   return NUTDB_OK;
 }

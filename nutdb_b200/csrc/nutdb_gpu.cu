@@ -994,9 +994,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
                                                           const uint32_t* __restrict__ tok_start,
                                                           const uint32_t* __restrict__ tok_end,
                                                           const uint32_t* __restrict__ punt,
-                                                          uint2* __restrict__ node_out, uint4* __restrict__ err_out,
-                                                          uint32_t* __restrict__ long_count, uint2* __restrict__ long_out,
-                                                          uint32_t long_cap) {
+                                                          uint32_t* __restrict__ node_out, uint4* __restrict__ err_out,
+                                                          uint32_t* __restrict__ ext_count, uint4* __restrict__ ext_out,
+                                                          uint32_t ext_cap) {
   __shared__ uint2 ws[32];
   __shared__ uint32_t lbegin[FIN_THREADS + 1];
   __shared__ uint32_t ltok[FIN_THREADS];
@@ -1047,25 +1047,48 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
     }
     // `lo` owns node j (statements without nodes share their offset with the next one and are skipped
     // by "last k"); its nodes are [lbegin[lo], lbegin[lo+1]) of this block's range.
-    // The WIRE node (NutdbCNode): interior nodes as the parser left them (header, subtree start); a leaf's token
-    // index becomes its byte span (start, length in the upper 15 bits of aux).
-    const uint2 c = lsrc[lo][j - lbegin[lo]];
-    uint32_t w0 = c.x, w1 = c.y;
-    if ((c.x & 0xFFu) < NUTDB_NK_FIRST_INTERIOR) {
-      uint32_t a = 0, len = 0;
-      if (c.y != NUTDB_CN_NOTOK) {
-        a = tok_start[ltok[lo] + c.y];
-        len = tok_end[ltok[lo] + c.y] - a;
+    // The WIRE node: one 32-bit word (nutdb_gpu.h, NUTDB_PN_*).  An interior node carries its subtree SIZE; a leaf
+    // carries its byte span as (gap to the end of the leaf before it, length) -- leaves come in text order, so the
+    // reader keeps a running position.  Whatever does not fit (a long literal, a long comment in front of a token, a
+    // huge subtree) goes to the side table with its exact fields.
+    const uint2* const nodes_s = lsrc[lo];
+    const uint32_t jj = j - lbegin[lo];
+    const uint2 c = nodes_s[jj];
+    const uint32_t kind = c.x & 0xFFu, sub = (c.x >> 8) & 0xFFu, aux = c.x >> 16;
+    uint32_t w = kind | ((sub & 31u) << NUTDB_PN_SUB_SHIFT) | ((aux & 1u) << NUTDB_PN_FLAG_SHIFT);
+    bool esc = sub > 31u || kind > 127u;
+    uint32_t ea = 0, eb = 0;
+    if (kind < NUTDB_NK_FIRST_INTERIOR) {
+      if (c.y == NUTDB_CN_NOTOK) {
+        w |= (NUTDB_PN_GAP_NOSPAN << NUTDB_PN_GAP_SHIFT) | (NUTDB_PN_LEN_SPECIAL << NUTDB_PN_LEN_SHIFT);
+        esc = esc || aux > 1u;
+      } else {
+        const uint32_t a = tok_start[ltok[lo] + c.y], b = tok_end[ltok[lo] + c.y];
+        uint32_t prev_end = 0;  // end of the nearest leaf with a span in front of this one
+        for (uint32_t k = jj; k-- > 0;) {
+          const uint2 p = nodes_s[k];
+          if ((p.x & 0xFFu) < NUTDB_NK_FIRST_INTERIOR && p.y != NUTDB_CN_NOTOK) {
+            prev_end = tok_end[ltok[lo] + p.y];
+            break;
+          }
+        }
+        ea = a;
+        eb = b - a;
+        esc = esc || aux > 1u || a < prev_end || a - prev_end > NUTDB_PN_GAP_MAX || b - a > NUTDB_PN_LEN_MAX;
+        w |= ((a - prev_end) << NUTDB_PN_GAP_SHIFT) | ((b - a) << NUTDB_PN_LEN_SHIFT);  // (overwritten below when escaped)
       }
-      if (len >= NUTDB_CN_LONG) {  // (a 32 KB literal: its length goes to a side table the host sorts)
-        const uint32_t q = atomicAdd(long_count, 1u);
-        if (q < long_cap) long_out[q] = make_uint2(base.x + j, len);
-        len = NUTDB_CN_LONG;
-      }
-      w0 = (c.x & 0x0001FFFFu) | (len << 17);
-      w1 = a;
+      if (esc) w = (w & ((1u << NUTDB_PN_GAP_SHIFT) - 1u)) | (NUTDB_PN_GAP_EXT << NUTDB_PN_GAP_SHIFT) | (NUTDB_PN_LEN_SPECIAL << NUTDB_PN_LEN_SHIFT);
+    } else {
+      const uint32_t size = jj - c.y;  // (c.y = subtree start, statement relative)
+      ea = c.y;
+      esc = esc || aux > 1u || size > NUTDB_PN_SIZE_MAX;
+      w |= (esc ? NUTDB_PN_SIZE_EXT : size) << NUTDB_PN_SIZE_SHIFT;
     }
-    node_out[(size_t)base.x + j] = make_uint2(w0, w1);
+    if (esc) {
+      const uint32_t q = atomicAdd(ext_count, 1u);
+      if (q < ext_cap) ext_out[q] = make_uint4(base.x + j, c.x, ea, eb);
+    }
+    node_out[(size_t)base.x + j] = w;
   }
 }
 
@@ -1108,9 +1131,9 @@ struct NutdbCtx {
   uint32_t dbg_ntiles = 0;
   bool debug_sync = false;  // NUTDB_GPU_DEBUG_SYNC=1: synchronise after every launch and name the kernel that failed
   DevBuf dbgTiles;
-  DevBuf longNodes;
-  HostBuf hLong;
-  std::vector<uint32_t> long_idx, long_len;
+  DevBuf extNodes;
+  HostBuf hExt;
+  std::vector<NutdbNodeExt> ext;
   DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
@@ -1234,7 +1257,7 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
   } while (0)
 
 void free_all(NutdbCtx* c) {
-  DevBuf* d[] = {&c->longNodes, &c->rangeByte, &c->rangeStmt, &c->rangeTokBase, &c->rangeCount, &c->rangeDense, &c->tokTypeD, &c->tokStartD, &c->tokEndD, &c->tokKwD, &c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
+  DevBuf* d[] = {&c->extNodes, &c->rangeByte, &c->rangeStmt, &c->rangeTokBase, &c->rangeCount, &c->rangeDense, &c->tokTypeD, &c->tokStartD, &c->tokEndD, &c->tokKwD, &c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
@@ -1242,7 +1265,7 @@ void free_all(NutdbCtx* c) {
                  &c->splitTile, &c->splitPref, &c->splitOff};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
-  HostBuf* h[] = {&c->hLong, &c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
+  HostBuf* h[] = {&c->hExt, &c->hSmall, &c->hStmt, &c->hTokType, &c->hTokStart, &c->hTokEnd, &c->hTokKw, &c->hNode, &c->hErr,
                   &c->hRetry, &c->hSplit};
   for (HostBuf* b : h)
     if (b->p) cudaFreeHost(b->p);
@@ -1606,6 +1629,7 @@ run_again:
 
   // ---- parser ----
   uint64_t n_node = 0, n_err = 0;
+  uint32_t ext_cap = 0;
   const bool native_lex = n > 0 && !lex_only;
   if (nstmt > 0) {
     // compact-node scratch: a disjoint range of tok_count + NODE_SLACK slots per statement (see node_slot)
@@ -1719,15 +1743,15 @@ run_again:
     }
     n_node = hS[8];
     n_err = hS[9];
-    ENSURE_DEV(nodes, 8 * (n_node + 1));
+    ENSURE_DEV(nodes, 4 * (n_node + 4));
     ENSURE_DEV(errs, 32 * (n_err + 1));
-    const uint32_t long_cap = n / NUTDB_CN_LONG + 16u;  // (a long leaf spans that many bytes of its own)
-    ENSURE_DEV(longNodes, 8 * (size_t)long_cap);
+    ext_cap = std::max<uint32_t>(n / 64u, 1024u);  // side table of the nodes that do not fit the 32-bit wire form
+    ENSURE_DEV(extNodes, 16 * (size_t)ext_cap);
     LAUNCH("k_finalize", k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
                                                (const uint2*)ctx->scratch.p, (const uint2*)ctx->retryNodes.p,
                                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
-                                               (const uint32_t*)ctx->puntFlag.p, (uint2*)ctx->nodes.p,
-                                               (uint4*)ctx->errs.p, dS + 26, (uint2*)ctx->longNodes.p, long_cap));
+                                               (const uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->nodes.p,
+                                               (uint4*)ctx->errs.p, dS + 26, (uint4*)ctx->extNodes.p, ext_cap));
   } else {
     CK(cudaMemcpyAsync(hS, dS, 128, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1763,16 +1787,16 @@ run_again:
   out->n_node = n_node;
   out->n_err = n_err;
   hS[48] = 0;
-  if (n_node) CK(cudaMemcpyAsync(hS + 48, dS + 26, 4, cudaMemcpyDeviceToHost, st));  // long leaves (almost always none)
+  if (n_node) CK(cudaMemcpyAsync(hS + 48, dS + 26, 4, cudaMemcpyDeviceToHost, st));  // side-table entries (almost always none)
   if (!(flags & NUTDB_F_NO_HOST_COPY)) {
     ENSURE_HOST(hStmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
-    ENSURE_HOST(hNode, 8 * (n_node + 1));
+    ENSURE_HOST(hNode, 4 * (n_node + 4));
     ENSURE_HOST(hErr, 32 * (n_err + 1));
     if (nstmt) CK(cudaMemcpyAsync(ctx->hStmt.p, ctx->stmt.p, sizeof(NutdbStmt) * (size_t)nstmt, cudaMemcpyDeviceToHost, st));
-    if (n_node) CK(cudaMemcpyAsync(ctx->hNode.p, ctx->nodes.p, 8 * n_node, cudaMemcpyDeviceToHost, st));
+    if (n_node) CK(cudaMemcpyAsync(ctx->hNode.p, ctx->nodes.p, 4 * n_node, cudaMemcpyDeviceToHost, st));
     if (n_err) CK(cudaMemcpyAsync(ctx->hErr.p, ctx->errs.p, 32 * n_err, cudaMemcpyDeviceToHost, st));
     out->stmt = (const NutdbStmt*)ctx->hStmt.p;
-    out->cnode = (const NutdbCNode*)ctx->hNode.p;
+    out->pnode = (const uint32_t*)ctx->hNode.p;
     out->err = (const NutdbError*)ctx->hErr.p;
     if (!(flags & NUTDB_F_NO_TOKENS)) {
       ENSURE_HOST(hTokType, (size_t)ntok + 16);
@@ -1794,23 +1818,19 @@ run_again:
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  if (n_node && hS[48]) {  // leaves of 32 KB and more: their lengths, by node index (a host table whatever the flags)
-    const uint32_t nl = std::min<uint32_t>(hS[48], n / NUTDB_CN_LONG + 16u);
-    ENSURE_HOST(hLong, 8 * (size_t)nl);
-    CK(cudaMemcpy(ctx->hLong.p, ctx->longNodes.p, 8 * (size_t)nl, cudaMemcpyDeviceToHost));
-    std::vector<std::pair<uint32_t, uint32_t>> v(nl);
-    const uint32_t* hp = (const uint32_t*)ctx->hLong.p;
-    for (uint32_t i = 0; i < nl; i++) v[i] = {hp[2 * i], hp[2 * i + 1]};
-    std::sort(v.begin(), v.end());
-    ctx->long_idx.resize(nl);
-    ctx->long_len.resize(nl);
-    for (uint32_t i = 0; i < nl; i++) {
-      ctx->long_idx[i] = v[i].first;
-      ctx->long_len[i] = v[i].second;
+  if (n_node && hS[48]) {  // nodes that did not fit the 32-bit wire form: their exact fields, sorted by node index
+    if (hS[48] > ext_cap) {
+      ctx->err = "node side table overflow";
+      return NUTDB_E_NOMEM;
     }
-    out->n_long = nl;
-    out->long_idx = ctx->long_idx.data();
-    out->long_len = ctx->long_len.data();
+    const uint32_t nl = hS[48];
+    ENSURE_HOST(hExt, 16 * (size_t)nl);
+    CK(cudaMemcpy(ctx->hExt.p, ctx->extNodes.p, 16 * (size_t)nl, cudaMemcpyDeviceToHost));
+    const NutdbNodeExt* hp = (const NutdbNodeExt*)ctx->hExt.p;
+    ctx->ext.assign(hp, hp + nl);
+    std::sort(ctx->ext.begin(), ctx->ext.end(), [](const NutdbNodeExt& x, const NutdbNodeExt& y) { return x.index < y.index; });
+    out->n_ext = nl;
+    out->ext = ctx->ext.data();
   }
   cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
@@ -1887,7 +1907,7 @@ int nutdb_gpu_batch_hash(const NutdbBatch* batch, uint64_t* out) {
     k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.tok_end, batch->n_tok, 3, acc);
     k_hash<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.tok_kw, batch->n_tok, 4, acc);
   }
-  if (batch->n_node) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.node, batch->n_node * (sizeof(NutdbCNode) / 4), 5, acc);
+  if (batch->n_node) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.node, batch->n_node, 5, acc);
   if (batch->n_err) k_hash<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)v.err, batch->n_err * (sizeof(NutdbError) / 4), 6, acc);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->hSmall.p, acc, 8, cudaMemcpyDeviceToHost, st));

@@ -13,7 +13,7 @@ from . import build as _build
 F_NO_TOKENS, F_DEVICE_INPUT, F_NO_HOST_COPY, F_ALL_TOKENS = 1, 2, 4, 8
 
 NODE_DT = np.dtype([("kind", "u1"), ("sub", "u1"), ("aux", "<u2"), ("parent", "<u4"), ("a", "<u4"), ("b", "<u4")])
-CNODE_DT = np.dtype([("kind", "u1"), ("sub", "u1"), ("aux", "<u2"), ("x", "<u4")])   # the wire form (NutdbCNode)
+PNODE_DT = np.dtype("<u4")   # the wire form of a node: one 32-bit word (NUTDB_PN_* in nutdb_gpu.h); kind = word & 127
 STMT_DT = np.dtype([("status", "<u4"), ("tok_begin", "<u4"), ("tok_count", "<u4"), ("node_begin", "<u4"),
                     ("node_count", "<u4"), ("tok_used", "<u4")])
 ERR_DT = np.dtype([("stmt", "<u4"), ("cls", "<u2"), ("code", "<u2"), ("line", "<u4"), ("col", "<u4"),
@@ -24,7 +24,7 @@ class NutdbBatch(C.Structure):
     _fields_ = [("n_stmt", C.c_uint64), ("n_tok", C.c_uint64), ("n_node", C.c_uint64), ("n_err", C.c_uint64),
                 ("stmt", C.c_void_p), ("tok_type", C.c_void_p), ("tok_start", C.c_void_p), ("tok_end", C.c_void_p),
                 ("tok_kw", C.c_void_p), ("node", C.c_void_p), ("err", C.c_void_p), ("impl", C.c_void_p),
-                ("cnode", C.c_void_p), ("n_long", C.c_uint64), ("long_idx", C.c_void_p), ("long_len", C.c_void_p)]
+                ("pnode", C.c_void_p), ("n_ext", C.c_uint64), ("ext", C.c_void_p)]
 
 
 class NutdbMShard(C.Structure):
@@ -136,7 +136,7 @@ class Batch:
         g = (lambda a: a.copy()) if copy else (lambda a: a)
         self.n_stmt, self.n_tok, self.n_node, self.n_err = raw.n_stmt, raw.n_tok, raw.n_node, raw.n_err
         self.stmt = g(_view(raw.stmt, raw.n_stmt, STMT_DT))
-        self.cnode = g(_view(raw.cnode, raw.n_node, CNODE_DT))   # what crossed PCIe: 8 bytes per node
+        self.pnode = g(_view(raw.pnode, raw.n_node, PNODE_DT))   # what crossed PCIe: 4 bytes per node
         # the expanded records (spans, child counts, parent links) are host arithmetic on top of them: eager for a
         # copied batch (the context's buffers are still this batch's), on first use for a view (streaming callers
         # that only want the wire form never pay for it)
@@ -150,8 +150,8 @@ class Batch:
         self.tok_end = g(_view(raw.tok_end, raw.n_tok, np.uint32))
 
     def _expand(self):
-        node = np.zeros(len(self.cnode), NODE_DT)
-        if len(self.cnode):
+        node = np.zeros(len(self.pnode), NODE_DT)
+        if len(self.pnode):
             rc = lib().nutdb_batch_expand_nodes(C.byref(self.raw), node.ctypes.data)
             if rc != 0:
                 raise NutdbGpuError(f"nutdb_batch_expand_nodes failed ({rc})")
@@ -190,7 +190,7 @@ def host_hash(batch):
 
     total = np.uint64(0)
     arrays = [np.ascontiguousarray(batch.stmt).view(np.uint32), batch.tok_type, batch.tok_start, batch.tok_end,
-              batch.tok_kw, np.ascontiguousarray(batch.cnode).view(np.uint32), np.ascontiguousarray(batch.err).view(np.uint32)]
+              batch.tok_kw, np.ascontiguousarray(batch.pnode).view(np.uint32), np.ascontiguousarray(batch.err).view(np.uint32)]
     with np.errstate(over="ignore"):
         for a, w in enumerate(arrays):
             w = np.asarray(w).reshape(-1)

@@ -342,11 +342,11 @@ def _collect(devices, text, offs, flags, chunk_bytes, workers=2):
         if c.on_device:   # gathered into device-0 memory: read it back through the library's CUDA runtime
             r = c.raw
             got[c.first_stmt] = dict(stmt=gpu.copy_to_host(r.stmt, r.n_stmt, gpu.STMT_DT),
-                                     cnode=gpu.copy_to_host(r.cnode, r.n_node, gpu.CNODE_DT),
+                                     pnode=gpu.copy_to_host(r.pnode, r.n_node, gpu.PNODE_DT),
                                      err=gpu.copy_to_host(r.err, r.n_err, gpu.ERR_DT), device=c.device, node=None, tok=None)
         else:
             b = c.batch
-            got[c.first_stmt] = dict(stmt=b.stmt.copy(), cnode=b.cnode.copy(), err=b.err.copy(), device=c.device,
+            got[c.first_stmt] = dict(stmt=b.stmt.copy(), pnode=b.pnode.copy(), err=b.err.copy(), device=c.device,
                                      node=b.node.copy(),
                                      tok=None if flags & gpu.F_NO_TOKENS else
                                      (b.tok_type.copy(), b.tok_start.copy(), b.tok_end.copy(), b.tok_kw.copy()))
@@ -371,7 +371,7 @@ def _check_dispatcher(ctx, devices, gather_flags):
     assert len(stmt) == whole.n_stmt
     for f in ("status", "tok_count", "node_count", "tok_used"):
         assert np.array_equal(stmt[f], whole.stmt[f]), f
-    assert np.array_equal(np.concatenate([got[k]["cnode"] for k in keys]), whole.cnode)
+    assert np.array_equal(np.concatenate([got[k]["pnode"] for k in keys]), whole.pnode)
     err = np.concatenate([got[k]["err"] for k in keys])
     err_stmt = np.concatenate([got[k]["err"]["stmt"].astype(np.int64) + k for k in keys])
     assert np.array_equal(err_stmt, whole.err["stmt"].astype(np.int64))

@@ -95,3 +95,71 @@ def test_library_exports_every_declared_symbol():
     L = gpu.lib()
     for n in names:
         assert hasattr(L, n), n
+
+
+# ---- the 32-bit wire form of a node (NUTDB_PN_* in nutdb_gpu.h): a reference encoder in numpy / Python -------------
+NODE_EXT_DT = np.dtype([("index", "<u4"), ("hdr", "<u4"), ("a", "<u4"), ("b", "<u4")])
+
+
+def encode_wire(stmt, node, gap_max=1021, len_max=510, size_max=0x7FFFE):
+    """NutdbNode records (oracle) -> (wire words, side table), statement by statement, by the rules of the header."""
+    words = np.zeros(len(node), np.uint32)
+    ext = []
+    for s in stmt:
+        if s["status"] != 0:
+            continue
+        b0, cnt = int(s["node_begin"]), int(s["node_count"])
+        pos = 0
+        for j in range(cnt):
+            nd = node[b0 + j]
+            kind, sub, aux, a, b = int(nd["kind"]), int(nd["sub"]), int(nd["aux"]), int(nd["a"]), int(nd["b"])
+            w = kind | ((sub & 31) << 7) | ((aux & 1) << 12)
+            if kind >= 32:
+                size = j - a
+                esc = sub > 31 or aux > 1 or size > size_max
+                w |= (0x7FFFF if esc else size) << 13
+                if esc:
+                    ext.append((b0 + j, kind | sub << 8 | aux << 16, a, 0))
+            elif a == 0 and b == 0:
+                w |= (1023 << 13) | (511 << 23)
+            else:
+                esc = sub > 31 or aux > 1 or a < pos or a - pos > gap_max or b - a > len_max
+                if esc:
+                    w |= (1022 << 13) | (511 << 23)
+                    ext.append((b0 + j, kind | sub << 8 | aux << 16, a, b - a))
+                else:
+                    w |= ((a - pos) << 13) | ((b - a) << 23)
+                pos = b
+            words[b0 + j] = w
+    return words, np.array(ext, NODE_EXT_DT) if ext else np.zeros(0, NODE_EXT_DT)
+
+
+def expand_wire(stmt, words, ext):
+    keep = [np.ascontiguousarray(stmt), np.ascontiguousarray(words), np.ascontiguousarray(ext)]
+    raw = gpu.NutdbBatch()
+    raw.n_stmt, raw.n_node = len(stmt), len(words)
+    raw.stmt, raw.pnode = keep[0].ctypes.data, keep[1].ctypes.data if len(words) else None
+    raw.n_ext, raw.ext = len(ext), keep[2].ctypes.data if len(ext) else None
+    out = np.zeros(len(words), gpu.NODE_DT)
+    rc = gpu.lib().nutdb_batch_expand_nodes(C.byref(raw), out.ctypes.data)
+    return rc, out
+
+
+def test_wire_nodes_expand_to_the_oracle_records():
+    """nutdb_batch_expand_nodes (what a host does with the 4-byte nodes that cross PCIe) reproduces the oracle's
+    NutdbNode records from their wire form -- with the real field limits and with tiny ones that push most nodes
+    through the side table."""
+    long_lit = "select '" + "x" * 700 + "', a /* " + "c" * 3000 + " */ , 'y', " + ", ".join("f(%d)" % i for i in range(50))
+    stmts = W.corpus_statements() + fuzz.EXTRA_SEEDS + [long_lit, "select 1d", "", "select a.b, t.* from t"] + \
+        fuzz.fuzz_statements(W.corpus_statements(), 1500, seed=12, max_mut=3)
+    text, offs = P.make_batch(stmts)
+    b = O.parse_batch(text, offs)
+    for limits in ((1021, 510, 0x7FFFE), (3, 2, 4), (0, 0, 0)):
+        words, ext = encode_wire(b.stmt, b.node, *limits)
+        rc, out = expand_wire(b.stmt, words, ext)
+        assert rc == 0
+        assert np.array_equal(out, b.node), limits
+    assert len(encode_wire(b.stmt, b.node)[1]) >= 2          # the long literal and the token behind the long comment
+    words, ext = encode_wire(b.stmt, b.node, 3, 2, 4)
+    rc, _ = expand_wire(b.stmt, words, ext[:-1])             # an escape without its entry is refused, not guessed
+    assert rc != 0
