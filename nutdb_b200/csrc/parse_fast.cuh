@@ -194,6 +194,46 @@ struct FastParser {
     return true;
   }
 
+  // ---- constant folding (simplify.rs), wide pass only: the narrow pass declines whatever would fold ----
+  // literal == literal (Literal: PartialEq): 0 / 1, or 2 = not decided here (floats, escaped strings: the automaton)
+  NUTDB_HD uint32_t lit_equal_simple(const CNode& x, const CNode& y) {
+    if (x.kind != y.kind) return 0u;
+    if (x.kind == NUTDB_NK_LIT_NULL) return 1u;
+    if (x.kind == NUTDB_NK_LIT_BOOL) return x.sub == y.sub ? 1u : 0u;
+    if (x.x == NUTDB_CN_NOTOK || y.x == NUTDB_CN_NOTOK) return 2u;
+    const uint32_t xa = tok.start(x.x), xb = tok.end(x.x), ya = tok.start(y.x), yb = tok.end(y.x);
+    if (x.kind == NUTDB_NK_LIT_INT) {  // sign + magnitude (at most 38 / 32 digits: int_ok let them in)
+      if ((x.sub & 1) != (y.sub & 1)) return 0u;
+      u128_t v[2] = {0, 0};
+      for (int k = 0; k < 2; k++) {
+        const bool hex = ((k ? y.aux : x.aux) & 1) != 0;
+        const uint32_t e = k ? yb : xb;
+        for (uint32_t p = k ? ya : xa; p < e; p++) {
+          const uint8_t ch = text.byte(p);
+          const uint32_t d = ch <= '9' ? (uint32_t)(ch - '0') : (uint32_t)((ch | 0x20) - 'a' + 10);
+          v[k] = v[k] * (hex ? 16u : 10u) + d;
+        }
+      }
+      return v[0] == v[1] ? 1u : 0u;
+    }
+    if (x.kind == NUTDB_NK_LIT_STR && x.sub == 0 && y.sub == 0) {  // raw strings: the bytes
+      if (xb - xa != yb - ya) return 0u;
+      for (uint32_t i = 0; i < xb - xa; i++)
+        if (text.byte(xa + i) != text.byte(ya + i)) return 0u;
+      return 1u;
+    }
+    return 2u;
+  }
+  // removes leaf node i, sliding [i + 1, n) down by one and re-basing the subtree starts stored in them
+  NUTDB_HD void remove_leaf(uint32_t i, uint32_t& n) {
+    for (uint32_t j = i + 1; j < n; j++) {
+      CNode x = nd.get(j);
+      if (x.kind >= NUTDB_NK_FIRST_INTERIOR) x.x -= 1;
+      nd.set(j - 1, x);
+    }
+    n -= 1;
+  }
+
   // parse_stmt (mod.rs:128-180).  true: res describes a successful parse with node_count nodes emitted.
   NUTDB_HD bool try_parse(ParseResult& res) {
     uint32_t p = tok.pair_at(0);
@@ -247,10 +287,48 @@ struct FastParser {
           if (type == E_OP) {
             // BinaryOp{op, left, right}; refuse whatever simplify.rs would fold
             const uint32_t bop = (top.x >> X_OP) & 63u, lkind = (top.x >> X_LKIND) & 255u;
-            if (bop == 9 || bop == 10) {  // simplified_eq / simplified_neq
-              if (is_literal(lkind) && is_literal(cur_kind)) return false;
-            } else if (bop >= 11 && bop <= 13) {  // simplified_and / or / xor
-              if (lkind == NUTDB_NK_LIT_BOOL || cur_kind == NUTDB_NK_LIT_BOOL) return false;
+            if (bop == 9 || bop == 10) {  // simplified_eq / simplified_neq (simplify.rs): literal = literal folds
+              if (is_literal(lkind) && is_literal(cur_kind)) {
+                if (!WIDE || n < 2u || cur_start != n - 1u || top.y != n - 2u) return false;
+                const uint32_t eq = lit_equal_simple(nd.get(n - 2u), nd.get(n - 1u));
+                if (eq > 1u) return false;
+                sp--;
+                n -= 2u;
+                cur_start = n;
+                cur_kind = NUTDB_NK_LIT_BOOL;
+                FAST_EMIT(NUTDB_NK_LIT_BOOL, ((bop == 9) == (eq == 1u)) ? 1 : 0, 0, NUTDB_CN_NOTOK);
+                continue;
+              }
+            } else if (bop >= 11 && bop <= 13) {  // simplified_and / or / xor: a boolean literal operand folds
+              if (lkind == NUTDB_NK_LIT_BOOL || cur_kind == NUTDB_NK_LIT_BOOL) {
+                if (!WIDE || n > cap) return false;
+                sp--;
+                const uint32_t li = top.y;  // the left operand's first node; the right operand is [cur_start, n)
+                if (lkind == NUTDB_NK_LIT_BOOL) {  // (the left operand is that one leaf: cur_start == li + 1)
+                  const bool b = nd.get(li).sub != 0;
+                  if (bop == 11 ? !b : (bop == 12 ? b : false)) {  // false AND x = false, true OR x = true
+                    n = li + 1u;
+                    cur_kind = NUTDB_NK_LIT_BOOL;
+                  } else {  // the right operand alone; true XOR x = NOT x
+                    remove_leaf(li, n);
+                    if (bop == 13 && b) FAST_EMIT(NUTDB_NK_UNARY, 1, 0, li);
+                    cur_kind = nd.get(n - 1u).kind;
+                  }
+                } else {  // the right operand is the boolean leaf n - 1
+                  const bool b = nd.get(n - 1u).sub != 0;
+                  if (bop == 11 ? !b : (bop == 12 ? b : false)) {  // x AND false = false, x OR true = true
+                    n = li;
+                    FAST_EMIT(NUTDB_NK_LIT_BOOL, b ? 1 : 0, 0, NUTDB_CN_NOTOK);
+                    cur_kind = NUTDB_NK_LIT_BOOL;
+                  } else {  // the left operand alone; x XOR true = NOT x
+                    n -= 1u;
+                    if (bop == 13 && b) FAST_EMIT(NUTDB_NK_UNARY, 1, 0, li);
+                    cur_kind = nd.get(n - 1u).kind;
+                  }
+                }
+                cur_start = li;
+                continue;
+              }
             }
             sp--;
             cur_start = top.y;
@@ -258,8 +336,15 @@ struct FastParser {
             FAST_EMIT(NUTDB_NK_BINARY, bop, 0, cur_start);
           } else if (type >= E_PAREN) {  // a bracket: the terminator belongs to it
             break;
-          } else if (type == E_NOT) {  // simplified_not (simplify.rs): a boolean literal would be flipped
-            if (cur_kind == NUTDB_NK_LIT_BOOL) return false;
+          } else if (type == E_NOT) {  // simplified_not (simplify.rs): a boolean literal is flipped
+            if (cur_kind == NUTDB_NK_LIT_BOOL) {
+              if (!WIDE || n > cap || n == 0u) return false;
+              CNode o = nd.get(n - 1u);
+              o.sub = o.sub ? 0 : 1;
+              nd.set(n - 1u, o);
+              sp--;
+              continue;
+            }
             sp--;
             cur_kind = NUTDB_NK_UNARY;
             FAST_EMIT(NUTDB_NK_UNARY, 1, 0, cur_start);
@@ -304,7 +389,15 @@ struct FastParser {
             } else if (kw1 != KW_NULL) {
               return false;
             }
-            if (is_literal(cur_kind)) return false;
+            if (is_literal(cur_kind)) {  // simplified_is_null / _is_not_null: a literal operand folds
+              if (!WIDE || cur_start != n - 1u) return false;
+              const bool isnull = cur_kind == NUTDB_NK_LIT_NULL;
+              n -= 1u;
+              cur_kind = NUTDB_NK_LIT_BOOL;
+              FAST_EMIT(NUTDB_NK_LIT_BOOL, ((sub == 2) == isnull) ? 1 : 0, 0, NUTDB_CN_NOTOK);
+              t += used;
+              continue;
+            }
             cur_kind = NUTDB_NK_UNARY;
             FAST_EMIT(NUTDB_NK_UNARY, sub, 0, cur_start);
             t += used;

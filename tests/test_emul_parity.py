@@ -329,3 +329,91 @@ def test_sequential_splitter_reference():
     assert E.split(b"select 1;\n\n\t ").tolist() == [0, 9]
     text, offs = W.generate(2, 64 << 10)
     assert np.array_equal(E.split(text[:int(offs[-1])])[1:], offs[1:] - 1)
+
+
+# ---- the WIDE table-driven pass: arrays, maps, index access, prefix ~, IF, parenthesised subqueries, deep nesting,
+# ---- constant folding (simplify.rs) -------------------------------------------------------------------------------
+WIDE = [b"select [1, 2, x]", b"select {1: 2, 'a': b}", b"select a[1]", b"select a[1][2] + b[c[d]]", b"select ~x, ~~x, ~x + 1, not ~x",
+        b"select if a then b else c end", b"select if a then if b then 1 else 2 end else 3 end from t",
+        b"select (select 1)", b"select (select a from t where b = (select max(c) from u)) as q, 2 from v",
+        b"select x in (select y from t)", b"select a from t where x in (select y from t limit 3) and z",
+        b"select a from t join u on a = (select 1) where b", b"insert into t values ((select 1), 2)",
+        b"select ((select 1))", b"select (select 1, 2) + 3", b"select not x[1]", b"select [1,2][0]", b"select {1:2}[1]",
+        b"select (select distinct a from t)", b"select (select a from t order by a desc limit 1, 2 with ties)",
+        b"select case when a then [1] end", b"select a from t where a between [1][0] and {1:2}[1]",
+        b"select (select (select (select x)))", b"select [1 = 1]", b"select [true and x]", b"select if true then 1 else 2 end",
+        b"SELECT * FROM table WHERE 1 = 1", b"select 1 != 'a', 1 is null, null is null or col is null, not true, random() xor true",
+        b"select true and false or false and true, 0x10 = 16, -1 = - 1, 'a' = 'a', 'a' = 'b', 1 = 01 from t"]
+WIDE_AUTOMATON = [b"select [", b"select []", b"select {}", b"select {1}", b"select {1:2,}", b"select a[", b"select a[1,2]",
+                  b"select if a then b end", b"select (select 1", b"select (select 1))", b"select (select 1) union select 2",
+                  b"select -x[1]", b"select - 1[1]", b"select f(a)[1](2)", b"select (with a as (select 1) select 2)",
+                  b"select 1.0 = 1.00, 'a' = \"a\", '\\x41' = 'A'", b"select f(select 1)", b"select exists (select 1)"]
+DEEP = [b"select " + b"[" * 300 + b"1" + b"]" * 300, b"select " + b"(select " * 200 + b"1" + b")" * 200, b"select " + b"~" * 300 + b"x",
+        b"select " + b"{1:" * 200 + b"x" + b"}" * 200, b"select " + b"a[" * 250 + b"x" + b"]" * 250,
+        b"select " + b"IF a THEN " * 120 + b"x" + b" ELSE 0 END" * 120, b"select " + b"(" * 300 + b"1" + b")" * 300,
+        b"select " + b"f(" * 300 + b"x" + b")" * 300, b"select " + b"not " * 400 + b"x",
+        b"select " + b"CASE WHEN a THEN " * 150 + b"1" + b" END" * 150, b"select a" + b" + b * c" * 300,
+        b"select a" + b" or b and c = d" * 200 + b" from t where " + b"x between 1 and 2 and " * 100 + b"y"]
+
+
+def test_wide_pass_constructs_and_depth():
+    E.fast_hits()
+    got = check(WIDE + DEEP)
+    wide = E.wide_hits()
+    assert E.fast_hits() == len(WIDE) + len(DEEP) and (got.stmt["status"] == 0).all()
+    assert wide >= len(WIDE) + len(DEEP) - 3  # (the flat operator chains of DEEP fit the narrow pass)
+    check(WIDE_AUTOMATON)
+    text, offs = P.make_batch(WIDE + DEEP)
+    a = E.parse_batch(text, offs)
+    E.set_fast(False)
+    try:
+        b = E.parse_batch(text, offs, stack_cap=1 << 16)
+    finally:
+        E.set_fast(True)
+    assert np.array_equal(a.node, b.node) and np.array_equal(a.stmt, b.stmt)
+
+
+def fold_statements(n_random=1500, seed=5):
+    import itertools
+    import random
+    lits = ["1", "2", "01", "0x1", "0x01", "-1", "- 1", "-0", "0", "99999999999999999999999999999999999999",
+            "340282366920938463463374607431768211455", "'a'", "'b'", "''", "'a''b'", "\"a\"", "'\\x41'", "1.0", "1.00", "-1.5",
+            "true", "false", "null", "x", "f(1)", "(1)", "[1]", "1+1"]
+    bools = ["true", "false", "1 = 1", "1 = 2", "x", "x + 1", "f(x, y)", "(x)", "not x", "x is null", "1 is null",
+             "null is not null", "not true", "a between 1 and 2", "x in (1, 2)", "case when a then 1 end"]
+    stmts = [f"select {a} = {b}, {a} != {b} from t where {a} <> {b}" for a, b in itertools.product(lits, lits)]
+    for a, b in itertools.product(bools, bools):
+        for o in ("and", "or", "xor"):
+            stmts.append(f"select a from t where c > 1 {o} {a} {o} {b} {o} d")
+            stmts.append(f"select f({a} {o} {b}, [{b} {o} {a}]), ({a} {o} {b}) = true")
+    r = random.Random(seed)
+    for _ in range(n_random):
+        parts = [r.choice(bools + lits)]
+        for _ in range(r.randint(2, 9)):
+            o = r.choice(["and", "or", "xor", "=", "!=", "+", "<", "like", "is null", "is not null"])
+            parts.append(o)
+            if not o.startswith("is"):
+                parts.append(r.choice(bools + lits))
+        stmts.append("select " + " ".join(parts) + " from t")
+    return stmts
+
+
+def test_wide_pass_constant_folding():
+    """simplified_eq / _neq / _and / _or / _xor / _not / _is_null (simplify.rs) in the wide pass: the same nodes as the
+    oracle for every pair of literal kinds and every boolean operand shape."""
+    E.fast_hits()
+    check(fold_statements())
+    assert E.wide_hits() > 1000
+
+
+@pytest.mark.parametrize("seed", [91, 92])
+def test_mutation_fuzz_wide_pass(seed):
+    check(fuzz.fuzz_statements(WIDE + WIDE_AUTOMATON + [d[:400] for d in DEEP], 6000, seed=seed, max_mut=3))
+
+
+def test_config4_is_almost_entirely_table_driven():
+    text, offs = W.generate(4, 1 << 20)
+    E.fast_hits()
+    got = E.parse_batch(text, offs)
+    assert E.fast_hits() >= 0.99 * (len(offs) - 1)
+    assert not P.compare_with_oracle(got, text, offs)

@@ -423,3 +423,23 @@ def test_dispatcher_errors(ctx):
             m.parse_stream(b"select 1", np.array([0, 8], np.uint64), lambda c: 1 // 0)
     finally:
         m.close()
+
+
+def test_wide_table_driven_pass(ctx):
+    """The second table-driven pass (k_parse_wide): arrays, maps, index access, prefix ~, IF, parenthesised subqueries,
+    nesting to any depth (operator stack at the top of the statement's node range) and constant folding -- same
+    records as the oracle, and the automaton only sees what both passes declined."""
+    import test_emul_parity as T
+    got = check(ctx, T.WIDE + T.DEEP)
+    assert (got.stmt["status"] == 0).all()
+    assert ctx.slow_statements() == 0 and ctx.wide_statements() >= len(T.WIDE) + len(T.DEEP) - 3
+    check(ctx, T.WIDE_AUTOMATON)
+    check(ctx, T.fold_statements())
+    assert ctx.wide_statements() > 1000
+    for seed in (93, 94):
+        check(ctx, fuzz.fuzz_statements(T.WIDE + T.WIDE_AUTOMATON + [d[:400] for d in T.DEEP], 20000, seed=seed, max_mut=3))
+    text, offs = W.generate(4, 8 << 20)
+    got = ctx.parse_batch(text, offs)
+    assert ctx.slow_statements() < 0.01 * (len(offs) - 1)
+    bad = P.compare_with_oracle(got, text, offs)
+    assert not bad, "\n".join(bad)
