@@ -88,7 +88,7 @@ enum FastState : uint8_t {
 
 enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT, FA_CASE,
                           // the wide instantiation only (the narrow one declines them):
-                          FA_IF, FA_ARRAY, FA_MAP, FA_BITNOT, FA_SUBQ_END };
+                          FA_PUSH, FA_INTERVAL, FA_SRC_SUBQ, FA_SUBQ_END };
 
 // ---- transition record: two words ----
 // lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28] subreg[29]
@@ -129,12 +129,13 @@ struct FastParser {
   // the scrutinee, 1 after a condition, 2 after a result, 3 after the ELSE expression).
   // Wide only: E_IF (x = type | position << 8: 0 after the condition, 1 after THEN's value, 2 after ELSE's),
   // E_BRACKET = [items], E_MAP = {k: v, ..} (position << 8: 0 after a key, 1 after a value), E_INDEX = left[ (y = start of
-  // left), E_SUBQ = (select ..: x = type | ctx << 8 | join register << 12, y = the outer query's base; the entry below
-  // it holds the outer m0 / m1).
+  // left), E_SUBQ = (select ..: x = type | ctx << 8 | join register << 12 | SUBQ_CALL / SUBQ_SOURCE, y = the outer query's
+  // base; the entry below it holds the outer m0 / m1).
   enum : uint32_t { E_OP = 0, E_NOT = 1, E_BITNOT = 2, E_BTW1 = 3, E_BTW2 = 4, E_PAREN = 5, E_CALL = 6, E_DT = 7, E_CASE = 8,
                     E_IF = 9, E_BRACKET = 10, E_MAP = 11, E_INDEX = 12, E_SUBQ = 13 };
   enum : uint32_t { SPEC_NONE = 0, SPEC_BAIL = 1, SPEC_NOT = 2, SPEC_IS = 3, SPEC_BETWEEN = 4 };  // FastTables::op >> 12
   enum : uint32_t { X_POWER = 4, X_OP = 8, X_LKIND = 14, X_COUNT = 22, X_COUNT_MAX = 1023 };
+  enum : uint32_t { SUBQ_CALL = 1u << 15, SUBQ_SOURCE = 1u << 16 };  // E_SUBQ: what the subquery is part of
   static const uint32_t DEPTH = WIDE ? 0x7FFFFFFFu : (uint32_t)FAST_STACK_DEPTH;  // (wide: bounded by the node range, see try_parse)
 
   NUTDB_HD FastParser(const FastTables* ft, const Tok& tk, const Nodes& nodes, const Text& tx, FastStackEntry* stack,
@@ -591,7 +592,21 @@ struct FastParser {
         const uint32_t ty1 = p1 & 255u;
         if (ty1 == NUTDB_TT_LParen && ty == NUTDB_TT_KeywordOrIdentifier) {
           const uint32_t p2 = tok.pair_at(t + 2);
-          if ((p2 & 255u) == NUTDB_TT_KeywordOrIdentifier && ((p2 >> 8) == KW_SELECT || (p2 >> 8) == KW_WITH)) return false;
+          if ((p2 & 255u) == NUTDB_TT_KeywordOrIdentifier && ((p2 >> 8) == KW_SELECT || (p2 >> 8) == KW_WITH)) {
+            // name(select ..): the subquery is the only argument, its `)` the call's (try_parse_fn_call_args, mod.rs:1538-1556)
+            if (!WIDE || (p2 >> 8) == KW_WITH) return false;
+            FAST_EMIT(NUTDB_NK_FN_NAME, 0, 0, t);
+            FAST_STK(sp) = FastStackEntry{m0, m1};
+            FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | SUBQ_CALL, qbase};
+            sp += 2;
+            qbase = n;
+            m0 = n;
+            m1 = n;
+            ctx = C_SEL_ITEM;
+            t += 3;  // name ( SELECT
+            st = FS_SEL0;
+            continue;
+          }
           const uint32_t m = n;
           FAST_EMIT(NUTDB_NK_FN_NAME, 0, 0, t);
           if ((p2 & 255u) == NUTDB_TT_RParen) {
@@ -725,26 +740,45 @@ struct FastParser {
         res.err_has_pos = false;
         res.err_pos = res.err_a = res.err_b = res.err_c = 0;
         return true;
-      } else if (WIDE && act == FA_IF) {  // IF c THEN a ELSE b END in operand position (mod.rs:1297-1299)
-        FAST_STK(sp) = FastStackEntry{E_IF, n};
+      } else if (WIDE && act == FA_PUSH) {
+        // IF c THEN a ELSE b END (mod.rs:1297-1299), [items] (at least one: must_parse_expr_list), {key : value, ..},
+        // prefix ~ (applies to the next PREFIX expression only, like NOT): the entry comes from the record's kind field
+        FAST_STK(sp) = FastStackEntry{(lo >> 15) & 255u, n};
         sp++;
         t++;
         st = FS_X_OPND;
-      } else if (WIDE && act == FA_ARRAY) {  // [items]: at least one (must_parse_expr_list)
-        FAST_STK(sp) = FastStackEntry{E_BRACKET, n};
-        sp++;
-        t++;
-        st = FS_X_OPND;
-      } else if (WIDE && act == FA_MAP) {  // {key : value, ..}
-        FAST_STK(sp) = FastStackEntry{E_MAP, n};
-        sp++;
-        t++;
-        st = FS_X_OPND;
-      } else if (WIDE && act == FA_BITNOT) {  // prefix ~ applies to the next PREFIX expression only, like NOT
-        FAST_STK(sp) = FastStackEntry{E_BITNOT | (15u << X_POWER), 0u};
-        sp++;
-        t++;
-        st = FS_X_OPND;
+      } else if (WIDE && act == FA_INTERVAL) {  // INTERVAL n unit (must_parse_interval, mod.rs:1489-1503)
+        const uint32_t p1 = tok.pair_at(t + 1);
+        const uint32_t ty1 = p1 & 255u;
+        if (ty1 != NUTDB_TT_IntegerLiteral && ty1 != NUTDB_TT_HexLiteral) return false;
+        if (!int_ok(ty1, p1 >> 8, 1)) return false;
+        const uint32_t p2 = tok.pair_at(t + 2);
+        const uint32_t k2 = (p2 & 255u) == NUTDB_TT_KeywordOrIdentifier ? (p2 >> 8) : 0u;
+        uint32_t unit;
+        if (k2 == KW_SECOND) unit = 0;
+        else if (k2 == KW_MINUTE) unit = 1;
+        else if (k2 == KW_HOUR) unit = 2;
+        else if (k2 == KW_DAY) unit = 3;
+        else if (k2 == KW_MONTH) unit = 4;
+        else if (k2 == KW_YEAR) unit = 5;
+        else return false;
+        cur_start = n;
+        cur_kind = NUTDB_NK_LIT_INTERVAL;
+        FAST_EMIT(NUTDB_NK_LIT_INTERVAL, unit, ty1 == NUTDB_TT_HexLiteral ? 1 : 0, t + 1);
+        t += 3;
+        st = FS_X_OPER;
+      } else if (WIDE && act == FA_SRC_SUBQ) {  // FROM (select ..) [AS alias] (must_parse_query_source, mod.rs:546-569)
+        const uint32_t p1 = tok.pair_at(t + 1);
+        if (!((p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && (p1 >> 8) == KW_SELECT)) return false;
+        FAST_STK(sp) = FastStackEntry{m0, m1};
+        FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | SUBQ_SOURCE, qbase};
+        sp += 2;
+        qbase = n;
+        m0 = n;
+        m1 = n;
+        ctx = C_SEL_ITEM;
+        t += 2;
+        st = FS_SEL0;
       } else if (WIDE && act == FA_SUBQ_END) {  // `)` right after a query body: the subquery's own parenthesis
         if (sp < 2u || (FAST_STK(sp - 1).x & 15u) != E_SUBQ) return false;
         const FastStackEntry f1 = FAST_STK(sp - 1), f0 = FAST_STK(sp - 2);
@@ -758,6 +792,13 @@ struct FastParser {
         m1 = f0.y;
         t++;
         st = FS_X_OPER;  // the outer expression goes on behind it
+        if (f1.x & SUBQ_CALL) {  // name(select ..): FnCall{Others, [subquery]} over the name in front of it
+          cur_start -= 1u;
+          cur_kind = NUTDB_NK_FNCALL;
+          FAST_EMIT(NUTDB_NK_FNCALL, 7, 0, cur_start);
+        } else if (f1.x & SUBQ_SOURCE) {
+          st = FS_SRC2B;  // a query source: [AS alias], then the clauses; an operator behind it goes to the automaton
+        }
       } else {
         return false;
       }

@@ -262,12 +262,14 @@ inline void fast_tables_build(FastTables& F) {
     B.on(st, FC_NULL, R().cur().leaf0(NUTDB_NK_LIT_NULL, 0).adv().to(FS_X_OPER));
     B.on(st, FC_NOT, R().act(FA_NOT));
     B.on(st, FC_CASE, R().act(FA_CASE));
-    B.bail(st, {FC_BADPFX});  // INTERVAL: the automaton
-    // the wide pass only (these actions make the narrow pass decline): IF .. END, [array], {map}, prefix ~
-    B.on(st, FC_IF, R().act(FA_IF));
-    B.on(st, FC_LBRACKET, R().act(FA_ARRAY));
-    B.on(st, FC_LBRACE, R().act(FA_MAP));
-    B.on(st, FC_BITNOT, R().act(FA_BITNOT));
+    // the wide pass only (these actions make the narrow pass decline): IF .. END, [array], {map}, prefix ~ push the
+    // stack entry named in the record's kind field (FastParser::E_IF = 9, E_BRACKET = 10, E_MAP = 11, E_BITNOT = 2
+    // with power 15); INTERVAL n unit
+    B.on(st, FC_IF, R().act(FA_PUSH).emit(FE_NONE, 9));
+    B.on(st, FC_LBRACKET, R().act(FA_PUSH).emit(FE_NONE, 10));
+    B.on(st, FC_LBRACE, R().act(FA_PUSH).emit(FE_NONE, 11));
+    B.on(st, FC_BITNOT, R().act(FA_PUSH).emit(FE_NONE, 2 | (15 << 4)));
+    B.on(st, FC_BADPFX, R().act(FA_INTERVAL));
     B.ident(st, R().act(FA_IDENT));
     B.on(st, FC_MINUS, R().act(FA_NEG));
     B.on(st, FC_PLUS, R().adv().to(FS_X_OPND));  // prefix plus is dropped (mod.rs:1270)
@@ -298,6 +300,7 @@ inline void fast_tables_build(FastTables& F) {
   B.bail(FS_FROM, {FC_JOIN});
   clauses(FS_FROM, 1);
   B.bail(FS_SRC, {FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_CASE});
+  B.on(FS_SRC, FC_LPAREN, R().act(FA_SRC_SUBQ));  // FROM (select ..) [AS alias]: the wide pass
   B.words(FS_SRC, R().look(FL_NOLP).leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));  // no table function
   B.on(FS_SRC, FC_DELIM, R().leaf(NUTDB_NK_IDENT).adv().to(FS_SRC2));
   // `db.table`: the reference keeps the table and DROPS the qualifier (mod.rs:549-562): the node just emitted is withdrawn

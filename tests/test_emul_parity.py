@@ -343,11 +343,22 @@ WIDE = [b"select [1, 2, x]", b"select {1: 2, 'a': b}", b"select a[1]", b"select 
         b"select case when a then [1] end", b"select a from t where a between [1][0] and {1:2}[1]",
         b"select (select (select (select x)))", b"select [1 = 1]", b"select [true and x]", b"select if true then 1 else 2 end",
         b"SELECT * FROM table WHERE 1 = 1", b"select 1 != 'a', 1 is null, null is null or col is null, not true, random() xor true",
-        b"select true and false or false and true, 0x10 = 16, -1 = - 1, 'a' = 'a', 'a' = 'b', 1 = 01 from t"]
+        b"select true and false or false and true, 0x10 = 16, -1 = - 1, 'a' = 'a', 'a' = 'b', 1 = 01 from t",
+        b"select a - interval 10 day, interval 0x3 month + b, interval 1 second, interval 2 minute, interval 3 hour, interval 4 year",
+        b"select a from t where exists (select * from u where u.a = t.a) and not exists (select 1)",
+        b"select exists(select 1), f(select a from t limit 1) + 1, g((select 1), 2)",
+        b"select a from (select b as a from t where c) as q where a > 1 group by a order by a desc",
+        b"select a from (select 1) join u on x = y where z", b"select a from (select (select 1) from (select 2) as i)",
+        b"select count(*) from (select a, b from t where substring(c, 1, 2) in ('13', '31') and d > (select avg(d) from t where d > 0.00)) as s"]
 WIDE_AUTOMATON = [b"select [", b"select []", b"select {}", b"select {1}", b"select {1:2,}", b"select a[", b"select a[1,2]",
                   b"select if a then b end", b"select (select 1", b"select (select 1))", b"select (select 1) union select 2",
                   b"select -x[1]", b"select - 1[1]", b"select f(a)[1](2)", b"select (with a as (select 1) select 2)",
-                  b"select 1.0 = 1.00, 'a' = \"a\", '\\x41' = 'A'", b"select f(select 1)", b"select exists (select 1)"]
+                  b"select 1.0 = 1.00, 'a' = \"a\", '\\x41' = 'A'", b"select interval", b"select interval 1", b"select interval day",
+                  b"select interval 1 week", b"select interval -1 day", b"select interval 99999999999999999999 day",
+                  b"select f(select 1", b"select f(select 1, 2)", b"select f(select 1) (2)", b"select f(with a as (select 1) select 2)",
+                  b"select a from (select 1) + 2", b"select a from (select 1) as", b"select a from (t)", b"select a from (select 1",
+                  b"select a from (select 1)) where b", b"select a from (select 1) union select 2", b"select a from ((select 1))",
+                  b"select a from t join (select 1) as u on x", b"select x not exists (select 1)"]
 DEEP = [b"select " + b"[" * 300 + b"1" + b"]" * 300, b"select " + b"(select " * 200 + b"1" + b")" * 200, b"select " + b"~" * 300 + b"x",
         b"select " + b"{1:" * 200 + b"x" + b"}" * 200, b"select " + b"a[" * 250 + b"x" + b"]" * 250,
         b"select " + b"IF a THEN " * 120 + b"x" + b" ELSE 0 END" * 120, b"select " + b"(" * 300 + b"1" + b")" * 300,
