@@ -93,3 +93,25 @@ def test_quirks():  # SURVEY.md App. B quirks, derived from the cited lines of s
     assert O.parse("SELECT 1 +").error.startswith("Syntax Error: expected token (RawStringLiteral, EscapedSingleQuoted")
     assert O.parse("foo").error == "Syntax Error: fail to parse (cannot recognize statement) at line 1 col 1"
     assert O.parse("1").error == "Syntax Error: fail to parse (statements should start with a keyword) at line 1 col 1"
+
+
+def test_oracle_reproduces_the_committed_outputs_for_the_rust_differential_harness():
+    """tests/golden/oracle_outputs.tsv holds `{:?}` / Display text of the oracle for ~1500 inputs (corpus, App. D,
+    seeds, fold / predicate / join / case / wide lists, fuzz, synthetic samples).  tests/rust_diff (cargo; no toolchain
+    here) compares the REAL reference against the same file; this test keeps the file and the oracle from drifting."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_oracle_outputs as M
+    n = 0
+    with open(os.path.join(here, "golden", "oracle_outputs.tsv"), encoding="utf-8", newline="\n") as f:
+        for ln in f.read().split("\n"):
+            if not ln:
+                continue
+            a, kind, b = ln.split("\t")
+            r = O.parse(M.unesc(a).encode("utf-8"))
+            assert (kind == "OK") == r.ok, a
+            assert M.unesc(b) == (r.debug if r.ok else r.error), a
+            n += 1
+    assert n > 1000
