@@ -9,7 +9,8 @@ hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 names = {"k_lex2_fn": "k_lex2_fn", "k_lex2_walk<0>": "k_lex2_count", "k_lex2_walk<1>": "k_lex2_emit",
-         "k_parse_fast": "k_parse_fast", "k_finalize": "k_finalize"}
+         "k_parse_fast": "k_parse_fast", "k_finalize": "k_finalize", "k_lex4": "k_lex4", "k_parse_wide": "k_parse_wide",
+         "k_parse": "k_parse"}
 res = {}
 for r in rows[2:]:
     k = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("(bool)", "")
