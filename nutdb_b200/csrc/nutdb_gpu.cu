@@ -747,7 +747,18 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
   __syncthreads();
   order[bin_base[key] + rank] = threadIdx.x;
   __syncthreads();
-  s = blockIdx.x * FAST_THREADS + order[threadIdx.x];
+  static_assert(FAST_THREADS == 2 * FAST_BINS, "the two bin arrays hold one packed range per thread");
+  // the token ranges found above travel with the statements (the bin arrays are free now): the second look-up -- a
+  // binary search of the range table plus four window loads -- is only repeated for the rare range that does not pack
+  {
+    uint32_t packed = 0xFFFFFFFFu;
+    if (tb0 != 0xFFFFFFFFu && tb0 >= lo16 && tb0 - lo16 < (1u << 18) && tc0 < (1u << 14)) packed = ((tb0 - lo16) << 14) | tc0;
+    (threadIdx.x < FAST_BINS ? bin_count[threadIdx.x] : bin_base[threadIdx.x - FAST_BINS]) = packed;
+  }
+  __syncthreads();
+  const uint32_t src_thread = order[threadIdx.x];
+  const uint32_t packed_range = src_thread < FAST_BINS ? bin_count[src_thread] : bin_base[src_thread - FAST_BINS];
+  s = blockIdx.x * FAST_THREADS + src_thread;
   if (s >= nstmt) return;
   const uint32_t o = off32[s], len = off32[s + 1] - o;
   if (len == 0) {
@@ -763,7 +774,12 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
     return;
   }
   uint32_t tb, tc;
-  stoks.range(s, o, o + len, tb, tc);
+  if (packed_range != 0xFFFFFFFFu) {
+    tb = lo16 + (packed_range >> 14);
+    tc = packed_range & 0x3FFFu;
+  } else {
+    stoks.range(s, o, o + len, tb, tc);
+  }
   if (lex_only) {
     NutdbStmt S;
     S.status = NUTDB_ST_OK;
