@@ -16,13 +16,17 @@
 #pragma once
 #include "lex3_core.cuh"
 
+#ifndef L3_WORKERS
 #define L3_WORKERS 256                    // worker threads: one 32-byte window each
+#endif
 #define L3_THREADS (L3_WORKERS + 32)      // + one helper warp that runs the two look-back scans beside them
 #define L3_WARPS (L3_WORKERS / 32)
 #define L3_WIN L3_WORKERS                 // windows per tile
 #define L3_TILE (L3_WIN * 32)             // bytes per tile
 #define L3_HALO 32
+#ifndef L3_RCAP
 #define L3_RCAP 2560                      // token records staged per round (a tile holds ~2000 on query logs)
+#endif
 #ifndef L3_MINBLOCKS
 #define L3_MINBLOCKS 3
 #endif
