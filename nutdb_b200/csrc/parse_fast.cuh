@@ -42,6 +42,9 @@
 #pragma once
 #include "parse_core.cuh"
 
+#ifndef NUTDB_WIDE_LITE
+#define NUTDB_WIDE_LITE 0   // experiment switch: 1 compiles the set operations / Enum out of the wide pass
+#endif
 #ifndef FAST_STACK_DEPTH
 #define FAST_STACK_DEPTH 8
 #endif
@@ -61,7 +64,7 @@ enum FastClass : uint8_t {
   FC_WORD, FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_KWBINOP, FC_ISBETWEEN,
   FC_FROM, FC_WHERE, FC_GROUP, FC_BY, FC_HAVING, FC_ORDER, FC_LIMIT, FC_OFFSET, FC_WITH, FC_TIES, FC_AS, FC_DESC,
   FC_INTO, FC_VALUES, FC_TABLE, FC_EXISTS, FC_DEFAULT, FC_COMMENT, FC_PRIMARY, FC_KEY, FC_PARTITION, FC_DISTINCT,
-  FC_SETOP, FC_JOIN, FC_INDEXCON, FC_SELECT, FC_DTYPE,
+  FC_SETOP, FC_JOIN, FC_INDEX, FC_CONSTRAINT, FC_CHECK, FC_SELECT, FC_DTYPE,
   FC_ON, FC_USING, FC_INNER, FC_FULL, FC_LEFT, FC_RIGHT, FC_OUTER, FC_KSEMI, FC_KANTI, FC_CASE,
   FC_COUNT
 };
@@ -69,7 +72,7 @@ static const uint32_t FC_FIRST_WORD = FC_WORD;
 
 // where the expression being parsed sits in its statement; the state after an expression is FS_AFTER + context
 enum FastCtx : uint8_t { C_SEL_ITEM = 0, C_WHERE, C_GROUP_ITEM, C_HAVING, C_ORDER_ITEM, C_INS_VALUE, C_COL_DEFAULT,
-                         C_TBL_PK_ITEM, C_TBL_ORDER_ITEM, C_TBL_PART, C_JOIN_ON, C_COUNT };
+                         C_TBL_PK_ITEM, C_TBL_ORDER_ITEM, C_TBL_PART, C_JOIN_ON, C_IDX_EXPR, C_CON_EXPR, C_COUNT };
 
 enum FastState : uint8_t {
   FS_X_OPND = 0, FS_X_OPER, FS_AFTER, FS_AFTER_END = FS_AFTER + C_COUNT - 1,
@@ -82,13 +85,14 @@ enum FastState : uint8_t {
   FS_INS_ROWN, FS_INS_END,
   FS_CRE0, FS_CRE1, FS_CRE_IF1, FS_CRE_IF2, FS_CRE_NAME, FS_CRE_LP, FS_COL_BEGIN, FS_DT, FS_DT_END, FS_COL_ATTRS,
   FS_COL_COMMENT, FS_COL_SEP, FS_TBL_ATTRS, FS_TBL_KEY, FS_TBL_ORDER_BY, FS_TBL_PART_BY, FS_TBL_COMMENT, FS_CRE_END,
+  FS_WITH0, FS_WITH_AS, FS_WITH_LP, FS_WITH_SEP, FS_IDX_NAME, FS_CON_NAME, FS_CON_CHECK,
   FS_FINAL,
   FS_COUNT
 };
 
-enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_NOT, FA_CASE,
+enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DTYPE, FA_DTEND, FA_ROWEND, FA_ACCEPT, FA_PUSH, FA_CASE,
                           // the wide instantiation only (the narrow one declines them):
-                          FA_PUSH, FA_INTERVAL, FA_SRC_SUBQ, FA_SUBQ_END };
+                          FA_SETOP, FA_INTERVAL, FA_SRC_SUBQ, FA_SUBQ_END };
 
 // ---- transition record: two words ----
 // lo: act[0:4) next[4:11) adv[11] emit[12:15) kind[15:23) sub[23:27) auxbit[27] auxreg[28] subreg[29]
@@ -96,7 +100,7 @@ enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DT
 //     setjr[26] jr[27:30)   (jr = the join type, kept in a register until the JOIN node is emitted: subreg)
 //     popnode[30]           (the node emitted last is withdrawn: the qualifier of `db.table`)
 enum : uint32_t { FE_NONE = 0, FE_LEAF_TOK, FE_LEAF_NOTOK, FE_NODE_M0, FE_NODE_M1, FE_NODE_ZERO };
-enum : uint32_t { FK_NONE = 0, FK_INT_W0, FK_INT_W1, FK_INT_W2, FK_STR };
+enum : uint32_t { FK_NONE = 0, FK_INT_W0, FK_INT_W1, FK_INT_W2, FK_STR, FK_FNCALL };
 enum : uint32_t { FL_NONE = 0, FL_NODOT, FL_NODOT_NOLP, FL_NOLP };
 static const uint32_t FAST_MAX_REC = 160;
 static const uint32_t FAST_HI_UNCOMMON = 0x7FFFFFE0u;  // every hi field except pre / post / setcur
@@ -130,12 +134,13 @@ struct FastParser {
   // Wide only: E_IF (x = type | position << 8: 0 after the condition, 1 after THEN's value, 2 after ELSE's),
   // E_BRACKET = [items], E_MAP = {k: v, ..} (position << 8: 0 after a key, 1 after a value), E_INDEX = left[ (y = start of
   // left), E_SUBQ = (select ..: x = type | ctx << 8 | join register << 12 | SUBQ_CALL / SUBQ_SOURCE, y = the outer query's
-  // base; the entry below it holds the outer m0 / m1).
+  // base; the entry below it holds the outer m0 / m1), E_UNION = a set operation waiting for its right query (x = type |
+  // UnionTypePower << 4 | UnionType << 8, y = first node of its left query).
   enum : uint32_t { E_OP = 0, E_NOT = 1, E_BITNOT = 2, E_BTW1 = 3, E_BTW2 = 4, E_PAREN = 5, E_CALL = 6, E_DT = 7, E_CASE = 8,
-                    E_IF = 9, E_BRACKET = 10, E_MAP = 11, E_INDEX = 12, E_SUBQ = 13 };
+                    E_IF = 9, E_BRACKET = 10, E_MAP = 11, E_INDEX = 12, E_SUBQ = 13, E_UNION = 14 };
   enum : uint32_t { SPEC_NONE = 0, SPEC_BAIL = 1, SPEC_NOT = 2, SPEC_IS = 3, SPEC_BETWEEN = 4 };  // FastTables::op >> 12
   enum : uint32_t { X_POWER = 4, X_OP = 8, X_LKIND = 14, X_COUNT = 22, X_COUNT_MAX = 1023 };
-  enum : uint32_t { SUBQ_CALL = 1u << 15, SUBQ_SOURCE = 1u << 16 };  // E_SUBQ: what the subquery is part of
+  enum : uint32_t { SUBQ_CALL = 1u << 15, SUBQ_SOURCE = 1u << 16, SUBQ_CTE = 1u << 17 };  // E_SUBQ: what the subquery is part of
   static const uint32_t DEPTH = WIDE ? 0x7FFFFFFFu : (uint32_t)FAST_STACK_DEPTH;  // (wide: bounded by the node range, see try_parse)
 
   NUTDB_HD FastParser(const FastTables* ft, const Tok& tk, const Nodes& nodes, const Text& tx, FastStackEntry* stack,
@@ -235,6 +240,53 @@ struct FastParser {
     n -= 1;
   }
 
+  // Enum('a' [= n], ..) from its `Enum` word at token t: the binds as NK_STR [NK_NUM] leaves under one DT_COMPOUND
+  // (must_parse_enum_binds, mod.rs:1799-1813).  (Out-of-line helpers measured 50 % SLOWER: the calls spill the parser state.)
+  NUTDB_HD bool parse_enum(uint32_t& t, uint32_t& n, uint32_t sp, uint32_t cap) {
+    const uint32_t m = n;
+    uint32_t u = t + 2u;
+    for (;;) {
+      if (n + sp + 6u > cap) return false;
+      const uint32_t ps = tok.pair_at(u) & 255u;
+      uint32_t ssub;
+      if (ps == NUTDB_TT_RawStringLiteral) ssub = 0;
+      else if (ps == NUTDB_TT_EscapedSQStringLiteral) ssub = 1;
+      else if (ps == NUTDB_TT_EscapedDQStringLiteral) ssub = 2;
+      else return false;
+      if (ssub && !string_ok(u, ssub == 1 ? '\'' : '"')) return false;
+      CNode c;
+      c.kind = NUTDB_NK_STR;
+      c.sub = (uint8_t)ssub;
+      c.aux = 0;
+      c.x = u;
+      nd.set(n++, c);
+      u++;
+      if ((tok.pair_at(u) & 255u) == NUTDB_TT_Eq) {
+        const uint32_t pi = tok.pair_at(u + 1u);
+        const uint32_t tyi = pi & 255u;
+        if (tyi != NUTDB_TT_IntegerLiteral && tyi != NUTDB_TT_HexLiteral) return false;
+        if (!int_ok(tyi, pi >> 8, 1)) return false;
+        c.kind = NUTDB_NK_NUM;
+        c.sub = 0;
+        c.aux = tyi == NUTDB_TT_HexLiteral ? 1 : 0;
+        c.x = u + 1u;
+        nd.set(n++, c);
+        u += 2u;
+      }
+      if ((tok.pair_at(u) & 255u) != NUTDB_TT_Comma) break;
+      u++;
+    }
+    if ((tok.pair_at(u) & 255u) != NUTDB_TT_RParen) return false;
+    CNode c;
+    c.kind = NUTDB_NK_DT_COMPOUND;
+    c.sub = 1;
+    c.aux = 0;
+    c.x = m;
+    nd.set(n++, c);
+    t = u + 1u;
+    return true;
+  }
+
   // parse_stmt (mod.rs:128-180).  true: res describes a successful parse with node_count nodes emitted.
   NUTDB_HD bool try_parse(ParseResult& res) {
     uint32_t p = tok.pair_at(0);
@@ -245,6 +297,7 @@ struct FastParser {
       if (first == KW_SELECT) st = FS_SEL0;
       else if (first == KW_INSERT) st = FS_INS0;
       else if (first == KW_CREATE) st = FS_CRE0;
+      else if (WIDE && first == KW_WITH) st = FS_WITH0;
       else return false;
     }
     const uint32_t cap = nd.capacity();
@@ -428,9 +481,10 @@ struct FastParser {
           st = FS_X_OPND;  // right operand
           continue;
         }
-        // a terminator.  Inside a bracket opened by this expression it belongs to the bracket; a subquery's frame is
-        // not such a bracket: the expression of the inner query is complete and the grammar table decides
-        if (sp != 0 && !(WIDE && (FAST_STK(sp - 1).x & 15u) == E_SUBQ)) {
+        // a terminator.  Inside a bracket opened by this expression it belongs to the bracket; a subquery's frame or a
+        // pending set operation is not such a bracket: the expression of the inner query is complete and the grammar
+        // table decides
+        if (sp != 0 && !(WIDE && (FAST_STK(sp - 1).x & 15u) >= E_SUBQ)) {
           const FastStackEntry br0 = FAST_STK(sp - 1);
           const uint32_t btype = br0.x & 15u;
           const uint32_t k = ty == NUTDB_TT_KeywordOrIdentifier ? kw : 0u;
@@ -541,6 +595,15 @@ struct FastParser {
         st = FS_AFTER + ctx;  // the expression is complete: the same token decides what follows it
       }
       const uint32_t cls = F->cls[ti];
+      if (WIDE && !NUTDB_WIDE_LITE && st == FS_END_SEL && cls != FC_SETOP) {
+        // the query expression ends here: the set operations still waiting for their right query get it
+        // (must_parse_query_tdop, mod.rs:243-276), innermost first
+        while (sp > 0 && (FAST_STK(sp - 1).x & 15u) == E_UNION) {
+          const FastStackEntry u = FAST_STK(--sp);
+          FAST_EMIT(NUTDB_NK_QUERY_UNION, (u.x >> 8) & 3u, 0, u.y);
+          qbase = u.y;  // (the whole expression now starts where its left-most query does)
+        }
+      }
       const uint32_t ri = F->trans[st][cls];
       const uint32_t lo = F->rec_lo[ri];
       const uint32_t act = lo & 15u;
@@ -556,6 +619,8 @@ struct FastParser {
           const uint32_t check = (hi >> 5) & 7u;
           if (check == FK_STR) {
             if (!string_ok(t, ty == NUTDB_TT_EscapedSQStringLiteral ? '\'' : '"')) return false;
+          } else if (check == FK_FNCALL) {  // the indexer of INDEX name f(..) must be a function call (mod.rs:923-931)
+            if (cur_kind != NUTDB_NK_FNCALL) return false;
           } else if (check != FK_NONE) {
             if (!int_ok(ty, kw, check - FK_INT_W0)) return false;
           }
@@ -667,9 +732,14 @@ struct FastParser {
         sp++;
         t += multi ? 2u : 1u;
         st = FS_X_OPND;
-      } else if (act == FA_NOT) {  // prefix NOT applies to the next PREFIX expression only (mod.rs:1294-1296): `not a = b`
-        if (sp >= DEPTH) return false;  // is `(not a) = b` -- so the entry is completed by whatever token comes next
-        FAST_STK(sp) = FastStackEntry{E_NOT | (15u << X_POWER), 0u};
+      } else if (act == FA_PUSH) {
+        // pushes the stack entry named in the record's kind field and goes on with an operand.  Prefix NOT (both
+        // passes) applies to the next PREFIX expression only (mod.rs:1294-1296): `not a = b` is `(not a) = b` -- so its
+        // entry (power 15) is completed by whatever token comes next; prefix ~ likewise.  Wide pass only: IF c THEN a
+        // ELSE b END (mod.rs:1297-1299), [items] (at least one: must_parse_expr_list), {key : value, ..}.
+        const uint32_t entry = (lo >> 15) & 255u;
+        if (sp >= DEPTH || (!WIDE && (entry & 15u) != E_NOT)) return false;
+        FAST_STK(sp) = FastStackEntry{entry, n};
         sp++;
         t++;
         st = FS_X_OPND;
@@ -692,7 +762,10 @@ struct FastParser {
       } else if (act == FA_DTYPE) {  // must_parse_datatype (mod.rs:1688-1797) without Enum / Tuple / Map
         const uint32_t i = kw - KW_INT8;
         const uint32_t ty1 = tok.pair_at(t + 1) & 255u;
-        if (i == 26 || i == 30 || i == 31) {  // Array / Dictionary / Nullable (inner)
+        if (WIDE && !NUTDB_WIDE_LITE && i == 27) {  // Enum('a' [= n], ..) (must_parse_enum_binds, mod.rs:1799-1813)
+          if (ty1 != NUTDB_TT_LParen || !parse_enum(t, n, sp, cap)) return false;
+          st = sp ? (uint32_t)FS_DT_END : (uint32_t)FS_COL_ATTRS;
+        } else if (i == 26 || i == 30 || i == 31) {  // Array / Dictionary / Nullable (inner)
           if (ty1 != NUTDB_TT_LParen || sp >= DEPTH) return false;
           FAST_STK(sp) = FastStackEntry{E_DT | ((i == 26 ? 0u : (i == 30 ? 4u : 5u)) << 4), n};
           sp++;
@@ -740,13 +813,41 @@ struct FastParser {
         res.err_has_pos = false;
         res.err_pos = res.err_a = res.err_b = res.err_c = 0;
         return true;
-      } else if (WIDE && act == FA_PUSH) {
-        // IF c THEN a ELSE b END (mod.rs:1297-1299), [items] (at least one: must_parse_expr_list), {key : value, ..},
-        // prefix ~ (applies to the next PREFIX expression only, like NOT): the entry comes from the record's kind field
-        FAST_STK(sp) = FastStackEntry{(lo >> 15) & 255u, n};
+      } else if (WIDE && !NUTDB_WIDE_LITE && act == FA_SETOP) {
+        // UNION ALL | UNION DISTINCT | INTERSECT | EXCEPT behind a query body (mod.rs:250-267): precedence climbing over
+        // UnionTypePower (Except < Union < Intersect), left-associative like the expression operators
+        uint32_t power, utype, used = 1;
+        if (kw == KW_UNION) {
+          const uint32_t p1 = tok.pair_at(t + 1);
+          const uint32_t k1 = (p1 & 255u) == NUTDB_TT_KeywordOrIdentifier ? (p1 >> 8) : 0u;
+          if (k1 == KW_ALL) utype = 0;
+          else if (k1 == KW_DISTINCT) utype = 1;
+          else return false;
+          power = U_Union;
+          used = 2;
+        } else if (kw == KW_INTERSECT) {
+          power = U_Intersect;
+          utype = 2;
+        } else {
+          power = U_Except;
+          utype = 3;
+        }
+        uint32_t left = qbase;
+        while (sp > 0 && (FAST_STK(sp - 1).x & 15u) == E_UNION && ((FAST_STK(sp - 1).x >> X_POWER) & 15u) >= power) {
+          const FastStackEntry u = FAST_STK(--sp);
+          FAST_EMIT(NUTDB_NK_QUERY_UNION, (u.x >> 8) & 3u, 0, u.y);
+          left = u.y;
+        }
+        const uint32_t pn = tok.pair_at(t + used);  // the right query: a plain SELECT here (`(` / WITH: the automaton)
+        if (!((pn & 255u) == NUTDB_TT_KeywordOrIdentifier && (pn >> 8) == KW_SELECT)) return false;
+        FAST_STK(sp) = FastStackEntry{E_UNION | (power << X_POWER) | (utype << 8), left};
         sp++;
-        t++;
-        st = FS_X_OPND;
+        qbase = n;
+        m0 = n;
+        m1 = n;
+        ctx = C_SEL_ITEM;
+        t += used + 1u;
+        st = FS_SEL0;
       } else if (WIDE && act == FA_INTERVAL) {  // INTERVAL n unit (must_parse_interval, mod.rs:1489-1503)
         const uint32_t p1 = tok.pair_at(t + 1);
         const uint32_t ty1 = p1 & 255u;
@@ -767,11 +868,12 @@ struct FastParser {
         FAST_EMIT(NUTDB_NK_LIT_INTERVAL, unit, ty1 == NUTDB_TT_HexLiteral ? 1 : 0, t + 1);
         t += 3;
         st = FS_X_OPER;
-      } else if (WIDE && act == FA_SRC_SUBQ) {  // FROM (select ..) [AS alias] (must_parse_query_source, mod.rs:546-569)
+      } else if (WIDE && act == FA_SRC_SUBQ) {  // FROM (select ..) [AS alias] (must_parse_query_source, mod.rs:546-569);
+                                                // WITH name AS (select ..) (must_parse_query_clause_with, mod.rs:327-347)
         const uint32_t p1 = tok.pair_at(t + 1);
         if (!((p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && (p1 >> 8) == KW_SELECT)) return false;
         FAST_STK(sp) = FastStackEntry{m0, m1};
-        FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | SUBQ_SOURCE, qbase};
+        FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | (((lo >> 15) & 255u) ? SUBQ_CTE : SUBQ_SOURCE), qbase};
         sp += 2;
         qbase = n;
         m0 = n;
@@ -798,6 +900,8 @@ struct FastParser {
           FAST_EMIT(NUTDB_NK_FNCALL, 7, 0, cur_start);
         } else if (f1.x & SUBQ_SOURCE) {
           st = FS_SRC2B;  // a query source: [AS alias], then the clauses; an operator behind it goes to the automaton
+        } else if (f1.x & SUBQ_CTE) {
+          st = FS_WITH_SEP;  // a common table expression: `,` and the next one, or SELECT
         }
       } else {
         return false;

@@ -219,7 +219,9 @@ inline uint8_t fast_keyword_class(uint32_t kw) {
     case KW_ANTI: return FC_KANTI;
     case KW_ON: return FC_ON;
     case KW_USING: return FC_USING;
-    case KW_INDEX: case KW_CONSTRAINT: return FC_INDEXCON;
+    case KW_INDEX: return FC_INDEX;
+    case KW_CONSTRAINT: return FC_CONSTRAINT;
+    case KW_CHECK: return FC_CHECK;
     case KW_SELECT: return FC_SELECT;
     default: return FC_WORD;  // an identifier, or a keyword that plays no part in this subset
   }
@@ -260,7 +262,7 @@ inline void fast_tables_build(FastTables& F) {
     B.on(st, FC_TRUE, R().cur().leaf0(NUTDB_NK_LIT_BOOL, 1).adv().to(FS_X_OPER));
     B.on(st, FC_FALSE, R().cur().leaf0(NUTDB_NK_LIT_BOOL, 0).adv().to(FS_X_OPER));
     B.on(st, FC_NULL, R().cur().leaf0(NUTDB_NK_LIT_NULL, 0).adv().to(FS_X_OPER));
-    B.on(st, FC_NOT, R().act(FA_NOT));
+    B.on(st, FC_NOT, R().act(FA_PUSH).emit(FE_NONE, 1 | (15 << 4)));  // FastParser::E_NOT with power 15
     B.on(st, FC_CASE, R().act(FA_CASE));
     // the wide pass only (these actions make the narrow pass decline): IF .. END, [array], {map}, prefix ~ push the
     // stack entry named in the record's kind field (FastParser::E_IF = 9, E_BRACKET = 10, E_MAP = 11, E_BITNOT = 2
@@ -387,9 +389,16 @@ inline void fast_tables_build(FastTables& F) {
     B.on(ties[k], FC_TIES, R().node_m1(NUTDB_NK_LIMIT, k, 1).adv().to(FS_BODY));
   }
   B.otherwise(FS_BODY, R().node0(NUTDB_NK_QUERY_BODY).to(FS_END_SEL));
-  B.bail(FS_END_SEL, {FC_SETOP});  // set operations (mod.rs:250-267)
+  B.on(FS_END_SEL, FC_SETOP, R().act(FA_SETOP));  // set operations (mod.rs:250-267): the wide pass
   B.on(FS_END_SEL, FC_RPAREN, R().act(FA_SUBQ_END));  // the `)` of a parenthesised subquery (wide pass)
   B.otherwise(FS_END_SEL, R().node0(NUTDB_NK_STMT_SELECT).to(FS_FINAL));
+  // WITH name AS (select ..) {, name AS (select ..)} SELECT .. (must_parse_query_clause_with, mod.rs:327-347): wide pass.
+  // The WITH node covers the common table expressions (m1 = where they begin); the select list starts behind it.
+  B.ident(FS_WITH0, R().leaf(NUTDB_NK_NAME).adv().to(FS_WITH_AS));
+  B.on(FS_WITH_AS, FC_AS, R().adv().to(FS_WITH_LP));
+  B.on(FS_WITH_LP, FC_LPAREN, R().act(FA_SRC_SUBQ).emit(FE_NONE, 1));
+  B.on(FS_WITH_SEP, FC_COMMA, R().adv().to(FS_WITH0));
+  B.on(FS_WITH_SEP, FC_SELECT, R().node_m1(NUTDB_NK_WITH).adv().post_m0().to(FS_SEL0));
   // statement-final position (mod.rs:165-172)
   B.on(FS_FINAL, {FC_EOF, FC_SEMI}, R().act(FA_ACCEPT));
 
@@ -418,7 +427,14 @@ inline void fast_tables_build(FastTables& F) {
   B.on(FS_CRE_IF2, FC_EXISTS, R().adv().setaux().to(FS_CRE_NAME));
   for (uint32_t st : {(uint32_t)FS_CRE1, (uint32_t)FS_CRE_NAME}) B.ident(st, FastRec(name).to(FS_CRE_LP));
   B.on(FS_CRE_LP, FC_LPAREN, R().adv().to(FS_COL_BEGIN));
-  B.bail(FS_COL_BEGIN, {FC_INDEXCON});  // INDEX / CONSTRAINT definitions: the automaton
+  // INDEX name indexer(..) / CONSTRAINT name CHECK expr among the columns (mod.rs:913-934)
+  B.on(FS_COL_BEGIN, FC_INDEX, R().adv().pre_m0().to(FS_IDX_NAME));
+  B.on(FS_COL_BEGIN, FC_CONSTRAINT, R().adv().pre_m0().to(FS_CON_NAME));
+  B.ident(FS_IDX_NAME, FastRec(name).ctx(C_IDX_EXPR).to(FS_X_OPND));
+  B.ident(FS_CON_NAME, FastRec(name).to(FS_CON_CHECK));
+  B.on(FS_CON_CHECK, FC_CHECK, R().adv().ctx(C_CON_EXPR).to(FS_X_OPND));
+  B.otherwise(FS_AFTER + C_IDX_EXPR, R().check(FK_FNCALL).node_m0(NUTDB_NK_INDEXDEF).to(FS_COL_SEP));
+  B.otherwise(FS_AFTER + C_CON_EXPR, R().node_m0(NUTDB_NK_CONSTRDEF).to(FS_COL_SEP));
   B.ident(FS_COL_BEGIN, FastRec(name).pre_m0().clr().to(FS_DT));
   B.on(FS_DT, FC_DTYPE, R().act(FA_DTYPE));
   B.otherwise(FS_DT_END, R().act(FA_DTEND));

@@ -349,7 +349,17 @@ WIDE = [b"select [1, 2, x]", b"select {1: 2, 'a': b}", b"select a[1]", b"select 
         b"select exists(select 1), f(select a from t limit 1) + 1, g((select 1), 2)",
         b"select a from (select b as a from t where c) as q where a > 1 group by a order by a desc",
         b"select a from (select 1) join u on x = y where z", b"select a from (select (select 1) from (select 2) as i)",
-        b"select count(*) from (select a, b from t where substring(c, 1, 2) in ('13', '31') and d > (select avg(d) from t where d > 0.00)) as s"]
+        b"select count(*) from (select a, b from t where substring(c, 1, 2) in ('13', '31') and d > (select avg(d) from t where d > 0.00)) as s",
+        b"select 1 union all select 2", b"select a from t union distinct select b from u intersect select c from v except select d",
+        b"select 1 intersect select 2 union all select 3 except select 4",
+        b"select 1 except select 2 except select 3 union all select 4 union distinct select 5",
+        b"select (select 1 union all select 2 intersect select 3), x in (select a from t union all select b from u) from v where y",
+        b"select a from (select 1 union all select 2) as q union all select b from u order by b limit 3",
+        b"create table t (a Enum('x' = 1, 'y', \"z\" = 0x10, 'w'), b Array(Enum('p')), index i minmax(a), constraint c check a < 2, d Int8 default 1) order by (a, b)",
+        b"CREATE TABLE IF NOT EXISTS uk (price UInt32, type Enum('terraced' = 1, 'semi-detached' = 2, 'other' = 0), is_new UInt8, INDEX idx_price minmax(price), CONSTRAINT c_is_new CHECK is_new < 2) ORDER BY (postcode1, postcode2)",
+        b"with c as (select 1) select * from c", b"with a as (select x from t where y), b as (select 1 union all select 2) select a.x, b.* from a join b on a.x = b.y",
+        b"with c_orders as (select c_custkey, count(o_orderkey) as c_count from customer left outer join orders on c_custkey = o_custkey and o_comment not like '%special%' group by c_custkey) select c_count, count(*) as custdist from c_orders where total_revenue = (select max(total_revenue) from revenue0) group by c_count order by custdist desc, c_count desc",
+        b"SELECT 1 = 1 UNION ALL SELECT 'a' = 'b' UNION ALL SELECT 1 != 'a' UNION ALL SELECT 1 IS NULL UNION ALL SELECT null IS NULL OR col IS NULL UNION ALL SELECT NOT true UNION ALL SELECT random() XOR true UNION ALL SELECT true AND false OR false AND true"]
 WIDE_AUTOMATON = [b"select [", b"select []", b"select {}", b"select {1}", b"select {1:2,}", b"select a[", b"select a[1,2]",
                   b"select if a then b end", b"select (select 1", b"select (select 1))", b"select (select 1) union select 2",
                   b"select -x[1]", b"select - 1[1]", b"select f(a)[1](2)", b"select (with a as (select 1) select 2)",
@@ -358,7 +368,17 @@ WIDE_AUTOMATON = [b"select [", b"select []", b"select {}", b"select {1}", b"sele
                   b"select f(select 1", b"select f(select 1, 2)", b"select f(select 1) (2)", b"select f(with a as (select 1) select 2)",
                   b"select a from (select 1) + 2", b"select a from (select 1) as", b"select a from (t)", b"select a from (select 1",
                   b"select a from (select 1)) where b", b"select a from (select 1) union select 2", b"select a from ((select 1))",
-                  b"select a from t join (select 1) as u on x", b"select x not exists (select 1)"]
+                  b"select a from t join (select 1) as u on x", b"select x not exists (select 1)",
+                  b"select 1 intersect select 2 union all select 3 except select 4 intersect select 5 intersect select 6",  # (more nodes than tokens + slack: the retry pass)
+                  b"select 1 union select 2", b"select 1 union all", b"select 1 union all (select 2)", b"select 1 union all with a as (select 1) select 2",
+                  b"select 1 intersect", b"select 1 except all select 2", b"select 1 union all select 2)", b"select (select 1 union all select 2",
+                  b"create table t (a Enum())", b"create table t (a Enum('x' =))", b"create table t (a Enum('x' = 'y'))", b"create table t (a Enum('x',))",
+                  b"create table t (a Enum('x' = 99999999999999999999))", b"create table t (a Enum('\\u{110000}'))", b"create table t (a Enum 'x')",
+                  b"create table t (index i a + 1)", b"create table t (index i)", b"create table t (index)", b"create table t (constraint c a < 2)",
+                  b"create table t (constraint c check)", b"create table t (constraint check check check)", b"create table t (index index index(1))",
+                  b"with", b"with c", b"with c as", b"with c as select 1", b"with c as (select 1)", b"with c as (select 1),", b"with c as (1) select 2",
+                  b"with c as (select 1) + 1 select 2", b"with c as (select 1) insert into t values (1)", b"with c as ((select 1)) select 2",
+                  b"with c as (with d as (select 1) select 2) select 3", b"select * from (with d as (select 1) select 2)"]
 DEEP = [b"select " + b"[" * 300 + b"1" + b"]" * 300, b"select " + b"(select " * 200 + b"1" + b")" * 200, b"select " + b"~" * 300 + b"x",
         b"select " + b"{1:" * 200 + b"x" + b"}" * 200, b"select " + b"a[" * 250 + b"x" + b"]" * 250,
         b"select " + b"IF a THEN " * 120 + b"x" + b" ELSE 0 END" * 120, b"select " + b"(" * 300 + b"1" + b")" * 300,
