@@ -43,6 +43,9 @@ using namespace nlex;
 #endif
 #ifndef FAST_THREADS
 #define FAST_THREADS 512
+#ifndef FAST_MAX_TOKENS
+#define FAST_MAX_TOKENS 64u  // statements with more tokens skip the narrow pass (config 4: narrow 2.2 -> 0.25 ms, wide unchanged)
+#endif
 #endif
 #ifndef FAST_MINBLOCKS
 #define FAST_MINBLOCKS 3
@@ -797,7 +800,9 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
   DText tx{text + o, len};
   npar::ParseResult res;
   npar::FastParser<DTokS, DNodes, DText> f(&FT, tk, nd, tx, fstack + threadIdx.x, FAST_THREADS);
-  if (f.try_parse(res)) {
+  // (a long statement goes straight to the wide pass: its tokens overflow this CTA's staged window, it nests deeper
+  // than eight entries more often than not, and its lane would hold the warp long after the others are done)
+  if (tc <= FAST_MAX_TOKENS && f.try_parse(res)) {
     store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
   } else {
     NutdbStmt S;  // token range for the slow pass
@@ -818,7 +823,9 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
 // so a deep statement needs neither a local-memory stack nor a second run.  Tokens come straight from global memory
 // (these statements are long: a lane walks its own run of the arrays, the L1 serves it).  What it declines too goes to
 // the exact automaton.
-#define WIDE_THREADS 128
+#ifndef WIDE_THREADS
+#define WIDE_THREADS 256  // (a larger CTA sorts more equal statements into a warp: 128 -> 256 measured 6.6 -> 5.9 ms on config 4)
+#endif
 __global__ void __launch_bounds__(WIDE_THREADS) k_parse_wide(
     const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint32_t* __restrict__ slow_list,
     const uint32_t* __restrict__ nslow_dev, const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start,

@@ -659,18 +659,22 @@ struct FastParser {
           const uint32_t p2 = tok.pair_at(t + 2);
           if ((p2 & 255u) == NUTDB_TT_KeywordOrIdentifier && ((p2 >> 8) == KW_SELECT || (p2 >> 8) == KW_WITH)) {
             // name(select ..): the subquery is the only argument, its `)` the call's (try_parse_fn_call_args, mod.rs:1538-1556)
-            if (!WIDE || (p2 >> 8) == KW_WITH) return false;
-            FAST_EMIT(NUTDB_NK_FN_NAME, 0, 0, t);
-            FAST_STK(sp) = FastStackEntry{m0, m1};
-            FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | SUBQ_CALL, qbase};
-            sp += 2;
-            qbase = n;
-            m0 = n;
-            m1 = n;
-            ctx = C_SEL_ITEM;
-            t += 3;  // name ( SELECT
-            st = FS_SEL0;
-            continue;
+            if constexpr (WIDE) {
+              if ((p2 >> 8) == KW_WITH) return false;
+              FAST_EMIT(NUTDB_NK_FN_NAME, 0, 0, t);
+              FAST_STK(sp) = FastStackEntry{m0, m1};
+              FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | SUBQ_CALL, qbase};
+              sp += 2;
+              qbase = n;
+              m0 = n;
+              m1 = n;
+              ctx = C_SEL_ITEM;
+              t += 3;  // name ( SELECT
+              st = FS_SEL0;
+              continue;
+            } else {
+              return false;
+            }
           }
           const uint32_t m = n;
           FAST_EMIT(NUTDB_NK_FN_NAME, 0, 0, t);
@@ -707,17 +711,21 @@ struct FastParser {
         const uint32_t p1 = tok.pair_at(t + 1);
         if ((p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && ((p1 >> 8) == KW_SELECT || (p1 >> 8) == KW_WITH)) {
           // a subquery (must_parse_subquery, mod.rs:206-241): narrow -> the wide pass; WITH -> the automaton
-          if (!WIDE || (p1 >> 8) == KW_WITH) return false;
-          FAST_STK(sp) = FastStackEntry{m0, m1};
-          FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12), qbase};
-          sp += 2;
-          qbase = n;
-          m0 = n;
-          m1 = n;
-          ctx = C_SEL_ITEM;
-          t += 2;  // `(` and SELECT
-          st = FS_SEL0;
-          continue;
+          if constexpr (WIDE) {
+            if ((p1 >> 8) == KW_WITH) return false;
+            FAST_STK(sp) = FastStackEntry{m0, m1};
+            FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12), qbase};
+            sp += 2;
+            qbase = n;
+            m0 = n;
+            m1 = n;
+            ctx = C_SEL_ITEM;
+            t += 2;  // `(` and SELECT
+            st = FS_SEL0;
+            continue;
+          } else {
+            return false;
+          }
         }
         if (sp >= DEPTH) return false;
         FAST_STK(sp) = FastStackEntry{E_PAREN, n};
