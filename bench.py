@@ -263,7 +263,7 @@ def run_log(args, rank, world, local, barrier):
     gather = None
     if args.gather != "none":
         m = gpu.MultiContext(devs, args.e2e_workers)
-        gflags = gpu.F_NO_TOKENS | (gpu.MF_GATHER_DEVICE0 if args.gather == "device0" else 0)
+        gflags = gpu.F_NO_TOKENS | gpu.F_WIRE_STMT | (gpu.MF_GATHER_DEVICE0 if args.gather == "device0" else 0)
         shards = [(d, dt.data_ptr(), do.data_ptr(), ns, gpu.F_DEVICE_INPUT, 0) for c, d, dt, do, ns, nb in staged]
         acc = {}
         lock = threading.Lock()
@@ -271,10 +271,10 @@ def run_log(args, rank, world, local, barrier):
         def consume(ch):   # the consumer's read of a gathered chunk
             r = ch.raw
             with lock:
-                acc["bytes"] = acc.get("bytes", 0) + 24 * r.n_stmt + 4 * r.n_node + 32 * r.n_err
+                acc["bytes"] = acc.get("bytes", 0) + 8 * r.n_stmt + 4 * r.n_node + 32 * r.n_err
                 acc["stmts"] = acc.get("stmts", 0) + r.n_stmt
                 if not ch.on_device and r.n_stmt:
-                    acc["last"] = int(ch.batch.stmt["status"][-1]) + int(ch.batch.pnode[-1] & 127)
+                    acc["last"] = int(ch.batch.wstmt[-1] & 15) + int(ch.batch.pnode[-1] & 127)
 
         for _ in range(2):
             acc.clear()
@@ -356,7 +356,7 @@ def run_log(args, rank, world, local, barrier):
                                     else "GPU 0 memory over NVLink (cudaMemcpyPeerAsync)",
                               "gathered_bytes_per_step": int(g_bytes),
                               "gather_rate_gbs": g_bytes / (g_ms_max * 1e-3) / 1e9,
-                              "api": f"nutdb_gpu_mctx_parse_shards, {args.e2e_workers} contexts per GPU, NUTDB_F_NO_TOKENS; "
+                              "api": f"nutdb_gpu_mctx_parse_shards, {args.e2e_workers} contexts per GPU, NUTDB_F_NO_TOKENS | NUTDB_F_WIRE_STMT; "
                                      "timed by the host clock between device synchronisations (several streams per GPU)"}
         print(json.dumps(line), flush=True)
     for cx in ctxs:
@@ -553,7 +553,10 @@ def main():
     if not args.no_e2e:
         h_text = torch.from_numpy(text).pin_memory()
         h_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
-        flags = gpu.F_NO_TOKENS  # the reference API never exposes tokens (mod.rs:27 returns Statement only)
+        # the reference API never exposes tokens (mod.rs:27 returns Statement only): no token arrays, and the statement
+        # records in their 8-byte wire form (status, node count, tokens pulled)
+        flags = gpu.F_NO_TOKENS
+        eflags = gpu.F_NO_TOKENS | gpu.F_WIRE_STMT
 
         # host-resident batch -> chunked, pipelined through --e2e-workers contexts (nutdb_b200.stream):
         # uploads, kernels and downloads of different chunks overlap
@@ -565,12 +568,12 @@ def main():
         def consume(first, bb):   # the caller's read of the step's result (arrays are in pinned host memory now)
             acc["n_node"] = acc.get("n_node", 0) + int(bb.n_node)
             acc["n_err"] = acc.get("n_err", 0) + int(bb.n_err)
-            acc["last_status"] = int(bb.stmt["status"][-1]) if bb.n_stmt else 0
+            acc["last_status"] = int(bb.wstmt[-1] & 15) if bb.n_stmt else 0
             acc["last_kind"] = int(bb.pnode[-1] & 127) if bb.n_node else 0
 
         def step_host():
             acc.clear()
-            sp.parse(h_text_np, h_offs_np, consume, chunk_bytes=args.e2e_chunk, flags=flags)
+            sp.parse(h_text_np, h_offs_np, consume, chunk_bytes=args.e2e_chunk, flags=eflags)
 
         # untimed: exact T (tokens the reference pulls) and the ok count from one plain host-buffer call
         hb0 = ctx.parse_batch_raw(h_text.data_ptr(), h_offs.data_ptr(), n_stmt, flags, copy=False)
@@ -586,7 +589,7 @@ def main():
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         sp.close()
         h2d = n_in + 8 * (n_stmt + 1)
-        d2h = 24 * n_stmt + 4 * int(acc["n_node"]) + 32 * int(acc["n_err"])   # NutdbStmt, wire nodes (32-bit), NutdbError
+        d2h = 8 * n_stmt + 4 * int(acc["n_node"]) + 32 * int(acc["n_err"])   # wire statement records (64-bit), wire nodes (32-bit), NutdbError
         e2e = {"ms": e2e_ms, "h2d": h2d, "d2h": d2h}
         del h_text, h_offs
 
@@ -645,7 +648,7 @@ def main():
                            "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
                            "ms_per_step": e2e_ms_max, "statements_per_s": tot_stmts / (e2e_ms_max * 1e-3),
                            "api": "nutdb_b200.stream.StreamParser: nutdb_gpu_parse_batch(pinned host text, host offsets, "
-                                  f"NUTDB_F_NO_TOKENS) per chunk on {args.e2e_workers} contexts -> pinned host stmt / wire-node "
+                                  f"NUTDB_F_NO_TOKENS | NUTDB_F_WIRE_STMT) per chunk on {args.e2e_workers} contexts -> pinned host wire-stmt (8 B) / wire-node "
                                   "(32-bit words) / err arrays",
                            "chunk_bytes": args.e2e_chunk}
         if not args.no_cpu_baseline:

@@ -363,6 +363,9 @@ typedef struct {
   const uint32_t *pnode;    /* [n_node] wire nodes (NUTDB_PN_*) */
   uint64_t n_ext;           /* nodes whose fields did not fit the wire word */
   const NutdbNodeExt *ext;  /* [n_ext] sorted by .index; host memory whatever the flags */
+  const uint64_t *wstmt;    /* [n_stmt] with NUTDB_F_WIRE_STMT (then `stmt` is NULL): status | node_count << 4 |
+                               tok_used << 34; node_begin is the running sum of node_count (nodes are dense, in statement
+                               order).  nutdb_batch_expand_stmts() rebuilds NutdbStmt records from them */
 } NutdbBatch;
 
 typedef struct NutdbCtx NutdbCtx;
@@ -373,6 +376,8 @@ typedef struct NutdbCtx NutdbCtx;
                                 [tok_begin, tok_begin + tok_count) of them, but the arrays have gaps between the lexer's ranges) */
 #define NUTDB_F_DEVICE_INPUT 2u /* `sql` and `stmt_off` are device pointers on the ctx's device */
 #define NUTDB_F_NO_HOST_COPY 4u /* leave every output on the device (use nutdb_gpu_batch_device) */
+#define NUTDB_F_WIRE_STMT 16u /* with NUTDB_F_NO_TOKENS: statement records cross PCIe in their 8-byte wire form (NutdbBatch.wstmt)
+                                 instead of the 24-byte NutdbStmt -- the token fields are dropped, node_begin is implied */
 #define NUTDB_F_ALL_TOKENS 8u /* lexer verify mode: token arrays also hold Whitespace / Comment tokens (the full stream of
                                  Tokenizer::next_token, tokenizer/mod.rs:66); statements are not parsed */
 
@@ -398,10 +403,13 @@ void nutdb_gpu_batch_free(NutdbCtx *ctx, NutdbBatch *batch);
 /* Expands the wire nodes of a batch into NutdbNode records (byte spans, child counts, parent links): pure host
  * arithmetic, no parsing.  `out` must hold n_node records.  Returns 0, or NUTDB_E_ARG. */
 int nutdb_batch_expand_nodes(const NutdbBatch *batch, NutdbNode *out);
+/* NutdbStmt records of a batch that carries wire statement records (tok_begin / tok_count are 0).  `out`: n_stmt records. */
+int nutdb_batch_expand_stmts(const NutdbBatch *batch, NutdbStmt *out);
 
 /* Device-side views of the last batch (valid until batch_free); `node` points at the WIRE nodes (32-bit words). */
 typedef struct {
   const void *stmt, *tok_type, *tok_start, *tok_end, *tok_kw, *node, *err;
+  const void *wstmt; /* wire statement records (NUTDB_F_WIRE_STMT), else NULL */
 } NutdbBatchDevice;
 int nutdb_gpu_batch_device(const NutdbBatch *batch, NutdbBatchDevice *out);
 

@@ -135,7 +135,7 @@ void work(Run& r, Worker& w) {
     if (k >= mine.size()) return;
     const NutdbMShard& sh = r.shards[mine[k]];
     NutdbBatch b;
-    const uint32_t pflags = (sh.flags & NUTDB_F_DEVICE_INPUT) | (r.flags & NUTDB_F_NO_TOKENS) | NUTDB_F_NO_HOST_COPY;
+    const uint32_t pflags = (sh.flags & NUTDB_F_DEVICE_INPUT) | (r.flags & (NUTDB_F_NO_TOKENS | NUTDB_F_WIRE_STMT)) | NUTDB_F_NO_HOST_COPY;
     int rc = nutdb_gpu_parse_batch(w.ctx, sh.sql, sh.stmt_off, sh.n_stmt, pflags, &b);
     if (rc != NUTDB_OK) {
       fail(r, rc, std::string("shard ") + std::to_string(mine[k]) + ": " + nutdb_gpu_last_error(w.ctx));
@@ -145,8 +145,9 @@ void work(Run& r, Worker& w) {
     nutdb_gpu_batch_device(&b, &dv);
     // ---- gather: one copy per array from the producing device to the gather point ----
     Slot& s = to_dev0 ? w.dev0 : w.host;
-    const void* src[7] = {dv.stmt, dv.node, dv.err, dv.tok_type, dv.tok_start, dv.tok_end, dv.tok_kw};
-    const size_t bytes[7] = {sizeof(NutdbStmt) * (size_t)b.n_stmt, sizeof(uint32_t) * (size_t)b.n_node,
+    const bool wire_stmt = dv.wstmt != nullptr;  // (NUTDB_F_WIRE_STMT, and every count fitted the 8-byte record)
+    const void* src[7] = {wire_stmt ? dv.wstmt : dv.stmt, dv.node, dv.err, dv.tok_type, dv.tok_start, dv.tok_end, dv.tok_kw};
+    const size_t bytes[7] = {(wire_stmt ? sizeof(uint64_t) : sizeof(NutdbStmt)) * (size_t)b.n_stmt, sizeof(uint32_t) * (size_t)b.n_node,
                              sizeof(NutdbError) * (size_t)b.n_err, want_tokens ? (size_t)b.n_tok : 0,
                              want_tokens ? 4 * (size_t)b.n_tok : 0, want_tokens ? 4 * (size_t)b.n_tok : 0,
                              want_tokens ? (size_t)b.n_tok : 0};
@@ -181,7 +182,8 @@ void work(Run& r, Worker& w) {
     c.batch.n_tok = b.n_tok;
     c.batch.n_node = b.n_node;
     c.batch.n_err = b.n_err;
-    c.batch.stmt = (const NutdbStmt*)(bytes[0] ? s.p[0] : nullptr);
+    if (wire_stmt) c.batch.wstmt = (const uint64_t*)(bytes[0] ? s.p[0] : nullptr);
+    else c.batch.stmt = (const NutdbStmt*)(bytes[0] ? s.p[0] : nullptr);
     c.batch.pnode = (const uint32_t*)(bytes[1] ? s.p[1] : nullptr);
     c.batch.err = (const NutdbError*)(bytes[2] ? s.p[2] : nullptr);
     if (want_tokens && b.n_tok) {

@@ -1077,10 +1077,38 @@ size_t nutdb_fmt_error(const NutdbBatch* batch, uint64_t i, const uint8_t* sql, 
   return deliver(r, buf, cap);
 }
 
-int nutdb_batch_expand_nodes(const NutdbBatch* batch, NutdbNode* out) {
-  if (!batch || !out || (batch->n_node && !batch->pnode) || (batch->n_stmt && !batch->stmt)) return NUTDB_E_ARG;
+int nutdb_batch_expand_stmts(const NutdbBatch* batch, NutdbStmt* out) {
+  if (!batch || !out || (batch->n_stmt && !batch->wstmt && !batch->stmt)) return NUTDB_E_ARG;
+  uint64_t node_begin = 0;
   for (uint64_t i = 0; i < batch->n_stmt; i++) {
-    const NutdbStmt& s = batch->stmt[i];
+    if (!batch->wstmt) {
+      out[i] = batch->stmt[i];
+      continue;
+    }
+    const uint64_t w = batch->wstmt[i];
+    NutdbStmt& s = out[i];
+    s.status = (uint32_t)(w & 15u);
+    s.tok_begin = 0;
+    s.tok_count = 0;
+    s.node_begin = (uint32_t)node_begin;
+    s.node_count = (uint32_t)((w >> 4) & 0x3FFFFFFFu);
+    s.tok_used = (uint32_t)(w >> 34);
+    node_begin += s.node_count;
+  }
+  return NUTDB_OK;
+}
+
+int nutdb_batch_expand_nodes(const NutdbBatch* batch, NutdbNode* out) {
+  if (!batch || !out || (batch->n_node && !batch->pnode) || (batch->n_stmt && !batch->stmt && !batch->wstmt)) return NUTDB_E_ARG;
+  std::vector<NutdbStmt> expanded;
+  const NutdbStmt* stmts = batch->stmt;
+  if (!stmts && batch->n_stmt) {
+    expanded.resize(batch->n_stmt);
+    nutdb_batch_expand_stmts(batch, expanded.data());
+    stmts = expanded.data();
+  }
+  for (uint64_t i = 0; i < batch->n_stmt; i++) {
+    const NutdbStmt& s = stmts[i];
     if (s.status == NUTDB_ST_OK && s.node_count && !expand_stmt_nodes(batch, s.node_begin, s.node_count, out + s.node_begin))
       return NUTDB_E_ARG;
   }

@@ -1019,7 +1019,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
                                                           const uint32_t* __restrict__ punt,
                                                           uint32_t* __restrict__ node_out, uint4* __restrict__ err_out,
                                                           uint32_t* __restrict__ ext_count, uint4* __restrict__ ext_out,
-                                                          uint32_t ext_cap) {
+                                                          uint32_t ext_cap, unsigned long long* __restrict__ wstmt,
+                                                          uint32_t* __restrict__ wstmt_overflow) {
   __shared__ uint2 ws[32];
   __shared__ uint32_t lbegin[FIN_THREADS + 1];
   __shared__ uint32_t ltok[FIN_THREADS];
@@ -1045,6 +1046,12 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
   if (threadIdx.x == 0) lbegin[FIN_THREADS] = total.x;
   if (s < nstmt) {
     stmt[s].node_begin = base.x + excl.x;
+    if (wstmt) {  // the 8-byte wire form of the record (NUTDB_F_WIRE_STMT): status | node count << 4 | tokens pulled << 34
+      const uint32_t nc = S.status == NUTDB_ST_OK ? S.node_count : 0u;
+      if (nc >= (1u << 30) || S.tok_used >= (1u << 30)) atomicOr(wstmt_overflow, 1u);
+      wstmt[s] = (unsigned long long)(S.status & 15u) | ((unsigned long long)(nc & 0x3FFFFFFFu) << 4) |
+                 ((unsigned long long)(S.tok_used & 0x3FFFFFFFu) << 34);
+    }
     if (v.y) {
       uint4 e0, e1;
       if (S.tok_count == 0) {  // empty statement: EmptyQuery, no position
@@ -1160,7 +1167,7 @@ struct NutdbCtx {
   DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, slowList2, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
+      tileS, tilePrefS, nodes, errs, small, slowList, slowList2, wstmt, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry, hSplit;
   float ms[5] = {0, 0, 0, 0, 0};
@@ -1284,7 +1291,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->slowList2, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
+                 &c->small, &c->slowList, &c->slowList2, &c->wstmt, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
                  &c->splitTile, &c->splitPref, &c->splitOff};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
@@ -1653,6 +1660,8 @@ run_again:
   // ---- parser ----
   uint64_t n_node = 0, n_err = 0;
   uint32_t ext_cap = 0;
+  // 8-byte statement records on the wire: only where nobody asked for tokens (the record's token fields are dropped)
+  const bool wire_stmt = (flags & NUTDB_F_WIRE_STMT) && (flags & NUTDB_F_NO_TOKENS) && !lex_only && nstmt > 0;
   const bool native_lex = n > 0 && !lex_only;
   if (nstmt > 0) {
     // compact-node scratch: a disjoint range of tok_count + NODE_SLACK slots per statement (see node_slot)
@@ -1768,13 +1777,15 @@ run_again:
     n_err = hS[9];
     ENSURE_DEV(nodes, 4 * (n_node + 4));
     ENSURE_DEV(errs, 32 * (n_err + 1));
+    if (wire_stmt) ENSURE_DEV(wstmt, 8 * ((size_t)nstmt + 1));
     ext_cap = std::max<uint32_t>(n / 64u, 1024u);  // side table of the nodes that do not fit the 32-bit wire form
     ENSURE_DEV(extNodes, 16 * (size_t)ext_cap);
     LAUNCH("k_finalize", k_finalize<<<stiles, FIN_THREADS, 0, st>>>((NutdbStmt*)ctx->stmt.p, nstmt, (const uint2*)ctx->tilePrefS.p,
                                                (const uint2*)ctx->scratch.p, (const uint2*)ctx->retryNodes.p,
                                                (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                                (const uint32_t*)ctx->puntFlag.p, (uint32_t*)ctx->nodes.p,
-                                               (uint4*)ctx->errs.p, dS + 26, (uint4*)ctx->extNodes.p, ext_cap));
+                                               (uint4*)ctx->errs.p, dS + 26, (uint4*)ctx->extNodes.p, ext_cap,
+                                               wire_stmt ? (unsigned long long*)ctx->wstmt.p : nullptr, dS + 28));
   } else {
     CK(cudaMemcpyAsync(hS, dS, 128, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1810,15 +1821,19 @@ run_again:
   out->n_node = n_node;
   out->n_err = n_err;
   hS[48] = 0;
+  hS[49] = 0;
   if (n_node) CK(cudaMemcpyAsync(hS + 48, dS + 26, 4, cudaMemcpyDeviceToHost, st));  // side-table entries (almost always none)
+  if (wire_stmt) CK(cudaMemcpyAsync(hS + 49, dS + 28, 4, cudaMemcpyDeviceToHost, st));  // a count did not fit the wire record
   if (!(flags & NUTDB_F_NO_HOST_COPY)) {
     ENSURE_HOST(hStmt, sizeof(NutdbStmt) * ((size_t)nstmt + 1));
     ENSURE_HOST(hNode, 4 * (n_node + 4));
     ENSURE_HOST(hErr, 32 * (n_err + 1));
-    if (nstmt) CK(cudaMemcpyAsync(ctx->hStmt.p, ctx->stmt.p, sizeof(NutdbStmt) * (size_t)nstmt, cudaMemcpyDeviceToHost, st));
+    if (nstmt && wire_stmt) CK(cudaMemcpyAsync(ctx->hStmt.p, ctx->wstmt.p, 8 * (size_t)nstmt, cudaMemcpyDeviceToHost, st));
+    else if (nstmt) CK(cudaMemcpyAsync(ctx->hStmt.p, ctx->stmt.p, sizeof(NutdbStmt) * (size_t)nstmt, cudaMemcpyDeviceToHost, st));
     if (n_node) CK(cudaMemcpyAsync(ctx->hNode.p, ctx->nodes.p, 4 * n_node, cudaMemcpyDeviceToHost, st));
     if (n_err) CK(cudaMemcpyAsync(ctx->hErr.p, ctx->errs.p, 32 * n_err, cudaMemcpyDeviceToHost, st));
-    out->stmt = (const NutdbStmt*)ctx->hStmt.p;
+    if (wire_stmt) out->wstmt = (const uint64_t*)ctx->hStmt.p;
+    else out->stmt = (const NutdbStmt*)ctx->hStmt.p;
     out->pnode = (const uint32_t*)ctx->hNode.p;
     out->err = (const NutdbError*)ctx->hErr.p;
     if (!(flags & NUTDB_F_NO_TOKENS)) {
@@ -1841,6 +1856,15 @@ run_again:
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
+  bool wire_ok = wire_stmt;
+  if (wire_stmt && hS[49]) {  // (a statement with 2^30 nodes or tokens: the full records after all)
+    wire_ok = false;
+    if (!(flags & NUTDB_F_NO_HOST_COPY)) {
+      CK(cudaMemcpy(ctx->hStmt.p, ctx->stmt.p, sizeof(NutdbStmt) * (size_t)nstmt, cudaMemcpyDeviceToHost));
+      out->wstmt = nullptr;
+      out->stmt = (const NutdbStmt*)ctx->hStmt.p;
+    }
+  }
   if (n_node && hS[48]) {  // nodes that did not fit the 32-bit wire form: their exact fields, sorted by node index
     if (hS[48] > ext_cap) {
       ctx->err = "node side table overflow";
@@ -1867,6 +1891,7 @@ run_again:
     ctx->kernel_ms.emplace_back(r.name, ms);
   }
   ctx->dev_view.stmt = ctx->stmt.p;
+  ctx->dev_view.wstmt = wire_ok ? ctx->wstmt.p : nullptr;
   ctx->dev_view.tok_type = dTokType;
   ctx->dev_view.tok_start = dTokStart;
   ctx->dev_view.tok_end = dTokEnd;

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import build as _build
 
-F_NO_TOKENS, F_DEVICE_INPUT, F_NO_HOST_COPY, F_ALL_TOKENS = 1, 2, 4, 8
+F_NO_TOKENS, F_DEVICE_INPUT, F_NO_HOST_COPY, F_ALL_TOKENS, F_WIRE_STMT = 1, 2, 4, 8, 16
 
 NODE_DT = np.dtype([("kind", "u1"), ("sub", "u1"), ("aux", "<u2"), ("parent", "<u4"), ("a", "<u4"), ("b", "<u4")])
 PNODE_DT = np.dtype("<u4")   # the wire form of a node: one 32-bit word (NUTDB_PN_* in nutdb_gpu.h); kind = word & 127
@@ -24,7 +24,7 @@ class NutdbBatch(C.Structure):
     _fields_ = [("n_stmt", C.c_uint64), ("n_tok", C.c_uint64), ("n_node", C.c_uint64), ("n_err", C.c_uint64),
                 ("stmt", C.c_void_p), ("tok_type", C.c_void_p), ("tok_start", C.c_void_p), ("tok_end", C.c_void_p),
                 ("tok_kw", C.c_void_p), ("node", C.c_void_p), ("err", C.c_void_p), ("impl", C.c_void_p),
-                ("pnode", C.c_void_p), ("n_ext", C.c_uint64), ("ext", C.c_void_p)]
+                ("pnode", C.c_void_p), ("n_ext", C.c_uint64), ("ext", C.c_void_p), ("wstmt", C.c_void_p)]
 
 
 class NutdbMShard(C.Structure):
@@ -42,7 +42,7 @@ MF_GATHER_DEVICE0, MF_SERIAL_CALLBACKS = 0x100, 0x200
 
 
 class NutdbBatchDevice(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("stmt", "tok_type", "tok_start", "tok_end", "tok_kw", "node", "err")]
+    _fields_ = [(n, C.c_void_p) for n in ("stmt", "tok_type", "tok_start", "tok_end", "tok_kw", "node", "err", "wstmt")]
 
 
 class NutdbGpuError(RuntimeError):
@@ -73,6 +73,8 @@ def lib():
     L.nutdb_gpu_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                         C.POINTER(NutdbBatch)]
     L.nutdb_gpu_batch_free.argtypes = [C.c_void_p, C.POINTER(NutdbBatch)]
+    L.nutdb_batch_expand_stmts.restype = C.c_int
+    L.nutdb_batch_expand_stmts.argtypes = [C.POINTER(NutdbBatch), C.c_void_p]
     L.nutdb_batch_expand_nodes.restype = C.c_int
     L.nutdb_batch_expand_nodes.argtypes = [C.POINTER(NutdbBatch), C.c_void_p]
     L.nutdb_gpu_batch_device.restype = C.c_int
@@ -135,7 +137,12 @@ class Batch:
         self._ctx, self.raw = ctx, raw
         g = (lambda a: a.copy()) if copy else (lambda a: a)
         self.n_stmt, self.n_tok, self.n_node, self.n_err = raw.n_stmt, raw.n_tok, raw.n_node, raw.n_err
-        self.stmt = g(_view(raw.stmt, raw.n_stmt, STMT_DT))
+        # NUTDB_F_WIRE_STMT: 8-byte records crossed PCIe (status | node_count << 4 | tok_used << 34); the NutdbStmt form
+        # is host arithmetic on top of them (the `stmt` property)
+        self.wstmt = g(_view(raw.wstmt, raw.n_stmt, np.uint64)) if raw.wstmt else None
+        self._stmt = g(_view(raw.stmt, raw.n_stmt, STMT_DT)) if (raw.stmt or not raw.wstmt) else None
+        if copy and self._stmt is None:
+            self._stmt = self._expand_stmts()
         self.pnode = g(_view(raw.pnode, raw.n_node, PNODE_DT))   # what crossed PCIe: 4 bytes per node
         # the expanded records (spans, child counts, parent links) are host arithmetic on top of them: eager for a
         # copied batch (the context's buffers are still this batch's), on first use for a view (streaming callers
@@ -148,6 +155,20 @@ class Batch:
         self.tok_kw = g(_view(raw.tok_kw, raw.n_tok, np.uint8))
         self.tok_start = g(_view(raw.tok_start, raw.n_tok, np.uint32))
         self.tok_end = g(_view(raw.tok_end, raw.n_tok, np.uint32))
+
+    def _expand_stmts(self):
+        out = np.zeros(int(self.n_stmt), STMT_DT)
+        if self.n_stmt:
+            rc = lib().nutdb_batch_expand_stmts(C.byref(self.raw), out.ctypes.data)
+            if rc != 0:
+                raise NutdbGpuError(f"nutdb_batch_expand_stmts failed ({rc})")
+        return out
+
+    @property
+    def stmt(self):
+        if self._stmt is None:
+            self._stmt = self._expand_stmts()
+        return self._stmt
 
     def _expand(self):
         node = np.zeros(len(self.pnode), NODE_DT)

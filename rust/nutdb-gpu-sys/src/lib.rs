@@ -29,11 +29,13 @@ pub struct NutdbBatch {
     pub pnode: *const u32,           // wire nodes, one 32-bit word each (PN_*)
     pub n_ext: u64,
     pub ext: *const NutdbNodeExt,    // side table, sorted by .index
+    pub wstmt: *const u64,           // F_WIRE_STMT: status | node_count << 4 | tok_used << 34 (then `stmt` is NULL)
 }
 #[repr(C)]
 pub struct NutdbBatchDevice {
     pub stmt: *const c_void, pub tok_type: *const c_void, pub tok_start: *const c_void, pub tok_end: *const c_void,
     pub tok_kw: *const c_void, pub node: *const c_void, pub err: *const c_void,
+    pub wstmt: *const c_void,
 }
 #[repr(C)]
 pub struct NutdbMShard {
@@ -50,6 +52,7 @@ pub const F_NO_TOKENS: u32 = 1;
 pub const F_DEVICE_INPUT: u32 = 2;
 pub const F_NO_HOST_COPY: u32 = 4;
 pub const F_ALL_TOKENS: u32 = 8;
+pub const F_WIRE_STMT: u32 = 16;
 pub const MF_GATHER_DEVICE0: u32 = 0x100;
 pub const MF_SERIAL_CALLBACKS: u32 = 0x200;
 pub const OK: c_int = 0;
@@ -82,6 +85,7 @@ extern "C" {
     pub fn nutdb_gpu_parse(ctx: *mut NutdbCtx, sql: *const u8, len: u64, out: *mut NutdbBatch) -> c_int;
     pub fn nutdb_gpu_batch_free(ctx: *mut NutdbCtx, batch: *mut NutdbBatch);
     pub fn nutdb_batch_expand_nodes(batch: *const NutdbBatch, out: *mut NutdbNode) -> c_int;
+    pub fn nutdb_batch_expand_stmts(batch: *const NutdbBatch, out: *mut NutdbStmt) -> c_int;
     pub fn nutdb_gpu_batch_device(batch: *const NutdbBatch, out: *mut NutdbBatchDevice) -> c_int;
     pub fn nutdb_gpu_batch_hash(batch: *const NutdbBatch, out: *mut u64) -> c_int;
     pub fn nutdb_gpu_split_statements(ctx: *mut NutdbCtx, sql: *const u8, len: u64, flags: u32, stmt_off: *mut *const u64,

@@ -79,7 +79,21 @@ fn expand(words: &[u32], first_index: u32, ext: &[sys::NutdbNodeExt]) -> Vec<Nod
 /// # Safety
 /// `b` must be a live batch of the library (or a chunk handed to a dispatcher callback) with host-resident arrays.
 pub(super) unsafe fn batch<'a>(b: &sys::NutdbBatch, sqls: &[&'a str]) -> Vec<Result<Statement<'a>, ParseError>> {
-    let stmts = core::slice::from_raw_parts(b.stmt, b.n_stmt as usize);
+    // statement records: the 24-byte form, or the 8-byte wire form (F_WIRE_STMT) expanded here
+    let expanded: Vec<sys::NutdbStmt>;
+    let stmts: &[sys::NutdbStmt] = if !b.stmt.is_null() || b.n_stmt == 0 {
+        if b.n_stmt == 0 { &[] } else { core::slice::from_raw_parts(b.stmt, b.n_stmt as usize) }
+    } else {
+        let w = core::slice::from_raw_parts(b.wstmt, b.n_stmt as usize);
+        let mut node_begin = 0u32;
+        expanded = w.iter().map(|&x| {
+            let s = sys::NutdbStmt { status: (x & 15) as u32, tok_begin: 0, tok_count: 0, node_begin,
+                                     node_count: ((x >> 4) & 0x3FFF_FFFF) as u32, tok_used: (x >> 34) as u32 };
+            node_begin += s.node_count;
+            s
+        }).collect();
+        &expanded
+    };
     let words = if b.n_node > 0 { core::slice::from_raw_parts(b.pnode, b.n_node as usize) } else { &[][..] };
     let errs = if b.n_err > 0 { core::slice::from_raw_parts(b.err, b.n_err as usize) } else { &[][..] };
     let ext = if b.n_ext > 0 { core::slice::from_raw_parts(b.ext, b.n_ext as usize) } else { &[][..] };

@@ -47,7 +47,7 @@ impl Context {
         text.resize(total + 16, 0);
         let mut b: sys::NutdbBatch = unsafe { core::mem::zeroed() };
         let rc = unsafe {
-            sys::nutdb_gpu_parse_batch(self.raw, text.as_ptr(), offs.as_ptr(), sqls.len() as u64, sys::F_NO_TOKENS, &mut b)
+            sys::nutdb_gpu_parse_batch(self.raw, text.as_ptr(), offs.as_ptr(), sqls.len() as u64, sys::F_NO_TOKENS | sys::F_WIRE_STMT, &mut b)
         };
         if rc != sys::OK {
             return Err(GpuError(format!("nutdb_gpu_parse_batch failed ({rc}): {}", self.last_error())));
@@ -126,7 +126,7 @@ impl MultiGpu {
         let n = offs.len() - 1;
         let st = State { text, offs, out: std::sync::Mutex::new((0..n).map(|_| None).collect()) };
         let rc = unsafe {
-            sys::nutdb_gpu_mctx_parse_stream(self.raw, text.as_ptr(), offs.as_ptr(), n as u64, chunk_bytes, sys::F_NO_TOKENS,
+            sys::nutdb_gpu_mctx_parse_stream(self.raw, text.as_ptr(), offs.as_ptr(), n as u64, chunk_bytes, sys::F_NO_TOKENS | sys::F_WIRE_STMT,
                                              Some(on_chunk), &st as *const State as *mut core::ffi::c_void)
         };
         if rc != sys::OK {

@@ -443,3 +443,23 @@ def test_wide_table_driven_pass(ctx):
     assert ctx.slow_statements() < 0.01 * (len(offs) - 1)
     bad = P.compare_with_oracle(got, text, offs)
     assert not bad, "\n".join(bad)
+
+
+def test_wire_statement_records(ctx):
+    """NUTDB_F_WIRE_STMT: 8-byte statement records on the wire; expanded on the host they equal the 24-byte records
+    (token fields aside), directly and through the dispatcher."""
+    from nutdb_b200 import gpu
+    text, offs = W.generate(3, 2 << 20, seed=41)
+    plain = ctx.parse_batch(text, offs, flags=gpu.F_NO_TOKENS)
+    wire = ctx.parse_batch(text, offs, flags=gpu.F_NO_TOKENS | gpu.F_WIRE_STMT)
+    assert wire.wstmt is not None and len(wire.wstmt) == plain.n_stmt
+    for f in ("status", "node_begin", "node_count", "tok_used"):
+        assert np.array_equal(wire.stmt[f], plain.stmt[f]), f
+    assert np.array_equal(wire.node, plain.node) and np.array_equal(wire.err, plain.err)
+    # without NUTDB_F_NO_TOKENS the flag is ignored (the token fields are needed)
+    assert ctx.parse_batch(text, offs, flags=gpu.F_WIRE_STMT).wstmt is None
+    got = _collect((0, 0), text, offs, gpu.F_NO_TOKENS | gpu.F_WIRE_STMT, 512 << 10)
+    keys = sorted(got)
+    assert np.array_equal(np.concatenate([got[k]["stmt"]["status"] for k in keys]), plain.stmt["status"])
+    assert np.array_equal(np.concatenate([got[k]["stmt"]["node_count"] for k in keys]), plain.stmt["node_count"])
+    assert np.array_equal(np.concatenate([got[k]["node"] for k in keys]), plain.node)
