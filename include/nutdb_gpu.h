@@ -374,7 +374,9 @@ typedef struct NutdbCtx NutdbCtx;
 #define NUTDB_F_NO_TOKENS 1u /* the caller does not want the token arrays (the reference never exposes tokens): no host copy, and the
                                 device copies stay in the lexer's segmented layout (statement i's tokens are still
                                 [tok_begin, tok_begin + tok_count) of them, but the arrays have gaps between the lexer's ranges) */
-#define NUTDB_F_DEVICE_INPUT 2u /* `sql` and `stmt_off` are device pointers on the ctx's device */
+#define NUTDB_F_DEVICE_INPUT 2u /* `sql` and `stmt_off` are device pointers on the ctx's device.  No padding is needed behind the last
+                                   statement: the kernels read whole 16-byte pieces only below sql + stmt_off[n] and the ragged
+                                   rest bytewise.  A text pointer that is not 16-byte aligned costs one device-to-device copy */
 #define NUTDB_F_NO_HOST_COPY 4u /* leave every output on the device (use nutdb_gpu_batch_device) */
 #define NUTDB_F_WIRE_STMT 16u /* with NUTDB_F_NO_TOKENS: statement records cross PCIe in their 8-byte wire form (NutdbBatch.wstmt)
                                  instead of the 24-byte NutdbStmt -- the token fields are dropped, node_begin is implied */

@@ -508,7 +508,7 @@ struct DTok {
 // shared memory: `rel` is the statement's first token relative to the staged window; tokens outside the window
 // (a statement lexed into the extra region, or a CTA with more than FAST_TOKCAP tokens) come from global memory.
 #ifndef FAST_TOKCAP
-#define FAST_TOKCAP 14848u
+#define FAST_TOKCAP 14080u
 #endif
 #define FAST_DYN_SMEM (FAST_TOKCAP * 2 + FAST_STACK_DEPTH * FAST_THREADS * 8)
 // k_parse_fast is tuned for FAST_MINBLOCKS resident CTAs per SM: tables + sort arrays + dynamic part + the 1 KB the

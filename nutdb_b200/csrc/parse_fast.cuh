@@ -64,7 +64,7 @@ enum FastClass : uint8_t {
   FC_WORD, FC_TRUE, FC_FALSE, FC_NULL, FC_NOT, FC_IF, FC_BADPFX, FC_KWBINOP, FC_ISBETWEEN,
   FC_FROM, FC_WHERE, FC_GROUP, FC_BY, FC_HAVING, FC_ORDER, FC_LIMIT, FC_OFFSET, FC_WITH, FC_TIES, FC_AS, FC_DESC,
   FC_INTO, FC_VALUES, FC_TABLE, FC_EXISTS, FC_DEFAULT, FC_COMMENT, FC_PRIMARY, FC_KEY, FC_PARTITION, FC_DISTINCT,
-  FC_SETOP, FC_JOIN, FC_INDEX, FC_CONSTRAINT, FC_CHECK, FC_SELECT, FC_DTYPE,
+  FC_SETOP, FC_JOIN, FC_INDEX, FC_CONSTRAINT, FC_CHECK, FC_VIEW, FC_UPDATE, FC_SELECT, FC_DTYPE,
   FC_ON, FC_USING, FC_INNER, FC_FULL, FC_LEFT, FC_RIGHT, FC_OUTER, FC_KSEMI, FC_KANTI, FC_CASE,
   FC_COUNT
 };
@@ -72,7 +72,8 @@ static const uint32_t FC_FIRST_WORD = FC_WORD;
 
 // where the expression being parsed sits in its statement; the state after an expression is FS_AFTER + context
 enum FastCtx : uint8_t { C_SEL_ITEM = 0, C_WHERE, C_GROUP_ITEM, C_HAVING, C_ORDER_ITEM, C_INS_VALUE, C_COL_DEFAULT,
-                         C_TBL_PK_ITEM, C_TBL_ORDER_ITEM, C_TBL_PART, C_JOIN_ON, C_IDX_EXPR, C_CON_EXPR, C_COUNT };
+                         C_TBL_PK_ITEM, C_TBL_ORDER_ITEM, C_TBL_PART, C_JOIN_ON, C_IDX_EXPR, C_CON_EXPR,
+                         C_V_PK_ITEM, C_V_ORDER_ITEM, C_V_PART, C_COUNT };
 
 enum FastState : uint8_t {
   FS_X_OPND = 0, FS_X_OPER, FS_AFTER, FS_AFTER_END = FS_AFTER + C_COUNT - 1,
@@ -86,6 +87,8 @@ enum FastState : uint8_t {
   FS_CRE0, FS_CRE1, FS_CRE_IF1, FS_CRE_IF2, FS_CRE_NAME, FS_CRE_LP, FS_COL_BEGIN, FS_DT, FS_DT_END, FS_COL_ATTRS,
   FS_COL_COMMENT, FS_COL_SEP, FS_TBL_ATTRS, FS_TBL_KEY, FS_TBL_ORDER_BY, FS_TBL_PART_BY, FS_TBL_COMMENT, FS_CRE_END,
   FS_WITH0, FS_WITH_AS, FS_WITH_LP, FS_WITH_SEP, FS_IDX_NAME, FS_CON_NAME, FS_CON_CHECK,
+  FS_CRV1, FS_CRV_IF1, FS_CRV_IF2, FS_CRV_NAME, FS_VIEW_ATTRS, FS_V_UPD, FS_V_STRAT, FS_V_KEY, FS_V_ORDER_BY, FS_V_PART_BY,
+  FS_V_COMMENT,
   FS_FINAL,
   FS_COUNT
 };
@@ -102,7 +105,7 @@ enum FastAct : uint32_t { FA_BAIL = 0, FA_STEP, FA_IDENT, FA_NEG, FA_OPEN, FA_DT
 enum : uint32_t { FE_NONE = 0, FE_LEAF_TOK, FE_LEAF_NOTOK, FE_NODE_M0, FE_NODE_M1, FE_NODE_ZERO };
 enum : uint32_t { FK_NONE = 0, FK_INT_W0, FK_INT_W1, FK_INT_W2, FK_STR, FK_FNCALL };
 enum : uint32_t { FL_NONE = 0, FL_NODOT, FL_NODOT_NOLP, FL_NOLP };
-static const uint32_t FAST_MAX_REC = 160;
+static const uint32_t FAST_MAX_REC = 192;
 static const uint32_t FAST_HI_UNCOMMON = 0x7FFFFFE0u;  // every hi field except pre / post / setcur
 
 // Token-indexed tables take ONE index for both kinds of token: the token type, or 64 + keyword id for a word.
@@ -140,7 +143,7 @@ struct FastParser {
                     E_IF = 9, E_BRACKET = 10, E_MAP = 11, E_INDEX = 12, E_SUBQ = 13, E_UNION = 14 };
   enum : uint32_t { SPEC_NONE = 0, SPEC_BAIL = 1, SPEC_NOT = 2, SPEC_IS = 3, SPEC_BETWEEN = 4 };  // FastTables::op >> 12
   enum : uint32_t { X_POWER = 4, X_OP = 8, X_LKIND = 14, X_COUNT = 22, X_COUNT_MAX = 1023 };
-  enum : uint32_t { SUBQ_CALL = 1u << 15, SUBQ_SOURCE = 1u << 16, SUBQ_CTE = 1u << 17 };  // E_SUBQ: what the subquery is part of
+  enum : uint32_t { SUBQ_CALL = 1u << 15, SUBQ_SOURCE = 1u << 16, SUBQ_CTE = 1u << 17, SUBQ_VIEW = 1u << 18 };  // E_SUBQ: what the subquery is part of
   static const uint32_t DEPTH = WIDE ? 0x7FFFFFFFu : (uint32_t)FAST_STACK_DEPTH;  // (wide: bounded by the node range, see try_parse)
 
   NUTDB_HD FastParser(const FastTables* ft, const Tok& tk, const Nodes& nodes, const Text& tx, FastStackEntry* stack,
@@ -603,6 +606,14 @@ struct FastParser {
           FAST_EMIT(NUTDB_NK_QUERY_UNION, (u.x >> 8) & 3u, 0, u.y);
           qbase = u.y;  // (the whole expression now starts where its left-most query does)
         }
+        // CREATE VIEW .. AS query: the statement ends with the query (no parenthesis): ViewDefinition + CreateStmt
+        if (sp >= 2u && (FAST_STK(sp - 1).x & (15u | SUBQ_VIEW)) == (E_SUBQ | SUBQ_VIEW) && (cls == FC_EOF || cls == FC_SEMI)) {
+          sp -= 2u;
+          qbase = 0u;
+          FAST_EMIT(NUTDB_NK_VIEWDEF, 0, 0, 0u);
+          FAST_EMIT(NUTDB_NK_STMT_CREATE, 0, auxr, 0u);
+          st = FS_FINAL;
+        }
       }
       const uint32_t ri = F->trans[st][cls];
       const uint32_t lo = F->rec_lo[ri];
@@ -881,7 +892,9 @@ struct FastParser {
         const uint32_t p1 = tok.pair_at(t + 1);
         if (!((p1 & 255u) == NUTDB_TT_KeywordOrIdentifier && (p1 >> 8) == KW_SELECT)) return false;
         FAST_STK(sp) = FastStackEntry{m0, m1};
-        FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | (((lo >> 15) & 255u) ? SUBQ_CTE : SUBQ_SOURCE), qbase};
+        const uint32_t what = (lo >> 15) & 255u;  // 0: a query source, 1: a common table expression, 2: the query of CREATE VIEW .. AS
+        if (what == 2u && !(seen & 1u)) return false;  // (AS needs the UPDATE BY first, mod.rs:824-828)
+        FAST_STK(sp + 1) = FastStackEntry{E_SUBQ | (ctx << 8) | (jreg << 12) | (what == 0u ? SUBQ_SOURCE : what == 1u ? SUBQ_CTE : SUBQ_VIEW), qbase};
         sp += 2;
         qbase = n;
         m0 = n;
@@ -890,7 +903,7 @@ struct FastParser {
         t += 2;
         st = FS_SEL0;
       } else if (WIDE && act == FA_SUBQ_END) {  // `)` right after a query body: the subquery's own parenthesis
-        if (sp < 2u || (FAST_STK(sp - 1).x & 15u) != E_SUBQ) return false;
+        if (sp < 2u || (FAST_STK(sp - 1).x & (15u | SUBQ_VIEW)) != E_SUBQ) return false;  // (a view's query has no parenthesis)
         const FastStackEntry f1 = FAST_STK(sp - 1), f0 = FAST_STK(sp - 2);
         sp -= 2;
         cur_start = qbase;

@@ -222,6 +222,8 @@ inline uint8_t fast_keyword_class(uint32_t kw) {
     case KW_INDEX: return FC_INDEX;
     case KW_CONSTRAINT: return FC_CONSTRAINT;
     case KW_CHECK: return FC_CHECK;
+    case KW_VIEW: return FC_VIEW;
+    case KW_UPDATE: return FC_UPDATE;
     case KW_SELECT: return FC_SELECT;
     default: return FC_WORD;  // an identifier, or a keyword that plays no part in this subset
   }
@@ -420,6 +422,31 @@ inline void fast_tables_build(FastTables& F) {
   B.on(FS_INS_ROWN, FC_LPAREN, R().adv().post_m1().to(FS_X_OPND));
   B.otherwise(FS_INS_END, R().node0(NUTDB_NK_STMT_INSERT).to(FS_FINAL));
 
+  // ---- CREATE VIEW [IF NOT EXISTS] name {UPDATE BY strategy | PRIMARY KEY es | ORDER BY es | PARTITION BY e | COMMENT s}
+  //      AS query (must_parse_view_definition, mod.rs:807-911): wide pass (the AS action is its own).  seen bit 1 =
+  //      UPDATE BY (AS needs it), the other bits as for tables ----
+  B.on(FS_CRE0, FC_VIEW, R().adv().to(FS_CRV1));
+  B.on(FS_CRV1, FC_IF, R().adv().to(FS_CRV_IF1));
+  B.on(FS_CRV_IF1, FC_NOT, R().adv().to(FS_CRV_IF2));
+  B.on(FS_CRV_IF2, FC_EXISTS, R().adv().setaux().to(FS_CRV_NAME));
+  for (uint32_t st : {(uint32_t)FS_CRV1, (uint32_t)FS_CRV_NAME}) B.ident(st, R().leaf(NUTDB_NK_NAME).adv().to(FS_VIEW_ATTRS));
+  B.on(FS_VIEW_ATTRS, FC_UPDATE, R().bit(1).adv().to(FS_V_UPD));
+  B.on(FS_VIEW_ATTRS, FC_PRIMARY, R().bit(16).adv().to(FS_V_KEY));
+  B.on(FS_VIEW_ATTRS, FC_ORDER, R().bit(32).adv().to(FS_V_ORDER_BY));
+  B.on(FS_VIEW_ATTRS, FC_PARTITION, R().bit(64).adv().to(FS_V_PART_BY));
+  B.on(FS_VIEW_ATTRS, FC_COMMENT, R().bit(128).adv().to(FS_V_COMMENT));
+  B.on(FS_VIEW_ATTRS, FC_AS, R().act(FA_SRC_SUBQ).emit(FE_NONE, 2));
+  B.on(FS_V_UPD, FC_BY, R().adv().to(FS_V_STRAT));
+  B.ident(FS_V_STRAT, R().leaf(NUTDB_NK_STRATEGY).adv().to(FS_VIEW_ATTRS));
+  B.on(FS_V_KEY, FC_KEY, R().adv().post_m1().ctx(C_V_PK_ITEM).to(FS_X_OPND));
+  B.on(FS_V_ORDER_BY, FC_BY, R().adv().post_m1().ctx(C_V_ORDER_ITEM).to(FS_X_OPND));
+  B.on(FS_V_PART_BY, FC_BY, R().adv().post_m1().ctx(C_V_PART).to(FS_X_OPND));
+  B.on(FS_AFTER + C_V_PK_ITEM, FC_COMMA, skip_to_operand);
+  B.otherwise(FS_AFTER + C_V_PK_ITEM, R().node_m1(NUTDB_NK_ATTR_PK).to(FS_VIEW_ATTRS));
+  B.on(FS_AFTER + C_V_ORDER_ITEM, FC_COMMA, skip_to_operand);
+  B.otherwise(FS_AFTER + C_V_ORDER_ITEM, R().node_m1(NUTDB_NK_ATTR_ORDER).to(FS_VIEW_ATTRS));
+  B.otherwise(FS_AFTER + C_V_PART, R().node_m1(NUTDB_NK_ATTR_PART).to(FS_VIEW_ATTRS));
+
   // ---- CREATE TABLE (mod.rs:689-805, :936-972) ----
   B.on(FS_CRE0, FC_TABLE, R().adv().to(FS_CRE1));
   B.on(FS_CRE1, FC_IF, R().adv().to(FS_CRE_IF1));
@@ -449,6 +476,7 @@ inline void fast_tables_build(FastTables& F) {
     B.on(st, FC_EDQ, R().check(FK_STR).leaf(NUTDB_NK_STR, 2).adv().to(next));
   };
   string_lit(FS_COL_COMMENT, FS_COL_ATTRS);
+  string_lit(FS_V_COMMENT, FS_VIEW_ATTRS);
   B.otherwise(FS_AFTER + C_COL_DEFAULT, R().node_m1(NUTDB_NK_ATTR_DEFAULT).to(FS_COL_ATTRS));
   B.on(FS_COL_SEP, FC_COMMA, R().adv().to(FS_COL_BEGIN));
   B.on(FS_COL_SEP, FC_RPAREN, R().adv().to(FS_TBL_ATTRS));

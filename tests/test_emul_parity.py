@@ -357,6 +357,8 @@ WIDE = [b"select [1, 2, x]", b"select {1: 2, 'a': b}", b"select a[1]", b"select 
         b"select a from (select 1 union all select 2) as q union all select b from u order by b limit 3",
         b"create table t (a Enum('x' = 1, 'y', \"z\" = 0x10, 'w'), b Array(Enum('p')), index i minmax(a), constraint c check a < 2, d Int8 default 1) order by (a, b)",
         b"CREATE TABLE IF NOT EXISTS uk (price UInt32, type Enum('terraced' = 1, 'semi-detached' = 2, 'other' = 0), is_new UInt8, INDEX idx_price minmax(price), CONSTRAINT c_is_new CHECK is_new < 2) ORDER BY (postcode1, postcode2)",
+        b"CREATE VIEW v UPDATE BY Summing ORDER BY supplyID AS SELECT supplyID, supplier FROM s1 WHERE sth = 1 UNION ALL SELECT supplyID, supplier FROM s2 UNION ALL SELECT a, b FROM s3",
+        b"create view if not exists v comment 'c' primary key (a, b), c partition by toDate(d) update by Replacing order by a as select 1 from t",
         b"with c as (select 1) select * from c", b"with a as (select x from t where y), b as (select 1 union all select 2) select a.x, b.* from a join b on a.x = b.y",
         b"with c_orders as (select c_custkey, count(o_orderkey) as c_count from customer left outer join orders on c_custkey = o_custkey and o_comment not like '%special%' group by c_custkey) select c_count, count(*) as custdist from c_orders where total_revenue = (select max(total_revenue) from revenue0) group by c_count order by custdist desc, c_count desc",
         b"SELECT 1 = 1 UNION ALL SELECT 'a' = 'b' UNION ALL SELECT 1 != 'a' UNION ALL SELECT 1 IS NULL UNION ALL SELECT null IS NULL OR col IS NULL UNION ALL SELECT NOT true UNION ALL SELECT random() XOR true UNION ALL SELECT true AND false OR false AND true"]
@@ -376,6 +378,10 @@ WIDE_AUTOMATON = [b"select [", b"select []", b"select {}", b"select {1}", b"sele
                   b"create table t (a Enum('x' = 99999999999999999999))", b"create table t (a Enum('\\u{110000}'))", b"create table t (a Enum 'x')",
                   b"create table t (index i a + 1)", b"create table t (index i)", b"create table t (index)", b"create table t (constraint c a < 2)",
                   b"create table t (constraint c check)", b"create table t (constraint check check check)", b"create table t (index index index(1))",
+                  b"create view v as select 1", b"create view v update by s", b"create view v update by s as", b"create view v update by s as (select 1)",
+                  b"create view v update by s update by t as select 1", b"create view v update by s order by a order by b as select 1",
+                  b"create view v update by s as select 1)", b"create view v update by s as select 1 x", b"create view v update s as select 1",
+                  b"create view v update by s comment c as select 1", b"create view v update by s as with c as (select 1) select 2",
                   b"with", b"with c", b"with c as", b"with c as select 1", b"with c as (select 1)", b"with c as (select 1),", b"with c as (1) select 2",
                   b"with c as (select 1) + 1 select 2", b"with c as (select 1) insert into t values (1)", b"with c as ((select 1)) select 2",
                   b"with c as (with d as (select 1) select 2) select 3", b"select * from (with d as (select 1) select 2)"]
