@@ -54,6 +54,7 @@ using namespace nlex;
 #define FAST_BINS 256         // 4 statement kinds x 64 token counts
 #define PARSE_STACK 160      // words of local stack in the fast path
 #define FIN_THREADS 256
+#define FIN_OWNER_CAP 6144u  // nodes per block of k_finalize whose owner look-up is a table (256 statements x 24 nodes)
 #define NODE_SLACK 8u        // fast-path node range of a statement = its token count + NODE_SLACK
 #define RETRY_NONE 0xFFFFFFFFu
 
@@ -1068,12 +1069,27 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(NutdbStmt* __restrict_
   }
   __syncthreads();
   const uint32_t nblock = lbegin[FIN_THREADS];
+  // node -> owning statement.  The usual block (a few thousand nodes) gets a byte table filled by the statements'
+  // own threads; a block with long statements falls back to a binary search per node.
+  __shared__ uint8_t owner[FIN_OWNER_CAP];
+  static_assert(FIN_THREADS <= 256, "owner[] holds statement indices in a byte");
+  const bool use_table = nblock <= FIN_OWNER_CAP;
+  if (use_table && v.x) {
+    for (uint32_t q = excl.x; q < excl.x + v.x; q++) owner[q] = (uint8_t)threadIdx.x;
+  }
+  __syncthreads();
   for (uint32_t j = threadIdx.x; j < nblock; j += FIN_THREADS) {
-    uint32_t lo = 0, hi = FIN_THREADS;  // last k with lbegin[k] <= j
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (lbegin[mid] <= j) lo = mid;
-      else hi = mid;
+    uint32_t lo;
+    if (use_table) {
+      lo = owner[j];
+    } else {
+      uint32_t hi = FIN_THREADS;  // last k with lbegin[k] <= j
+      lo = 0;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (lbegin[mid] <= j) lo = mid;
+        else hi = mid;
+      }
     }
     // `lo` owns node j (statements without nodes share their offset with the next one and are skipped
     // by "last k"); its nodes are [lbegin[lo], lbegin[lo+1]) of this block's range.
