@@ -427,13 +427,42 @@ __global__ void __launch_bounds__(1024) k_cuts(const uint32_t* __restrict__ off3
     s_keep[r] = (s_stmt[r] < nstmt && (r == 0 || s_stmt[r] != s_stmt[r - 1])) ? 1u : 0u;
   __syncthreads();
   __shared__ uint32_t s_cap[L4_MAX_RANGES + 1], s_b0[L4_MAX_RANGES + 1], s_long;
-  if (threadIdx.x == 0) {  // (at most 2048 entries of shared memory: a serial pass is a few microseconds)
-    uint32_t k = 0;
-    for (uint32_t r = 0; r < want; r++)
-      if (s_keep[r]) s_pos[k++] = s_stmt[r];
-    s_pos[k] = nstmt;
-    s_n = k;
-    s_long = 0;
+  __shared__ uint32_t s_wtot[32];
+  // exclusive prefix sum of v over the block's 2 x 1024 slots (slot = 2 * thread + {0, 1}); returns this thread's
+  // exclusive prefix for its first slot and the grand total
+  auto block_excl2 = [&](uint32_t v0, uint32_t v1, uint32_t& total) -> uint32_t {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = v0 + v1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= (uint32_t)d) incl += o;
+    }
+    if (lane == 31u) s_wtot[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+    for (uint32_t q = 0; q < 32u; q++) {
+      const uint32_t w = s_wtot[q];
+      if (q < warp) before += w;
+      tot += w;
+    }
+    __syncthreads();
+    total = tot;
+    return before + incl - (v0 + v1);
+  };
+  static_assert(L4_MAX_RANGES == 2048, "k_cuts: two slots per thread of its 1024-thread block");
+  {  // compaction of the kept cut points (was a serial pass of thread 0: most of this kernel's 0.13 ms)
+    const uint32_t r0 = 2u * threadIdx.x, r1 = r0 + 1u;
+    const uint32_t k0 = r0 < want ? s_keep[r0] : 0u, k1 = r1 < want ? s_keep[r1] : 0u;
+    uint32_t total;
+    const uint32_t pos = block_excl2(k0, k1, total);
+    if (k0) s_pos[pos] = s_stmt[r0];
+    if (k1) s_pos[pos + k0] = s_stmt[r1];
+    if (threadIdx.x == 0) {
+      s_pos[total] = nstmt;
+      s_n = total;
+      s_long = 0;
+    }
   }
   __syncthreads();
   const uint32_t k = s_n;
@@ -445,18 +474,20 @@ __global__ void __launch_bounds__(1024) k_cuts(const uint32_t* __restrict__ off3
     atomicMax(&s_long, b1 - b0);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t base = 0;
-    for (uint32_t r = 0; r < k; r++) {
-      const uint32_t c = s_cap[r];
-      s_cap[r] = base;
-      base += c;
+  {  // capacities -> first token slot of every range
+    const uint32_t r0 = 2u * threadIdx.x, r1 = r0 + 1u;
+    const uint32_t c0 = r0 < k ? s_cap[r0] : 0u, c1 = r1 < k ? s_cap[r1] : 0u;
+    uint32_t total;
+    const uint32_t pos = block_excl2(c0, c1, total);
+    if (r0 < k) s_cap[r0] = pos;
+    if (r1 < k) s_cap[r1] = pos + c0;
+    if (threadIdx.x == 0) {
+      s_cap[k] = total;
+      s_b0[k] = n;
+      info[0] = k;
+      info[1] = total;
+      info[2] = s_long;
     }
-    s_cap[k] = base;
-    s_b0[k] = n;
-    info[0] = k;
-    info[1] = base;
-    info[2] = s_long;
   }
   __syncthreads();
   for (uint32_t r = threadIdx.x; r <= k; r += 1024u) {
