@@ -463,3 +463,34 @@ def test_wire_statement_records(ctx):
     assert np.array_equal(np.concatenate([got[k]["stmt"]["status"] for k in keys]), plain.stmt["status"])
     assert np.array_equal(np.concatenate([got[k]["stmt"]["node_count"] for k in keys]), plain.stmt["node_count"])
     assert np.array_equal(np.concatenate([got[k]["node"] for k in keys]), plain.node)
+
+
+def test_dispatcher_shards_with_device_resident_text(ctx):
+    """nutdb_gpu_mctx_parse_shards: statement ranges whose text already sits in the GPU's memory (config 5's path),
+    gathered to pinned host memory in the 8-byte / 4-byte wire forms; against the one-batch result."""
+    import torch
+    from nutdb_b200 import gpu, dispatch
+    text, offs = W.generate(3, 4 << 20, seed=51)
+    whole = ctx.parse_batch(text, offs, flags=gpu.F_NO_TOKENS)
+    parts = [r for r in dispatch.split_statements(offs, 5) if r[1] > r[0]]
+    keep, shards = [], []
+    for lo, hi in parts:
+        o = offs[lo:hi + 1] - offs[lo]
+        t = np.concatenate([text[int(offs[lo]):int(offs[hi])], np.zeros(3, np.uint8)])   # (ragged end: no padding promised)
+        dt, do = torch.from_numpy(t).cuda(), torch.from_numpy(o.astype(np.int64)).cuda()
+        keep += [dt, do]
+        shards.append((0, dt.data_ptr(), do.data_ptr(), hi - lo, gpu.F_DEVICE_INPUT, lo))
+    torch.cuda.synchronize()
+    m = gpu.MultiContext((0,), 2)
+    got = {}
+    try:
+        m.parse_shards(shards, lambda c: got.__setitem__(c.first_stmt, (c.shard, c.batch.stmt.copy(), c.batch.pnode.copy(), c.batch.err.copy())),
+                       gpu.F_NO_TOKENS | gpu.F_WIRE_STMT)
+    finally:
+        m.close()
+    keys = sorted(got)
+    assert keys == [lo for lo, _ in parts] and [got[k][0] for k in keys] == list(range(len(parts)))
+    assert np.array_equal(np.concatenate([got[k][1]["status"] for k in keys]), whole.stmt["status"])
+    assert np.array_equal(np.concatenate([got[k][1]["tok_used"] for k in keys]), whole.stmt["tok_used"])
+    assert np.array_equal(np.concatenate([got[k][2] for k in keys]), whole.pnode)
+    assert sum(len(got[k][3]) for k in keys) == whole.n_err
