@@ -3,20 +3,25 @@
 // Pipeline of one nutdb_gpu_parse_batch() call (replaces n calls of Parser::parse,
 // reference src/parser/mod.rs:27):
 //
-//   k_prep        statement offsets -> 32-bit relative offsets + a bitmap of statement starts
-//   k_lex_A       per 32-byte chunk: transition function of the context automaton (strings, quoted
-//                 identifiers, comments); block scan; S: k_scan_vec8 over the tile aggregates
-//   k_lex_B       same for the code-token automaton, entry context now known
-//   k_lex_C       per chunk: number of tokens / statement starts / token in progress; block scan
-//   k_lex_D       per chunk: emit tokens (type, payload span, keyword id) at their final index
-//   k_parse       one thread per statement: bytecode pushdown automaton -> post-order nodes into a
-//                 per-statement scratch range; first error in pull order + (line, col)
-//   k_parse_retry statements that overflowed the fast path's stack / node range (deep nesting)
-//   k_stmt_sums, k_scan_u2, k_finalize   dense node / error arrays in statement order
+//   k_prep          statement offsets -> 32-bit relative offsets + a bitmap of statement starts; validation
+//   k_cuts          cut points of the lexer's ranges (statement starts nearest to the multiples of n / 2048)
+//   k_lex4          the single-pass lexer (lex4_kernel.cuh, lex3_core.cuh): persistent CTAs, one range of whole
+//                   statements at a time, 8 KB tiles by cp.async.bulk + mbarrier; class masks, context transition
+//                   functions + scans, token masks, thread-per-token emission, keyword hash.  (k_lex3: the same for
+//                   one token stream with look-back scans, the fallback for a statement too long to cut around.)
+//   k_punt_list, k_lex_exact<0/1>   statements the mask lexer flagged: the exact sequential walker, one thread each
+//   k_parse_fast    one thread per statement: table-driven operator-precedence parser, stack in shared memory
+//   k_parse_wide    the same parser for what it declined: stack in the statement's node range, wider grammar, folding
+//   k_parse         what both declined: the bytecode pushdown automaton (whole grammar, every error, pull order)
+//   k_parse_retry   automaton statements that overflowed its local stack (stacks in global memory)
+//   k_stmt_sums, k_scan_tiles, k_finalize   dense 32-bit wire nodes / 8-byte wire statement records / error records
+//   k_tok_compact, k_stmt_tok_remap         dense token arrays, only for callers that ask for tokens
+//   k_lex_A..D      the chunk-parallel exact walker of the verify mode NUTDB_F_ALL_TOKENS (every token incl. white
+//                   space and comments; stages its tile TRANSPOSED so 32 lanes walking 32 chunks hit 32 banks)
+//   k_lex2_fn, k_split<0/1>                 the raw-buffer statement splitter (nutdb_gpu_split_statements)
 //
-// Lexer kernels stage their 8 KB tile in shared memory TRANSPOSED (word w of chunk c at
-// [w][c], row padded by one word) so that 32 lanes walking 32 different chunks byte by byte hit
-// 32 different banks.  No CPU fallback anywhere: without a device every entry point fails.
+// The host side issues all of it without looking at a device-side count, up to one synchronisation.  No CPU fallback
+// anywhere: without a device every entry point fails.  The multi-GPU dispatcher (nutdb_gpu_mctx_*) is dispatch.cpp.
 #include <cuda_runtime.h>
 
 #include <algorithm>
