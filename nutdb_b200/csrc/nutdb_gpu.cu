@@ -729,7 +729,8 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
     const uint32_t p0 = (j0 < FAST_TOKCAP && !lex_only) ? (uint32_t)stok[j0] : ((uint32_t)tok_type[tb0] | ((uint32_t)tok_kw[tb0] << 8));
     const uint32_t k0 = (p0 & 0xFFu) == NUTDB_TT_KeywordOrIdentifier ? (p0 >> 8) : 0u;
     const uint32_t kind = k0 == npar::KW_SELECT ? 0u : (k0 == npar::KW_INSERT ? 1u : (k0 == npar::KW_CREATE ? 2u : 3u));
-    key = kind * 64u + min(63u, tc0);  // equal token counts in a warp: its lanes finish together
+    key = kind * 64u + min(63u, tc0);  // equal token counts in a warp: its lanes finish together (a bit of token-type
+                                       // hash in the key instead of length resolution measured 1 % slower)
   }
   rank = atomicAdd(&bin_count[key], 1u);
   __syncthreads();
