@@ -556,13 +556,14 @@ def main():
         # the reference API never exposes tokens (mod.rs:27 returns Statement only): no token arrays, and the statement
         # records in their 8-byte wire form (status, node count, tokens pulled)
         flags = gpu.F_NO_TOKENS
-        eflags = gpu.F_NO_TOKENS | gpu.F_WIRE_STMT
+        eflags = gpu.F_NO_TOKENS | gpu.F_WIRE_STMT | gpu.F_OFFSETS32   # (the batch ends below 4 GiB: 32-bit offsets go up)
 
         # host-resident batch -> chunked, pipelined through --e2e-workers contexts (nutdb_b200.stream):
         # uploads, kernels and downloads of different chunks overlap
         from nutdb_b200 import stream
         sp = stream.StreamParser(local, workers=args.e2e_workers)
-        h_text_np, h_offs_np = h_text.numpy(), h_offs.numpy().view(np.uint64)
+        h_offs32 = torch.from_numpy(offs.astype(np.uint32).view(np.int32)).pin_memory()
+        h_text_np, h_offs_np = h_text.numpy(), h_offs32.numpy().view(np.uint32)
         acc = {}
 
         def consume(first, bb):   # the caller's read of the step's result (arrays are in pinned host memory now)
@@ -588,10 +589,10 @@ def main():
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         sp.close()
-        h2d = n_in + 8 * (n_stmt + 1)
+        h2d = n_in + 4 * (n_stmt + 1)
         d2h = 8 * n_stmt + 4 * int(acc["n_node"]) + 32 * int(acc["n_err"])   # wire statement records (64-bit), wire nodes (32-bit), NutdbError
         e2e = {"ms": e2e_ms, "h2d": h2d, "d2h": d2h}
-        del h_text, h_offs
+        del h_text, h_offs, h_offs32
 
     # ---- max over ranks ----
     def allmax(x):
@@ -647,8 +648,8 @@ def main():
             line["e2e"] = {"value": tot_bytes / (e2e_ms_max * 1e-3) / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
                            "ms_per_step": e2e_ms_max, "statements_per_s": tot_stmts / (e2e_ms_max * 1e-3),
-                           "api": "nutdb_b200.stream.StreamParser: nutdb_gpu_parse_batch(pinned host text, host offsets, "
-                                  f"NUTDB_F_NO_TOKENS | NUTDB_F_WIRE_STMT) per chunk on {args.e2e_workers} contexts -> pinned host wire-stmt (8 B) / wire-node "
+                           "api": "nutdb_b200.stream.StreamParser: nutdb_gpu_parse_batch(pinned host text, pinned 32-bit host offsets, "
+                                  f"NUTDB_F_NO_TOKENS | NUTDB_F_WIRE_STMT | NUTDB_F_OFFSETS32) per chunk on {args.e2e_workers} contexts -> pinned host wire-stmt (8 B) / wire-node "
                                   "(32-bit words) / err arrays",
                            "chunk_bytes": args.e2e_chunk}
         if not args.no_cpu_baseline:

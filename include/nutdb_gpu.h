@@ -380,6 +380,8 @@ typedef struct NutdbCtx NutdbCtx;
 #define NUTDB_F_NO_HOST_COPY 4u /* leave every output on the device (use nutdb_gpu_batch_device) */
 #define NUTDB_F_WIRE_STMT 16u /* with NUTDB_F_NO_TOKENS: statement records cross PCIe in their 8-byte wire form (NutdbBatch.wstmt)
                                  instead of the 24-byte NutdbStmt -- the token fields are dropped, node_begin is implied */
+#define NUTDB_F_OFFSETS32 32u /* `stmt_off` points at n_stmt + 1 uint32_t offsets (cast the pointer): half the upload of the
+                                 64-bit form for batches whose text ends below 4 GiB */
 #define NUTDB_F_ALL_TOKENS 8u /* lexer verify mode: token arrays also hold Whitespace / Comment tokens (the full stream of
                                  Tokenizer::next_token, tokenizer/mod.rs:66); statements are not parsed */
 
@@ -481,7 +483,7 @@ typedef struct {
   const uint8_t *sql;      /* text; a device pointer on that device with NUTDB_F_DEVICE_INPUT in `flags` */
   const uint64_t *stmt_off;/* n_stmt + 1 ascending offsets into sql (same memory space as sql) */
   uint64_t n_stmt;
-  uint32_t flags;          /* 0 or NUTDB_F_DEVICE_INPUT */
+  uint32_t flags;          /* 0 or NUTDB_F_DEVICE_INPUT, NUTDB_F_OFFSETS32 */
   uint64_t first_stmt;     /* handed through to the chunk */
 } NutdbMShard;
 
@@ -506,8 +508,8 @@ int nutdb_gpu_mctx_device_count(const NutdbMCtx *m);
  * NUTDB_MF_*.  Returns NUTDB_OK or the first error (nutdb_gpu_mctx_last_error). */
 int nutdb_gpu_mctx_parse_shards(NutdbMCtx *m, const NutdbMShard *shards, uint64_t n_shards, uint32_t flags,
                                 nutdb_chunk_fn fn, void *user);
-/* One HOST batch (the arguments of nutdb_gpu_parse_batch; any size): cut at statement boundaries into chunks of about
- * `chunk_bytes`, contiguous ranges of chunks dealt to the devices balanced by bytes, parsed and gathered as above. */
+/* One HOST batch (the arguments of nutdb_gpu_parse_batch; any size; NUTDB_F_OFFSETS32 in `flags` for 32-bit offsets): cut at
+ * statement boundaries into chunks of about `chunk_bytes`, contiguous ranges of chunks dealt to the devices balanced by bytes, parsed and gathered as above. */
 int nutdb_gpu_mctx_parse_stream(NutdbMCtx *m, const uint8_t *sql, const uint64_t *stmt_off, uint64_t n_stmt,
                                 uint64_t chunk_bytes, uint32_t flags, nutdb_chunk_fn fn, void *user);
 

@@ -135,7 +135,7 @@ void work(Run& r, Worker& w) {
     if (k >= mine.size()) return;
     const NutdbMShard& sh = r.shards[mine[k]];
     NutdbBatch b;
-    const uint32_t pflags = (sh.flags & NUTDB_F_DEVICE_INPUT) | (r.flags & (NUTDB_F_NO_TOKENS | NUTDB_F_WIRE_STMT)) | NUTDB_F_NO_HOST_COPY;
+    const uint32_t pflags = (sh.flags & (NUTDB_F_DEVICE_INPUT | NUTDB_F_OFFSETS32)) | (r.flags & (NUTDB_F_NO_TOKENS | NUTDB_F_WIRE_STMT)) | NUTDB_F_NO_HOST_COPY;
     int rc = nutdb_gpu_parse_batch(w.ctx, sh.sql, sh.stmt_off, sh.n_stmt, pflags, &b);
     if (rc != NUTDB_OK) {
       fail(r, rc, std::string("shard ") + std::to_string(mine[k]) + ": " + nutdb_gpu_last_error(w.ctx));
@@ -310,13 +310,16 @@ int nutdb_gpu_mctx_parse_stream(NutdbMCtx* m, const uint8_t* sql, const uint64_t
   // (the offsets are validated where they are used: every shard's by k_prep on its device -- walking 8 bytes per
   // statement here would cost more host time than a chunk's kernels; a descending pair either trips the range checks
   // below or makes its shard fail with NUTDB_E_ARG)
-  if (stmt_off[n_stmt] < stmt_off[0]) {
+  const bool o32 = (flags & NUTDB_F_OFFSETS32) != 0;
+  const uint32_t* const off32p = reinterpret_cast<const uint32_t*>(stmt_off);
+  auto off = [&](uint64_t i) -> uint64_t { return o32 ? (uint64_t)off32p[i] : stmt_off[i]; };
+  if (off(n_stmt) < off(0)) {
     m->err = "statement offsets must ascend";
     return NUTDB_E_ARG;
   }
   if (chunk_bytes < 4096) chunk_bytes = 4096;
   if (chunk_bytes > 0x70000000ull) chunk_bytes = 0x70000000ull;
-  const uint64_t total = stmt_off[n_stmt] - stmt_off[0];
+  const uint64_t total = off(n_stmt) - off(0);
   const size_t ndev = m->devices.size();
   // cut points: statement boundaries nearest to the multiples of `chunk_bytes`; chunk k goes to device k * ndev / nchunks
   // (contiguous ranges of the batch per device, balanced by bytes)
@@ -325,24 +328,25 @@ int nutdb_gpu_mctx_parse_stream(NutdbMCtx* m, const uint8_t* sql, const uint64_t
   std::vector<uint64_t> cut(nchunks + 1, n_stmt);
   cut[0] = 0;
   for (uint64_t k = 1; k < nchunks; k++) {
-    const uint64_t target = stmt_off[0] + (uint64_t)((unsigned __int128)total * k / nchunks);
-    const uint64_t s = (uint64_t)(std::lower_bound(stmt_off, stmt_off + n_stmt + 1, target) - stmt_off);
+    const uint64_t target = off(0) + (uint64_t)((unsigned __int128)total * k / nchunks);
+    const uint64_t s = o32 ? (uint64_t)(std::lower_bound(off32p, off32p + n_stmt + 1, (uint32_t)std::min<uint64_t>(target, 0xFFFFFFFFull)) - off32p)
+                           : (uint64_t)(std::lower_bound(stmt_off, stmt_off + n_stmt + 1, target) - stmt_off);
     cut[k] = std::min<uint64_t>(std::max<uint64_t>(s, cut[k - 1]), n_stmt);
   }
   std::vector<NutdbMShard> sh;
   sh.reserve(nchunks);
   for (uint64_t k = 0; k < nchunks; k++) {
     if (cut[k + 1] <= cut[k]) continue;
-    if (stmt_off[cut[k + 1]] < stmt_off[cut[k]] || stmt_off[cut[k + 1]] - stmt_off[cut[k]] >= 0x7FFFFFFFull) {
+    if (off(cut[k + 1]) < off(cut[k]) || off(cut[k + 1]) - off(cut[k]) >= 0x7FFFFFFFull) {
       m->err = "statement offsets must ascend, and no chunk may exceed 2^31 bytes";
       return NUTDB_E_ARG;
     }
     NutdbMShard s;
     s.device_index = (int)(k * ndev / nchunks);
     s.sql = sql;
-    s.stmt_off = stmt_off + cut[k];
+    s.stmt_off = o32 ? reinterpret_cast<const uint64_t*>(off32p + cut[k]) : stmt_off + cut[k];
     s.n_stmt = cut[k + 1] - cut[k];
-    s.flags = 0;
+    s.flags = o32 ? NUTDB_F_OFFSETS32 : 0u;
     s.first_stmt = cut[k];
     sh.push_back(s);
   }

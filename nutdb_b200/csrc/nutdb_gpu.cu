@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_vec8(const uint32_t* __re
 // ------------------------------------------------------------------------------------------
 // k_prep
 // ------------------------------------------------------------------------------------------
-__global__ void k_prep(const uint64_t* __restrict__ off, uint64_t nstmt, uint64_t nbytes, uint32_t* __restrict__ off32,
+template <typename OffT>  // uint64_t, or uint32_t with NUTDB_F_OFFSETS32
+__global__ void k_prep(const OffT* __restrict__ off, uint64_t nstmt, uint64_t nbytes, uint32_t* __restrict__ off32,
                        uint32_t* __restrict__ bitmap, uint32_t* __restrict__ first_stmt, uint32_t* __restrict__ bad) {
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nstmt) return;
@@ -1443,12 +1444,19 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
 
   // ---- input ----
   uint64_t off_first = 0, off_last = 0;
+  const bool off32_in = (flags & NUTDB_F_OFFSETS32) != 0;  // the offsets are 32-bit words (half the upload)
+  const size_t off_size = off32_in ? 4 : 8;
+  const uint8_t* const off_bytes = reinterpret_cast<const uint8_t*>(stmt_off);
   if (dev_in) {
-    CK(cudaMemcpyAsync(hS, stmt_off, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hS + 2, stmt_off + n_stmt, 8, cudaMemcpyDeviceToHost, st));
+    hS[0] = hS[1] = hS[2] = hS[3] = 0;
+    CK(cudaMemcpyAsync(hS, off_bytes, off_size, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hS + 2, off_bytes + off_size * n_stmt, off_size, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::memcpy(&off_first, hS, 8);
-    std::memcpy(&off_last, hS + 2, 8);
+    std::memcpy(&off_first, hS, off_size);
+    std::memcpy(&off_last, hS + 2, off_size);
+  } else if (off32_in) {
+    off_first = reinterpret_cast<const uint32_t*>(stmt_off)[0];
+    off_last = reinterpret_cast<const uint32_t*>(stmt_off)[n_stmt];
   } else {
     off_first = stmt_off[0];
     off_last = stmt_off[n_stmt];
@@ -1483,7 +1491,7 @@ int nutdb_gpu_parse_batch(NutdbCtx* ctx, const uint8_t* sql, const uint64_t* stm
     ENSURE_DEV(text, (size_t)ntiles * LEX_TILE + 16);
     ENSURE_DEV(off64, 8 * ((size_t)nstmt + 1));
     if (n) CK(cudaMemcpyAsync(ctx->text.p, sql + off_first, n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->off64.p, stmt_off, 8 * ((size_t)nstmt + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->off64.p, stmt_off, off_size * ((size_t)nstmt + 1), cudaMemcpyHostToDevice, st));
     dText = (const uint8_t*)ctx->text.p;
     dOff = (const uint64_t*)ctx->off64.p;
   }
@@ -1505,8 +1513,13 @@ run_again:
   CK(cudaMemsetAsync(dS, 0, 128, st));
   {
     const uint32_t blocks = (uint32_t)(((uint64_t)nstmt + 1 + 255) / 256);
-    LAUNCH("k_prep", k_prep<<<blocks, 256, 0, st>>>(dOff, nstmt, (uint64_t)n, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p,
-                                                  (uint32_t*)ctx->firstStmt.p, dS));
+    if (off32_in)
+      LAUNCH("k_prep", k_prep<uint32_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(dOff), nstmt, (uint64_t)n,
+                                                              (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p,
+                                                              (uint32_t*)ctx->firstStmt.p, dS));
+    else
+      LAUNCH("k_prep", k_prep<uint64_t><<<blocks, 256, 0, st>>>(dOff, nstmt, (uint64_t)n, (uint32_t*)ctx->off32.p, (uint32_t*)ctx->bitmap.p,
+                                                              (uint32_t*)ctx->firstStmt.p, dS));
   }
   uint32_t ntok = 0;
   ctx->n_punt = 0;

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import build as _build
 
-F_NO_TOKENS, F_DEVICE_INPUT, F_NO_HOST_COPY, F_ALL_TOKENS, F_WIRE_STMT = 1, 2, 4, 8, 16
+F_NO_TOKENS, F_DEVICE_INPUT, F_NO_HOST_COPY, F_ALL_TOKENS, F_WIRE_STMT, F_OFFSETS32 = 1, 2, 4, 8, 16, 32
 
 NODE_DT = np.dtype([("kind", "u1"), ("sub", "u1"), ("aux", "<u2"), ("parent", "<u4"), ("a", "<u4"), ("b", "<u4")])
 PNODE_DT = np.dtype("<u4")   # the wire form of a node: one 32-bit word (NUTDB_PN_* in nutdb_gpu.h); kind = word & 127
@@ -252,7 +252,7 @@ class Context:
     def parse_batch(self, text, offs, flags=0, copy=True):
         """text: bytes / uint8 array holding all statements; offs: uint64[n+1] ascending offsets into it."""
         t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text)
-        o = np.ascontiguousarray(offs, np.uint64)
+        o = np.ascontiguousarray(offs, np.uint32 if flags & F_OFFSETS32 else np.uint64)
         assert t.dtype == np.uint8 and o.ndim == 1 and len(o) >= 1
         return self.parse_batch_raw(t.ctypes.data, o.ctypes.data, len(o) - 1, flags, copy)
 
@@ -360,7 +360,8 @@ class MultiContext:
     def parse_stream(self, text, offs, on_chunk, chunk_bytes=64 << 20, flags=F_NO_TOKENS):
         """One host batch -> on_chunk(Chunk) per chunk, in completion order, from the dispatcher's worker threads."""
         t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text)
-        o = np.ascontiguousarray(offs, np.uint64)
+        # NUTDB_F_OFFSETS32: the caller's offsets are uint32 (half the upload); otherwise uint64
+        o = np.ascontiguousarray(offs, np.uint32 if flags & F_OFFSETS32 else np.uint64)
         errs = []
         cb = self._callback(on_chunk, errs)
         rc = lib().nutdb_gpu_mctx_parse_stream(self._h, t.ctypes.data, o.ctypes.data, len(o) - 1, int(chunk_bytes), flags, cb, None)

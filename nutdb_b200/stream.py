@@ -31,5 +31,5 @@ class StreamParser:
                 n[0] += 1
             on_batch(c.first_stmt, c.batch)
 
-        self.m.parse_stream(np.ascontiguousarray(text), np.ascontiguousarray(offs, np.uint64), on_chunk, chunk_bytes, flags)
+        self.m.parse_stream(np.ascontiguousarray(text), np.ascontiguousarray(offs), on_chunk, chunk_bytes, flags)
         return n[0]

@@ -53,6 +53,7 @@ pub const F_DEVICE_INPUT: u32 = 2;
 pub const F_NO_HOST_COPY: u32 = 4;
 pub const F_ALL_TOKENS: u32 = 8;
 pub const F_WIRE_STMT: u32 = 16;
+pub const F_OFFSETS32: u32 = 32;
 pub const MF_GATHER_DEVICE0: u32 = 0x100;
 pub const MF_SERIAL_CALLBACKS: u32 = 0x200;
 pub const OK: c_int = 0;

@@ -456,6 +456,15 @@ def test_wire_statement_records(ctx):
     for f in ("status", "node_begin", "node_count", "tok_used"):
         assert np.array_equal(wire.stmt[f], plain.stmt[f]), f
     assert np.array_equal(wire.node, plain.node) and np.array_equal(wire.err, plain.err)
+    # NUTDB_F_OFFSETS32: the same batch described by 32-bit offsets, directly and through the dispatcher
+    o32 = ctx.parse_batch(text, offs.astype(np.uint32), flags=gpu.F_NO_TOKENS | gpu.F_OFFSETS32)
+    assert np.array_equal(o32.stmt, plain.stmt) and np.array_equal(o32.pnode, plain.pnode) and np.array_equal(o32.err, plain.err)
+    got32 = _collect((0, 0), text, offs.astype(np.uint32), gpu.F_NO_TOKENS | gpu.F_WIRE_STMT | gpu.F_OFFSETS32, 512 << 10)
+    k32 = sorted(got32)
+    assert np.array_equal(np.concatenate([got32[k]["pnode"] for k in k32]), plain.pnode)
+    assert np.array_equal(np.concatenate([got32[k]["stmt"]["status"] for k in k32]), plain.stmt["status"])
+    with pytest.raises(gpu.NutdbGpuError):   # (descending 32-bit offsets are refused like 64-bit ones)
+        ctx.parse_batch(b"select 1", np.array([0, 8, 4], np.uint32), flags=gpu.F_OFFSETS32)
     # without NUTDB_F_NO_TOKENS the flag is ignored (the token fields are needed)
     assert ctx.parse_batch(text, offs, flags=gpu.F_WIRE_STMT).wstmt is None
     got = _collect((0, 0), text, offs, gpu.F_NO_TOKENS | gpu.F_WIRE_STMT, 512 << 10)
