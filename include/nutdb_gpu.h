@@ -362,7 +362,8 @@ typedef struct {
   void *impl;               /* opaque */
   const uint32_t *pnode;    /* [n_node] wire nodes (NUTDB_PN_*) */
   uint64_t n_ext;           /* nodes whose fields did not fit the wire word */
-  const NutdbNodeExt *ext;  /* [n_ext] sorted by .index; host memory whatever the flags */
+  const NutdbNodeExt *ext;  /* [n_ext] sorted by .index; host memory (NULL with NUTDB_F_NO_HOST_COPY until
+                               nutdb_gpu_batch_fetch_ext) */
   const uint64_t *wstmt;    /* [n_stmt] with NUTDB_F_WIRE_STMT (then `stmt` is NULL): status | node_count << 4 |
                                tok_used << 34; node_begin is the running sum of node_count (nodes are dense, in statement
                                order).  nutdb_batch_expand_stmts() rebuilds NutdbStmt records from them */
@@ -416,6 +417,9 @@ typedef struct {
   const void *wstmt; /* wire statement records (NUTDB_F_WIRE_STMT), else NULL */
 } NutdbBatchDevice;
 int nutdb_gpu_batch_device(const NutdbBatch *batch, NutdbBatchDevice *out);
+/* With NUTDB_F_NO_HOST_COPY a batch reports n_ext but leaves the side table of its wire nodes on the device (ext = NULL);
+ * this fetches and sorts it into host memory and sets batch->ext.  A no-op for batches that have it or need none. */
+int nutdb_gpu_batch_fetch_ext(NutdbBatch *batch);
 
 /* 64-bit checksum of everything the batch holds on the device (statement records, the four token arrays, nodes,
  * error records), computed on the device:

@@ -143,6 +143,10 @@ void work(Run& r, Worker& w) {
     }
     NutdbBatchDevice dv;
     nutdb_gpu_batch_device(&b, &dv);
+    if (b.n_ext && nutdb_gpu_batch_fetch_ext(&b) != NUTDB_OK) {  // (rare: nodes that did not fit the 32-bit wire word)
+      fail(r, NUTDB_E_CUDA, "cannot fetch the wire nodes' side table");
+      return;
+    }
     // ---- gather: one copy per array from the producing device to the gather point ----
     Slot& s = to_dev0 ? w.dev0 : w.host;
     const bool wire_stmt = dv.wstmt != nullptr;  // (NUTDB_F_WIRE_STMT, and every count fitted the 8-byte record)

@@ -1187,6 +1187,7 @@ struct NutdbCtx {
   DevBuf extNodes;
   HostBuf hExt;
   std::vector<NutdbNodeExt> ext;
+  uint32_t ext_count = 0;  // side-table entries of the last batch (on the device until fetched)
   DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
@@ -1308,6 +1309,19 @@ int ensure_host(NutdbCtx* ctx, HostBuf& b, size_t bytes) {
     int rc_ = ensure_host(ctx, ctx->buf, (bytes));  \
     if (rc_ != NUTDB_OK) return rc_;                \
   } while (0)
+
+// the side table of the last batch's wire nodes: device -> host, sorted by node index
+int fetch_ext(NutdbCtx* ctx) {
+  const uint32_t nl = ctx->ext_count;
+  ctx->ext.clear();
+  if (!nl) return NUTDB_OK;
+  ENSURE_HOST(hExt, 16 * (size_t)nl);
+  CK(cudaMemcpy(ctx->hExt.p, ctx->extNodes.p, 16 * (size_t)nl, cudaMemcpyDeviceToHost));
+  const NutdbNodeExt* hp = (const NutdbNodeExt*)ctx->hExt.p;
+  ctx->ext.assign(hp, hp + nl);
+  std::sort(ctx->ext.begin(), ctx->ext.end(), [](const NutdbNodeExt& x, const NutdbNodeExt& y) { return x.index < y.index; });
+  return NUTDB_OK;
+}
 
 void free_all(NutdbCtx* c) {
   DevBuf* d[] = {&c->extNodes, &c->rangeByte, &c->rangeStmt, &c->rangeTokBase, &c->rangeCount, &c->rangeDense, &c->tokTypeD, &c->tokStartD, &c->tokEndD, &c->tokKwD, &c->dbgTim, &c->dbgTiles, &c->winIdx, &c->winHas, &c->winEof, &c->descFn, &c->descA, &c->descI, &c->descB, &c->descC, &c->winCtx, &c->winFn, &c->scanTotals, &c->hashAcc, &c->puntBlockCount, &c->puntBlockPref, &c->text, &c->off64, &c->off32, &c->bitmap, &c->localA, &c->localB, &c->localC, &c->tileA, &c->tileB,
@@ -1900,19 +1914,20 @@ run_again:
       out->stmt = (const NutdbStmt*)ctx->hStmt.p;
     }
   }
+  ctx->ext_count = 0;
   if (n_node && hS[48]) {  // nodes that did not fit the 32-bit wire form: their exact fields, sorted by node index
     if (hS[48] > ext_cap) {
       ctx->err = "node side table overflow";
       return NUTDB_E_NOMEM;
     }
-    const uint32_t nl = hS[48];
-    ENSURE_HOST(hExt, 16 * (size_t)nl);
-    CK(cudaMemcpy(ctx->hExt.p, ctx->extNodes.p, 16 * (size_t)nl, cudaMemcpyDeviceToHost));
-    const NutdbNodeExt* hp = (const NutdbNodeExt*)ctx->hExt.p;
-    ctx->ext.assign(hp, hp + nl);
-    std::sort(ctx->ext.begin(), ctx->ext.end(), [](const NutdbNodeExt& x, const NutdbNodeExt& y) { return x.index < y.index; });
-    out->n_ext = nl;
-    out->ext = ctx->ext.data();
+    ctx->ext_count = hS[48];
+    out->n_ext = hS[48];
+    // (outputs left on the device: the table is fetched and sorted when somebody asks -- nutdb_gpu_batch_fetch_ext)
+    if (!(flags & NUTDB_F_NO_HOST_COPY)) {
+      const int rc = fetch_ext(ctx);
+      if (rc != NUTDB_OK) return rc;
+      out->ext = ctx->ext.data();
+    }
   }
   cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
@@ -1996,6 +2011,18 @@ int nutdb_gpu_batch_hash(const NutdbBatch* batch, uint64_t* out) {
   CK(cudaMemcpyAsync(ctx->hSmall.p, acc, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   *out = *(const uint64_t*)ctx->hSmall.p;
+  return NUTDB_OK;
+}
+
+int nutdb_gpu_batch_fetch_ext(NutdbBatch* batch) {
+  if (!batch || !batch->impl) return NUTDB_E_ARG;
+  NutdbCtx* ctx = (NutdbCtx*)batch->impl;
+  if (!ctx->batch_live) return NUTDB_E_ARG;
+  if (batch->ext || !batch->n_ext) return NUTDB_OK;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return NUTDB_E_CUDA;
+  const int rc = fetch_ext(ctx);
+  if (rc != NUTDB_OK) return rc;
+  batch->ext = ctx->ext.data();
   return NUTDB_OK;
 }
 

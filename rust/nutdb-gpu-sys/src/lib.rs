@@ -88,6 +88,7 @@ extern "C" {
     pub fn nutdb_batch_expand_nodes(batch: *const NutdbBatch, out: *mut NutdbNode) -> c_int;
     pub fn nutdb_batch_expand_stmts(batch: *const NutdbBatch, out: *mut NutdbStmt) -> c_int;
     pub fn nutdb_gpu_batch_device(batch: *const NutdbBatch, out: *mut NutdbBatchDevice) -> c_int;
+    pub fn nutdb_gpu_batch_fetch_ext(batch: *mut NutdbBatch) -> c_int;
     pub fn nutdb_gpu_batch_hash(batch: *const NutdbBatch, out: *mut u64) -> c_int;
     pub fn nutdb_gpu_split_statements(ctx: *mut NutdbCtx, sql: *const u8, len: u64, flags: u32, stmt_off: *mut *const u64,
                                       n_stmt: *mut u64) -> c_int;
