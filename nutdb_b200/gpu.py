@@ -279,6 +279,17 @@ class Context:
     def slow_statements(self):
         return lib().nutdb_gpu_last_slow_statements(self._h)
 
+    def force_lookback(self, on):
+        """Debug: lex with k_lex3 (one token stream, look-back scans between tiles) instead of the range lexer."""
+        L = lib()
+        L.nutdb_gpu_debug_force_lookback.argtypes = [C.c_void_p, C.c_int]
+        L.nutdb_gpu_debug_force_lookback(self._h, 1 if on else 0)
+
+    def last_lookback(self):
+        L = lib()
+        L.nutdb_gpu_debug_last_lookback.argtypes = [C.c_void_p]
+        return bool(L.nutdb_gpu_debug_last_lookback(self._h))
+
     def wide_statements(self):
         return lib().nutdb_gpu_last_wide_statements(self._h)
 

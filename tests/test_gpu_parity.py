@@ -503,3 +503,49 @@ def test_dispatcher_shards_with_device_resident_text(ctx):
     assert np.array_equal(np.concatenate([got[k][1]["tok_used"] for k in keys]), whole.stmt["tok_used"])
     assert np.array_equal(np.concatenate([got[k][2] for k in keys]), whole.pnode)
     assert sum(len(got[k][3]) for k in keys) == whole.n_err
+
+
+def test_lookback_lexer_fallback(ctx):
+    """k_lex3 -- one token stream, chained look-back scans between tiles -- takes over when a statement is too long to cut
+    the batch around it.  Forced on ordinary workloads, and reached on its own by a batch with a giant statement."""
+    from nutdb_b200 import gpu
+    c2 = gpu.Context(0)
+    try:
+        c2.force_lookback(True)
+        for config in (2, 3, 4):
+            text, offs = W.generate(config, 2 << 20, seed=61 + config)
+            got = c2.parse_batch(text, offs)
+            assert c2.last_lookback()
+            bad = P.compare_with_oracle(got, text, offs)
+            assert not bad, "\n".join(bad)
+        check(c2, fuzz.fuzz_statements(CORPUS + fuzz.EXTRA_SEEDS, 8000, seed=65, max_mut=4))
+    finally:
+        c2.close()
+    # a 40 MiB statement (one string literal) between ordinary ones: the range lexer gives up, the look-back lexer runs
+    text, offs = W.generate(2, 1 << 20, seed=66)
+    stmts = [bytes(text[int(offs[i]):int(offs[i + 1])]) for i in range(len(offs) - 1)]
+    giant = b"select '" + b"x" * (40 << 20) + b"', 1 from t"
+    batch = stmts[:2000] + [giant] + stmts[2000:4000]
+    t2, o2 = P.make_batch(batch)
+    got = ctx.parse_batch(t2, o2)
+    assert ctx.last_lookback()
+    bad = P.compare_with_oracle(got, t2, o2)
+    assert not bad, "\n".join(bad)
+    got = ctx.parse_batch(text, offs)      # and the context goes back to the range lexer afterwards
+    assert not ctx.last_lookback()
+    assert not P.compare_with_oracle(got, text, offs)
+
+
+def test_deep_malformed_statements_reach_the_automaton_and_its_retry_pass(ctx):
+    """Deep nests the table-driven passes decline (errors, constructs outside their grammar) still get the reference's
+    first error and position from the automaton -- through its global-memory retry pass where its local stack overflows."""
+    d = 300
+    stmts = ["select " + "(" * d + "1" + ")" * (d - 1), "select " + "(" * d + "1" + ")" * (d + 1),
+             "select " + "(select " * 200 + "1d" + ")" * 200, "select " + "[" * d + "1" + "]" * (d - 1) + " from t",
+             "select " + "f(" * d + "x" + ")" * d + " from", "select " + "not " * 300 + "1d",
+             "select " + "CASE WHEN a THEN " * 150 + "1" + " END" * 149, "select " + "{1:" * 200 + "x" + "}" * 199,
+             "select " + "a[" * 250 + "x" + "]" * 249, "select " + "(" * d + "1 union all select 2" + ")" * d,
+             "select " + "(" * d + "$1" + ")" * d, "select " + "(" * 40 + "1" + ")" * 40]
+    got = check(ctx, stmts)
+    assert ctx.slow_statements() >= 8
+    assert int((got.stmt["status"] != 0).sum()) >= 8
