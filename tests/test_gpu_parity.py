@@ -549,3 +549,32 @@ def test_deep_malformed_statements_reach_the_automaton_and_its_retry_pass(ctx):
     got = check(ctx, stmts)
     assert ctx.slow_statements() >= 8
     assert int((got.stmt["status"] != 0).sum()) >= 8
+
+
+def test_batch_near_the_two_gib_limit(ctx):
+    """One batch of 1.9 GiB (the ABI's limit is 2^31 bytes): the statement records and the wire nodes equal those of
+    the same statements parsed in four separate batches, a sample equals the oracle's, and one byte more than the limit
+    is refused."""
+    from nutdb_b200 import gpu
+    text, offs = W.generate(2, 1900 << 20, seed=71)
+    n = len(offs) - 1
+    whole = ctx.parse_batch(text, offs, flags=gpu.F_NO_TOKENS | gpu.F_WIRE_STMT, copy=False)
+    w_stmt, w_node, n_err = whole.wstmt.copy(), whole.pnode.copy(), whole.n_err
+    assert n_err == 0 and len(w_stmt) == n
+    cuts = [0, n // 4, n // 2, 3 * n // 4, n]
+    parts_s, parts_n = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = ctx.parse_batch(text, offs[a:b + 1], flags=gpu.F_NO_TOKENS | gpu.F_WIRE_STMT, copy=False)
+        parts_s.append(part.wstmt.copy())
+        parts_n.append(part.pnode.copy())
+    assert np.array_equal(np.concatenate(parts_s), w_stmt)
+    assert np.array_equal(np.concatenate(parts_n), w_node)
+    k = int(np.searchsorted(offs, np.uint64(4 << 20)))
+    tail = offs[n - k:] - offs[n - k]                       # the LAST statements of the batch against the oracle
+    t_tail = np.concatenate([text[int(offs[n - k]):int(offs[n])], np.zeros(16, np.uint8)])
+    got = ctx.parse_batch(t_tail, tail)
+    assert not P.compare_with_oracle(got, t_tail, tail)
+    first_nodes = int((w_stmt[:n - k] >> np.uint64(4) & np.uint64(0x3FFFFFFF)).sum())
+    assert np.array_equal(w_node[first_nodes:], got.pnode)
+    with pytest.raises(gpu.NutdbGpuError):
+        ctx.parse_batch(text[:16], np.array([0, 1 << 31], np.uint64))
