@@ -356,7 +356,8 @@ typedef struct {
   const uint8_t *tok_type;  /* [n_tok]  NUTDB_TT_* (no Whitespace / Comment) */
   const uint32_t *tok_start;/* [n_tok]  payload span start, statement-relative */
   const uint32_t *tok_end;  /* [n_tok] */
-  const uint8_t *tok_kw;    /* [n_tok]  KeywordOrIdentifier: keyword id or 0; Integer/HexLiteral: digit count (max 255); else 0 */
+  const uint8_t *tok_kw;    /* [n_tok]  KeywordOrIdentifier: keyword id or 0; Integer/HexLiteral: digit count (max 255);
+                             *          Escaped{SQ,DQ}StringLiteral: 1 = holds no backslash-u escape (unescaping cannot fail); else 0 */
   const NutdbNode *node;    /* [n_node] expanded nodes: NULL in batches produced by the library (see pnode) */
   const NutdbError *err;    /* [n_err]  sorted by .stmt */
   void *impl;               /* opaque */

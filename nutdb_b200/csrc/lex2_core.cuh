@@ -79,6 +79,7 @@ inline void build_lex2_tables(Lex2Tables& T) {
 // raw class masks of one 32-byte window (bit i = byte base+i); bytes at or beyond the batch end are 0
 struct Win {
   uint32_t sq, dq, bt, nl, bs, dash, slash, star, L, D, DOT, OP, P, WS, IE, NE;
+  uint32_t u = 0;  // bytes 'u' (lex3: an escaped one inside a literal means a backslash-u escape the parser must validate)
   uint32_t bnd;    // a statement starts at this byte; also set at position n (virtual end) if inside the window
   uint32_t valid;  // bytes that exist (< n)
 };
@@ -141,6 +142,7 @@ NUTDB_HD uint8_t esc_carry_out(uint32_t bs, uint8_t carry_in) {
 
 struct Events {
   uint32_t quotes, dd, slst, stsl, all, own;
+  uint32_t uesc = 0;  // escaped 'u' bytes
 };
 NUTDB_HD Events make_events(const Win& w, uint32_t esc, uint8_t prev) {
   Events e;
@@ -150,6 +152,7 @@ NUTDB_HD Events make_events(const Win& w, uint32_t esc, uint8_t prev) {
   e.stsl = w.slash & ((w.star << 1) | (prev == '*' ? 1u : 0u)) & ~w.bnd;
   e.own = (e.quotes | w.bt | w.nl | e.dd | e.slst | e.stsl) & w.valid;
   e.all = e.own | w.bnd;
+  e.uesc = esc & w.u;
   return e;
 }
 NUTDB_HD uint8_t event_type(const Win& w, const Events& ev, int e) {
@@ -207,12 +210,14 @@ NUTDB_HD uint32_t esc_mask32(uint32_t bs, uint8_t carry_in) {
 struct StrCarry {  // what later windows need to know about a string / quoted identifier still open
   uint8_t has_open = 0;   // one was opened in this window (and that is the last opening)
   uint8_t esc = 0;        // escaped-flag since that opening (or over the whole window if none)
+  uint8_t chk = 0;        // ... a backslash-u escape since that opening: the literal needs the parser's validation
   uint32_t open_pos = 0;  // absolute offset of the opening quote
 };
 NUTDB_HD StrCarry str_then(const StrCarry& a, const StrCarry& b) {
   if (b.has_open) return b;
   StrCarry r = a;
   r.esc = (uint8_t)(a.esc | b.esc);
+  r.chk = (uint8_t)(a.chk | b.chk);
   return r;
 }
 struct WinCtx {

@@ -102,6 +102,7 @@ NUTDB_HD void classify_planes(const uint32_t p[8], uint32_t valid, Win& w, Ops& 
   op.EQ = r3 & h11 & l01;
   op.GT = r3 & h11 & l10;
   w.bs = r5 & h11 & l00;
+  w.u = r7 & h01 & l01;
   w.bt = r6 & h00 & l00;
   w.D = r3 & n7 & (~b3 | (~b2 & ~b1));
   const uint32_t lo_nz = b3 | b2 | b1 | b0, lo_leA = ~b3 | (~b2 & ~l11);
@@ -129,12 +130,14 @@ struct WinCtx3 {
   uint32_t in_str = 0;    // bytes lexed inside '..' / ".."
   uint32_t in_bt = 0;     // bytes lexed inside `..`
   uint32_t close = 0, openm = 0, escd = 0;
+  uint32_t chkd = 0;      // closes of literals opened here that hold a backslash-u escape
   uint32_t csq = 0, cdq = 0;  // closes by quote character (the rest of `close` are backticks)
   uint32_t bad = 0;       // the statement containing this byte needs the exact path
   uint32_t bad_prev = 0;  // the statement ENDING right before this (statement start) byte needs the exact path
   uint32_t escm = 0;
   uint8_t s_out = A_C;
   uint8_t esc_first = 0;  // this window's escaped-flag contribution before a carried close
+  uint8_t chk_first = 0;  // ... and its backslash-u contribution
   StrCarry sc;
   uint32_t last_bnd1 = 0;  // 1 + absolute offset of the last statement start in the window, 0 if none
 };
@@ -151,7 +154,7 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
   int s_pos = -1, p0 = 0;
   uint32_t m_code = 0, m_str = 0, m_bt = 0;
   bool open_local = false;
-  uint8_t cur_esc = 0;
+  uint8_t cur_esc = 0, cur_chk = 0;
   auto assign = [&](int lo, int hi) {
     if (hi < lo) return;
     const uint32_t r = bits_range(lo, hi);
@@ -159,6 +162,7 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
     else if (s == A_SQ || s == A_DQ) {
       m_str |= r;
       if (w.bs & r) cur_esc = 1;
+      if (ev.uesc & r) cur_chk = 1;
     } else if (s == A_BT) m_bt |= r;
   };
   while (todo) {
@@ -173,6 +177,7 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
       s_pos = -100;
       reopen_at = -1;
       cur_esc = 0;
+      cur_chk = 0;
       open_local = true;  // nothing can be carried into a new statement
       o.last_bnd1 = base + (uint32_t)e + 1u;
       p0 = e;
@@ -190,6 +195,7 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
         } else {
           open_local = true;
           cur_esc = 0;
+          cur_chk = 0;
           o.openm |= bit;
           o.sc.has_open = 1;
           o.sc.open_pos = base + (uint32_t)e;
@@ -212,13 +218,19 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
           if (open_local) o.escd |= bit;
           else o.esc_first = 1;
         }
+        if (cur_chk) {
+          if (open_local) o.chkd |= bit;
+          else o.chk_first = 1;
+        }
         cur_esc = 0;
+        cur_chk = 0;
       }
     } else if (a0 == A_BT && t == EV_BT) {
       o.close |= bit;
       // `` : Incomplete (tokenizer/mod.rs:323): the previous byte is the opening backtick
       if (e > 0 ? ((w.bt >> (e - 1)) & 1u) != 0 : prev_byte == '`') o.bad |= bit;
       cur_esc = 0;
+      cur_chk = 0;
     }
     s = a1;
     s_pos = e;
@@ -227,6 +239,7 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
   if (s_pos < 31) s = decay(s);
   o.s_out = s;
   o.sc.esc = cur_esc;
+  o.sc.chk = cur_chk;
   o.ct = m_code & ~consumed & w.valid;
   o.in_str = m_str & w.valid;
   o.in_bt = m_bt & w.valid;
@@ -367,6 +380,8 @@ enum : uint32_t {
   R3_NUM = 7       // digit- or dot-led token of more than one byte
 };
 #define NUTDB_R3_KIND_SHIFT 14
+// flag bit of R3_ESQ / R3_EDQ records (shares the bit range of R3_NUM's dot count)
+#define R3_STR_CLEAN 8u
 
 // Rec: void operator()(uint32_t index, uint32_t start_abs, uint32_t end_abs, uint32_t flags /* kind | dots << 3 | letter << 5 */)
 // index = index of the window's first token.
@@ -383,17 +398,21 @@ NUTDB_HD void win_records3(const WinCtx3& o, const TokMasks& m, uint32_t base, c
     if (o.close & bit) {  // a literal / quoted identifier closes here
       const uint32_t opens = o.openm & (bit - 1u);
       uint32_t start;
-      bool escd;
+      bool escd, chkd;
       if (opens) {
         start = base + (uint32_t)(31 - clz32(opens)) + 1u;
         escd = (o.escd & bit) != 0;
+        chkd = (o.chkd & bit) != 0;
       } else {  // opened in an earlier window: offset and escaped flag come from the carry
         start = sc_in.open_pos + 1u;
         escd = (sc_in.esc | o.esc_first) != 0;
+        chkd = (sc_in.chk | o.chk_first) != 0;
       }
       const uint32_t kind = (o.csq & bit) ? (escd ? (uint32_t)R3_ESQ : (uint32_t)R3_RAW)
                             : (o.cdq & bit) ? (escd ? (uint32_t)R3_EDQ : (uint32_t)R3_RAW) : (uint32_t)R3_BT;
-      rec(idx, start, end, kind);
+      // (R3_STR_CLEAN: an escaped literal without a backslash-u escape unescapes without error -- literal.rs:45-102 can
+      // only reject such an escape -- so the parser may skip its validation)
+      rec(idx, start, end, kind | (chkd ? 0u : (uint32_t)R3_STR_CLEAN));
       continue;
     }
     const uint32_t incl = i >= 31 ? 0xFFFFFFFFu : ((2u << i) - 1u);
@@ -488,6 +507,7 @@ NUTDB_HD bool token_finish3(const LexTables& T, Src& src, uint32_t start, uint32
              : kind == R3_ESQ ? (uint8_t)NUTDB_TT_EscapedSQStringLiteral
              : kind == R3_EDQ ? (uint8_t)NUTDB_TT_EscapedDQStringLiteral : (uint8_t)NUTDB_TT_DelimitedIdentifier;
     r.end = end - 1u - sst;
+    if ((kind == R3_ESQ || kind == R3_EDQ) && (flags & R3_STR_CLEAN)) r.kw = 1;  // tok_kw of an escaped literal: 1 = no \u escape
   }
   return false;
 }

@@ -61,8 +61,9 @@ struct alignas(16) Lex3Shared {
 //        the tile -- written by the SCANNER (block 0), see l3_scanner.
 //   yd : tag = epoch << 2 | status; low = 1 + last statement start (status 2), or nothing (status 1: the tile has no
 //        statement start -- look further back)
-//   zd : tag = epoch << 4 | status << 2 | flags; low = offset of the last opening quote.  Status 2: flags = 1 |
-//        escaped << 1; status 1 (no literal opened in the tile): flags = its contribution to the escaped flag << 1
+//   zd : tag = epoch << 5 | status << 3 | flags; low = offset of the last opening quote.  Status 2: flags = 1 |
+//        escaped << 1 | backslash-u << 2; status 1 (no literal opened in the tile): flags = its contribution to the
+//        escaped and backslash-u flags
 struct Lex3Desc {
   unsigned long long* fn;
   unsigned long long* cA;
@@ -161,7 +162,7 @@ __device__ __forceinline__ uint4 c3_then(const uint4& a, const uint4& b) {
     r.w = b.w;
   } else {
     r.z = a.z;
-    r.w = a.w | (b.w & 2u);
+    r.w = a.w | (b.w & (2u | 8u));  // escaped flag, backslash-u flag
   }
   return r;
 }
@@ -216,6 +217,9 @@ __device__ __forceinline__ uint32_t l3_lookback_y(const Lex3Desc& desc, uint32_t
   }
   return 0u;
 }
+// carry word (bit 0 open, 1 escaped, 3 backslash-u) <-> the three descriptor flag bits
+__device__ __forceinline__ uint32_t l3_zflags(uint32_t w) { return (w & 3u) | ((w & 8u) >> 1); }
+__device__ __forceinline__ uint32_t l3_zcarry(uint32_t f) { return (f & 3u) | ((f & 4u) << 1); }
 __device__ __forceinline__ void l3_lookback_z(const Lex3Desc& desc, uint32_t epoch, uint32_t tile, uint32_t& z, uint32_t& w) {
   uint32_t p = tile, esc = 0;
   z = 0;
@@ -227,15 +231,15 @@ __device__ __forceinline__ void l3_lookback_z(const Lex3Desc& desc, uint32_t epo
     for (;;) {
       d = ld_poll_u64(desc.zd + p);
       tag = (uint32_t)(d >> 32);
-      if ((tag >> 4) == epoch && ((tag >> 2) & 3u) != 0u) break;
+      if ((tag >> 5) == epoch && ((tag >> 3) & 3u) != 0u) break;
       __nanosleep(100);
     }
-    if (((tag >> 2) & 3u) == 2u) {
+    if (((tag >> 3) & 3u) == 2u) {
       z = (uint32_t)d;
-      w = (tag & 3u) | esc;
+      w = l3_zcarry(tag & 7u) | esc;
       return;
     }
-    esc |= tag & 2u;
+    esc |= l3_zcarry(tag & 6u);
   }
   w = esc;
 }
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(L3_THREADS, L3_MINBLOCKS) k_lex3(const uint8_t
         if (lane == 0 && !published) {
           st_pub_u64(desc.cA + tile, l3_tag2(epoch, 1u) | (unsigned long long)agg.x);
           st_pub_u64(desc.yd + tile, l3_tag2(epoch, agg.y ? 2u : 1u) | agg.y);
-          st_pub_u64(desc.zd + tile, ((unsigned long long)((epoch << 4) | ((agg.w & 1u) ? 8u : 4u) | (agg.w & 3u)) << 32) | agg.z);
+          st_pub_u64(desc.zd + tile, ((unsigned long long)((epoch << 5) | ((agg.w & 1u) ? 16u : 8u) | l3_zflags(agg.w)) << 32) | agg.z);
         }
         published = true;
         return agg;
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(L3_THREADS, L3_MINBLOCKS) k_lex3(const uint8_t
           // a tile without a statement start / an opening quote passes on what it found: later walks end here
           if (!agg.y) st_pub_u64(desc.yd + tile, l3_tag2(epoch, 2u) | y_in);
           if (in_literal && !(agg.w & 1u))
-            st_pub_u64(desc.zd + tile, ((unsigned long long)((epoch << 4) | 8u | ((w_in | agg.w) & 3u)) << 32) | z_in);
+            st_pub_u64(desc.zd + tile, ((unsigned long long)((epoch << 5) | 16u | l3_zflags(w_in | agg.w)) << 32) | z_in);
           S.c_tile_pre = make_uint4(pre_count, y_in, z_in, w_in);
         }
       }
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(L3_THREADS, L3_MINBLOCKS) k_lex3(const uint8_t
         mine.x = (uint32_t)__popc(m.has) + (uint32_t)__popc(m.eofm);
         mine.y = o.last_bnd1;
         mine.z = o.sc.open_pos;
-        mine.w = (uint32_t)(o.sc.has_open != 0) | ((uint32_t)(o.sc.esc != 0) << 1);
+        mine.w = (uint32_t)(o.sc.has_open != 0) | ((uint32_t)(o.sc.esc != 0) << 1) | ((uint32_t)(o.sc.chk != 0) << 3);
         // a literal opened in an earlier window closes here: its record needs look-back (b)'s open-quote offset
         deferred = nlex3::has_carried_close(o);
       }
@@ -665,13 +669,14 @@ __global__ void __launch_bounds__(L3_THREADS, L3_MINBLOCKS) k_lex3(const uint8_t
           }
           // keep the open-literal carry for the deferred windows
           mine.z = cin.z;
-          mine.w = (mine.w & ~3u) | (cin.w & 3u);
+          mine.w = (mine.w & ~11u) | (cin.w & 11u);
         }
       }
       if (mine_now && deferred) {
         nlex2::StrCarry sc_in;
         sc_in.has_open = (uint8_t)(mine.w & 1u);
         sc_in.esc = (uint8_t)((mine.w >> 1) & 1u);
+        sc_in.chk = (uint8_t)((mine.w >> 3) & 1u);
         sc_in.open_pos = mine.z;
         nlex3::win_records3(o, m, base, sc_in, local, rec);
       }

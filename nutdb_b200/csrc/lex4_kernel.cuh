@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(L4_THREADS, L4_MINBLOCKS) k_lex4(const uint8_t
         mine.x = (uint32_t)__popc(m.has) + (uint32_t)__popc(m.eofm);
         mine.y = o.last_bnd1;
         mine.z = o.sc.open_pos;
-        mine.w = (uint32_t)(o.sc.has_open != 0) | ((uint32_t)(o.sc.esc != 0) << 1);
+        mine.w = (uint32_t)(o.sc.has_open != 0) | ((uint32_t)(o.sc.esc != 0) << 1) | ((uint32_t)(o.sc.chk != 0) << 3);
       }
       // ---------------- scan of (count, statement start, open literal) over the tile ----------------
       uint4 incl = mine;
@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(L4_THREADS, L4_MINBLOCKS) k_lex4(const uint8_t
       nlex2::StrCarry sc_in;
       sc_in.has_open = (uint8_t)(cin.w & 1u);
       sc_in.esc = (uint8_t)((cin.w >> 1) & 1u);
+      sc_in.chk = (uint8_t)((cin.w >> 3) & 1u);
       sc_in.open_pos = cin.z;
       const uint32_t local = cin.x - tile_first;
       for (uint32_t r0 = 0; r0 < tile_count; r0 += L3_RCAP) {

@@ -347,6 +347,16 @@ struct Walker {
     emit(NUTDB_TT_KeywordOrIdentifier, s, e, kw);
   }
 
+  // side byte of an escaped string literal: 1 = it holds no backslash-u escape, so unescaping it (literal.rs:45-102)
+  // cannot fail and the parser need not look at its bytes; the mask lexer computes the same bit (R3_STR_CLEAN)
+  NUTDB_HD bool no_escaped_u(uint32_t s, uint32_t e) {
+    for (uint32_t p = s; p < e; p++)
+      if (src.byte(p) == '\\') {
+        if (++p < e && src.byte(p) == 'u') return false;
+      }
+    return true;
+  }
+
   // block comment payload end: start of the star run before the closing '/', not before the body
   // (the reference keeps `end` at the last position where comment_end == 0, mod.rs:441-460)
   NUTDB_HD uint32_t bc_payload_end(uint32_t slash_pos) {
@@ -434,9 +444,11 @@ struct Walker {
       case PK_SLASH: emit(NUTDB_TT_Div, ts, pos); break;
       case PK_SQ:
       case PK_DQ:  // closed by the quote at pos-1 (we are in code context again)
-        emit(c.escaped ? (pk == PK_SQ ? NUTDB_TT_EscapedSQStringLiteral : NUTDB_TT_EscapedDQStringLiteral)
-                       : NUTDB_TT_RawStringLiteral,
-             ts + 1, pos - 1);
+        if (c.escaped)
+          emit(pk == PK_SQ ? NUTDB_TT_EscapedSQStringLiteral : NUTDB_TT_EscapedDQStringLiteral, ts + 1, pos - 1,
+               counting ? (uint8_t)0 : (uint8_t)no_escaped_u(ts + 1, pos - 1));
+        else
+          emit(NUTDB_TT_RawStringLiteral, ts + 1, pos - 1);
         break;
       default: poison(pos, NUTDB_LE_INVALID_CHAR); break;  // PK_BT/LC/BC in code context: only after a poison
     }

@@ -1665,7 +1665,7 @@ run_again:
         lo3.tim = (unsigned long long*)ctx->dbgTim.p;
         ctx->dbg_ntiles = ntiles3;
       }
-      ctx->epoch = (ctx->epoch + 1u) & 0x0FFFFFFFu;  // (the tags hold 28 bits of it)
+      ctx->epoch = (ctx->epoch + 1u) & 0x07FFFFFFu;  // (the tags hold 27 bits of it)
       if (ctx->epoch == 0u) ctx->epoch = 1u;
       // one range: the whole batch, window slots unshifted, tokens dense from 0
       const uint32_t one[8] = {0u, n, 0u, nstmt, 0u, tok_cap, 1u, 0u};

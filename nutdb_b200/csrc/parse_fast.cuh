@@ -250,13 +250,13 @@ struct FastParser {
     uint32_t u = t + 2u;
     for (;;) {
       if (n + sp + 6u > cap) return false;
-      const uint32_t ps = tok.pair_at(u) & 255u;
+      const uint32_t pu = tok.pair_at(u), ps = pu & 255u;
       uint32_t ssub;
       if (ps == NUTDB_TT_RawStringLiteral) ssub = 0;
       else if (ps == NUTDB_TT_EscapedSQStringLiteral) ssub = 1;
       else if (ps == NUTDB_TT_EscapedDQStringLiteral) ssub = 2;
       else return false;
-      if (ssub && !string_ok(u, ssub == 1 ? '\'' : '"')) return false;
+      if (ssub && (pu >> 8) != 1u && !string_ok(u, ssub == 1 ? '\'' : '"')) return false;
       CNode c;
       c.kind = NUTDB_NK_STR;
       c.sub = (uint8_t)ssub;
@@ -629,7 +629,8 @@ struct FastParser {
           }
           const uint32_t check = (hi >> 5) & 7u;
           if (check == FK_STR) {
-            if (!string_ok(t, ty == NUTDB_TT_EscapedSQStringLiteral ? '\'' : '"')) return false;
+            // (kw byte 1: the lexer saw no backslash-u escape in the literal, nothing can be rejected)
+            if (kw != 1u && !string_ok(t, ty == NUTDB_TT_EscapedSQStringLiteral ? '\'' : '"')) return false;
           } else if (check == FK_FNCALL) {  // the indexer of INDEX name f(..) must be a function call (mod.rs:923-931)
             if (cur_kind != NUTDB_NK_FNCALL) return false;
           } else if (check != FK_NONE) {

@@ -90,3 +90,36 @@ SIMPLE_SEEDS = [
     b"SELECT a FROM t LIMIT 99999999999999999999", b"SELECT a FROM t ORDER BY a ASC",
     b"select date, type, value, level from table where date = 'x'", b"select f (a) , g( b )from t",
 ]
+
+
+def escaped_literal_statements(count, seed=7):
+    """Statements built around escaped string literals: backslash-u escapes (valid, invalid, not an escape after all),
+    doubled quotes, plain escapes, literals from a few bytes to several lexer windows long -- the cases that decide the
+    lexer's side byte of an escaped literal and whether the parser has to validate it (literal.rs:45-102)."""
+    import random
+    rng = random.Random(seed)
+
+    def lit():
+        q = rng.choice("'\"")
+        parts = []
+        for _ in range(rng.choice([1, 2, 3, 5, 20, 60])):
+            r = rng.random()
+            if r < 0.15: parts.append("\\u{41}")
+            elif r < 0.25: parts.append("\\\\u")
+            elif r < 0.35: parts.append("\\" + rng.choice("ntu'\"x\\"))
+            elif r < 0.45: parts.append(q + q)
+            elif r < 0.50: parts.append("\\u{zz}")
+            elif r < 0.55: parts.append("u")
+            else: parts.append("".join(rng.choice("abcu \n;-/*") for _ in range(rng.randint(0, 40))))
+        return q + "".join(parts) + q
+
+    out = []
+    for _ in range(count):
+        k = rng.random()
+        if k < 0.5:
+            out.append("select " + ", ".join(lit() for _ in range(rng.randint(1, 4))) + " from t")
+        elif k < 0.8:
+            out.append("select a from t where b = " + lit() + " and c in (" + lit() + ")")
+        else:
+            out.append("create table t (a enum(" + ", ".join(lit() for _ in range(rng.randint(1, 3))) + "))")
+    return out

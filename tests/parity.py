@@ -1,7 +1,13 @@
 """Shared comparison of a batch result (GPU or host-emulated device code) against the oracle."""
+import re
+
 import numpy as np
 
 import oracle_lib as O
+
+TT_ESCAPED_SQ, TT_ESCAPED_DQ = 5, 6   # include/nutdb_gpu.h NUTDB_TT_Escaped{SQ,DQ}StringLiteral (token.rs ordinals)
+KW_SAMPLE = 20000                     # escaped literals whose side byte is recomputed from the text per comparison
+SIDE_BYTE = True                      # (off for the emulated round-1 warp lexer, which no kernel launches any more)
 
 
 def make_batch(stmts):
@@ -83,4 +89,18 @@ def compare_with_oracle(got, text, offs, stmts=None, check_tokens=True):
                 bad.append(f"stmt {i}: pulled token {j} differs: got ({got.tok_type[gi[k]]}, {got.tok_start[gi[k]]}, "
                            f"{got.tok_end[gi[k]]}, kw {got.tok_kw[gi[k]]}) oracle ({want.tok_type[wi[k]]}, "
                            f"{want.tok_start[wi[k]]}, {want.tok_end[wi[k]]}, kw {want.tok_kw[wi[k]]}): {sql(i)!r}")
+            # side byte of escaped literals (no oracle counterpart: the reference has no such field): 1 iff the literal
+            # holds no backslash-u escape, recomputed here by walking backslash pairs (literal.rs:59-63)
+            es = np.nonzero((want.tok_type[wi] == TT_ESCAPED_SQ) | (want.tok_type[wi] == TT_ESCAPED_DQ))[0]
+            if SIDE_BYTE and not bad and len(es):
+                if len(es) > KW_SAMPLE:
+                    es = es[np.linspace(0, len(es) - 1, KW_SAMPLE).astype(np.int64)]
+                st_of = np.searchsorted(first, es, side="right") - 1
+                for k, i in zip(es.tolist(), st_of.tolist()):
+                    lit = bytes(text[int(offs[i]) + int(want.tok_start[wi[k]]):int(offs[i]) + int(want.tok_end[wi[k]])])
+                    clean = all(m.group(1) != b"u" for m in re.finditer(rb"\\(.)", lit, re.S))
+                    if int(got.tok_kw[gi[k]]) != int(clean):
+                        bad.append(f"stmt {i}: escaped literal {lit!r}: side byte {got.tok_kw[gi[k]]}, expected {int(clean)}")
+                        if len(bad) >= 4:
+                            break
     return bad

@@ -20,6 +20,7 @@ def _default_lexer():
     E.set_lexer(3, 1024)   # the single-pass lexer with the device's warp-block size
     yield
     E.set_lexer(3, 1024)
+    P.SIDE_BYTE = True
 
 
 def check(stmts, chunk=32):
@@ -40,6 +41,7 @@ def test_corpus_and_known_vectors(chunk):
 @pytest.mark.parametrize("lexer,seg", [(3, 1024), (3, 32), (3, 96), (2, 1024), (2, 96)])
 def test_corpus_and_known_vectors_warp_lexer(lexer, seg):
     E.set_lexer(lexer, seg)
+    P.SIDE_BYTE = lexer != 2   # (lex2's token walk writes no side byte for escaped literals)
     got = check(CORPUS + APP_D + fuzz.EXTRA_SEEDS + fuzz.SIMPLE_SEEDS)
     assert (got.stmt["status"][:len(CORPUS)] == 0).all()
 
@@ -47,6 +49,7 @@ def test_corpus_and_known_vectors_warp_lexer(lexer, seg):
 @pytest.mark.parametrize("lexer,seg", [(1, 0), (2, 64), (3, 64)])
 def test_synthetic_config_other_lexers(lexer, seg):
     E.set_lexer(lexer, seg or 1024)
+    P.SIDE_BYTE = lexer != 2
     for config in (2, 3, 4):
         text, offs = W.generate(config, 96 << 10, seed=3)
         got = E.parse_batch(text, offs)
@@ -454,3 +457,13 @@ def test_config4_is_almost_entirely_table_driven():
     got = E.parse_batch(text, offs)
     assert E.fast_hits() >= 0.99 * (len(offs) - 1)
     assert not P.compare_with_oracle(got, text, offs)
+
+
+@pytest.mark.parametrize("seg", [32, 96, 1024])
+def test_escaped_literal_side_byte(seg):
+    """The lexer marks an escaped literal that holds no backslash-u escape (tok_kw = 1), and the table-driven parsers
+    skip its validation: statuses, errors and the side byte itself (parity.py) against the oracle."""
+    E.set_lexer(3, seg)
+    stmts = fuzz.escaped_literal_statements(1500, seed=seg)
+    got = check(stmts)
+    assert (got.stmt["status"] != 0).any() and (got.stmt["status"] == 0).any()

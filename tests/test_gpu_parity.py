@@ -578,3 +578,22 @@ def test_batch_near_the_two_gib_limit(ctx):
     assert np.array_equal(w_node[first_nodes:], got.pnode)
     with pytest.raises(gpu.NutdbGpuError):
         ctx.parse_batch(text[:16], np.array([0, 1 << 31], np.uint64))
+
+
+def test_escaped_literal_side_byte(ctx):
+    """tok_kw of an escaped literal: 1 iff it holds no backslash-u escape (then the parsers skip its validation) --
+    the range lexer, the look-back lexer and the exact walker agree, and statuses / errors equal the oracle's."""
+    from nutdb_b200 import gpu
+    stmts = fuzz.escaped_literal_statements(60000, seed=11)
+    got = check(ctx, stmts)
+    assert (got.stmt["status"] != 0).any() and (got.stmt["status"] == 0).any()
+    text, offs = P.make_batch(stmts)
+    c2 = gpu.Context(0)
+    try:
+        c2.force_lookback(True)
+        got2 = c2.parse_batch(text, offs)
+        assert c2.last_lookback()
+        assert not P.compare_with_oracle(got2, text, offs)
+        assert np.array_equal(got2.tok_kw, got.tok_kw)
+    finally:
+        c2.close()
