@@ -831,60 +831,122 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
 // so a deep statement needs neither a local-memory stack nor a second run.  Tokens come straight from global memory
 // (these statements are long: a lane walks its own run of the arrays, the L1 serves it).  What it declines too goes to
 // the exact automaton.
+//
+// These statements differ in length by orders of magnitude, and their lanes rarely run in step (different statements
+// are in different grammar states: 5.5 of 32 lanes active on config 4), so a warp costs close to the SUM of its lanes'
+// work and the kernel used to last as long as the one warp that drew 32 of the longest statements.  Hence:
+// (1) k_wide_order sorts every WIDE_POOL consecutive statements of the list by length and shape and cuts the sorted run
+//     into GROUPS of at most 32 statements and at most WIDE_BUDGET tokens -- a 2000-token statement gets a warp to
+//     itself, short ones still share one -- listed heavy groups first;
+// (2) k_parse_wide is PERSISTENT: its warps pull group after group from a queue and never wait for one another.
 #ifndef WIDE_THREADS
-#define WIDE_THREADS 256  // (a larger CTA sorts more equal statements into a warp: 128 -> 256 measured 6.6 -> 5.9 ms on config 4)
+#define WIDE_THREADS 256
 #endif
+#ifndef WIDE_POOL
+#define WIDE_POOL 256  // statements sorted together (a larger pool sorts more equal statements into a group)
+#endif
+#ifndef WIDE_CTAS_PER_SM
+#define WIDE_CTAS_PER_SM 5
+#endif
+#ifndef WIDE_BUDGET
+#define WIDE_BUDGET 6144u  // tokens per group (measured on config 4: 1024 -> 7.2 ms, 2048 -> 6.0, 4096 -> 4.7, 6144 / 8192 -> 4.5, 16384 -> 5.5)
+#endif
+#ifndef WIDE_HEAVY
+#define WIDE_HEAVY 512u    // a group with a statement of this many tokens is scheduled before the others
+#endif
+// counters[0] = heavy groups (listed from the front of `groups`), counters[1] = the others (listed from its back)
+__global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ nslow_dev,
+                                                          const uint8_t* __restrict__ tok_type, const NutdbStmt* __restrict__ stmt,
+                                                          uint32_t* __restrict__ order, uint2* __restrict__ groups, uint32_t group_cap,
+                                                          uint32_t* __restrict__ counters) {
+  const uint32_t nslow = *nslow_dev;
+  if (blockIdx.x * WIDE_POOL >= nslow) return;
+  __shared__ uint32_t skey[WIDE_POOL], stc[WIDE_POOL];
+  __shared__ uint2 sgrp[WIDE_POOL];
+  __shared__ uint32_t sn[2], sbase[2];
+  const uint32_t i0 = blockIdx.x * WIDE_POOL + threadIdx.x;
+  uint32_t key = 0xFFFFFFFFu, s0 = 0xFFFFFFFFu, tc0 = 0;
+  if (i0 < nslow) {
+    s0 = slow_list[i0];
+    const uint32_t tb0 = stmt[s0].tok_begin;
+    tc0 = stmt[s0].tok_count;
+    uint32_t h = 0;
+    const uint32_t m = min(tc0, 12u);
+    for (uint32_t q = 0; q < m; q++) h = h * 31u + tok_type[tb0 + q];
+    key = (min(tc0, 0xFFFFu) << 15) | (h & 0x7FFFu);
+  }
+  skey[threadIdx.x] = key;
+  __syncthreads();
+  uint32_t rank = 0;
+  for (uint32_t j = 0; j < WIDE_POOL; j++) {
+    const uint32_t kj = skey[j];
+    rank += (kj < key || (kj == key && j < threadIdx.x)) ? 1u : 0u;
+  }
+  order[blockIdx.x * WIDE_POOL + rank] = s0;  // (the tail of the last pool: 0xFFFFFFFF, sorted behind everything)
+  stc[rank] = tc0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // cut the sorted run, longest statement first: heavy groups collect at the front of sgrp, the others at its back
+    const uint32_t nv = min((uint32_t)WIDE_POOL, nslow - blockIdx.x * WIDE_POOL);
+    uint32_t nh = 0, nl = 0, hi = nv;  // the open group is [lo, hi)
+    while (hi > 0) {
+      uint32_t lo = hi - 1u, sum = stc[lo];
+      while (lo > 0 && hi - lo < 32u && sum + stc[lo - 1u] <= WIDE_BUDGET) sum += stc[--lo];
+      const uint2 g = make_uint2(blockIdx.x * WIDE_POOL + lo, hi - lo);
+      if (stc[hi - 1u] >= WIDE_HEAVY) sgrp[nh++] = g;
+      else sgrp[WIDE_POOL - 1u - nl++] = g;
+      hi = lo;
+    }
+    sn[0] = nh;
+    sn[1] = nl;
+    sbase[0] = nh ? atomicAdd(counters, nh) : 0u;
+    sbase[1] = nl ? atomicAdd(counters + 1, nl) : 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x < sn[0]) groups[sbase[0] + threadIdx.x] = sgrp[threadIdx.x];
+  if (threadIdx.x < sn[1]) groups[group_cap - 1u - (sbase[1] + threadIdx.x)] = sgrp[WIDE_POOL - 1u - threadIdx.x];
+}
+
 __global__ void __launch_bounds__(WIDE_THREADS) k_parse_wide(
-    const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint32_t* __restrict__ slow_list,
-    const uint32_t* __restrict__ nslow_dev, const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start,
+    const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint32_t* __restrict__ order,
+    const uint2* __restrict__ groups, uint32_t group_cap, const uint32_t* __restrict__ counters,
+    const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start,
     const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw, const npar::FastTables* __restrict__ gF,
     NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch, uint32_t* __restrict__ slow2_list,
-    uint32_t* __restrict__ slow2_count, uint32_t nstmt, const uint32_t* __restrict__ punt) {
-  const uint32_t nslow = *nslow_dev;
-  if (blockIdx.x * WIDE_THREADS >= nslow) return;
+    uint32_t* __restrict__ slow2_count, uint32_t nstmt, const uint32_t* __restrict__ punt, uint32_t* __restrict__ queue) {
+  const uint32_t nheavy = counters[0], ngroups = nheavy + counters[1];
+  if (blockIdx.x * (WIDE_THREADS / 32u) >= ngroups) return;  // (fewer groups than resident warps: the rest of the grid has nothing to pull)
   __shared__ npar::FastTables FT;
-  __shared__ uint32_t skey[WIDE_THREADS], sorder[WIDE_THREADS];
   {
     const uint32_t* a = reinterpret_cast<const uint32_t*>(gF);
     uint32_t* b = reinterpret_cast<uint32_t*>(&FT);
     for (uint32_t i = threadIdx.x; i < sizeof(npar::FastTables) / 4; i += WIDE_THREADS) b[i] = a[i];
   }
-  {  // same shapes into the same warp (see k_parse)
-    const uint32_t i0 = blockIdx.x * WIDE_THREADS + threadIdx.x;
-    uint32_t key = 0xFFFFFFFFu;
-    if (i0 < nslow) {
-      const uint32_t s0 = slow_list[i0];
-      const uint32_t tb0 = stmt[s0].tok_begin, tc0 = stmt[s0].tok_count;
-      uint32_t h = 0;
-      const uint32_t m = min(tc0, 12u);
-      for (uint32_t q = 0; q < m; q++) h = h * 31u + tok_type[tb0 + q];
-      key = (min(tc0, 0xFFFFu) << 15) | (h & 0x7FFFu);
-    }
-    skey[threadIdx.x] = key;
-    __syncthreads();
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < WIDE_THREADS; j++) {
-      const uint32_t kj = skey[j];
-      rank += (kj < key || (kj == key && j < threadIdx.x)) ? 1u : 0u;
-    }
-    sorder[rank] = threadIdx.x;
-  }
   __syncthreads();
-  const uint32_t i = blockIdx.x * WIDE_THREADS + sorder[threadIdx.x];
-  if (i >= nslow) return;
-  const uint32_t s = slow_list[i];
-  const uint32_t o = off32[s], len = off32[s + 1] - o;
-  const uint32_t tb = stmt[s].tok_begin, tc = stmt[s].tok_count;
-  DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
-  uint2* range = scratch + node_slot(s, tb, nstmt, punt);
-  const uint32_t cap = tc + NODE_SLACK;
-  DNodes nd{range, cap};
-  DText tx{text + o, len};
-  npar::ParseResult res;
   static_assert(sizeof(npar::FastStackEntry) == sizeof(uint2), "the wide parser's stack shares the node range");
-  npar::FastParser<DTok, DNodes, DText, true> f(&FT, tk, nd, tx, reinterpret_cast<npar::FastStackEntry*>(range) + (cap - 1), -1);
-  if (f.try_parse(res)) store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
-  else slow2_list[atomicAdd(slow2_count, 1u)] = s;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;) {
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(queue, 1u);
+    q = __shfl_sync(0xFFFFFFFFu, q, 0);
+    if (q >= ngroups) break;
+    const uint2 g = q < nheavy ? groups[q] : groups[group_cap - 1u - (q - nheavy)];
+    if (lane < g.y) {
+      const uint32_t s = order[g.x + lane];
+      const uint32_t o = off32[s], len = off32[s + 1] - o;
+      const uint32_t tb = stmt[s].tok_begin, tc = stmt[s].tok_count;
+      DTok tk{tok_type + tb, tok_start + tb, tok_end + tb, tok_kw + tb, tc};
+      uint2* range = scratch + node_slot(s, tb, nstmt, punt);
+      const uint32_t cap = tc + NODE_SLACK;
+      DNodes nd{range, cap};
+      DText tx{text + o, len};
+      npar::ParseResult res;
+      npar::FastParser<DTok, DNodes, DText, true> f(&FT, tk, nd, tx, reinterpret_cast<npar::FastStackEntry*>(range) + (cap - 1), -1);
+      if (f.try_parse(res)) store_result(res, s, tb, tc, RETRY_NONE, tx, range, stmt);
+      else slow2_list[atomicAdd(slow2_count, 1u)] = s;
+    }
+    __syncwarp();
+  }
 }
 
 // Pass 2, one thread per statement of the slow list: the exact bytecode automaton (parse_core.cuh)
@@ -1191,7 +1253,7 @@ struct NutdbCtx {
   DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, slowList2, wstmt, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
+      tileS, tilePrefS, nodes, errs, small, slowList, slowList2, wideOrder, wideGroups, wstmt, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry, hSplit;
   float ms[5] = {0, 0, 0, 0, 0};
@@ -1328,7 +1390,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->slowList2, &c->wstmt, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
+                 &c->small, &c->slowList, &c->slowList2, &c->wideOrder, &c->wideGroups, &c->wstmt, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
                  &c->splitTile, &c->splitPref, &c->splitOff};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
@@ -1730,12 +1792,21 @@ run_again:
                                (uint32_t*)ctx->slowList.p, dS + 2, (const uint32_t*)ctx->puntFlag.p, lex_only ? 1 : 0,
                                native_lex ? tok_cap : (uint32_t)min((size_t)0xFFFFFFF0u, (size_t)ntok + 16), ctx->dFast,
                                native_lex ? (use_lookback ? dS + 16 : dS + 21) : nullptr, native_lex ? dS + 10 : nullptr, dS));
-    if (!lex_only)
-      LAUNCH("k_parse_wide", k_parse_wide<<<(nstmt + WIDE_THREADS - 1) / WIDE_THREADS, WIDE_THREADS, 0, st>>>(
-                                 dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList.p, dS + 2,
+    if (!lex_only) {
+      const uint32_t gcap = nstmt + 1u;  // (a group holds at least one statement)
+      ENSURE_DEV(wideOrder, 4 * ((size_t)nstmt + WIDE_POOL));
+      ENSURE_DEV(wideGroups, 8 * (size_t)gcap);
+      LAUNCH("k_wide_order", k_wide_order<<<(nstmt + WIDE_POOL - 1) / WIDE_POOL, WIDE_POOL, 0, st>>>(
+                                 (const uint32_t*)ctx->slowList.p, dS + 2, (const uint8_t*)ctx->tokType.p,
+                                 (const NutdbStmt*)ctx->stmt.p, (uint32_t*)ctx->wideOrder.p, (uint2*)ctx->wideGroups.p, gcap, dS + 30));
+      const uint32_t wgrid = (uint32_t)min(((size_t)nstmt + WIDE_THREADS / 32 - 1) / (WIDE_THREADS / 32), (size_t)ctx->sm_count * WIDE_CTAS_PER_SM);
+      LAUNCH("k_parse_wide", k_parse_wide<<<wgrid, WIDE_THREADS, 0, st>>>(
+                                 dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->wideOrder.p,
+                                 (const uint2*)ctx->wideGroups.p, gcap, dS + 30,
                                  (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                  (const uint8_t*)ctx->tokKw.p, ctx->dFast, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
-                                 (uint32_t*)ctx->slowList2.p, dS + 27, nstmt, (const uint32_t*)ctx->puntFlag.p));
+                                 (uint32_t*)ctx->slowList2.p, dS + 27, nstmt, (const uint32_t*)ctx->puntFlag.p, dS + 29));
+    }
     if (!lex_only)
       LAUNCH("k_parse", k_parse<<<(nstmt + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
                             dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->slowList2.p, 0u,
