@@ -79,7 +79,7 @@ inline void build_lex2_tables(Lex2Tables& T) {
 // raw class masks of one 32-byte window (bit i = byte base+i); bytes at or beyond the batch end are 0
 struct Win {
   uint32_t sq, dq, bt, nl, bs, dash, slash, star, L, D, DOT, OP, P, WS, IE, NE;
-  uint32_t u = 0;  // bytes 'u' (lex3: an escaped one inside a literal means a backslash-u escape the parser must validate)
+  uint32_t u;      // bytes 'u' (lex3 only, 0 in the three-pass lexer): an escaped one inside a literal is a backslash-u escape
   uint32_t bnd;    // a statement starts at this byte; also set at position n (virtual end) if inside the window
   uint32_t valid;  // bytes that exist (< n)
 };
@@ -142,7 +142,7 @@ NUTDB_HD uint8_t esc_carry_out(uint32_t bs, uint8_t carry_in) {
 
 struct Events {
   uint32_t quotes, dd, slst, stsl, all, own;
-  uint32_t uesc = 0;  // escaped 'u' bytes
+  uint32_t uesc;  // escaped 'u' bytes
 };
 NUTDB_HD Events make_events(const Win& w, uint32_t esc, uint8_t prev) {
   Events e;

@@ -91,7 +91,7 @@ template <bool All>
 __device__ __forceinline__ void build_masks(const Lex2Shared& S, const Tile2Src& src, uint32_t blk, uint32_t n, int lane,
                                             nlex2::Win& w) {
   const uint32_t full = 0xFFFFFFFFu;
-  w.sq = w.dq = w.bt = w.nl = w.bs = w.dash = w.slash = w.star = w.L = w.D = w.DOT = w.OP = w.P = w.WS = w.IE = w.NE = 0u;
+  w.sq = w.dq = w.bt = w.nl = w.bs = w.dash = w.slash = w.star = w.L = w.D = w.DOT = w.OP = w.P = w.WS = w.IE = w.NE = w.u = 0u;
 #pragma unroll 4
   for (int jj = 0; jj < 32; jj++) {
     const uint32_t pos = blk + 32u * (uint32_t)jj + (uint32_t)lane;
@@ -174,6 +174,7 @@ __device__ __forceinline__ void build_masks_transpose(const Lex2Shared& S, uint3
   w.WS = A[13] & valid;
   w.IE = A[14] & valid;
   w.NE = A[15] & valid;
+  w.u = 0u;
 }
 
 // class masks of every window, computed once by k_lex2_fn: 14 arrays of nwin words (structure of arrays)
@@ -213,6 +214,7 @@ __device__ __forceinline__ void load_masks(const uint32_t* __restrict__ g, size_
   w.WS = g[13 * stride + win];
   w.IE = g[14 * stride + win];
   w.NE = g[15 * stride + win];
+  w.u = 0u;
 }
 
 struct WinSetup {

@@ -130,14 +130,13 @@ struct WinCtx3 {
   uint32_t in_str = 0;    // bytes lexed inside '..' / ".."
   uint32_t in_bt = 0;     // bytes lexed inside `..`
   uint32_t close = 0, openm = 0, escd = 0;
-  uint32_t chkd = 0;      // closes of literals opened here that hold a backslash-u escape
+  uint32_t ustr = 0;      // escaped 'u' bytes inside '..' / "..": a literal that holds one has a backslash-u escape
   uint32_t csq = 0, cdq = 0;  // closes by quote character (the rest of `close` are backticks)
   uint32_t bad = 0;       // the statement containing this byte needs the exact path
   uint32_t bad_prev = 0;  // the statement ENDING right before this (statement start) byte needs the exact path
   uint32_t escm = 0;
   uint8_t s_out = A_C;
   uint8_t esc_first = 0;  // this window's escaped-flag contribution before a carried close
-  uint8_t chk_first = 0;  // ... and its backslash-u contribution
   StrCarry sc;
   uint32_t last_bnd1 = 0;  // 1 + absolute offset of the last statement start in the window, 0 if none
 };
@@ -154,7 +153,7 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
   int s_pos = -1, p0 = 0;
   uint32_t m_code = 0, m_str = 0, m_bt = 0;
   bool open_local = false;
-  uint8_t cur_esc = 0, cur_chk = 0;
+  uint8_t cur_esc = 0;
   auto assign = [&](int lo, int hi) {
     if (hi < lo) return;
     const uint32_t r = bits_range(lo, hi);
@@ -162,7 +161,6 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
     else if (s == A_SQ || s == A_DQ) {
       m_str |= r;
       if (w.bs & r) cur_esc = 1;
-      if (ev.uesc & r) cur_chk = 1;
     } else if (s == A_BT) m_bt |= r;
   };
   while (todo) {
@@ -177,7 +175,6 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
       s_pos = -100;
       reopen_at = -1;
       cur_esc = 0;
-      cur_chk = 0;
       open_local = true;  // nothing can be carried into a new statement
       o.last_bnd1 = base + (uint32_t)e + 1u;
       p0 = e;
@@ -195,7 +192,6 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
         } else {
           open_local = true;
           cur_esc = 0;
-          cur_chk = 0;
           o.openm |= bit;
           o.sc.has_open = 1;
           o.sc.open_pos = base + (uint32_t)e;
@@ -218,19 +214,13 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
           if (open_local) o.escd |= bit;
           else o.esc_first = 1;
         }
-        if (cur_chk) {
-          if (open_local) o.chkd |= bit;
-          else o.chk_first = 1;
-        }
         cur_esc = 0;
-        cur_chk = 0;
       }
     } else if (a0 == A_BT && t == EV_BT) {
       o.close |= bit;
       // `` : Incomplete (tokenizer/mod.rs:323): the previous byte is the opening backtick
       if (e > 0 ? ((w.bt >> (e - 1)) & 1u) != 0 : prev_byte == '`') o.bad |= bit;
       cur_esc = 0;
-      cur_chk = 0;
     }
     s = a1;
     s_pos = e;
@@ -239,9 +229,12 @@ NUTDB_HD void ctx_window3(const Win& w, const Events& ev, uint32_t base, const N
   if (s_pos < 31) s = decay(s);
   o.s_out = s;
   o.sc.esc = cur_esc;
-  o.sc.chk = cur_chk;
   o.ct = m_code & ~consumed & w.valid;
   o.in_str = m_str & w.valid;
+  // backslash-u escapes, by mask: of the literal still open at the end (everything behind its opening quote, or the
+  // whole window if it was open on entry; what a literal that closed here leaves in the carry is never used)
+  o.ustr = ev.uesc & o.in_str;
+  o.sc.chk = (o.ustr & (o.sc.has_open ? ~((2u << (o.sc.open_pos - base)) - 1u) : 0xFFFFFFFFu)) != 0u;
   o.in_bt = m_bt & w.valid;
 }
 // the first literal that closes in the window was opened in an earlier one
@@ -402,11 +395,11 @@ NUTDB_HD void win_records3(const WinCtx3& o, const TokMasks& m, uint32_t base, c
       if (opens) {
         start = base + (uint32_t)(31 - clz32(opens)) + 1u;
         escd = (o.escd & bit) != 0;
-        chkd = (o.chkd & bit) != 0;
+        chkd = (o.ustr & (bit - 1u) & ~((2u << (31 - clz32(opens))) - 1u)) != 0;  // between its two quotes
       } else {  // opened in an earlier window: offset and escaped flag come from the carry
         start = sc_in.open_pos + 1u;
         escd = (sc_in.esc | o.esc_first) != 0;
-        chkd = (sc_in.chk | o.chk_first) != 0;
+        chkd = sc_in.chk != 0 || (o.ustr & (bit - 1u)) != 0;
       }
       const uint32_t kind = (o.csq & bit) ? (escd ? (uint32_t)R3_ESQ : (uint32_t)R3_RAW)
                             : (o.cdq & bit) ? (escd ? (uint32_t)R3_EDQ : (uint32_t)R3_RAW) : (uint32_t)R3_BT;

@@ -860,51 +860,54 @@ __global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __rest
                                                           uint32_t* __restrict__ order, uint2* __restrict__ groups, uint32_t group_cap,
                                                           uint32_t* __restrict__ counters) {
   const uint32_t nslow = *nslow_dev;
-  if (blockIdx.x * WIDE_POOL >= nslow) return;
   __shared__ uint32_t skey[WIDE_POOL], stc[WIDE_POOL];
   __shared__ uint2 sgrp[WIDE_POOL];
   __shared__ uint32_t sn[2], sbase[2];
-  const uint32_t i0 = blockIdx.x * WIDE_POOL + threadIdx.x;
-  uint32_t key = 0xFFFFFFFFu, s0 = 0xFFFFFFFFu, tc0 = 0;
-  if (i0 < nslow) {
-    s0 = slow_list[i0];
-    const uint32_t tb0 = stmt[s0].tok_begin;
-    tc0 = stmt[s0].tok_count;
-    uint32_t h = 0;
-    const uint32_t m = min(tc0, 12u);
-    for (uint32_t q = 0; q < m; q++) h = h * 31u + tok_type[tb0 + q];
-    key = (min(tc0, 0xFFFFu) << 15) | (h & 0x7FFFu);
-  }
-  skey[threadIdx.x] = key;
-  __syncthreads();
-  uint32_t rank = 0;
-  for (uint32_t j = 0; j < WIDE_POOL; j++) {
-    const uint32_t kj = skey[j];
-    rank += (kj < key || (kj == key && j < threadIdx.x)) ? 1u : 0u;
-  }
-  order[blockIdx.x * WIDE_POOL + rank] = s0;  // (the tail of the last pool: 0xFFFFFFFF, sorted behind everything)
-  stc[rank] = tc0;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // cut the sorted run, longest statement first: heavy groups collect at the front of sgrp, the others at its back
-    const uint32_t nv = min((uint32_t)WIDE_POOL, nslow - blockIdx.x * WIDE_POOL);
-    uint32_t nh = 0, nl = 0, hi = nv;  // the open group is [lo, hi)
-    while (hi > 0) {
-      uint32_t lo = hi - 1u, sum = stc[lo];
-      while (lo > 0 && hi - lo < 32u && sum + stc[lo - 1u] <= WIDE_BUDGET) sum += stc[--lo];
-      const uint2 g = make_uint2(blockIdx.x * WIDE_POOL + lo, hi - lo);
-      if (stc[hi - 1u] >= WIDE_HEAVY) sgrp[nh++] = g;
-      else sgrp[WIDE_POOL - 1u - nl++] = g;
-      hi = lo;
+  // (a grid-stride loop over the pools: the list's length is only known on the device, and it is usually short)
+  for (uint32_t pool = blockIdx.x; (uint64_t)pool * WIDE_POOL < nslow; pool += gridDim.x) {
+    const uint32_t i0 = pool * WIDE_POOL + threadIdx.x;
+    uint32_t key = 0xFFFFFFFFu, s0 = 0xFFFFFFFFu, tc0 = 0;
+    if (i0 < nslow) {
+      s0 = slow_list[i0];
+      const uint32_t tb0 = stmt[s0].tok_begin;
+      tc0 = stmt[s0].tok_count;
+      uint32_t h = 0;
+      const uint32_t m = min(tc0, 12u);
+      for (uint32_t q = 0; q < m; q++) h = h * 31u + tok_type[tb0 + q];
+      key = (min(tc0, 0xFFFFu) << 15) | (h & 0x7FFFu);
     }
-    sn[0] = nh;
-    sn[1] = nl;
-    sbase[0] = nh ? atomicAdd(counters, nh) : 0u;
-    sbase[1] = nl ? atomicAdd(counters + 1, nl) : 0u;
+    skey[threadIdx.x] = key;
+    __syncthreads();
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < WIDE_POOL; j++) {
+      const uint32_t kj = skey[j];
+      rank += (kj < key || (kj == key && j < threadIdx.x)) ? 1u : 0u;
+    }
+    order[pool * WIDE_POOL + rank] = s0;  // (the tail of the last pool: 0xFFFFFFFF, sorted behind everything)
+    stc[rank] = tc0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // cut the sorted run, longest statement first: heavy groups collect at the front of sgrp, the others at its back
+      const uint32_t nv = min((uint32_t)WIDE_POOL, nslow - pool * WIDE_POOL);
+      uint32_t nh = 0, nl = 0, hi = nv;  // the open group is [lo, hi)
+      while (hi > 0) {
+        uint32_t lo = hi - 1u, sum = stc[lo];
+        while (lo > 0 && hi - lo < 32u && sum + stc[lo - 1u] <= WIDE_BUDGET) sum += stc[--lo];
+        const uint2 g = make_uint2(pool * WIDE_POOL + lo, hi - lo);
+        if (stc[hi - 1u] >= WIDE_HEAVY) sgrp[nh++] = g;
+        else sgrp[WIDE_POOL - 1u - nl++] = g;
+        hi = lo;
+      }
+      sn[0] = nh;
+      sn[1] = nl;
+      sbase[0] = nh ? atomicAdd(counters, nh) : 0u;
+      sbase[1] = nl ? atomicAdd(counters + 1, nl) : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x < sn[0]) groups[sbase[0] + threadIdx.x] = sgrp[threadIdx.x];
+    if (threadIdx.x < sn[1]) groups[group_cap - 1u - (sbase[1] + threadIdx.x)] = sgrp[WIDE_POOL - 1u - threadIdx.x];
+    __syncthreads();  // (the shared arrays are reused by the next pool)
   }
-  __syncthreads();
-  if (threadIdx.x < sn[0]) groups[sbase[0] + threadIdx.x] = sgrp[threadIdx.x];
-  if (threadIdx.x < sn[1]) groups[group_cap - 1u - (sbase[1] + threadIdx.x)] = sgrp[WIDE_POOL - 1u - threadIdx.x];
 }
 
 __global__ void __launch_bounds__(WIDE_THREADS) k_parse_wide(
@@ -1796,7 +1799,7 @@ run_again:
       const uint32_t gcap = nstmt + 1u;  // (a group holds at least one statement)
       ENSURE_DEV(wideOrder, 4 * ((size_t)nstmt + WIDE_POOL));
       ENSURE_DEV(wideGroups, 8 * (size_t)gcap);
-      LAUNCH("k_wide_order", k_wide_order<<<(nstmt + WIDE_POOL - 1) / WIDE_POOL, WIDE_POOL, 0, st>>>(
+      LAUNCH("k_wide_order", k_wide_order<<<(uint32_t)min(((size_t)nstmt + WIDE_POOL - 1) / WIDE_POOL, (size_t)ctx->sm_count * 8), WIDE_POOL, 0, st>>>(
                                  (const uint32_t*)ctx->slowList.p, dS + 2, (const uint8_t*)ctx->tokType.p,
                                  (const NutdbStmt*)ctx->stmt.p, (uint32_t*)ctx->wideOrder.p, (uint2*)ctx->wideGroups.p, gcap, dS + 30));
       const uint32_t wgrid = (uint32_t)min(((size_t)nstmt + WIDE_THREADS / 32 - 1) / (WIDE_THREADS / 32), (size_t)ctx->sm_count * WIDE_CTAS_PER_SM);
