@@ -206,18 +206,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const typename Op::
   typedef typename Op::T T;
   __shared__ T ws[32];
   if (n_dev) n = min(n, *n_dev);  // the number of entries is only known on the device
-  const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-  const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
-  T f = Op::identity();
-  for (uint32_t i = lo; i < hi; i++) f = Op::then(f, in[i]);
-  T incl, total;
-  T g = block_scan<Op>(f, ws, incl, total);
-  for (uint32_t i = lo; i < hi; i++) {
-    T x = in[i];
-    out[i] = g;
-    g = Op::then(g, x);
+  // chunks of 4 * SCAN_THREADS entries, four consecutive ones per thread: the loads of a warp are one contiguous run
+  // (a thread walking its own n / SCAN_THREADS entries touched a cache line of its own per step: 0.1 ms for 48 K entries)
+  T carry = Op::identity();
+  for (uint32_t base = 0; base < n; base += 4u * SCAN_THREADS) {
+    const uint32_t i0 = base + 4u * threadIdx.x;
+    T v[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) v[k] = i0 + k < n ? in[i0 + k] : Op::identity();
+    T incl, total;
+    T g = Op::then(carry, block_scan<Op>(Op::then(Op::then(v[0], v[1]), Op::then(v[2], v[3])), ws, incl, total));
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) {
+      if (i0 + k < n) out[i0 + k] = g;
+      g = Op::then(g, v[k]);
+    }
+    carry = Op::then(carry, total);
   }
-  if (threadIdx.x == 0 && total_out) *total_out = total;
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
 // The same scans in two grid-wide passes for long inputs (one entry per 8 KB tile: 131K entries per GiB): a
