@@ -891,14 +891,23 @@ __global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __rest
     }
     order[pool * WIDE_POOL + rank] = s0;  // (the tail of the last pool: 0xFFFFFFFF, sorted behind everything)
     stc[rank] = tc0;
+    __syncthreads();  // (everyone has read skey)
+    skey[rank] = key;
     __syncthreads();
     if (threadIdx.x == 0) {
       // cut the sorted run, longest statement first: heavy groups collect at the front of sgrp, the others at its back
       const uint32_t nv = min((uint32_t)WIDE_POOL, nslow - pool * WIDE_POOL);
       uint32_t nh = 0, nl = 0, hi = nv;  // the open group is [lo, hi)
       while (hi > 0) {
+        // (statements of one shape -- same length, same leading token types: a log repeats its templates -- run in
+        // step and cost the warp what one of them costs)
         uint32_t lo = hi - 1u, sum = stc[lo];
-        while (lo > 0 && hi - lo < 32u && sum + stc[lo - 1u] <= WIDE_BUDGET) sum += stc[--lo];
+        while (lo > 0 && hi - lo < 32u) {
+          const uint32_t add = skey[lo - 1u] == skey[lo] ? 0u : stc[lo - 1u];
+          if (sum + add > WIDE_BUDGET) break;
+          sum += add;
+          lo--;
+        }
         const uint2 g = make_uint2(pool * WIDE_POOL + lo, hi - lo);
         if (stc[hi - 1u] >= WIDE_HEAVY) sgrp[nh++] = g;
         else sgrp[WIDE_POOL - 1u - nl++] = g;
