@@ -894,29 +894,39 @@ __global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __rest
     __syncthreads();  // (everyone has read skey)
     skey[rank] = key;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      // cut the sorted run, longest statement first: heavy groups collect at the front of sgrp, the others at its back
+    if (threadIdx.x < 32u) {
+      // Cut the sorted run, longest statement first: heavy groups collect at the front of sgrp, the others at its back.
+      // Warp 0, one group per turn: lane l looks at the l-th statement below the open end, a warp scan gives the
+      // budget used up to it (statements of one shape -- same length, same leading token types: a log repeats its
+      // templates -- run in step and cost the warp what one of them costs), the first lane over the budget ends the group.
+      const uint32_t lane = threadIdx.x;
       const uint32_t nv = min((uint32_t)WIDE_POOL, nslow - pool * WIDE_POOL);
-      uint32_t nh = 0, nl = 0, hi = nv;  // the open group is [lo, hi)
+      uint32_t nh = 0, nl = 0, hi = nv;
       while (hi > 0) {
-        // (statements of one shape -- same length, same leading token types: a log repeats its templates -- run in
-        // step and cost the warp what one of them costs)
-        uint32_t lo = hi - 1u, sum = stc[lo];
-        while (lo > 0 && hi - lo < 32u) {
-          const uint32_t add = skey[lo - 1u] == skey[lo] ? 0u : stc[lo - 1u];
-          if (sum + add > WIDE_BUDGET) break;
-          sum += add;
-          lo--;
+        const bool in = lane < hi;
+        const uint32_t e = hi - 1u - lane;
+        uint32_t pre = 0;
+        if (in) pre = (lane == 0u || skey[e] != skey[e + 1u]) ? stc[e] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, pre, d);
+          if ((int)lane >= d) pre += up;
         }
-        const uint2 g = make_uint2(pool * WIDE_POOL + lo, hi - lo);
-        if (stc[hi - 1u] >= WIDE_HEAVY) sgrp[nh++] = g;
-        else sgrp[WIDE_POOL - 1u - nl++] = g;
+        const uint32_t ok = __ballot_sync(0xFFFFFFFFu, in && (lane == 0u || pre <= WIDE_BUDGET));
+        const uint32_t cnt = ok == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~ok) - 1u;  // (pre ascends: `ok` is a run of low bits)
+        const uint32_t lo = hi - cnt;
+        const bool heavy = stc[hi - 1u] >= WIDE_HEAVY;
+        if (lane == 0u) sgrp[heavy ? nh : WIDE_POOL - 1u - nl] = make_uint2(pool * WIDE_POOL + lo, cnt);
+        if (heavy) nh++;
+        else nl++;
         hi = lo;
       }
-      sn[0] = nh;
-      sn[1] = nl;
-      sbase[0] = nh ? atomicAdd(counters, nh) : 0u;
-      sbase[1] = nl ? atomicAdd(counters + 1, nl) : 0u;
+      if (lane == 0u) {
+        sn[0] = nh;
+        sn[1] = nl;
+        sbase[0] = nh ? atomicAdd(counters, nh) : 0u;
+        sbase[1] = nl ? atomicAdd(counters + 1, nl) : 0u;
+      }
     }
     __syncthreads();
     if (threadIdx.x < sn[0]) groups[sbase[0] + threadIdx.x] = sgrp[threadIdx.x];
