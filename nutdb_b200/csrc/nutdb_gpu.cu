@@ -11,7 +11,8 @@
 //                   one token stream with look-back scans, the fallback for a statement too long to cut around.)
 //   k_punt_list, k_lex_exact<0/1>   statements the mask lexer flagged: the exact sequential walker, one thread each
 //   k_parse_fast    one thread per statement: table-driven operator-precedence parser, stack in shared memory
-//   k_parse_wide    the same parser for what it declined: stack in the statement's node range, wider grammar, folding
+//   k_wide_order, k_parse_wide   the same parser for what it declined: stack in the statement's node range, wider
+//                   grammar, folding; persistent warps pull groups of statements cut by a token budget
 //   k_parse         what both declined: the bytecode pushdown automaton (whole grammar, every error, pull order)
 //   k_parse_retry   automaton statements that overflowed its local stack (stacks in global memory)
 //   k_stmt_sums, k_scan_tiles, k_finalize   dense 32-bit wire nodes / 8-byte wire statement records / error records
