@@ -861,11 +861,13 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
 #ifndef WIDE_HEAVY
 #define WIDE_HEAVY 512u    // a group with a statement of this many tokens is scheduled before the others
 #endif
-// counters[0] = heavy groups (listed from the front of `groups`), counters[1] = the others (listed from its back)
+// counters[0] = heavy groups (listed from the front of `groups`), counters[1] = the others (listed from its back, the
+// groups of one pool next to each other: `pools` says where)
 __global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __restrict__ slow_list, const uint32_t* __restrict__ nslow_dev,
                                                           const uint8_t* __restrict__ tok_type, const NutdbStmt* __restrict__ stmt,
                                                           uint32_t* __restrict__ order, uint2* __restrict__ groups, uint32_t group_cap,
-                                                          uint32_t* __restrict__ counters) {
+                                                          uint32_t* __restrict__ counters, uint2* __restrict__ pools,
+                                                          uint32_t* __restrict__ pool_count) {
   const uint32_t nslow = *nslow_dev;
   __shared__ uint32_t skey[WIDE_POOL], stc[WIDE_POOL];
   __shared__ uint2 sgrp[WIDE_POOL];
@@ -927,6 +929,7 @@ __global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __rest
         sn[1] = nl;
         sbase[0] = nh ? atomicAdd(counters, nh) : 0u;
         sbase[1] = nl ? atomicAdd(counters + 1, nl) : 0u;
+        if (nl) pools[atomicAdd(pool_count, 1u)] = make_uint2(sbase[1], nl);  // this pool's light groups: first, count
       }
     }
     __syncthreads();
@@ -939,27 +942,74 @@ __global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __rest
 __global__ void __launch_bounds__(WIDE_THREADS) k_parse_wide(
     const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint32_t* __restrict__ order,
     const uint2* __restrict__ groups, uint32_t group_cap, const uint32_t* __restrict__ counters,
+    const uint2* __restrict__ pools, const uint32_t* __restrict__ pool_count,
     const uint8_t* __restrict__ tok_type, const uint32_t* __restrict__ tok_start,
     const uint32_t* __restrict__ tok_end, const uint8_t* __restrict__ tok_kw, const npar::FastTables* __restrict__ gF,
     NutdbStmt* __restrict__ stmt, uint2* __restrict__ scratch, uint32_t* __restrict__ slow2_list,
-    uint32_t* __restrict__ slow2_count, uint32_t nstmt, const uint32_t* __restrict__ punt, uint32_t* __restrict__ queue) {
-  const uint32_t nheavy = counters[0], ngroups = nheavy + counters[1];
+    uint32_t* __restrict__ slow2_count, uint32_t nstmt, const uint32_t* __restrict__ punt, uint32_t* __restrict__ queue,
+    uint32_t* __restrict__ pool_queue) {
+  const uint32_t nheavy = counters[0], ngroups = nheavy + counters[1], npools = *pool_count;
   if (blockIdx.x * (WIDE_THREADS / 32u) >= ngroups) return;  // (fewer groups than resident warps: the rest of the grid has nothing to pull)
   __shared__ npar::FastTables FT;
+  // the light groups: pool (index into `pools`) << 32 | next group of it; POOL_NONE before the first, POOL_DONE at the end
+  __shared__ unsigned long long pool_state;
+  __shared__ uint32_t pool_lock;
+  constexpr uint32_t POOL_NONE = 0xFFFFFFFEu, POOL_DONE = 0xFFFFFFFFu;
   {
     const uint32_t* a = reinterpret_cast<const uint32_t*>(gF);
     uint32_t* b = reinterpret_cast<uint32_t*>(&FT);
     for (uint32_t i = threadIdx.x; i < sizeof(npar::FastTables) / 4; i += WIDE_THREADS) b[i] = a[i];
+    if (threadIdx.x == 0) {
+      pool_state = (unsigned long long)POOL_NONE << 32;
+      pool_lock = 0u;
+    }
   }
   __syncthreads();
   static_assert(sizeof(npar::FastStackEntry) == sizeof(uint2), "the wide parser's stack shares the node range");
   const uint32_t lane = threadIdx.x & 31u;
+  bool heavy_phase = true;
   for (;;) {
-    uint32_t q = 0;
-    if (lane == 0) q = atomicAdd(queue, 1u);
-    q = __shfl_sync(0xFFFFFFFFu, q, 0);
-    if (q >= ngroups) break;
-    const uint2 g = q < nheavy ? groups[q] : groups[group_cap - 1u - (q - nheavy)];
+    // ---- the next group: heavy ones from the global queue, one per trip (they decide when the kernel ends); then the
+    // light ones POOL-wise per CTA -- the 256 statements of a pool are neighbours in every array (offsets, token
+    // arrays, node ranges share cache lines across statement boundaries), so the CTA's warps work through one pool's
+    // groups together.  No barrier: a warp that finds the pool used up fetches the next one under a lock while the
+    // others retry; warps still busy with a group of the old pool simply finish it.
+    uint32_t gi = 0xFFFFFFFFu;  // index into `groups`
+    if (lane == 0) {
+      if (heavy_phase) {
+        const uint32_t q = atomicAdd(queue, 1u);
+        if (q < nheavy) gi = q;
+      }
+      if (gi == 0xFFFFFFFFu) {
+        for (;;) {
+          const unsigned long long old = atomicAdd(&pool_state, 1ull);
+          const uint32_t p = (uint32_t)(old >> 32), idx = (uint32_t)old;
+          if (p == POOL_DONE) break;
+          if (p != POOL_NONE) {
+            const uint2 d = pools[p];
+            if (idx < d.y) {
+              gi = group_cap - 1u - (d.x + idx);
+              break;
+            }
+          }
+          if (atomicCAS(&pool_lock, 0u, 1u) == 0u) {
+            // (another warp may have moved the CTA on between this warp's ticket and the lock)
+            if ((uint32_t)(*(volatile unsigned long long*)&pool_state >> 32) == p) {
+              const uint32_t np = atomicAdd(pool_queue, 1u);
+              atomicExch(&pool_state, (unsigned long long)(np < npools ? np : POOL_DONE) << 32);
+            }
+            __threadfence_block();
+            atomicExch(&pool_lock, 0u);
+          } else {
+            __nanosleep(100);
+          }
+        }
+      }
+    }
+    gi = __shfl_sync(0xFFFFFFFFu, gi, 0);
+    if (gi == 0xFFFFFFFFu) break;
+    heavy_phase = gi < nheavy;
+    const uint2 g = groups[gi];
     if (lane < g.y) {
       const uint32_t s = order[g.x + lane];
       const uint32_t o = off32[s], len = off32[s + 1] - o;
@@ -1282,7 +1332,7 @@ struct NutdbCtx {
   DevBuf rangeByte, rangeStmt, rangeTokBase, rangeCount, rangeDense, tokTypeD, tokStartD, tokEndD, tokKwD;
   DevBuf winIdx, winHas, winEof, descFn, descA, descI, descB, descC, winCtx, winFn, scanTotals, hashAcc, puntBlockCount, puntBlockPref, text, off64, off32, bitmap, localA, localB, localC, tileA, tileB, tileC, tilePrefC, entA, entB, tokType, tokStart,
       tokEnd, tokKw, stmtTokBegin, stmtTokEnd, stmt, scratch, retryList, retryNodeOff, retryStackOff, retryNodes, retryStack,
-      tileS, tilePrefS, nodes, errs, small, slowList, slowList2, wideOrder, wideGroups, wstmt, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
+      tileS, tilePrefS, nodes, errs, small, slowList, slowList2, wideOrder, wideGroups, widePools, wstmt, puntFlag, puntList, puntCounts, puntOffs, winCount, winMasks, firstStmt, winState, splitLocal, splitTile, splitPref, splitOff;
   // pinned host buffers
   HostBuf hSmall, hStmt, hTokType, hTokStart, hTokEnd, hTokKw, hNode, hErr, hRetry, hSplit;
   float ms[5] = {0, 0, 0, 0, 0};
@@ -1419,7 +1469,7 @@ void free_all(NutdbCtx* c) {
                  &c->tileC, &c->tilePrefC, &c->entA, &c->entB, &c->tokType, &c->tokStart, &c->tokEnd, &c->tokKw,
                  &c->stmtTokBegin, &c->stmtTokEnd, &c->stmt, &c->scratch, &c->retryList, &c->retryNodeOff,
                  &c->retryStackOff, &c->retryNodes, &c->retryStack, &c->tileS, &c->tilePrefS, &c->nodes, &c->errs,
-                 &c->small, &c->slowList, &c->slowList2, &c->wideOrder, &c->wideGroups, &c->wstmt, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
+                 &c->small, &c->slowList, &c->slowList2, &c->wideOrder, &c->wideGroups, &c->widePools, &c->wstmt, &c->puntFlag, &c->puntList, &c->puntCounts, &c->puntOffs, &c->winCount, &c->winMasks, &c->firstStmt, &c->winState, &c->splitLocal,
                  &c->splitTile, &c->splitPref, &c->splitOff};
   for (DevBuf* b : d)
     if (b->p) cudaFree(b->p);
@@ -1825,16 +1875,18 @@ run_again:
       const uint32_t gcap = nstmt + 1u;  // (a group holds at least one statement)
       ENSURE_DEV(wideOrder, 4 * ((size_t)nstmt + WIDE_POOL));
       ENSURE_DEV(wideGroups, 8 * (size_t)gcap);
+      ENSURE_DEV(widePools, 8 * ((size_t)nstmt / WIDE_POOL + 2));
       LAUNCH("k_wide_order", k_wide_order<<<(uint32_t)min(((size_t)nstmt + WIDE_POOL - 1) / WIDE_POOL, (size_t)ctx->sm_count * 8), WIDE_POOL, 0, st>>>(
                                  (const uint32_t*)ctx->slowList.p, dS + 2, (const uint8_t*)ctx->tokType.p,
-                                 (const NutdbStmt*)ctx->stmt.p, (uint32_t*)ctx->wideOrder.p, (uint2*)ctx->wideGroups.p, gcap, dS + 30));
+                                 (const NutdbStmt*)ctx->stmt.p, (uint32_t*)ctx->wideOrder.p, (uint2*)ctx->wideGroups.p, gcap, dS + 30,
+                                 (uint2*)ctx->widePools.p, dS + 3));
       const uint32_t wgrid = (uint32_t)min(((size_t)nstmt + WIDE_THREADS / 32 - 1) / (WIDE_THREADS / 32), (size_t)ctx->sm_count * WIDE_CTAS_PER_SM);
       LAUNCH("k_parse_wide", k_parse_wide<<<wgrid, WIDE_THREADS, 0, st>>>(
                                  dText, (const uint32_t*)ctx->off32.p, (const uint32_t*)ctx->wideOrder.p,
-                                 (const uint2*)ctx->wideGroups.p, gcap, dS + 30,
+                                 (const uint2*)ctx->wideGroups.p, gcap, dS + 30, (const uint2*)ctx->widePools.p, dS + 3,
                                  (const uint8_t*)ctx->tokType.p, (const uint32_t*)ctx->tokStart.p, (const uint32_t*)ctx->tokEnd.p,
                                  (const uint8_t*)ctx->tokKw.p, ctx->dFast, (NutdbStmt*)ctx->stmt.p, (uint2*)ctx->scratch.p,
-                                 (uint32_t*)ctx->slowList2.p, dS + 27, nstmt, (const uint32_t*)ctx->puntFlag.p, dS + 29));
+                                 (uint32_t*)ctx->slowList2.p, dS + 27, nstmt, (const uint32_t*)ctx->puntFlag.p, dS + 29, dS + 23));
     }
     if (!lex_only)
       LAUNCH("k_parse", k_parse<<<(nstmt + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(

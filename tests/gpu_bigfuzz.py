@@ -17,6 +17,7 @@ pools['hex'] = [b"select 0x1F, 0X2a, 0x, 0x0 from t where a = 0xdeadBEEF limit 0
                 b"insert into t values (0x1, '0x2', 0xFF), (0xa,0xb,0xc)", b"select 'a\\u{41}', 'b\\u{110000}', \"c\\u{+7a}\" from `t` where x = 'it''s' -- c\n and y"]
 import test_emul_parity as T
 pools['wide'] = T.WIDE + T.WIDE_AUTOMATON + [d[:400] for d in T.DEEP] + [s.encode() for s in T.fold_statements(n_random=200)[::5]]
+pools['escaped'] = [s.encode() for s in fuzz.escaped_literal_statements(600, seed=77)]
 pools['predicates'] = T.PREDICATES + T.PREDICATES_AUTOMATON + T.JOINS + T.JOINS_AUTOMATON + T.CASES + T.CASES_AUTOMATON + T.QUALIFIED + T.QUALIFIED_AUTOMATON + fuzz.SIMPLE_SEEDS[:40]
 t0 = time.time(); total = 0; nbad = 0
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0

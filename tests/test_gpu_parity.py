@@ -597,3 +597,24 @@ def test_escaped_literal_side_byte(ctx):
         assert np.array_equal(got2.tok_kw, got.tok_kw)
     finally:
         c2.close()
+
+
+def test_wide_pass_group_scheduling_edges(ctx):
+    """The wide pass's queue of statement groups (k_wide_order / k_parse_wide): pools that end exactly on, one short of and
+    one past the 256-statement boundary, a single statement, statements far over the token budget of a group (alone in
+    theirs), many equal statements (one shape: a full group whatever its tokens) -- all against the oracle."""
+    def nest(depth, width):
+        return "select " + "(" * depth + " + ".join(f"a{i} * (b{i} - {i})" for i in range(width)) + ")" * depth + " from t where x[1] = {'k': [1, 2]}"
+    giant = nest(40, 3000)        # ~27 K tokens: over the budget on its own
+    big = nest(200, 300)
+    mid = [nest(3 + i % 7, 12 + i % 5) for i in range(40)]
+    same = "select a[1], ~b, if c then 1 else 2 end from t where (x + 1) * (y - 2) in [1, 2, 3] and z = {'k': 1}"
+    for n in (1, 255, 256, 257, 513):
+        stmts = [mid[i % len(mid)] for i in range(n)]
+        got = check(ctx, stmts)
+        assert ctx.wide_statements() == n
+    stmts = [giant, big] + [same] * 300 + mid + [big, giant] + [same] * 211
+    got = check(ctx, stmts)
+    assert (got.stmt["status"] == 0).all()
+    assert ctx.wide_statements() == len(stmts) and ctx.slow_statements() == 0
+    assert int(got.stmt["tok_count"].max()) > 20000
