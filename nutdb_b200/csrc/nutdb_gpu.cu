@@ -853,10 +853,13 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
 #define WIDE_POOL 256  // statements sorted together (a larger pool sorts more equal statements into a group)
 #endif
 #ifndef WIDE_CTAS_PER_SM
-#define WIDE_CTAS_PER_SM 5
+#define WIDE_CTAS_PER_SM 4  // (57 registers: four 256-thread CTAs fit an SM; 3 and 5 measured the same)
 #endif
 #ifndef WIDE_BUDGET
 #define WIDE_BUDGET 6144u  // tokens per group (measured on config 4: 1024 -> 7.2 ms, 2048 -> 6.0, 4096 -> 4.7, 6144 / 8192 -> 4.5, 16384 -> 5.5)
+#endif
+#ifndef WIDE_MINBLOCKS
+#define WIDE_MINBLOCKS 1
 #endif
 #ifndef WIDE_HEAVY
 #define WIDE_HEAVY 512u    // a group with a statement of this many tokens is scheduled before the others
@@ -939,7 +942,7 @@ __global__ void __launch_bounds__(WIDE_POOL) k_wide_order(const uint32_t* __rest
   }
 }
 
-__global__ void __launch_bounds__(WIDE_THREADS) k_parse_wide(
+__global__ void __launch_bounds__(WIDE_THREADS, WIDE_MINBLOCKS) k_parse_wide(
     const uint8_t* __restrict__ text, const uint32_t* __restrict__ off32, const uint32_t* __restrict__ order,
     const uint2* __restrict__ groups, uint32_t group_cap, const uint32_t* __restrict__ counters,
     const uint2* __restrict__ pools, const uint32_t* __restrict__ pool_count,
