@@ -845,12 +845,13 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
 // (1) k_wide_order sorts every WIDE_POOL consecutive statements of the list by length and shape and cuts the sorted run
 //     into GROUPS of at most 32 statements and at most WIDE_BUDGET tokens -- a 2000-token statement gets a warp to
 //     itself, short ones still share one -- listed heavy groups first;
-// (2) k_parse_wide is PERSISTENT: its warps pull group after group from a queue and never wait for one another.
+// (2) k_parse_wide is PERSISTENT: its warps pull group after group and never wait for one another -- the heavy
+//     groups from one global queue, the others pool-wise per CTA (see the kernel).
 #ifndef WIDE_THREADS
 #define WIDE_THREADS 256
 #endif
 #ifndef WIDE_POOL
-#define WIDE_POOL 256  // statements sorted together (a larger pool sorts more equal statements into a group)
+#define WIDE_POOL 512  // statements sorted together, and the unit a CTA works through (config 4: 128 -> 4.7 ms, 256 -> 4.4, 512 -> 3.8, 1024 -> 3.9 + a slower sort)
 #endif
 #ifndef WIDE_CTAS_PER_SM
 #define WIDE_CTAS_PER_SM 4  // (57 registers: four 256-thread CTAs fit an SM; 3 and 5 measured the same)
@@ -973,7 +974,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_MINBLOCKS) k_parse_wide(
   bool heavy_phase = true;
   for (;;) {
     // ---- the next group: heavy ones from the global queue, one per trip (they decide when the kernel ends); then the
-    // light ones POOL-wise per CTA -- the 256 statements of a pool are neighbours in every array (offsets, token
+    // light ones POOL-wise per CTA -- the statements of a pool are neighbours in every array (offsets, token
     // arrays, node ranges share cache lines across statement boundaries), so the CTA's warps work through one pool's
     // groups together.  No barrier: a warp that finds the pool used up fetches the next one under a lock while the
     // others retry; warps still busy with a group of the old pool simply finish it.
