@@ -857,7 +857,8 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
 #define WIDE_CTAS_PER_SM 4  // (57 registers: four 256-thread CTAs fit an SM; 3 and 5 measured the same)
 #endif
 #ifndef WIDE_BUDGET
-#define WIDE_BUDGET 6144u  // tokens per group (measured on config 4: 1024 -> 7.2 ms, 2048 -> 6.0, 4096 -> 4.7, 6144 / 8192 -> 4.5, 16384 -> 5.5)
+#define WIDE_BUDGET 8192u  // tokens per group (config 4, global queue: 1024 -> 7.2 ms, 2048 -> 6.0, 4096 -> 4.7, 6144 / 8192 -> 4.5,
+                           // 16384 -> 5.5; pool-wise: 4096 -> 4.0, 6144 -> 3.85, 8192 -> 3.7, 12288 -> 4.1)
 #endif
 #ifndef WIDE_MINBLOCKS
 #define WIDE_MINBLOCKS 1
