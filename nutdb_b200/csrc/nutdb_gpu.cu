@@ -574,6 +574,27 @@ struct DText {
   const uint8_t* p;
   uint32_t n;
   __device__ __forceinline__ uint8_t byte(uint32_t i) const { return i < n ? p[i] : (uint8_t)0; }
+  __device__ __forceinline__ uint8_t raw(uint32_t i) const { return p[i]; }  // i < n is the caller's business
+  // Advances p0 over four-byte words of [p0, e) that hold neither a backslash nor `quote` (1 <= p0, e <= n).  Aligned
+  // word loads, one per step (a step's high word is the next one's low word), none of them beyond the statement's own
+  // bytes: device input needs no padding (nutdb_gpu.h), and the text buffer itself is 16-byte aligned.
+  __device__ __forceinline__ uint32_t skip_plain(uint32_t p0, uint32_t e, uint32_t quote) const {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p + p0);
+    const uint32_t mis = (uint32_t)(a & 3u);
+    if (p0 + 4u > e || p0 + 8u - mis > n) return p0;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a - mis);
+    const uint32_t sh = mis * 8u, q4 = quote * 0x01010101u;
+    uint32_t lo = __ldg(w);
+    do {
+      const uint32_t hi = __ldg(++w);
+      const uint32_t v = __funnelshift_r(lo, hi, sh);
+      const uint32_t x = v ^ 0x5C5C5C5Cu, y = v ^ q4;
+      if ((((x - 0x01010101u) & ~x) | ((y - 0x01010101u) & ~y)) & 0x80808080u) break;  // a zero byte in x or y
+      lo = hi;
+      p0 += 4u;
+    } while (p0 + 4u <= e && p0 + 8u - mis <= n);
+    return p0;
+  }
 };
 
 __device__ __forceinline__ void stage_parse_tables(const npar::ParseTables* g, npar::ParseTables* s) {
@@ -854,7 +875,8 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MINBLOCKS) k_parse_fast(
 #define WIDE_POOL 512  // statements sorted together, and the unit a CTA works through (config 4: 128 -> 4.7 ms, 256 -> 4.4, 512 -> 3.8, 1024 -> 3.9 + a slower sort)
 #endif
 #ifndef WIDE_CTAS_PER_SM
-#define WIDE_CTAS_PER_SM 4  // (57 registers: four 256-thread CTAs fit an SM; 3 and 5 measured the same)
+#define WIDE_CTAS_PER_SM 3  // (70 registers: three 256-thread CTAs fit an SM; capped at 64 / 48 registers for four / five
+                            // CTAs the uniform config 1 got 25 % slower -- more lanes thrash the L1 -- and config 4 no faster)
 #endif
 #ifndef WIDE_BUDGET
 #define WIDE_BUDGET 8192u  // tokens per group (config 4, global queue: 1024 -> 7.2 ms, 2048 -> 6.0, 4096 -> 4.7, 6144 / 8192 -> 4.5,

@@ -168,19 +168,21 @@ struct FastParser {
     uint32_t p = tok.start(i);
     const uint32_t e = tok.end(i);
     while (p < e) {
-      const uint32_t c = text.byte(p++);
+      p = text.skip_plain(p, e, quote);  // (four bytes at a time over what is neither a backslash nor the quote)
+      if (p >= e) break;
+      const uint32_t c = text.raw(p++);  // (every index below is < e <= the statement's length)
       if (c == quote) {
         p++;  // chars.next()
         continue;
       }
       if (c != '\\') continue;
       if (p >= e) return false;  // the reference panics here
-      if (text.byte(p++) != 'u') continue;
-      if (p >= e || text.byte(p++) != '{') continue;  // plain 'u'; the character after it is dropped
+      if (text.raw(p++) != 'u') continue;
+      if (p >= e || text.raw(p++) != '{') continue;  // plain 'u'; the character after it is dropped
       bool ok = true, any = false, first = true;
       uint64_t v = 0;
       while (p < e) {  // take_while(|&ch| ch != '}') then u32::from_str_radix(.., 16) and char::from_u32
-        const uint32_t h = text.byte(p++);
+        const uint32_t h = text.raw(p++);
         if (h == '}') break;
         if (first && h == '+') {
           first = false;

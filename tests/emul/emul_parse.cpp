@@ -81,6 +81,17 @@ struct HText {
   const uint8_t* p;
   uint32_t n;
   uint8_t byte(uint32_t i) const { return i < n ? p[i] : 0; }
+  uint8_t raw(uint32_t i) const { return p[i]; }
+  // the device's DText::skip_plain, same four-byte granularity
+  uint32_t skip_plain(uint32_t p0, uint32_t e, uint32_t quote) const {
+    while (p0 + 4u <= e) {
+      bool hit = false;
+      for (uint32_t k = 0; k < 4; k++) hit |= p[p0 + k] == '\\' || p[p0 + k] == quote;
+      if (hit) break;
+      p0 += 4u;
+    }
+    return p0;
+  }
 };
 }  // namespace
 
