@@ -1,6 +1,7 @@
 // TEST HARNESS (not shipped): runs the device lexer + parser logic (lex_core.cuh, parse_core.cuh)
 // on the host, statement by statement, producing the same arrays the CUDA path produces.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -82,11 +83,18 @@ struct HText {
   uint32_t n;
   uint8_t byte(uint32_t i) const { return i < n ? p[i] : 0; }
   uint8_t raw(uint32_t i) const { return p[i]; }
-  // the device's DText::skip_plain, same four-byte granularity
+  // the device's DText::skip_plain: same four-byte granularity and the same zero-byte test on the word (the device
+  // builds the word from two aligned loads); checked here against the plain byte comparison on every call
   uint32_t skip_plain(uint32_t p0, uint32_t e, uint32_t quote) const {
+    const uint32_t q4 = quote * 0x01010101u;
     while (p0 + 4u <= e) {
       bool hit = false;
       for (uint32_t k = 0; k < 4; k++) hit |= p[p0 + k] == '\\' || p[p0 + k] == quote;
+      uint32_t v;
+      std::memcpy(&v, p + p0, 4);  // (little-endian host, like the device)
+      const uint32_t x = v ^ 0x5C5C5C5Cu, y = v ^ q4;
+      const bool swar = ((((x - 0x01010101u) & ~x) | ((y - 0x01010101u) & ~y)) & 0x80808080u) != 0u;
+      if (swar != hit) std::abort();
       if (hit) break;
       p0 += 4u;
     }
