@@ -92,10 +92,11 @@ SIMPLE_SEEDS = [
 ]
 
 
-def escaped_literal_statements(count, seed=7):
+def escaped_literal_statements(count, seed=7, unicode=False):
     """Statements built around escaped string literals: backslash-u escapes (valid, invalid, not an escape after all),
     doubled quotes, plain escapes, literals from a few bytes to several lexer windows long -- the cases that decide the
-    lexer's side byte of an escaped literal and whether the parser has to validate it (literal.rs:45-102)."""
+    lexer's side byte of an escaped literal and whether the parser has to validate it (literal.rs:45-102).
+    unicode=True: the plain runs are random scalar values of every UTF-8 length (control characters included)."""
     import random
     rng = random.Random(seed)
 
@@ -110,8 +111,19 @@ def escaped_literal_statements(count, seed=7):
             elif r < 0.45: parts.append(q + q)
             elif r < 0.50: parts.append("\\u{zz}")
             elif r < 0.55: parts.append("u")
+            elif unicode: parts.append("".join(uchar(q) for _ in range(rng.randint(0, 12))))
             else: parts.append("".join(rng.choice("abcu \n;-/*") for _ in range(rng.randint(0, 40))))
         return q + "".join(parts) + q
+
+    def uchar(q):  # any scalar value, 1-4 bytes of UTF-8; the neighbours of a backslash instead of an escape of its own
+        while True:
+            r = rng.random()
+            cp = (rng.randint(1, 0x7F) if r < 0.5 else rng.randint(0x80, 0x7FF) if r < 0.7
+                  else rng.randint(0x800, 0xFFFF) if r < 0.9 else rng.randint(0x10000, 0x10FFFF))
+            if 0xD800 <= cp <= 0xDFFF:
+                continue
+            c = chr(cp)
+            return rng.choice("[]") if c in ("\\", q) else c
 
     out = []
     for _ in range(count):

@@ -467,3 +467,5 @@ def test_escaped_literal_side_byte(seg):
     stmts = fuzz.escaped_literal_statements(1500, seed=seg)
     got = check(stmts)
     assert (got.stmt["status"] != 0).any() and (got.stmt["status"] == 0).any()
+    got = check(fuzz.escaped_literal_statements(1500, seed=seg + 1, unicode=True))
+    assert (got.stmt["status"] != 0).any() and (got.stmt["status"] == 0).any()

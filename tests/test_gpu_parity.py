@@ -584,6 +584,7 @@ def test_escaped_literal_side_byte(ctx):
     """tok_kw of an escaped literal: 1 iff it holds no backslash-u escape (then the parsers skip its validation) --
     the range lexer, the look-back lexer and the exact walker agree, and statuses / errors equal the oracle's."""
     from nutdb_b200 import gpu
+    check(ctx, fuzz.escaped_literal_statements(30000, seed=12, unicode=True))
     stmts = fuzz.escaped_literal_statements(60000, seed=11)
     got = check(ctx, stmts)
     assert (got.stmt["status"] != 0).any() and (got.stmt["status"] == 0).any()
